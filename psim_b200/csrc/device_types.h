@@ -1,0 +1,132 @@
+// Plain-old-data records shared by the host flattener (flatten.cpp) and the CUDA kernels (kernels.cu).
+// Everything the per-phonon loop reads is in these structs; nothing here owns memory.
+//
+// Coordinates: a phonon's position is stored in the BARYCENTRIC frame of its current triangular cell,
+//   p = P1 + b1 (P2 - P1) + b2 (P3 - P1),    b1 >= 0, b2 >= 0, b1 + b2 <= 1,
+// so the three boundary edges are the coordinate lines b2 = 0 (edge 0, P1->P2), b1 + b2 = 1 (edge 1, P2->P3)
+// and b1 = 0 (edge 2, P3->P1), and "time to hit an edge" is one division per edge.  The reference instead
+// intersects the path segment with three slope/intercept lines in absolute fp64 coordinates
+// (reference psim/src/modelSimulator.cpp:87-122, geometry.cpp:104-138); in fp32 that is not watertight, the
+// barycentric form is (a phonon can never be outside its own cell), and it costs a fraction of the arithmetic.
+#ifndef PSIM_B200_DEVICE_TYPES_H
+#define PSIM_B200_DEVICE_TYPES_H
+
+#include <stdint.h>
+#include <vector_types.h>  // float2 / float4 / uint4 (header-only, usable from g++ too)
+
+#define PSIM_BINS 1000           // reference Material::NUM_FREQ_BINS (material.h:14)
+#define PSIM_MAX_COLLISIONS 100  // reference MAX_COLLISIONS (modelSimulator.cpp:25)
+#define PSIM_FLUX_FRAC_BITS 8    // flux tallies are int64 fixed point, 1/256 m/s resolution
+#define PSIM_FREQ_SCALE 1e-13    // angular frequencies are carried as omega * 1e-13 (fp32 range)
+#define PSIM_BIRTH_STEP 0xFFFFFFFFu  // Philox stream selector for the draws made at emission
+
+// edge link word: [31:30] kind, then payload
+#define PSIM_LINK_BOUNDARY 0u    // payload unused
+#define PSIM_LINK_TRANSITION 1u  // [29:28] neighbour edge, [27] same-direction flag, [26:0] neighbour cell
+#define PSIM_LINK_EMIT 2u        // [26:0] emitter index
+#define PSIM_LINK_COMPOSITE 3u   // [26:7] first sub-surface, [6:0] number of sub-surfaces
+#define PSIM_LINK_KIND(w) ((w) >> 30)
+#define PSIM_LINK_INDEX(w) ((w)&0x07FFFFFFu)
+
+#if defined(__CUDACC__)
+#define PSIM_ALIGN(n) __align__(n)
+#else
+#define PSIM_ALIGN(n) alignas(n)
+#endif
+
+// 64 bytes = four 16-byte loads.
+struct PSIM_ALIGN(16) DevCell {
+    float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [P2-P1 | P3-P1])
+    float n0x, n0y, n1x, n1y;  // unit normals of edge 0 and edge 1 pointing INTO the cell (geometry.cpp:97-100)
+    float n2x, n2y;            // same for edge 2
+    float spec;                // specularity of the cell's boundary surfaces, clamped to [0,1] (cell.cpp:115-119)
+    uint32_t sensor_mat;       // [31:8] sensor index, [7:0] material index
+    uint32_t link[3];          // what lies behind each edge
+    uint32_t pad;
+};
+
+// A part of an edge that is a transition to a neighbour or an emitting surface (compositeSurface.h:60-66).
+struct PSIM_ALIGN(16) DevSub {
+    float s0, s1;   // extent along the edge, as fractions of the edge from its first to its second vertex
+    float a, b;     // transition: position along the neighbour's edge = a * s + b
+    uint32_t link;  // PSIM_LINK_TRANSITION or PSIM_LINK_EMIT word
+    uint32_t pad[3];
+};
+
+// Relaxation-rate coefficients of one sensor area, in 1/ns, for omega in units of 1e13 rad/s
+// (material.cpp:207-239 evaluated at the sensor's temperature, sensorController.h:68-70,86-88).
+struct PSIM_ALIGN(16) DevSensor {
+    float c_la;     // LA: N = U = c_la w^2
+    float c_tn;     // TA, w <  w_cut: N = c_tn w
+    float c_tu;     // TA, w >= w_cut: U = c_tu w^2 / sinh(x_t w)
+    float x_t;      // hbar * 1e13 / (k_B T)
+    float c_i;      // impurity: I = c_i w^4
+    float w_cut;
+    uint32_t scatter_table;  // table sampled on an intrinsic scatter
+    uint32_t base_table;     // table sampled for phonons born inside a cell
+};
+
+struct DevMaterial {
+    float w_max_la, w_max_ta;  // scaled; a phonon above the neighbour's cutoff back-scatters at an interface
+    float freq_width;          // scaled bin width
+    float pad;
+};
+
+struct PSIM_ALIGN(16) DevEmitter {
+    uint32_t cell, edge;
+    float s_p1, s_p2;       // edge coordinate of the surface's two end points (Line::getRandPoint, geometry.cpp:140-143)
+    uint32_t table;         // velocity-weighted table at the surface temperature
+    uint32_t pad;
+    uint32_t k_on, k_off;   // absorbing while k_on <= measurement step < k_off (surface.cpp:61-65)
+    double start, duration; // emission window in ns
+};
+
+struct DevSource {
+    uint32_t kind;   // 0: cell interior, 1: emitting surface, 2: phasor surface
+    uint32_t index;  // cell or emitter index
+    int32_t sign;    // +1 if the source is hotter than t_eq, -1 otherwise (phononBuilder.cpp:8,33)
+    uint32_t pad;
+    uint64_t count;  // phonons of this source over the whole run
+    uint64_t first_id;
+};
+
+// One (measurement step, source) group of phonons this shard has to create.
+struct DevBirth {
+    uint32_t source;
+    uint32_t step;
+    uint64_t j0;      // first source-local phonon index owned by this shard
+    uint32_t count;   // phonons created for it: j0, j0 + stride, ...
+    uint32_t stride;  // = number of shards
+};
+
+// Phonon state in HBM: two 16-byte words per phonon, structure-of-arrays.
+//   A = (b1, b2, dx, dy)            position in the cell frame, direction (|d| <= 1: 3-D direction projected)
+//   B = (omega, packed, cell, id)   packed = [9:0] bin, [10] polarisation (1 = TA), [11] sign (1 = negative),
+//                                            [15:12] material the (omega, v) pair was sampled in, [31:16] id bits 47:32
+#define PSIM_PACK_BIN(p) ((p)&0x3FFu)
+#define PSIM_PACK_TA(p) (((p) >> 10) & 1u)
+#define PSIM_PACK_NEG(p) (((p) >> 11) & 1u)
+#define PSIM_PACK_MAT(p) (((p) >> 12) & 0xFu)
+#define PSIM_PACK_IDHI(p) ((p) >> 16)
+
+struct DevParams {
+    const DevCell* cells;
+    const DevSub* subs;
+    const DevSensor* sensors;
+    const DevMaterial* materials;
+    const DevEmitter* emitters;
+    const DevSource* sources;
+    const float2* tables;      // [n_tables][PSIM_BINS] (cumulative probability, LA fraction)  (material.cpp:170-180)
+    const float* velocities;   // [n_materials][2][PSIM_BINS] group velocity, LA then TA, m/s == nm/ns
+    uint32_t n_cells, n_sensors, n_materials, n_tables, n_emitters, n_sources;
+    uint32_t num_steps;        // measurement steps M
+    uint32_t first_tally_step; // reference step_adjustment_ (modelSimulator.h:24-26)
+    uint32_t recorded_steps;   // M - first_tally_step
+    uint32_t full_mode;        // t_eq == 0: bin-centre frequencies, no jitter (material.cpp:77-80)
+    uint32_t phasor;           // phasor_sim: no intrinsic scattering (modelSimulator.cpp:189)
+    float step_time;           // ns
+    double step_time_d;
+    uint32_t seed_lo, seed_hi;
+};
+
+#endif
