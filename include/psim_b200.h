@@ -124,6 +124,9 @@ typedef struct psim_stats {
     uint32_t steps_per_launch;
     uint32_t warps;                     /* resident warps = pool segments */
     uint32_t tally_in_shared;           /* 1 if sensor tallies were staged in shared memory */
+    uint64_t image_bytes;               /* host->device bytes of the model image (psim_gpu_create) */
+    uint64_t plan_bytes;                /* host->device bytes of the sources + birth plan (psim_gpu_set_sources) */
+    uint64_t tally_bytes;               /* device->host bytes of psim_gpu_get_tallies */
 } psim_stats;
 
 typedef struct psim_gpu psim_gpu;

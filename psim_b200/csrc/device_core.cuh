@@ -156,6 +156,7 @@ PSIM_HD void sample_table(const DevParams& P, uint32_t table_idx, uint32_t mat, 
 }
 
 PSIM_HD float phonon_velocity(const DevParams& P, uint32_t packed) {
+    if (P.phasor) { return 1000.f; }  // PhasorBuilder, phononBuilder.cpp:46
     return ldg(&P.velocities[(PSIM_PACK_MAT(packed) * 2u + PSIM_PACK_TA(packed)) * PSIM_BINS + PSIM_PACK_BIN(packed)]);
 }
 
@@ -330,7 +331,7 @@ PSIM_HD bool advance_interval(const DevParams& P, Phonon& p, float t, uint32_t s
             place_on_edge(e, s, p);
             t -= th;
             tts -= th;
-            uint32_t link = c.link[e];
+            uint32_t link = (e == 0u) ? c.link[0] : ((e == 1u) ? c.link[1] : c.link[2]);
             float ma = (link & (1u << 27)) ? 1.f : -1.f, mb = (link & (1u << 27)) ? 0.f : 1.f;
             if (PSIM_LINK_KIND(link) == PSIM_LINK_COMPOSITE) {
                 const uint32_t first = (link >> 7) & 0xFFFFFu, n = link & 0x7Fu;

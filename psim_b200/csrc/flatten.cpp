@@ -1,0 +1,342 @@
+#include "flatten.h"
+
+#include <algorithm>
+#include <cmath>
+#include <sstream>
+
+namespace psim {
+namespace {
+
+constexpr double HBAR = 1.054517e-34;   // reference material.cpp:12
+constexpr double BOLTZ = 1.38065e-23;   // reference material.cpp:13
+constexpr double PER_NS = 1e-9;         // rates are carried in 1/ns (reference SCALING_FACTOR, modelSimulator.cpp:17)
+
+uint32_t transition_word(uint32_t cell, uint32_t edge, bool same_dir) {
+    return (PSIM_LINK_TRANSITION << 30) | (edge << 28) | (same_dir ? (1u << 27) : 0u) | cell;
+}
+
+bool fail(std::string& err, int code, const std::string& msg, int& rc) {
+    err = msg;
+    rc = code;
+    return false;
+}
+
+}  // namespace
+
+int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
+    int rc = 0;
+    if (!d.materials || !d.sensors || !d.cells || !d.tables || !d.velocities || d.num_materials == 0 ||
+        d.num_sensors == 0 || d.num_cells == 0 || d.num_tables == 0) {
+        fail(err, PSIM_E_INVALID, "model description has empty or null arrays", rc);
+        return rc;
+    }
+    if (d.num_materials > 16 || d.num_sensors >= (1u << 24) || d.num_cells >= (1u << 27) ||
+        d.num_emitters >= (1u << 27) || d.num_subsurfaces >= (1u << 27)) {
+        fail(err, PSIM_E_INVALID, "model exceeds packed-index limits (16 materials, 2^24 sensors, 2^27 cells)", rc);
+        return rc;
+    }
+    if (d.measurement_steps < 2 || !(d.simulation_time > 0.) || d.step_adjustment >= d.measurement_steps) {
+        fail(err, PSIM_E_INVALID, "invalid measurement_steps / simulation_time / step_adjustment", rc);
+        return rc;
+    }
+    const double step_time = d.simulation_time / static_cast<double>(d.measurement_steps);
+
+    out = HostImage{};
+    out.material_consts.assign(d.materials, d.materials + d.num_materials);
+    out.materials.resize(d.num_materials);
+    for (uint32_t m = 0; m < d.num_materials; ++m) {
+        out.materials[m].w_max_la = static_cast<float>(d.materials[m].w_max_la * PSIM_FREQ_SCALE);
+        out.materials[m].w_max_ta = static_cast<float>(d.materials[m].w_max_ta * PSIM_FREQ_SCALE);
+        out.materials[m].freq_width = static_cast<float>(d.materials[m].freq_width * PSIM_FREQ_SCALE);
+        out.materials[m].pad = 0.f;
+    }
+    out.velocities.resize(static_cast<size_t>(d.num_materials) * 2 * PSIM_BINS);
+    for (size_t i = 0; i < out.velocities.size(); ++i) { out.velocities[i] = static_cast<float>(d.velocities[i]); }
+
+    out.tables.resize(static_cast<size_t>(d.num_tables) * PSIM_BINS);
+    for (uint32_t t = 0; t < d.num_tables; ++t) {
+        if (!d.tables[t].cumulative || !d.tables[t].la_fraction) {
+            fail(err, PSIM_E_INVALID, "null table", rc);
+            return rc;
+        }
+        for (uint32_t i = 0; i < PSIM_BINS; ++i) {
+            float2 e;
+            e.x = static_cast<float>(d.tables[t].cumulative[i]);
+            e.y = static_cast<float>(d.tables[t].la_fraction[i]);
+            out.tables[static_cast<size_t>(t) * PSIM_BINS + i] = e;
+        }
+    }
+
+    // sensors: fold temperature powers and unit scalings into the rate coefficients (fp64 here, fp32 on device)
+    out.sensors.resize(d.num_sensors);
+    out.sensor_temperature.resize(d.num_sensors);
+    for (uint32_t s = 0; s < d.num_sensors; ++s) {
+        const psim_sensor& in = d.sensors[s];
+        if (in.material >= d.num_materials || in.base_table >= d.num_tables || in.scatter_table >= d.num_tables ||
+            !(in.temperature > 0.)) {
+            fail(err, PSIM_E_INVALID, "sensor refers to a missing material/table or has a non-positive temperature", rc);
+            return rc;
+        }
+        const psim_material& mt = d.materials[in.material];
+        const double T = in.temperature;
+        const double k = 1. / PSIM_FREQ_SCALE;  // omega = k * w
+        DevSensor o{};
+        o.c_la = static_cast<float>(mt.b_l * T * T * T * k * k * PER_NS);
+        o.c_tn = static_cast<float>(mt.b_tn * T * T * T * T * k * PER_NS);
+        o.c_tu = static_cast<float>(mt.b_tu * k * k * PER_NS);
+        o.x_t = static_cast<float>(HBAR * k / (BOLTZ * T));
+        o.c_i = static_cast<float>(mt.b_i * k * k * k * k * PER_NS);
+        o.w_cut = static_cast<float>(mt.w * PSIM_FREQ_SCALE);
+        o.scatter_table = in.scatter_table;
+        o.base_table = in.base_table;
+        out.sensors[s] = o;
+        out.sensor_temperature[s] = T;
+    }
+
+    // emitters
+    out.emitters.resize(d.num_emitters);
+    for (uint32_t e = 0; e < d.num_emitters; ++e) {
+        const psim_emitter& in = d.emitters[e];
+        if (in.cell >= d.num_cells || in.edge > 2 || in.table >= d.num_tables || in.duration < 0. || in.start_time < 0.) {
+            fail(err, PSIM_E_INVALID, "emitter refers to a missing cell/edge/table or has a negative window", rc);
+            return rc;
+        }
+        DevEmitter o{};
+        o.cell = in.cell;
+        o.edge = in.edge;
+        o.s_p1 = static_cast<float>(in.s_p1);
+        o.s_p2 = static_cast<float>(in.s_p2);
+        o.table = in.table;
+        o.start = in.start_time;
+        o.duration = in.duration;
+        // the reference's own test, evaluated per measurement step in fp64 (surface.cpp:61-65):
+        //   reflect if  k*dt < start  ||  k*dt + dt > start + duration ; absorb otherwise
+        uint32_t k_on = d.measurement_steps, k_off = 0;
+        for (uint32_t k = 0; k < d.measurement_steps; ++k) {
+            const double pt = static_cast<double>(k) * step_time;
+            if (!(pt < in.start_time || pt + step_time > in.start_time + in.duration)) {
+                k_on = std::min(k_on, k);
+                k_off = k + 1;
+            }
+        }
+        if (k_off == 0) { k_on = 0; }
+        o.k_on = k_on;
+        o.k_off = k_off;
+        out.emitters[e] = o;
+    }
+
+    // cells
+    out.cells.resize(d.num_cells);
+    for (uint32_t c = 0; c < d.num_cells; ++c) {
+        const psim_cell& in = d.cells[c];
+        if (in.sensor >= d.num_sensors) {
+            fail(err, PSIM_E_INVALID, "cell refers to a missing sensor", rc);
+            return rc;
+        }
+        const double e1x = in.x[1] - in.x[0], e1y = in.y[1] - in.y[0];
+        const double e2x = in.x[2] - in.x[0], e2y = in.y[2] - in.y[0];
+        const double det = e1x * e2y - e2x * e1y;
+        if (!(std::fabs(det) > 0.)) {
+            std::ostringstream os;
+            os << "cell " << c << " is degenerate";
+            fail(err, PSIM_E_INVALID, os.str(), rc);
+            return rc;
+        }
+        const double m00 = e2y / det, m01 = -e2x / det, m10 = -e1y / det, m11 = e1x / det;
+        auto unit = [](double x, double y, float& ox, float& oy) {
+            const double n = std::sqrt(x * x + y * y);
+            ox = static_cast<float>(x / n);
+            oy = static_cast<float>(y / n);
+        };
+        DevCell o{};
+        o.m00 = static_cast<float>(m00);
+        o.m01 = static_cast<float>(m01);
+        o.m10 = static_cast<float>(m10);
+        o.m11 = static_cast<float>(m11);
+        unit(m10, m11, o.n0x, o.n0y);                   // edge 0 is b2 = 0: inward = grad b2
+        unit(-(m00 + m10), -(m01 + m11), o.n1x, o.n1y); // edge 1 is b1 + b2 = 1
+        unit(m00, m01, o.n2x, o.n2y);                   // edge 2 is b1 = 0
+        o.spec = static_cast<float>(std::min(1., std::max(0., in.specularity)));
+        o.sensor_mat = (in.sensor << 8) | d.sensors[in.sensor].material;
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t n = in.sub_count[k], first = in.sub_first[k];
+            if (n == 0) {
+                o.link[k] = PSIM_LINK_BOUNDARY << 30;
+                continue;
+            }
+            if (!d.subsurfaces || first + n > d.num_subsurfaces || n > 127) {
+                fail(err, PSIM_E_INVALID, "cell edge sub-surface range is out of bounds", rc);
+                return rc;
+            }
+            auto word = [&](const psim_subsurface& sb, float& a, float& b) -> uint32_t {
+                if (sb.kind == PSIM_SURF_EMIT) {
+                    a = 0.f;
+                    b = 0.f;
+                    return (PSIM_LINK_EMIT << 30) | sb.target;
+                }
+                const double aa = (sb.t1 - sb.t0) / (sb.s1 - sb.s0);
+                a = static_cast<float>(aa);
+                b = static_cast<float>(sb.t0 - aa * sb.s0);
+                return transition_word(sb.target, sb.target_edge, aa > 0.);
+            };
+            for (uint32_t i = 0; i < n; ++i) {
+                const psim_subsurface& sb = d.subsurfaces[first + i];
+                const bool ok = (sb.kind == PSIM_SURF_EMIT && sb.target < d.num_emitters) ||
+                                (sb.kind == PSIM_SURF_TRANSITION && sb.target < d.num_cells && sb.target_edge < 3);
+                if (!ok || sb.s0 == sb.s1) {
+                    fail(err, PSIM_E_INVALID, "invalid sub-surface record", rc);
+                    return rc;
+                }
+            }
+            const psim_subsurface& s0 = d.subsurfaces[first];
+            const double lo = std::min(s0.s0, s0.s1), hi = std::max(s0.s0, s0.s1);
+            const bool whole = n == 1 && lo < 1e-9 && hi > 1. - 1e-9;
+            float a, b;
+            if (whole && (s0.kind == PSIM_SURF_EMIT ||
+                          (std::fabs(std::fabs(s0.t1 - s0.t0) - 1.) < 1e-9 && std::min(s0.t0, s0.t1) < 1e-9))) {
+                o.link[k] = word(s0, a, b);  // the whole edge is one neighbour / one emitter: no sub-table lookup
+                continue;
+            }
+            if (out.subs.size() + n >= (1u << 20)) {
+                fail(err, PSIM_E_INVALID, "too many partial-edge sub-surfaces", rc);
+                return rc;
+            }
+            o.link[k] = (PSIM_LINK_COMPOSITE << 30) | (static_cast<uint32_t>(out.subs.size()) << 7) | n;
+            for (uint32_t i = 0; i < n; ++i) {
+                const psim_subsurface& sb = d.subsurfaces[first + i];
+                DevSub ds{};
+                ds.s0 = static_cast<float>(std::min(sb.s0, sb.s1));
+                ds.s1 = static_cast<float>(std::max(sb.s0, sb.s1));
+                ds.link = word(sb, ds.a, ds.b);
+                out.subs.push_back(ds);
+            }
+        }
+        out.cells[c] = o;
+    }
+    if (out.subs.empty()) { out.subs.push_back(DevSub{}); }
+    if (out.emitters.empty()) { out.emitters.push_back(DevEmitter{}); }
+
+    DevParams& P = out.scalars;
+    P.n_cells = d.num_cells;
+    P.n_sensors = d.num_sensors;
+    P.n_materials = d.num_materials;
+    P.n_tables = d.num_tables;
+    P.n_emitters = d.num_emitters;
+    P.n_sources = 0;
+    P.num_steps = d.measurement_steps;
+    P.first_tally_step = d.step_adjustment;
+    P.recorded_steps = d.measurement_steps - d.step_adjustment;
+    P.full_mode = d.full_simulation ? 1u : 0u;
+    P.phasor = d.phasor_sim ? 1u : 0u;
+    P.step_time = static_cast<float>(step_time);
+    P.step_time_d = step_time;
+    return 0;
+}
+
+int plan_births(const HostImage& img, const psim_source* sources, size_t n, uint32_t shard, uint32_t num_shards,
+                BirthPlan& out, std::string& err) {
+    out = BirthPlan{};
+    if (num_shards == 0 || shard >= num_shards || (n > 0 && !sources)) {
+        err = "invalid shard / source arguments";
+        return PSIM_E_INVALID;
+    }
+    const DevParams& P = img.scalars;
+    const uint32_t M = P.num_steps;
+    const double dt = P.step_time_d;
+    const uint32_t last = M - 1;  // the interval that starts at step M-1 records nothing: not simulated
+    uint64_t next_id = 0;
+    std::vector<DevBirth> births;
+    auto add = [&](uint32_t src, uint32_t step, uint64_t first_id, uint64_t ja, uint64_t jb) -> bool {
+        if (jb <= ja) { return true; }
+        const uint64_t G = num_shards;
+        const uint64_t r = (first_id + ja) % G;
+        const uint64_t j0 = ja + ((shard + G - r) % G);
+        if (j0 >= jb) { return true; }
+        const uint64_t cnt = (jb - 1 - j0) / G + 1;
+        if (step >= last) {
+            out.shard_unrecorded += cnt;
+            return true;
+        }
+        if (cnt > 0xFFFFFFFFull) { return false; }
+        DevBirth b{};
+        b.source = src;
+        b.step = step;
+        b.j0 = j0;
+        b.count = static_cast<uint32_t>(cnt);
+        b.stride = num_shards;
+        births.push_back(b);
+        out.shard_phonons += cnt;
+        return true;
+    };
+    for (size_t i = 0; i < n; ++i) {
+        const psim_source& s = sources[i];
+        DevSource ds{};
+        ds.kind = s.kind;
+        ds.index = s.index;
+        ds.sign = s.sign >= 0 ? 1 : -1;
+        ds.count = s.count;
+        ds.first_id = next_id;
+        if (s.kind == PSIM_SRC_CELL) {
+            if (s.index >= P.n_cells) {
+                err = "cell source refers to a missing cell";
+                return PSIM_E_INVALID;
+            }
+            if (!add(static_cast<uint32_t>(i), 0, next_id, 0, s.count)) {
+                err = "more than 2^32 phonons in one (source, step) group";
+                return PSIM_E_INVALID;
+            }
+        } else if (s.kind == PSIM_SRC_SURFACE) {
+            if (s.index >= P.n_emitters) {
+                err = "surface source refers to a missing emitter";
+                return PSIM_E_INVALID;
+            }
+            if (P.phasor) { ds.kind = 2u; }
+            const DevEmitter& em = img.emitters[s.index];
+            if (s.count > 0 && !(em.duration > 0.)) {
+                err = "surface source with phonons but an empty emission window";
+                return PSIM_E_INVALID;
+            }
+            // phonon j is born at start + duration * (j + u) / count; it is assigned to the step that contains
+            // the START of its stratum, so J(k) = first j with start + duration * j / count >= k * dt
+            const double cnt = static_cast<double>(s.count);
+            auto J = [&](uint32_t k) -> uint64_t {
+                const double x = (static_cast<double>(k) * dt - em.start) / em.duration * cnt;
+                if (!(x > 0.)) { return 0; }
+                if (x >= cnt) { return s.count; }
+                return static_cast<uint64_t>(std::ceil(x));
+            };
+            uint64_t ja = 0;
+            for (uint32_t k = 0; k < M && ja < s.count; ++k) {
+                const uint64_t jb = (k + 1 == M) ? s.count : std::max(ja, J(k + 1));
+                if (!add(static_cast<uint32_t>(i), k, next_id, ja, jb)) {
+                    err = "more than 2^32 phonons in one (source, step) group";
+                    return PSIM_E_INVALID;
+                }
+                ja = jb;
+            }
+        } else {
+            err = "unknown source kind";
+            return PSIM_E_INVALID;
+        }
+        out.sources.push_back(ds);
+        next_id += s.count;
+    }
+    out.total_phonons = next_id;
+    if (next_id >= (1ull << 48)) {
+        err = "more than 2^48 phonons";
+        return PSIM_E_INVALID;
+    }
+    std::stable_sort(births.begin(), births.end(), [](const DevBirth& a, const DevBirth& b) { return a.step < b.step; });
+    out.births = births;
+    out.prefix.assign(births.size() + 1, 0);
+    out.step_begin.assign(M + 1, 0);
+    for (size_t i = 0; i < births.size(); ++i) {
+        out.prefix[i + 1] = out.prefix[i] + births[i].count;
+        out.step_begin[births[i].step + 1] = static_cast<uint32_t>(i + 1);
+    }
+    for (uint32_t k = 1; k <= M; ++k) { out.step_begin[k] = std::max(out.step_begin[k], out.step_begin[k - 1]); }
+    if (out.sources.empty()) { out.sources.push_back(DevSource{}); }
+    return 0;
+}
+
+}  // namespace psim

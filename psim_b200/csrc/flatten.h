@@ -1,0 +1,43 @@
+// Host-side preparation of the device image: psim_model_desc (C ABI, include/psim_b200.h) -> arrays of the
+// records in device_types.h, and the birth plan (which phonon indices each measurement step creates).
+// Pure C++17, no CUDA calls: shared by the GPU library and by the CPU-side test emulation.
+#ifndef PSIM_B200_FLATTEN_H
+#define PSIM_B200_FLATTEN_H
+
+#include "../../include/psim_b200.h"
+#include "device_types.h"
+#include <string>
+#include <vector>
+
+namespace psim {
+
+struct HostImage {
+    std::vector<DevCell> cells;
+    std::vector<DevSub> subs;
+    std::vector<DevSensor> sensors;
+    std::vector<DevMaterial> materials;
+    std::vector<DevEmitter> emitters;
+    std::vector<float2> tables;      // [n_tables][PSIM_BINS]
+    std::vector<float> velocities;   // [n_materials][2][PSIM_BINS]
+    std::vector<double> sensor_temperature;
+    std::vector<psim_material> material_consts;
+    DevParams scalars{};             // pointers left null; counts and settings filled in
+};
+
+struct BirthPlan {
+    std::vector<DevSource> sources;
+    std::vector<DevBirth> births;         // sorted by step, then by source
+    std::vector<uint64_t> prefix;         // births.size() + 1, exclusive running sum of DevBirth::count
+    std::vector<uint32_t> step_begin;     // num_steps + 1: first entry of each step
+    uint64_t total_phonons = 0;           // all shards
+    uint64_t shard_phonons = 0;           // created by this shard (excludes those born in the unrecorded last step)
+    uint64_t shard_unrecorded = 0;        // owned by this shard but born in the last interval (never tallied)
+};
+
+// returns 0 or a PSIM_E_* code with `err` set
+int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err);
+int plan_births(const HostImage& img, const psim_source* sources, size_t n, uint32_t shard, uint32_t num_shards,
+                BirthPlan& out, std::string& err);
+
+}  // namespace psim
+#endif

@@ -1,0 +1,335 @@
+// C ABI of the host layer (include/psim_host.h) over psim::Model.
+#include "../../../include/psim_host.h"
+#include "model.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <string>
+
+struct psim_model {
+    std::unique_ptr<psim::Model> m;
+};
+
+namespace {
+
+thread_local std::string g_error;
+
+template<typename F> int guarded(int model_error_code, F&& f) {
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return model_error_code;
+    } catch (...) {
+        g_error = "unknown error";
+        return model_error_code;
+    }
+}
+
+int load_with(psim_model** out, const std::function<std::unique_ptr<psim::Model>()>& make) {
+    if (!out) {
+        g_error = "null argument";
+        return PSIM_E_INVALID;
+    }
+    *out = nullptr;
+    return guarded(PSIM_E_MODEL, [&]() {
+        auto m = make();
+        *out = new psim_model{ std::move(m) };
+        return PSIM_OK;
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* psim_host_last_error(void) { return g_error.c_str(); }
+
+int psim_model_load(const char* json_path, psim_model** out) {
+    if (!json_path) {
+        g_error = "null path";
+        return PSIM_E_INVALID;
+    }
+    return load_with(out, [&]() { return psim::Model::from_file(json_path); });
+}
+
+int psim_model_load_text(const char* json_text, psim_model** out) {
+    if (!json_text) {
+        g_error = "null text";
+        return PSIM_E_INVALID;
+    }
+    return load_with(out, [&]() { return psim::Model::from_json_text(json_text); });
+}
+
+void psim_model_free(psim_model* m) { delete m; }
+
+int psim_model_get_info(const psim_model* pm, psim_model_info* out) {
+    if (!pm || !out) { return PSIM_E_INVALID; }
+    const psim::Model& m = *pm->m;
+    std::memset(out, 0, sizeof(*out));
+    out->num_runs = m.num_runs;
+    out->measurement_steps = m.measurement_steps;
+    out->recorded_steps = m.recorded_steps;
+    out->num_phonons = m.num_phonons;
+    out->step_interval = m.step_interval;
+    out->simulation_time = m.simulation_time;
+    out->t_eq = m.t_eq;
+    out->sim_type = static_cast<uint32_t>(m.sim_type);
+    out->phasor_sim = m.phasor_sim ? 1u : 0u;
+    out->num_materials = static_cast<uint32_t>(m.materials.size());
+    out->num_sensors = static_cast<uint32_t>(m.sensors.size());
+    out->num_cells = static_cast<uint32_t>(m.cells.size());
+    out->num_emitters = static_cast<uint32_t>(m.emitters.size());
+    for (const auto& c : m.cells) {
+        for (int k = 0; k < 3; ++k) {
+            for (const auto& t : c.transitions[k]) {
+                ++out->num_transition_links;
+                const double lo = std::min(t.s0, t.s1), hi = std::max(t.s0, t.s1);
+                if (lo > 1e-9 || hi < 1. - 1e-9) { ++out->num_partial_links; }
+            }
+        }
+    }
+    return PSIM_OK;
+}
+
+int psim_model_set_num_phonons(psim_model* pm, uint64_t n) {
+    if (!pm || n == 0) { return PSIM_E_INVALID; }
+    pm->m->num_phonons = n;
+    return PSIM_OK;
+}
+
+int psim_model_set_num_runs(psim_model* pm, uint64_t n) {
+    if (!pm || n == 0) { return PSIM_E_INVALID; }
+    pm->m->num_runs = n;
+    return PSIM_OK;
+}
+
+int psim_model_prepare(psim_model* pm) {
+    if (!pm) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_MODEL, [&]() {
+        pm->m->prepare();
+        return PSIM_OK;
+    });
+}
+
+int psim_model_energy(psim_model* pm, double* total, double* per_phonon) {
+    if (!pm) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_STATE, [&]() {
+        const double t = pm->m->total_initial_energy();
+        if (total) { *total = t; }
+        if (per_phonon) { *per_phonon = t / static_cast<double>(pm->m->num_phonons); }
+        return PSIM_OK;
+    });
+}
+
+int psim_model_material_arrays(psim_model* pm, uint32_t material, double* freq, double* vel_la, double* vel_ta,
+                               double* dens_la, double* dens_ta) {
+    if (!pm || material >= pm->m->materials.size()) { return PSIM_E_INVALID; }
+    const psim::Material& mt = pm->m->materials[material];
+    const size_t bytes = sizeof(double) * psim::kBins;
+    if (freq) { std::memcpy(freq, mt.freq.data(), bytes); }
+    if (vel_la) { std::memcpy(vel_la, mt.vel_la.data(), bytes); }
+    if (vel_ta) { std::memcpy(vel_ta, mt.vel_ta.data(), bytes); }
+    if (dens_la) { std::memcpy(dens_la, mt.dens_la.data(), bytes); }
+    if (dens_ta) { std::memcpy(dens_ta, mt.dens_ta.data(), bytes); }
+    return PSIM_OK;
+}
+
+int psim_model_table(psim_model* pm, uint32_t material, uint32_t kind, double temperature, double* cumulative,
+                     double* la_fraction, double* sum) {
+    if (!pm || material >= pm->m->materials.size() || kind > 2) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_STATE, [&]() {
+        const psim::Table& t = pm->m->materials[material].table(static_cast<psim::Material::Kind>(kind), temperature);
+        if (cumulative) { std::memcpy(cumulative, t.cumulative.data(), sizeof(double) * psim::kBins); }
+        if (la_fraction) { std::memcpy(la_fraction, t.la_fraction.data(), sizeof(double) * psim::kBins); }
+        if (sum) { *sum = t.sum; }
+        return PSIM_OK;
+    });
+}
+
+int psim_model_cell_energies(psim_model* pm, double* area, double* init_energy, double* emit_energy) {
+    if (!pm) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_STATE, [&]() {
+        psim::Model& m = *pm->m;
+        for (size_t i = 0; i < m.cells.size(); ++i) {
+            const auto& c = m.cells[i];
+            const auto& s = m.sensors[c.sensor];
+            const double t_init = (m.sim_type == psim::SimType::SteadyState) ? s.t_steady : s.t_init;
+            if (area) { area[i] = c.area; }
+            if (init_energy) {
+                const double e = c.area * s.heat_capacity;
+                init_energy[i] = (m.t_eq == 0.) ? e : e * std::fabs(t_init - m.t_eq);
+            }
+            if (emit_energy) {
+                double sum = 0.;
+                for (int k = 0; k < 3; ++k) {
+                    for (const auto& sub : c.emits[k]) {
+                        const auto& e = m.emitters[sub.target];
+                        const double en = e.length * e.duration * m.materials[s.material].emit_energy(e.temp) / 4.;
+                        sum += (m.t_eq == 0.) ? en : en * std::fabs(e.temp - m.t_eq);
+                    }
+                }
+                emit_energy[i] = sum;
+            }
+        }
+        return PSIM_OK;
+    });
+}
+
+int psim_model_sensor_ids(const psim_model* pm, uint64_t* ids, double* areas) {
+    if (!pm) { return PSIM_E_INVALID; }
+    for (size_t i = 0; i < pm->m->sensors.size(); ++i) {
+        if (ids) { ids[i] = pm->m->sensors[i].id; }
+        if (areas) { areas[i] = pm->m->sensors[i].area; }
+    }
+    return PSIM_OK;
+}
+
+int psim_model_describe(psim_model* pm, const psim_model_desc** out) {
+    if (!pm || !out) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_STATE, [&]() {
+        *out = &pm->m->describe();
+        return PSIM_OK;
+    });
+}
+
+int psim_model_sources(psim_model* pm, uint64_t seed, psim_source* sources, size_t* n) {
+    if (!pm || !n) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_STATE, [&]() {
+        const auto v = pm->m->source_counts(seed);
+        if (sources) {
+            if (*n < v.size()) {
+                g_error = "source buffer too small";
+                return static_cast<int>(PSIM_E_INVALID);
+            }
+            std::memcpy(sources, v.data(), v.size() * sizeof(psim_source));
+        }
+        *n = v.size();
+        return static_cast<int>(PSIM_OK);
+    });
+}
+
+int psim_model_set_tallies(psim_model* pm, const int32_t* energy, const double* flux) {
+    if (!pm || !energy || !flux) { return PSIM_E_INVALID; }
+    pm->m->set_tallies(energy, flux);
+    return PSIM_OK;
+}
+
+int psim_model_finish_run(psim_model* pm, uint64_t run_id, int* stable) {
+    if (!pm) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_STATE, [&]() {
+        const int s = pm->m->finish_run(run_id, nullptr);
+        if (stable) { *stable = s; }
+        return PSIM_OK;
+    });
+}
+
+int psim_model_next_run(psim_model* pm) {
+    if (!pm) { return PSIM_E_INVALID; }
+    pm->m->reset_for_next_run();
+    return PSIM_OK;
+}
+
+int psim_model_run(psim_model* pm, int device, uint64_t seed, int steps_per_launch, int verbose, psim_stats* stats) {
+    if (!pm) { return PSIM_E_INVALID; }
+    psim::Model& m = *pm->m;
+    psim_gpu* gpu = nullptr;
+    const int rc = guarded(PSIM_E_STATE, [&]() -> int {
+        m.runs.clear();
+        for (uint64_t run = 0; run < m.num_runs; ++run) {
+            if (verbose) { std::cout << "Run: " << run + 1 << '\n'; }
+            m.prepare();
+            if (!gpu) {
+                if (int e = psim_gpu_create(&m.describe(), device, &gpu)) {
+                    g_error = psim_gpu_last_error(nullptr);
+                    return e;
+                }
+                if (steps_per_launch > 0) {
+                    if (int e = psim_gpu_set_option(gpu, "steps_per_launch", steps_per_launch)) {
+                        g_error = psim_gpu_last_error(gpu);
+                        return e;
+                    }
+                }
+            }
+            const auto sources = m.source_counts(seed + run);
+            int e = psim_gpu_set_sources(gpu, sources.data(), sources.size(), seed + run, 0, 1);
+            if (!e) { e = psim_gpu_run(gpu); }
+            std::vector<int32_t> energy(m.sensors.size() * m.recorded_steps);
+            std::vector<double> flux(energy.size() * 2);
+            if (!e) { e = psim_gpu_get_tallies(gpu, energy.data(), flux.data(), nullptr); }
+            if (!e && stats) { e = psim_gpu_get_stats(gpu, stats); }
+            if (e) {
+                g_error = psim_gpu_last_error(gpu);
+                return e;
+            }
+            m.set_tallies(energy.data(), flux.data());
+            std::string log;
+            m.finish_run(run, &log);
+            if (verbose) { std::cout << log; }
+            if (run + 1 < m.num_runs) { m.reset_for_next_run(); }
+        }
+        return PSIM_OK;
+    });
+    psim_gpu_destroy(gpu);
+    return rc;
+}
+
+int psim_model_results(const psim_model* pm, uint64_t run_id, double* six, double* temps, double* fluxes) {
+    if (!pm) { return PSIM_E_INVALID; }
+    const psim::Model& m = *pm->m;
+    std::vector<psim::SensorResult> avg;
+    const std::vector<psim::SensorResult>* res = nullptr;
+    if (run_id == std::numeric_limits<uint64_t>::max()) {
+        avg = m.averaged();
+        res = &avg;
+    } else if (run_id < m.runs.size()) {
+        res = &m.runs[run_id];
+    }
+    if (!res || res->empty()) {
+        g_error = "no results for this run";
+        return PSIM_E_STATE;
+    }
+    const size_t R = m.recorded_steps;
+    for (size_t i = 0; i < res->size(); ++i) {
+        const auto& r = (*res)[i];
+        if (six) {
+            const double row[6] = { r.t_steady, r.std_t_steady, r.x_flux, r.std_x_flux, r.y_flux, r.std_y_flux };
+            std::memcpy(six + 6 * i, row, sizeof(row));
+        }
+        for (size_t k = 0; k < R; ++k) {
+            if (temps) { temps[i * R + k] = r.final_temps[k]; }
+            if (fluxes) {
+                fluxes[2 * (i * R + k)] = r.final_fluxes[k][0];
+                fluxes[2 * (i * R + k) + 1] = r.final_fluxes[k][1];
+            }
+        }
+    }
+    return PSIM_OK;
+}
+
+double psim_model_energy_per_phonon(const psim_model* pm) { return pm ? pm->m->energy_per_phonon() : 0.; }
+
+int psim_model_export(const psim_model* pm, const char* model_path, double seconds) {
+    if (!pm || !model_path) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_IO, [&]() {
+        pm->m->export_results(model_path, seconds);
+        return PSIM_OK;
+    });
+}
+
+int psim_model_export_text(const psim_model* pm, const char* model_filename, double seconds, const char* when, char* buf,
+                           size_t* len) {
+    if (!pm || !model_filename || !len) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_IO, [&]() {
+        const std::string s = pm->m->export_text(model_filename, seconds, when ? when : "");
+        if (buf && *len > s.size()) { std::memcpy(buf, s.c_str(), s.size() + 1); }
+        *len = s.size() + 1;
+        return PSIM_OK;
+    });
+}
+
+}  // extern "C"

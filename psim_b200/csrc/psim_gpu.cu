@@ -1,0 +1,773 @@
+// sm_100a kernels and the C ABI of include/psim_b200.h.
+//
+// Data layout in HBM
+//   phonon pool   two ping-pong copies of  A: float4[W][cap] (b1, b2, dx, dy)   B: uint4[W][cap] (omega, packed, cell, id)
+//                 W = number of resident warps of the drift kernel.  Warp w owns segment w of both copies:
+//                 it streams its segment of the input copy (two fully coalesced 16-byte loads per lane),
+//                 advances every phonon across the measurement intervals of this launch, and appends the
+//                 survivors - and the phonons it creates - to its segment of the output copy.  Compaction is
+//                 therefore a warp ballot + popcount: no block barrier, no global atomic, no holes.
+//   tallies       energy int32[R][S], flux int64[R][S][2] (fixed point), R recorded steps, S sensors.
+//   model image   cells / sensors / tables ... (device_types.h), read-only, L1/L2 resident.
+//
+// One launch = one pass of the whole pool over `steps_per_launch` measurement intervals (1 by default: 32 B read
+// + 32 B written per phonon per interval = the 64 algorithmic bytes per drift-step of SURVEY.md 8d).
+#include "../../include/psim_b200.h"
+#include "device_core.cuh"
+#include "flatten.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+struct LaunchArgs {
+    DevParams P;
+    const float4* in_a;
+    const uint4* in_b;
+    float4* out_a;
+    uint4* out_b;
+    const uint32_t* cnt_in;
+    uint32_t* cnt_out;
+    uint32_t seg_cap;
+    uint32_t n_warps;
+    uint32_t step_begin, step_end;
+    const DevBirth* births;        // entries of this launch
+    const uint64_t* birth_prefix;  // n_birth_entries + 1 running counts (absolute; subtract birth_base)
+    uint32_t n_birth_entries;
+    uint32_t birth_warp_offset;
+    uint64_t birth_base;
+    uint64_t n_births;
+    int32_t* tally_e;
+    long long* tally_f;
+    uint32_t tally_shared;
+    uint32_t tally_aggregate;
+    unsigned long long* stats;     // [0] drift steps [1] events [2] absorbed [3] overflow
+    unsigned long long* alive_hist;  // [launch]: pool population after this launch
+    uint32_t launch_index;
+};
+
+__device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t local_row,
+                                          uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
+    const uint32_t S = a.P.n_sensors;
+    if (a.tally_shared) {
+        const uint32_t k = local_row * S + sensor;
+        atomicAdd(&acc_e[k], e);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&acc_f[2 * k]), static_cast<unsigned long long>(static_cast<long long>(fx)));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&acc_f[2 * k + 1]), static_cast<unsigned long long>(static_cast<long long>(fy)));
+    } else {
+        const size_t row = static_cast<size_t>(a.step_begin + local_row + 1 - a.P.first_tally_step);
+        const size_t k = row * S + sensor;
+        atomicAdd(&a.tally_e[k], e);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k]), static_cast<unsigned long long>(static_cast<long long>(fx)));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k + 1]), static_cast<unsigned long long>(static_cast<long long>(fy)));
+    }
+}
+
+// The drift step: emission + free flight / scattering / surfaces / cell transitions + tally + compaction.
+__global__ void __launch_bounds__(kBlock) drift_kernel(const __grid_constant__ LaunchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevParams& P = a.P;
+    const uint32_t S = P.n_sensors;
+    const uint32_t nst = a.step_end - a.step_begin;
+    int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
+    long long* acc_f = reinterpret_cast<long long*>(smem_raw + ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)));
+    if (a.tally_shared) {
+        for (uint32_t i = threadIdx.x; i < nst * S; i += kBlock) {
+            acc_e[i] = 0;
+            acc_f[2 * i] = 0;
+            acc_f[2 * i + 1] = 0;
+        }
+        __syncthreads();
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t W = a.n_warps;
+    const size_t seg = static_cast<size_t>(w) * a.seg_cap;
+    const uint32_t n_in = a.cnt_in[w];
+    const uint32_t pool_tiles = (n_in + 31u) >> 5;
+    const uint64_t n_chunks = (a.n_births + 31u) >> 5;
+    uint64_t chunk = (w + W - (a.birth_warp_offset % W)) % W;  // birth chunks are dealt round-robin over the warps
+    uint32_t n_out = 0;
+    unsigned long long my_steps = 0, my_absorbed = 0;
+    uint32_t my_events = 0;
+    bool overflow = false;
+
+    for (uint32_t tile = 0;; ++tile) {
+        const bool from_pool = tile < pool_tiles;  // warp-uniform
+        if (!from_pool && chunk >= n_chunks) { break; }
+        psim::Phonon p;
+        float t_first = P.step_time;
+        uint32_t start = a.step_begin;
+        bool alive = false;
+        if (from_pool) {
+            const uint32_t idx = tile * 32u + lane;
+            if (idx < n_in) {
+                const float4 va = a.in_a[seg + idx];
+                const uint4 vb = a.in_b[seg + idx];
+                p.b1 = va.x;
+                p.b2 = va.y;
+                p.dx = va.z;
+                p.dy = va.w;
+                p.w = __uint_as_float(vb.x);
+                p.packed = vb.y;
+                p.cell = vb.z;
+                p.id_lo = vb.w;
+                alive = true;
+            }
+        } else {
+            const uint64_t item = chunk * 32u + lane;
+            if (item < a.n_births) {
+                // which (step, source) group does this item belong to?
+                const uint64_t key = item + a.birth_base;
+                uint32_t lo = 0, hi = a.n_birth_entries;  // prefix[lo] <= key < prefix[hi]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (key < __ldg(&a.birth_prefix[mid])) {
+                        hi = mid;
+                    } else {
+                        lo = mid;
+                    }
+                }
+                const DevBirth b = a.births[lo];
+                const uint64_t j = b.j0 + (key - __ldg(&a.birth_prefix[lo])) * b.stride;
+                start = b.step;
+                t_first = psim::create_phonon(P, P.sources[b.source], j, b.step, p);
+                alive = true;
+            }
+            chunk += W;
+        }
+        float vel = alive ? ((P.phasor) ? 1000.f : psim::phonon_velocity(P, p.packed)) : 0.f;
+        for (uint32_t s = a.step_begin; s < a.step_end; ++s) {  // warp-uniform trip count
+            const bool act = alive && s >= start;
+            uint32_t sensor = 0;
+            if (act) {
+                alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, vel, sensor, my_events);
+                ++my_steps;
+                if (!alive) { ++my_absorbed; }
+            }
+            // measurement event: the phonon now belongs to step s + 1 (modelSimulator.cpp:182-186)
+            if (act && alive && s + 1 >= P.first_tally_step) {
+                const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
+                const int32_t fx = psim::flux_fixed(p.dx * vel) * sg;
+                const int32_t fy = psim::flux_fixed(p.dy * vel) * sg;
+                if (a.tally_aggregate) {
+                    // warp shuffle stage: lanes that hit the same sensor combine before touching memory
+                    const unsigned peers = __match_any_sync(__activemask(), sensor);
+                    const int32_t es = __reduce_add_sync(peers, sg);
+                    const int32_t fxs = __reduce_add_sync(peers, fx);
+                    const int32_t fys = __reduce_add_sync(peers, fy);
+                    if (lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
+                        tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, es, fxs, fys);
+                    }
+                } else {
+                    tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, sg, fx, fy);
+                }
+            }
+        }
+        // compaction: survivors go to consecutive slots of this warp's output segment
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, alive);
+        if (alive) {
+            const uint32_t slot = n_out + __popc(m & ((1u << lane) - 1u));
+            if (slot < a.seg_cap) {
+                a.out_a[seg + slot] = make_float4(p.b1, p.b2, p.dx, p.dy);
+                a.out_b[seg + slot] = make_uint4(__float_as_uint(p.w), p.packed, p.cell, p.id_lo);
+            } else {
+                overflow = true;
+            }
+        }
+        n_out += __popc(m);
+    }
+    if (lane == 0) { a.cnt_out[w] = min(n_out, a.seg_cap); }
+
+    // statistics: one atomic per warp
+    unsigned long long ev = my_events;
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_xor_sync(0xFFFFFFFFu, my_steps, o);
+        ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o);
+        my_absorbed += __shfl_xor_sync(0xFFFFFFFFu, my_absorbed, o);
+    }
+    const bool any_overflow = __any_sync(0xFFFFFFFFu, overflow);
+    if (lane == 0) {
+        if (my_steps) { atomicAdd(&a.stats[0], my_steps); }
+        if (ev) { atomicAdd(&a.stats[1], ev); }
+        if (my_absorbed) { atomicAdd(&a.stats[2], my_absorbed); }
+        if (any_overflow) { atomicAdd(&a.stats[3], 1ull); }
+        if (n_out) { atomicAdd(&a.alive_hist[a.launch_index], static_cast<unsigned long long>(min(n_out, a.seg_cap))); }
+    }
+
+    // block stage -> one global atomic per (sensor, step) the block touched
+    if (a.tally_shared) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nst * S; i += kBlock) {
+            const uint32_t row = a.step_begin + i / S + 1;
+            if (row < P.first_tally_step) { continue; }
+            const size_t k = static_cast<size_t>(row - P.first_tally_step) * S + (i % S);
+            const int32_t e = acc_e[i];
+            const long long fx = acc_f[2 * i], fy = acc_f[2 * i + 1];
+            if (e) { atomicAdd(&a.tally_e[k], e); }
+            if (fx) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k]), static_cast<unsigned long long>(fx)); }
+            if (fy) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k + 1]), static_cast<unsigned long long>(fy)); }
+        }
+    }
+}
+
+__global__ void cell_histogram_kernel(const uint4* pool_b, const uint32_t* cnt, uint32_t seg_cap, uint32_t n_warps,
+                                      unsigned long long* hist) {
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (w >= n_warps) { return; }
+    const uint32_t n = cnt[w];
+    for (uint32_t i = threadIdx.x & 31u; i < n; i += 32u) {
+        atomicAdd(&hist[pool_b[static_cast<size_t>(w) * seg_cap + i].z], 1ull);
+    }
+}
+
+__global__ void probe_sample_kernel(DevParams P, uint32_t table, const float* u1, const float* u2, size_t n,
+                                    uint32_t* out_bin, uint32_t* out_ta) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) { return; }
+    const float2* t = P.tables + static_cast<size_t>(table) * PSIM_BINS;
+    const uint32_t bin = psim::bisect_table(t, u1[i]);
+    out_bin[i] = bin;
+    out_ta[i] = (u2[i] <= t[bin].y) ? 0u : 1u;
+}
+
+__global__ void probe_rates_kernel(DevParams P, uint32_t sensor, const float* w, const uint32_t* ta, size_t n, float* out) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) { return; }
+    const DevSensor s = psim::load_sensor(P.sensors, sensor);
+    float rn, ru, ri;
+    psim::relax_rates(s, w[i], ta[i], rn, ru, ri);
+    out[3 * i] = rn;
+    out[3 * i + 1] = ru;
+    out[3 * i + 2] = ri;
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------------------
+struct psim_gpu {
+    int device = 0;
+    int sm_count = 0;
+    psim::HostImage img;
+    psim::BirthPlan plan;
+    DevParams P{};  // device pointers
+    void* d_cells = nullptr;
+    void* d_subs = nullptr;
+    void* d_sensors = nullptr;
+    void* d_materials = nullptr;
+    void* d_emitters = nullptr;
+    void* d_tables = nullptr;
+    void* d_velocities = nullptr;
+    void* d_sources = nullptr;
+    DevBirth* d_births = nullptr;
+    uint64_t* d_prefix = nullptr;
+    float4* pool_a[2] = { nullptr, nullptr };
+    uint4* pool_b[2] = { nullptr, nullptr };
+    uint32_t* cnt[2] = { nullptr, nullptr };
+    int cur = 0;  // copy holding the live pool
+    uint32_t seg_cap = 0, n_warps = 0;
+    int32_t* tally_e = nullptr;
+    long long* tally_f = nullptr;
+    unsigned long long* d_stats = nullptr;
+    unsigned long long* d_alive_hist = nullptr;
+    unsigned long long* d_hist = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool have_sources = false;
+    bool timing_open = false;
+    uint32_t next_step = 0;
+    uint32_t launches = 0;
+    uint32_t birth_offset = 0;
+    double kernel_ms = 0.;
+    // options
+    int64_t opt_steps_per_launch = 1;
+    int64_t opt_warps_per_sm = 0;
+    int64_t opt_tally_shared = -1;
+    int64_t opt_tally_aggregate = 0;
+    uint32_t last_tally_shared = 0;
+    std::string err;
+};
+
+namespace {
+
+int cuda_fail(psim_gpu* h, cudaError_t e, const char* what) {
+    h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return PSIM_E_CUDA;
+}
+
+#define PSIM_CUDA(call)                                               \
+    do {                                                              \
+        const cudaError_t e_ = (call);                                \
+        if (e_ != cudaSuccess) { return cuda_fail(h, e_, #call); }    \
+    } while (0)
+
+template<typename T> int upload(psim_gpu* h, void** dst, const std::vector<T>& v) {
+    PSIM_CUDA(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) { PSIM_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    return 0;
+}
+
+void free_pool(psim_gpu* h) {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->pool_a[i]);
+        cudaFree(h->pool_b[i]);
+        cudaFree(h->cnt[i]);
+        h->pool_a[i] = nullptr;
+        h->pool_b[i] = nullptr;
+        h->cnt[i] = nullptr;
+    }
+    cudaFree(h->d_births);
+    cudaFree(h->d_prefix);
+    cudaFree(h->d_sources);
+    cudaFree(h->d_alive_hist);
+    h->d_births = nullptr;
+    h->d_prefix = nullptr;
+    h->d_sources = nullptr;
+    h->d_alive_hist = nullptr;
+}
+
+size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
+    return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
+}
+
+int zero_run_state(psim_gpu* h) {
+    const DevParams& P = h->P;
+    const size_t n = static_cast<size_t>(P.recorded_steps) * P.n_sensors;
+    PSIM_CUDA(cudaMemsetAsync(h->tally_e, 0, n * sizeof(int32_t), h->stream));
+    PSIM_CUDA(cudaMemsetAsync(h->tally_f, 0, n * 2 * sizeof(long long), h->stream));
+    PSIM_CUDA(cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
+    if (h->d_alive_hist) {
+        PSIM_CUDA(cudaMemsetAsync(h->d_alive_hist, 0, static_cast<size_t>(P.num_steps + 1) * sizeof(unsigned long long), h->stream));
+    }
+    if (h->cnt[0]) {
+        PSIM_CUDA(cudaMemsetAsync(h->cnt[0], 0, h->n_warps * sizeof(uint32_t), h->stream));
+        PSIM_CUDA(cudaMemsetAsync(h->cnt[1], 0, h->n_warps * sizeof(uint32_t), h->stream));
+    }
+    h->cur = 0;
+    h->next_step = 0;
+    h->launches = 0;
+    h->birth_offset = 0;
+    h->kernel_ms = 0.;
+    h->timing_open = false;
+    PSIM_CUDA(cudaStreamSynchronize(h->stream));  // callers may launch on a different stream next
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
+    if (!desc || !out) {
+        g_create_error = "null argument";
+        return PSIM_E_INVALID;
+    }
+    *out = nullptr;
+    int n_dev = 0;
+    const cudaError_t e0 = cudaGetDeviceCount(&n_dev);
+    if (e0 != cudaSuccess || n_dev == 0) {
+        g_create_error = std::string("no usable CUDA device (this library has no CPU path): ") +
+                         (e0 != cudaSuccess ? cudaGetErrorString(e0) : "device count is 0");
+        return PSIM_E_NO_DEVICE;
+    }
+    psim_gpu* h = new psim_gpu();
+    auto bail = [&](int rc) {
+        g_create_error = h->err;
+        psim_gpu_destroy(h);
+        return rc;
+    };
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) { device = 0; }
+    }
+    if (device >= n_dev) {
+        h->err = "device index out of range";
+        return bail(PSIM_E_NO_DEVICE);
+    }
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        h->err = "cudaSetDevice failed";
+        return bail(PSIM_E_NO_DEVICE);
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        h->err = "cudaGetDeviceProperties failed";
+        return bail(PSIM_E_NO_DEVICE);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if (int rc = psim::flatten_model(*desc, h->img, h->err)) { return bail(rc); }
+    auto setup = [&]() -> int {
+        if (int rc = upload(h, &h->d_cells, h->img.cells)) { return rc; }
+        if (int rc = upload(h, &h->d_subs, h->img.subs)) { return rc; }
+        if (int rc = upload(h, &h->d_sensors, h->img.sensors)) { return rc; }
+        if (int rc = upload(h, &h->d_materials, h->img.materials)) { return rc; }
+        if (int rc = upload(h, &h->d_emitters, h->img.emitters)) { return rc; }
+        if (int rc = upload(h, &h->d_tables, h->img.tables)) { return rc; }
+        if (int rc = upload(h, &h->d_velocities, h->img.velocities)) { return rc; }
+        h->P = h->img.scalars;
+        h->P.cells = static_cast<const DevCell*>(h->d_cells);
+        h->P.subs = static_cast<const DevSub*>(h->d_subs);
+        h->P.sensors = static_cast<const DevSensor*>(h->d_sensors);
+        h->P.materials = static_cast<const DevMaterial*>(h->d_materials);
+        h->P.emitters = static_cast<const DevEmitter*>(h->d_emitters);
+        h->P.tables = static_cast<const float2*>(h->d_tables);
+        h->P.velocities = static_cast<const float*>(h->d_velocities);
+        const size_t n = static_cast<size_t>(h->P.recorded_steps) * h->P.n_sensors;
+        PSIM_CUDA(cudaMalloc(&h->tally_e, n * sizeof(int32_t)));
+        PSIM_CUDA(cudaMalloc(&h->tally_f, n * 2 * sizeof(long long)));
+        PSIM_CUDA(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
+        PSIM_CUDA(cudaMalloc(&h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
+        PSIM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        PSIM_CUDA(cudaEventCreate(&h->ev_begin));
+        PSIM_CUDA(cudaEventCreate(&h->ev_end));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        return zero_run_state(h);
+    };
+    if (int rc = setup()) { return bail(rc); }
+    *out = h;
+    return PSIM_OK;
+}
+
+int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint64_t seed, uint32_t shard,
+                         uint32_t num_shards) {
+    if (!h) { return PSIM_E_INVALID; }
+    PSIM_CUDA(cudaSetDevice(h->device));
+    PSIM_CUDA(cudaStreamSynchronize(h->stream));
+    if (int rc = psim::plan_births(h->img, sources, n, shard, num_shards, h->plan, h->err)) { return rc; }
+    free_pool(h);
+    h->have_sources = false;
+    if (int rc = upload(h, &h->d_sources, h->plan.sources)) { return rc; }
+    {
+        void* p = nullptr;
+        if (int rc = upload(h, &p, h->plan.births)) { return rc; }
+        h->d_births = static_cast<DevBirth*>(p);
+        p = nullptr;
+        if (int rc = upload(h, &p, h->plan.prefix)) { return rc; }
+        h->d_prefix = static_cast<uint64_t*>(p);
+    }
+    h->P.sources = static_cast<const DevSource*>(h->d_sources);
+    h->P.n_sources = static_cast<uint32_t>(n);
+    h->P.seed_lo = static_cast<uint32_t>(seed);
+    h->P.seed_hi = static_cast<uint32_t>(seed >> 32);
+
+    // pool geometry: one segment per resident warp
+    int blocks_per_sm = 0;
+    PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel, kBlock, 0));
+    if (blocks_per_sm < 1) { blocks_per_sm = 1; }
+    int warps_per_sm = blocks_per_sm * kWarpsPerBlock;
+    if (h->opt_warps_per_sm > 0) {
+        warps_per_sm = static_cast<int>(std::max<int64_t>(kWarpsPerBlock, h->opt_warps_per_sm / kWarpsPerBlock * kWarpsPerBlock));
+    }
+    h->n_warps = static_cast<uint32_t>(h->sm_count * warps_per_sm);
+    const uint64_t per_warp = (h->plan.shard_phonons + h->n_warps - 1) / h->n_warps;
+    const uint64_t cap = per_warp + per_warp / 8 + 1024;
+    if (cap > 0xFFFFFFF0ull) {
+        h->err = "shard too large for one device";
+        return PSIM_E_INVALID;
+    }
+    h->seg_cap = static_cast<uint32_t>((cap + 31) & ~31ull);
+    const size_t slots = static_cast<size_t>(h->seg_cap) * h->n_warps;
+    for (int i = 0; i < 2; ++i) {
+        PSIM_CUDA(cudaMalloc(&h->pool_a[i], slots * sizeof(float4)));
+        PSIM_CUDA(cudaMalloc(&h->pool_b[i], slots * sizeof(uint4)));
+        PSIM_CUDA(cudaMalloc(&h->cnt[i], h->n_warps * sizeof(uint32_t)));
+    }
+    PSIM_CUDA(cudaMalloc(&h->d_alive_hist, static_cast<size_t>(h->P.num_steps + 1) * sizeof(unsigned long long)));
+    h->have_sources = true;
+    return zero_run_state(h);
+}
+
+int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void* cuda_stream) {
+    if (!h) { return PSIM_E_INVALID; }
+    if (!h->have_sources) {
+        h->err = "psim_gpu_set_sources must be called before running";
+        return PSIM_E_STATE;
+    }
+    const uint32_t last = h->P.num_steps - 1;
+    step_end = std::min(step_end, last);
+    if (step_begin != h->next_step || step_end < step_begin) {
+        h->err = "measurement steps must be submitted in order, starting at 0 after set_sources/reset";
+        return PSIM_E_STATE;
+    }
+    PSIM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+    const uint32_t B = static_cast<uint32_t>(std::max<int64_t>(1, h->opt_steps_per_launch));
+    for (uint32_t s0 = step_begin; s0 < step_end; s0 += B) {
+        const uint32_t s1 = std::min(s0 + B, step_end);
+        LaunchArgs a{};
+        a.P = h->P;
+        a.in_a = h->pool_a[h->cur];
+        a.in_b = h->pool_b[h->cur];
+        a.out_a = h->pool_a[h->cur ^ 1];
+        a.out_b = h->pool_b[h->cur ^ 1];
+        a.cnt_in = h->cnt[h->cur];
+        a.cnt_out = h->cnt[h->cur ^ 1];
+        a.seg_cap = h->seg_cap;
+        a.n_warps = h->n_warps;
+        a.step_begin = s0;
+        a.step_end = s1;
+        const uint32_t e0 = h->plan.step_begin[s0], e1 = h->plan.step_begin[s1];
+        a.births = h->d_births + e0;
+        a.birth_prefix = h->d_prefix + e0;
+        a.n_birth_entries = e1 - e0;
+        a.birth_base = h->plan.prefix[e0];
+        a.n_births = h->plan.prefix[e1] - h->plan.prefix[e0];
+        a.birth_warp_offset = h->birth_offset;
+        h->birth_offset = static_cast<uint32_t>((h->birth_offset + ((a.n_births + 31) >> 5)) % h->n_warps);
+        a.tally_e = h->tally_e;
+        a.tally_f = h->tally_f;
+        const size_t smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
+        const bool tallies_here = s1 + 1 > h->P.first_tally_step;  // any recorded measurement in this launch?
+        bool shared = h->opt_tally_shared < 0 ? (smem <= 32 * 1024) : (h->opt_tally_shared != 0 && smem <= 200 * 1024);
+        if (!tallies_here) { shared = false; }
+        a.tally_shared = shared ? 1u : 0u;
+        a.tally_aggregate = h->opt_tally_aggregate ? 1u : 0u;
+        a.stats = h->d_stats;
+        a.alive_hist = h->d_alive_hist;
+        a.launch_index = h->launches;
+        h->last_tally_shared = a.tally_shared;
+        if (!h->timing_open) {
+            PSIM_CUDA(cudaEventRecord(h->ev_begin, st));
+            h->timing_open = true;
+        }
+        drift_kernel<<<h->n_warps / kWarpsPerBlock, kBlock, shared ? smem : 0, st>>>(a);
+        PSIM_CUDA(cudaGetLastError());
+        h->cur ^= 1;
+        ++h->launches;
+    }
+    PSIM_CUDA(cudaEventRecord(h->ev_end, st));
+    h->next_step = step_end;
+    return PSIM_OK;
+}
+
+int psim_gpu_synchronize(psim_gpu* h) {
+    if (!h) { return PSIM_E_INVALID; }
+    PSIM_CUDA(cudaSetDevice(h->device));
+    PSIM_CUDA(cudaDeviceSynchronize());
+    if (h->timing_open) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end) == cudaSuccess) { h->kernel_ms = ms; }
+    }
+    unsigned long long st[4] = { 0, 0, 0, 0 };
+    PSIM_CUDA(cudaMemcpy(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[3]) {
+        h->err = "phonon pool capacity exceeded";
+        return PSIM_E_OVERFLOW;
+    }
+    return PSIM_OK;
+}
+
+int psim_gpu_run(psim_gpu* h) {
+    if (!h) { return PSIM_E_INVALID; }
+    if (int rc = psim_gpu_run_steps(h, h->next_step, h->P.num_steps - 1, nullptr)) { return rc; }
+    return psim_gpu_synchronize(h);
+}
+
+int psim_gpu_get_tallies(psim_gpu* h, int32_t* energy, double* flux, int64_t* flux_fixed) {
+    if (!h) { return PSIM_E_INVALID; }
+    if (int rc = psim_gpu_synchronize(h)) { return rc; }
+    const uint32_t R = h->P.recorded_steps, S = h->P.n_sensors;
+    const size_t n = static_cast<size_t>(R) * S;
+    std::vector<int32_t> e(n);
+    std::vector<long long> f(2 * n);
+    PSIM_CUDA(cudaMemcpy(e.data(), h->tally_e, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    PSIM_CUDA(cudaMemcpy(f.data(), h->tally_f, 2 * n * sizeof(long long), cudaMemcpyDeviceToHost));
+    const double scale = 1. / static_cast<double>(1 << PSIM_FLUX_FRAC_BITS);
+    for (uint32_t r = 0; r < R; ++r) {
+        for (uint32_t s = 0; s < S; ++s) {  // device [R][S] -> caller [S][R], the reference's per-sensor vectors
+            const size_t src = static_cast<size_t>(r) * S + s, dst = static_cast<size_t>(s) * R + r;
+            if (energy) { energy[dst] = e[src]; }
+            if (flux) {
+                flux[2 * dst] = static_cast<double>(f[2 * src]) * scale;
+                flux[2 * dst + 1] = static_cast<double>(f[2 * src + 1]) * scale;
+            }
+            if (flux_fixed) {
+                flux_fixed[2 * dst] = f[2 * src];
+                flux_fixed[2 * dst + 1] = f[2 * src + 1];
+            }
+        }
+    }
+    return PSIM_OK;
+}
+
+int psim_gpu_tally_buffers(psim_gpu* h, void** energy_dev, void** flux_dev, uint32_t* recorded_steps, uint32_t* num_sensors) {
+    if (!h) { return PSIM_E_INVALID; }
+    if (energy_dev) { *energy_dev = h->tally_e; }
+    if (flux_dev) { *flux_dev = h->tally_f; }
+    if (recorded_steps) { *recorded_steps = h->P.recorded_steps; }
+    if (num_sensors) { *num_sensors = h->P.n_sensors; }
+    return PSIM_OK;
+}
+
+int psim_gpu_alive(psim_gpu* h, uint64_t* alive) {
+    if (!h || !alive) { return PSIM_E_INVALID; }
+    *alive = 0;
+    if (!h->have_sources) { return PSIM_OK; }
+    if (int rc = psim_gpu_synchronize(h)) { return rc; }
+    std::vector<uint32_t> c(h->n_warps);
+    PSIM_CUDA(cudaMemcpy(c.data(), h->cnt[h->cur], c.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t v : c) { *alive += v; }
+    return PSIM_OK;
+}
+
+int psim_gpu_cell_histogram(psim_gpu* h, uint64_t* per_cell) {
+    if (!h || !per_cell) { return PSIM_E_INVALID; }
+    if (!h->have_sources) {
+        h->err = "no pool yet";
+        return PSIM_E_STATE;
+    }
+    if (int rc = psim_gpu_synchronize(h)) { return rc; }
+    PSIM_CUDA(cudaMemset(h->d_hist, 0, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
+    cell_histogram_kernel<<<h->n_warps / kWarpsPerBlock, kBlock>>>(h->pool_b[h->cur], h->cnt[h->cur], h->seg_cap, h->n_warps, h->d_hist);
+    PSIM_CUDA(cudaGetLastError());
+    PSIM_CUDA(cudaMemcpy(per_cell, h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return PSIM_OK;
+}
+
+int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
+    if (!h || !out) { return PSIM_E_INVALID; }
+    std::memset(out, 0, sizeof(*out));
+    if (int rc = psim_gpu_synchronize(h)) { return rc; }
+    unsigned long long st[4] = { 0, 0, 0, 0 };
+    PSIM_CUDA(cudaMemcpy(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    out->total_phonons = h->plan.total_phonons;
+    out->shard_phonons = h->plan.shard_phonons + h->plan.shard_unrecorded;
+    out->drift_steps = st[0];
+    out->events = st[1];
+    if (h->d_alive_hist && h->launches) {
+        std::vector<unsigned long long> hist(h->launches);
+        PSIM_CUDA(cudaMemcpy(hist.data(), h->d_alive_hist, hist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        out->peak_alive = *std::max_element(hist.begin(), hist.end());
+    }
+    out->kernel_ms = h->kernel_ms;
+    out->launches = h->launches;
+    out->steps_per_launch = static_cast<uint32_t>(std::max<int64_t>(1, h->opt_steps_per_launch));
+    out->warps = h->n_warps;
+    out->tally_in_shared = h->last_tally_shared;
+    out->image_bytes = h->img.cells.size() * sizeof(DevCell) + h->img.subs.size() * sizeof(DevSub) +
+                       h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
+                       h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +
+                       h->img.velocities.size() * sizeof(float);
+    out->plan_bytes = h->plan.sources.size() * sizeof(DevSource) + h->plan.births.size() * sizeof(DevBirth) +
+                      h->plan.prefix.size() * sizeof(uint64_t);
+    out->tally_bytes = static_cast<uint64_t>(h->P.recorded_steps) * h->P.n_sensors * 20ull;
+    return PSIM_OK;
+}
+
+int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
+    if (!h || !name) { return PSIM_E_INVALID; }
+    const std::string k(name);
+    if (k == "steps_per_launch") {
+        if (value < 1 || value > 64) {
+            h->err = "steps_per_launch must be in [1, 64]";
+            return PSIM_E_INVALID;
+        }
+        h->opt_steps_per_launch = value;
+    } else if (k == "warps_per_sm") {
+        if (h->have_sources) {
+            h->err = "warps_per_sm must be set before set_sources";
+            return PSIM_E_STATE;
+        }
+        h->opt_warps_per_sm = value;
+    } else if (k == "tally_shared") {
+        h->opt_tally_shared = value;
+    } else if (k == "tally_aggregate") {
+        h->opt_tally_aggregate = value;
+    } else {
+        h->err = "unknown option: " + k;
+        return PSIM_E_INVALID;
+    }
+    return PSIM_OK;
+}
+
+int psim_gpu_reset(psim_gpu* h) {
+    if (!h) { return PSIM_E_INVALID; }
+    PSIM_CUDA(cudaSetDevice(h->device));
+    PSIM_CUDA(cudaDeviceSynchronize());
+    if (int rc = zero_run_state(h)) { return rc; }
+    PSIM_CUDA(cudaStreamSynchronize(h->stream));
+    return PSIM_OK;
+}
+
+void psim_gpu_destroy(psim_gpu* h) {
+    if (!h) { return; }
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_pool(h);
+    cudaFree(h->d_cells);
+    cudaFree(h->d_subs);
+    cudaFree(h->d_sensors);
+    cudaFree(h->d_materials);
+    cudaFree(h->d_emitters);
+    cudaFree(h->d_tables);
+    cudaFree(h->d_velocities);
+    cudaFree(h->tally_e);
+    cudaFree(h->tally_f);
+    cudaFree(h->d_stats);
+    cudaFree(h->d_hist);
+    if (h->ev_begin) { cudaEventDestroy(h->ev_begin); }
+    if (h->ev_end) { cudaEventDestroy(h->ev_end); }
+    if (h->stream) { cudaStreamDestroy(h->stream); }
+    delete h;
+}
+
+const char* psim_gpu_last_error(const psim_gpu* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int psim_gpu_probe_sample(psim_gpu* h, uint32_t table, const float* u1, const float* u2, size_t n, uint32_t* out_bin,
+                          uint32_t* out_ta) {
+    if (!h || !u1 || !u2 || !out_bin || !out_ta || table >= h->P.n_tables) { return PSIM_E_INVALID; }
+    if (n == 0) { return PSIM_OK; }
+    PSIM_CUDA(cudaSetDevice(h->device));
+    float *d1 = nullptr, *d2 = nullptr;
+    uint32_t *db = nullptr, *dt = nullptr;
+    PSIM_CUDA(cudaMalloc(&d1, n * 4));
+    PSIM_CUDA(cudaMalloc(&d2, n * 4));
+    PSIM_CUDA(cudaMalloc(&db, n * 4));
+    PSIM_CUDA(cudaMalloc(&dt, n * 4));
+    PSIM_CUDA(cudaMemcpy(d1, u1, n * 4, cudaMemcpyHostToDevice));
+    PSIM_CUDA(cudaMemcpy(d2, u2, n * 4, cudaMemcpyHostToDevice));
+    probe_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, table, d1, d2, n, db, dt);
+    PSIM_CUDA(cudaGetLastError());
+    PSIM_CUDA(cudaMemcpy(out_bin, db, n * 4, cudaMemcpyDeviceToHost));
+    PSIM_CUDA(cudaMemcpy(out_ta, dt, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d1);
+    cudaFree(d2);
+    cudaFree(db);
+    cudaFree(dt);
+    return PSIM_OK;
+}
+
+int psim_gpu_probe_rates(psim_gpu* h, uint32_t sensor, const double* omega, const uint32_t* ta, size_t n, double* rates) {
+    if (!h || !omega || !ta || !rates || sensor >= h->P.n_sensors) { return PSIM_E_INVALID; }
+    if (n == 0) { return PSIM_OK; }
+    PSIM_CUDA(cudaSetDevice(h->device));
+    std::vector<float> w(n), r(3 * n);
+    for (size_t i = 0; i < n; ++i) { w[i] = static_cast<float>(omega[i] * PSIM_FREQ_SCALE); }
+    float *dw = nullptr, *dr = nullptr;
+    uint32_t* dta = nullptr;
+    PSIM_CUDA(cudaMalloc(&dw, n * 4));
+    PSIM_CUDA(cudaMalloc(&dr, 3 * n * 4));
+    PSIM_CUDA(cudaMalloc(&dta, n * 4));
+    PSIM_CUDA(cudaMemcpy(dw, w.data(), n * 4, cudaMemcpyHostToDevice));
+    PSIM_CUDA(cudaMemcpy(dta, ta, n * 4, cudaMemcpyHostToDevice));
+    probe_rates_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, sensor, dw, dta, n, dr);
+    PSIM_CUDA(cudaGetLastError());
+    PSIM_CUDA(cudaMemcpy(r.data(), dr, 3 * n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dw);
+    cudaFree(dr);
+    cudaFree(dta);
+    for (size_t i = 0; i < 3 * n; ++i) { rates[i] = static_cast<double>(r[i]) * 1e9; }  // 1/ns -> 1/s
+    return PSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+"""The parity cases: name -> model dict, at the reduced phonon counts the golden fixtures were generated with.
+
+Shared by tests/golden/make_golden.py (which runs the reference on them) and by the tests (which run the CUDA
+path, or the CPU-side emulation of its device functions, on the SAME model files).  BASELINE.json's configs:
+linear_demo, kinked (specular as shipped + a diffuse variant), linear_sides periodic / transient, full
+(non-deviational) mode, and the synthetic Si/Ge grid.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+
+from psim_b200 import configs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+KINKED_GZ = os.path.join(GOLDEN, "kinked_demo_120_35_spec.json.gz")
+REF_KINKED = "/root/reference/psim_python/json/kinked_demo_120_35_spec.json"
+
+HOLLAND_SI = {
+    "name": "Silicon",
+    "d_data": {"la_data": [-2.01e-07, 9010.0, 0.0], "max_freq_la": 7.63916048e13,
+               "ta_data": [-2.26e-07, 5230.0, 0.0], "max_freq_ta": 3.0100793072e13},
+    "r_data": {"b_l": 2.0e-24, "b_tn": 9.3e-13, "b_tu": 5.5e-18, "b_i": 1.2e-45, "w": 2.417e13},
+}
+
+
+def kinked_model():
+    """The reference's shipped kinked-wire model (its generator is outside the hot path; the geometry is a fixture)."""
+    if os.path.exists(KINKED_GZ):
+        with gzip.open(KINKED_GZ, "rt") as f:
+            return json.load(f)
+    if os.path.exists(REF_KINKED):
+        return json.load(open(REF_KINKED))
+    return None
+
+
+def cases(include_kinked: bool = True):
+    c = {}
+    c["linear_demo"] = configs.linear(num_phonons=400_000).to_dict()
+    c["linear_diffuse"] = configs.linear(num_phonons=200_000, spec=0.3).to_dict()
+    c["linear_hot_cells"] = configs.linear(num_phonons=200_000, t_init=305.0).to_dict()
+    c["linear_impurity"] = configs.linear(num_phonons=200_000, material=HOLLAND_SI).to_dict()
+    c["linear_full"] = configs.full_mode(configs.linear(num_phonons=200_000).to_dict(), t_init=25.0,
+                                         temp_map={310: 30.0, 290: 20.0})
+    c["sides_ss"] = configs.linear_sides(num_phonons=100_000).to_dict()
+    c["sides_per"] = configs.linear_sides(num_phonons=100_000, sim_type=1, step_interval=4).to_dict()
+    c["sides_trans"] = configs.linear_sides(num_phonons=100_000, sim_type=2, step_interval=4, start_time=0.1,
+                                            duration=0.15).to_dict()
+    c["sides_per_full"] = configs.full_mode(
+        configs.linear_sides(num_phonons=100_000, sim_type=1, step_interval=4).to_dict(), t_init=25.0,
+        temp_map={330: 30.0, 270: 20.0, 300.0: 25.0})
+    c["sige"] = configs.si_ge_grid(num_phonons=200_000).to_dict()
+    if include_kinked:
+        kinked = kinked_model()
+        if kinked is not None:
+            c["kinked_spec"] = configs.with_settings(kinked, num_phonons=50_000)
+            c["kinked_diffuse"] = configs.with_specularity(configs.with_settings(kinked, num_phonons=30_000), 0.5)
+    return c

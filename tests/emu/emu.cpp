@@ -1,0 +1,102 @@
+// TEST INFRASTRUCTURE ONLY.  Host build of psim_b200/csrc/device_core.cuh: the same per-phonon functions the
+// sm_100a kernels call, driven by a plain loop, so that the ALGORITHM (barycentric flight, stratified births,
+// fp32 arithmetic, Philox streams) can be checked statistically against the reference's golden data in the
+// GPU-less authoring container.  It is compiled into tests/emu/libpsim_emu.so by psim_b200/build.py:build_emu,
+// is loaded only by tests/, and is never part of libpsim_b200.so (which has no CPU path).
+#include "../../psim_b200/csrc/device_core.cuh"
+#include "../../psim_b200/csrc/flatten.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sources, size_t n_sources, uint64_t seed,
+                            uint32_t shard, uint32_t num_shards, uint32_t steps_per_pass, int32_t* energy /*[S][R]*/,
+                            double* flux /*[S][R][2]*/, int64_t* flux_fixed, uint64_t* drift_steps, uint64_t* events,
+                            uint64_t* alive_per_pass /* [M] or NULL */, uint64_t* cell_hist_steps /* [M][cells] or NULL */,
+                            char* err, size_t err_len) {
+    psim::HostImage img;
+    psim::BirthPlan plan;
+    std::string e;
+    int rc = psim::flatten_model(*desc, img, e);
+    if (!rc) { rc = psim::plan_births(img, sources, n_sources, shard, num_shards, plan, e); }
+    if (rc) {
+        if (err && err_len) { std::strncpy(err, e.c_str(), err_len - 1), err[err_len - 1] = 0; }
+        return rc;
+    }
+    DevParams P = img.scalars;
+    P.cells = img.cells.data();
+    P.subs = img.subs.data();
+    P.sensors = img.sensors.data();
+    P.materials = img.materials.data();
+    P.emitters = img.emitters.data();
+    P.tables = img.tables.data();
+    P.velocities = img.velocities.data();
+    P.sources = plan.sources.data();
+    P.n_sources = static_cast<uint32_t>(n_sources);
+    P.seed_lo = static_cast<uint32_t>(seed);
+    P.seed_hi = static_cast<uint32_t>(seed >> 32);
+    const uint32_t S = P.n_sensors, R = P.recorded_steps, M = P.num_steps;
+    std::vector<long long> te(static_cast<size_t>(R) * S, 0), tf(static_cast<size_t>(R) * S * 2, 0);
+    std::vector<psim::Phonon> pool, next;
+    uint64_t n_steps = 0;
+    uint32_t n_events = 0;
+    uint64_t total_events = 0;
+    const uint32_t B = steps_per_pass ? steps_per_pass : 1;
+    auto run_one = [&](psim::Phonon p, uint32_t start, float t_first, uint32_t s0, uint32_t s1) {
+        float vel = P.phasor ? 1000.f : psim::phonon_velocity(P, p.packed);
+        bool alive = true;
+        for (uint32_t s = start; s < s1 && alive; ++s) {
+            uint32_t sensor = 0;
+            n_events = 0;
+            alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, vel, sensor, n_events);
+            total_events += n_events;
+            ++n_steps;
+            if (alive && s + 1 >= P.first_tally_step) {
+                const int sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
+                const size_t k = static_cast<size_t>(s + 1 - P.first_tally_step) * S + sensor;
+                te[k] += sg;
+                tf[2 * k] += static_cast<long long>(psim::flux_fixed(p.dx * vel)) * sg;
+                tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(p.dy * vel)) * sg;
+            }
+        }
+        (void)s0;
+        if (alive) { next.push_back(p); }
+    };
+    for (uint32_t s0 = 0; s0 + 1 < M; s0 += B) {
+        const uint32_t s1 = std::min(s0 + B, M - 1);
+        next.clear();
+        for (const auto& p : pool) { run_one(p, s0, P.step_time, s0, s1); }
+        for (uint32_t eidx = plan.step_begin[s0]; eidx < plan.step_begin[s1]; ++eidx) {
+            const DevBirth& b = plan.births[eidx];
+            for (uint32_t i = 0; i < b.count; ++i) {
+                psim::Phonon p;
+                const float t_first = psim::create_phonon(P, plan.sources[b.source], b.j0 + static_cast<uint64_t>(i) * b.stride, b.step, p);
+                run_one(p, b.step, t_first, s0, s1);
+            }
+        }
+        pool.swap(next);
+        if (alive_per_pass) { alive_per_pass[s1 - 1] = pool.size(); }
+        if (cell_hist_steps) {
+            for (const auto& p : pool) { ++cell_hist_steps[static_cast<size_t>(s1 - 1) * P.n_cells + p.cell]; }
+        }
+    }
+    const double scale = 1. / static_cast<double>(1 << PSIM_FLUX_FRAC_BITS);
+    for (uint32_t r = 0; r < R; ++r) {
+        for (uint32_t s = 0; s < S; ++s) {
+            const size_t src = static_cast<size_t>(r) * S + s, dst = static_cast<size_t>(s) * R + r;
+            if (energy) { energy[dst] = static_cast<int32_t>(te[src]); }
+            if (flux) {
+                flux[2 * dst] = static_cast<double>(tf[2 * src]) * scale;
+                flux[2 * dst + 1] = static_cast<double>(tf[2 * src + 1]) * scale;
+            }
+            if (flux_fixed) {
+                flux_fixed[2 * dst] = tf[2 * src];
+                flux_fixed[2 * dst + 1] = tf[2 * src + 1];
+            }
+        }
+    }
+    if (drift_steps) { *drift_steps = n_steps; }
+    if (events) { *events = total_events; }
+    return 0;
+}

@@ -32,45 +32,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from psim_b200 import configs  # noqa: E402
+from tests import cases as test_cases  # noqa: E402
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "psim_ref")
 REF_JSON = "/root/reference/psim_python/json"
 NBLOCKS = 20  # periodic / transient traces are compared as NBLOCKS block means over the recorded steps
 
-HOLLAND_SI = {
-    "name": "Silicon",
-    "d_data": {"la_data": [-2.01e-07, 9010.0, 0.0], "max_freq_la": 7.63916048e13,
-               "ta_data": [-2.26e-07, 5230.0, 0.0], "max_freq_ta": 3.0100793072e13},
-    "r_data": {"b_l": 2.0e-24, "b_tn": 9.3e-13, "b_tu": 5.5e-18, "b_i": 1.2e-45, "w": 2.417e13},
-}
-
 
 def cases():
-    """name -> model dict (reduced phonon counts; everything else as BASELINE.json's configs)."""
-    c = {}
-    c["linear_demo"] = configs.linear(num_phonons=400_000).to_dict()
-    c["linear_diffuse"] = configs.linear(num_phonons=200_000, spec=0.3).to_dict()
-    c["linear_hot_cells"] = configs.linear(num_phonons=200_000, t_init=305.0).to_dict()
-    c["linear_impurity"] = configs.linear(num_phonons=200_000, material=HOLLAND_SI).to_dict()
-    c["linear_full"] = configs.full_mode(configs.linear(num_phonons=200_000).to_dict(), t_init=25.0,
-                                         temp_map={310: 30.0, 290: 20.0})
-    c["sides_ss"] = configs.linear_sides(num_phonons=100_000).to_dict()
-    c["sides_per"] = configs.linear_sides(num_phonons=100_000, sim_type=1, step_interval=4).to_dict()
-    c["sides_trans"] = configs.linear_sides(num_phonons=100_000, sim_type=2, step_interval=4, start_time=0.1,
-                                            duration=0.15).to_dict()
-    c["sides_per_full"] = configs.full_mode(
-        configs.linear_sides(num_phonons=100_000, sim_type=1, step_interval=4).to_dict(), t_init=25.0,
-        temp_map={330: 30.0, 270: 20.0, 300.0: 25.0})
-    c["sige"] = configs.si_ge_grid(num_phonons=200_000).to_dict()
+    """name -> model dict (tests/cases.py); also refreshes the compressed kinked-wire geometry fixture."""
     kinked_path = os.path.join(REF_JSON, "kinked_demo_120_35_spec.json")
     if os.path.exists(kinked_path):
         kinked = json.load(open(kinked_path))
-        # the geometry travels to the GPU box as a compressed fixture
         with gzip.open(os.path.join(HERE, "kinked_demo_120_35_spec.json.gz"), "wt", compresslevel=9) as f:
             json.dump(kinked, f, separators=(",", ":"))
-        c["kinked_spec"] = configs.with_settings(kinked, num_phonons=50_000)
-        c["kinked_diffuse"] = configs.with_specularity(configs.with_settings(kinked, num_phonons=30_000), 0.5)
-    return c
+    return test_cases.cases()
 
 
 def read_run(prefix):
