@@ -229,11 +229,12 @@ PSIM_HD void edge_normal(const DevCell& c, uint32_t e, float& nx, float& ny) {
 // Emission (CellOriginBuilder::operator() phononBuilder.cpp:6-16, SurfaceOriginBuilder :31-40,
 // PhasorBuilder :42-49, EmitSurface::getPhononTime surface.cpp:67-69, Triangle::getRandPoint
 // geometry.cpp:234-242, Line::getRandPoint :140-143).
-// `j` is the phonon's index within its source.  Birth times are STRATIFIED over the emission window,
-//   t = start + duration * (j + u) / count,
-// which has the same expectation as the reference's independent uniform draws (lower variance) and makes
-// "the phonons born in measurement step k" a contiguous index range - no sort, no birth-time array.
-// `step` is the measurement step the host assigned this index to; returns the time left in that interval.
+// `j` is the phonon's index within its source.  Birth times are STRATIFIED BY MEASUREMENT STEP: the host deals
+// a source's `count` phonons over the steps of its emission window in proportion to the time each step overlaps
+// the window (flatten.cpp:plan_births, J(k) = ceil(count * (k dt - start) / duration)), and a phonon is born
+// uniformly inside its step.  Same expectation as the reference's independent uniform draws over the window
+// (EmitSurface::getPhononTime), lower variance, and "the phonons born in step k" is a contiguous index range:
+// no sort, no birth-time array.  Returns the time left in the birth interval.
 // ---------------------------------------------------------------------------------------------------------
 PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j, uint32_t step, Phonon& p) {
     const uint64_t id = src.first_id + j;
@@ -261,10 +262,12 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     const DevEmitter em = P.emitters[src.index];
     p.cell = em.cell;
     const DevCell c = load_cell(P.cells, p.cell);
-    const double t_birth = em.start + em.duration * ((static_cast<double>(j) + static_cast<double>(rng.u01())) /
-                                                     static_cast<double>(src.count));
-    double frac = t_birth / P.step_time_d - static_cast<double>(step);
+    // birth time: uniform over the part of measurement step `step` that lies inside the emission window
+    const double step_lo = static_cast<double>(step) * P.step_time_d;
+    const double lo = fmax(em.start - step_lo, 0.), hi = fmin(em.start + em.duration - step_lo, P.step_time_d);
+    double frac = (lo + (hi - lo) * static_cast<double>(rng.u01())) / P.step_time_d;
     frac = frac < 0. ? 0. : (frac > 0.999999 ? 0.999999 : frac);
+    (void)j;
     sample_table(P, em.table, c.sensor_mat & 0xFFu, rng, p, vel);
     const float u = rng.u01();
     place_on_edge(em.edge, clamp01(em.s_p1 * u + em.s_p2 * (1.f - u)), p);

@@ -296,8 +296,9 @@ int plan_births(const HostImage& img, const psim_source* sources, size_t n, uint
                 err = "surface source with phonons but an empty emission window";
                 return PSIM_E_INVALID;
             }
-            // phonon j is born at start + duration * (j + u) / count; it is assigned to the step that contains
-            // the START of its stratum, so J(k) = first j with start + duration * j / count >= k * dt
+            // the source's phonons are dealt over the measurement steps in proportion to the time each step
+            // overlaps the emission window: indices [J(k), J(k+1)) are born (uniformly) inside step k, with
+            // J(k) = ceil(count * (k * dt - start) / duration) clamped to [0, count]
             const double cnt = static_cast<double>(s.count);
             auto J = [&](uint32_t k) -> uint64_t {
                 const double x = (static_cast<double>(k) * dt - em.start) / em.duration * cnt;
