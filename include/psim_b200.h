@@ -169,7 +169,9 @@ int psim_gpu_cell_histogram(psim_gpu* h, uint64_t* per_cell /* [num_cells] */);
 int psim_gpu_get_stats(psim_gpu* h, psim_stats* out);
 
 /* Tunables: "steps_per_launch" (measurement intervals advanced per pass over the pool, default 1),
- * "warps_per_sm" (0 = occupancy-derived), "tally_shared" (0/1, default auto), "tally_aggregate" (0/1). */
+ * "warps_per_sm" (0 = occupancy-derived), "blocks_per_sm" (2..4: register budget the kernel is compiled for),
+ * "kernel" (0 lane-refill, 1 lock-step first version), "tally_shared" (0/1, default auto),
+ * "tally_aggregate" (0/1, lock-step kernel only: warp match/reduce before the shared-memory atomics). */
 int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value);
 
 /* Replaces ModelSimulator::reset (modelSimulator.h:20-23) + Sensor::reset (sensor.cpp:54-60). */
@@ -178,9 +180,11 @@ void psim_gpu_destroy(psim_gpu* h);
 const char* psim_gpu_last_error(const psim_gpu* h); /* h may be NULL: error of the last failed create */
 
 /* Per-function probes used by the parity tests: run the device implementation of one reference function
- * on caller-supplied inputs.  out_bin/out_ta: Material::freqIndex (material.cpp:64-75) for uniforms u1,u2. */
+ * on caller-supplied inputs.  out_bin/out_ta: Material::freqIndex (material.cpp:64-75) for uniforms u1,u2 as
+ * the flight loop computes it (guided search); out_bin_bisect: the reference's plain bisection on the same
+ * fp32 table - the two must be identical. */
 int psim_gpu_probe_sample(psim_gpu* h, uint32_t table, const float* u1, const float* u2, size_t n,
-                          uint32_t* out_bin, uint32_t* out_ta);
+                          uint32_t* out_bin, uint32_t* out_ta, uint32_t* out_bin_bisect);
 /* rates: [n][3] = (N, U, I) in 1/s for sensor `sensor` (Material::relaxRates, material.cpp:54-57). */
 int psim_gpu_probe_rates(psim_gpu* h, uint32_t sensor, const double* omega, const uint32_t* ta, size_t n,
                          double* rates);

@@ -31,15 +31,12 @@ PSIM_HD float f_sqrt(float x) { return sqrtf(x); }
 PSIM_HD float f_div(float a, float b) { return __fdividef(a, b); }
 PSIM_HD float f_inf() { return __int_as_float(0x7f800000); }
 template<typename T> PSIM_HD T ldg(const T* p) { return __ldg(p); }
-PSIM_HD DevCell load_cell(const DevCell* cells, uint32_t i) {
-    const float4* q = reinterpret_cast<const float4*>(cells + i);
-    union { float4 v[4]; DevCell c; } u;
-    u.v[0] = __ldg(q);
-    u.v[1] = __ldg(q + 1);
-    u.v[2] = __ldg(q + 2);
-    u.v[3] = __ldg(q + 3);
-    return u.c;
+PSIM_HD float4 load_cell_matrix(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const float4*>(cells + i)); }
+PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint4*>(cells + i) + 1); }
+PSIM_HD float2 load_cell_normal(const DevCell* cells, uint32_t i, uint32_t e) {
+    return __ldg(reinterpret_cast<const float2*>(cells + i) + 4 + e);
 }
+PSIM_HD float load_cell_spec(const DevCell* cells, uint32_t i) { return __ldg(&cells[i].spec); }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) {
     const float4* q = reinterpret_cast<const float4*>(sensors + i);
     union { float4 v[2]; DevSensor s; } u;
@@ -56,65 +53,82 @@ PSIM_HD float f_sqrt(float x) { return std::sqrt(x); }
 PSIM_HD float f_div(float a, float b) { return a / b; }
 PSIM_HD float f_inf() { return INFINITY; }
 template<typename T> PSIM_HD T ldg(const T* p) { return *p; }
-PSIM_HD DevCell load_cell(const DevCell* cells, uint32_t i) { return cells[i]; }
+PSIM_HD float4 load_cell_matrix(const DevCell* cells, uint32_t i) {
+    float4 m;
+    m.x = cells[i].m00, m.y = cells[i].m01, m.z = cells[i].m10, m.w = cells[i].m11;
+    return m;
+}
+PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) {
+    uint4 q;
+    q.x = cells[i].link[0], q.y = cells[i].link[1], q.z = cells[i].link[2], q.w = cells[i].sensor_mat;
+    return q;
+}
+PSIM_HD float2 load_cell_normal(const DevCell* cells, uint32_t i, uint32_t e) {
+    float2 n;
+    n.x = cells[i].n[e][0], n.y = cells[i].n[e][1];
+    return n;
+}
+PSIM_HD float load_cell_spec(const DevCell* cells, uint32_t i) { return cells[i].spec; }
+PSIM_HD uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) { return sensors[i]; }
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Replaces the reference's thread_local mt19937 seeded from
-// std::random_device (utils.h:16-21).  key = seed, counter = (block, step, id_lo, id_hi).
+// std::random_device (utils.h:16-21).  key = seed, counter = (block, step, id_lo, id_hi): the stream of a phonon
+// in a measurement step is addressed by its global id and the step, so it does not matter which lane produces it.
+// A refill yields four 32-bit words; code that consumes randoms asks for what it needs at ONE place per code
+// block (rng_need) so that the 10-round function is instantiated a handful of times, not once per draw.
 // ---------------------------------------------------------------------------------------------------------
 struct Rng {
-    uint32_t k0, k1;
-    uint32_t step, id_lo, id_hi;
-    uint32_t block;        // next 4-word block of this (id, step) stream
+    uint32_t block;  // next 4-word block of this (id, step) stream
+    uint32_t left;   // unread words among v0..v3
     uint32_t v0, v1, v2, v3;
-    uint32_t left;         // unread words among v0..v3
+};
 
-    PSIM_HD void init(uint32_t seed_lo, uint32_t seed_hi, uint32_t step_, uint32_t id_lo_, uint32_t id_hi_) {
-        k0 = seed_lo;
-        k1 = seed_hi;
-        step = step_;
-        id_lo = id_lo_;
-        id_hi = id_hi_;
-        block = 0;
-        left = 0;
-        v0 = v1 = v2 = v3 = 0;
-    }
-    PSIM_HD void refill() {
-        uint32_t c0 = block++, c1 = step, c2 = id_lo, c3 = id_hi;
-        uint32_t a = k0, b = k1;
+PSIM_HD void rng_begin(Rng& r) {
+    r.block = 0;
+    r.left = 0;
+    r.v0 = r.v1 = r.v2 = r.v3 = 0;
+}
+
+PSIM_HD void rng_refill(Rng& r, const DevParams& P, uint32_t step, uint32_t id_lo, uint32_t id_hi) {
+    uint32_t c0 = r.block++, c1 = step, c2 = id_lo, c3 = id_hi;
+    uint32_t a = P.seed_lo, b = P.seed_hi;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int r = 0; r < 10; ++r) {
-            const uint32_t hi0 = mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            const uint32_t hi1 = mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            c0 = hi1 ^ c1 ^ a;
-            c1 = lo1;
-            c2 = hi0 ^ c3 ^ b;
-            c3 = lo0;
-            a += 0x9E3779B9u;
-            b += 0xBB67AE85u;
-        }
-        v0 = c0;
-        v1 = c1;
-        v2 = c2;
-        v3 = c3;
-        left = 4;
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ a;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ b;
+        c3 = lo0;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
     }
-    PSIM_HD uint32_t next() {
-        if (left == 0) { refill(); }
-        const uint32_t r = v0;
-        v0 = v1;
-        v1 = v2;
-        v2 = v3;
-        --left;
-        return r;
-    }
-    // uniform on (0, 1] with 24 random bits (the reference draws doubles on [0, 1], utils.h:19)
-    PSIM_HD float u01() { return static_cast<float>((next() >> 8) + 1u) * 5.9604644775390625e-8f; }
-};
+    r.v0 = c0;
+    r.v1 = c1;
+    r.v2 = c2;
+    r.v3 = c3;
+    r.left = 4;
+}
+
+// at least n (<= 4) unread words; leftovers of the previous block are dropped
+PSIM_HD void rng_need(Rng& r, uint32_t n, const DevParams& P, uint32_t step, uint32_t id_lo, uint32_t id_hi) {
+    if (r.left < n) { rng_refill(r, P, step, id_lo, id_hi); }
+}
+
+// uniform on (0, 1] with 24 random bits (the reference draws doubles on [0, 1], utils.h:19); needs left > 0
+PSIM_HD float rng_u01(Rng& r) {
+    const uint32_t x = r.v0;
+    r.v0 = r.v1;
+    r.v1 = r.v2;
+    r.v2 = r.v3;
+    --r.left;
+    return static_cast<float>((x >> 8) + 1u) * 5.9604644775390625e-8f;
+}
 
 struct Phonon {
     float b1, b2;     // position in the current cell's frame
@@ -128,10 +142,12 @@ struct Phonon {
 // ---------------------------------------------------------------------------------------------------------
 // Frequency / polarisation sampling  (Material::freqIndex material.cpp:64-75, getFreq :77-80, getVel :82-84,
 // called from SensorController::initialUpdate / scatterUpdate, sensorController.cpp:28-36,52-55).
-// Same bisection as the reference, so the same quirk: it returns `high`, i.e. bin 0 is never produced.
+// Same inverse-CDF bisection as the reference, hence the same quirk: it returns `high`, i.e. bin 0 is never
+// produced.  bisect_table is the reference's loop verbatim in structure; sample_bin brackets the answer with a
+// 256-entry guide first (flatten.cpp builds it with bisect_table), then bisects inside the bracket: for a
+// non-decreasing table both return the unique h with cdf[h-1] <= r < cdf[h], so the results are identical.
 // ---------------------------------------------------------------------------------------------------------
-PSIM_HD uint32_t bisect_table(const float2* table, float r) {
-    uint32_t lo = 0, hi = PSIM_BINS - 1;
+PSIM_HD uint32_t bisect_range(const float2* table, float r, uint32_t lo, uint32_t hi) {
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (r < ldg(&table[mid].x)) {
@@ -143,13 +159,23 @@ PSIM_HD uint32_t bisect_table(const float2* table, float r) {
     return hi;
 }
 
-PSIM_HD void sample_table(const DevParams& P, uint32_t table_idx, uint32_t mat, Rng& rng, Phonon& p, float& vel) {
+PSIM_HD uint32_t bisect_table(const float2* table, float r) { return bisect_range(table, r, 0u, PSIM_BINS - 1u); }
+
+PSIM_HD uint32_t sample_bin(const DevParams& P, uint32_t table_idx, float r) {
     const float2* table = P.tables + static_cast<size_t>(table_idx) * PSIM_BINS;
-    const uint32_t bin = bisect_table(table, rng.u01());
-    const uint32_t ta = (rng.u01() <= ldg(&table[bin].y)) ? 0u : 1u;
+    const uint32_t k = min(static_cast<uint32_t>(r * static_cast<float>(PSIM_GUIDE)), static_cast<uint32_t>(PSIM_GUIDE - 1));
+    const uint32_t g = ldg(&P.guides[static_cast<size_t>(table_idx) * PSIM_GUIDE + k]);  // [15:0] low bracket, [31:16] high bracket
+    return bisect_range(table, r, g & 0xFFFFu, g >> 16);
+}
+
+// consumes 2 uniforms (3 in deviational mode): bin, polarisation, (frequency jitter)
+PSIM_HD void sample_table(const DevParams& P, uint32_t table_idx, uint32_t mat, float u_bin, float u_pol, float u_jit,
+                          Phonon& p, float& vel) {
+    const uint32_t bin = sample_bin(P, table_idx, u_bin);
+    const uint32_t ta = (u_pol <= ldg(&P.tables[static_cast<size_t>(table_idx) * PSIM_BINS + bin].y)) ? 0u : 1u;
     const float fw = ldg(&P.materials[mat].freq_width);
     float w = (2.f * static_cast<float>(bin) + 1.f) * 0.5f * fw;
-    if (!P.full_mode) { w += (2.f * rng.u01() - 1.f) * 0.5f * fw; }
+    if (!P.full_mode) { w += (2.f * u_jit - 1.f) * 0.5f * fw; }
     p.w = w;
     p.packed = (p.packed & 0xFFFF0800u) | bin | (ta << 10) | (mat << 12);
     vel = ldg(&P.velocities[(mat * 2u + ta) * PSIM_BINS + bin]);
@@ -178,29 +204,29 @@ PSIM_HD void relax_rates(const DevSensor& s, float w, uint32_t ta, float& rn, fl
 }
 
 // Phonon::setRandDirection (phonon.cpp:28-31)
-PSIM_HD void isotropic_direction(Rng& rng, Phonon& p) {
-    const float dx = 2.f * rng.u01() - 1.f;
+PSIM_HD void isotropic_direction(float u1, float u2, Phonon& p) {
+    const float dx = 2.f * u1 - 1.f;
     p.dx = dx;
-    p.dy = f_sqrt(fmaxf(1.f - dx * dx, 0.f)) * f_cos2pi(rng.u01());
+    p.dy = f_sqrt(fmaxf(1.f - dx * dx, 0.f)) * f_cos2pi(u2);
 }
 
 // Surface::redirectPhonon (surface.cpp:23-30): cosine-law direction about the inward normal n
-PSIM_HD void diffuse_direction(Rng& rng, float nx, float ny, Phonon& p) {
-    const float r = rng.u01();
-    const float a = f_sqrt(r);
-    const float b = f_sqrt(fmaxf(1.f - r, 0.f)) * f_cos2pi(rng.u01());
+PSIM_HD void diffuse_direction(float u1, float u2, float nx, float ny, Phonon& p) {
+    const float a = f_sqrt(u1);
+    const float b = f_sqrt(fmaxf(1.f - u1, 0.f)) * f_cos2pi(u2);
     p.dx = nx * a - ny * b;
     p.dy = ny * a + nx * b;
 }
 
-// Surface::boundaryHandlePhonon (surface.cpp:32-44)
+// Surface::boundaryHandlePhonon (surface.cpp:32-44); needs up to 3 unread random words
 PSIM_HD void boundary_reflect(Rng& rng, float spec, float nx, float ny, Phonon& p) {
-    if (spec >= 1.f || rng.u01() < spec) {
+    if (spec >= 1.f || rng_u01(rng) < spec) {
         const float dn = p.dx * nx + p.dy * ny;
         p.dx -= 2.f * dn * nx;
         p.dy -= 2.f * dn * ny;
     } else {
-        diffuse_direction(rng, nx, ny, p);
+        const float u1 = rng_u01(rng), u2 = rng_u01(rng);
+        diffuse_direction(u1, u2, nx, ny, p);
     }
 }
 
@@ -220,21 +246,16 @@ PSIM_HD void place_on_edge(uint32_t e, float s, Phonon& p) {
     }
 }
 
-PSIM_HD void edge_normal(const DevCell& c, uint32_t e, float& nx, float& ny) {
-    nx = (e == 0u) ? c.n0x : ((e == 1u) ? c.n1x : c.n2x);
-    ny = (e == 0u) ? c.n0y : ((e == 1u) ? c.n1y : c.n2y);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Emission (CellOriginBuilder::operator() phononBuilder.cpp:6-16, SurfaceOriginBuilder :31-40,
 // PhasorBuilder :42-49, EmitSurface::getPhononTime surface.cpp:67-69, Triangle::getRandPoint
 // geometry.cpp:234-242, Line::getRandPoint :140-143).
-// `j` is the phonon's index within its source.  Birth times are STRATIFIED BY MEASUREMENT STEP: the host deals
-// a source's `count` phonons over the steps of its emission window in proportion to the time each step overlaps
-// the window (flatten.cpp:plan_births, J(k) = ceil(count * (k dt - start) / duration)), and a phonon is born
-// uniformly inside its step.  Same expectation as the reference's independent uniform draws over the window
-// (EmitSurface::getPhononTime), lower variance, and "the phonons born in step k" is a contiguous index range:
-// no sort, no birth-time array.  Returns the time left in the birth interval.
+// Birth times are STRATIFIED BY MEASUREMENT STEP: the host deals a source's `count` phonons over the steps of
+// its emission window in proportion to the time each step overlaps the window (flatten.cpp:plan_births,
+// J(k) = ceil(count * (k dt - start) / duration)), and a phonon is born uniformly inside its step.  Same
+// expectation as the reference's independent uniform draws over the window (EmitSurface::getPhononTime), lower
+// variance, and "the phonons born in step k" is a contiguous index range: no sort, no birth-time array.
+// `j` is the phonon's index within its source.  Returns the time left in the birth interval.
 // ---------------------------------------------------------------------------------------------------------
 PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j, uint32_t step, Phonon& p) {
     const uint64_t id = src.first_id + j;
@@ -242,192 +263,246 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     const uint32_t id_hi = static_cast<uint32_t>(id >> 32);
     p.packed = (id_hi << 16) | ((src.sign < 0) ? 0x800u : 0u);
     Rng rng;
-    rng.init(P.seed_lo, P.seed_hi, PSIM_BIRTH_STEP, p.id_lo, id_hi);
+    rng_begin(rng);
+    rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
+    const float u_time = rng_u01(rng), u_bin = rng_u01(rng), u_pol = rng_u01(rng), u_jit = rng_u01(rng);
+    rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
+    const float u_a = rng_u01(rng), u_b = rng_u01(rng), u_c = rng_u01(rng), u_d = rng_u01(rng);
     float vel;
     if (src.kind == 0u) {
         p.cell = src.index;
-        const DevCell c = load_cell(P.cells, p.cell);
-        const DevSensor s = load_sensor(P.sensors, c.sensor_mat >> 8);
-        sample_table(P, s.base_table, c.sensor_mat & 0xFFu, rng, p, vel);
-        float r1 = rng.u01(), r2 = rng.u01();
+        const uint4 info = load_cell_info(P.cells, p.cell);
+        const DevSensor s = load_sensor(P.sensors, info.w >> 8);
+        sample_table(P, s.base_table, info.w & 0xFFu, u_bin, u_pol, u_jit, p, vel);
+        float r1 = u_a, r2 = u_b;
         if (r1 + r2 > 1.f) {
             r1 = 1.f - r1;
             r2 = 1.f - r2;
         }
         p.b1 = r1;
         p.b2 = r2;
-        isotropic_direction(rng, p);
+        isotropic_direction(u_c, u_d, p);
         return P.step_time;  // born at t = 0
     }
     const DevEmitter em = P.emitters[src.index];
     p.cell = em.cell;
-    const DevCell c = load_cell(P.cells, p.cell);
+    const uint4 info = load_cell_info(P.cells, p.cell);
     // birth time: uniform over the part of measurement step `step` that lies inside the emission window
     const double step_lo = static_cast<double>(step) * P.step_time_d;
     const double lo = fmax(em.start - step_lo, 0.), hi = fmin(em.start + em.duration - step_lo, P.step_time_d);
-    double frac = (lo + (hi - lo) * static_cast<double>(rng.u01())) / P.step_time_d;
+    double frac = (lo + (hi - lo) * static_cast<double>(u_time)) / P.step_time_d;
     frac = frac < 0. ? 0. : (frac > 0.999999 ? 0.999999 : frac);
     (void)j;
-    sample_table(P, em.table, c.sensor_mat & 0xFFu, rng, p, vel);
-    const float u = rng.u01();
-    place_on_edge(em.edge, clamp01(em.s_p1 * u + em.s_p2 * (1.f - u)), p);
-    float nx, ny;
-    edge_normal(c, em.edge, nx, ny);
+    sample_table(P, em.table, info.w & 0xFFu, u_bin, u_pol, u_jit, p, vel);
+    place_on_edge(em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
+    const float2 n = load_cell_normal(P.cells, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
         p.w = static_cast<float>(PSIM_FREQ_SCALE);
-        p.packed = (p.packed & 0xFFFF0800u) | 1u | ((c.sensor_mat & 0xFu) << 12);
-        p.dx = nx;
-        p.dy = ny;
+        p.packed = (p.packed & 0xFFFF0800u) | 1u | ((info.w & 0xFu) << 12);
+        p.dx = n.x;
+        p.dy = n.y;
     } else {
-        diffuse_direction(rng, nx, ny, p);
+        diffuse_direction(u_b, u_c, n.x, n.y, p);
     }
     return static_cast<float>((1. - frac) * P.step_time_d);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// One phonon across (the rest of) one measurement interval: free flight, intrinsic scattering, surface
-// interaction, cell transition.  Replaces the body of ModelSimulator::simulatePhonon (modelSimulator.cpp:
-// 139-198) between two measurement events, handleImpacts (:205-225), nextImpact (:87-122), scatter (:124-137),
+// One phonon inside one measurement interval, as a small state machine so that the kernel can keep all 32
+// lanes of a warp busy (a lane that finishes its phonon fetches the next one instead of idling):
+//   interval_begin   rates of the current sensor area, time to the next intrinsic scatter
+//   flight_event     ONE free-flight segment: it ends at an edge (handled here), at the end of the interval
+//                    (EV_END), or at an intrinsic scatter (EV_SCATTER, handled by scatter_event)
+//   scatter_event    the intrinsic scatter itself
+// Together they replace the body of ModelSimulator::simulatePhonon (modelSimulator.cpp:139-198) between two
+// measurement events, handleImpacts (:205-225), nextImpact (:87-122), scatter (:124-137),
 // Cell::handleSurfaceCollision (cell.cpp:103-108), CompositeSurface::handlePhonon (compositeSurface.cpp:47-66),
 // EmitSurface::handlePhonon (surface.cpp:61-65) and TransitionSurface::handlePhonon (surface.cpp:71-109).
 // The time to the next intrinsic scatter is redrawn at the start of every interval instead of being carried
 // in the state: the exponential law is memoryless and the rates are constant inside a sensor area (the
 // reference redraws on every sensor change too, modelSimulator.cpp:192-194).
-// Returns false if the phonon left the system through an absorbing (emitting) surface.
-// `vel` is in/out (group velocity, changes when the phonon is resampled); `sensor_out` = sensor at the end.
 // ---------------------------------------------------------------------------------------------------------
-PSIM_HD bool advance_interval(const DevParams& P, Phonon& p, float t, uint32_t step, float& vel,
-                              uint32_t& sensor_out, uint32_t& events) {
+enum { EV_CONTINUE = 0, EV_END = 1, EV_DEAD = 2, EV_SCATTER = 3 };
+
+struct Flight {
+    float m00, m01, m10, m11;  // barycentric rate matrix of the current cell
+    uint32_t sensor_mat;       // [31:8] sensor, [7:0] material of the current cell
+    float vel;                 // group velocity of the phonon
+    float r1, r2;              // d(b1)/dt, d(b2)/dt
+    float tts;                 // time to the next intrinsic scatter (ns)
+    float t;                   // time left in the measurement interval (ns)
+    uint32_t ncoll;            // impacts since the last scatter / interval start (stuck-phonon guard)
     Rng rng;
-    rng.init(P.seed_lo, P.seed_hi, step, p.id_lo, PSIM_PACK_IDHI(p.packed));
-    DevCell c = load_cell(P.cells, p.cell);
-    DevSensor sen = load_sensor(P.sensors, c.sensor_mat >> 8);
-    uint32_t ta = PSIM_PACK_TA(p.packed);
+};
+
+PSIM_HD void set_cell_matrix(Flight& f, const float4 m) {
+    f.m00 = m.x;
+    f.m01 = m.y;
+    f.m10 = m.z;
+    f.m11 = m.w;
+}
+
+PSIM_HD void update_rates_of_motion(Flight& f, const Phonon& p) {
+    const float vx = p.dx * f.vel, vy = p.dy * f.vel;
+    f.r1 = f.m00 * vx + f.m01 * vy;
+    f.r2 = f.m10 * vx + f.m11 * vy;
+}
+
+PSIM_HD float draw_scatter_time(const DevParams& P, const DevSensor& sen, const Phonon& p, float u) {
     float rn, ru, ri;
-    relax_rates(sen, p.w, ta, rn, ru, ri);
-    float gam = rn + ru + ri;
+    relax_rates(sen, p.w, PSIM_PACK_TA(p.packed), rn, ru, ri);
+    const float gam = rn + ru + ri;
+    return (P.phasor || !(gam > 0.f)) ? f_inf() : f_div(-f_log(u), gam);
+}
+
+PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, float t, uint32_t step) {
+    set_cell_matrix(f, load_cell_matrix(P.cells, p.cell));
+    f.sensor_mat = load_cell_info(P.cells, p.cell).w;
+    f.vel = phonon_velocity(P, p.packed);
+    update_rates_of_motion(f, p);
+    f.t = t;
+    f.ncoll = 0;
+    rng_begin(f.rng);
+    rng_refill(f.rng, P, step, p.id_lo, PSIM_PACK_IDHI(p.packed));
+    f.tts = draw_scatter_time(P, load_sensor(P.sensors, f.sensor_mat >> 8), p, rng_u01(f.rng));
+}
+
+PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     const float inf = f_inf();
-    float tts = (P.phasor || !(gam > 0.f)) ? inf : f_div(-f_log(rng.u01()), gam);
-    float vx = p.dx * vel, vy = p.dy * vel;
-    float r1 = c.m00 * vx + c.m01 * vy;
-    float r2 = c.m10 * vx + c.m11 * vy;
-    uint32_t ncoll = 0;
+    const float dt = fminf(f.tts, f.t);
+    const float t0 = (f.r2 < 0.f) ? f_div(-p.b2, f.r2) : inf;
+    const float t2 = (f.r1 < 0.f) ? f_div(-p.b1, f.r1) : inf;
+    const float rs = f.r1 + f.r2;
+    const float t1 = (rs > 0.f) ? f_div(1.f - p.b1 - p.b2, rs) : inf;
+    float th = fminf(t0, fminf(t1, t2));
+    if (!(th <= dt)) {  // no edge on the way (reference: impact_time <= time, modelSimulator.cpp:111)
+        p.b1 += f.r1 * dt;
+        p.b2 += f.r2 * dt;
+        if (!(f.tts < f.t)) { return EV_END; }  // measurement event (it wins ties, modelSimulator.cpp:182)
+        f.t -= dt;
+        return EV_SCATTER;
+    }
+    const uint32_t e = (th == t0) ? 0u : ((th == t1) ? 1u : 2u);
+    th = fmaxf(th, 0.f);
+    float s;
+    if (e == 0u) {
+        s = clamp01(p.b1 + f.r1 * th);
+    } else if (e == 1u) {
+        s = clamp01(p.b2 + f.r2 * th);
+    } else {
+        s = clamp01(1.f - (p.b2 + f.r2 * th));
+    }
+    place_on_edge(e, s, p);
+    f.t -= th;
+    f.tts -= th;
+    const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
+    rng_need(f.rng, 3u, P, step, p.id_lo, id_hi);  // the one refill site of this block
+    const uint4 info = load_cell_info(P.cells, p.cell);
+    uint32_t link = (e == 0u) ? info.x : ((e == 1u) ? info.y : info.z);
+    float ma = (link & (1u << 27)) ? 1.f : -1.f, mb = (link & (1u << 27)) ? 0.f : 1.f;
+    if (PSIM_LINK_KIND(link) == PSIM_LINK_COMPOSITE) {
+        const uint32_t first = (link >> 7) & 0xFFFFFu, n = link & 0x7Fu;
+        link = 0u;  // boundary unless a sub-surface covers the hit point
+        for (uint32_t i = 0; i < n; ++i) {
+            const float4 q = ldg(reinterpret_cast<const float4*>(P.subs + first + i));
+            if (s >= q.x && s <= q.y) {
+                ma = q.z;
+                mb = q.w;
+                link = ldg(&P.subs[first + i].link);
+                break;
+            }
+        }
+    }
+    const uint32_t kind = PSIM_LINK_KIND(link);
+    if (kind == PSIM_LINK_TRANSITION) {
+        const uint32_t ncell = PSIM_LINK_INDEX(link);
+        const uint32_t nsm = load_cell_info(P.cells, ncell).w;
+        const uint32_t nmat = nsm & 0xFFu;
+        bool pass = true;
+        if (nmat != (f.sensor_mat & 0xFFu)) {  // material interface: no state above the neighbour's cutoff
+            const float wmax = PSIM_PACK_TA(p.packed) ? ldg(&P.materials[nmat].w_max_ta) : ldg(&P.materials[nmat].w_max_la);
+            pass = !(p.w > wmax);
+        }
+        if (pass) {
+            place_on_edge((link >> 28) & 3u, clamp01(ma * s + mb), p);
+            p.cell = ncell;
+            const bool new_sensor = (nsm >> 8) != (f.sensor_mat >> 8);
+            f.sensor_mat = nsm;
+            set_cell_matrix(f, load_cell_matrix(P.cells, ncell));
+            if (new_sensor) {  // the old time-to-scatter is void in the new sensor area (modelSimulator.cpp:167-172,192-194)
+                f.tts = draw_scatter_time(P, load_sensor(P.sensors, nsm >> 8), p, rng_u01(f.rng));
+            }
+        } else {  // back into the same cell, about the true inward normal
+            const float2 n = load_cell_normal(P.cells, p.cell, e);
+            const float u1 = rng_u01(f.rng), u2 = rng_u01(f.rng);
+            diffuse_direction(u1, u2, n.x, n.y, p);
+        }
+    } else {
+        if (kind == PSIM_LINK_EMIT) {
+            const DevEmitter* em = P.emitters + PSIM_LINK_INDEX(link);
+            if (step >= ldg(&em->k_on) && step < ldg(&em->k_off)) { return EV_DEAD; }  // absorbed
+        }  // outside its window an emitting surface is an ordinary wall (surface.cpp:61-65)
+        const float2 n = load_cell_normal(P.cells, p.cell, e);
+        boundary_reflect(f.rng, load_cell_spec(P.cells, p.cell), n.x, n.y, p);
+    }
+    update_rates_of_motion(f, p);
+    if (++f.ncoll > PSIM_MAX_COLLISIONS) {
+        // stuck in a corner: random point of the current cell, and the rest of this free flight is spent
+        // (modelSimulator.cpp:215-218)
+        rng_need(f.rng, 2u, P, step, p.id_lo, id_hi);
+        float q1 = rng_u01(f.rng), q2 = rng_u01(f.rng);
+        if (q1 + q2 > 1.f) {
+            q1 = 1.f - q1;
+            q2 = 1.f - q2;
+        }
+        p.b1 = q1;
+        p.b2 = q2;
+        f.r1 = 0.f;
+        f.r2 = 0.f;
+    }
+    return EV_CONTINUE;
+}
+
+// ModelSimulator::scatter (modelSimulator.cpp:124-137) with the rates of the free flight that just ended,
+// then the rates and the time to scatter of the next one (get_scatter_info, :148-153)
+PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
+    const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
+    const DevSensor sen = load_sensor(P.sensors, f.sensor_mat >> 8);
+    float rn, ru, ri;
+    relax_rates(sen, p.w, PSIM_PACK_TA(p.packed), rn, ru, ri);
+    rng_refill(f.rng, P, step, p.id_lo, id_hi);
+    const float r = rng_u01(f.rng) * (rn + ru + ri);
+    const float u_bin = rng_u01(f.rng), u_pol = rng_u01(f.rng), u_jit = rng_u01(f.rng);
+    rng_refill(f.rng, P, step, p.id_lo, id_hi);
+    const float u_d1 = rng_u01(f.rng), u_d2 = rng_u01(f.rng), u_tts = rng_u01(f.rng);
+    if (r <= rn + ru) {
+        sample_table(P, sen.scatter_table, f.sensor_mat & 0xFFu, u_bin, u_pol, u_jit, p, f.vel);
+        if (r > rn) { isotropic_direction(u_d1, u_d2, p); }  // Umklapp
+    } else if (ri > 0.f) {
+        isotropic_direction(u_d1, u_d2, p);
+    }
+    f.ncoll = 0;
+    f.tts = draw_scatter_time(P, sen, p, u_tts);
+    update_rates_of_motion(f, p);
+}
+
+// One phonon across (the rest of) one measurement interval; false if it was absorbed.  The lock-step form of
+// the three functions above (used by the lock-step kernel variant and by the CPU-side test emulation).
+PSIM_HD bool advance_interval(const DevParams& P, Phonon& p, float t, uint32_t step, uint32_t& sensor_out, uint32_t& events) {
+    Flight f;
+    interval_begin(P, p, f, t, step);
     for (;;) {
         ++events;
-        const float dt = fminf(tts, t);
-        const float t0 = (r2 < 0.f) ? f_div(-p.b2, r2) : inf;
-        const float t2 = (r1 < 0.f) ? f_div(-p.b1, r1) : inf;
-        const float rs = r1 + r2;
-        const float t1 = (rs > 0.f) ? f_div(1.f - p.b1 - p.b2, rs) : inf;
-        float th = fminf(t0, fminf(t1, t2));
-        if (th <= dt) {  // reaches an edge first (reference: impact_time <= time, modelSimulator.cpp:111)
-            const uint32_t e = (th == t0) ? 0u : ((th == t1) ? 1u : 2u);
-            th = fmaxf(th, 0.f);
-            float s;
-            if (e == 0u) {
-                s = clamp01(p.b1 + r1 * th);
-            } else if (e == 1u) {
-                s = clamp01(p.b2 + r2 * th);
-            } else {
-                s = clamp01(1.f - (p.b2 + r2 * th));
-            }
-            place_on_edge(e, s, p);
-            t -= th;
-            tts -= th;
-            uint32_t link = (e == 0u) ? c.link[0] : ((e == 1u) ? c.link[1] : c.link[2]);
-            float ma = (link & (1u << 27)) ? 1.f : -1.f, mb = (link & (1u << 27)) ? 0.f : 1.f;
-            if (PSIM_LINK_KIND(link) == PSIM_LINK_COMPOSITE) {
-                const uint32_t first = (link >> 7) & 0xFFFFFu, n = link & 0x7Fu;
-                link = 0u;  // boundary unless a sub-surface covers the hit point
-                for (uint32_t i = 0; i < n; ++i) {
-                    const float4 q = ldg(reinterpret_cast<const float4*>(P.subs + first + i));
-                    if (s >= q.x && s <= q.y) {
-                        ma = q.z;
-                        mb = q.w;
-                        link = ldg(&P.subs[first + i].link);
-                        break;
-                    }
-                }
-            }
-            const uint32_t kind = PSIM_LINK_KIND(link);
-            float nx, ny;
-            edge_normal(c, e, nx, ny);
-            bool redirected = true;
-            if (kind == PSIM_LINK_TRANSITION) {
-                const uint32_t ncell = PSIM_LINK_INDEX(link);
-                const DevCell nb = load_cell(P.cells, ncell);
-                const uint32_t nmat = nb.sensor_mat & 0xFFu;
-                bool pass = true;
-                if (nmat != (c.sensor_mat & 0xFFu)) {  // material interface: no state above the neighbour's cutoff
-                    const float wmax = ta ? ldg(&P.materials[nmat].w_max_ta) : ldg(&P.materials[nmat].w_max_la);
-                    pass = !(p.w > wmax);
-                }
-                if (pass) {
-                    place_on_edge((link >> 28) & 3u, clamp01(ma * s + mb), p);
-                    p.cell = ncell;
-                    const bool new_sensor = (nb.sensor_mat >> 8) != (c.sensor_mat >> 8);
-                    c = nb;
-                    redirected = false;
-                    if (new_sensor) {  // old time-to-scatter is void in the new sensor area (modelSimulator.cpp:167-172,192-194)
-                        sen = load_sensor(P.sensors, c.sensor_mat >> 8);
-                        relax_rates(sen, p.w, ta, rn, ru, ri);
-                        gam = rn + ru + ri;
-                        tts = (P.phasor || !(gam > 0.f)) ? inf : f_div(-f_log(rng.u01()), gam);
-                    }
-                } else {
-                    diffuse_direction(rng, nx, ny, p);  // back into the same cell, about the true inward normal
-                }
-            } else if (kind == PSIM_LINK_EMIT) {
-                const DevEmitter* em = P.emitters + PSIM_LINK_INDEX(link);
-                if (step >= ldg(&em->k_on) && step < ldg(&em->k_off)) { return false; }  // absorbed
-                boundary_reflect(rng, c.spec, nx, ny, p);  // outside its window it is an ordinary wall
-            } else {
-                boundary_reflect(rng, c.spec, nx, ny, p);
-            }
-            if (redirected) {
-                vx = p.dx * vel;
-                vy = p.dy * vel;
-            }
-            r1 = c.m00 * vx + c.m01 * vy;
-            r2 = c.m10 * vx + c.m11 * vy;
-            if (++ncoll > PSIM_MAX_COLLISIONS) {
-                // stuck in a corner: random point of the current cell, and the rest of this free flight is
-                // spent (modelSimulator.cpp:215-218)
-                float q1 = rng.u01(), q2 = rng.u01();
-                if (q1 + q2 > 1.f) {
-                    q1 = 1.f - q1;
-                    q2 = 1.f - q2;
-                }
-                p.b1 = q1;
-                p.b2 = q2;
-                r1 = 0.f;
-                r2 = 0.f;
-            }
-            continue;
+        const int ev = flight_event(P, p, f, step);
+        if (ev == EV_SCATTER) {
+            scatter_event(P, p, f, step);
+        } else if (ev == EV_END) {
+            break;
+        } else if (ev == EV_DEAD) {
+            return false;
         }
-        p.b1 += r1 * dt;
-        p.b2 += r2 * dt;
-        if (!(tts < t)) { break; }  // measurement event (it wins ties, modelSimulator.cpp:182)
-        t -= dt;
-        ncoll = 0;
-        // intrinsic scatter (ModelSimulator::scatter, modelSimulator.cpp:124-137)
-        const float r = rng.u01() * gam;
-        if (r <= rn + ru) {
-            sample_table(P, sen.scatter_table, c.sensor_mat & 0xFFu, rng, p, vel);
-            ta = PSIM_PACK_TA(p.packed);
-            if (r > rn) { isotropic_direction(rng, p); }  // Umklapp
-        } else if (ri > 0.f) {
-            isotropic_direction(rng, p);
-        }
-        relax_rates(sen, p.w, ta, rn, ru, ri);
-        gam = rn + ru + ri;
-        tts = !(gam > 0.f) ? inf : f_div(-f_log(rng.u01()), gam);
-        vx = p.dx * vel;
-        vy = p.dy * vel;
-        r1 = c.m00 * vx + c.m01 * vy;
-        r2 = c.m10 * vx + c.m11 * vy;
     }
-    sensor_out = c.sensor_mat >> 8;
+    sensor_out = f.sensor_mat >> 8;
     return true;
 }
 

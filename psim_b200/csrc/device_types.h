@@ -19,6 +19,7 @@
 #define PSIM_FLUX_FRAC_BITS 8    // flux tallies are int64 fixed point, 1/256 m/s resolution
 #define PSIM_FREQ_SCALE 1e-13    // angular frequencies are carried as omega * 1e-13 (fp32 range)
 #define PSIM_BIRTH_STEP 0xFFFFFFFFu  // Philox stream selector for the draws made at emission
+#define PSIM_GUIDE 256           // entries of the per-table guide that brackets the inverse-CDF search
 
 // edge link word: [31:30] kind, then payload
 #define PSIM_LINK_BOUNDARY 0u    // payload unused
@@ -34,14 +35,14 @@
 #define PSIM_ALIGN(n) alignas(n)
 #endif
 
-// 64 bytes = four 16-byte loads.
+// 64 bytes, ordered by how often the flight loop needs each 16-byte quad:
+//   quad 0 every interval, quad 1 every interval (sensor_mat) and every impact (links), quads 2-3 only on reflection.
 struct PSIM_ALIGN(16) DevCell {
     float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [P2-P1 | P3-P1])
-    float n0x, n0y, n1x, n1y;  // unit normals of edge 0 and edge 1 pointing INTO the cell (geometry.cpp:97-100)
-    float n2x, n2y;            // same for edge 2
-    float spec;                // specularity of the cell's boundary surfaces, clamped to [0,1] (cell.cpp:115-119)
-    uint32_t sensor_mat;       // [31:8] sensor index, [7:0] material index
     uint32_t link[3];          // what lies behind each edge
+    uint32_t sensor_mat;       // [31:8] sensor index, [7:0] material index
+    float n[3][2];             // unit normals of edges 0..2 pointing INTO the cell (geometry.cpp:97-100)
+    float spec;                // specularity of the cell's boundary surfaces, clamped to [0,1] (cell.cpp:115-119)
     uint32_t pad;
 };
 
@@ -117,6 +118,7 @@ struct DevParams {
     const DevEmitter* emitters;
     const DevSource* sources;
     const float2* tables;      // [n_tables][PSIM_BINS] (cumulative probability, LA fraction)  (material.cpp:170-180)
+    const uint32_t* guides;    // [n_tables][PSIM_GUIDE] search bracket for r in [k/256, (k+1)/256): low | high << 16
     const float* velocities;   // [n_materials][2][PSIM_BINS] group velocity, LA then TA, m/s == nm/ns
     uint32_t n_cells, n_sensors, n_materials, n_tables, n_emitters, n_sources;
     uint32_t num_steps;        // measurement steps M

@@ -66,6 +66,29 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
             out.tables[static_cast<size_t>(t) * PSIM_BINS + i] = e;
         }
     }
+    // guide: for r in [k/256, (k+1)/256) the inverse-CDF answer lies in (low, high]; both ends come from the
+    // reference's own bisection (material.cpp:64-75) evaluated on the fp32 table at the bracket's end points
+    out.guides.resize(static_cast<size_t>(d.num_tables) * PSIM_GUIDE);
+    for (uint32_t t = 0; t < d.num_tables; ++t) {
+        const float2* tab = out.tables.data() + static_cast<size_t>(t) * PSIM_BINS;
+        auto bisect = [&](float r) {
+            uint32_t lo = 0, hi = PSIM_BINS - 1;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (r < tab[mid].x) {
+                    hi = mid;
+                } else {
+                    lo = mid;
+                }
+            }
+            return hi;
+        };
+        for (uint32_t k = 0; k < PSIM_GUIDE; ++k) {
+            const uint32_t low = bisect(static_cast<float>(k) / PSIM_GUIDE) - 1u;
+            const uint32_t high = (k + 1 == PSIM_GUIDE) ? PSIM_BINS - 1u : bisect(static_cast<float>(k + 1) / PSIM_GUIDE);
+            out.guides[static_cast<size_t>(t) * PSIM_GUIDE + k] = low | (high << 16);
+        }
+    }
 
     // sensors: fold temperature powers and unit scalings into the rate coefficients (fp64 here, fp32 on device)
     out.sensors.resize(d.num_sensors);
@@ -153,9 +176,9 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         o.m01 = static_cast<float>(m01);
         o.m10 = static_cast<float>(m10);
         o.m11 = static_cast<float>(m11);
-        unit(m10, m11, o.n0x, o.n0y);                   // edge 0 is b2 = 0: inward = grad b2
-        unit(-(m00 + m10), -(m01 + m11), o.n1x, o.n1y); // edge 1 is b1 + b2 = 1
-        unit(m00, m01, o.n2x, o.n2y);                   // edge 2 is b1 = 0
+        unit(m10, m11, o.n[0][0], o.n[0][1]);                   // edge 0 is b2 = 0: inward = grad b2
+        unit(-(m00 + m10), -(m01 + m11), o.n[1][0], o.n[1][1]); // edge 1 is b1 + b2 = 1
+        unit(m00, m01, o.n[2][0], o.n[2][1]);                   // edge 2 is b1 = 0
         o.spec = static_cast<float>(std::min(1., std::max(0., in.specularity)));
         o.sensor_mat = (in.sensor << 8) | d.sensors[in.sensor].material;
         for (int k = 0; k < 3; ++k) {

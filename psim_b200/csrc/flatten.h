@@ -18,6 +18,7 @@ struct HostImage {
     std::vector<DevMaterial> materials;
     std::vector<DevEmitter> emitters;
     std::vector<float2> tables;      // [n_tables][PSIM_BINS]
+    std::vector<uint32_t> guides;    // [n_tables][PSIM_GUIDE]
     std::vector<float> velocities;   // [n_materials][2][PSIM_BINS]
     std::vector<double> sensor_temperature;
     std::vector<psim_material> material_consts;

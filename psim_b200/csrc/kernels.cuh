@@ -1,0 +1,397 @@
+// sm_100a kernels of the particle loop.  Included by psim_gpu.cu only.
+//
+// drift_kernel          persistent, one pool segment per resident warp, LANE REFILL: the warp walks its segment
+//                       as a stream; a lane whose phonon reached the end of the launch window (or was absorbed)
+//                       immediately fetches the next phonon, so all 32 lanes execute free-flight segments all the
+//                       time instead of waiting for the slowest phonon of a 32-wide tile.  (First version, lock
+//                       step: ncu smsp__thread_inst_executed_per_inst_executed = 9.6 of 32, profiles/r01.)
+//                       Intrinsic scatters - rare (8 % of flight segments) and expensive (two Philox blocks, an
+//                       inverse-CDF search) - are deferred until kScatterBatch lanes of the warp wait for one.
+// drift_kernel_lockstep the first version, kept for A/B measurements and as a cross-check: both kernels must give
+//                       bit-identical tallies because a phonon's random stream is addressed by (id, step).
+#ifndef PSIM_B200_KERNELS_CUH
+#define PSIM_B200_KERNELS_CUH
+
+#include "device_core.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kScatterBatch = 8;
+
+struct LaunchArgs {
+    DevParams P;
+    const float4* in_a;
+    const uint4* in_b;
+    float4* out_a;
+    uint4* out_b;
+    const uint32_t* cnt_in;
+    uint32_t* cnt_out;
+    uint32_t seg_cap;
+    uint32_t n_warps;
+    uint32_t step_begin, step_end;
+    const DevBirth* births;        // (step, source) groups of this launch
+    const uint64_t* birth_prefix;  // n_birth_entries + 1 running counts (absolute; birth_base = value at [0])
+    uint32_t n_birth_entries;
+    uint32_t birth_warp_offset;
+    uint64_t birth_base;
+    uint64_t n_births;
+    int32_t* tally_e;
+    long long* tally_f;
+    uint32_t tally_shared;
+    uint32_t tally_aggregate;
+    unsigned long long* stats;       // [0] drift steps [1] flight segments [2] absorbed [3] overflow
+    unsigned long long* alive_hist;  // [launch]: pool population after this launch
+    uint32_t launch_index;
+};
+
+__device__ __forceinline__ size_t tally_smem_offset_f(uint32_t nst, uint32_t S) {
+    return (static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15);
+}
+
+__device__ __forceinline__ void atomic_add_i64(long long* p, long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+}
+
+// Sensor::updateHeatParams (sensor.cpp:43-52): energy += sign, flux += sign * v.  Block stage in shared memory
+// (flushed with one global atomic per touched (sensor, step) at the end of the kernel) or straight to global.
+__device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t local_row,
+                                          uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
+    const uint32_t S = a.P.n_sensors;
+    if (a.tally_shared) {
+        const uint32_t k = local_row * S + sensor;
+        atomicAdd(&acc_e[k], e);
+        atomic_add_i64(&acc_f[2 * k], fx);
+        atomic_add_i64(&acc_f[2 * k + 1], fy);
+    } else {
+        const size_t k = static_cast<size_t>(a.step_begin + local_row + 1 - a.P.first_tally_step) * S + sensor;
+        atomicAdd(&a.tally_e[k], e);
+        atomic_add_i64(&a.tally_f[2 * k], fx);
+        atomic_add_i64(&a.tally_f[2 * k + 1], fy);
+    }
+}
+
+__device__ __forceinline__ void tally_init(const LaunchArgs& a, int32_t* acc_e, long long* acc_f) {
+    if (!a.tally_shared) { return; }
+    const uint32_t n = (a.step_end - a.step_begin) * a.P.n_sensors;
+    for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
+        acc_e[i] = 0;
+        acc_f[2 * i] = 0;
+        acc_f[2 * i + 1] = 0;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void tally_flush(const LaunchArgs& a, const int32_t* acc_e, const long long* acc_f) {
+    if (!a.tally_shared) { return; }
+    __syncthreads();
+    const uint32_t S = a.P.n_sensors, n = (a.step_end - a.step_begin) * S;
+    for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
+        const uint32_t row = a.step_begin + i / S + 1;
+        if (row < a.P.first_tally_step) { continue; }
+        const size_t k = static_cast<size_t>(row - a.P.first_tally_step) * S + (i % S);
+        const int32_t e = acc_e[i];
+        const long long fx = acc_f[2 * i], fy = acc_f[2 * i + 1];
+        if (e) { atomicAdd(&a.tally_e[k], e); }
+        if (fx) { atomic_add_i64(&a.tally_f[2 * k], fx); }
+        if (fy) { atomic_add_i64(&a.tally_f[2 * k + 1], fy); }
+    }
+}
+
+__device__ __forceinline__ void load_phonon(const LaunchArgs& a, size_t i, psim::Phonon& p) {
+    const float4 va = __ldcs(a.in_a + i);  // streamed once: evict-first
+    const uint4 vb = __ldcs(a.in_b + i);
+    p.b1 = va.x;
+    p.b2 = va.y;
+    p.dx = va.z;
+    p.dy = va.w;
+    p.w = __uint_as_float(vb.x);
+    p.packed = vb.y;
+    p.cell = vb.z;
+    p.id_lo = vb.w;
+}
+
+__device__ __forceinline__ void store_phonon(const LaunchArgs& a, size_t i, const psim::Phonon& p) {
+    a.out_a[i] = make_float4(p.b1, p.b2, p.dx, p.dy);
+    a.out_b[i] = make_uint4(__float_as_uint(p.w), p.packed, p.cell, p.id_lo);
+}
+
+// emission: which (step, source) group does birth item `item` of this launch belong to, then build the phonon
+__device__ __forceinline__ float birth_phonon(const LaunchArgs& a, uint64_t item, psim::Phonon& p, uint32_t& step) {
+    const uint64_t key = item + a.birth_base;
+    uint32_t lo = 0, hi = a.n_birth_entries;  // prefix[lo] <= key < prefix[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key < __ldg(&a.birth_prefix[mid])) {
+            hi = mid;
+        } else {
+            lo = mid;
+        }
+    }
+    const DevBirth b = a.births[lo];
+    step = b.step;
+    return psim::create_phonon(a.P, a.P.sources[b.source], b.j0 + (key - __ldg(&a.birth_prefix[lo])) * b.stride, b.step, p);
+}
+
+__device__ __forceinline__ void warp_stats(const LaunchArgs& a, uint32_t lane, unsigned long long steps, unsigned long long events,
+                                           unsigned long long absorbed, bool overflow, uint32_t n_out) {
+    for (int o = 16; o > 0; o >>= 1) {
+        steps += __shfl_xor_sync(0xFFFFFFFFu, steps, o);
+        events += __shfl_xor_sync(0xFFFFFFFFu, events, o);
+        absorbed += __shfl_xor_sync(0xFFFFFFFFu, absorbed, o);
+    }
+    const bool any_overflow = __any_sync(0xFFFFFFFFu, overflow);
+    if (lane == 0) {
+        if (steps) { atomicAdd(&a.stats[0], steps); }
+        if (events) { atomicAdd(&a.stats[1], events); }
+        if (absorbed) { atomicAdd(&a.stats[2], absorbed); }
+        if (any_overflow) { atomicAdd(&a.stats[3], 1ull); }
+        if (n_out) { atomicAdd(&a.alive_hist[a.launch_index], static_cast<unsigned long long>(n_out)); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The drift step: emission + free flight / intrinsic scattering / surfaces / cell transitions + tally + compaction.
+// ---------------------------------------------------------------------------------------------------------------
+template<int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_constant__ LaunchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevParams& P = a.P;
+    int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
+    long long* acc_f = reinterpret_cast<long long*>(smem_raw + tally_smem_offset_f(a.step_end - a.step_begin, P.n_sensors));
+    tally_init(a, acc_e, acc_f);
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t W = a.n_warps;
+    const size_t seg = static_cast<size_t>(w) * a.seg_cap;
+    const uint32_t n_in = a.cnt_in[w];
+    // birth chunks (32 consecutive birth items) are dealt round-robin over the warps, starting at a rotating offset
+    const uint64_t n_chunks = (a.n_births + 31u) >> 5;
+    const uint32_t c0 = (w + W - (a.birth_warp_offset % W)) % W;
+    const uint32_t my_chunks = (c0 < n_chunks) ? static_cast<uint32_t>((n_chunks - 1 - c0) / W + 1) : 0u;
+    const uint32_t total = n_in + my_chunks * 32u;
+
+    uint32_t next = 0, n_out = 0;
+    uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
+    bool overflow = false;
+    bool have = false, begin = false, pending = false;
+    uint32_t s = 0;
+    float t_begin = 0.f;
+    psim::Phonon p;
+    psim::Flight f;
+    p.b1 = p.b2 = p.dx = p.dy = p.w = 0.f;
+    p.packed = p.cell = p.id_lo = 0u;
+
+    for (;;) {
+        // ---- acquire: idle lanes take the next items of the warp's stream (pool first, then births)
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have);
+        if (idle != 0u && next < total) {
+            if (!have) {
+                const uint32_t idx = next + __popc(idle & lt_mask);
+                if (idx < n_in) {
+                    load_phonon(a, seg + idx, p);
+                    s = a.step_begin;
+                    t_begin = P.step_time;
+                    have = true;
+                } else if (idx < total) {
+                    const uint32_t b = idx - n_in;
+                    const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
+                    if (item < a.n_births) {
+                        t_begin = birth_phonon(a, item, p, s);
+                        have = true;
+                    }
+                }
+                begin = have;
+                pending = false;
+            }
+            next += __popc(idle);
+        }
+        const unsigned busy = __ballot_sync(0xFFFFFFFFu, have);
+        if (busy == 0u) {
+            if (next >= total) { break; }
+            continue;
+        }
+        // ---- start of a measurement interval (new phonon, or the next interval of the same launch)
+        if (have && begin) {
+            psim::interval_begin(P, p, f, t_begin, s);
+            begin = false;
+        }
+        // ---- one free-flight segment
+        int ev = psim::EV_CONTINUE;
+        if (have && !pending) {
+            ev = psim::flight_event(P, p, f, s);
+            ++n_events;
+            pending = (ev == psim::EV_SCATTER);
+        }
+        // ---- end of interval: measurement (modelSimulator.cpp:182-186), then next interval or write-back
+        bool store = false;
+        if (ev == psim::EV_END) {
+            ++n_steps;
+            if (s + 1 >= P.first_tally_step) {
+                const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
+                tally_add(a, acc_e, acc_f, s - a.step_begin, f.sensor_mat >> 8, sg, psim::flux_fixed(p.dx * f.vel) * sg,
+                          psim::flux_fixed(p.dy * f.vel) * sg);
+            }
+            if (s + 1 < a.step_end) {
+                ++s;
+                t_begin = P.step_time;
+                begin = true;
+            } else {
+                store = true;
+                have = false;
+            }
+        } else if (ev == psim::EV_DEAD) {
+            ++n_steps;
+            ++n_absorbed;
+            have = false;
+        }
+        const unsigned storing = __ballot_sync(0xFFFFFFFFu, store);
+        if (storing != 0u) {
+            if (store) {
+                const uint32_t slot = n_out + __popc(storing & lt_mask);
+                if (slot < a.seg_cap) {
+                    store_phonon(a, seg + slot, p);
+                } else {
+                    overflow = true;
+                }
+            }
+            n_out += __popc(storing);
+        }
+        // ---- deferred intrinsic scatters: run when enough lanes wait, or when nobody else can make progress
+        const unsigned waiting = __ballot_sync(0xFFFFFFFFu, pending);
+        if (waiting != 0u) {
+            const unsigned flying = __ballot_sync(0xFFFFFFFFu, have && !pending);
+            if (__popc(waiting) >= kScatterBatch || (flying == 0u && next >= total)) {
+                if (pending) {
+                    psim::scatter_event(P, p, f, s);
+                    pending = false;
+                }
+            }
+        }
+    }
+    n_out = min(n_out, a.seg_cap);
+    if (lane == 0) { a.cnt_out[w] = n_out; }
+    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
+    tally_flush(a, acc_e, acc_f);
+}
+
+// First version: tiles of 32 phonons in lock step (every lane waits for the slowest phonon of its tile).
+__global__ void __launch_bounds__(kBlock, 2) drift_kernel_lockstep(const __grid_constant__ LaunchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevParams& P = a.P;
+    int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
+    long long* acc_f = reinterpret_cast<long long*>(smem_raw + tally_smem_offset_f(a.step_end - a.step_begin, P.n_sensors));
+    tally_init(a, acc_e, acc_f);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t W = a.n_warps;
+    const size_t seg = static_cast<size_t>(w) * a.seg_cap;
+    const uint32_t n_in = a.cnt_in[w];
+    const uint32_t pool_tiles = (n_in + 31u) >> 5;
+    const uint64_t n_chunks = (a.n_births + 31u) >> 5;
+    uint64_t chunk = (w + W - (a.birth_warp_offset % W)) % W;
+    uint32_t n_out = 0, n_steps = 0, n_events = 0, n_absorbed = 0;
+    bool overflow = false;
+    for (uint32_t tile = 0;; ++tile) {
+        const bool from_pool = tile < pool_tiles;  // warp-uniform
+        if (!from_pool && chunk >= n_chunks) { break; }
+        psim::Phonon p;
+        float t_first = P.step_time;
+        uint32_t start = a.step_begin;
+        bool alive = false;
+        if (from_pool) {
+            const uint32_t idx = tile * 32u + lane;
+            if (idx < n_in) {
+                load_phonon(a, seg + idx, p);
+                alive = true;
+            }
+        } else {
+            const uint64_t item = chunk * 32u + lane;
+            if (item < a.n_births) {
+                t_first = birth_phonon(a, item, p, start);
+                alive = true;
+            }
+            chunk += W;
+        }
+        for (uint32_t s = a.step_begin; s < a.step_end; ++s) {  // warp-uniform trip count
+            const bool act = alive && s >= start;
+            uint32_t sensor = 0;
+            if (act) {
+                alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, sensor, n_events);
+                ++n_steps;
+                if (!alive) { ++n_absorbed; }
+            }
+            if (act && alive && s + 1 >= P.first_tally_step) {
+                const float vel = psim::phonon_velocity(P, p.packed);
+                const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
+                const int32_t fx = psim::flux_fixed(p.dx * vel) * sg;
+                const int32_t fy = psim::flux_fixed(p.dy * vel) * sg;
+                if (a.tally_aggregate) {
+                    // warp-shuffle stage: lanes that hit the same sensor combine before touching memory
+                    const unsigned peers = __match_any_sync(__activemask(), sensor);
+                    const int32_t es = __reduce_add_sync(peers, sg);
+                    const int32_t fxs = __reduce_add_sync(peers, fx);
+                    const int32_t fys = __reduce_add_sync(peers, fy);
+                    if (lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
+                        tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, es, fxs, fys);
+                    }
+                } else {
+                    tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, sg, fx, fy);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, alive);
+        if (alive) {
+            const uint32_t slot = n_out + __popc(m & ((1u << lane) - 1u));
+            if (slot < a.seg_cap) {
+                store_phonon(a, seg + slot, p);
+            } else {
+                overflow = true;
+            }
+        }
+        n_out += __popc(m);
+    }
+    n_out = min(n_out, a.seg_cap);
+    if (lane == 0) { a.cnt_out[w] = n_out; }
+    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
+    tally_flush(a, acc_e, acc_f);
+}
+
+__global__ void cell_histogram_kernel(const uint4* pool_b, const uint32_t* cnt, uint32_t seg_cap, uint32_t n_warps,
+                                      unsigned long long* hist) {
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (w >= n_warps) { return; }
+    const uint32_t n = cnt[w];
+    for (uint32_t i = threadIdx.x & 31u; i < n; i += 32u) {
+        atomicAdd(&hist[pool_b[static_cast<size_t>(w) * seg_cap + i].z], 1ull);
+    }
+}
+
+// per-function probes for the parity tests
+__global__ void probe_sample_kernel(DevParams P, uint32_t table, const float* u1, const float* u2, size_t n,
+                                    uint32_t* out_bin, uint32_t* out_ta, uint32_t* out_bin_plain) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) { return; }
+    const float2* t = P.tables + static_cast<size_t>(table) * PSIM_BINS;
+    const uint32_t bin = psim::sample_bin(P, table, u1[i]);   // guided search, as the flight loop does it
+    out_bin[i] = bin;
+    out_bin_plain[i] = psim::bisect_table(t, u1[i]);          // the reference's plain bisection
+    out_ta[i] = (u2[i] <= t[bin].y) ? 0u : 1u;
+}
+
+__global__ void probe_rates_kernel(DevParams P, uint32_t sensor, const float* w, const uint32_t* ta, size_t n, float* out) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) { return; }
+    const DevSensor s = psim::load_sensor(P.sensors, sensor);
+    float rn, ru, ri;
+    psim::relax_rates(s, w[i], ta[i], rn, ru, ri);
+    out[3 * i] = rn;
+    out[3 * i + 1] = ru;
+    out[3 * i + 2] = ri;
+}
+
+}  // namespace
+#endif

@@ -13,8 +13,8 @@
 // One launch = one pass of the whole pool over `steps_per_launch` measurement intervals (1 by default: 32 B read
 // + 32 B written per phonon per interval = the 64 algorithmic bytes per drift-step of SURVEY.md 8d).
 #include "../../include/psim_b200.h"
-#include "device_core.cuh"
 #include "flatten.h"
+#include "kernels.cuh"
 
 #include <cuda_runtime.h>
 
@@ -25,231 +25,6 @@
 #include <vector>
 
 namespace {
-
-constexpr int kBlock = 256;
-constexpr int kWarpsPerBlock = kBlock / 32;
-
-struct LaunchArgs {
-    DevParams P;
-    const float4* in_a;
-    const uint4* in_b;
-    float4* out_a;
-    uint4* out_b;
-    const uint32_t* cnt_in;
-    uint32_t* cnt_out;
-    uint32_t seg_cap;
-    uint32_t n_warps;
-    uint32_t step_begin, step_end;
-    const DevBirth* births;        // entries of this launch
-    const uint64_t* birth_prefix;  // n_birth_entries + 1 running counts (absolute; subtract birth_base)
-    uint32_t n_birth_entries;
-    uint32_t birth_warp_offset;
-    uint64_t birth_base;
-    uint64_t n_births;
-    int32_t* tally_e;
-    long long* tally_f;
-    uint32_t tally_shared;
-    uint32_t tally_aggregate;
-    unsigned long long* stats;     // [0] drift steps [1] events [2] absorbed [3] overflow
-    unsigned long long* alive_hist;  // [launch]: pool population after this launch
-    uint32_t launch_index;
-};
-
-__device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t local_row,
-                                          uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
-    const uint32_t S = a.P.n_sensors;
-    if (a.tally_shared) {
-        const uint32_t k = local_row * S + sensor;
-        atomicAdd(&acc_e[k], e);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&acc_f[2 * k]), static_cast<unsigned long long>(static_cast<long long>(fx)));
-        atomicAdd(reinterpret_cast<unsigned long long*>(&acc_f[2 * k + 1]), static_cast<unsigned long long>(static_cast<long long>(fy)));
-    } else {
-        const size_t row = static_cast<size_t>(a.step_begin + local_row + 1 - a.P.first_tally_step);
-        const size_t k = row * S + sensor;
-        atomicAdd(&a.tally_e[k], e);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k]), static_cast<unsigned long long>(static_cast<long long>(fx)));
-        atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k + 1]), static_cast<unsigned long long>(static_cast<long long>(fy)));
-    }
-}
-
-// The drift step: emission + free flight / scattering / surfaces / cell transitions + tally + compaction.
-__global__ void __launch_bounds__(kBlock) drift_kernel(const __grid_constant__ LaunchArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const DevParams& P = a.P;
-    const uint32_t S = P.n_sensors;
-    const uint32_t nst = a.step_end - a.step_begin;
-    int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
-    long long* acc_f = reinterpret_cast<long long*>(smem_raw + ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)));
-    if (a.tally_shared) {
-        for (uint32_t i = threadIdx.x; i < nst * S; i += kBlock) {
-            acc_e[i] = 0;
-            acc_f[2 * i] = 0;
-            acc_f[2 * i + 1] = 0;
-        }
-        __syncthreads();
-    }
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const uint32_t W = a.n_warps;
-    const size_t seg = static_cast<size_t>(w) * a.seg_cap;
-    const uint32_t n_in = a.cnt_in[w];
-    const uint32_t pool_tiles = (n_in + 31u) >> 5;
-    const uint64_t n_chunks = (a.n_births + 31u) >> 5;
-    uint64_t chunk = (w + W - (a.birth_warp_offset % W)) % W;  // birth chunks are dealt round-robin over the warps
-    uint32_t n_out = 0;
-    unsigned long long my_steps = 0, my_absorbed = 0;
-    uint32_t my_events = 0;
-    bool overflow = false;
-
-    for (uint32_t tile = 0;; ++tile) {
-        const bool from_pool = tile < pool_tiles;  // warp-uniform
-        if (!from_pool && chunk >= n_chunks) { break; }
-        psim::Phonon p;
-        float t_first = P.step_time;
-        uint32_t start = a.step_begin;
-        bool alive = false;
-        if (from_pool) {
-            const uint32_t idx = tile * 32u + lane;
-            if (idx < n_in) {
-                const float4 va = a.in_a[seg + idx];
-                const uint4 vb = a.in_b[seg + idx];
-                p.b1 = va.x;
-                p.b2 = va.y;
-                p.dx = va.z;
-                p.dy = va.w;
-                p.w = __uint_as_float(vb.x);
-                p.packed = vb.y;
-                p.cell = vb.z;
-                p.id_lo = vb.w;
-                alive = true;
-            }
-        } else {
-            const uint64_t item = chunk * 32u + lane;
-            if (item < a.n_births) {
-                // which (step, source) group does this item belong to?
-                const uint64_t key = item + a.birth_base;
-                uint32_t lo = 0, hi = a.n_birth_entries;  // prefix[lo] <= key < prefix[hi]
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (key < __ldg(&a.birth_prefix[mid])) {
-                        hi = mid;
-                    } else {
-                        lo = mid;
-                    }
-                }
-                const DevBirth b = a.births[lo];
-                const uint64_t j = b.j0 + (key - __ldg(&a.birth_prefix[lo])) * b.stride;
-                start = b.step;
-                t_first = psim::create_phonon(P, P.sources[b.source], j, b.step, p);
-                alive = true;
-            }
-            chunk += W;
-        }
-        float vel = alive ? ((P.phasor) ? 1000.f : psim::phonon_velocity(P, p.packed)) : 0.f;
-        for (uint32_t s = a.step_begin; s < a.step_end; ++s) {  // warp-uniform trip count
-            const bool act = alive && s >= start;
-            uint32_t sensor = 0;
-            if (act) {
-                alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, vel, sensor, my_events);
-                ++my_steps;
-                if (!alive) { ++my_absorbed; }
-            }
-            // measurement event: the phonon now belongs to step s + 1 (modelSimulator.cpp:182-186)
-            if (act && alive && s + 1 >= P.first_tally_step) {
-                const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
-                const int32_t fx = psim::flux_fixed(p.dx * vel) * sg;
-                const int32_t fy = psim::flux_fixed(p.dy * vel) * sg;
-                if (a.tally_aggregate) {
-                    // warp shuffle stage: lanes that hit the same sensor combine before touching memory
-                    const unsigned peers = __match_any_sync(__activemask(), sensor);
-                    const int32_t es = __reduce_add_sync(peers, sg);
-                    const int32_t fxs = __reduce_add_sync(peers, fx);
-                    const int32_t fys = __reduce_add_sync(peers, fy);
-                    if (lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
-                        tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, es, fxs, fys);
-                    }
-                } else {
-                    tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, sg, fx, fy);
-                }
-            }
-        }
-        // compaction: survivors go to consecutive slots of this warp's output segment
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, alive);
-        if (alive) {
-            const uint32_t slot = n_out + __popc(m & ((1u << lane) - 1u));
-            if (slot < a.seg_cap) {
-                a.out_a[seg + slot] = make_float4(p.b1, p.b2, p.dx, p.dy);
-                a.out_b[seg + slot] = make_uint4(__float_as_uint(p.w), p.packed, p.cell, p.id_lo);
-            } else {
-                overflow = true;
-            }
-        }
-        n_out += __popc(m);
-    }
-    if (lane == 0) { a.cnt_out[w] = min(n_out, a.seg_cap); }
-
-    // statistics: one atomic per warp
-    unsigned long long ev = my_events;
-    for (int o = 16; o > 0; o >>= 1) {
-        my_steps += __shfl_xor_sync(0xFFFFFFFFu, my_steps, o);
-        ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o);
-        my_absorbed += __shfl_xor_sync(0xFFFFFFFFu, my_absorbed, o);
-    }
-    const bool any_overflow = __any_sync(0xFFFFFFFFu, overflow);
-    if (lane == 0) {
-        if (my_steps) { atomicAdd(&a.stats[0], my_steps); }
-        if (ev) { atomicAdd(&a.stats[1], ev); }
-        if (my_absorbed) { atomicAdd(&a.stats[2], my_absorbed); }
-        if (any_overflow) { atomicAdd(&a.stats[3], 1ull); }
-        if (n_out) { atomicAdd(&a.alive_hist[a.launch_index], static_cast<unsigned long long>(min(n_out, a.seg_cap))); }
-    }
-
-    // block stage -> one global atomic per (sensor, step) the block touched
-    if (a.tally_shared) {
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nst * S; i += kBlock) {
-            const uint32_t row = a.step_begin + i / S + 1;
-            if (row < P.first_tally_step) { continue; }
-            const size_t k = static_cast<size_t>(row - P.first_tally_step) * S + (i % S);
-            const int32_t e = acc_e[i];
-            const long long fx = acc_f[2 * i], fy = acc_f[2 * i + 1];
-            if (e) { atomicAdd(&a.tally_e[k], e); }
-            if (fx) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k]), static_cast<unsigned long long>(fx)); }
-            if (fy) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.tally_f[2 * k + 1]), static_cast<unsigned long long>(fy)); }
-        }
-    }
-}
-
-__global__ void cell_histogram_kernel(const uint4* pool_b, const uint32_t* cnt, uint32_t seg_cap, uint32_t n_warps,
-                                      unsigned long long* hist) {
-    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (w >= n_warps) { return; }
-    const uint32_t n = cnt[w];
-    for (uint32_t i = threadIdx.x & 31u; i < n; i += 32u) {
-        atomicAdd(&hist[pool_b[static_cast<size_t>(w) * seg_cap + i].z], 1ull);
-    }
-}
-
-__global__ void probe_sample_kernel(DevParams P, uint32_t table, const float* u1, const float* u2, size_t n,
-                                    uint32_t* out_bin, uint32_t* out_ta) {
-    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (i >= n) { return; }
-    const float2* t = P.tables + static_cast<size_t>(table) * PSIM_BINS;
-    const uint32_t bin = psim::bisect_table(t, u1[i]);
-    out_bin[i] = bin;
-    out_ta[i] = (u2[i] <= t[bin].y) ? 0u : 1u;
-}
-
-__global__ void probe_rates_kernel(DevParams P, uint32_t sensor, const float* w, const uint32_t* ta, size_t n, float* out) {
-    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (i >= n) { return; }
-    const DevSensor s = psim::load_sensor(P.sensors, sensor);
-    float rn, ru, ri;
-    psim::relax_rates(s, w[i], ta[i], rn, ru, ri);
-    out[3 * i] = rn;
-    out[3 * i + 1] = ru;
-    out[3 * i + 2] = ri;
-}
 
 thread_local std::string g_create_error;
 
@@ -268,6 +43,7 @@ struct psim_gpu {
     void* d_materials = nullptr;
     void* d_emitters = nullptr;
     void* d_tables = nullptr;
+    void* d_guides = nullptr;
     void* d_velocities = nullptr;
     void* d_sources = nullptr;
     DevBirth* d_births = nullptr;
@@ -293,6 +69,8 @@ struct psim_gpu {
     // options
     int64_t opt_steps_per_launch = 1;
     int64_t opt_warps_per_sm = 0;
+    int64_t opt_blocks_per_sm = 3;   // occupancy target the kernel is compiled for (register budget)
+    int64_t opt_kernel = 0;          // 0: lane-refill kernel, 1: lock-step kernel (first version, for A/B)
     int64_t opt_tally_shared = -1;
     int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
@@ -414,6 +192,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         if (int rc = upload(h, &h->d_emitters, h->img.emitters)) { return rc; }
         if (int rc = upload(h, &h->d_tables, h->img.tables)) { return rc; }
         if (int rc = upload(h, &h->d_velocities, h->img.velocities)) { return rc; }
+        if (int rc = upload(h, &h->d_guides, h->img.guides)) { return rc; }
         h->P = h->img.scalars;
         h->P.cells = static_cast<const DevCell*>(h->d_cells);
         h->P.subs = static_cast<const DevSub*>(h->d_subs);
@@ -422,6 +201,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         h->P.emitters = static_cast<const DevEmitter*>(h->d_emitters);
         h->P.tables = static_cast<const float2*>(h->d_tables);
         h->P.velocities = static_cast<const float*>(h->d_velocities);
+        h->P.guides = static_cast<const uint32_t*>(h->d_guides);
         const size_t n = static_cast<size_t>(h->P.recorded_steps) * h->P.n_sensors;
         PSIM_CUDA(cudaMalloc(&h->tally_e, n * sizeof(int32_t)));
         PSIM_CUDA(cudaMalloc(&h->tally_f, n * 2 * sizeof(long long)));
@@ -430,7 +210,10 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         PSIM_CUDA(cudaEventCreate(&h->ev_begin));
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
@@ -462,8 +245,17 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
 
     // pool geometry: one segment per resident warp
     int blocks_per_sm = 0;
-    PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel, kBlock, 0));
-    if (blocks_per_sm < 1) { blocks_per_sm = 1; }
+    const int target = h->opt_kernel == 1 ? 2 : static_cast<int>(h->opt_blocks_per_sm);
+    if (h->opt_kernel == 1) {
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
+    } else if (target == 4) {
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel<4>, kBlock, 0));
+    } else if (target == 3) {
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel<3>, kBlock, 0));
+    } else {
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel<2>, kBlock, 0));
+    }
+    blocks_per_sm = std::max(1, std::min(blocks_per_sm, target));
     int warps_per_sm = blocks_per_sm * kWarpsPerBlock;
     if (h->opt_warps_per_sm > 0) {
         warps_per_sm = static_cast<int>(std::max<int64_t>(kWarpsPerBlock, h->opt_warps_per_sm / kWarpsPerBlock * kWarpsPerBlock));
@@ -528,7 +320,8 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         a.tally_f = h->tally_f;
         const size_t smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
         const bool tallies_here = s1 + 1 > h->P.first_tally_step;  // any recorded measurement in this launch?
-        bool shared = h->opt_tally_shared < 0 ? (smem <= 32 * 1024) : (h->opt_tally_shared != 0 && smem <= 200 * 1024);
+        const size_t smem_cap = h->opt_kernel == 1 ? 100 * 1024 : h->opt_blocks_per_sm == 4 ? 48 * 1024 : (h->opt_blocks_per_sm == 3 ? 64 * 1024 : 100 * 1024);
+        bool shared = h->opt_tally_shared < 0 ? (smem <= 32 * 1024) : (h->opt_tally_shared != 0 && smem <= smem_cap);
         if (!tallies_here) { shared = false; }
         a.tally_shared = shared ? 1u : 0u;
         a.tally_aggregate = h->opt_tally_aggregate ? 1u : 0u;
@@ -540,7 +333,17 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
             PSIM_CUDA(cudaEventRecord(h->ev_begin, st));
             h->timing_open = true;
         }
-        drift_kernel<<<h->n_warps / kWarpsPerBlock, kBlock, shared ? smem : 0, st>>>(a);
+        const dim3 grid(h->n_warps / kWarpsPerBlock);
+        const size_t dyn = shared ? smem : 0;
+        if (h->opt_kernel == 1) {
+            drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
+        } else if (h->opt_blocks_per_sm == 4) {
+            drift_kernel<4><<<grid, kBlock, dyn, st>>>(a);
+        } else if (h->opt_blocks_per_sm == 3) {
+            drift_kernel<3><<<grid, kBlock, dyn, st>>>(a);
+        } else {
+            drift_kernel<2><<<grid, kBlock, dyn, st>>>(a);
+        }
         PSIM_CUDA(cudaGetLastError());
         h->cur ^= 1;
         ++h->launches;
@@ -679,6 +482,18 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
             return PSIM_E_STATE;
         }
         h->opt_warps_per_sm = value;
+    } else if (k == "kernel") {
+        if (h->have_sources || value < 0 || value > 1) {
+            h->err = "kernel must be 0 (lane refill) or 1 (lock step) and set before set_sources";
+            return PSIM_E_STATE;
+        }
+        h->opt_kernel = value;
+    } else if (k == "blocks_per_sm") {
+        if (h->have_sources || value < 2 || value > 4) {
+            h->err = "blocks_per_sm must be 2, 3 or 4 and set before set_sources";
+            return PSIM_E_STATE;
+        }
+        h->opt_blocks_per_sm = value;
     } else if (k == "tally_shared") {
         h->opt_tally_shared = value;
     } else if (k == "tally_aggregate") {
@@ -711,6 +526,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaFree(h->d_emitters);
     cudaFree(h->d_tables);
     cudaFree(h->d_velocities);
+    cudaFree(h->d_guides);
     cudaFree(h->tally_e);
     cudaFree(h->tally_f);
     cudaFree(h->d_stats);
@@ -724,20 +540,23 @@ void psim_gpu_destroy(psim_gpu* h) {
 const char* psim_gpu_last_error(const psim_gpu* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int psim_gpu_probe_sample(psim_gpu* h, uint32_t table, const float* u1, const float* u2, size_t n, uint32_t* out_bin,
-                          uint32_t* out_ta) {
-    if (!h || !u1 || !u2 || !out_bin || !out_ta || table >= h->P.n_tables) { return PSIM_E_INVALID; }
+                          uint32_t* out_ta, uint32_t* out_bin_bisect) {
+    if (!h || !u1 || !u2 || !out_bin || !out_ta || !out_bin_bisect || table >= h->P.n_tables) { return PSIM_E_INVALID; }
     if (n == 0) { return PSIM_OK; }
     PSIM_CUDA(cudaSetDevice(h->device));
     float *d1 = nullptr, *d2 = nullptr;
-    uint32_t *db = nullptr, *dt = nullptr;
+    uint32_t *db = nullptr, *dt = nullptr, *dp = nullptr;
     PSIM_CUDA(cudaMalloc(&d1, n * 4));
     PSIM_CUDA(cudaMalloc(&d2, n * 4));
+    PSIM_CUDA(cudaMalloc(&dp, n * 4));
     PSIM_CUDA(cudaMalloc(&db, n * 4));
     PSIM_CUDA(cudaMalloc(&dt, n * 4));
     PSIM_CUDA(cudaMemcpy(d1, u1, n * 4, cudaMemcpyHostToDevice));
     PSIM_CUDA(cudaMemcpy(d2, u2, n * 4, cudaMemcpyHostToDevice));
-    probe_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, table, d1, d2, n, db, dt);
+    probe_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, table, d1, d2, n, db, dt, dp);
     PSIM_CUDA(cudaGetLastError());
+    PSIM_CUDA(cudaMemcpy(out_bin_bisect, dp, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dp);
     PSIM_CUDA(cudaMemcpy(out_bin, db, n * 4, cudaMemcpyDeviceToHost));
     PSIM_CUDA(cudaMemcpy(out_ta, dt, n * 4, cudaMemcpyDeviceToHost));
     cudaFree(d1);

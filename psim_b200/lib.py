@@ -110,7 +110,7 @@ SYMBOLS = {
     "psim_gpu_reset": (C.c_int, [_P]),
     "psim_gpu_destroy": (None, [_P]),
     "psim_gpu_last_error": (C.c_char_p, [_P]),
-    "psim_gpu_probe_sample": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P, _P]),
+    "psim_gpu_probe_sample": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P, _P, _P]),
     "psim_gpu_probe_rates": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P]),
     # include/psim_host.h
     "psim_host_last_error": (C.c_char_p, []),
@@ -376,8 +376,9 @@ class GpuSimulator:
         u2 = np.ascontiguousarray(u2, dtype=np.float32)
         b = np.zeros(u1.size, dtype=np.uint32)
         t = np.zeros(u1.size, dtype=np.uint32)
-        self._check(self.lib.psim_gpu_probe_sample(self.handle, table, _ptr(u1), _ptr(u2), u1.size, _ptr(b), _ptr(t)))
-        return b, t
+        plain = np.zeros(u1.size, dtype=np.uint32)
+        self._check(self.lib.psim_gpu_probe_sample(self.handle, table, _ptr(u1), _ptr(u2), u1.size, _ptr(b), _ptr(t), _ptr(plain)))
+        return b, t, plain
 
     def probe_rates(self, sensor: int, omega: np.ndarray, ta: np.ndarray) -> np.ndarray:
         omega = np.ascontiguousarray(omega, dtype=np.float64)

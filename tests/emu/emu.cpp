@@ -32,6 +32,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     P.emitters = img.emitters.data();
     P.tables = img.tables.data();
     P.velocities = img.velocities.data();
+    P.guides = img.guides.data();
     P.sources = plan.sources.data();
     P.n_sources = static_cast<uint32_t>(n_sources);
     P.seed_lo = static_cast<uint32_t>(seed);
@@ -44,12 +45,12 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     uint64_t total_events = 0;
     const uint32_t B = steps_per_pass ? steps_per_pass : 1;
     auto run_one = [&](psim::Phonon p, uint32_t start, float t_first, uint32_t s0, uint32_t s1) {
-        float vel = P.phasor ? 1000.f : psim::phonon_velocity(P, p.packed);
         bool alive = true;
         for (uint32_t s = start; s < s1 && alive; ++s) {
             uint32_t sensor = 0;
             n_events = 0;
-            alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, vel, sensor, n_events);
+            alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, sensor, n_events);
+            const float vel = psim::phonon_velocity(P, p.packed);
             total_events += n_events;
             ++n_steps;
             if (alive && s + 1 >= P.first_tally_step) {

@@ -63,14 +63,79 @@ def test_steps_per_launch_does_not_change_results(name):
         assert np.array_equal(got["fixed"], ref["fixed"])
 
 
-def test_tally_paths_agree():
+def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
+    """Lane-refill kernel (default) vs the lock-step first version, shared-memory vs global tallies, warp
+    aggregation on/off, different register budgets: a phonon's random stream is addressed by (id, step), so every
+    variant must produce the same integers."""
     model = T.load_model(T.case_model("sides_per"), num_phonons=50_000)
-    ref = gpu_run_case(model, 5, options={"tally_shared": 0, "tally_aggregate": 0}, finish=False)
-    for opts in ({"tally_shared": 1, "tally_aggregate": 0}, {"tally_shared": 1, "tally_aggregate": 1},
-                 {"tally_shared": 0, "tally_aggregate": 1}):
+    ref = gpu_run_case(model, 5, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
+    for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 1, "tally_shared": 1, "tally_aggregate": 1},
+                 {"kernel": 1, "tally_shared": 0, "tally_aggregate": 1}, {"kernel": 0, "tally_shared": 1},
+                 {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "blocks_per_sm": 2}, {"kernel": 0, "blocks_per_sm": 4}):
         got = gpu_run_case(model, 5, options=opts, finish=False)
         assert np.array_equal(got["energy"], ref["energy"]), opts
         assert np.array_equal(got["fixed"], ref["fixed"]), opts
+        assert got["stats"][0]["drift_steps"] == ref["stats"][0]["drift_steps"], opts
+        assert got["stats"][0]["events"] == ref["stats"][0]["events"], opts
+
+
+def test_device_sampling_matches_reference_bisection():
+    """Material::freqIndex (material.cpp:64-75): the guided search of the flight loop, the plain bisection run on
+    the device, and the same bisection run here in numpy on the fp32 table must give identical bins."""
+    from psim_b200 import lib as psim
+    model = T.load_model(T.case_model("sige"))
+    model.prepare()
+    desc = model.describe()
+    g = psim.GpuSimulator(desc, 0)
+    rng = np.random.default_rng(0)
+    u1 = np.concatenate([rng.random(200_000, dtype=np.float32), np.array([1.0, 2.0 ** -24, 0.5, 0.999999], dtype=np.float32)])
+    u2 = rng.random(u1.size, dtype=np.float32)
+    d = desc.contents
+    for table in range(d.num_tables):
+        cum = np.ctypeslib.as_array(d.tables[table].cumulative, shape=(1000,)).astype(np.float32)
+        la = np.ctypeslib.as_array(d.tables[table].la_fraction, shape=(1000,)).astype(np.float32)
+        lo = np.zeros(u1.size, dtype=np.int64)
+        hi = np.full(u1.size, 999, dtype=np.int64)
+        for _ in range(12):
+            mid = (lo + hi) // 2
+            active = hi - lo > 1
+            take_hi = active & (u1 < cum[mid])
+            hi = np.where(take_hi, mid, hi)
+            lo = np.where(active & ~take_hi, mid, lo)
+        b, t, plain = g.probe_sample(table, u1, u2)
+        assert np.array_equal(plain, hi)
+        assert np.array_equal(b, hi)
+        assert np.array_equal(t, (u2 > la[hi]).astype(np.uint32))
+    g.close()
+
+
+def test_device_relaxation_rates_match_reference_formulas():
+    """Material::relaxRates (material.cpp:54-57,207-239) in fp64 vs the device's fp32 evaluation."""
+    from psim_b200 import lib as psim
+    for name in ("sige", "linear_impurity", "linear_full"):
+        model = T.load_model(T.case_model(name))
+        model.prepare()
+        desc = model.describe()
+        d = desc.contents
+        g = psim.GpuSimulator(desc, 0)
+        rng = np.random.default_rng(1)
+        for sensor in (0, d.num_sensors - 1):
+            mat = d.materials[d.sensors[sensor].material]
+            T_s = d.sensors[sensor].temperature
+            omega = rng.uniform(0.01, 1.0, 4000) * max(mat.w_max_la, mat.w_max_ta)
+            ta = (rng.random(4000) < 0.5).astype(np.uint32)
+            got = g.probe_rates(sensor, omega, ta)
+            hbar, kb = 1.054517e-34, 1.38065e-23
+            n = np.where(ta == 0, mat.b_l * omega ** 2 * T_s ** 3, np.where(omega < mat.w, mat.b_tn * omega * T_s ** 4, 0.0))
+            with np.errstate(over="ignore"):
+                u = np.where(ta == 0, mat.b_l * omega ** 2 * T_s ** 3,
+                             np.where(omega >= mat.w, mat.b_tu * omega ** 2 / np.sinh(hbar * omega / (T_s * kb)), 0.0))
+            i = mat.b_i * omega ** 4
+            want = np.stack([n, u, i], axis=1)
+            scale = np.maximum(np.abs(want).max(), 1e-30)
+            # fp32 arithmetic with __expf / __fdividef: 1e-5 relative to the largest rate is ample for a Monte Carlo rate
+            assert np.abs(got - want).max() <= 2e-5 * scale, name
+        g.close()
 
 
 def test_cell_population_matches_emulation():
