@@ -57,6 +57,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: dict) -> str:
+    """Tuning helper: the same library with -D overrides (e.g. scheduler thresholds) under lib/variants/."""
+    out_dir = os.path.join(LIB_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libpsim_b200_{name}.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o", out,
+           *[f"-D{k}={v}" for k, v in defines.items()], *srcs]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build_emu(force: bool = False) -> str:
     """Test-only: the device core compiled for the host (tests/emu). Never loaded by the package."""
     src = os.path.join(ROOT, "tests", "emu", "emu.cpp")

@@ -133,7 +133,8 @@ PSIM_HD float rng_u01(Rng& r) {
 struct Phonon {
     float b1, b2;     // position in the current cell's frame
     float dx, dy;     // direction; in-plane speed = velocity * |d|   (phonon.cpp:28-31)
-    float w;          // angular frequency * 1e-13
+    float tts;        // time to the next intrinsic scatter (ns); carried from interval to interval like the
+                      // reference's time_to_scatter (modelSimulator.cpp:145,155,180)
     uint32_t packed;  // see device_types.h
     uint32_t cell;
     uint32_t id_lo;
@@ -168,16 +169,23 @@ PSIM_HD uint32_t sample_bin(const DevParams& P, uint32_t table_idx, float r) {
     return bisect_range(table, r, g & 0xFFFFu, g >> 16);
 }
 
+// Angular frequency (* 1e-13) of a phonon: bin centre, plus in deviational mode the jitter inside the bin
+// (Material::getFreq, material.cpp:77-80).  The jitter is kept as 8 bits in the packed word, i.e. the
+// reference's uniform draw over the bin is resolved to 1/256 of a bin (0.001 % of the spectrum).
+PSIM_HD float phonon_omega(const DevParams& P, uint32_t packed) {
+    const float fw = ldg(&P.materials[PSIM_PACK_MAT(packed)].freq_width);
+    float w = (2.f * static_cast<float>(PSIM_PACK_BIN(packed)) + 1.f) * 0.5f * fw;
+    if (!P.full_mode) { w += ((2.f * static_cast<float>(PSIM_PACK_JIT(packed)) + 1.f) * (1.f / 256.f) - 1.f) * 0.5f * fw; }
+    return P.phasor ? static_cast<float>(PSIM_FREQ_SCALE) : w;  // PhasorBuilder: freq = 1 rad/s (phononBuilder.cpp:46)
+}
+
 // consumes 2 uniforms (3 in deviational mode): bin, polarisation, (frequency jitter)
 PSIM_HD void sample_table(const DevParams& P, uint32_t table_idx, uint32_t mat, float u_bin, float u_pol, float u_jit,
                           Phonon& p, float& vel) {
     const uint32_t bin = sample_bin(P, table_idx, u_bin);
     const uint32_t ta = (u_pol <= ldg(&P.tables[static_cast<size_t>(table_idx) * PSIM_BINS + bin].y)) ? 0u : 1u;
-    const float fw = ldg(&P.materials[mat].freq_width);
-    float w = (2.f * static_cast<float>(bin) + 1.f) * 0.5f * fw;
-    if (!P.full_mode) { w += (2.f * u_jit - 1.f) * 0.5f * fw; }
-    p.w = w;
-    p.packed = (p.packed & 0xFFFF0800u) | bin | (ta << 10) | (mat << 12);
+    const uint32_t jit = min(static_cast<uint32_t>(u_jit * 256.f), 255u);
+    p.packed = (p.packed & 0xFF000800u) | bin | (ta << 10) | (mat << 12) | (jit << 16);
     vel = ldg(&P.velocities[(mat * 2u + ta) * PSIM_BINS + bin]);
 }
 
@@ -257,11 +265,13 @@ PSIM_HD void place_on_edge(uint32_t e, float s, Phonon& p) {
 // variance, and "the phonons born in step k" is a contiguous index range: no sort, no birth-time array.
 // `j` is the phonon's index within its source.  Returns the time left in the birth interval.
 // ---------------------------------------------------------------------------------------------------------
+PSIM_HD float draw_scatter_time(const DevParams& P, const DevSensor& sen, const Phonon& p, float u);
+
 PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j, uint32_t step, Phonon& p) {
     const uint64_t id = src.first_id + j;
     p.id_lo = static_cast<uint32_t>(id);
     const uint32_t id_hi = static_cast<uint32_t>(id >> 32);
-    p.packed = (id_hi << 16) | ((src.sign < 0) ? 0x800u : 0u);
+    p.packed = (id_hi << 24) | ((src.sign < 0) ? 0x800u : 0u);
     Rng rng;
     rng_begin(rng);
     rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
@@ -282,6 +292,8 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
         p.b1 = r1;
         p.b2 = r2;
         isotropic_direction(u_c, u_d, p);
+        rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
+        p.tts = draw_scatter_time(P, s, p, rng_u01(rng));
         return P.step_time;  // born at t = 0
     }
     const DevEmitter em = P.emitters[src.index];
@@ -297,13 +309,13 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     place_on_edge(em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
     const float2 n = load_cell_normal(P.cells, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
-        p.w = static_cast<float>(PSIM_FREQ_SCALE);
-        p.packed = (p.packed & 0xFFFF0800u) | 1u | ((info.w & 0xFu) << 12);
+        p.packed = (p.packed & 0xFF000800u) | 1u | ((info.w & 0xFu) << 12);
         p.dx = n.x;
         p.dy = n.y;
     } else {
         diffuse_direction(u_b, u_c, n.x, n.y, p);
     }
+    p.tts = draw_scatter_time(P, load_sensor(P.sensors, info.w >> 8), p, u_d);
     return static_cast<float>((1. - frac) * P.step_time_d);
 }
 
@@ -311,27 +323,29 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
 // One phonon inside one measurement interval, as a small state machine so that the kernel can keep all 32
 // lanes of a warp busy (a lane that finishes its phonon fetches the next one instead of idling):
 //   interval_begin   rates of the current sensor area, time to the next intrinsic scatter
-//   flight_event     ONE free-flight segment: it ends at an edge (handled here), at the end of the interval
-//                    (EV_END), or at an intrinsic scatter (EV_SCATTER, handled by scatter_event)
+//   flight_step      ONE free-flight segment: it ends at an edge (EV_IMPACT), at the end of the interval (EV_END)
+//                    or at an intrinsic scatter (EV_SCATTER)
+//   impact_event     what the edge does: reflect, transmit to the neighbour cell, absorb (EV_DEAD)
 //   scatter_event    the intrinsic scatter itself
 // Together they replace the body of ModelSimulator::simulatePhonon (modelSimulator.cpp:139-198) between two
 // measurement events, handleImpacts (:205-225), nextImpact (:87-122), scatter (:124-137),
 // Cell::handleSurfaceCollision (cell.cpp:103-108), CompositeSurface::handlePhonon (compositeSurface.cpp:47-66),
 // EmitSurface::handlePhonon (surface.cpp:61-65) and TransitionSurface::handlePhonon (surface.cpp:71-109).
-// The time to the next intrinsic scatter is redrawn at the start of every interval instead of being carried
-// in the state: the exponential law is memoryless and the rates are constant inside a sensor area (the
-// reference redraws on every sensor change too, modelSimulator.cpp:192-194).
+// The time to the next intrinsic scatter travels with the phonon (state word `tts`), so an interval in which
+// nothing happens costs no random number, no logarithm and no rate evaluation; it is redrawn after a scatter
+// and on every change of sensor area, as in the reference (modelSimulator.cpp:155,192-194).
 // ---------------------------------------------------------------------------------------------------------
-enum { EV_CONTINUE = 0, EV_END = 1, EV_DEAD = 2, EV_SCATTER = 3 };
+enum { EV_CONTINUE = 0, EV_END = 1, EV_DEAD = 2, EV_SCATTER = 3, EV_IMPACT = 4 };
 
 struct Flight {
     float m00, m01, m10, m11;  // barycentric rate matrix of the current cell
     uint32_t sensor_mat;       // [31:8] sensor, [7:0] material of the current cell
     float vel;                 // group velocity of the phonon
     float r1, r2;              // d(b1)/dt, d(b2)/dt
-    float tts;                 // time to the next intrinsic scatter (ns)
     float t;                   // time left in the measurement interval (ns)
     uint32_t ncoll;            // impacts since the last scatter / interval start (stuck-phonon guard)
+    uint32_t edge;             // edge reached by the last flight segment (EV_IMPACT) ...
+    float s_hit;               // ... and where on it, as a fraction from the edge's first vertex
     Rng rng;
 };
 
@@ -350,7 +364,7 @@ PSIM_HD void update_rates_of_motion(Flight& f, const Phonon& p) {
 
 PSIM_HD float draw_scatter_time(const DevParams& P, const DevSensor& sen, const Phonon& p, float u) {
     float rn, ru, ri;
-    relax_rates(sen, p.w, PSIM_PACK_TA(p.packed), rn, ru, ri);
+    relax_rates(sen, phonon_omega(P, p.packed), PSIM_PACK_TA(p.packed), rn, ru, ri);
     const float gam = rn + ru + ri;
     return (P.phasor || !(gam > 0.f)) ? f_inf() : f_div(-f_log(u), gam);
 }
@@ -362,14 +376,13 @@ PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, floa
     update_rates_of_motion(f, p);
     f.t = t;
     f.ncoll = 0;
-    rng_begin(f.rng);
-    rng_refill(f.rng, P, step, p.id_lo, PSIM_PACK_IDHI(p.packed));
-    f.tts = draw_scatter_time(P, load_sensor(P.sensors, f.sensor_mat >> 8), p, rng_u01(f.rng));
+    rng_begin(f.rng);  // the stream of this (phonon, step) starts at block 0; nothing is drawn unless an event needs it
+    (void)step;
 }
 
-PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
+PSIM_HD int flight_step(Phonon& p, Flight& f) {
     const float inf = f_inf();
-    const float dt = fminf(f.tts, f.t);
+    const float dt = fminf(p.tts, f.t);
     const float t0 = (f.r2 < 0.f) ? f_div(-p.b2, f.r2) : inf;
     const float t2 = (f.r1 < 0.f) ? f_div(-p.b1, f.r1) : inf;
     const float rs = f.r1 + f.r2;
@@ -378,7 +391,10 @@ PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     if (!(th <= dt)) {  // no edge on the way (reference: impact_time <= time, modelSimulator.cpp:111)
         p.b1 += f.r1 * dt;
         p.b2 += f.r2 * dt;
-        if (!(f.tts < f.t)) { return EV_END; }  // measurement event (it wins ties, modelSimulator.cpp:182)
+        if (!(p.tts < f.t)) {  // measurement event (it wins ties, modelSimulator.cpp:182)
+            p.tts -= f.t;
+            return EV_END;
+        }
         f.t -= dt;
         return EV_SCATTER;
     }
@@ -394,9 +410,16 @@ PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     }
     place_on_edge(e, s, p);
     f.t -= th;
-    f.tts -= th;
+    p.tts -= th;
+    f.edge = e;
+    f.s_hit = s;
+    return EV_IMPACT;
+}
+
+PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
+    const uint32_t e = f.edge;
+    const float s = f.s_hit;
     const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
-    rng_need(f.rng, 3u, P, step, p.id_lo, id_hi);  // the one refill site of this block
     const uint4 info = load_cell_info(P.cells, p.cell);
     uint32_t link = (e == 0u) ? info.x : ((e == 1u) ? info.y : info.z);
     float ma = (link & (1u << 27)) ? 1.f : -1.f, mb = (link & (1u << 27)) ? 0.f : 1.f;
@@ -414,6 +437,10 @@ PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
         }
     }
     const uint32_t kind = PSIM_LINK_KIND(link);
+    // random words this surface can consume: a transition at most 2 (new time-to-scatter, or a back-scatter
+    // direction), a wall 3 (specular test + diffuse direction) unless it is perfectly specular
+    const float spec = (kind == PSIM_LINK_TRANSITION) ? 0.f : load_cell_spec(P.cells, p.cell);
+    rng_need(f.rng, (kind == PSIM_LINK_TRANSITION) ? 2u : ((spec >= 1.f) ? 0u : 3u), P, step, p.id_lo, id_hi);
     if (kind == PSIM_LINK_TRANSITION) {
         const uint32_t ncell = PSIM_LINK_INDEX(link);
         const uint32_t nsm = load_cell_info(P.cells, ncell).w;
@@ -421,7 +448,7 @@ PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
         bool pass = true;
         if (nmat != (f.sensor_mat & 0xFFu)) {  // material interface: no state above the neighbour's cutoff
             const float wmax = PSIM_PACK_TA(p.packed) ? ldg(&P.materials[nmat].w_max_ta) : ldg(&P.materials[nmat].w_max_la);
-            pass = !(p.w > wmax);
+            pass = !(phonon_omega(P, p.packed) > wmax);
         }
         if (pass) {
             place_on_edge((link >> 28) & 3u, clamp01(ma * s + mb), p);
@@ -430,7 +457,7 @@ PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
             f.sensor_mat = nsm;
             set_cell_matrix(f, load_cell_matrix(P.cells, ncell));
             if (new_sensor) {  // the old time-to-scatter is void in the new sensor area (modelSimulator.cpp:167-172,192-194)
-                f.tts = draw_scatter_time(P, load_sensor(P.sensors, nsm >> 8), p, rng_u01(f.rng));
+                p.tts = draw_scatter_time(P, load_sensor(P.sensors, nsm >> 8), p, rng_u01(f.rng));
             }
         } else {  // back into the same cell, about the true inward normal
             const float2 n = load_cell_normal(P.cells, p.cell, e);
@@ -443,7 +470,7 @@ PSIM_HD int flight_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
             if (step >= ldg(&em->k_on) && step < ldg(&em->k_off)) { return EV_DEAD; }  // absorbed
         }  // outside its window an emitting surface is an ordinary wall (surface.cpp:61-65)
         const float2 n = load_cell_normal(P.cells, p.cell, e);
-        boundary_reflect(f.rng, load_cell_spec(P.cells, p.cell), n.x, n.y, p);
+        boundary_reflect(f.rng, spec, n.x, n.y, p);
     }
     update_rates_of_motion(f, p);
     if (++f.ncoll > PSIM_MAX_COLLISIONS) {
@@ -469,7 +496,7 @@ PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t st
     const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
     const DevSensor sen = load_sensor(P.sensors, f.sensor_mat >> 8);
     float rn, ru, ri;
-    relax_rates(sen, p.w, PSIM_PACK_TA(p.packed), rn, ru, ri);
+    relax_rates(sen, phonon_omega(P, p.packed), PSIM_PACK_TA(p.packed), rn, ru, ri);
     rng_refill(f.rng, P, step, p.id_lo, id_hi);
     const float r = rng_u01(f.rng) * (rn + ru + ri);
     const float u_bin = rng_u01(f.rng), u_pol = rng_u01(f.rng), u_jit = rng_u01(f.rng);
@@ -482,7 +509,7 @@ PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t st
         isotropic_direction(u_d1, u_d2, p);
     }
     f.ncoll = 0;
-    f.tts = draw_scatter_time(P, sen, p, u_tts);
+    p.tts = draw_scatter_time(P, sen, p, u_tts);
     update_rates_of_motion(f, p);
 }
 
@@ -493,13 +520,13 @@ PSIM_HD bool advance_interval(const DevParams& P, Phonon& p, float t, uint32_t s
     interval_begin(P, p, f, t, step);
     for (;;) {
         ++events;
-        const int ev = flight_event(P, p, f, step);
-        if (ev == EV_SCATTER) {
+        const int ev = flight_step(p, f);
+        if (ev == EV_IMPACT) {
+            if (impact_event(P, p, f, step) == EV_DEAD) { return false; }
+        } else if (ev == EV_SCATTER) {
             scatter_event(P, p, f, step);
-        } else if (ev == EV_END) {
+        } else {
             break;
-        } else if (ev == EV_DEAD) {
-            return false;
         }
     }
     sensor_out = f.sensor_mat >> 8;

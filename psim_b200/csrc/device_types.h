@@ -102,13 +102,16 @@ struct DevBirth {
 
 // Phonon state in HBM: two 16-byte words per phonon, structure-of-arrays.
 //   A = (b1, b2, dx, dy)            position in the cell frame, direction (|d| <= 1: 3-D direction projected)
-//   B = (omega, packed, cell, id)   packed = [9:0] bin, [10] polarisation (1 = TA), [11] sign (1 = negative),
-//                                            [15:12] material the (omega, v) pair was sampled in, [31:16] id bits 47:32
+//   B = (tts, packed, cell, id)     tts = time to the next intrinsic scatter (ns)
+//                                   packed = [9:0] bin, [10] polarisation (1 = TA), [11] sign (1 = negative),
+//                                            [15:12] material the (omega, v) pair was sampled in,
+//                                            [23:16] position of omega inside the bin (1/256ths), [31:24] id bits 39:32
 #define PSIM_PACK_BIN(p) ((p)&0x3FFu)
 #define PSIM_PACK_TA(p) (((p) >> 10) & 1u)
 #define PSIM_PACK_NEG(p) (((p) >> 11) & 1u)
 #define PSIM_PACK_MAT(p) (((p) >> 12) & 0xFu)
-#define PSIM_PACK_IDHI(p) ((p) >> 16)
+#define PSIM_PACK_JIT(p) (((p) >> 16) & 0xFFu)
+#define PSIM_PACK_IDHI(p) ((p) >> 24)
 
 struct DevParams {
     const DevCell* cells;

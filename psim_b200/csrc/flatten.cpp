@@ -346,8 +346,8 @@ int plan_births(const HostImage& img, const psim_source* sources, size_t n, uint
         next_id += s.count;
     }
     out.total_phonons = next_id;
-    if (next_id >= (1ull << 48)) {
-        err = "more than 2^48 phonons";
+    if (next_id >= (1ull << 40)) {
+        err = "more than 2^40 phonons";
         return PSIM_E_INVALID;
     }
     std::stable_sort(births.begin(), births.end(), [](const DevBirth& a, const DevBirth& b) { return a.step < b.step; });

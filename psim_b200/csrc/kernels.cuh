@@ -5,8 +5,11 @@
 //                       immediately fetches the next phonon, so all 32 lanes execute free-flight segments all the
 //                       time instead of waiting for the slowest phonon of a 32-wide tile.  (First version, lock
 //                       step: ncu smsp__thread_inst_executed_per_inst_executed = 9.6 of 32, profiles/r01.)
-//                       Intrinsic scatters - rare (8 % of flight segments) and expensive (two Philox blocks, an
-//                       inverse-CDF search) - are deferred until kScatterBatch lanes of the warp wait for one.
+//                       On top of that the warp SCHEDULES its work by kind: each lane records what its phonon
+//                       needs next (start an interval / fly / hit a surface / scatter / finish the interval) and a
+//                       kind of work is executed only when enough lanes wait for it, so that rare, expensive paths
+//                       (intrinsic scatter: two Philox blocks + an inverse-CDF search; surface interaction) run
+//                       with many lanes active instead of one or two.
 // drift_kernel_lockstep the first version, kept for A/B measurements and as a cross-check: both kernels must give
 //                       bit-identical tallies because a phonon's random stream is addressed by (id, step).
 #ifndef PSIM_B200_KERNELS_CUH
@@ -18,7 +21,18 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarpsPerBlock = kBlock / 32;
-constexpr int kScatterBatch = 8;
+// lane states of the drift kernel's scheduler and how many lanes must wait for a kind of work before it runs
+enum : uint32_t { ST_IDLE = 0, ST_BEGIN = 1, ST_FLIGHT = 2, ST_IMPACT = 3, ST_SCATTER = 4, ST_FINISH = 5 };
+#ifndef PSIM_MIN_ACQUIRE
+#define PSIM_MIN_ACQUIRE 8
+#define PSIM_MIN_BEGIN 8
+#define PSIM_MIN_FLIGHT 12
+#define PSIM_MIN_IMPACT 10
+#define PSIM_MIN_SCATTER 8
+#define PSIM_MIN_FINISH 10
+#endif
+constexpr int kMinAcquire = PSIM_MIN_ACQUIRE, kMinBegin = PSIM_MIN_BEGIN, kMinFlight = PSIM_MIN_FLIGHT,
+              kMinImpact = PSIM_MIN_IMPACT, kMinScatter = PSIM_MIN_SCATTER, kMinFinish = PSIM_MIN_FINISH;
 
 struct LaunchArgs {
     DevParams P;
@@ -106,7 +120,7 @@ __device__ __forceinline__ void load_phonon(const LaunchArgs& a, size_t i, psim:
     p.b2 = va.y;
     p.dx = va.z;
     p.dy = va.w;
-    p.w = __uint_as_float(vb.x);
+    p.tts = __uint_as_float(vb.x);
     p.packed = vb.y;
     p.cell = vb.z;
     p.id_lo = vb.w;
@@ -114,7 +128,7 @@ __device__ __forceinline__ void load_phonon(const LaunchArgs& a, size_t i, psim:
 
 __device__ __forceinline__ void store_phonon(const LaunchArgs& a, size_t i, const psim::Phonon& p) {
     a.out_a[i] = make_float4(p.b1, p.b2, p.dx, p.dy);
-    a.out_b[i] = make_uint4(__float_as_uint(p.w), p.packed, p.cell, p.id_lo);
+    a.out_b[i] = make_uint4(__float_as_uint(p.tts), p.packed, p.cell, p.id_lo);
 }
 
 // emission: which (step, source) group does birth item `item` of this launch belong to, then build the phonon
@@ -177,80 +191,105 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
     uint32_t next = 0, n_out = 0;
     uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
     bool overflow = false;
-    bool have = false, begin = false, pending = false;
-    uint32_t s = 0;
+    uint32_t st = ST_IDLE;   // what this lane's phonon needs next
+    uint32_t s = 0;          // its measurement step
     float t_begin = 0.f;
     psim::Phonon p;
     psim::Flight f;
-    p.b1 = p.b2 = p.dx = p.dy = p.w = 0.f;
+    p.b1 = p.b2 = p.dx = p.dy = p.tts = 0.f;
     p.packed = p.cell = p.id_lo = 0u;
 
+    // Warp-level event scheduler.  Every lane carries one phonon and the kind of work it needs next; each pass
+    // executes a kind of work only if enough lanes of the warp wait for it (so the code of that kind runs with
+    // many lanes active), and a pass in which nothing qualified is followed by a pass that runs everything.
+    // The order of execution does not influence any result: a phonon's random stream is its own.
+    bool flush = false;
     for (;;) {
+        bool ran = false;
         // ---- acquire: idle lanes take the next items of the warp's stream (pool first, then births)
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have);
-        if (idle != 0u && next < total) {
-            if (!have) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
+        if (next < total && (__popc(idle) >= kMinAcquire || flush)) {
+            if (st == ST_IDLE) {
                 const uint32_t idx = next + __popc(idle & lt_mask);
                 if (idx < n_in) {
                     load_phonon(a, seg + idx, p);
                     s = a.step_begin;
                     t_begin = P.step_time;
-                    have = true;
+                    st = ST_BEGIN;
                 } else if (idx < total) {
                     const uint32_t b = idx - n_in;
                     const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
                     if (item < a.n_births) {
                         t_begin = birth_phonon(a, item, p, s);
-                        have = true;
+                        st = ST_BEGIN;
                     }
                 }
-                begin = have;
-                pending = false;
             }
             next += __popc(idle);
+            ran = true;
+        } else if (idle == 0xFFFFFFFFu && next >= total) {
+            break;  // nothing in flight, nothing left to fetch
         }
-        const unsigned busy = __ballot_sync(0xFFFFFFFFu, have);
-        if (busy == 0u) {
-            if (next >= total) { break; }
-            continue;
-        }
-        // ---- start of a measurement interval (new phonon, or the next interval of the same launch)
-        if (have && begin) {
-            psim::interval_begin(P, p, f, t_begin, s);
-            begin = false;
+        // ---- start of a measurement interval (new phonon, or the next interval inside the same launch)
+        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_BEGIN)) >= (flush ? 1 : kMinBegin)) {
+            if (st == ST_BEGIN) {
+                psim::interval_begin(P, p, f, t_begin, s);
+                st = ST_FLIGHT;
+            }
+            ran = true;
         }
         // ---- one free-flight segment
-        int ev = psim::EV_CONTINUE;
-        if (have && !pending) {
-            ev = psim::flight_event(P, p, f, s);
-            ++n_events;
-            pending = (ev == psim::EV_SCATTER);
+        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_FLIGHT)) >= (flush ? 1 : kMinFlight)) {
+            if (st == ST_FLIGHT) {
+                const int ev = psim::flight_step(p, f);
+                ++n_events;
+                st = (ev == psim::EV_IMPACT) ? ST_IMPACT : ((ev == psim::EV_SCATTER) ? ST_SCATTER : ST_FINISH);
+            }
+            ran = true;
+        }
+        // ---- surface interaction / cell transition
+        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_IMPACT)) >= (flush ? 1 : kMinImpact)) {
+            if (st == ST_IMPACT) {
+                if (psim::impact_event(P, p, f, s) == psim::EV_DEAD) {
+                    ++n_steps;
+                    ++n_absorbed;
+                    st = ST_IDLE;
+                } else {
+                    st = ST_FLIGHT;
+                }
+            }
+            ran = true;
+        }
+        // ---- intrinsic scatter
+        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_SCATTER)) >= (flush ? 1 : kMinScatter)) {
+            if (st == ST_SCATTER) {
+                psim::scatter_event(P, p, f, s);
+                st = ST_FLIGHT;
+            }
+            ran = true;
         }
         // ---- end of interval: measurement (modelSimulator.cpp:182-186), then next interval or write-back
-        bool store = false;
-        if (ev == psim::EV_END) {
-            ++n_steps;
-            if (s + 1 >= P.first_tally_step) {
-                const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
-                tally_add(a, acc_e, acc_f, s - a.step_begin, f.sensor_mat >> 8, sg, psim::flux_fixed(p.dx * f.vel) * sg,
-                          psim::flux_fixed(p.dy * f.vel) * sg);
+        const unsigned fin = __ballot_sync(0xFFFFFFFFu, st == ST_FINISH);
+        if (__popc(fin) >= (flush ? 1 : kMinFinish)) {
+            bool store = false;
+            if (st == ST_FINISH) {
+                ++n_steps;
+                if (s + 1 >= P.first_tally_step) {
+                    const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
+                    tally_add(a, acc_e, acc_f, s - a.step_begin, f.sensor_mat >> 8, sg, psim::flux_fixed(p.dx * f.vel) * sg,
+                              psim::flux_fixed(p.dy * f.vel) * sg);
+                }
+                if (s + 1 < a.step_end) {
+                    ++s;
+                    t_begin = P.step_time;
+                    st = ST_BEGIN;
+                } else {
+                    store = true;
+                    st = ST_IDLE;
+                }
             }
-            if (s + 1 < a.step_end) {
-                ++s;
-                t_begin = P.step_time;
-                begin = true;
-            } else {
-                store = true;
-                have = false;
-            }
-        } else if (ev == psim::EV_DEAD) {
-            ++n_steps;
-            ++n_absorbed;
-            have = false;
-        }
-        const unsigned storing = __ballot_sync(0xFFFFFFFFu, store);
-        if (storing != 0u) {
-            if (store) {
+            const unsigned storing = __ballot_sync(0xFFFFFFFFu, store);
+            if (store) {  // compaction: survivors go to consecutive slots of this warp's output segment
                 const uint32_t slot = n_out + __popc(storing & lt_mask);
                 if (slot < a.seg_cap) {
                     store_phonon(a, seg + slot, p);
@@ -259,18 +298,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
                 }
             }
             n_out += __popc(storing);
+            ran = true;
         }
-        // ---- deferred intrinsic scatters: run when enough lanes wait, or when nobody else can make progress
-        const unsigned waiting = __ballot_sync(0xFFFFFFFFu, pending);
-        if (waiting != 0u) {
-            const unsigned flying = __ballot_sync(0xFFFFFFFFu, have && !pending);
-            if (__popc(waiting) >= kScatterBatch || (flying == 0u && next >= total)) {
-                if (pending) {
-                    psim::scatter_event(P, p, f, s);
-                    pending = false;
-                }
-            }
-        }
+        flush = !ran;
     }
     n_out = min(n_out, a.seg_cap);
     if (lane == 0) { a.cnt_out[w] = n_out; }

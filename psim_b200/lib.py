@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpsim_b200.so")
+LIB_PATH = os.environ.get("PSIM_B200_LIB") or os.path.join(_HERE, "lib", "libpsim_b200.so")  # env: tuning builds only
 BINS = 1000
 
 ERRORS = {0: "OK", -1: "PSIM_E_INVALID", -2: "PSIM_E_NO_DEVICE", -3: "PSIM_E_CUDA", -4: "PSIM_E_OVERFLOW",

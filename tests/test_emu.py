@@ -1,0 +1,101 @@
+"""CPU-side checks of the device algorithm: psim_b200/csrc/device_core.cuh compiled for the host (tests/emu).
+The GPU tests run the same checks on the CUDA build; these keep the algorithm honest where no GPU exists."""
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+import pytest
+
+from tests import common as T
+
+
+def _one(args):
+    name, seed, n = args
+    model = T.load_model(T.case_model(name), num_phonons=n)
+    model.prepare()
+    r = T.emu_run(model, seed)
+    model.set_tallies(r["energy"], r["flux"])
+    model.finish_run(0)
+    six, temps, fluxes = model.results(0)
+    return T.run_features(r["energy"], r["flux"], model.info.sim_type, six, temps, fluxes)
+
+
+def _features(name, seeds, n=None):
+    T.emu_lib()
+    with ProcessPoolExecutor(8) as ex:
+        return list(ex.map(_one, [(name, s, n) for s in seeds]))
+
+
+@pytest.mark.parametrize("name", ["linear_demo", "sige"])
+def test_emulated_device_algorithm_steady_state_parity(name):
+    gold = T.golden(name)
+    runs = _features(name, range(1, 9))
+    T.assert_parity(T.welch_z(runs, gold, "tally_e"), f"emu {name} energy tallies")
+    T.assert_parity(T.welch_z(runs, gold, "tally_f"), f"emu {name} flux tallies")
+    six = T.welch_z(runs, gold, "out6")
+    for col in (0, 2, 4):
+        T.assert_parity(six[:, col], f"emu {name} ss column {col}")
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", ["sides_trans", "sides_per_full", "kinked_diffuse"])
+def test_emulated_device_algorithm_trace_parity(name):
+    if name not in T.all_case_names():
+        pytest.skip("fixture geometry missing")
+    gold = T.golden(name)
+    runs = _features(name, range(1, 9))
+    T.assert_parity(T.welch_z(runs, gold, "tally_e_blk"), f"emu {name} energy trace")
+    T.assert_parity(T.welch_z(runs, gold, "temp_blk"), f"emu {name} temperature trace")
+    T.assert_parity(T.welch_z(runs, gold, "flux_blk"), f"emu {name} flux trace")
+
+
+@pytest.mark.parametrize("name", ["linear_demo", "sides_trans", "linear_full"])
+def test_integer_bookkeeping_is_shard_invariant(name):
+    """Emitted counts, int32 energy tallies, fixed-point flux tallies, drift-step counts and the per-cell
+    population at every step are identical whether 1, 2, 4 or 8 shards share the phonons."""
+    model = T.load_model(T.case_model(name), num_phonons=12_000)
+    model.prepare()
+    ref = T.emu_run(model, 7, want_alive=True, want_hist=True)
+    for shards in (2, 4, 8):
+        parts = [T.emu_run(model, 7, shard=k, num_shards=shards, want_alive=True, want_hist=True) for k in range(shards)]
+        assert all(p["sources"] == ref["sources"] for p in parts)
+        assert np.array_equal(sum(p["energy"].astype(np.int64) for p in parts), ref["energy"])
+        assert np.array_equal(sum(p["fixed"] for p in parts), ref["fixed"])
+        assert sum(p["drift_steps"] for p in parts) == ref["drift_steps"]
+        assert np.array_equal(sum(p["alive"] for p in parts), ref["alive"])
+        assert np.array_equal(sum(p["hist"] for p in parts), ref["hist"])
+
+
+def test_steps_per_pass_does_not_change_results():
+    model = T.load_model(T.case_model("sides_per"), num_phonons=8_000)
+    model.prepare()
+    ref = T.emu_run(model, 3, steps_per_pass=1)
+    for spp in (2, 7, 64):
+        got = T.emu_run(model, 3, steps_per_pass=spp)
+        assert np.array_equal(got["energy"], ref["energy"])
+        assert np.array_equal(got["fixed"], ref["fixed"])
+
+
+def test_birth_bookkeeping():
+    """Every phonon of every source is created exactly once (or falls in the unrecorded last interval), windows of
+    transient surfaces are honoured, and the pool population never exceeds what was emitted."""
+    model = T.load_model(T.case_model("sides_trans"), num_phonons=20_000)
+    model.prepare()
+    r = T.emu_run(model, 5, want_alive=True)
+    total = sum(c for _, _, _, c in r["sources"])
+    assert abs(total - 20_000) <= len(r["sources"])
+    alive = r["alive"].astype(np.int64)
+    assert alive.max() <= total
+    M = model.info.measurement_steps
+    # transient patches emit in [0.1, 0.25] and [0.25, 0.4] ns of 0.5 ns: nothing is alive before step 200
+    assert alive[: int(0.1 / 0.5 * M) - 1].max() == 0
+    assert alive[int(0.2 / 0.5 * M)] > 0
+
+
+def test_full_mode_initial_population():
+    model = T.load_model(T.case_model("linear_full"), num_phonons=10_000)
+    model.prepare()
+    r = T.emu_run(model, 2, want_alive=True, want_hist=True)
+    cells = sum(c for k, _, _, c in r["sources"] if k == 0)
+    assert cells > 100                    # in a full simulation every cell starts with its thermal population
+    assert r["alive"][0] >= 0.9 * cells   # which is alive after the first interval
+    assert (r["hist"][0] > 0).sum() >= 38  # in (nearly) every one of the 40 cells
