@@ -167,6 +167,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=local)  # the drift kernels are launched on THIS stream, and so are the events
     torch.cuda.set_stream(stream)
     chunk = max(args.steps_per_launch, args.reduce_every)
+    chunk -= chunk % max(args.steps_per_launch, 1)
 
     def one_job(seed):
         """All measurement steps; the tally all-reduce of a group of steps is issued as soon as they are done."""
@@ -267,7 +268,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "synthetic 100-cell Si/Ge 2D structure (BASELINE.json configs[4]), steady-state deviational",
                        "phonons_per_gpu": per_gpu, "phonons_total": per_gpu * world, "measurement_steps": M, "cells": info.num_cells,
-                       "sensors": S, "drift_steps_per_job": total_drift, "steps_per_launch": args.steps_per_launch,
+                       "sensors": S, "drift_steps_per_job": total_drift, "steps_per_launch": last_stats["steps_per_launch"],
                        "sharding": f"phonon id mod {world}", "l2": "inputs larger than L2 (live pool >> 126 MB, streamed every launch)",
                        "rng": "Philox4x32-10 keyed by (seed, phonon id, step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -340,7 +341,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--phonons", type=int, default=100_000_000, help="phonons per GPU")
-    ap.add_argument("--steps-per-launch", type=int, default=1)
+    ap.add_argument("--steps-per-launch", type=int, default=0, help="0 = library default (automatic)")
     ap.add_argument("--reduce-every", type=int, default=50, help="measurement steps per tally all-reduce group (N > 1)")
     ap.add_argument("--tally-aggregate", type=int, default=-1)
     ap.add_argument("--tally-shared", type=int, default=-1)

@@ -28,7 +28,11 @@ PSIM_HD float f_log(float x) { return __logf(x); }
 PSIM_HD float f_exp(float x) { return __expf(x); }
 PSIM_HD float f_cos2pi(float u) { return cospif(2.f * u); }
 PSIM_HD float f_sqrt(float x) { return sqrtf(x); }
-PSIM_HD float f_div(float a, float b) { return __fdividef(a, b); }
+PSIM_HD float f_div(float a, float b) {  // a / b with one MUFU.RCP (1 ulp) - ample for hit times and scatter times
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return a * r;
+}
 PSIM_HD float f_inf() { return __int_as_float(0x7f800000); }
 template<typename T> PSIM_HD T ldg(const T* p) { return __ldg(p); }
 PSIM_HD float4 load_cell_matrix(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const float4*>(cells + i)); }
@@ -380,6 +384,13 @@ PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, floa
     (void)step;
 }
 
+// next measurement interval of a phonon whose flight state is still in registers (several steps per launch)
+PSIM_HD void interval_continue(const DevParams& P, Flight& f) {
+    f.t = P.step_time;
+    f.ncoll = 0;
+    rng_begin(f.rng);
+}
+
 PSIM_HD int flight_step(Phonon& p, Flight& f) {
     const float inf = f_inf();
     const float dt = fminf(p.tts, f.t);
@@ -437,19 +448,24 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
         }
     }
     const uint32_t kind = PSIM_LINK_KIND(link);
-    // random words this surface can consume: a transition at most 2 (new time-to-scatter, or a back-scatter
-    // direction), a wall 3 (specular test + diffuse direction) unless it is perfectly specular
+    // Random words this surface can consume - asked for at ONE place, and only if any is needed: a transition
+    // into the same sensor area none, into another area 1 (new time to scatter), a blocked material interface 2
+    // (back-scatter direction), a wall 3 (specular test + diffuse direction) unless it is perfectly specular.
     const float spec = (kind == PSIM_LINK_TRANSITION) ? 0.f : load_cell_spec(P.cells, p.cell);
-    rng_need(f.rng, (kind == PSIM_LINK_TRANSITION) ? 2u : ((spec >= 1.f) ? 0u : 3u), P, step, p.id_lo, id_hi);
+    uint32_t ncell = 0u, nsm = 0u, need = (spec >= 1.f) ? 0u : 3u;
+    bool pass = true;
     if (kind == PSIM_LINK_TRANSITION) {
-        const uint32_t ncell = PSIM_LINK_INDEX(link);
-        const uint32_t nsm = load_cell_info(P.cells, ncell).w;
+        ncell = PSIM_LINK_INDEX(link);
+        nsm = load_cell_info(P.cells, ncell).w;
         const uint32_t nmat = nsm & 0xFFu;
-        bool pass = true;
         if (nmat != (f.sensor_mat & 0xFFu)) {  // material interface: no state above the neighbour's cutoff
             const float wmax = PSIM_PACK_TA(p.packed) ? ldg(&P.materials[nmat].w_max_ta) : ldg(&P.materials[nmat].w_max_la);
             pass = !(phonon_omega(P, p.packed) > wmax);
         }
+        need = pass ? (((nsm >> 8) != (f.sensor_mat >> 8)) ? 1u : 0u) : 2u;
+    }
+    rng_need(f.rng, need, P, step, p.id_lo, id_hi);
+    if (kind == PSIM_LINK_TRANSITION) {
         if (pass) {
             place_on_edge((link >> 28) & 3u, clamp01(ma * s + mb), p);
             p.cell = ncell;

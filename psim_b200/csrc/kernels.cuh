@@ -22,17 +22,16 @@ namespace {
 constexpr int kBlock = 256;
 constexpr int kWarpsPerBlock = kBlock / 32;
 // lane states of the drift kernel's scheduler and how many lanes must wait for a kind of work before it runs
-enum : uint32_t { ST_IDLE = 0, ST_BEGIN = 1, ST_FLIGHT = 2, ST_IMPACT = 3, ST_SCATTER = 4, ST_FINISH = 5 };
+enum : uint32_t { ST_IDLE = 0, ST_FLIGHT = 2, ST_IMPACT = 3, ST_SCATTER = 4, ST_FINISH = 5 };
 #ifndef PSIM_MIN_ACQUIRE
-#define PSIM_MIN_ACQUIRE 8
-#define PSIM_MIN_BEGIN 8
-#define PSIM_MIN_FLIGHT 12
-#define PSIM_MIN_IMPACT 10
+#define PSIM_MIN_ACQUIRE 12
+#define PSIM_MIN_FLIGHT 16
+#define PSIM_MIN_IMPACT 12
 #define PSIM_MIN_SCATTER 8
-#define PSIM_MIN_FINISH 10
+#define PSIM_MIN_FINISH 12
 #endif
-constexpr int kMinAcquire = PSIM_MIN_ACQUIRE, kMinBegin = PSIM_MIN_BEGIN, kMinFlight = PSIM_MIN_FLIGHT,
-              kMinImpact = PSIM_MIN_IMPACT, kMinScatter = PSIM_MIN_SCATTER, kMinFinish = PSIM_MIN_FINISH;
+constexpr int kMinAcquire = PSIM_MIN_ACQUIRE, kMinFlight = PSIM_MIN_FLIGHT, kMinImpact = PSIM_MIN_IMPACT,
+              kMinScatter = PSIM_MIN_SCATTER, kMinFinish = PSIM_MIN_FINISH;
 
 struct LaunchArgs {
     DevParams P;
@@ -193,84 +192,37 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
     bool overflow = false;
     uint32_t st = ST_IDLE;   // what this lane's phonon needs next
     uint32_t s = 0;          // its measurement step
-    float t_begin = 0.f;
     psim::Phonon p;
     psim::Flight f;
     p.b1 = p.b2 = p.dx = p.dy = p.tts = 0.f;
     p.packed = p.cell = p.id_lo = 0u;
 
-    // Warp-level event scheduler.  Every lane carries one phonon and the kind of work it needs next; each pass
-    // executes a kind of work only if enough lanes of the warp wait for it (so the code of that kind runs with
-    // many lanes active), and a pass in which nothing qualified is followed by a pass that runs everything.
-    // The order of execution does not influence any result: a phonon's random stream is its own.
-    bool flush = false;
+    // Warp-level event scheduler.  Every lane carries one phonon and the kind of work it needs next.  Each pass
+    // counts the lanes waiting for each kind of work and executes the kinds that have enough takers (so that
+    // their code runs with many lanes active); if none has, only the most wanted kind runs.  The order of
+    // execution does not influence any result: a phonon's random stream is its own.
     for (;;) {
-        bool ran = false;
-        // ---- acquire: idle lanes take the next items of the warp's stream (pool first, then births)
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
-        if (next < total && (__popc(idle) >= kMinAcquire || flush)) {
-            if (st == ST_IDLE) {
-                const uint32_t idx = next + __popc(idle & lt_mask);
-                if (idx < n_in) {
-                    load_phonon(a, seg + idx, p);
-                    s = a.step_begin;
-                    t_begin = P.step_time;
-                    st = ST_BEGIN;
-                } else if (idx < total) {
-                    const uint32_t b = idx - n_in;
-                    const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
-                    if (item < a.n_births) {
-                        t_begin = birth_phonon(a, item, p, s);
-                        st = ST_BEGIN;
-                    }
-                }
-            }
-            next += __popc(idle);
-            ran = true;
-        } else if (idle == 0xFFFFFFFFu && next >= total) {
-            break;  // nothing in flight, nothing left to fetch
-        }
-        // ---- start of a measurement interval (new phonon, or the next interval inside the same launch)
-        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_BEGIN)) >= (flush ? 1 : kMinBegin)) {
-            if (st == ST_BEGIN) {
-                psim::interval_begin(P, p, f, t_begin, s);
-                st = ST_FLIGHT;
-            }
-            ran = true;
-        }
-        // ---- one free-flight segment
-        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_FLIGHT)) >= (flush ? 1 : kMinFlight)) {
-            if (st == ST_FLIGHT) {
-                const int ev = psim::flight_step(p, f);
-                ++n_events;
-                st = (ev == psim::EV_IMPACT) ? ST_IMPACT : ((ev == psim::EV_SCATTER) ? ST_SCATTER : ST_FINISH);
-            }
-            ran = true;
-        }
-        // ---- surface interaction / cell transition
-        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_IMPACT)) >= (flush ? 1 : kMinImpact)) {
-            if (st == ST_IMPACT) {
-                if (psim::impact_event(P, p, f, s) == psim::EV_DEAD) {
-                    ++n_steps;
-                    ++n_absorbed;
-                    st = ST_IDLE;
-                } else {
-                    st = ST_FLIGHT;
-                }
-            }
-            ran = true;
-        }
-        // ---- intrinsic scatter
-        if (__popc(__ballot_sync(0xFFFFFFFFu, st == ST_SCATTER)) >= (flush ? 1 : kMinScatter)) {
-            if (st == ST_SCATTER) {
-                psim::scatter_event(P, p, f, s);
-                st = ST_FLIGHT;
-            }
-            ran = true;
+        const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
+        const unsigned m_fly = __ballot_sync(0xFFFFFFFFu, st == ST_FLIGHT);
+        const unsigned m_hit = __ballot_sync(0xFFFFFFFFu, st == ST_IMPACT);
+        const unsigned m_sct = __ballot_sync(0xFFFFFFFFu, st == ST_SCATTER);
+        const unsigned m_fin = __ballot_sync(0xFFFFFFFFu, st == ST_FINISH);
+        const bool input = next < total;
+        if (m_idle == 0xFFFFFFFFu && !input) { break; }  // nothing in flight, nothing left to fetch
+        const int c_acq = input ? __popc(m_idle) : 0, c_fly = __popc(m_fly), c_hit = __popc(m_hit), c_sct = __popc(m_sct),
+                  c_fin = __popc(m_fin);
+        bool do_acq = c_acq >= kMinAcquire, do_fly = c_fly >= kMinFlight, do_hit = c_hit >= kMinImpact,
+             do_sct = c_sct >= kMinScatter, do_fin = c_fin >= kMinFinish;
+        if (!(do_acq || do_fly || do_hit || do_sct || do_fin)) {  // nobody qualifies: the most wanted kind runs alone
+            const int best = max(max(c_acq, c_fly), max(max(c_hit, c_sct), c_fin));
+            do_fin = c_fin == best;
+            do_fly = !do_fin && c_fly == best;
+            do_hit = !do_fin && !do_fly && c_hit == best;
+            do_acq = !do_fin && !do_fly && !do_hit && c_acq == best;
+            do_sct = !do_fin && !do_fly && !do_hit && !do_acq;
         }
         // ---- end of interval: measurement (modelSimulator.cpp:182-186), then next interval or write-back
-        const unsigned fin = __ballot_sync(0xFFFFFFFFu, st == ST_FINISH);
-        if (__popc(fin) >= (flush ? 1 : kMinFinish)) {
+        if (do_fin) {
             bool store = false;
             if (st == ST_FINISH) {
                 ++n_steps;
@@ -279,10 +231,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
                     tally_add(a, acc_e, acc_f, s - a.step_begin, f.sensor_mat >> 8, sg, psim::flux_fixed(p.dx * f.vel) * sg,
                               psim::flux_fixed(p.dy * f.vel) * sg);
                 }
-                if (s + 1 < a.step_end) {
+                if (s + 1 < a.step_end) {  // next interval of the same launch: the flight state stays in registers
                     ++s;
-                    t_begin = P.step_time;
-                    st = ST_BEGIN;
+                    psim::interval_continue(P, f);
+                    st = ST_FLIGHT;
                 } else {
                     store = true;
                     st = ST_IDLE;
@@ -298,9 +250,60 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
                 }
             }
             n_out += __popc(storing);
-            ran = true;
         }
-        flush = !ran;
+        // ---- acquire: idle lanes take the next items of the warp's stream (pool first, then births)
+        if (do_acq || (do_fin && input)) {
+            const unsigned idle = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
+            if (st == ST_IDLE) {
+                const uint32_t idx = next + __popc(idle & lt_mask);
+                float t_begin = P.step_time;
+                bool got = false;
+                if (idx < n_in) {
+                    load_phonon(a, seg + idx, p);
+                    s = a.step_begin;
+                    got = true;
+                } else if (idx < total) {
+                    const uint32_t b = idx - n_in;
+                    const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
+                    if (item < a.n_births) {
+                        t_begin = birth_phonon(a, item, p, s);
+                        got = true;
+                    }
+                }
+                if (got) {
+                    psim::interval_begin(P, p, f, t_begin, s);
+                    st = ST_FLIGHT;
+                }
+            }
+            next += __popc(idle);
+        }
+        // ---- one free-flight segment
+        if (do_fly) {
+            if (st == ST_FLIGHT) {
+                const int ev = psim::flight_step(p, f);
+                ++n_events;
+                st = (ev == psim::EV_IMPACT) ? ST_IMPACT : ((ev == psim::EV_SCATTER) ? ST_SCATTER : ST_FINISH);
+            }
+        }
+        // ---- surface interaction / cell transition
+        if (do_hit) {
+            if (st == ST_IMPACT) {
+                if (psim::impact_event(P, p, f, s) == psim::EV_DEAD) {
+                    ++n_steps;
+                    ++n_absorbed;
+                    st = ST_IDLE;
+                } else {
+                    st = ST_FLIGHT;
+                }
+            }
+        }
+        // ---- intrinsic scatter
+        if (do_sct) {
+            if (st == ST_SCATTER) {
+                psim::scatter_event(P, p, f, s);
+                st = ST_FLIGHT;
+            }
+        }
     }
     n_out = min(n_out, a.seg_cap);
     if (lane == 0) { a.cnt_out[w] = n_out; }

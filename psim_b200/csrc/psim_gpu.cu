@@ -67,7 +67,7 @@ struct psim_gpu {
     uint32_t birth_offset = 0;
     double kernel_ms = 0.;
     // options
-    int64_t opt_steps_per_launch = 1;
+    int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
     int64_t opt_warps_per_sm = 0;
     int64_t opt_blocks_per_sm = 3;   // occupancy target the kernel is compiled for (register budget)
     int64_t opt_kernel = 0;          // 0: lane-refill kernel, 1: lock-step kernel (first version, for A/B)
@@ -117,6 +117,12 @@ void free_pool(psim_gpu* h) {
 
 size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
     return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
+}
+
+uint32_t effective_steps_per_launch(const psim_gpu* h) {
+    if (h->opt_steps_per_launch > 0) { return static_cast<uint32_t>(h->opt_steps_per_launch); }
+    const size_t per_step = tally_smem_bytes(1, h->P.n_sensors);
+    return static_cast<uint32_t>(std::min<size_t>(16, std::max<size_t>(1, (32 * 1024) / per_step)));
 }
 
 int zero_run_state(psim_gpu* h) {
@@ -293,7 +299,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
     }
     PSIM_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
-    const uint32_t B = static_cast<uint32_t>(std::max<int64_t>(1, h->opt_steps_per_launch));
+    const uint32_t B = effective_steps_per_launch(h);
     for (uint32_t s0 = step_begin; s0 < step_end; s0 += B) {
         const uint32_t s1 = std::min(s0 + B, step_end);
         LaunchArgs a{};
@@ -454,7 +460,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     }
     out->kernel_ms = h->kernel_ms;
     out->launches = h->launches;
-    out->steps_per_launch = static_cast<uint32_t>(std::max<int64_t>(1, h->opt_steps_per_launch));
+    out->steps_per_launch = effective_steps_per_launch(h);
     out->warps = h->n_warps;
     out->tally_in_shared = h->last_tally_shared;
     out->image_bytes = h->img.cells.size() * sizeof(DevCell) + h->img.subs.size() * sizeof(DevSub) +
@@ -471,8 +477,8 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
     if (!h || !name) { return PSIM_E_INVALID; }
     const std::string k(name);
     if (k == "steps_per_launch") {
-        if (value < 1 || value > 64) {
-            h->err = "steps_per_launch must be in [1, 64]";
+        if (value < 0 || value > 64) {
+            h->err = "steps_per_launch must be in [0, 64] (0 = automatic)";
             return PSIM_E_INVALID;
         }
         h->opt_steps_per_launch = value;
