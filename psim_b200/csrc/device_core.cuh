@@ -286,8 +286,8 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     if (src.kind == 0u) {
         p.cell = src.index;
         const uint4 info = load_cell_info(P.cells, p.cell);
-        const DevSensor s = load_sensor(P.sensors, info.w >> 8);
-        sample_table(P, s.base_table, info.w & 0xFFu, u_bin, u_pol, u_jit, p, vel);
+        const DevSensor s = load_sensor(P.sensors, PSIM_CELL_SENSOR(info.w));
+        sample_table(P, s.base_table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
         float r1 = u_a, r2 = u_b;
         if (r1 + r2 > 1.f) {
             r1 = 1.f - r1;
@@ -309,17 +309,17 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     double frac = (lo + (hi - lo) * static_cast<double>(u_time)) / P.step_time_d;
     frac = frac < 0. ? 0. : (frac > 0.999999 ? 0.999999 : frac);
     (void)j;
-    sample_table(P, em.table, info.w & 0xFFu, u_bin, u_pol, u_jit, p, vel);
+    sample_table(P, em.table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
     place_on_edge(em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
     const float2 n = load_cell_normal(P.cells, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
-        p.packed = (p.packed & 0xFF000800u) | 1u | ((info.w & 0xFu) << 12);
+        p.packed = (p.packed & 0xFF000800u) | 1u | (PSIM_CELL_MAT(info.w) << 12);
         p.dx = n.x;
         p.dy = n.y;
     } else {
         diffuse_direction(u_b, u_c, n.x, n.y, p);
     }
-    p.tts = draw_scatter_time(P, load_sensor(P.sensors, info.w >> 8), p, u_d);
+    p.tts = draw_scatter_time(P, load_sensor(P.sensors, PSIM_CELL_SENSOR(info.w)), p, u_d);
     return static_cast<float>((1. - frac) * P.step_time_d);
 }
 
@@ -343,7 +343,7 @@ enum { EV_CONTINUE = 0, EV_END = 1, EV_DEAD = 2, EV_SCATTER = 3, EV_IMPACT = 4 }
 
 struct Flight {
     float m00, m01, m10, m11;  // barycentric rate matrix of the current cell
-    uint32_t sensor_mat;       // [31:8] sensor, [7:0] material of the current cell
+    uint32_t sensor_mat;       // sensor / rate class / material word of the current cell (PSIM_CELL_*)
     float vel;                 // group velocity of the phonon
     float r1, r2;              // d(b1)/dt, d(b2)/dt
     float t;                   // time left in the measurement interval (ns)
@@ -427,6 +427,33 @@ PSIM_HD int flight_step(Phonon& p, Flight& f) {
     return EV_IMPACT;
 }
 
+// The reference redraws the time to scatter whenever a phonon enters another sensor area (modelSimulator.cpp:
+// 167-172,192-194) because the rates may differ there.  Where they provably do not - same material, same
+// temperature, i.e. the same "rate class" - the exponential law is memoryless and keeping the old time is the same
+// distribution, so no random number is spent.  Class 255 = "unclassified": always redraw.
+PSIM_HD bool rates_differ(uint32_t cell_word_a, uint32_t cell_word_b) {
+    return ((cell_word_a ^ cell_word_b) & 0xFFFu) != 0u || PSIM_CELL_CLASS(cell_word_a) == 255u;
+}
+
+// Fast path of a surface interaction, taken inline by the flight loop: the edge is wholly a transition into a
+// neighbour cell with the same material and rate class (by far the most frequent impact inside a mesh).
+// Everything else (walls, emitters, material interfaces, partial edges, stuck-phonon guard) goes to impact_event.
+PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) {
+    const uint4 info = load_cell_info(P.cells, p.cell);
+    const uint32_t link = (f.edge == 0u) ? info.x : ((f.edge == 1u) ? info.y : info.z);
+    if (PSIM_LINK_KIND(link) != PSIM_LINK_TRANSITION || f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
+    const uint32_t ncell = PSIM_LINK_INDEX(link);
+    const uint32_t nsm = load_cell_info(P.cells, ncell).w;
+    if (rates_differ(nsm, f.sensor_mat)) { return false; }
+    place_on_edge((link >> 28) & 3u, (link & (1u << 27)) ? f.s_hit : 1.f - f.s_hit, p);
+    p.cell = ncell;
+    f.sensor_mat = nsm;
+    set_cell_matrix(f, load_cell_matrix(P.cells, ncell));
+    update_rates_of_motion(f, p);
+    ++f.ncoll;
+    return true;
+}
+
 PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     const uint32_t e = f.edge;
     const float s = f.s_hit;
@@ -457,23 +484,23 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     if (kind == PSIM_LINK_TRANSITION) {
         ncell = PSIM_LINK_INDEX(link);
         nsm = load_cell_info(P.cells, ncell).w;
-        const uint32_t nmat = nsm & 0xFFu;
-        if (nmat != (f.sensor_mat & 0xFFu)) {  // material interface: no state above the neighbour's cutoff
+        const uint32_t nmat = PSIM_CELL_MAT(nsm);
+        if (nmat != PSIM_CELL_MAT(f.sensor_mat)) {  // material interface: no state above the neighbour's cutoff
             const float wmax = PSIM_PACK_TA(p.packed) ? ldg(&P.materials[nmat].w_max_ta) : ldg(&P.materials[nmat].w_max_la);
             pass = !(phonon_omega(P, p.packed) > wmax);
         }
-        need = pass ? (((nsm >> 8) != (f.sensor_mat >> 8)) ? 1u : 0u) : 2u;
+        need = pass ? (rates_differ(nsm, f.sensor_mat) ? 1u : 0u) : 2u;
     }
     rng_need(f.rng, need, P, step, p.id_lo, id_hi);
     if (kind == PSIM_LINK_TRANSITION) {
         if (pass) {
             place_on_edge((link >> 28) & 3u, clamp01(ma * s + mb), p);
             p.cell = ncell;
-            const bool new_sensor = (nsm >> 8) != (f.sensor_mat >> 8);
+            const bool new_sensor = rates_differ(nsm, f.sensor_mat);
             f.sensor_mat = nsm;
             set_cell_matrix(f, load_cell_matrix(P.cells, ncell));
-            if (new_sensor) {  // the old time-to-scatter is void in the new sensor area (modelSimulator.cpp:167-172,192-194)
-                p.tts = draw_scatter_time(P, load_sensor(P.sensors, nsm >> 8), p, rng_u01(f.rng));
+            if (new_sensor) {  // the old time-to-scatter is void where the rates differ (modelSimulator.cpp:167-172,192-194)
+                p.tts = draw_scatter_time(P, load_sensor(P.sensors, PSIM_CELL_SENSOR(nsm)), p, rng_u01(f.rng));
             }
         } else {  // back into the same cell, about the true inward normal
             const float2 n = load_cell_normal(P.cells, p.cell, e);
@@ -510,7 +537,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
 // then the rates and the time to scatter of the next one (get_scatter_info, :148-153)
 PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
-    const DevSensor sen = load_sensor(P.sensors, f.sensor_mat >> 8);
+    const DevSensor sen = load_sensor(P.sensors, PSIM_CELL_SENSOR(f.sensor_mat));
     float rn, ru, ri;
     relax_rates(sen, phonon_omega(P, p.packed), PSIM_PACK_TA(p.packed), rn, ru, ri);
     rng_refill(f.rng, P, step, p.id_lo, id_hi);
@@ -519,7 +546,7 @@ PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t st
     rng_refill(f.rng, P, step, p.id_lo, id_hi);
     const float u_d1 = rng_u01(f.rng), u_d2 = rng_u01(f.rng), u_tts = rng_u01(f.rng);
     if (r <= rn + ru) {
-        sample_table(P, sen.scatter_table, f.sensor_mat & 0xFFu, u_bin, u_pol, u_jit, p, f.vel);
+        sample_table(P, sen.scatter_table, PSIM_CELL_MAT(f.sensor_mat), u_bin, u_pol, u_jit, p, f.vel);
         if (r > rn) { isotropic_direction(u_d1, u_d2, p); }  // Umklapp
     } else if (ri > 0.f) {
         isotropic_direction(u_d1, u_d2, p);
@@ -538,6 +565,7 @@ PSIM_HD bool advance_interval(const DevParams& P, Phonon& p, float t, uint32_t s
         ++events;
         const int ev = flight_step(p, f);
         if (ev == EV_IMPACT) {
+            if (fast_transition(P, p, f)) { continue; }
             if (impact_event(P, p, f, step) == EV_DEAD) { return false; }
         } else if (ev == EV_SCATTER) {
             scatter_event(P, p, f, step);
@@ -545,7 +573,7 @@ PSIM_HD bool advance_interval(const DevParams& P, Phonon& p, float t, uint32_t s
             break;
         }
     }
-    sensor_out = f.sensor_mat >> 8;
+    sensor_out = PSIM_CELL_SENSOR(f.sensor_mat);
     return true;
 }
 

@@ -29,6 +29,12 @@
 #define PSIM_LINK_KIND(w) ((w) >> 30)
 #define PSIM_LINK_INDEX(w) ((w)&0x07FFFFFFu)
 
+// DevCell::sensor_mat.  Rate class: sensors with the same material and the same temperature have identical
+// relaxation rates; 255 = unclassified (more than 255 distinct classes in the model).
+#define PSIM_CELL_SENSOR(w) ((w) >> 12)
+#define PSIM_CELL_CLASS(w) (((w) >> 4) & 0xFFu)
+#define PSIM_CELL_MAT(w) ((w)&0xFu)
+
 #if defined(__CUDACC__)
 #define PSIM_ALIGN(n) __align__(n)
 #else
@@ -40,7 +46,7 @@
 struct PSIM_ALIGN(16) DevCell {
     float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [P2-P1 | P3-P1])
     uint32_t link[3];          // what lies behind each edge
-    uint32_t sensor_mat;       // [31:8] sensor index, [7:0] material index
+    uint32_t sensor_mat;       // [31:12] sensor index, [11:4] rate class, [3:0] material index (PSIM_CELL_*)
     float n[3][2];             // unit normals of edges 0..2 pointing INTO the cell (geometry.cpp:97-100)
     float spec;                // specularity of the cell's boundary surfaces, clamped to [0,1] (cell.cpp:115-119)
     uint32_t pad;

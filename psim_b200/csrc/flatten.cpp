@@ -30,9 +30,9 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         fail(err, PSIM_E_INVALID, "model description has empty or null arrays", rc);
         return rc;
     }
-    if (d.num_materials > 16 || d.num_sensors >= (1u << 24) || d.num_cells >= (1u << 27) ||
+    if (d.num_materials > 16 || d.num_sensors >= (1u << 20) || d.num_cells >= (1u << 27) ||
         d.num_emitters >= (1u << 27) || d.num_subsurfaces >= (1u << 27)) {
-        fail(err, PSIM_E_INVALID, "model exceeds packed-index limits (16 materials, 2^24 sensors, 2^27 cells)", rc);
+        fail(err, PSIM_E_INVALID, "model exceeds packed-index limits (16 materials, 2^20 sensors, 2^27 cells)", rc);
         return rc;
     }
     if (d.measurement_steps < 2 || !(d.simulation_time > 0.) || d.step_adjustment >= d.measurement_steps) {
@@ -148,6 +148,19 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         out.emitters[e] = o;
     }
 
+    // rate classes: sensors of the same material at the same temperature have identical relaxation rates
+    std::vector<uint32_t> sensor_class(d.num_sensors, 255u);
+    {
+        std::vector<std::pair<uint32_t, double>> classes;
+        for (uint32_t s = 0; s < d.num_sensors; ++s) {
+            const std::pair<uint32_t, double> key{ d.sensors[s].material, d.sensors[s].temperature };
+            size_t k = 0;
+            while (k < classes.size() && classes[k] != key) { ++k; }
+            if (k == classes.size() && classes.size() < 255) { classes.push_back(key); }
+            sensor_class[s] = k < 255 ? static_cast<uint32_t>(k) : 255u;
+        }
+    }
+
     // cells
     out.cells.resize(d.num_cells);
     for (uint32_t c = 0; c < d.num_cells; ++c) {
@@ -180,7 +193,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         unit(-(m00 + m10), -(m01 + m11), o.n[1][0], o.n[1][1]); // edge 1 is b1 + b2 = 1
         unit(m00, m01, o.n[2][0], o.n[2][1]);                   // edge 2 is b1 = 0
         o.spec = static_cast<float>(std::min(1., std::max(0., in.specularity)));
-        o.sensor_mat = (in.sensor << 8) | d.sensors[in.sensor].material;
+        o.sensor_mat = (in.sensor << 12) | (sensor_class[in.sensor] << 4) | d.sensors[in.sensor].material;
         for (int k = 0; k < 3; ++k) {
             const uint32_t n = in.sub_count[k], first = in.sub_first[k];
             if (n == 0) {

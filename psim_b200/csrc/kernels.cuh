@@ -221,25 +221,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
             do_acq = !do_fin && !do_fly && !do_hit && c_acq == best;
             do_sct = !do_fin && !do_fly && !do_hit && !do_acq;
         }
-        // ---- end of interval: measurement (modelSimulator.cpp:182-186), then next interval or write-back
+        // ---- write-back of the phonons that reached the end of the launch window
         if (do_fin) {
-            bool store = false;
-            if (st == ST_FINISH) {
-                ++n_steps;
-                if (s + 1 >= P.first_tally_step) {
-                    const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
-                    tally_add(a, acc_e, acc_f, s - a.step_begin, f.sensor_mat >> 8, sg, psim::flux_fixed(p.dx * f.vel) * sg,
-                              psim::flux_fixed(p.dy * f.vel) * sg);
-                }
-                if (s + 1 < a.step_end) {  // next interval of the same launch: the flight state stays in registers
-                    ++s;
-                    psim::interval_continue(P, f);
-                    st = ST_FLIGHT;
-                } else {
-                    store = true;
-                    st = ST_IDLE;
-                }
-            }
+            const bool store = st == ST_FINISH;
             const unsigned storing = __ballot_sync(0xFFFFFFFFu, store);
             if (store) {  // compaction: survivors go to consecutive slots of this warp's output segment
                 const uint32_t slot = n_out + __popc(storing & lt_mask);
@@ -248,6 +232,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
                 } else {
                     overflow = true;
                 }
+                st = ST_IDLE;
             }
             n_out += __popc(storing);
         }
@@ -280,9 +265,24 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
         // ---- one free-flight segment
         if (do_fly) {
             if (st == ST_FLIGHT) {
-                const int ev = psim::flight_step(p, f);
+                int ev = psim::flight_step(p, f);
                 ++n_events;
-                st = (ev == psim::EV_IMPACT) ? ST_IMPACT : ((ev == psim::EV_SCATTER) ? ST_SCATTER : ST_FINISH);
+                if (ev == psim::EV_IMPACT && psim::fast_transition(P, p, f)) { ev = psim::EV_CONTINUE; }
+                if (ev == psim::EV_END) {  // measurement event: the phonon now belongs to step s + 1 (modelSimulator.cpp:182-186)
+                    ++n_steps;
+                    if (s + 1 >= P.first_tally_step) {
+                        const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
+                        tally_add(a, acc_e, acc_f, s - a.step_begin, PSIM_CELL_SENSOR(f.sensor_mat), sg,
+                                  psim::flux_fixed(p.dx * f.vel) * sg, psim::flux_fixed(p.dy * f.vel) * sg);
+                    }
+                    if (s + 1 < a.step_end) {  // next interval of the same launch: the flight state stays in registers
+                        ++s;
+                        psim::interval_continue(P, f);
+                        ev = psim::EV_CONTINUE;
+                    }
+                }
+                st = (ev == psim::EV_CONTINUE) ? ST_FLIGHT
+                     : ((ev == psim::EV_IMPACT) ? ST_IMPACT : ((ev == psim::EV_SCATTER) ? ST_SCATTER : ST_FINISH));
             }
         }
         // ---- surface interaction / cell transition

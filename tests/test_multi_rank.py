@@ -23,15 +23,17 @@ def _worker(rank, world, port, out_dir):
     model = T.load_model(T.case_model("sides_trans"), num_phonons=6_000)
     model.prepare()
     r = T.emu_run(model, 9, shard=rank, num_shards=world)
-    energy = torch.from_numpy(r["energy"].astype(np.int64))
-    fixed = torch.from_numpy(r["fixed"].copy())
+    # device layout of the tallies: [recorded step][sensor], so a group of steps is one contiguous slice
+    energy = torch.from_numpy(np.ascontiguousarray(r["energy"].astype(np.int64).T))
+    fixed = torch.from_numpy(np.ascontiguousarray(r["fixed"].transpose(1, 0, 2)))
     steps = torch.tensor([r["drift_steps"]], dtype=torch.int64)
-    R = energy.shape[1]
+    R = energy.shape[0]
     for lo in range(0, R, 250):  # per group of measurement steps, like the NCCL path
-        dist.all_reduce(energy[:, lo:lo + 250])
-        dist.all_reduce(fixed[:, lo:lo + 250])
+        dist.all_reduce(energy[lo:lo + 250])
+        dist.all_reduce(fixed[lo:lo + 250])
     dist.all_reduce(steps)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), energy=energy.numpy(), fixed=fixed.numpy(), steps=steps.numpy())
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), energy=energy.numpy().T, fixed=fixed.numpy().transpose(1, 0, 2),
+             steps=steps.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
