@@ -124,15 +124,22 @@ PSIM_HD void rng_need(Rng& r, uint32_t n, const DevParams& P, uint32_t step, uin
     if (r.left < n) { rng_refill(r, P, step, id_lo, id_hi); }
 }
 
-// uniform on (0, 1] with 24 random bits (the reference draws doubles on [0, 1], utils.h:19); needs left > 0
-PSIM_HD float rng_u01(Rng& r) {
+// next unread 32-bit word; needs left > 0
+PSIM_HD uint32_t rng_word(Rng& r) {
     const uint32_t x = r.v0;
     r.v0 = r.v1;
     r.v1 = r.v2;
     r.v2 = r.v3;
     --r.left;
-    return static_cast<float>((x >> 8) + 1u) * 5.9604644775390625e-8f;
+    return x;
 }
+
+// uniform on (0, 1] with 24 random bits (the reference draws doubles on [0, 1], utils.h:19)
+PSIM_HD float u01_from24(uint32_t x) { return static_cast<float>((x >> 8) + 1u) * 5.9604644775390625e-8f; }
+// two uniforms on (0, 1] with 16 random bits each from one word (directions, branch selection)
+PSIM_HD float u01_hi16(uint32_t x) { return static_cast<float>((x >> 16) + 1u) * 1.52587890625e-5f; }
+PSIM_HD float u01_lo16(uint32_t x) { return static_cast<float>((x & 0xFFFFu) + 1u) * 1.52587890625e-5f; }
+PSIM_HD float rng_u01(Rng& r) { return u01_from24(rng_word(r)); }
 
 struct Phonon {
     float b1, b2;     // position in the current cell's frame
@@ -183,12 +190,11 @@ PSIM_HD float phonon_omega(const DevParams& P, uint32_t packed) {
     return P.phasor ? static_cast<float>(PSIM_FREQ_SCALE) : w;  // PhasorBuilder: freq = 1 rad/s (phononBuilder.cpp:46)
 }
 
-// consumes 2 uniforms (3 in deviational mode): bin, polarisation, (frequency jitter)
-PSIM_HD void sample_table(const DevParams& P, uint32_t table_idx, uint32_t mat, float u_bin, float u_pol, float u_jit,
+// bin and polarisation from two uniforms; `jit` = position of the frequency inside the bin in 1/256ths
+PSIM_HD void sample_table(const DevParams& P, uint32_t table_idx, uint32_t mat, float u_bin, float u_pol, uint32_t jit,
                           Phonon& p, float& vel) {
     const uint32_t bin = sample_bin(P, table_idx, u_bin);
     const uint32_t ta = (u_pol <= ldg(&P.tables[static_cast<size_t>(table_idx) * PSIM_BINS + bin].y)) ? 0u : 1u;
-    const uint32_t jit = min(static_cast<uint32_t>(u_jit * 256.f), 255u);
     p.packed = (p.packed & 0xFF000800u) | bin | (ta << 10) | (mat << 12) | (jit << 16);
     vel = ldg(&P.velocities[(mat * 2u + ta) * PSIM_BINS + bin]);
 }
@@ -279,7 +285,8 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     Rng rng;
     rng_begin(rng);
     rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
-    const float u_time = rng_u01(rng), u_bin = rng_u01(rng), u_pol = rng_u01(rng), u_jit = rng_u01(rng);
+    const float u_time = rng_u01(rng), u_bin = rng_u01(rng), u_pol = rng_u01(rng);
+    const uint32_t u_jit = rng_word(rng) >> 24;
     rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
     const float u_a = rng_u01(rng), u_b = rng_u01(rng), u_c = rng_u01(rng), u_d = rng_u01(rng);
     float vel;
@@ -455,6 +462,7 @@ PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) {
 }
 
 PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
+    f.rng.left = 0;  // every event that needs random numbers starts a fresh Philox block of its (phonon, step) stream
     const uint32_t e = f.edge;
     const float s = f.s_hit;
     const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
@@ -540,11 +548,14 @@ PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t st
     const DevSensor sen = load_sensor(P.sensors, PSIM_CELL_SENSOR(f.sensor_mat));
     float rn, ru, ri;
     relax_rates(sen, phonon_omega(P, p.packed), PSIM_PACK_TA(p.packed), rn, ru, ri);
+    // ONE Philox block per scatter: word 0 -> bin (24 bits) + position inside the bin (8 bits), word 1 -> branch
+    // selection + polarisation (16 bits each), word 2 -> next time to scatter, word 3 -> new direction (2 x 16 bits)
     rng_refill(f.rng, P, step, p.id_lo, id_hi);
-    const float r = rng_u01(f.rng) * (rn + ru + ri);
-    const float u_bin = rng_u01(f.rng), u_pol = rng_u01(f.rng), u_jit = rng_u01(f.rng);
-    rng_refill(f.rng, P, step, p.id_lo, id_hi);
-    const float u_d1 = rng_u01(f.rng), u_d2 = rng_u01(f.rng), u_tts = rng_u01(f.rng);
+    const uint32_t w0 = rng_word(f.rng), w1 = rng_word(f.rng), w2 = rng_word(f.rng), w3 = rng_word(f.rng);
+    const float r = u01_hi16(w1) * (rn + ru + ri);
+    const float u_bin = u01_from24(w0), u_pol = u01_lo16(w1);
+    const uint32_t u_jit = w0 & 0xFFu;
+    const float u_d1 = u01_hi16(w3), u_d2 = u01_lo16(w3), u_tts = u01_from24(w2);
     if (r <= rn + ru) {
         sample_table(P, sen.scatter_table, PSIM_CELL_MAT(f.sensor_mat), u_bin, u_pol, u_jit, p, f.vel);
         if (r > rn) { isotropic_direction(u_d1, u_d2, p); }  // Umklapp

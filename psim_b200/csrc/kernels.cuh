@@ -311,6 +311,255 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_
     tally_flush(a, acc_e, acc_f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// drift_kernel_slots<K>: the same step, with K phonons IN FLIGHT PER LANE instead of one.
+//
+// The scheduler of drift_kernel can only regroup the 32 phonons a warp holds in registers: with five kinds of work a
+// kind rarely has more than ~14 takers (ncu: 14.4 of 32 threads active per instruction).  Here every lane owns K
+// slots in shared memory (12 words each, laid out [field][slot][lane] so that lane l only ever touches bank l: no
+// bank conflicts), i.e. a warp has 32 K phonons to choose from.  A pass picks the kind of work wanted by the most
+// LANES (a lane wants a kind if any of its slots does - one bit mask per kind per lane, in a register) and every
+// such lane executes it for one of its slots.  With K = 4 a lane almost always has a slot that wants to fly, and the
+// rare kinds are executed when (nearly) every lane has one waiting.
+// ---------------------------------------------------------------------------------------------------------------
+enum : int { SF_B1 = 0, SF_B2, SF_DX, SF_DY, SF_TTS, SF_PACKED, SF_CELL, SF_ID, SF_T, SF_R1, SF_R2, SF_MISC, SF_COUNT };
+// SF_MISC: [5:0] measurement step relative to the launch, [12:6] impacts since the last scatter, [14:13] edge hit,
+//          [24:15] next Philox block of this (phonon, step) stream
+#define PSIM_MISC_STEP(m) ((m)&63u)
+#define PSIM_MISC_NCOLL(m) (((m) >> 6) & 127u)
+#define PSIM_MISC_EDGE(m) (((m) >> 13) & 3u)
+#define PSIM_MISC_BLOCK(m) (((m) >> 15) & 1023u)
+
+template<int K>
+__global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_constant__ LaunchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevParams& P = a.P;
+    const uint32_t nst = a.step_end - a.step_begin;
+    int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
+    long long* acc_f = reinterpret_cast<long long*>(smem_raw + tally_smem_offset_f(nst, P.n_sensors));
+    tally_init(a, acc_e, acc_f);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const size_t tally_bytes = a.tally_shared ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
+    uint32_t* sw = reinterpret_cast<uint32_t*>(smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127))) +
+                   (threadIdx.x >> 5) * (SF_COUNT * K * 32) + lane;
+    auto slot_u = [&](int field, uint32_t k) -> uint32_t& { return sw[(field * K + k) * 32]; };
+    auto slot_f = [&](int field, uint32_t k) -> float& { return reinterpret_cast<float*>(sw)[(field * K + k) * 32]; };
+
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t W = a.n_warps;
+    const size_t seg = static_cast<size_t>(w) * a.seg_cap;
+    const uint32_t n_in = a.cnt_in[w];
+    const uint64_t n_chunks = (a.n_births + 31u) >> 5;
+    const uint32_t c0 = (w + W - (a.birth_warp_offset % W)) % W;
+    const uint32_t my_chunks = (c0 < n_chunks) ? static_cast<uint32_t>((n_chunks - 1 - c0) / W + 1) : 0u;
+    const uint32_t total = n_in + my_chunks * 32u;
+
+    uint32_t next = 0, n_out = 0;
+    uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
+    bool overflow = false;
+    uint32_t m_free = (1u << K) - 1u, m_fly = 0, m_hit = 0, m_sct = 0, m_fin = 0;  // which of my slots want what
+
+    for (;;) {
+        const bool input = next < total;
+        const int c_fly = __popc(__ballot_sync(0xFFFFFFFFu, m_fly != 0u));
+        const int c_hit = __popc(__ballot_sync(0xFFFFFFFFu, m_hit != 0u));
+        const int c_sct = __popc(__ballot_sync(0xFFFFFFFFu, m_sct != 0u));
+        const int c_fin = __popc(__ballot_sync(0xFFFFFFFFu, m_fin != 0u));
+        const int c_acq = input ? __popc(__ballot_sync(0xFFFFFFFFu, m_free != 0u)) : 0;
+        const int best = max(max(c_fly, c_hit), max(max(c_sct, c_fin), c_acq));
+        if (best == 0) { break; }
+        // the kind wanted by the most lanes runs; ties go to the rarer kinds (they waited longest to get there)
+        if (c_sct == best) {
+            // ---- intrinsic scatter
+            if (m_sct != 0u) {
+                const uint32_t k = __ffs(m_sct) - 1u;
+                psim::Phonon p;
+                psim::Flight f;
+                p.dx = slot_f(SF_DX, k);
+                p.dy = slot_f(SF_DY, k);
+                p.packed = slot_u(SF_PACKED, k);
+                p.cell = slot_u(SF_CELL, k);
+                p.id_lo = slot_u(SF_ID, k);
+                uint32_t misc = slot_u(SF_MISC, k);
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.vel = psim::phonon_velocity(P, p.packed);
+                f.rng.block = PSIM_MISC_BLOCK(misc);
+                f.rng.left = 0;
+                psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                misc = (misc & 0x603Fu) | (min(f.rng.block, 1023u) << 15);  // impacts since the last scatter := 0
+                slot_f(SF_DX, k) = p.dx;
+                slot_f(SF_DY, k) = p.dy;
+                slot_u(SF_PACKED, k) = p.packed;
+                slot_f(SF_TTS, k) = p.tts;
+                slot_f(SF_R1, k) = f.r1;
+                slot_f(SF_R2, k) = f.r2;
+                slot_u(SF_MISC, k) = misc;
+                m_sct &= ~(1u << k);
+                m_fly |= 1u << k;
+            }
+        } else if (c_hit == best) {
+            // ---- surface interaction / cell transition
+            if (m_hit != 0u) {
+                const uint32_t k = __ffs(m_hit) - 1u;
+                psim::Phonon p;
+                psim::Flight f;
+                p.b1 = slot_f(SF_B1, k);
+                p.b2 = slot_f(SF_B2, k);
+                p.dx = slot_f(SF_DX, k);
+                p.dy = slot_f(SF_DY, k);
+                p.tts = slot_f(SF_TTS, k);
+                p.packed = slot_u(SF_PACKED, k);
+                p.cell = slot_u(SF_CELL, k);
+                p.id_lo = slot_u(SF_ID, k);
+                uint32_t misc = slot_u(SF_MISC, k);
+                f.edge = PSIM_MISC_EDGE(misc);
+                f.s_hit = (f.edge == 0u) ? p.b1 : ((f.edge == 1u) ? p.b2 : 1.f - p.b2);
+                f.ncoll = PSIM_MISC_NCOLL(misc);
+                f.rng.block = PSIM_MISC_BLOCK(misc);
+                f.rng.left = 0;
+                f.r1 = slot_f(SF_R1, k);
+                f.r2 = slot_f(SF_R2, k);
+                f.t = 0.f;
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.vel = psim::phonon_velocity(P, p.packed);
+                const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                m_hit &= ~(1u << k);
+                if (ev == psim::EV_DEAD) {
+                    ++n_steps;
+                    ++n_absorbed;
+                    m_free |= 1u << k;
+                } else {
+                    misc = (misc & 0x603Fu) | (min(f.ncoll, 127u) << 6) | (min(f.rng.block, 1023u) << 15);
+                    slot_f(SF_B1, k) = p.b1;
+                    slot_f(SF_B2, k) = p.b2;
+                    slot_f(SF_DX, k) = p.dx;
+                    slot_f(SF_DY, k) = p.dy;
+                    slot_f(SF_TTS, k) = p.tts;
+                    slot_u(SF_CELL, k) = p.cell;
+                    slot_f(SF_R1, k) = f.r1;
+                    slot_f(SF_R2, k) = f.r2;
+                    slot_u(SF_MISC, k) = misc;
+                    m_fly |= 1u << k;
+                }
+            }
+        } else if (c_fin == best) {
+            // ---- write-back of phonons that reached the end of the launch window (compacted, coalesced)
+            const bool store = m_fin != 0u;
+            const unsigned storing = __ballot_sync(0xFFFFFFFFu, store);
+            if (store) {
+                const uint32_t k = __ffs(m_fin) - 1u;
+                const uint32_t slot = n_out + __popc(storing & lt_mask);
+                if (slot < a.seg_cap) {
+                    a.out_a[seg + slot] = make_float4(slot_f(SF_B1, k), slot_f(SF_B2, k), slot_f(SF_DX, k), slot_f(SF_DY, k));
+                    a.out_b[seg + slot] = make_uint4(slot_u(SF_TTS, k), slot_u(SF_PACKED, k), slot_u(SF_CELL, k), slot_u(SF_ID, k));
+                } else {
+                    overflow = true;
+                }
+                m_fin &= ~(1u << k);
+                m_free |= 1u << k;
+            }
+            n_out += __popc(storing);
+        } else if (c_acq == best) {
+            // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots
+            const unsigned taking = __ballot_sync(0xFFFFFFFFu, m_free != 0u);
+            if (m_free != 0u) {
+                const uint32_t k = __ffs(m_free) - 1u;
+                const uint32_t idx = next + __popc(taking & lt_mask);
+                psim::Phonon p;
+                uint32_t s = a.step_begin;
+                float t_begin = P.step_time;
+                bool got = false;
+                if (idx < n_in) {
+                    load_phonon(a, seg + idx, p);
+                    got = true;
+                } else if (idx < total) {
+                    const uint32_t b = idx - n_in;
+                    const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
+                    if (item < a.n_births) {
+                        t_begin = birth_phonon(a, item, p, s);
+                        got = true;
+                    }
+                }
+                if (got) {
+                    psim::Flight f;
+                    psim::interval_begin(P, p, f, t_begin, s);
+                    slot_f(SF_B1, k) = p.b1;
+                    slot_f(SF_B2, k) = p.b2;
+                    slot_f(SF_DX, k) = p.dx;
+                    slot_f(SF_DY, k) = p.dy;
+                    slot_f(SF_TTS, k) = p.tts;
+                    slot_u(SF_PACKED, k) = p.packed;
+                    slot_u(SF_CELL, k) = p.cell;
+                    slot_u(SF_ID, k) = p.id_lo;
+                    slot_f(SF_T, k) = f.t;
+                    slot_f(SF_R1, k) = f.r1;
+                    slot_f(SF_R2, k) = f.r2;
+                    slot_u(SF_MISC, k) = s - a.step_begin;
+                    m_free &= ~(1u << k);
+                    m_fly |= 1u << k;
+                }
+            }
+            next += __popc(taking);
+        } else {
+            // ---- one free-flight segment
+            if (m_fly != 0u) {
+                const uint32_t k = __ffs(m_fly) - 1u;
+                psim::Phonon p;
+                psim::Flight f;
+                p.b1 = slot_f(SF_B1, k);
+                p.b2 = slot_f(SF_B2, k);
+                p.tts = slot_f(SF_TTS, k);
+                f.t = slot_f(SF_T, k);
+                f.r1 = slot_f(SF_R1, k);
+                f.r2 = slot_f(SF_R2, k);
+                f.edge = 0u;
+                uint32_t misc = slot_u(SF_MISC, k);
+                int ev = psim::flight_step(p, f);
+                ++n_events;
+                if (ev == psim::EV_END) {  // measurement event: the phonon now belongs to step s + 1 (modelSimulator.cpp:182-186)
+                    ++n_steps;
+                    const uint32_t s = a.step_begin + PSIM_MISC_STEP(misc);
+                    if (s + 1 >= P.first_tally_step) {
+                        const uint32_t packed = slot_u(SF_PACKED, k);
+                        const float vel = psim::phonon_velocity(P, packed);
+                        const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
+                        tally_add(a, acc_e, acc_f, s - a.step_begin, PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w),
+                                  sg, psim::flux_fixed(slot_f(SF_DX, k) * vel) * sg, psim::flux_fixed(slot_f(SF_DY, k) * vel) * sg);
+                    }
+                    if (s + 1 < a.step_end) {  // next interval of the same launch
+                        misc = PSIM_MISC_STEP(misc) + 1u;
+                        f.t = P.step_time;
+                        ev = psim::EV_CONTINUE;
+                    }
+                }
+                slot_f(SF_B1, k) = p.b1;
+                slot_f(SF_B2, k) = p.b2;
+                slot_f(SF_TTS, k) = p.tts;
+                slot_f(SF_T, k) = f.t;
+                if (ev != psim::EV_CONTINUE) {
+                    m_fly &= ~(1u << k);
+                    if (ev == psim::EV_IMPACT) {
+                        misc = (misc & ~0x6000u) | (f.edge << 13);
+                        m_hit |= 1u << k;
+                    } else if (ev == psim::EV_SCATTER) {
+                        m_sct |= 1u << k;
+                    } else {
+                        m_fin |= 1u << k;
+                    }
+                }
+                slot_u(SF_MISC, k) = misc;
+            }
+        }
+    }
+    n_out = min(n_out, a.seg_cap);
+    if (lane == 0) { a.cnt_out[w] = n_out; }
+    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
+    tally_flush(a, acc_e, acc_f);
+}
+
 // First version: tiles of 32 phonons in lock step (every lane waits for the slowest phonon of its tile).
 __global__ void __launch_bounds__(kBlock, 2) drift_kernel_lockstep(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

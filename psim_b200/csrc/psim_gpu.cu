@@ -115,6 +115,8 @@ void free_pool(psim_gpu* h) {
     h->d_alive_hist = nullptr;
 }
 
+constexpr size_t kSlotBytesPerBlock = static_cast<size_t>(SF_COUNT) * 4 * 32 * 4 * kWarpsPerBlock;  // K = 4 slots per lane
+
 size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
     return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
 }
@@ -220,6 +222,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
@@ -251,8 +254,11 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
 
     // pool geometry: one segment per resident warp
     int blocks_per_sm = 0;
-    const int target = h->opt_kernel == 1 ? 2 : static_cast<int>(h->opt_blocks_per_sm);
-    if (h->opt_kernel == 1) {
+    const int target = h->opt_kernel == 1 ? 2 : (h->opt_kernel == 2 ? 4 : static_cast<int>(h->opt_blocks_per_sm));
+    if (h->opt_kernel == 2) {
+        const size_t dyn = kSlotBytesPerBlock + ((tally_smem_bytes(effective_steps_per_launch(h), h->P.n_sensors) + 127) & ~static_cast<size_t>(127));
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_slots<4>, kBlock, dyn));
+    } else if (h->opt_kernel == 1) {
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
     } else if (target == 4) {
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel<4>, kBlock, 0));
@@ -326,7 +332,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         a.tally_f = h->tally_f;
         const size_t smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
         const bool tallies_here = s1 + 1 > h->P.first_tally_step;  // any recorded measurement in this launch?
-        const size_t smem_cap = h->opt_kernel == 1 ? 100 * 1024 : h->opt_blocks_per_sm == 4 ? 48 * 1024 : (h->opt_blocks_per_sm == 3 ? 64 * 1024 : 100 * 1024);
+        const size_t smem_cap = h->opt_kernel == 2 ? 24 * 1024 : h->opt_kernel == 1 ? 100 * 1024 : h->opt_blocks_per_sm == 4 ? 48 * 1024 : (h->opt_blocks_per_sm == 3 ? 64 * 1024 : 100 * 1024);
         bool shared = h->opt_tally_shared < 0 ? (smem <= 32 * 1024) : (h->opt_tally_shared != 0 && smem <= smem_cap);
         if (!tallies_here) { shared = false; }
         a.tally_shared = shared ? 1u : 0u;
@@ -341,7 +347,10 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         }
         const dim3 grid(h->n_warps / kWarpsPerBlock);
         const size_t dyn = shared ? smem : 0;
-        if (h->opt_kernel == 1) {
+        if (h->opt_kernel == 2) {
+            const size_t slots = kSlotBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
+            drift_kernel_slots<4><<<grid, kBlock, slots, st>>>(a);
+        } else if (h->opt_kernel == 1) {
             drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
         } else if (h->opt_blocks_per_sm == 4) {
             drift_kernel<4><<<grid, kBlock, dyn, st>>>(a);
@@ -489,8 +498,8 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
         }
         h->opt_warps_per_sm = value;
     } else if (k == "kernel") {
-        if (h->have_sources || value < 0 || value > 1) {
-            h->err = "kernel must be 0 (lane refill) or 1 (lock step) and set before set_sources";
+        if (h->have_sources || value < 0 || value > 2) {
+            h->err = "kernel must be 0 (register scheduler), 1 (lock step) or 2 (shared-memory slots) and set before set_sources";
             return PSIM_E_STATE;
         }
         h->opt_kernel = value;

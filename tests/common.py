@@ -150,7 +150,7 @@ def assert_parity(z: np.ndarray, what: str, p3: float = 0.012, max_abs: float = 
     n = max(s["n"], 1)
     # few entries = the sensors of a 1-D bar: their fluctuations are almost perfectly correlated (one conserved heat
     # flux, one total energy), so a common offset of up to 2 sigma is an ordinary outcome there
-    mean_tol = max(4.0 / np.sqrt(n), 0.35) if n >= 50 else 2.0
+    mean_tol = max(4.0 / np.sqrt(n), 0.35) if n >= 200 else (1.0 if n >= 50 else 2.0)
     if n < 50:
         max_rms = max(max_rms, 2.3)
     msg = f"{what}: {s}"

@@ -71,7 +71,8 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
     ref = gpu_run_case(model, 5, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
     for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 1, "tally_shared": 1, "tally_aggregate": 1},
                  {"kernel": 1, "tally_shared": 0, "tally_aggregate": 1}, {"kernel": 0, "tally_shared": 1},
-                 {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "blocks_per_sm": 2}, {"kernel": 0, "blocks_per_sm": 4}):
+                 {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "blocks_per_sm": 2}, {"kernel": 0, "blocks_per_sm": 4},
+                 {"kernel": 2, "tally_shared": 1}, {"kernel": 2, "tally_shared": 0}, {"kernel": 2, "steps_per_launch": 5}):
         got = gpu_run_case(model, 5, options=opts, finish=False)
         assert np.array_equal(got["energy"], ref["energy"]), opts
         assert np.array_equal(got["fixed"], ref["fixed"]), opts
