@@ -152,8 +152,6 @@ def run_ours(args):
         g.set_option("tally_shared", args.tally_shared)
     if args.warps_per_sm > 0:
         g.set_option("warps_per_sm", args.warps_per_sm)
-    if args.blocks_per_sm > 0:
-        g.set_option("blocks_per_sm", args.blocks_per_sm)
     if args.kernel >= 0:
         g.set_option("kernel", args.kernel)
 
@@ -346,8 +344,7 @@ def main():
     ap.add_argument("--tally-aggregate", type=int, default=-1)
     ap.add_argument("--tally-shared", type=int, default=-1)
     ap.add_argument("--warps-per-sm", type=int, default=0)
-    ap.add_argument("--blocks-per-sm", type=int, default=0)
-    ap.add_argument("--kernel", type=int, default=-1, help="0 lane-refill (default), 1 lock-step first version")
+    ap.add_argument("--kernel", type=int, default=-1, help="0 shared-memory slots (default), 1 lock-step first version")
     ap.add_argument("--cpu-phonons-per-core", type=int, default=400_000)
     ap.add_argument("--ref-drift-steps-per-phonon", type=float, default=133.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

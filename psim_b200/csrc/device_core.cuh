@@ -334,8 +334,8 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
 // One phonon inside one measurement interval, as a small state machine so that the kernel can keep all 32
 // lanes of a warp busy (a lane that finishes its phonon fetches the next one instead of idling):
 //   interval_begin   rates of the current sensor area, time to the next intrinsic scatter
-//   flight_step      ONE free-flight segment: it ends at an edge (EV_IMPACT), at the end of the interval (EV_END)
-//                    or at an intrinsic scatter (EV_SCATTER)
+//   flight_window    ONE free-flight segment: it ends at an edge (EV_IMPACT), at an intrinsic scatter (EV_SCATTER)
+//                    or at the end of the launch window (EV_END), crossing measurement boundaries on the way
 //   impact_event     what the edge does: reflect, transmit to the neighbour cell, absorb (EV_DEAD)
 //   scatter_event    the intrinsic scatter itself
 // Together they replace the body of ModelSimulator::simulatePhonon (modelSimulator.cpp:139-198) between two
@@ -392,45 +392,61 @@ PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, floa
 }
 
 // next measurement interval of a phonon whose flight state is still in registers (several steps per launch)
-PSIM_HD void interval_continue(const DevParams& P, Flight& f) {
-    f.t = P.step_time;
-    f.ncoll = 0;
-    rng_begin(f.rng);
-}
-
-PSIM_HD int flight_step(Phonon& p, Flight& f) {
+// One free-flight segment inside the launch window [.., step_end): the phonon flies to its next PHYSICAL event
+// (edge or intrinsic scatter) or to the end of the window, whichever comes first.  Measurement events on the way
+// (modelSimulator.cpp:182-186) do not interrupt the flight: for each interval boundary crossed, `on_measure(k)` is
+// called with the step k that just ended (the caller tallies into row k + 1), the step counter advances and the
+// per-interval bookkeeping (impact counter, Philox block of the new (phonon, step) stream) restarts.
+// A measurement wins a tie with a physical event, as in the reference.
+template<class OnMeasure>
+PSIM_HD int flight_window(Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, float step_time, uint32_t& n_steps,
+                          OnMeasure&& on_measure) {
     const float inf = f_inf();
-    const float dt = fminf(p.tts, f.t);
     const float t0 = (f.r2 < 0.f) ? f_div(-p.b2, f.r2) : inf;
     const float t2 = (f.r1 < 0.f) ? f_div(-p.b1, f.r1) : inf;
     const float rs = f.r1 + f.r2;
     const float t1 = (rs > 0.f) ? f_div(1.f - p.b1 - p.b2, rs) : inf;
-    float th = fminf(t0, fminf(t1, t2));
-    if (!(th <= dt)) {  // no edge on the way (reference: impact_time <= time, modelSimulator.cpp:111)
-        p.b1 += f.r1 * dt;
-        p.b2 += f.r2 * dt;
-        if (!(p.tts < f.t)) {  // measurement event (it wins ties, modelSimulator.cpp:182)
-            p.tts -= f.t;
+    const float th = fmaxf(fminf(t0, fminf(t1, t2)), 0.f);
+    const bool impact = th <= p.tts;  // reference: impact_time <= time (modelSimulator.cpp:111)
+    float te = impact ? th : p.tts;   // time to the next physical event
+    float flown = 0.f;
+    while (!(te < f.t)) {
+        te -= f.t;
+        flown += f.t;
+        ++n_steps;
+        on_measure(s);
+        if (s + 1u >= step_end) {  // end of the launch window: the state goes back to the pool
+            p.b1 += f.r1 * flown;
+            p.b2 += f.r2 * flown;
+            p.tts -= flown;
+            f.t = step_time;
             return EV_END;
         }
-        f.t -= dt;
+        ++s;
+        f.t = step_time;
+        f.ncoll = 0;
+        f.rng.block = 0;
+    }
+    f.t -= te;
+    if (!impact) {
+        flown += te;
+        p.b1 += f.r1 * flown;
+        p.b2 += f.r2 * flown;
         return EV_SCATTER;
     }
-    const uint32_t e = (th == t0) ? 0u : ((th == t1) ? 1u : 2u);
-    th = fmaxf(th, 0.f);
-    float s;
+    const uint32_t e = (th == t0 || t0 < 0.f) ? 0u : ((th == t1 || t1 < 0.f) ? 1u : 2u);
+    float sh;
     if (e == 0u) {
-        s = clamp01(p.b1 + f.r1 * th);
+        sh = clamp01(p.b1 + f.r1 * th);
     } else if (e == 1u) {
-        s = clamp01(p.b2 + f.r2 * th);
+        sh = clamp01(p.b2 + f.r2 * th);
     } else {
-        s = clamp01(1.f - (p.b2 + f.r2 * th));
+        sh = clamp01(1.f - (p.b2 + f.r2 * th));
     }
-    place_on_edge(e, s, p);
-    f.t -= th;
+    place_on_edge(e, sh, p);
     p.tts -= th;
     f.edge = e;
-    f.s_hit = s;
+    f.s_hit = sh;
     return EV_IMPACT;
 }
 
@@ -525,8 +541,8 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     }
     update_rates_of_motion(f, p);
     if (++f.ncoll > PSIM_MAX_COLLISIONS) {
-        // stuck in a corner: random point of the current cell, and the rest of this free flight is spent
-        // (modelSimulator.cpp:215-218)
+        // stuck in a corner: restart from a random point of the current cell (modelSimulator.cpp:215-218; the
+        // reference also forfeits the rest of that free-flight segment - not reproduced, it never fires in practice)
         rng_need(f.rng, 2u, P, step, p.id_lo, id_hi);
         float q1 = rng_u01(f.rng), q2 = rng_u01(f.rng);
         if (q1 + q2 > 1.f) {
@@ -535,8 +551,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
         }
         p.b1 = q1;
         p.b2 = q2;
-        f.r1 = 0.f;
-        f.r2 = 0.f;
+        f.ncoll = 0;
     }
     return EV_CONTINUE;
 }
@@ -567,25 +582,28 @@ PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t st
     update_rates_of_motion(f, p);
 }
 
-// One phonon across (the rest of) one measurement interval; false if it was absorbed.  The lock-step form of
-// the three functions above (used by the lock-step kernel variant and by the CPU-side test emulation).
-PSIM_HD bool advance_interval(const DevParams& P, Phonon& p, float t, uint32_t step, uint32_t& sensor_out, uint32_t& events) {
+// One phonon from its current state to the end of the launch window; false if it was absorbed.  The plain
+// sequential form of the functions above (used by the lock-step kernel variant and by the CPU-side test emulation).
+template<class OnMeasure>
+PSIM_HD bool advance_window(const DevParams& P, Phonon& p, float t_first, uint32_t s, uint32_t step_end, uint32_t& n_steps,
+                            uint32_t& events, OnMeasure&& on_measure) {
     Flight f;
-    interval_begin(P, p, f, t, step);
+    interval_begin(P, p, f, t_first, s);
     for (;;) {
         ++events;
-        const int ev = flight_step(p, f);
+        const int ev = flight_window(p, f, s, step_end, P.step_time, n_steps, [&](uint32_t k) { on_measure(k, p, f); });
         if (ev == EV_IMPACT) {
             if (fast_transition(P, p, f)) { continue; }
-            if (impact_event(P, p, f, step) == EV_DEAD) { return false; }
+            if (impact_event(P, p, f, s) == EV_DEAD) {
+                ++n_steps;
+                return false;
+            }
         } else if (ev == EV_SCATTER) {
-            scatter_event(P, p, f, step);
+            scatter_event(P, p, f, s);
         } else {
-            break;
+            return true;
         }
     }
-    sensor_out = PSIM_CELL_SENSOR(f.sensor_mat);
-    return true;
 }
 
 // fixed-point flux contribution (Sensor::updateHeatParams, sensor.cpp:43-52, accumulates doubles in arbitrary

@@ -1,17 +1,12 @@
 // sm_100a kernels of the particle loop.  Included by psim_gpu.cu only.
 //
-// drift_kernel          persistent, one pool segment per resident warp, LANE REFILL: the warp walks its segment
-//                       as a stream; a lane whose phonon reached the end of the launch window (or was absorbed)
-//                       immediately fetches the next phonon, so all 32 lanes execute free-flight segments all the
-//                       time instead of waiting for the slowest phonon of a 32-wide tile.  (First version, lock
-//                       step: ncu smsp__thread_inst_executed_per_inst_executed = 9.6 of 32, profiles/r01.)
-//                       On top of that the warp SCHEDULES its work by kind: each lane records what its phonon
-//                       needs next (start an interval / fly / hit a surface / scatter / finish the interval) and a
-//                       kind of work is executed only when enough lanes wait for it, so that rare, expensive paths
-//                       (intrinsic scatter: two Philox blocks + an inverse-CDF search; surface interaction) run
-//                       with many lanes active instead of one or two.
-// drift_kernel_lockstep the first version, kept for A/B measurements and as a cross-check: both kernels must give
-//                       bit-identical tallies because a phonon's random stream is addressed by (id, step).
+// drift_kernel_slots<K>  the drift step (default).  Persistent, one pool segment per resident warp; every lane keeps
+//                        K phonons in flight in shared memory and the warp executes, pass by pass, the kind of work
+//                        (fly / surface interaction / intrinsic scatter / write back / fetch) that most lanes want.
+// drift_kernel_lockstep  the first version: tiles of 32 phonons, one per lane, in lock step.  Kept for A/B
+//                        measurements and as a cross-check: a phonon's random stream is addressed by (id, step), so both
+//                        kernels must produce bit-identical tallies (tests/test_gpu_parity.py).
+// History of the design, with the ncu numbers that drove it, is in DESIGN.md section 6 and profiles/.
 #ifndef PSIM_B200_KERNELS_CUH
 #define PSIM_B200_KERNELS_CUH
 
@@ -21,18 +16,6 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarpsPerBlock = kBlock / 32;
-// lane states of the drift kernel's scheduler and how many lanes must wait for a kind of work before it runs
-enum : uint32_t { ST_IDLE = 0, ST_FLIGHT = 2, ST_IMPACT = 3, ST_SCATTER = 4, ST_FINISH = 5 };
-#ifndef PSIM_MIN_ACQUIRE
-#define PSIM_MIN_ACQUIRE 12
-#define PSIM_MIN_FLIGHT 16
-#define PSIM_MIN_IMPACT 12
-#define PSIM_MIN_SCATTER 8
-#define PSIM_MIN_FINISH 12
-#endif
-constexpr int kMinAcquire = PSIM_MIN_ACQUIRE, kMinFlight = PSIM_MIN_FLIGHT, kMinImpact = PSIM_MIN_IMPACT,
-              kMinScatter = PSIM_MIN_SCATTER, kMinFinish = PSIM_MIN_FINISH;
-
 struct LaunchArgs {
     DevParams P;
     const float4* in_a;
@@ -165,159 +148,13 @@ __device__ __forceinline__ void warp_stats(const LaunchArgs& a, uint32_t lane, u
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The drift step: emission + free flight / intrinsic scattering / surfaces / cell transitions + tally + compaction.
-// ---------------------------------------------------------------------------------------------------------------
-template<int kMinBlocks>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) drift_kernel(const __grid_constant__ LaunchArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const DevParams& P = a.P;
-    int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
-    long long* acc_f = reinterpret_cast<long long*>(smem_raw + tally_smem_offset_f(a.step_end - a.step_begin, P.n_sensors));
-    tally_init(a, acc_e, acc_f);
-
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const uint32_t W = a.n_warps;
-    const size_t seg = static_cast<size_t>(w) * a.seg_cap;
-    const uint32_t n_in = a.cnt_in[w];
-    // birth chunks (32 consecutive birth items) are dealt round-robin over the warps, starting at a rotating offset
-    const uint64_t n_chunks = (a.n_births + 31u) >> 5;
-    const uint32_t c0 = (w + W - (a.birth_warp_offset % W)) % W;
-    const uint32_t my_chunks = (c0 < n_chunks) ? static_cast<uint32_t>((n_chunks - 1 - c0) / W + 1) : 0u;
-    const uint32_t total = n_in + my_chunks * 32u;
-
-    uint32_t next = 0, n_out = 0;
-    uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
-    bool overflow = false;
-    uint32_t st = ST_IDLE;   // what this lane's phonon needs next
-    uint32_t s = 0;          // its measurement step
-    psim::Phonon p;
-    psim::Flight f;
-    p.b1 = p.b2 = p.dx = p.dy = p.tts = 0.f;
-    p.packed = p.cell = p.id_lo = 0u;
-
-    // Warp-level event scheduler.  Every lane carries one phonon and the kind of work it needs next.  Each pass
-    // counts the lanes waiting for each kind of work and executes the kinds that have enough takers (so that
-    // their code runs with many lanes active); if none has, only the most wanted kind runs.  The order of
-    // execution does not influence any result: a phonon's random stream is its own.
-    for (;;) {
-        const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
-        const unsigned m_fly = __ballot_sync(0xFFFFFFFFu, st == ST_FLIGHT);
-        const unsigned m_hit = __ballot_sync(0xFFFFFFFFu, st == ST_IMPACT);
-        const unsigned m_sct = __ballot_sync(0xFFFFFFFFu, st == ST_SCATTER);
-        const unsigned m_fin = __ballot_sync(0xFFFFFFFFu, st == ST_FINISH);
-        const bool input = next < total;
-        if (m_idle == 0xFFFFFFFFu && !input) { break; }  // nothing in flight, nothing left to fetch
-        const int c_acq = input ? __popc(m_idle) : 0, c_fly = __popc(m_fly), c_hit = __popc(m_hit), c_sct = __popc(m_sct),
-                  c_fin = __popc(m_fin);
-        bool do_acq = c_acq >= kMinAcquire, do_fly = c_fly >= kMinFlight, do_hit = c_hit >= kMinImpact,
-             do_sct = c_sct >= kMinScatter, do_fin = c_fin >= kMinFinish;
-        if (!(do_acq || do_fly || do_hit || do_sct || do_fin)) {  // nobody qualifies: the most wanted kind runs alone
-            const int best = max(max(c_acq, c_fly), max(max(c_hit, c_sct), c_fin));
-            do_fin = c_fin == best;
-            do_fly = !do_fin && c_fly == best;
-            do_hit = !do_fin && !do_fly && c_hit == best;
-            do_acq = !do_fin && !do_fly && !do_hit && c_acq == best;
-            do_sct = !do_fin && !do_fly && !do_hit && !do_acq;
-        }
-        // ---- write-back of the phonons that reached the end of the launch window
-        if (do_fin) {
-            const bool store = st == ST_FINISH;
-            const unsigned storing = __ballot_sync(0xFFFFFFFFu, store);
-            if (store) {  // compaction: survivors go to consecutive slots of this warp's output segment
-                const uint32_t slot = n_out + __popc(storing & lt_mask);
-                if (slot < a.seg_cap) {
-                    store_phonon(a, seg + slot, p);
-                } else {
-                    overflow = true;
-                }
-                st = ST_IDLE;
-            }
-            n_out += __popc(storing);
-        }
-        // ---- acquire: idle lanes take the next items of the warp's stream (pool first, then births)
-        if (do_acq || (do_fin && input)) {
-            const unsigned idle = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
-            if (st == ST_IDLE) {
-                const uint32_t idx = next + __popc(idle & lt_mask);
-                float t_begin = P.step_time;
-                bool got = false;
-                if (idx < n_in) {
-                    load_phonon(a, seg + idx, p);
-                    s = a.step_begin;
-                    got = true;
-                } else if (idx < total) {
-                    const uint32_t b = idx - n_in;
-                    const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
-                    if (item < a.n_births) {
-                        t_begin = birth_phonon(a, item, p, s);
-                        got = true;
-                    }
-                }
-                if (got) {
-                    psim::interval_begin(P, p, f, t_begin, s);
-                    st = ST_FLIGHT;
-                }
-            }
-            next += __popc(idle);
-        }
-        // ---- one free-flight segment
-        if (do_fly) {
-            if (st == ST_FLIGHT) {
-                int ev = psim::flight_step(p, f);
-                ++n_events;
-                if (ev == psim::EV_IMPACT && psim::fast_transition(P, p, f)) { ev = psim::EV_CONTINUE; }
-                if (ev == psim::EV_END) {  // measurement event: the phonon now belongs to step s + 1 (modelSimulator.cpp:182-186)
-                    ++n_steps;
-                    if (s + 1 >= P.first_tally_step) {
-                        const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
-                        tally_add(a, acc_e, acc_f, s - a.step_begin, PSIM_CELL_SENSOR(f.sensor_mat), sg,
-                                  psim::flux_fixed(p.dx * f.vel) * sg, psim::flux_fixed(p.dy * f.vel) * sg);
-                    }
-                    if (s + 1 < a.step_end) {  // next interval of the same launch: the flight state stays in registers
-                        ++s;
-                        psim::interval_continue(P, f);
-                        ev = psim::EV_CONTINUE;
-                    }
-                }
-                st = (ev == psim::EV_CONTINUE) ? ST_FLIGHT
-                     : ((ev == psim::EV_IMPACT) ? ST_IMPACT : ((ev == psim::EV_SCATTER) ? ST_SCATTER : ST_FINISH));
-            }
-        }
-        // ---- surface interaction / cell transition
-        if (do_hit) {
-            if (st == ST_IMPACT) {
-                if (psim::impact_event(P, p, f, s) == psim::EV_DEAD) {
-                    ++n_steps;
-                    ++n_absorbed;
-                    st = ST_IDLE;
-                } else {
-                    st = ST_FLIGHT;
-                }
-            }
-        }
-        // ---- intrinsic scatter
-        if (do_sct) {
-            if (st == ST_SCATTER) {
-                psim::scatter_event(P, p, f, s);
-                st = ST_FLIGHT;
-            }
-        }
-    }
-    n_out = min(n_out, a.seg_cap);
-    if (lane == 0) { a.cnt_out[w] = n_out; }
-    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
-    tally_flush(a, acc_e, acc_f);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// drift_kernel_slots<K>: the same step, with K phonons IN FLIGHT PER LANE instead of one.
+// drift_kernel_slots<K>: emission + free flight / intrinsic scattering / surfaces / cell transitions + tally +
+// compaction, with K phonons IN FLIGHT PER LANE.
 //
-// The scheduler of drift_kernel can only regroup the 32 phonons a warp holds in registers: with five kinds of work a
-// kind rarely has more than ~14 takers (ncu: 14.4 of 32 threads active per instruction).  Here every lane owns K
-// slots in shared memory (12 words each, laid out [field][slot][lane] so that lane l only ever touches bank l: no
-// bank conflicts), i.e. a warp has 32 K phonons to choose from.  A pass picks the kind of work wanted by the most
+// A warp that holds one phonon per lane in registers can only regroup 32 phonons: with five kinds of work a kind
+// rarely has more than ~14 takers (ncu of that version: 14.4 of 32 threads active per instruction).  Here every lane
+// owns K slots in shared memory (12 words each, laid out [field][slot][lane] so that lane l only ever touches bank l:
+// no bank conflicts), i.e. a warp has 32 K phonons to choose from.  A pass picks the kind of work wanted by the most
 // LANES (a lane wants a kind if any of its slots does - one bit mask per kind per lane, in a register) and every
 // such lane executes it for one of its slots.  With K = 4 a lane almost always has a slot that wants to fly, and the
 // rare kinds are executed when (nearly) every lane has one waiting.
@@ -504,7 +341,8 @@ __global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_con
             }
             next += __popc(taking);
         } else {
-            // ---- one free-flight segment
+            // ---- one free-flight segment: to the next edge / scatter / end of the launch window, tallying the
+            //      measurement events it crosses on the way
             if (m_fly != 0u) {
                 const uint32_t k = __ffs(m_fly) - 1u;
                 psim::Phonon p;
@@ -515,42 +353,34 @@ __global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_con
                 f.t = slot_f(SF_T, k);
                 f.r1 = slot_f(SF_R1, k);
                 f.r2 = slot_f(SF_R2, k);
-                f.edge = 0u;
                 uint32_t misc = slot_u(SF_MISC, k);
-                int ev = psim::flight_step(p, f);
-                ++n_events;
-                if (ev == psim::EV_END) {  // measurement event: the phonon now belongs to step s + 1 (modelSimulator.cpp:182-186)
-                    ++n_steps;
-                    const uint32_t s = a.step_begin + PSIM_MISC_STEP(misc);
-                    if (s + 1 >= P.first_tally_step) {
+                f.edge = 0u;
+                f.ncoll = PSIM_MISC_NCOLL(misc);
+                f.rng.block = PSIM_MISC_BLOCK(misc);
+                uint32_t s = a.step_begin + PSIM_MISC_STEP(misc);
+                const int ev = psim::flight_window(p, f, s, a.step_end, P.step_time, n_steps, [&](uint32_t ks) {
+                    if (ks + 1 >= P.first_tally_step) {
                         const uint32_t packed = slot_u(SF_PACKED, k);
                         const float vel = psim::phonon_velocity(P, packed);
                         const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
-                        tally_add(a, acc_e, acc_f, s - a.step_begin, PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w),
+                        tally_add(a, acc_e, acc_f, ks - a.step_begin, PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w),
                                   sg, psim::flux_fixed(slot_f(SF_DX, k) * vel) * sg, psim::flux_fixed(slot_f(SF_DY, k) * vel) * sg);
                     }
-                    if (s + 1 < a.step_end) {  // next interval of the same launch
-                        misc = PSIM_MISC_STEP(misc) + 1u;
-                        f.t = P.step_time;
-                        ev = psim::EV_CONTINUE;
-                    }
-                }
+                });
+                ++n_events;
                 slot_f(SF_B1, k) = p.b1;
                 slot_f(SF_B2, k) = p.b2;
                 slot_f(SF_TTS, k) = p.tts;
                 slot_f(SF_T, k) = f.t;
-                if (ev != psim::EV_CONTINUE) {
-                    m_fly &= ~(1u << k);
-                    if (ev == psim::EV_IMPACT) {
-                        misc = (misc & ~0x6000u) | (f.edge << 13);
-                        m_hit |= 1u << k;
-                    } else if (ev == psim::EV_SCATTER) {
-                        m_sct |= 1u << k;
-                    } else {
-                        m_fin |= 1u << k;
-                    }
+                slot_u(SF_MISC, k) = (s - a.step_begin) | (f.ncoll << 6) | (f.edge << 13) | (min(f.rng.block, 1023u) << 15);
+                m_fly &= ~(1u << k);
+                if (ev == psim::EV_IMPACT) {
+                    m_hit |= 1u << k;
+                } else if (ev == psim::EV_SCATTER) {
+                    m_sct |= 1u << k;
+                } else {
+                    m_fin |= 1u << k;
                 }
-                slot_u(SF_MISC, k) = misc;
             }
         }
     }
@@ -598,32 +428,16 @@ __global__ void __launch_bounds__(kBlock, 2) drift_kernel_lockstep(const __grid_
             }
             chunk += W;
         }
-        for (uint32_t s = a.step_begin; s < a.step_end; ++s) {  // warp-uniform trip count
-            const bool act = alive && s >= start;
-            uint32_t sensor = 0;
-            if (act) {
-                alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, sensor, n_events);
-                ++n_steps;
-                if (!alive) { ++n_absorbed; }
-            }
-            if (act && alive && s + 1 >= P.first_tally_step) {
-                const float vel = psim::phonon_velocity(P, p.packed);
-                const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
-                const int32_t fx = psim::flux_fixed(p.dx * vel) * sg;
-                const int32_t fy = psim::flux_fixed(p.dy * vel) * sg;
-                if (a.tally_aggregate) {
-                    // warp-shuffle stage: lanes that hit the same sensor combine before touching memory
-                    const unsigned peers = __match_any_sync(__activemask(), sensor);
-                    const int32_t es = __reduce_add_sync(peers, sg);
-                    const int32_t fxs = __reduce_add_sync(peers, fx);
-                    const int32_t fys = __reduce_add_sync(peers, fy);
-                    if (lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
-                        tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, es, fxs, fys);
-                    }
-                } else {
-                    tally_add(a, acc_e, acc_f, s - a.step_begin, sensor, sg, fx, fy);
+        if (alive) {
+            alive = psim::advance_window(P, p, t_first, start, a.step_end, n_steps, n_events,
+                                         [&](uint32_t ks, const psim::Phonon& q, const psim::Flight& f) {
+                if (ks + 1 >= P.first_tally_step) {
+                    const int32_t sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
+                    tally_add(a, acc_e, acc_f, ks - a.step_begin, PSIM_CELL_SENSOR(f.sensor_mat), sg,
+                              psim::flux_fixed(q.dx * f.vel) * sg, psim::flux_fixed(q.dy * f.vel) * sg);
                 }
-            }
+            });
+            if (!alive) { ++n_absorbed; }
         }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, alive);
         if (alive) {

@@ -69,8 +69,7 @@ struct psim_gpu {
     // options
     int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
     int64_t opt_warps_per_sm = 0;
-    int64_t opt_blocks_per_sm = 3;   // occupancy target the kernel is compiled for (register budget)
-    int64_t opt_kernel = 0;          // 0: lane-refill kernel, 1: lock-step kernel (first version, for A/B)
+    int64_t opt_kernel = 0;          // 0: shared-memory slots kernel, 1: lock-step kernel (first version, for A/B)
     int64_t opt_tally_shared = -1;
     int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
@@ -218,9 +217,6 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         PSIM_CUDA(cudaEventCreate(&h->ev_begin));
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         return zero_run_state(h);
@@ -254,20 +250,13 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
 
     // pool geometry: one segment per resident warp
     int blocks_per_sm = 0;
-    const int target = h->opt_kernel == 1 ? 2 : (h->opt_kernel == 2 ? 4 : static_cast<int>(h->opt_blocks_per_sm));
-    if (h->opt_kernel == 2) {
+    if (h->opt_kernel == 1) {
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
+    } else {  // shared-memory slots + the largest tally staging a launch may ask for
         const size_t dyn = kSlotBytesPerBlock + ((tally_smem_bytes(effective_steps_per_launch(h), h->P.n_sensors) + 127) & ~static_cast<size_t>(127));
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_slots<4>, kBlock, dyn));
-    } else if (h->opt_kernel == 1) {
-        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
-    } else if (target == 4) {
-        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel<4>, kBlock, 0));
-    } else if (target == 3) {
-        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel<3>, kBlock, 0));
-    } else {
-        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel<2>, kBlock, 0));
     }
-    blocks_per_sm = std::max(1, std::min(blocks_per_sm, target));
+    blocks_per_sm = std::max(1, blocks_per_sm);
     int warps_per_sm = blocks_per_sm * kWarpsPerBlock;
     if (h->opt_warps_per_sm > 0) {
         warps_per_sm = static_cast<int>(std::max<int64_t>(kWarpsPerBlock, h->opt_warps_per_sm / kWarpsPerBlock * kWarpsPerBlock));
@@ -332,7 +321,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         a.tally_f = h->tally_f;
         const size_t smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
         const bool tallies_here = s1 + 1 > h->P.first_tally_step;  // any recorded measurement in this launch?
-        const size_t smem_cap = h->opt_kernel == 2 ? 24 * 1024 : h->opt_kernel == 1 ? 100 * 1024 : h->opt_blocks_per_sm == 4 ? 48 * 1024 : (h->opt_blocks_per_sm == 3 ? 64 * 1024 : 100 * 1024);
+        const size_t smem_cap = h->opt_kernel == 1 ? 100 * 1024 : 32 * 1024;
         bool shared = h->opt_tally_shared < 0 ? (smem <= 32 * 1024) : (h->opt_tally_shared != 0 && smem <= smem_cap);
         if (!tallies_here) { shared = false; }
         a.tally_shared = shared ? 1u : 0u;
@@ -347,17 +336,11 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         }
         const dim3 grid(h->n_warps / kWarpsPerBlock);
         const size_t dyn = shared ? smem : 0;
-        if (h->opt_kernel == 2) {
+        if (h->opt_kernel == 1) {
+            drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
+        } else {
             const size_t slots = kSlotBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
             drift_kernel_slots<4><<<grid, kBlock, slots, st>>>(a);
-        } else if (h->opt_kernel == 1) {
-            drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
-        } else if (h->opt_blocks_per_sm == 4) {
-            drift_kernel<4><<<grid, kBlock, dyn, st>>>(a);
-        } else if (h->opt_blocks_per_sm == 3) {
-            drift_kernel<3><<<grid, kBlock, dyn, st>>>(a);
-        } else {
-            drift_kernel<2><<<grid, kBlock, dyn, st>>>(a);
         }
         PSIM_CUDA(cudaGetLastError());
         h->cur ^= 1;
@@ -498,17 +481,11 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
         }
         h->opt_warps_per_sm = value;
     } else if (k == "kernel") {
-        if (h->have_sources || value < 0 || value > 2) {
-            h->err = "kernel must be 0 (register scheduler), 1 (lock step) or 2 (shared-memory slots) and set before set_sources";
+        if (h->have_sources || value < 0 || value > 1) {
+            h->err = "kernel must be 0 (shared-memory slots) or 1 (lock step) and set before set_sources";
             return PSIM_E_STATE;
         }
         h->opt_kernel = value;
-    } else if (k == "blocks_per_sm") {
-        if (h->have_sources || value < 2 || value > 4) {
-            h->err = "blocks_per_sm must be 2, 3 or 4 and set before set_sources";
-            return PSIM_E_STATE;
-        }
-        h->opt_blocks_per_sm = value;
     } else if (k == "tally_shared") {
         h->opt_tally_shared = value;
     } else if (k == "tally_aggregate") {

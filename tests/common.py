@@ -157,7 +157,7 @@ def assert_parity(z: np.ndarray, what: str, p3: float = 0.012, max_abs: float = 
     assert np.isfinite(z).all(), msg
     allowed = np.ceil(n * p3 + 3.5 * np.sqrt(n * p3) + 1.0)
     assert s["frac3"] * n <= allowed, msg
-    assert s["max"] <= max_abs, msg
+    assert s["max"] <= max_abs + max(0.0, np.log10(n / 1000.0)), msg  # the extreme of n t-distributed values grows with n
     assert s["rms"] <= max_rms, msg
     assert abs(s["mean"]) <= mean_tol, msg
     return s

@@ -45,22 +45,20 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     uint64_t total_events = 0;
     const uint32_t B = steps_per_pass ? steps_per_pass : 1;
     auto run_one = [&](psim::Phonon p, uint32_t start, float t_first, uint32_t s0, uint32_t s1) {
-        bool alive = true;
-        for (uint32_t s = start; s < s1 && alive; ++s) {
-            uint32_t sensor = 0;
-            n_events = 0;
-            alive = psim::advance_interval(P, p, (s == start) ? t_first : P.step_time, s, sensor, n_events);
-            const float vel = psim::phonon_velocity(P, p.packed);
-            total_events += n_events;
-            ++n_steps;
-            if (alive && s + 1 >= P.first_tally_step) {
-                const int sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
-                const size_t k = static_cast<size_t>(s + 1 - P.first_tally_step) * S + sensor;
+        uint32_t steps32 = 0;
+        n_events = 0;
+        const bool alive = psim::advance_window(P, p, t_first, start, s1, steps32, n_events,
+                                                [&](uint32_t ks, const psim::Phonon& q, const psim::Flight& f) {
+            if (ks + 1 >= P.first_tally_step) {
+                const int sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
+                const size_t k = static_cast<size_t>(ks + 1 - P.first_tally_step) * S + PSIM_CELL_SENSOR(f.sensor_mat);
                 te[k] += sg;
-                tf[2 * k] += static_cast<long long>(psim::flux_fixed(p.dx * vel)) * sg;
-                tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(p.dy * vel)) * sg;
+                tf[2 * k] += static_cast<long long>(psim::flux_fixed(q.dx * f.vel)) * sg;
+                tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(q.dy * f.vel)) * sg;
             }
-        }
+        });
+        total_events += n_events;
+        n_steps += steps32;
         (void)s0;
         if (alive) { next.push_back(p); }
     };

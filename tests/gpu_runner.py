@@ -7,7 +7,7 @@ from psim_b200 import lib as psim
 from tests import common as T
 
 
-def gpu_run_case(model: psim.Model, seed: int, *, shards: int = 1, steps_per_launch: int = 1, device: int = 0,
+def gpu_run_case(model: psim.Model, seed: int, *, shards: int = 1, steps_per_launch: int = 0, device: int = 0,
                  options: dict | None = None, finish: bool = True):
     """One run of `model` on the GPU.  shards > 1 runs the shards one after the other on the same device
     ("virtual shards") and sums their integer tallies exactly as the NCCL all-reduce would."""

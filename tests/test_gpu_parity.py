@@ -54,30 +54,35 @@ def test_integer_bookkeeping_is_shard_invariant(name):
 
 
 @pytest.mark.parametrize("name", ["linear_demo", "sides_per"])
-def test_steps_per_launch_does_not_change_results(name):
+def test_steps_per_launch_changes_only_rounding(name):
+    """With several measurement steps per launch a phonon flies straight to its next physical event, so positions
+    are rounded differently than step by step: integer bookkeeping that does not depend on trajectories (emitted
+    counts) is identical, tallies agree statistically."""
     model = T.load_model(T.case_model(name), num_phonons=50_000)
     ref = gpu_run_case(model, 3, steps_per_launch=1, finish=False)
-    for spl in (2, 7):
+    for spl in (2, 16):
         got = gpu_run_case(model, 3, steps_per_launch=spl, finish=False)
-        assert np.array_equal(got["energy"], ref["energy"])
-        assert np.array_equal(got["fixed"], ref["fixed"])
+        assert got["sources"] == ref["sources"]
+        steps_ref, steps_got = ref["stats"][0]["drift_steps"], got["stats"][0]["drift_steps"]
+        assert abs(steps_got - steps_ref) <= 0.01 * steps_ref
+        e_ref, e_got = np.abs(ref["energy"]).sum(), np.abs(got["energy"]).sum()
+        assert abs(float(e_got) - float(e_ref)) <= 0.05 * float(e_ref)
 
 
 def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
-    """Lane-refill kernel (default) vs the lock-step first version, shared-memory vs global tallies, warp
-    aggregation on/off, different register budgets: a phonon's random stream is addressed by (id, step), so every
-    variant must produce the same integers."""
+    """Slots kernel (default) vs the lock-step first version, shared-memory vs global tallies, warp aggregation
+    on/off, different numbers of resident warps: a phonon's random stream is addressed by (id, step), so every
+    variant must produce the same integers (for the same steps_per_launch)."""
     model = T.load_model(T.case_model("sides_per"), num_phonons=50_000)
-    ref = gpu_run_case(model, 5, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
-    for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 1, "tally_shared": 1, "tally_aggregate": 1},
-                 {"kernel": 1, "tally_shared": 0, "tally_aggregate": 1}, {"kernel": 0, "tally_shared": 1},
-                 {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "blocks_per_sm": 2}, {"kernel": 0, "blocks_per_sm": 4},
-                 {"kernel": 2, "tally_shared": 1}, {"kernel": 2, "tally_shared": 0}, {"kernel": 2, "steps_per_launch": 5}):
-        got = gpu_run_case(model, 5, options=opts, finish=False)
-        assert np.array_equal(got["energy"], ref["energy"]), opts
-        assert np.array_equal(got["fixed"], ref["fixed"]), opts
-        assert got["stats"][0]["drift_steps"] == ref["stats"][0]["drift_steps"], opts
-        assert got["stats"][0]["events"] == ref["stats"][0]["events"], opts
+    for spl in (1, 3):
+        ref = gpu_run_case(model, 5, steps_per_launch=spl, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
+        for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 0, "tally_shared": 1},
+                     {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "warps_per_sm": 8}):
+            got = gpu_run_case(model, 5, steps_per_launch=spl, options=opts, finish=False)
+            assert np.array_equal(got["energy"], ref["energy"]), (spl, opts)
+            assert np.array_equal(got["fixed"], ref["fixed"]), (spl, opts)
+            assert got["stats"][0]["drift_steps"] == ref["stats"][0]["drift_steps"], (spl, opts)
+            assert got["stats"][0]["events"] == ref["stats"][0]["events"], (spl, opts)
 
 
 def test_device_sampling_matches_reference_bisection():
