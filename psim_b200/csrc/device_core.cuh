@@ -394,12 +394,13 @@ PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, floa
 // next measurement interval of a phonon whose flight state is still in registers (several steps per launch)
 // One free-flight segment inside the launch window [.., step_end): the phonon flies to its next PHYSICAL event
 // (edge or intrinsic scatter) or to the end of the window, whichever comes first.  Measurement events on the way
-// (modelSimulator.cpp:182-186) do not interrupt the flight: for each interval boundary crossed, `on_measure(k)` is
-// called with the step k that just ended (the caller tallies into row k + 1), the step counter advances and the
-// per-interval bookkeeping (impact counter, Philox block of the new (phonon, step) stream) restarts.
+// (modelSimulator.cpp:182-186) do not interrupt the flight: for each RECORDED interval boundary crossed,
+// `on_measure(k)` is called with the step k that just ended (the caller tallies into row k + 1); the step counter
+// advances and the per-interval bookkeeping (impact counter, Philox block of the new (phonon, step) stream) restarts.
+// The callee of on_measure must not test first_tally_step again.
 // A measurement wins a tie with a physical event, as in the reference.
 template<class OnMeasure>
-PSIM_HD int flight_window(Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, float step_time, uint32_t& n_steps,
+PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, uint32_t& n_steps,
                           OnMeasure&& on_measure) {
     const float inf = f_inf();
     const float t0 = (f.r2 < 0.f) ? f_div(-p.b2, f.r2) : inf;
@@ -410,20 +411,28 @@ PSIM_HD int flight_window(Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, 
     const bool impact = th <= p.tts;  // reference: impact_time <= time (modelSimulator.cpp:111)
     float te = impact ? th : p.tts;   // time to the next physical event
     float flown = 0.f;
-    while (!(te < f.t)) {
-        te -= f.t;
-        flown += f.t;
-        ++n_steps;
-        on_measure(s);
-        if (s + 1u >= step_end) {  // end of the launch window: the state goes back to the pool
+    if (!(te < f.t)) {
+        // Boundaries of this window lie at f.t, f.t + dt, ... (step_end - s of them).  Those at or before the event
+        // are crossed first (a measurement wins a tie): n = min(left, floor((te - f.t) / dt) + 1), in closed form so
+        // that a phonon that is many intervals away from its next event costs no loop.
+        const uint32_t left = step_end - s;
+        const float q = fminf(floorf((te - f.t) * P.step_time_inv), 1.0e6f);
+        const uint32_t n = min(left, static_cast<uint32_t>(q) + 1u);
+        n_steps += n;
+        const uint32_t first = (P.first_tally_step > s + 1u) ? P.first_tally_step - 1u : s;  // first RECORDED one
+        for (uint32_t k = first; k < s + n; ++k) { on_measure(k); }
+        flown = f.t + static_cast<float>(n - 1u) * P.step_time;
+        if (n == left) {  // end of the launch window: the state goes back to the pool
             p.b1 += f.r1 * flown;
             p.b2 += f.r2 * flown;
             p.tts -= flown;
-            f.t = step_time;
+            s = step_end - 1u;
+            f.t = P.step_time;
             return EV_END;
         }
-        ++s;
-        f.t = step_time;
+        s += n;
+        te = fminf(fmaxf(te - flown, 0.f), P.step_time);  // time from the last boundary crossed to the event
+        f.t = P.step_time;
         f.ncoll = 0;
         f.rng.block = 0;
     }
@@ -432,6 +441,7 @@ PSIM_HD int flight_window(Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, 
         flown += te;
         p.b1 += f.r1 * flown;
         p.b2 += f.r2 * flown;
+        p.tts = 0.f;
         return EV_SCATTER;
     }
     const uint32_t e = (th == t0 || t0 < 0.f) ? 0u : ((th == t1 || t1 < 0.f) ? 1u : 2u);
@@ -591,7 +601,7 @@ PSIM_HD bool advance_window(const DevParams& P, Phonon& p, float t_first, uint32
     interval_begin(P, p, f, t_first, s);
     for (;;) {
         ++events;
-        const int ev = flight_window(p, f, s, step_end, P.step_time, n_steps, [&](uint32_t k) { on_measure(k, p, f); });
+        const int ev = flight_window(P, p, f, s, step_end, n_steps, [&](uint32_t k) { on_measure(k, p, f); });
         if (ev == EV_IMPACT) {
             if (fast_transition(P, p, f)) { continue; }
             if (impact_event(P, p, f, s) == EV_DEAD) {

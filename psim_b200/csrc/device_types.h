@@ -136,6 +136,7 @@ struct DevParams {
     uint32_t full_mode;        // t_eq == 0: bin-centre frequencies, no jitter (material.cpp:77-80)
     uint32_t phasor;           // phasor_sim: no intrinsic scattering (modelSimulator.cpp:189)
     float step_time;           // ns
+    float step_time_inv;
     double step_time_d;
     uint32_t seed_lo, seed_hi;
 };

@@ -265,6 +265,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
     P.full_mode = d.full_simulation ? 1u : 0u;
     P.phasor = d.phasor_sim ? 1u : 0u;
     P.step_time = static_cast<float>(step_time);
+    P.step_time_inv = static_cast<float>(1. / step_time);
     P.step_time_d = step_time;
     return 0;
 }

@@ -18,7 +18,7 @@ def one(args):
     model = T.load_model(T.case_model(name))
     model.prepare()
     sim_type = model.info.sim_type
-    r = T.emu_run(model, seed)
+    r = T.emu_run(model, seed, steps_per_pass=int(os.environ.get("SPP", "1")))
     model.set_tallies(r["energy"], r["flux"])
     model.finish_run(0)
     six, temps, fluxes = model.results(0)
