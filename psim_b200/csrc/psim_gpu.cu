@@ -120,10 +120,31 @@ size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
     return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
 }
 
+constexpr size_t kTallyStageBudget = 24 * 1024;  // per block; with the slot storage this keeps 3 blocks per SM
+constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
+
+// Measurement intervals a launch may cover (its "window").
 uint32_t effective_steps_per_launch(const psim_gpu* h) {
-    if (h->opt_steps_per_launch > 0) { return static_cast<uint32_t>(h->opt_steps_per_launch); }
-    const size_t per_step = tally_smem_bytes(1, h->P.n_sensors);
-    return static_cast<uint32_t>(std::min<size_t>(16, std::max<size_t>(1, (32 * 1024) / per_step)));
+    return h->opt_steps_per_launch > 0 ? static_cast<uint32_t>(h->opt_steps_per_launch) : 16u;
+}
+
+// How a launch that starts at step s0 tallies, and how far it may reach: windows without a recorded measurement need
+// no staging at all; otherwise the per-block staging must fit the budget, unless the model has so many sensors that
+// tallying straight into global memory is contention-free - with few sensors the window is shortened instead.
+void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1, bool& shared, size_t& smem) {
+    const uint32_t B = effective_steps_per_launch(h);
+    s1 = std::min(s0 + B, step_end);
+    shared = false;
+    smem = 0;
+    if (s1 + 1 <= h->P.first_tally_step) { return; }  // nothing recorded in this window
+    const size_t budget = h->opt_kernel == 1 ? 100 * 1024 : kTallyStageBudget;
+    const bool want_shared = h->opt_tally_shared != 0;
+    if (!want_shared) { return; }
+    if (h->opt_tally_shared < 0 && h->P.n_sensors >= kManySensors && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) { return; }
+    while (s1 > s0 + 1 && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) { --s1; }
+    smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
+    shared = smem <= budget;
+    if (!shared) { smem = 0; }
 }
 
 int zero_run_state(psim_gpu* h) {
@@ -253,7 +274,7 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
     if (h->opt_kernel == 1) {
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
     } else {  // shared-memory slots + the largest tally staging a launch may ask for
-        const size_t dyn = kSlotBytesPerBlock + ((tally_smem_bytes(effective_steps_per_launch(h), h->P.n_sensors) + 127) & ~static_cast<size_t>(127));
+        const size_t dyn = kSlotBytesPerBlock + kTallyStageBudget;
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_slots<4>, kBlock, dyn));
     }
     blocks_per_sm = std::max(1, blocks_per_sm);
@@ -294,9 +315,10 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
     }
     PSIM_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
-    const uint32_t B = effective_steps_per_launch(h);
-    for (uint32_t s0 = step_begin; s0 < step_end; s0 += B) {
-        const uint32_t s1 = std::min(s0 + B, step_end);
+    for (uint32_t s0 = step_begin, s1 = 0; s0 < step_end; s0 = s1) {
+        bool shared = false;
+        size_t smem = 0;
+        plan_launch(h, s0, step_end, s1, shared, smem);
         LaunchArgs a{};
         a.P = h->P;
         a.in_a = h->pool_a[h->cur];
@@ -319,11 +341,6 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         h->birth_offset = static_cast<uint32_t>((h->birth_offset + ((a.n_births + 31) >> 5)) % h->n_warps);
         a.tally_e = h->tally_e;
         a.tally_f = h->tally_f;
-        const size_t smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
-        const bool tallies_here = s1 + 1 > h->P.first_tally_step;  // any recorded measurement in this launch?
-        const size_t smem_cap = h->opt_kernel == 1 ? 100 * 1024 : 32 * 1024;
-        bool shared = h->opt_tally_shared < 0 ? (smem <= 32 * 1024) : (h->opt_tally_shared != 0 && smem <= smem_cap);
-        if (!tallies_here) { shared = false; }
         a.tally_shared = shared ? 1u : 0u;
         a.tally_aggregate = h->opt_tally_aggregate ? 1u : 0u;
         a.stats = h->d_stats;
