@@ -72,8 +72,10 @@ def test_steps_per_launch_changes_only_rounding(name):
 def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
     """Slots kernel (default) vs the lock-step first version, shared-memory vs global tallies, warp aggregation
     on/off, different numbers of resident warps: a phonon's random stream is addressed by (id, step), so every
-    variant must produce the same integers (for the same steps_per_launch)."""
-    model = T.load_model(T.case_model("sides_per"), num_phonons=50_000)
+    variant must produce the same integers (for the same launch windows: a periodic 20-sensor bar, whose tally
+    staging fits shared memory for every window length used here)."""
+    from psim_b200 import configs
+    model = T.load_model(configs.linear(num_phonons=50_000, sim_type=1, step_interval=4).to_dict())
     for spl in (1, 3):
         ref = gpu_run_case(model, 5, steps_per_launch=spl, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
         for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 0, "tally_shared": 1},
