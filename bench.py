@@ -113,7 +113,7 @@ def reference_cpu_run(model: dict, phonons_per_proc: int, procs: int, drift_step
     driver main) as `procs` independent processes (no TBB in this image, so std::execution::par is serial; phonons
     are independent, so P processes of n/P phonons are the reference's parallel path).  Wall = slowest process."""
     if not os.path.exists(REF_BIN):
-        return None
+        return oracle_cpu_run(model, phonons_per_proc * procs, procs, drift_steps_per_phonon)
     with tempfile.TemporaryDirectory() as tmp:
         path = configs.save(configs.with_settings(model, num_phonons=phonons_per_proc), os.path.join(tmp, "m.json"))
         t0 = time.perf_counter()
@@ -124,10 +124,25 @@ def reference_cpu_run(model: dict, phonons_per_proc: int, procs: int, drift_step
             return None
         inner = max(json.load(open(os.path.join(tmp, f"o{i}.meta.json")))["seconds"] for i in range(procs))
     total = phonons_per_proc * procs
-    out = {"phonons": total, "seconds": inner, "wall_with_load": wall}
+    out = {"phonons": total, "seconds": inner, "wall_with_load": wall, "kind": "reference"}
     if drift_steps_per_phonon:
         out["drift_steps_per_s"] = total * drift_steps_per_phonon / inner
     return out
+
+
+def oracle_cpu_run(model: dict, phonons: int, threads: int, drift_steps_per_phonon):
+    """Fallback when the reference binary is not on the box: the plain-C restatement under oracle/ (OpenMP)."""
+    try:
+        from oracle.model import OracleModel
+        om = OracleModel(configs.with_settings(model, num_phonons=phonons))
+        om.prepare()
+        t0 = time.perf_counter()
+        _, _, steps, _ = om.run(1, threads=threads)
+        secs = time.perf_counter() - t0
+    except Exception:
+        return None
+    return {"phonons": phonons, "seconds": secs, "wall_with_load": secs, "kind": "port",
+            "drift_steps_per_s": (phonons * drift_steps_per_phonon if drift_steps_per_phonon else steps) / secs}
 
 
 # --------------------------------------------------------------------------------------------------------- ours
@@ -304,7 +319,7 @@ def run_ours(args):
             cpu = reference_cpu_run(model_dict, args.cpu_phonons_per_core, cores, per_phonon)
             if cpu:
                 out["cpu_baseline"] = {"value": cpu["drift_steps_per_s"], "unit": "drift-steps/s", "cores": cores,
-                                       "kind": "reference",
+                                       "kind": cpu["kind"],
                                        "sample": f"{cores} processes x {args.cpu_phonons_per_core} phonons of the same model "
                                                  f"({cpu['seconds']:.1f} s); drift-steps per phonon taken from the GPU run"}
             else:
@@ -326,15 +341,14 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     model = workload_model(args.phonons * args.gpus)
     per_phonon = args.ref_drift_steps_per_phonon
-    if not os.path.exists(REF_BIN):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/psim_ref is not built on this box"}))
-        return
     vals, secs = [], []
+    kind = "reference"
     for it in range(args.warmup + args.steps):
         r = reference_cpu_run(model, args.cpu_phonons_per_core, cores, per_phonon)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "reference run failed"}))
             return
+        kind = r["kind"]
         if it >= args.warmup:
             vals.append(r["drift_steps_per_s"])
             secs.append(r["seconds"])
@@ -347,7 +361,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic 100-cell Si/Ge 2D structure (BASELINE.json configs[4]), steady-state deviational",
                    "phonons_per_step": args.cpu_phonons_per_core * cores},
-        "cpu_baseline": {"value": v, "unit": "drift-steps/s", "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "drift-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "drift-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
