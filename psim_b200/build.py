@@ -19,7 +19,7 @@ CLI = os.path.join(BIN_DIR, "psim")
 EMU = os.path.join(ROOT, "tests", "emu", "libpsim_emu.so")
 
 SOURCES = ["psim_gpu.cu", "flatten.cpp", "host/model.cpp", "host/host_api.cpp"]
-HEADERS = ["device_core.cuh", "device_types.h", "flatten.h", "host/model.h", "host/json.h",
+HEADERS = ["device_core.cuh", "kernels.cuh", "device_types.h", "flatten.h", "host/model.h", "host/json.h",
            "../../include/psim_b200.h", "../../include/psim_host.h"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -16,6 +16,14 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarpsPerBlock = kBlock / 32;
+// tuning of the slots kernel: phonons in flight per lane, CTAs per SM it is compiled for, tally staging budget (KB)
+#ifndef PSIM_SLOTS
+#define PSIM_SLOTS 4
+#define PSIM_SLOT_BLOCKS 3
+#define PSIM_STAGE_KB 24
+#endif
+constexpr int kSlots = PSIM_SLOTS;
+constexpr int kSlotBlocks = PSIM_SLOT_BLOCKS;
 struct LaunchArgs {
     DevParams P;
     const float4* in_a;
@@ -168,7 +176,7 @@ enum : int { SF_B1 = 0, SF_B2, SF_DX, SF_DY, SF_TTS, SF_PACKED, SF_CELL, SF_ID, 
 #define PSIM_MISC_BLOCK(m) (((m) >> 15) & 1023u)
 
 template<int K>
-__global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_constant__ LaunchArgs a) {
+__global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& P = a.P;
     const uint32_t nst = a.step_end - a.step_begin;
@@ -195,16 +203,17 @@ __global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_con
     uint32_t next = 0, n_out = 0;
     uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
     bool overflow = false;
-    uint32_t m_free = (1u << K) - 1u, m_fly = 0, m_hit = 0, m_sct = 0, m_fin = 0;  // which of my slots want what
+    uint32_t m_free = (1u << K) - 1u, m_fly = 0, m_hit = 0, m_wall = 0, m_sct = 0, m_fin = 0;  // which of my slots want what
 
     for (;;) {
         const bool input = next < total;
         const int c_fly = __popc(__ballot_sync(0xFFFFFFFFu, m_fly != 0u));
         const int c_hit = __popc(__ballot_sync(0xFFFFFFFFu, m_hit != 0u));
+        const int c_wall = __popc(__ballot_sync(0xFFFFFFFFu, m_wall != 0u));
         const int c_sct = __popc(__ballot_sync(0xFFFFFFFFu, m_sct != 0u));
         const int c_fin = __popc(__ballot_sync(0xFFFFFFFFu, m_fin != 0u));
         const int c_acq = input ? __popc(__ballot_sync(0xFFFFFFFFu, m_free != 0u)) : 0;
-        const int best = max(max(c_fly, c_hit), max(max(c_sct, c_fin), c_acq));
+        const int best = max(max(max(c_fly, c_hit), c_wall), max(max(c_sct, c_fin), c_acq));
         if (best == 0) { break; }
         // the kind wanted by the most lanes runs; ties go to the rarer kinds (they waited longest to get there)
         if (c_sct == best) {
@@ -236,10 +245,11 @@ __global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_con
                 m_sct &= ~(1u << k);
                 m_fly |= 1u << k;
             }
-        } else if (c_hit == best) {
-            // ---- surface interaction / cell transition
-            if (m_hit != 0u) {
-                const uint32_t k = __ffs(m_hit) - 1u;
+        } else if (c_wall == best) {
+            // ---- surface interaction, general case: wall (specular / diffuse), emitting surface, material interface,
+            //      transition into a sensor area with other rates, partial edges, stuck-phonon guard
+            if (m_wall != 0u) {
+                const uint32_t k = __ffs(m_wall) - 1u;
                 psim::Phonon p;
                 psim::Flight f;
                 p.b1 = slot_f(SF_B1, k);
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_con
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
                 const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
-                m_hit &= ~(1u << k);
+                m_wall &= ~(1u << k);
                 if (ev == psim::EV_DEAD) {
                     ++n_steps;
                     ++n_absorbed;
@@ -280,6 +290,38 @@ __global__ void __launch_bounds__(kBlock, 3) drift_kernel_slots(const __grid_con
                     slot_f(SF_R2, k) = f.r2;
                     slot_u(SF_MISC, k) = misc;
                     m_fly |= 1u << k;
+                }
+            }
+        } else if (c_hit == best) {
+            // ---- edge reached: the frequent case, a whole-edge transition into a cell with the same material and
+            //      rates, is done here; anything else is handed to the general kind above (no work lost: it only
+            //      changes which mask the slot sits in)
+            if (m_hit != 0u) {
+                const uint32_t k = __ffs(m_hit) - 1u;
+                psim::Phonon p;
+                psim::Flight f;
+                p.b1 = slot_f(SF_B1, k);
+                p.b2 = slot_f(SF_B2, k);
+                p.dx = slot_f(SF_DX, k);
+                p.dy = slot_f(SF_DY, k);
+                p.cell = slot_u(SF_CELL, k);
+                const uint32_t misc = slot_u(SF_MISC, k);
+                f.edge = PSIM_MISC_EDGE(misc);
+                f.s_hit = (f.edge == 0u) ? p.b1 : ((f.edge == 1u) ? p.b2 : 1.f - p.b2);
+                f.ncoll = PSIM_MISC_NCOLL(misc);
+                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.vel = psim::phonon_velocity(P, slot_u(SF_PACKED, k));
+                m_hit &= ~(1u << k);
+                if (psim::fast_transition(P, p, f)) {
+                    slot_f(SF_B1, k) = p.b1;
+                    slot_f(SF_B2, k) = p.b2;
+                    slot_u(SF_CELL, k) = p.cell;
+                    slot_f(SF_R1, k) = f.r1;
+                    slot_f(SF_R2, k) = f.r2;
+                    slot_u(SF_MISC, k) = (misc & ~0x1FC0u) | (min(f.ncoll, 127u) << 6);
+                    m_fly |= 1u << k;
+                } else {
+                    m_wall |= 1u << k;
                 }
             }
         } else if (c_fin == best) {

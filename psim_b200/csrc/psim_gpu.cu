@@ -114,13 +114,13 @@ void free_pool(psim_gpu* h) {
     h->d_alive_hist = nullptr;
 }
 
-constexpr size_t kSlotBytesPerBlock = static_cast<size_t>(SF_COUNT) * 4 * 32 * 4 * kWarpsPerBlock;  // K = 4 slots per lane
+constexpr size_t kSlotBytesPerBlock = static_cast<size_t>(SF_COUNT) * kSlots * 32 * 4 * kWarpsPerBlock;
 
 size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
     return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
 }
 
-constexpr size_t kTallyStageBudget = 24 * 1024;  // per block; with the slot storage this keeps 3 blocks per SM
+constexpr size_t kTallyStageBudget = PSIM_STAGE_KB * 1024;  // per block; with the slot storage this keeps kSlotBlocks blocks per SM
 constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
 
 // Measurement intervals a launch may cover (its "window").
@@ -239,7 +239,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaEventCreate(&h->ev_begin));
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
@@ -275,7 +275,7 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
     } else {  // shared-memory slots + the largest tally staging a launch may ask for
         const size_t dyn = kSlotBytesPerBlock + kTallyStageBudget;
-        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_slots<4>, kBlock, dyn));
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_slots<kSlots>, kBlock, dyn));
     }
     blocks_per_sm = std::max(1, blocks_per_sm);
     int warps_per_sm = blocks_per_sm * kWarpsPerBlock;
@@ -357,7 +357,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
             drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
         } else {
             const size_t slots = kSlotBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
-            drift_kernel_slots<4><<<grid, kBlock, slots, st>>>(a);
+            drift_kernel_slots<kSlots><<<grid, kBlock, slots, st>>>(a);
         }
         PSIM_CUDA(cudaGetLastError());
         h->cur ^= 1;
