@@ -168,12 +168,13 @@ __device__ __forceinline__ void warp_stats(const LaunchArgs& a, uint32_t lane, u
 // rare kinds are executed when (nearly) every lane has one waiting.
 // ---------------------------------------------------------------------------------------------------------------
 enum : int { SF_B1 = 0, SF_B2, SF_DX, SF_DY, SF_TTS, SF_PACKED, SF_CELL, SF_ID, SF_T, SF_R1, SF_R2, SF_MISC, SF_COUNT };
-// SF_MISC: [5:0] measurement step relative to the launch, [12:6] impacts since the last scatter, [14:13] edge hit,
-//          [24:15] next Philox block of this (phonon, step) stream
-#define PSIM_MISC_STEP(m) ((m)&63u)
-#define PSIM_MISC_NCOLL(m) (((m) >> 6) & 127u)
-#define PSIM_MISC_EDGE(m) (((m) >> 13) & 3u)
-#define PSIM_MISC_BLOCK(m) (((m) >> 15) & 1023u)
+// SF_MISC: [9:0] measurement step relative to the launch, [16:10] impacts since the last scatter, [18:17] edge hit,
+//          [28:19] next Philox block of this (phonon, step) stream
+#define PSIM_MISC_STEP(m) ((m)&1023u)
+#define PSIM_MISC_NCOLL(m) (((m) >> 10) & 127u)
+#define PSIM_MISC_EDGE(m) (((m) >> 17) & 3u)
+#define PSIM_MISC_BLOCK(m) (((m) >> 19) & 1023u)
+#define PSIM_MISC_PACK(step, ncoll, edge, block) ((step) | (min((ncoll), 127u) << 10) | ((edge) << 17) | (min((block), 1023u) << 19))
 
 template<int K>
 __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const __grid_constant__ LaunchArgs a) {
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
                 psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
-                misc = (misc & 0x603Fu) | (min(f.rng.block, 1023u) << 15);  // impacts since the last scatter := 0
+                misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
                 slot_f(SF_DX, k) = p.dx;
                 slot_f(SF_DY, k) = p.dy;
                 slot_u(SF_PACKED, k) = p.packed;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     ++n_absorbed;
                     m_free |= 1u << k;
                 } else {
-                    misc = (misc & 0x603Fu) | (min(f.ncoll, 127u) << 6) | (min(f.rng.block, 1023u) << 15);
+                    misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), f.ncoll, PSIM_MISC_EDGE(misc), f.rng.block);
                     slot_f(SF_B1, k) = p.b1;
                     slot_f(SF_B2, k) = p.b2;
                     slot_f(SF_DX, k) = p.dx;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     slot_u(SF_CELL, k) = p.cell;
                     slot_f(SF_R1, k) = f.r1;
                     slot_f(SF_R2, k) = f.r2;
-                    slot_u(SF_MISC, k) = (misc & ~0x1FC0u) | (min(f.ncoll, 127u) << 6);
+                    slot_u(SF_MISC, k) = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), f.ncoll, PSIM_MISC_EDGE(misc), PSIM_MISC_BLOCK(misc));
                     m_fly |= 1u << k;
                 } else {
                     m_wall |= 1u << k;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 slot_f(SF_B2, k) = p.b2;
                 slot_f(SF_TTS, k) = p.tts;
                 slot_f(SF_T, k) = f.t;
-                slot_u(SF_MISC, k) = (s - a.step_begin) | (f.ncoll << 6) | (f.edge << 13) | (min(f.rng.block, 1023u) << 15);
+                slot_u(SF_MISC, k) = PSIM_MISC_PACK(s - a.step_begin, f.ncoll, f.edge, f.rng.block);
                 m_fly &= ~(1u << k);
                 if (ev == psim::EV_IMPACT) {
                     m_hit |= 1u << k;

@@ -121,6 +121,7 @@ size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
 }
 
 constexpr size_t kTallyStageBudget = PSIM_STAGE_KB * 1024;  // per block; with the slot storage this keeps kSlotBlocks blocks per SM
+constexpr uint32_t kLongWindow = 1023;           // steps per launch while nothing is recorded (10 bits of step in the slot word)
 constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
 
 // Measurement intervals a launch may cover (its "window").
@@ -133,9 +134,15 @@ uint32_t effective_steps_per_launch(const psim_gpu* h) {
 // tallying straight into global memory is contention-free - with few sensors the window is shortened instead.
 void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1, bool& shared, size_t& smem) {
     const uint32_t B = effective_steps_per_launch(h);
-    s1 = std::min(s0 + B, step_end);
     shared = false;
     smem = 0;
+    if (h->opt_steps_per_launch <= 0 && s0 + 2 <= h->P.first_tally_step) {
+        // automatic mode, nothing recorded yet (steady state: the first 90 % of the steps): long windows, cut at the
+        // first recorded measurement
+        s1 = std::min(std::min(s0 + kLongWindow, step_end), h->P.first_tally_step - 1);
+        if (s1 > s0) { return; }
+    }
+    s1 = std::min(s0 + B, step_end);
     if (s1 + 1 <= h->P.first_tally_step) { return; }  // nothing recorded in this window
     const size_t budget = h->opt_kernel == 1 ? 100 * 1024 : kTallyStageBudget;
     const bool want_shared = h->opt_tally_shared != 0;
@@ -486,8 +493,8 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
     if (!h || !name) { return PSIM_E_INVALID; }
     const std::string k(name);
     if (k == "steps_per_launch") {
-        if (value < 0 || value > 64) {
-            h->err = "steps_per_launch must be in [0, 64] (0 = automatic)";
+        if (value < 0 || value > 1023) {
+            h->err = "steps_per_launch must be in [0, 1023] (0 = automatic)";
             return PSIM_E_INVALID;
         }
         h->opt_steps_per_launch = value;
