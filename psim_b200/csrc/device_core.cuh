@@ -394,10 +394,10 @@ PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, floa
 // next measurement interval of a phonon whose flight state is still in registers (several steps per launch)
 // One free-flight segment inside the launch window [.., step_end): the phonon flies to its next PHYSICAL event
 // (edge or intrinsic scatter) or to the end of the window, whichever comes first.  Measurement events on the way
-// (modelSimulator.cpp:182-186) do not interrupt the flight: for each RECORDED interval boundary crossed,
-// `on_measure(k)` is called with the step k that just ended (the caller tallies into row k + 1); the step counter
+// (modelSimulator.cpp:182-186) do not interrupt the flight: `on_measure(k0, k1)` is called once with the range
+// [k0, k1) of RECORDED steps that ended during this segment (the caller tallies the phonon into rows k + 1 - first
+// recorded step, k0 <= k < k1; its direction, velocity and cell are the same for all of them); the step counter
 // advances and the per-interval bookkeeping (impact counter, Philox block of the new (phonon, step) stream) restarts.
-// The callee of on_measure must not test first_tally_step again.
 // A measurement wins a tie with a physical event, as in the reference.
 template<class OnMeasure>
 PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, uint32_t& n_steps,
@@ -420,7 +420,7 @@ PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s,
         const uint32_t n = min(left, static_cast<uint32_t>(q) + 1u);
         n_steps += n;
         const uint32_t first = (P.first_tally_step > s + 1u) ? P.first_tally_step - 1u : s;  // first RECORDED one
-        for (uint32_t k = first; k < s + n; ++k) { on_measure(k); }
+        if (first < s + n) { on_measure(first, s + n); }
         flown = f.t + static_cast<float>(n - 1u) * P.step_time;
         if (n == left) {  // end of the launch window: the state goes back to the pool
             p.b1 += f.r1 * flown;
@@ -601,7 +601,7 @@ PSIM_HD bool advance_window(const DevParams& P, Phonon& p, float t_first, uint32
     interval_begin(P, p, f, t_first, s);
     for (;;) {
         ++events;
-        const int ev = flight_window(P, p, f, s, step_end, n_steps, [&](uint32_t k) { on_measure(k, p, f); });
+        const int ev = flight_window(P, p, f, s, step_end, n_steps, [&](uint32_t k0, uint32_t k1) { on_measure(k0, k1, p, f); });
         if (ev == EV_IMPACT) {
             if (fast_transition(P, p, f)) { continue; }
             if (impact_event(P, p, f, s) == EV_DEAD) {

@@ -401,12 +401,13 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 f.ncoll = PSIM_MISC_NCOLL(misc);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 uint32_t s = a.step_begin + PSIM_MISC_STEP(misc);
-                const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t ks) {
+                const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
                     const uint32_t packed = slot_u(SF_PACKED, k);
                     const float vel = psim::phonon_velocity(P, packed);
                     const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
-                    tally_add(a, acc_e, acc_f, ks - a.step_begin, PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w),
-                              sg, psim::flux_fixed(slot_f(SF_DX, k) * vel) * sg, psim::flux_fixed(slot_f(SF_DY, k) * vel) * sg);
+                    const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
+                    const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k) * vel) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k) * vel) * sg;
+                    for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, sg, fx, fy); }
                 });
                 ++n_events;
                 slot_f(SF_B1, k) = p.b1;
@@ -471,10 +472,12 @@ __global__ void __launch_bounds__(kBlock, 2) drift_kernel_lockstep(const __grid_
         }
         if (alive) {
             alive = psim::advance_window(P, p, t_first, start, a.step_end, n_steps, n_events,
-                                         [&](uint32_t ks, const psim::Phonon& q, const psim::Flight& f) {
+                                         [&](uint32_t k0, uint32_t k1, const psim::Phonon& q, const psim::Flight& f) {
                 const int32_t sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
-                tally_add(a, acc_e, acc_f, ks - a.step_begin, PSIM_CELL_SENSOR(f.sensor_mat), sg,
-                          psim::flux_fixed(q.dx * f.vel) * sg, psim::flux_fixed(q.dy * f.vel) * sg);
+                const int32_t fx = psim::flux_fixed(q.dx * f.vel) * sg, fy = psim::flux_fixed(q.dy * f.vel) * sg;
+                for (uint32_t ks = k0; ks < k1; ++ks) {
+                    tally_add(a, acc_e, acc_f, ks - a.step_begin, PSIM_CELL_SENSOR(f.sensor_mat), sg, fx, fy);
+                }
             });
             if (!alive) { ++n_absorbed; }
         }

@@ -122,6 +122,7 @@ size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
 
 constexpr size_t kTallyStageBudget = PSIM_STAGE_KB * 1024;  // per block; with the slot storage this keeps kSlotBlocks blocks per SM
 constexpr uint32_t kLongWindow = 1023;           // steps per launch while nothing is recorded (10 bits of step in the slot word)
+constexpr uint32_t kGlobalTallyWindow = 128;     // steps per launch when recorded tallies go straight to global memory
 constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
 
 // Measurement intervals a launch may cover (its "window").
@@ -147,7 +148,10 @@ void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1
     const size_t budget = h->opt_kernel == 1 ? 100 * 1024 : kTallyStageBudget;
     const bool want_shared = h->opt_tally_shared != 0;
     if (!want_shared) { return; }
-    if (h->opt_tally_shared < 0 && h->P.n_sensors >= kManySensors && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) { return; }
+    if (h->opt_tally_shared < 0 && h->P.n_sensors >= kManySensors && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) {
+        if (h->opt_steps_per_launch <= 0) { s1 = std::min(s0 + kGlobalTallyWindow, step_end); }  // no staging: nothing limits the window
+        return;
+    }
     while (s1 > s0 + 1 && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) { --s1; }
     smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
     shared = smem <= budget;

@@ -48,12 +48,14 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         uint32_t steps32 = 0;
         n_events = 0;
         const bool alive = psim::advance_window(P, p, t_first, start, s1, steps32, n_events,
-                                                [&](uint32_t ks, const psim::Phonon& q, const psim::Flight& f) {
+                                                [&](uint32_t k0, uint32_t k1, const psim::Phonon& q, const psim::Flight& f) {
             const int sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
-            const size_t k = static_cast<size_t>(ks + 1 - P.first_tally_step) * S + PSIM_CELL_SENSOR(f.sensor_mat);
-            te[k] += sg;
-            tf[2 * k] += static_cast<long long>(psim::flux_fixed(q.dx * f.vel)) * sg;
-            tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(q.dy * f.vel)) * sg;
+            for (uint32_t ks = k0; ks < k1; ++ks) {
+                const size_t k = static_cast<size_t>(ks + 1 - P.first_tally_step) * S + PSIM_CELL_SENSOR(f.sensor_mat);
+                te[k] += sg;
+                tf[2 * k] += static_cast<long long>(psim::flux_fixed(q.dx * f.vel)) * sg;
+                tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(q.dy * f.vel)) * sg;
+            }
         });
         total_events += n_events;
         n_steps += steps32;
