@@ -42,12 +42,14 @@ def workload_model(num_phonons: int) -> dict:
     return configs.si_ge_grid(num_phonons=num_phonons).to_dict()
 
 
-def ncu_traffic_per_launch(per_gpu: int, steps_per_launch: int):
+def ncu_traffic_per_launch(per_gpu: int, steps_per_launch: int, auto_windows: bool):
     """DRAM bytes per drift-kernel launch from the committed ncu --set full capture (profiles/), if it was taken on this
     configuration; None otherwise."""
     path = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
     try:
         d = json.load(open(path))
+        if d["phonons_per_gpu"] == per_gpu and auto_windows:
+            return d["default_job"]["dram_bytes_per_launch_avg"]
         if d["phonons_per_gpu"] == per_gpu and d["steps_per_launch"] == steps_per_launch:
             return d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"]
     except Exception:
@@ -305,7 +307,7 @@ def run_ours(args):
                        "sharding": f"phonon id mod {world}", "l2": "inputs larger than L2 (live pool >> 126 MB, streamed every launch)",
                        "rng": "Philox4x32-10 keyed by (seed, phonon id, step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(per_gpu, last_stats["steps_per_launch"]),
+                         "traffic": ncu_traffic_per_launch(per_gpu, last_stats["steps_per_launch"], args.steps_per_launch == 0),
                          "peak_source": peak_src, "kernel": "drift_kernel_slots<4>",
                          "algorithmic_bytes_per_drift_step": ALGO_BYTES_PER_DRIFT_STEP,
                          "algorithmic_bytes_per_launch": float(np.mean(drift)) * ALGO_BYTES_PER_DRIFT_STEP / launches_per_job,
