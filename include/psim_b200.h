@@ -188,6 +188,12 @@ int psim_gpu_probe_sample(psim_gpu* h, uint32_t table, const float* u1, const fl
 /* rates: [n][3] = (N, U, I) in 1/s for sensor `sensor` (Material::relaxRates, material.cpp:54-57). */
 int psim_gpu_probe_rates(psim_gpu* h, uint32_t sensor, const double* omega, const uint32_t* ta, size_t n,
                          double* rates);
+/* One free flight + specular reflection, the geometry core of ModelSimulator::nextImpact (modelSimulator.cpp:87-122,
+ * Line::getIntersection geometry.cpp:104-138) and Surface::boundaryHandlePhonon (surface.cpp:32-44): for phonon i
+ * in cell cell[i] at barycentric position (b1, b2) moving with velocity (vx, vy) nm/ns, the device returns the edge
+ * it reaches first, the time, the barycentric position of the hit and the mirrored direction about that edge's
+ * inward normal.  in: [n][4] = b1, b2, vx, vy; out: [n][6] = edge, time, b1, b2, dx', dy' (direction of unit input). */
+int psim_gpu_probe_flight(psim_gpu* h, const uint32_t* cell, const float* in, size_t n, float* out);
 
 #ifdef __cplusplus
 }

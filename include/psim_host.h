@@ -68,6 +68,12 @@ int psim_model_next_run(psim_model* m);  /* reset(true), model.cpp:178-180 */
  * when verbose != 0).  seed: run r uses seed + r.  steps_per_launch <= 0 keeps the library default. */
 int psim_model_run(psim_model* m, int device, uint64_t seed, int steps_per_launch, int verbose, psim_stats* stats);
 
+/* The same over several GPUs of this process: device d simulates the phonon ids == d (mod n_devices), one host thread
+ * per device, and the integer tallies are summed on the host (the payload is recorded_steps x sensors x 20 bytes).
+ * The result is bit-identical to the one-GPU run with the same seed.  stats: summed over the devices (kernel_ms: max). */
+int psim_model_run_devices(psim_model* m, const int* devices, int n_devices, uint64_t seed, int steps_per_launch,
+                           int verbose, psim_stats* stats);
+
 /* Results of run `run_id` (sensors sorted by id): six[S][6] = T, stdT, qx, std qx, qy, std qy;
  * temps[S][R]; fluxes[S][R][2]; any pointer may be NULL.  run_id == UINT64_MAX: average over runs. */
 int psim_model_results(const psim_model* m, uint64_t run_id, double* six, double* temps, double* fluxes);

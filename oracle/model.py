@@ -405,5 +405,17 @@ def load_sim():
         lib.oracle_run.argtypes = ([C.c_int, vp, vp, vp, vp] + [C.c_int] + [vp] * 8 + [C.c_int, vp, vp, vp, vp] +
                                    [C.c_int, vp, vp, C.c_int, vp] + [C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_int] +
                                    [C.c_int, vp, C.c_uint64, C.c_int] + [vp, vp, vp])
+        lib.oracle_flight.restype = C.c_int
+        lib.oracle_flight.argtypes = [vp, vp, C.c_double, vp]
         _sim = lib
     return _sim
+
+
+def oracle_flight(tri, state, horizon=1.0e4):
+    """Reference geometry of one free flight + specular reflection (oracle/sim.c:oracle_flight)."""
+    lib = load_sim()
+    tri = np.ascontiguousarray(tri, dtype=np.float64)
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    out = np.zeros(6)
+    lib.oracle_flight(tri.ctypes.data_as(C.c_void_p), state.ctypes.data_as(C.c_void_p), float(horizon), out.ctypes.data_as(C.c_void_p))
+    return out

@@ -445,6 +445,51 @@ static void build_phonon(const model_t* m, const source_t* s, rng_t* r, phonon_t
     }
 }
 
+/* Test hook: the reference's geometry for ONE free flight in a wall-only triangle - nextImpact (modelSimulator.cpp:
+ * 87-122) with Line::getIntersection (geometry.cpp:104-138), then the specular branch of boundaryHandlePhonon
+ * (surface.cpp:32-44) about the edge's inward normal (Line::normal, geometry.cpp:97-100).
+ * tri[6] = x1 y1 x2 y2 x3 y3; state = px py vx vy (nm, nm/ns); out = edge, time, x, y, dx', dy' (unit input direction). */
+int oracle_flight(const double* tri, const double* state, double horizon, double* out) {
+    cell_t c;
+    memset(&c, 0, sizeof(c));
+    for (int k = 0; k < 3; ++k) { c.v[k].x = tri[2 * k]; c.v[k].y = tri[2 * k + 1]; }
+    const double cw = (c.v[1].x - c.v[0].x) * (c.v[1].y + c.v[0].y) + (c.v[2].x - c.v[1].x) * (c.v[2].y + c.v[1].y) +
+                      (c.v[0].x - c.v[2].x) * (c.v[0].y + c.v[2].y);   /* Triangle::isClockwise, geometry.cpp:217-222 */
+    const int ns = cw >= 0. ? 1 : -1;
+    for (int k = 0; k < 3; ++k) {
+        surf_t* s = &c.main[k];
+        s->line = make_line(c.v[k], c.v[(k + 1) % 3]);
+        s->nx = ns * (s->line.p2.y - s->line.p1.y) / s->line.length;
+        s->ny = -ns * (s->line.p2.x - s->line.p1.x) / s->line.length;
+        s->spec = 1.;
+    }
+    const double speed = sqrt(state[2] * state[2] + state[3] * state[3]);
+    const pt start = { state[0], state[1] }, end = { state[0] + horizon * state[2], state[1] + horizon * state[3] };
+    const line_t path = make_line(start, end);
+    double time = horizon;
+    int edge = -1;
+    pt impact = { 0., 0. };
+    for (int k = 0; k < 3; ++k) {
+        pt poi;
+        if (line_intersection(&c.main[k].line, &path, &poi) && !pt_eq(poi, start)) {
+            const double tx = (state[2] > VELOCITY_EPS || state[2] < -VELOCITY_EPS) ? (poi.x - start.x) / state[2] : time;
+            const double ty = (state[3] > VELOCITY_EPS || state[3] < -VELOCITY_EPS) ? (poi.y - start.y) / state[3] : time;
+            const double ti = (tx <= ty) ? tx : ty;
+            if (ti <= time) { time = ti; impact = poi; edge = k; }
+        }
+    }
+    out[0] = edge; out[1] = time; out[2] = impact.x; out[3] = impact.y;
+    double dx = state[2] / speed, dy = state[3] / speed;
+    if (edge >= 0) {
+        const surf_t* s = &c.main[edge];
+        const double ndx = -dx * s->nx - dy * s->ny, ndy = -dx * s->ny + dy * s->nx;
+        dx = s->nx * ndx - s->ny * ndy;
+        dy = s->ny * ndx + s->nx * ndy;
+    }
+    out[4] = dx; out[5] = dy;
+    return 0;
+}
+
 /* Entry point.  Flat arrays in, tallies out; everything is copied into the structs above first.
  *   cell_xy[C][6], cell_sensor[C], cell_spec[C], cell_norm_sign[C]
  *   sub_*[n_subs]: kind (1 transition, 2 emit), owner cell, owner edge, target cell, x1 y1 x2 y2, nx ny, table, temp, start, duration

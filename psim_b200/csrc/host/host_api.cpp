@@ -9,6 +9,8 @@
 #include <iostream>
 #include <limits>
 #include <string>
+#include <thread>
+#include <vector>
 
 struct psim_model {
     std::unique_ptr<psim::Model> m;
@@ -235,38 +237,81 @@ int psim_model_next_run(psim_model* pm) {
 }
 
 int psim_model_run(psim_model* pm, int device, uint64_t seed, int steps_per_launch, int verbose, psim_stats* stats) {
-    if (!pm) { return PSIM_E_INVALID; }
+    return psim_model_run_devices(pm, &device, 1, seed, steps_per_launch, verbose, stats);
+}
+
+int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, uint64_t seed, int steps_per_launch, int verbose,
+                           psim_stats* stats) {
+    if (!pm || !devices || n_devices < 1) { return PSIM_E_INVALID; }
     psim::Model& m = *pm->m;
-    psim_gpu* gpu = nullptr;
+    const size_t G = static_cast<size_t>(n_devices);
+    std::vector<psim_gpu*> gpus(G, nullptr);
     const int rc = guarded(PSIM_E_STATE, [&]() -> int {
         m.runs.clear();
         for (uint64_t run = 0; run < m.num_runs; ++run) {
             if (verbose) { std::cout << "Run: " << run + 1 << '\n'; }
             m.prepare();
-            if (!gpu) {
-                if (int e = psim_gpu_create(&m.describe(), device, &gpu)) {
-                    g_error = psim_gpu_last_error(nullptr);
-                    return e;
-                }
-                if (steps_per_launch > 0) {
-                    if (int e = psim_gpu_set_option(gpu, "steps_per_launch", steps_per_launch)) {
-                        g_error = psim_gpu_last_error(gpu);
-                        return e;
+            const psim_model_desc& desc = m.describe();
+            const auto sources = m.source_counts(seed + run);
+            const size_t n_tally = m.sensors.size() * m.recorded_steps;
+            std::vector<std::vector<int32_t>> energy(G, std::vector<int32_t>(n_tally));
+            std::vector<std::vector<int64_t>> fixed(G, std::vector<int64_t>(2 * n_tally));
+            std::vector<psim_stats> st(G);
+            std::vector<int> codes(G, PSIM_OK);
+            std::vector<std::string> errors(G);
+            auto work = [&](size_t d) {
+                int e = PSIM_OK;
+                if (!gpus[d]) {
+                    e = psim_gpu_create(&desc, devices[d], &gpus[d]);
+                    if (e) {
+                        errors[d] = psim_gpu_last_error(nullptr);
+                    } else if (steps_per_launch > 0) {
+                        e = psim_gpu_set_option(gpus[d], "steps_per_launch", steps_per_launch);
                     }
                 }
+                if (!e) { e = psim_gpu_set_sources(gpus[d], sources.data(), sources.size(), seed + run, static_cast<uint32_t>(d), static_cast<uint32_t>(G)); }
+                if (!e) { e = psim_gpu_run(gpus[d]); }
+                if (!e) { e = psim_gpu_get_tallies(gpus[d], energy[d].data(), nullptr, fixed[d].data()); }
+                if (!e) { e = psim_gpu_get_stats(gpus[d], &st[d]); }
+                if (e && errors[d].empty() && gpus[d]) { errors[d] = psim_gpu_last_error(gpus[d]); }
+                codes[d] = e;
+            };
+            if (G == 1) {
+                work(0);
+            } else {
+                std::vector<std::thread> threads;
+                for (size_t d = 0; d < G; ++d) { threads.emplace_back(work, d); }
+                for (auto& t : threads) { t.join(); }
             }
-            const auto sources = m.source_counts(seed + run);
-            int e = psim_gpu_set_sources(gpu, sources.data(), sources.size(), seed + run, 0, 1);
-            if (!e) { e = psim_gpu_run(gpu); }
-            std::vector<int32_t> energy(m.sensors.size() * m.recorded_steps);
-            std::vector<double> flux(energy.size() * 2);
-            if (!e) { e = psim_gpu_get_tallies(gpu, energy.data(), flux.data(), nullptr); }
-            if (!e && stats) { e = psim_gpu_get_stats(gpu, stats); }
-            if (e) {
-                g_error = psim_gpu_last_error(gpu);
-                return e;
+            for (size_t d = 0; d < G; ++d) {
+                if (codes[d]) {
+                    g_error = errors[d];
+                    return codes[d];
+                }
             }
-            m.set_tallies(energy.data(), flux.data());
+            std::vector<double> flux(2 * n_tally);
+            for (size_t i = 0; i < n_tally; ++i) {  // integer sums: independent of the number of devices
+                int64_t e = 0, fx = 0, fy = 0;
+                for (size_t d = 0; d < G; ++d) {
+                    e += energy[d][i];
+                    fx += fixed[d][2 * i];
+                    fy += fixed[d][2 * i + 1];
+                }
+                energy[0][i] = static_cast<int32_t>(e);
+                flux[2 * i] = static_cast<double>(fx) / 256.;
+                flux[2 * i + 1] = static_cast<double>(fy) / 256.;
+            }
+            if (stats) {
+                *stats = st[0];
+                for (size_t d = 1; d < G; ++d) {
+                    stats->shard_phonons += st[d].shard_phonons;
+                    stats->drift_steps += st[d].drift_steps;
+                    stats->events += st[d].events;
+                    stats->peak_alive += st[d].peak_alive;
+                    stats->kernel_ms = std::max(stats->kernel_ms, st[d].kernel_ms);
+                }
+            }
+            m.set_tallies(energy[0].data(), flux.data());
             std::string log;
             m.finish_run(run, &log);
             if (verbose) { std::cout << log; }
@@ -274,7 +319,7 @@ int psim_model_run(psim_model* pm, int device, uint64_t seed, int steps_per_laun
         }
         return PSIM_OK;
     });
-    psim_gpu_destroy(gpu);
+    for (psim_gpu* g : gpus) { psim_gpu_destroy(g); }
     return rc;
 }
 

@@ -520,6 +520,47 @@ __global__ void probe_sample_kernel(DevParams P, uint32_t table, const float* u1
     out_ta[i] = (u2[i] <= t[bin].y) ? 0u : 1u;
 }
 
+__global__ void probe_flight_kernel(DevParams P, const uint32_t* cell, const float* in, size_t n, float* out) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) { return; }
+    psim::Phonon p;
+    psim::Flight f;
+    p.b1 = in[4 * i];
+    p.b2 = in[4 * i + 1];
+    const float vx = in[4 * i + 2], vy = in[4 * i + 3];
+    const float speed = sqrtf(vx * vx + vy * vy);
+    p.dx = vx / speed;
+    p.dy = vy / speed;
+    p.tts = psim::f_inf();
+    p.cell = cell[i];
+    p.packed = 0u;
+    p.id_lo = 0u;
+    psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+    f.vel = speed;
+    psim::update_rates_of_motion(f, p);
+    f.t = 1.0e30f;  // no measurement boundary in the way
+    f.ncoll = 0;
+    psim::rng_begin(f.rng);
+    uint32_t s = 0, n_steps = 0;
+    const float tts0 = 1.0e30f;
+    p.tts = tts0;
+    const int ev = psim::flight_window(P, p, f, s, 1u, n_steps, [](uint32_t, uint32_t) {});
+    const float t_hit = tts0 - p.tts;
+    float dx = p.dx, dy = p.dy;
+    if (ev == psim::EV_IMPACT) {
+        const float2 nrm = psim::load_cell_normal(P.cells, p.cell, f.edge);
+        const float dn = dx * nrm.x + dy * nrm.y;
+        dx -= 2.f * dn * nrm.x;
+        dy -= 2.f * dn * nrm.y;
+    }
+    out[6 * i] = (ev == psim::EV_IMPACT) ? static_cast<float>(f.edge) : -1.f;
+    out[6 * i + 1] = t_hit;
+    out[6 * i + 2] = p.b1;
+    out[6 * i + 3] = p.b2;
+    out[6 * i + 4] = dx;
+    out[6 * i + 5] = dy;
+}
+
 __global__ void probe_rates_kernel(DevParams P, uint32_t sensor, const float* w, const uint32_t* ta, size_t n, float* out) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i >= n) { return; }

@@ -586,6 +586,32 @@ int psim_gpu_probe_sample(psim_gpu* h, uint32_t table, const float* u1, const fl
     return PSIM_OK;
 }
 
+int psim_gpu_probe_flight(psim_gpu* h, const uint32_t* cell, const float* in, size_t n, float* out) {
+    if (!h || !cell || !in || !out) { return PSIM_E_INVALID; }
+    if (n == 0) { return PSIM_OK; }
+    for (size_t i = 0; i < n; ++i) {
+        if (cell[i] >= h->P.n_cells) {
+            h->err = "probe_flight: cell index out of range";
+            return PSIM_E_INVALID;
+        }
+    }
+    PSIM_CUDA(cudaSetDevice(h->device));
+    uint32_t* dc = nullptr;
+    float *di = nullptr, *dout = nullptr;
+    PSIM_CUDA(cudaMalloc(&dc, n * 4));
+    PSIM_CUDA(cudaMalloc(&di, n * 16));
+    PSIM_CUDA(cudaMalloc(&dout, n * 24));
+    PSIM_CUDA(cudaMemcpy(dc, cell, n * 4, cudaMemcpyHostToDevice));
+    PSIM_CUDA(cudaMemcpy(di, in, n * 16, cudaMemcpyHostToDevice));
+    probe_flight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, dc, di, n, dout);
+    PSIM_CUDA(cudaGetLastError());
+    PSIM_CUDA(cudaMemcpy(out, dout, n * 24, cudaMemcpyDeviceToHost));
+    cudaFree(dc);
+    cudaFree(di);
+    cudaFree(dout);
+    return PSIM_OK;
+}
+
 int psim_gpu_probe_rates(psim_gpu* h, uint32_t sensor, const double* omega, const uint32_t* ta, size_t n, double* rates) {
     if (!h || !omega || !ta || !rates || sensor >= h->P.n_sensors) { return PSIM_E_INVALID; }
     if (n == 0) { return PSIM_OK; }

@@ -112,6 +112,7 @@ SYMBOLS = {
     "psim_gpu_last_error": (C.c_char_p, [_P]),
     "psim_gpu_probe_sample": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P, _P, _P]),
     "psim_gpu_probe_rates": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P]),
+    "psim_gpu_probe_flight": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     # include/psim_host.h
     "psim_host_last_error": (C.c_char_p, []),
     "psim_model_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
@@ -132,6 +133,7 @@ SYMBOLS = {
     "psim_model_finish_run": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int)]),
     "psim_model_next_run": (C.c_int, [_P]),
     "psim_model_run": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(Stats)]),
+    "psim_model_run_devices": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(Stats)]),
     "psim_model_results": (C.c_int, [_P, C.c_uint64, _P, _P, _P]),
     "psim_model_energy_per_phonon": (C.c_double, [_P]),
     "psim_model_export": (C.c_int, [_P, C.c_char_p, C.c_double]),
@@ -268,6 +270,14 @@ class Model:
         self.runs_done = self.info.num_runs
         return st
 
+    def run_devices(self, devices, seed: int = 1, steps_per_launch: int = 0, verbose: bool = False) -> Stats:
+        """All runs of the model with the phonons shared between several GPUs of this process."""
+        st = Stats()
+        arr = (C.c_int * len(devices))(*devices)
+        self._check(self.lib.psim_model_run_devices(self.handle, arr, len(devices), int(seed), steps_per_launch, int(verbose), C.byref(st)))
+        self.runs_done = self.info.num_runs
+        return st
+
     def results(self, run_id: Optional[int] = 0, traces: bool = True):
         i = self.info
         S, R = i.num_sensors, i.recorded_steps
@@ -379,6 +389,13 @@ class GpuSimulator:
         plain = np.zeros(u1.size, dtype=np.uint32)
         self._check(self.lib.psim_gpu_probe_sample(self.handle, table, _ptr(u1), _ptr(u2), u1.size, _ptr(b), _ptr(t), _ptr(plain)))
         return b, t, plain
+
+    def probe_flight(self, cell: np.ndarray, state: np.ndarray) -> np.ndarray:
+        cell = np.ascontiguousarray(cell, dtype=np.uint32)
+        state = np.ascontiguousarray(state, dtype=np.float32)
+        out = np.zeros((cell.size, 6), dtype=np.float32)
+        self._check(self.lib.psim_gpu_probe_flight(self.handle, _ptr(cell), _ptr(state), cell.size, _ptr(out)))
+        return out
 
     def probe_rates(self, sensor: int, omega: np.ndarray, ta: np.ndarray) -> np.ndarray:
         omega = np.ascontiguousarray(omega, dtype=np.float64)

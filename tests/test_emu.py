@@ -101,3 +101,24 @@ def test_full_mode_initial_population():
     assert cells > 100                    # in a full simulation every cell starts with its thermal population
     assert r["alive"][0] >= 0.9 * cells   # which is alive after the first interval
     assert (r["hist"][0] > 0).sum() >= 38  # in (nearly) every one of the 40 cells
+
+
+def test_phasor_mode_is_exact_kinematics():
+    """phasor_sim (phononBuilder.cpp:42-49, modelSimulator.cpp:189): every phonon leaves its wall along the normal at
+    1000 m/s and never scatters.  In the 1000 nm bar each of the 20 sensors (50 nm = 5 measurement steps of flight)
+    therefore holds, at every recorded step, the phonons emitted during 5 steps by BOTH walls: N * 5 / 1000 in
+    total, all carrying +1000 m/s of signed x-velocity (hot phonons move right, cold phonons are negative and move
+    left), no y-velocity at all, and the walls absorb everything that arrives."""
+    from psim_b200 import configs
+    model = configs.with_settings(configs.linear(num_phonons=20_000).to_dict(), phasor_sim=True)
+    m = T.load_model(model)
+    m.prepare()
+    r = T.emu_run(m, 4, steps_per_pass=16, want_alive=True)
+    n = sum(c for _, _, _, c in r["sources"])
+    per_sensor = n * 5 / 1000.0
+    counts = r["flux"][:, :, 0] / 1000.0
+    assert np.abs(counts - per_sensor).max() <= 3.0
+    assert np.abs(r["flux"][:, :, 1]).max() == 0.0
+    assert np.abs(r["energy"]).max() <= 0.05 * per_sensor + 3
+    # flight time across the bar is 1 ns = 100 steps: the population saturates at n / 10
+    assert abs(int(r["alive"][16 * 31 - 1]) - n / 10) <= 0.01 * n  # population is recorded at the end of each 16-step pass

@@ -165,3 +165,70 @@ def test_cell_population_matches_emulation():
     emu = T.emu_run(model, 11, want_alive=True, want_hist=True)
     assert abs(int(emu["alive"][39]) - alive) <= 6 * np.sqrt(alive)
     assert np.abs(hist.astype(float) - emu["hist"][39].astype(float)).max() <= 6 * np.sqrt(hist.max() + 1)
+
+
+def test_device_flight_geometry_matches_reference_intersection():
+    """Barycentric time-to-edge + mirror reflection on the device vs the reference's slope/intercept intersection and
+    reflection formulas (oracle/sim.c:oracle_flight, fp64) for random phonons in the cells of the kinked wire
+    (arbitrary triangle shapes and orientations)."""
+    from oracle.model import oracle_flight
+    from psim_b200 import lib as psim
+    name = "kinked_spec" if "kinked_spec" in T.all_case_names() else "sige"
+    model_dict = T.case_model(name)
+    model = T.load_model(model_dict)
+    model.prepare()
+    g = psim.GpuSimulator(model.describe(), 0)
+    rng = np.random.default_rng(3)
+    cells = rng.integers(0, len(model_dict["cells"]), 4000)
+    tris = np.array([[[c["triangle"][p]["x"], c["triangle"][p]["y"]] for p in ("p1", "p2", "p3")] for c in model_dict["cells"]])
+    r1, r2 = rng.random(cells.size) * 0.96 + 0.02, rng.random(cells.size) * 0.96 + 0.02
+    flip = r1 + r2 > 0.98
+    r1[flip], r2[flip] = 0.98 - r1[flip] * 0.98, 0.98 - r2[flip] * 0.98
+    r1, r2 = np.clip(r1, 0.01, 0.97), np.clip(r2, 0.01, 0.97)
+    over = r1 + r2 > 0.98
+    r2[over] = 0.98 - r1[over]
+    ang = rng.random(cells.size) * 2 * np.pi
+    speed = rng.uniform(500, 9000, cells.size)
+    vx, vy = speed * np.cos(ang), speed * np.sin(ang)
+    t = tris[cells]
+    px = t[:, 0, 0] + r1 * (t[:, 1, 0] - t[:, 0, 0]) + r2 * (t[:, 2, 0] - t[:, 0, 0])
+    py = t[:, 0, 1] + r1 * (t[:, 1, 1] - t[:, 0, 1]) + r2 * (t[:, 2, 1] - t[:, 0, 1])
+    got = g.probe_flight(cells, np.stack([r1, r2, vx, vy], axis=1))
+    g.close()
+    checked = 0
+    for i in range(cells.size):
+        want = oracle_flight(t[i].reshape(6), [px[i], py[i], vx[i], vy[i]])
+        if want[0] < 0:
+            continue  # the reference missed the edge (its own leak, SURVEY A.11): nothing to compare
+        checked += 1
+        assert int(got[i, 0]) == int(want[0]), i
+        assert got[i, 1] == pytest.approx(want[1], rel=2e-4, abs=1e-7), i
+        hx = t[i, 0, 0] + got[i, 2] * (t[i, 1, 0] - t[i, 0, 0]) + got[i, 3] * (t[i, 2, 0] - t[i, 0, 0])
+        hy = t[i, 0, 1] + got[i, 2] * (t[i, 1, 1] - t[i, 0, 1]) + got[i, 3] * (t[i, 2, 1] - t[i, 0, 1])
+        size = np.abs(t[i] - t[i].mean(axis=0)).max()
+        assert abs(hx - want[2]) <= 2e-4 * size and abs(hy - want[3]) <= 2e-4 * size, i
+        assert got[i, 4] == pytest.approx(want[4], abs=2e-4) and got[i, 5] == pytest.approx(want[5], abs=2e-4), i
+    assert checked > 3500
+
+
+def test_model_run_end_to_end_and_multi_run():
+    """psim_model_run: the reference's Model::runSimulation loop (prepare -> sources -> GPU -> epilogue) including
+    num_runs > 1 and the averaged export; and, when the box has several GPUs, psim_model_run_devices must reproduce
+    the one-GPU result exactly (integer tallies summed on the host)."""
+    import torch
+    from psim_b200 import configs
+    model = configs.with_settings(configs.linear(num_phonons=100_000).to_dict(), num_runs=2)
+    m = T.load_model(model)
+    st = m.run(device=0, seed=5)
+    assert st.drift_steps > 0 and st.total_phonons in range(99_990, 100_010)
+    six0, six1, avg = m.results(0)[0], m.results(1)[0], m.results(None)[0]
+    assert not np.array_equal(six0, six1)  # different seeds
+    np.testing.assert_allclose(avg, (six0 + six1) / 2, rtol=1e-12)
+    assert 306.5 < avg[0, 0] < 309.0 and 291.0 < avg[-1, 0] < 293.5  # hot and cold ends of the 310 K / 290 K bar
+    text = m.export_text("linear_demo.json", 0.1, "now")
+    assert text.startswith('Steady State Results from "linear_demo.json" @ now - Time Taken 0.1[s] over 2 runs')
+    if torch.cuda.device_count() >= 2:
+        m2 = T.load_model(model)
+        m2.run_devices([0, 1], seed=5)
+        np.testing.assert_array_equal(m2.results(0)[0], six0)
+        np.testing.assert_array_equal(m2.results(1)[0], six1)
