@@ -350,8 +350,65 @@ void Model::build_geometry() {
     std::nth_element(lengths.begin(), lengths.begin() + lengths.size() / 2, lengths.end());
     const double h = std::max(lengths[lengths.size() / 2], 1e-6);
     EdgeGrid grid(h, x0, y0);
+    EdgeGrid boxes(h, x0, y0);  // bounding boxes of the cells already placed, for the validity checks
     std::vector<uint32_t> stamp(cells.size() * 3, 0xFFFFFFFFu);
+    std::vector<uint32_t> cell_stamp(cells.size(), 0xFFFFFFFFu);
+    auto describe = [](const CellRec& c) {
+        std::ostringstream os;
+        os << "Triangle: [Point (" << c.x[0] << ", " << c.y[0] << "), Point (" << c.x[1] << ", " << c.y[1] << "), Point (" << c.x[2]
+           << ", " << c.y[2] << ")]";
+        return os.str();
+    };
+    auto orient = [](double ax, double ay, double bx, double by, double px, double py) {
+        return (bx - ax) * (py - ay) - (px - ax) * (by - ay);
+    };
+    auto strictly_inside = [&](const CellRec& c, double px, double py) {
+        const double d0 = orient(c.x[0], c.y[0], c.x[1], c.y[1], px, py), d1 = orient(c.x[1], c.y[1], c.x[2], c.y[2], px, py),
+                     d2 = orient(c.x[2], c.y[2], c.x[0], c.y[0], px, py);
+        const double eps = 1e-9 * (std::fabs(c.x[1] - c.x[0]) + std::fabs(c.y[1] - c.y[0]) + std::fabs(c.x[2] - c.x[0]) + std::fabs(c.y[2] - c.y[0]) + 1.);
+        return (d0 > eps && d1 > eps && d2 > eps) || (d0 < -eps && d1 < -eps && d2 < -eps);
+    };
     for (uint32_t ci = 0; ci < cells.size(); ++ci) {
+        // Model::addCell -> Cell::validate (model.cpp:98-113, cell.cpp:21-25): an incoming cell must not be a
+        // duplicate of, be contained in, or contain an existing cell.  (The reference's point-in-triangle test,
+        // geometry.cpp:176-201, only fires next to the first vertex; the plain test is used here.)
+        {
+            const CellRec& c = cells[ci];
+            const Seg box{ std::min({ c.x[0], c.x[1], c.x[2] }), std::min({ c.y[0], c.y[1], c.y[2] }),
+                           std::max({ c.x[0], c.x[1], c.x[2] }), std::max({ c.y[0], c.y[1], c.y[2] }) };
+            boxes.visit(box, [&](uint32_t cj) {
+                if (cell_stamp[cj] == ci) { return; }
+                cell_stamp[cj] = ci;
+                const CellRec& o = cells[cj];
+                int same = 0;
+                for (int a = 0; a < 3; ++a) {
+                    for (int b = 0; b < 3; ++b) {
+                        const double dx = c.x[a] - o.x[b], dy = c.y[a] - o.y[b];
+                        if (dx * dx + dy * dy < GEOEPS * GEOEPS) { ++same; }
+                    }
+                }
+                if (same >= 3) { throw std::runtime_error("Duplicate cell detected.\n"); }
+                // Triangle::intersects (geometry.cpp:160-183): edges that cross away from their end points
+                for (int a = 0; a < 3; ++a) {
+                    const Seg ea = cell_edge(c, a);
+                    for (int b = 0; b < 3; ++b) {
+                        const Seg eb = cell_edge(o, b);
+                        const double o1 = orient(ea.ax, ea.ay, ea.bx, ea.by, eb.ax, eb.ay), o2 = orient(ea.ax, ea.ay, ea.bx, ea.by, eb.bx, eb.by);
+                        const double o3 = orient(eb.ax, eb.ay, eb.bx, eb.by, ea.ax, ea.ay), o4 = orient(eb.ax, eb.ay, eb.bx, eb.by, ea.bx, ea.by);
+                        const double tol = 1e-9 * (ea.length() * eb.length() + 1.);
+                        if (((o1 > tol && o2 < -tol) || (o1 < -tol && o2 > tol)) && ((o3 > tol && o4 < -tol) || (o3 < -tol && o4 > tol))) {
+                            throw std::runtime_error("Incoming " + describe(c) + "\nintersects\nExisting" + describe(o) + "\n");
+                        }
+                    }
+                }
+                // no edges cross: one vertex strictly inside means the whole cell lies inside the other
+                for (int a = 0; a < 3; ++a) {
+                    if (strictly_inside(o, c.x[a], c.y[a])) { throw std::runtime_error(describe(c) + "\nis contained within\n" + describe(o) + "\n"); }
+                    if (strictly_inside(c, o.x[a], o.y[a])) { throw std::runtime_error(describe(o) + "\nis contained within\n" + describe(c) + "\n"); }
+                }
+            });
+            boxes.insert(box, ci);
+        }
         for (int a = 0; a < 3; ++a) {
             const uint32_t id = ci * 3 + static_cast<uint32_t>(a);
             const Seg ea = cell_edge(cells[ci], a);

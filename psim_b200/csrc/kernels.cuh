@@ -544,8 +544,10 @@ __global__ void probe_flight_kernel(DevParams P, const uint32_t* cell, const flo
     uint32_t s = 0, n_steps = 0;
     const float tts0 = 1.0e30f;
     p.tts = tts0;
+    const float b1_start = p.b1, b2_start = p.b2, r1_rate = f.r1, r2_rate = f.r2;
     const int ev = psim::flight_window(P, p, f, s, 1u, n_steps, [](uint32_t, uint32_t) {});
-    const float t_hit = tts0 - p.tts;
+    // elapsed time from the displacement along the faster barycentric axis (tts0 - p.tts has no digits left)
+    const float t_hit = (fabsf(r1_rate) > fabsf(r2_rate)) ? (p.b1 - b1_start) / r1_rate : (p.b2 - b2_start) / r2_rate;
     float dx = p.dx, dy = p.dy;
     if (ev == psim::EV_IMPACT) {
         const float2 nrm = psim::load_cell_normal(P.cells, p.cell, f.edge);

@@ -214,6 +214,16 @@ def test_loader_rejections(built_library):
     bad = json.loads(json.dumps(base))
     bad["sensors"][1]["id"] = 0
     rejected(bad, "already exists")
+    # invalid meshes (Cell::validate, cell.cpp:21-25): crossing edges, a cell inside another, a duplicate
+    bad = json.loads(json.dumps(base))
+    bad["cells"].append({"triangle": {"p1": {"x": 10, "y": 10}, "p2": {"x": 60, "y": 150}, "p3": {"x": 90, "y": 20}}, "sensorID": 0, "specularity": 1})
+    rejected(bad, "intersects")
+    bad = json.loads(json.dumps(base))
+    bad["cells"].append({"triangle": {"p1": {"x": 5, "y": 5}, "p2": {"x": 5, "y": 40}, "p3": {"x": 20, "y": 5}}, "sensorID": 0, "specularity": 1})
+    rejected(bad, "is contained within")
+    bad = json.loads(json.dumps(base))
+    bad["cells"].append(json.loads(json.dumps(bad["cells"][3])))
+    rejected(bad, "Duplicate cell")
     with pytest.raises(psim.PsimError):
         psim.Model(text="{ not json")
     with pytest.raises(psim.PsimError):
