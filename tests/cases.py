@@ -40,6 +40,7 @@ def cases(include_kinked: bool = True):
     c = {}
     c["linear_demo"] = configs.linear(num_phonons=400_000).to_dict()
     c["linear_diffuse"] = configs.linear(num_phonons=200_000, spec=0.3).to_dict()
+    c["linear_rough"] = configs.linear(num_phonons=200_000, spec=0.0).to_dict()
     c["linear_hot_cells"] = configs.linear(num_phonons=200_000, t_init=305.0).to_dict()
     c["linear_impurity"] = configs.linear(num_phonons=200_000, material=HOLLAND_SI).to_dict()
     c["linear_full"] = configs.full_mode(configs.linear(num_phonons=200_000).to_dict(), t_init=25.0,
@@ -57,4 +58,5 @@ def cases(include_kinked: bool = True):
         if kinked is not None:
             c["kinked_spec"] = configs.with_settings(kinked, num_phonons=50_000)
             c["kinked_diffuse"] = configs.with_specularity(configs.with_settings(kinked, num_phonons=30_000), 0.5)
+            c["kinked_rough"] = configs.with_specularity(configs.with_settings(kinked, num_phonons=30_000), 0.0)
     return c

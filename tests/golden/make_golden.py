@@ -44,8 +44,10 @@ def cases():
     kinked_path = os.path.join(REF_JSON, "kinked_demo_120_35_spec.json")
     if os.path.exists(kinked_path):
         kinked = json.load(open(kinked_path))
-        with gzip.open(os.path.join(HERE, "kinked_demo_120_35_spec.json.gz"), "wt", compresslevel=9) as f:
-            json.dump(kinked, f, separators=(",", ":"))
+        fixture = os.path.join(HERE, "kinked_demo_120_35_spec.json.gz")
+        if not os.path.exists(fixture):
+            with gzip.open(fixture, "wt", compresslevel=9) as f:
+                json.dump(kinked, f, separators=(",", ":"))
     return test_cases.cases()
 
 

@@ -12,8 +12,8 @@ pytestmark = pytest.mark.gpu
 
 SEEDS = list(range(1, 9))
 
-STEADY = ["linear_demo", "linear_diffuse", "linear_hot_cells", "linear_impurity", "linear_full", "sides_ss", "sige",
-          "kinked_spec", "kinked_diffuse"]
+STEADY = ["linear_demo", "linear_diffuse", "linear_rough", "linear_hot_cells", "linear_impurity", "linear_full", "sides_ss", "sige",
+          "kinked_spec", "kinked_diffuse", "kinked_rough"]
 TRACES = ["sides_per", "sides_trans", "sides_per_full"]
 
 
