@@ -26,8 +26,12 @@ namespace psim {
 PSIM_HD uint32_t mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 PSIM_HD float f_log(float x) { return __logf(x); }
 PSIM_HD float f_exp(float x) { return __expf(x); }
-PSIM_HD float f_cos2pi(float u) { return cospif(2.f * u); }
-PSIM_HD float f_sqrt(float x) { return sqrtf(x); }
+PSIM_HD float f_cos2pi(float u) { return __cosf(6.283185307179586f * u); }  // MUFU.COS, abs. error < 1e-6 on [0, 2 pi]
+PSIM_HD float f_sqrt(float x) {                                              // MUFU.SQRT (x >= 0)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 PSIM_HD float f_div(float a, float b) {  // a / b with one MUFU.RCP (1 ulp) - ample for hit times and scatter times
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
@@ -74,6 +78,7 @@ PSIM_HD float2 load_cell_normal(const DevCell* cells, uint32_t i, uint32_t e) {
 }
 PSIM_HD float load_cell_spec(const DevCell* cells, uint32_t i) { return cells[i].spec; }
 PSIM_HD uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+PSIM_HD uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) { return sensors[i]; }
 #endif
 
@@ -185,8 +190,9 @@ PSIM_HD uint32_t sample_bin(const DevParams& P, uint32_t table_idx, float r) {
 // reference's uniform draw over the bin is resolved to 1/256 of a bin (0.001 % of the spectrum).
 PSIM_HD float phonon_omega(const DevParams& P, uint32_t packed) {
     const float fw = ldg(&P.materials[PSIM_PACK_MAT(packed)].freq_width);
-    float w = (2.f * static_cast<float>(PSIM_PACK_BIN(packed)) + 1.f) * 0.5f * fw;
-    if (!P.full_mode) { w += ((2.f * static_cast<float>(PSIM_PACK_JIT(packed)) + 1.f) * (1.f / 256.f) - 1.f) * 0.5f * fw; }
+    // bin + (jitter + 1/2) / 256 bins in deviational mode, bin + 1/2 otherwise: one exact integer -> float conversion
+    const uint32_t fine = P.full_mode ? (PSIM_PACK_BIN(packed) << 9) + 256u : (PSIM_PACK_BIN(packed) << 9) + (PSIM_PACK_JIT(packed) << 1) + 1u;
+    const float w = static_cast<float>(fine) * (1.f / 512.f) * fw;
     return P.phasor ? static_cast<float>(PSIM_FREQ_SCALE) : w;  // PhasorBuilder: freq = 1 rad/s (phononBuilder.cpp:46)
 }
 
@@ -248,20 +254,19 @@ PSIM_HD void boundary_reflect(Rng& rng, float spec, float nx, float ny, Phonon& 
     }
 }
 
-PSIM_HD float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+PSIM_HD float clamp01(float x) {
+#if defined(__CUDA_ARCH__)
+    return __saturatef(x);
+#else
+    return fminf(fmaxf(x, 0.f), 1.f);
+#endif
+}
 
 // position on edge `e` at fraction s from the edge's first vertex
 PSIM_HD void place_on_edge(uint32_t e, float s, Phonon& p) {
-    if (e == 0u) {
-        p.b1 = s;
-        p.b2 = 0.f;
-    } else if (e == 1u) {
-        p.b1 = 1.f - s;
-        p.b2 = s;
-    } else {
-        p.b1 = 0.f;
-        p.b2 = 1.f - s;
-    }
+    const float r = 1.f - s;
+    p.b1 = (e == 0u) ? s : ((e == 1u) ? r : 0.f);
+    p.b2 = (e == 0u) ? 0.f : ((e == 1u) ? s : r);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -402,15 +407,19 @@ PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, floa
 template<class OnMeasure>
 PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, uint32_t& n_steps,
                           OnMeasure&& on_measure) {
+    // times to the three edges (b2 = 0, b1 + b2 = 1, b1 = 0); a position that rounding left marginally outside gives a
+    // negative time, taken as 0, so that the edge reached is always the one whose time equals the minimum
     const float inf = f_inf();
-    const float t0 = (f.r2 < 0.f) ? f_div(-p.b2, f.r2) : inf;
-    const float t2 = (f.r1 < 0.f) ? f_div(-p.b1, f.r1) : inf;
+    const float t0 = (f.r2 < 0.f) ? fmaxf(f_div(-p.b2, f.r2), 0.f) : inf;
+    const float t2 = (f.r1 < 0.f) ? fmaxf(f_div(-p.b1, f.r1), 0.f) : inf;
     const float rs = f.r1 + f.r2;
-    const float t1 = (rs > 0.f) ? f_div(1.f - p.b1 - p.b2, rs) : inf;
-    const float th = fmaxf(fminf(t0, fminf(t1, t2)), 0.f);
-    const bool impact = th <= p.tts;  // reference: impact_time <= time (modelSimulator.cpp:111)
-    float te = impact ? th : p.tts;   // time to the next physical event
-    float flown = 0.f;
+    const float t1 = (rs > 0.f) ? fmaxf(f_div(1.f - p.b1 - p.b2, rs), 0.f) : inf;
+    const float th = fminf(t0, fminf(t1, t2));
+    const bool impact = th <= p.tts;        // reference: impact_time <= time (modelSimulator.cpp:111)
+    const float te = impact ? th : p.tts;   // time to the next physical event
+    int ev = impact ? EV_IMPACT : EV_SCATTER;
+    float flown = te;                       // time flown in this segment
+    float t_left = f.t - te;                // time left in the measurement interval in which the segment ends
     if (!(te < f.t)) {
         // Boundaries of this window lie at f.t, f.t + dt, ... (step_end - s of them).  Those at or before the event
         // are crossed first (a measurement wins a tie): n = min(left, floor((te - f.t) / dt) + 1), in closed form so
@@ -419,45 +428,29 @@ PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s,
         const float q = fminf(floorf((te - f.t) * P.step_time_inv), 1.0e6f);
         const uint32_t n = min(left, static_cast<uint32_t>(q) + 1u);
         n_steps += n;
-        const uint32_t first = (P.first_tally_step > s + 1u) ? P.first_tally_step - 1u : s;  // first RECORDED one
+        const uint32_t first = max(P.first_tally_step, s + 1u) - 1u;  // first RECORDED one among them
         if (first < s + n) { on_measure(first, s + n); }
-        flown = f.t + static_cast<float>(n - 1u) * P.step_time;
-        if (n == left) {  // end of the launch window: the state goes back to the pool
-            p.b1 += f.r1 * flown;
-            p.b2 += f.r2 * flown;
-            p.tts -= flown;
-            s = step_end - 1u;
-            f.t = P.step_time;
-            return EV_END;
-        }
-        s += n;
-        te = fminf(fmaxf(te - flown, 0.f), P.step_time);  // time from the last boundary crossed to the event
-        f.t = P.step_time;
+        const float to_last = f.t + static_cast<float>(n - 1u) * P.step_time;  // up to the last boundary crossed
+        const bool end = n == left;  // end of the launch window: the state goes back to the pool
+        s = end ? step_end - 1u : s + n;
+        ev = end ? EV_END : ev;
+        flown = end ? to_last : te;
+        t_left = end ? P.step_time : (to_last + P.step_time) - te;
         f.ncoll = 0;
         f.rng.block = 0;
     }
-    f.t -= te;
-    if (!impact) {
-        flown += te;
-        p.b1 += f.r1 * flown;
-        p.b2 += f.r2 * flown;
-        p.tts = 0.f;
-        return EV_SCATTER;
-    }
-    const uint32_t e = (th == t0 || t0 < 0.f) ? 0u : ((th == t1 || t1 < 0.f) ? 1u : 2u);
-    float sh;
-    if (e == 0u) {
-        sh = clamp01(p.b1 + f.r1 * th);
-    } else if (e == 1u) {
-        sh = clamp01(p.b2 + f.r2 * th);
-    } else {
-        sh = clamp01(1.f - (p.b2 + f.r2 * th));
-    }
-    place_on_edge(e, sh, p);
-    p.tts -= th;
-    f.edge = e;
-    f.s_hit = sh;
-    return EV_IMPACT;
+    f.t = t_left;
+    const float nb1 = p.b1 + f.r1 * flown, nb2 = p.b2 + f.r2 * flown;
+    p.tts = (ev == EV_SCATTER) ? 0.f : p.tts - flown;
+    // an impact snaps the position onto the edge it reached
+    const bool is0 = th == t0, is1 = !is0 && th == t1, hit = ev == EV_IMPACT;
+    const float c1 = clamp01(nb1), c2 = clamp01(nb2), r2 = 1.f - c2;
+    const float hb1 = is0 ? c1 : (is1 ? r2 : 0.f), hb2 = is0 ? 0.f : c2;
+    p.b1 = hit ? hb1 : nb1;
+    p.b2 = hit ? hb2 : nb2;
+    f.edge = hit ? (is0 ? 0u : (is1 ? 1u : 2u)) : 0u;
+    f.s_hit = is0 ? c1 : (is1 ? c2 : r2);  // fraction of the edge from its first vertex
+    return ev;
 }
 
 // The reference redraws the time to scatter whenever a phonon enters another sensor area (modelSimulator.cpp:

@@ -19,7 +19,9 @@
 #define PSIM_FLUX_FRAC_BITS 8    // flux tallies are int64 fixed point, 1/256 m/s resolution
 #define PSIM_FREQ_SCALE 1e-13    // angular frequencies are carried as omega * 1e-13 (fp32 range)
 #define PSIM_BIRTH_STEP 0xFFFFFFFFu  // Philox stream selector for the draws made at emission
-#define PSIM_GUIDE 256           // entries of the per-table guide that brackets the inverse-CDF search
+#ifndef PSIM_GUIDE
+#define PSIM_GUIDE 1024          // entries of the per-table guide that brackets the inverse-CDF search
+#endif
 
 // edge link word: [31:30] kind, then payload
 #define PSIM_LINK_BOUNDARY 0u    // payload unused
@@ -127,7 +129,7 @@ struct DevParams {
     const DevEmitter* emitters;
     const DevSource* sources;
     const float2* tables;      // [n_tables][PSIM_BINS] (cumulative probability, LA fraction)  (material.cpp:170-180)
-    const uint32_t* guides;    // [n_tables][PSIM_GUIDE] search bracket for r in [k/256, (k+1)/256): low | high << 16
+    const uint32_t* guides;    // [n_tables][PSIM_GUIDE] search bracket for r in [k/G, (k+1)/G), G = PSIM_GUIDE: low | high << 16
     const float* velocities;   // [n_materials][2][PSIM_BINS] group velocity, LA then TA, m/s == nm/ns
     uint32_t n_cells, n_sensors, n_materials, n_tables, n_emitters, n_sources;
     uint32_t num_steps;        // measurement steps M

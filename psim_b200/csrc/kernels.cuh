@@ -204,17 +204,16 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
     uint32_t next = 0, n_out = 0;
     uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
     bool overflow = false;
-    uint32_t m_free = (1u << K) - 1u, m_fly = 0, m_hit = 0, m_wall = 0, m_sct = 0, m_fin = 0;  // which of my slots want what
+    uint32_t m_free = (1u << K) - 1u, m_fly = 0, m_wall = 0, m_sct = 0, m_fin = 0;  // which of my slots want what
 
     for (;;) {
         const bool input = next < total;
         const int c_fly = __popc(__ballot_sync(0xFFFFFFFFu, m_fly != 0u));
-        const int c_hit = __popc(__ballot_sync(0xFFFFFFFFu, m_hit != 0u));
         const int c_wall = __popc(__ballot_sync(0xFFFFFFFFu, m_wall != 0u));
         const int c_sct = __popc(__ballot_sync(0xFFFFFFFFu, m_sct != 0u));
         const int c_fin = __popc(__ballot_sync(0xFFFFFFFFu, m_fin != 0u));
         const int c_acq = input ? __popc(__ballot_sync(0xFFFFFFFFu, m_free != 0u)) : 0;
-        const int best = max(max(max(c_fly, c_hit), c_wall), max(max(c_sct, c_fin), c_acq));
+        const int best = max(max(c_fly, c_wall), max(max(c_sct, c_fin), c_acq));
         if (best == 0) { break; }
         // the kind wanted by the most lanes runs; ties go to the rarer kinds (they waited longest to get there)
         if (c_sct == best) {
@@ -293,38 +292,6 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     m_fly |= 1u << k;
                 }
             }
-        } else if (c_hit == best) {
-            // ---- edge reached: the frequent case, a whole-edge transition into a cell with the same material and
-            //      rates, is done here; anything else is handed to the general kind above (no work lost: it only
-            //      changes which mask the slot sits in)
-            if (m_hit != 0u) {
-                const uint32_t k = __ffs(m_hit) - 1u;
-                psim::Phonon p;
-                psim::Flight f;
-                p.b1 = slot_f(SF_B1, k);
-                p.b2 = slot_f(SF_B2, k);
-                p.dx = slot_f(SF_DX, k);
-                p.dy = slot_f(SF_DY, k);
-                p.cell = slot_u(SF_CELL, k);
-                const uint32_t misc = slot_u(SF_MISC, k);
-                f.edge = PSIM_MISC_EDGE(misc);
-                f.s_hit = (f.edge == 0u) ? p.b1 : ((f.edge == 1u) ? p.b2 : 1.f - p.b2);
-                f.ncoll = PSIM_MISC_NCOLL(misc);
-                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
-                f.vel = psim::phonon_velocity(P, slot_u(SF_PACKED, k));
-                m_hit &= ~(1u << k);
-                if (psim::fast_transition(P, p, f)) {
-                    slot_f(SF_B1, k) = p.b1;
-                    slot_f(SF_B2, k) = p.b2;
-                    slot_u(SF_CELL, k) = p.cell;
-                    slot_f(SF_R1, k) = f.r1;
-                    slot_f(SF_R2, k) = f.r2;
-                    slot_u(SF_MISC, k) = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), f.ncoll, PSIM_MISC_EDGE(misc), PSIM_MISC_BLOCK(misc));
-                    m_fly |= 1u << k;
-                } else {
-                    m_wall |= 1u << k;
-                }
-            }
         } else if (c_fin == best) {
             // ---- write-back of phonons that reached the end of the launch window (compacted, coalesced)
             const bool store = m_fin != 0u;
@@ -400,7 +367,8 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 f.edge = 0u;
                 f.ncoll = PSIM_MISC_NCOLL(misc);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
-                uint32_t s = a.step_begin + PSIM_MISC_STEP(misc);
+                const uint32_t s0 = a.step_begin + PSIM_MISC_STEP(misc);
+                uint32_t s = s0;
                 const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
                     const uint32_t packed = slot_u(SF_PACKED, k);
                     const float vel = psim::phonon_velocity(P, packed);
@@ -410,20 +378,319 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, sg, fx, fy); }
                 });
                 ++n_events;
-                slot_f(SF_B1, k) = p.b1;
-                slot_f(SF_B2, k) = p.b2;
-                slot_f(SF_TTS, k) = p.tts;
-                slot_f(SF_T, k) = f.t;
-                slot_u(SF_MISC, k) = PSIM_MISC_PACK(s - a.step_begin, f.ncoll, f.edge, f.rng.block);
+                // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
+                // block): only the step survives in the packed word; otherwise only the edge changes
+                misc = ((s != s0) ? (s - a.step_begin) : (misc & ~(3u << 17))) | (f.edge << 17);
                 m_fly &= ~(1u << k);
                 if (ev == psim::EV_IMPACT) {
-                    m_hit |= 1u << k;
+                    // the frequent case - a whole-edge transition into a cell with the same material and rates - is done
+                    // at once, and the slot keeps flying; anything else waits for the general surface-interaction kind
+                    p.dx = slot_f(SF_DX, k);
+                    p.dy = slot_f(SF_DY, k);
+                    p.cell = slot_u(SF_CELL, k);
+                    f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                    f.vel = psim::phonon_velocity(P, slot_u(SF_PACKED, k));
+                    if (psim::fast_transition(P, p, f)) {
+                        slot_u(SF_CELL, k) = p.cell;
+                        slot_f(SF_R1, k) = f.r1;
+                        slot_f(SF_R2, k) = f.r2;
+                        misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
+                        m_fly |= 1u << k;
+                    } else {
+                        m_wall |= 1u << k;
+                    }
                 } else if (ev == psim::EV_SCATTER) {
                     m_sct |= 1u << k;
                 } else {
                     m_fin |= 1u << k;
                 }
+                slot_f(SF_B1, k) = p.b1;
+                slot_f(SF_B2, k) = p.b2;
+                slot_f(SF_TTS, k) = p.tts;
+                slot_f(SF_T, k) = f.t;
+                slot_u(SF_MISC, k) = misc;
             }
+        }
+    }
+    n_out = min(n_out, a.seg_cap);
+    if (lane == 0) { a.cnt_out[w] = n_out; }
+    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
+    tally_flush(a, acc_e, acc_f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// drift_kernel_queues<NS>: the same work as drift_kernel_slots with the binding between slots and lanes removed.
+//
+// In the slots kernel a lane can only work on its own K slots, so a pass runs with the lanes that happen to hold a
+// slot of the chosen kind (ncu: 26 of 32 for flights, 21-22 for scatters and walls, 19.7 on average).  Here a warp
+// owns NS slots ([field][slot] in shared memory) and ONE QUEUE OF SLOT NUMBERS PER KIND of work; a pass pops up to 32
+// entries of the fullest queue - lane i takes the i-th - so every kind runs with all 32 lanes as soon as 32 slots
+// want it, and rare kinds simply wait in their queue until then.  Queue heads and counts are warp-uniform registers:
+// choosing the kind costs no ballot.  Pushing into the queue of the next kind is a ballot + popc rank.  The price is
+// shared-memory bank conflicts (32 arbitrary slot numbers per access instead of lane == bank), paid on the LSU pipe,
+// which has headroom, not on the issue slots, which have none.
+// ---------------------------------------------------------------------------------------------------------------
+enum : int { Q_FLY = 0, Q_SCT, Q_WALL, Q_FIN, Q_FREE, Q_COUNT };
+
+template<int NS>
+__global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const __grid_constant__ LaunchArgs a) {
+    static_assert(NS <= 256 && (NS & (NS - 1)) == 0 && NS >= 32, "slot numbers are bytes; the queues are power-of-two rings");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevParams& P = a.P;
+    const uint32_t nst = a.step_end - a.step_begin;
+    int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
+    long long* acc_f = reinterpret_cast<long long*>(smem_raw + tally_smem_offset_f(nst, P.n_sensors));
+    tally_init(a, acc_e, acc_f);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const size_t tally_bytes = a.tally_shared ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
+    unsigned char* base = smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127));
+    uint32_t* sw = reinterpret_cast<uint32_t*>(base) + (threadIdx.x >> 5) * (SF_COUNT * NS);
+    unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SF_COUNT * NS * 4 + (threadIdx.x >> 5) * (Q_COUNT * NS);
+    auto slot_u = [&](int field, uint32_t k) -> uint32_t& { return sw[field * NS + k]; };
+    auto slot_f = [&](int field, uint32_t k) -> float& { return reinterpret_cast<float*>(sw)[field * NS + k]; };
+    struct Queue {
+        uint32_t head, count;
+    };
+    Queue q_fly{ 0, 0 }, q_sct{ 0, 0 }, q_wall{ 0, 0 }, q_fin{ 0, 0 }, q_free{ 0, NS };
+    // lane i takes the i-th of the first `take` entries
+    auto pop = [&](Queue& q, int qi, uint32_t take, bool& active) -> uint32_t {
+        active = lane < take;
+        const uint32_t k = active ? qb[qi * NS + ((q.head + lane) & (NS - 1))] : 0u;
+        q.head += take;
+        q.count -= take;
+        return k;
+    };
+    auto push = [&](Queue& q, int qi, bool mine, uint32_t k) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+        if (mine) { qb[qi * NS + ((q.head + q.count + __popc(m & lt_mask)) & (NS - 1))] = static_cast<unsigned char>(k); }
+        q.count += __popc(m);
+    };
+    for (uint32_t i = lane; i < NS; i += 32u) { qb[Q_FREE * NS + i] = static_cast<unsigned char>(i); }
+
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t W = a.n_warps;
+    const size_t seg = static_cast<size_t>(w) * a.seg_cap;
+    const uint32_t n_in = a.cnt_in[w];
+    const uint64_t n_chunks = (a.n_births + 31u) >> 5;
+    const uint32_t c0 = (w + W - (a.birth_warp_offset % W)) % W;
+    const uint32_t my_chunks = (c0 < n_chunks) ? static_cast<uint32_t>((n_chunks - 1 - c0) / W + 1) : 0u;
+    const uint32_t total = n_in + my_chunks * 32u;
+
+    uint32_t next = 0, n_out = 0;
+    uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
+    bool overflow = false;
+
+    for (;;) {
+        __syncwarp();  // slot words and queue entries written by other lanes in the previous pass
+        const uint32_t c_fly = min(q_fly.count, 32u), c_wall = min(q_wall.count, 32u), c_sct = min(q_sct.count, 32u);
+        const uint32_t c_fin = min(q_fin.count, 32u), c_acq = min(min(q_free.count, total - next), 32u);
+        const uint32_t best = max(max(c_fly, c_wall), max(max(c_sct, c_fin), c_acq));
+        if (best == 0u) { break; }
+        bool act;
+        // the fullest queue runs; ties go to the rarer kinds (they waited longest to get there)
+        if (c_sct == best) {
+            // ---- intrinsic scatter
+            const uint32_t k = pop(q_sct, Q_SCT, c_sct, act);
+            if (act) {
+                psim::Phonon p;
+                psim::Flight f;
+                p.dx = slot_f(SF_DX, k);
+                p.dy = slot_f(SF_DY, k);
+                p.packed = slot_u(SF_PACKED, k);
+                p.cell = slot_u(SF_CELL, k);
+                p.id_lo = slot_u(SF_ID, k);
+                uint32_t misc = slot_u(SF_MISC, k);
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.vel = psim::phonon_velocity(P, p.packed);
+                f.rng.block = PSIM_MISC_BLOCK(misc);
+                f.rng.left = 0;
+                psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
+                slot_f(SF_DX, k) = p.dx;
+                slot_f(SF_DY, k) = p.dy;
+                slot_u(SF_PACKED, k) = p.packed;
+                slot_f(SF_TTS, k) = p.tts;
+                slot_f(SF_R1, k) = f.r1;
+                slot_f(SF_R2, k) = f.r2;
+                slot_u(SF_MISC, k) = misc;
+            }
+            push(q_fly, Q_FLY, act, k);
+        } else if (c_wall == best) {
+            // ---- surface interaction, general case: wall (specular / diffuse), emitting surface, material interface,
+            //      transition into a sensor area with other rates, partial edges, stuck-phonon guard
+            const uint32_t k = pop(q_wall, Q_WALL, c_wall, act);
+            bool dead = false;
+            if (act) {
+                psim::Phonon p;
+                psim::Flight f;
+                p.b1 = slot_f(SF_B1, k);
+                p.b2 = slot_f(SF_B2, k);
+                p.dx = slot_f(SF_DX, k);
+                p.dy = slot_f(SF_DY, k);
+                p.tts = slot_f(SF_TTS, k);
+                p.packed = slot_u(SF_PACKED, k);
+                p.cell = slot_u(SF_CELL, k);
+                p.id_lo = slot_u(SF_ID, k);
+                uint32_t misc = slot_u(SF_MISC, k);
+                f.edge = PSIM_MISC_EDGE(misc);
+                f.s_hit = (f.edge == 0u) ? p.b1 : ((f.edge == 1u) ? p.b2 : 1.f - p.b2);
+                f.ncoll = PSIM_MISC_NCOLL(misc);
+                f.rng.block = PSIM_MISC_BLOCK(misc);
+                f.rng.left = 0;
+                f.r1 = slot_f(SF_R1, k);
+                f.r2 = slot_f(SF_R2, k);
+                f.t = 0.f;
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.vel = psim::phonon_velocity(P, p.packed);
+                const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                if (ev == psim::EV_DEAD) {
+                    ++n_steps;
+                    ++n_absorbed;
+                    dead = true;
+                } else {
+                    misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), f.ncoll, PSIM_MISC_EDGE(misc), f.rng.block);
+                    slot_f(SF_B1, k) = p.b1;
+                    slot_f(SF_B2, k) = p.b2;
+                    slot_f(SF_DX, k) = p.dx;
+                    slot_f(SF_DY, k) = p.dy;
+                    slot_f(SF_TTS, k) = p.tts;
+                    slot_u(SF_CELL, k) = p.cell;
+                    slot_f(SF_R1, k) = f.r1;
+                    slot_f(SF_R2, k) = f.r2;
+                    slot_u(SF_MISC, k) = misc;
+                }
+            }
+            push(q_fly, Q_FLY, act && !dead, k);
+            push(q_free, Q_FREE, act && dead, k);
+        } else if (c_fin == best) {
+            // ---- write-back of phonons that reached the end of the launch window (compacted, coalesced)
+            const uint32_t k = pop(q_fin, Q_FIN, c_fin, act);
+            if (act) {
+                const uint32_t slot = n_out + lane;
+                if (slot < a.seg_cap) {
+                    a.out_a[seg + slot] = make_float4(slot_f(SF_B1, k), slot_f(SF_B2, k), slot_f(SF_DX, k), slot_f(SF_DY, k));
+                    a.out_b[seg + slot] = make_uint4(slot_u(SF_TTS, k), slot_u(SF_PACKED, k), slot_u(SF_CELL, k), slot_u(SF_ID, k));
+                } else {
+                    overflow = true;
+                }
+            }
+            n_out += c_fin;
+            push(q_free, Q_FREE, act, k);
+        } else if (c_acq == best) {
+            // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots
+            const uint32_t k = pop(q_free, Q_FREE, c_acq, act);
+            bool got = false;
+            if (act) {
+                const uint32_t idx = next + lane;
+                psim::Phonon p;
+                uint32_t s = a.step_begin;
+                float t_begin = P.step_time;
+                if (idx < n_in) {
+                    load_phonon(a, seg + idx, p);
+                    got = true;
+                } else {
+                    const uint32_t b = idx - n_in;
+                    const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
+                    if (item < a.n_births) {
+                        t_begin = birth_phonon(a, item, p, s);
+                        got = true;
+                    }
+                }
+                if (got) {
+                    psim::Flight f;
+                    psim::interval_begin(P, p, f, t_begin, s);
+                    slot_f(SF_B1, k) = p.b1;
+                    slot_f(SF_B2, k) = p.b2;
+                    slot_f(SF_DX, k) = p.dx;
+                    slot_f(SF_DY, k) = p.dy;
+                    slot_f(SF_TTS, k) = p.tts;
+                    slot_u(SF_PACKED, k) = p.packed;
+                    slot_u(SF_CELL, k) = p.cell;
+                    slot_u(SF_ID, k) = p.id_lo;
+                    slot_f(SF_T, k) = f.t;
+                    slot_f(SF_R1, k) = f.r1;
+                    slot_f(SF_R2, k) = f.r2;
+                    slot_u(SF_MISC, k) = s - a.step_begin;
+                }
+            }
+            next += c_acq;
+            push(q_fly, Q_FLY, got, k);
+            push(q_free, Q_FREE, act && !got, k);
+        } else {
+            // ---- one free-flight segment: to the next edge / scatter / end of the launch window, tallying the
+            //      measurement events it crosses on the way
+            const uint32_t k = pop(q_fly, Q_FLY, c_fly, act);
+            int dest = -1;
+            if (act) {
+                psim::Phonon p;
+                psim::Flight f;
+                p.b1 = slot_f(SF_B1, k);
+                p.b2 = slot_f(SF_B2, k);
+                p.tts = slot_f(SF_TTS, k);
+                f.t = slot_f(SF_T, k);
+                f.r1 = slot_f(SF_R1, k);
+                f.r2 = slot_f(SF_R2, k);
+                uint32_t misc = slot_u(SF_MISC, k);
+                f.edge = 0u;
+                f.ncoll = PSIM_MISC_NCOLL(misc);
+                f.rng.block = PSIM_MISC_BLOCK(misc);
+                const uint32_t s0 = a.step_begin + PSIM_MISC_STEP(misc);
+                uint32_t s = s0;
+                const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
+                    const uint32_t packed = slot_u(SF_PACKED, k);
+                    const float vel = psim::phonon_velocity(P, packed);
+                    const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
+                    const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
+                    const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k) * vel) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k) * vel) * sg;
+                    for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, sg, fx, fy); }
+                });
+                ++n_events;
+                // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
+                // block): only the step survives in the packed word; otherwise only the edge changes
+                misc = ((s != s0) ? (s - a.step_begin) : (misc & ~(3u << 17))) | (f.edge << 17);
+                if (ev == psim::EV_IMPACT) {
+                    // the frequent case - a whole-edge transition into a cell with the same material and rates - is done
+                    // at once, and the slot keeps flying; anything else waits for the general surface-interaction kind
+                    p.dx = slot_f(SF_DX, k);
+                    p.dy = slot_f(SF_DY, k);
+                    p.cell = slot_u(SF_CELL, k);
+                    f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                    f.vel = psim::phonon_velocity(P, slot_u(SF_PACKED, k));
+                    if (psim::fast_transition(P, p, f)) {
+                        slot_u(SF_CELL, k) = p.cell;
+                        slot_f(SF_R1, k) = f.r1;
+                        slot_f(SF_R2, k) = f.r2;
+                        misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
+                        dest = Q_FLY;
+                    } else {
+                        dest = Q_WALL;
+                    }
+                } else {
+                    dest = (ev == psim::EV_SCATTER) ? Q_SCT : Q_FIN;
+                }
+                slot_f(SF_B1, k) = p.b1;
+                slot_f(SF_B2, k) = p.b2;
+                slot_f(SF_TTS, k) = p.tts;
+                slot_f(SF_T, k) = f.t;
+                slot_u(SF_MISC, k) = misc;
+            }
+            // four-way push with one address computation
+            const unsigned m_fly = __ballot_sync(0xFFFFFFFFu, dest == Q_FLY), m_sct = __ballot_sync(0xFFFFFFFFu, dest == Q_SCT);
+            const unsigned m_wall = __ballot_sync(0xFFFFFFFFu, dest == Q_WALL), m_fin = __ballot_sync(0xFFFFFFFFu, dest == Q_FIN);
+            if (dest >= 0) {
+                const unsigned peers = (dest == Q_FLY) ? m_fly : ((dest == Q_SCT) ? m_sct : ((dest == Q_WALL) ? m_wall : m_fin));
+                const uint32_t tail = (dest == Q_FLY) ? q_fly.head + q_fly.count
+                                                      : ((dest == Q_SCT) ? q_sct.head + q_sct.count
+                                                                         : ((dest == Q_WALL) ? q_wall.head + q_wall.count : q_fin.head + q_fin.count));
+                qb[dest * NS + ((tail + __popc(peers & lt_mask)) & (NS - 1))] = static_cast<unsigned char>(k);
+            }
+            q_fly.count += __popc(m_fly);
+            q_sct.count += __popc(m_sct);
+            q_wall.count += __popc(m_wall);
+            q_fin.count += __popc(m_fin);
         }
     }
     n_out = min(n_out, a.seg_cap);

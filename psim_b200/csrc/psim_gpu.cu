@@ -69,7 +69,7 @@ struct psim_gpu {
     // options
     int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
     int64_t opt_warps_per_sm = 0;
-    int64_t opt_kernel = 0;          // 0: shared-memory slots kernel, 1: lock-step kernel (first version, for A/B)
+    int64_t opt_kernel = 2;          // 2: work-queue kernel (default), 0: lane-bound slots kernel, 1: lock-step kernel (both for A/B)
     int64_t opt_tally_shared = -1;
     int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
@@ -95,6 +95,15 @@ template<typename T> int upload(psim_gpu* h, void** dst, const std::vector<T>& v
     return 0;
 }
 
+void free_plan(psim_gpu* h) {
+    cudaFree(h->d_births);
+    cudaFree(h->d_prefix);
+    cudaFree(h->d_sources);
+    h->d_births = nullptr;
+    h->d_prefix = nullptr;
+    h->d_sources = nullptr;
+}
+
 void free_pool(psim_gpu* h) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->pool_a[i]);
@@ -104,14 +113,10 @@ void free_pool(psim_gpu* h) {
         h->pool_b[i] = nullptr;
         h->cnt[i] = nullptr;
     }
-    cudaFree(h->d_births);
-    cudaFree(h->d_prefix);
-    cudaFree(h->d_sources);
     cudaFree(h->d_alive_hist);
-    h->d_births = nullptr;
-    h->d_prefix = nullptr;
-    h->d_sources = nullptr;
     h->d_alive_hist = nullptr;
+    h->seg_cap = 0;
+    h->n_warps = 0;
 }
 
 constexpr size_t kSlotBytesPerBlock = static_cast<size_t>(SF_COUNT) * kSlots * 32 * 4 * kWarpsPerBlock;
@@ -121,6 +126,13 @@ size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
 }
 
 constexpr size_t kTallyStageBudget = PSIM_STAGE_KB * 1024;  // per block; with the slot storage this keeps kSlotBlocks blocks per SM
+constexpr int kQueueSlots = 32 * kSlots;                     // slots per warp of the queues kernel
+constexpr size_t kQueueBytesPerBlock = kSlotBytesPerBlock + static_cast<size_t>(Q_COUNT) * kQueueSlots * kWarpsPerBlock;
+constexpr size_t kTallyStageBudgetQueues = kTallyStageBudget - 6 * 1024;
+
+size_t stage_budget(const psim_gpu* h) {
+    return h->opt_kernel == 1 ? 100 * 1024 : (h->opt_kernel == 2 ? kTallyStageBudgetQueues : kTallyStageBudget);
+}
 constexpr uint32_t kLongWindow = 1023;           // steps per launch while nothing is recorded (10 bits of step in the slot word)
 constexpr uint32_t kGlobalTallyWindow = 128;     // steps per launch when recorded tallies go straight to global memory
 constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
@@ -145,7 +157,7 @@ void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1
     }
     s1 = std::min(s0 + B, step_end);
     if (s1 + 1 <= h->P.first_tally_step) { return; }  // nothing recorded in this window
-    const size_t budget = h->opt_kernel == 1 ? 100 * 1024 : kTallyStageBudget;
+    const size_t budget = stage_budget(h);
     const bool want_shared = h->opt_tally_shared != 0;
     if (!want_shared) { return; }
     if (h->opt_tally_shared < 0 && h->P.n_sensors >= kManySensors && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) {
@@ -251,6 +263,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
@@ -264,7 +277,7 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
     PSIM_CUDA(cudaSetDevice(h->device));
     PSIM_CUDA(cudaStreamSynchronize(h->stream));
     if (int rc = psim::plan_births(h->img, sources, n, shard, num_shards, h->plan, h->err)) { return rc; }
-    free_pool(h);
+    free_plan(h);
     h->have_sources = false;
     if (int rc = upload(h, &h->d_sources, h->plan.sources)) { return rc; }
     {
@@ -284,6 +297,9 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
     int blocks_per_sm = 0;
     if (h->opt_kernel == 1) {
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
+    } else if (h->opt_kernel == 2) {
+        const size_t dyn = kQueueBytesPerBlock + kTallyStageBudgetQueues;
+        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlots>, kBlock, dyn));
     } else {  // shared-memory slots + the largest tally staging a launch may ask for
         const size_t dyn = kSlotBytesPerBlock + kTallyStageBudget;
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_slots<kSlots>, kBlock, dyn));
@@ -293,21 +309,27 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
     if (h->opt_warps_per_sm > 0) {
         warps_per_sm = static_cast<int>(std::max<int64_t>(kWarpsPerBlock, h->opt_warps_per_sm / kWarpsPerBlock * kWarpsPerBlock));
     }
-    h->n_warps = static_cast<uint32_t>(h->sm_count * warps_per_sm);
-    const uint64_t per_warp = (h->plan.shard_phonons + h->n_warps - 1) / h->n_warps;
+    const uint32_t n_warps = static_cast<uint32_t>(h->sm_count * warps_per_sm);
+    const uint64_t per_warp = (h->plan.shard_phonons + n_warps - 1) / n_warps;
     const uint64_t cap = per_warp + per_warp / 8 + 1024;
     if (cap > 0xFFFFFFF0ull) {
         h->err = "shard too large for one device";
         return PSIM_E_INVALID;
     }
-    h->seg_cap = static_cast<uint32_t>((cap + 31) & ~31ull);
-    const size_t slots = static_cast<size_t>(h->seg_cap) * h->n_warps;
-    for (int i = 0; i < 2; ++i) {
-        PSIM_CUDA(cudaMalloc(&h->pool_a[i], slots * sizeof(float4)));
-        PSIM_CUDA(cudaMalloc(&h->pool_b[i], slots * sizeof(uint4)));
-        PSIM_CUDA(cudaMalloc(&h->cnt[i], h->n_warps * sizeof(uint32_t)));
+    const uint32_t seg_cap = static_cast<uint32_t>((cap + 31) & ~31ull);
+    if (n_warps != h->n_warps || seg_cap > h->seg_cap) {
+        // (re)allocate the pool; a later run of the same handle that fits (the runs of a multi-run model) keeps it
+        free_pool(h);
+        const size_t slots = static_cast<size_t>(seg_cap) * n_warps;
+        for (int i = 0; i < 2; ++i) {
+            PSIM_CUDA(cudaMalloc(&h->pool_a[i], slots * sizeof(float4)));
+            PSIM_CUDA(cudaMalloc(&h->pool_b[i], slots * sizeof(uint4)));
+            PSIM_CUDA(cudaMalloc(&h->cnt[i], n_warps * sizeof(uint32_t)));
+        }
+        PSIM_CUDA(cudaMalloc(&h->d_alive_hist, static_cast<size_t>(h->P.num_steps + 1) * sizeof(unsigned long long)));
+        h->seg_cap = seg_cap;
+        h->n_warps = n_warps;
     }
-    PSIM_CUDA(cudaMalloc(&h->d_alive_hist, static_cast<size_t>(h->P.num_steps + 1) * sizeof(unsigned long long)));
     h->have_sources = true;
     return zero_run_state(h);
 }
@@ -366,6 +388,9 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         const size_t dyn = shared ? smem : 0;
         if (h->opt_kernel == 1) {
             drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
+        } else if (h->opt_kernel == 2) {
+            const size_t bytes = kQueueBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
+            drift_kernel_queues<kQueueSlots><<<grid, kBlock, bytes, st>>>(a);
         } else {
             const size_t slots = kSlotBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
             drift_kernel_slots<kSlots><<<grid, kBlock, slots, st>>>(a);
@@ -509,8 +534,8 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
         }
         h->opt_warps_per_sm = value;
     } else if (k == "kernel") {
-        if (h->have_sources || value < 0 || value > 1) {
-            h->err = "kernel must be 0 (shared-memory slots) or 1 (lock step) and set before set_sources";
+        if (h->have_sources || value < 0 || value > 2) {
+            h->err = "kernel must be 0 (shared-memory slots), 1 (lock step) or 2 (work queues) and set before set_sources";
             return PSIM_E_STATE;
         }
         h->opt_kernel = value;
@@ -539,6 +564,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_pool(h);
+    free_plan(h);
     cudaFree(h->d_cells);
     cudaFree(h->d_subs);
     cudaFree(h->d_sensors);
