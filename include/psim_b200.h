@@ -169,7 +169,7 @@ int psim_gpu_cell_histogram(psim_gpu* h, uint64_t* per_cell /* [num_cells] */);
 int psim_gpu_get_stats(psim_gpu* h, psim_stats* out);
 
 /* Tunables: "steps_per_launch" (measurement intervals advanced per pass over the pool; 0 = automatic, the default),
- * "warps_per_sm" (0 = occupancy-derived), "kernel" (0 shared-memory slots, 1 lock-step first version),
+ * "warps_per_sm" (0 = occupancy-derived), "kernel" (2 work queues = default, 0 lane-bound shared-memory slots, 1 lock-step first version),
  * "tally_shared" (0/1, default auto),
  * "tally_aggregate" (0/1, lock-step kernel only: warp match/reduce before the shared-memory atomics). */
 int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value);

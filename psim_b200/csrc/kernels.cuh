@@ -60,10 +60,23 @@ __device__ __forceinline__ void atomic_add_i64(long long* p, long long v) {
 
 // Sensor::updateHeatParams (sensor.cpp:43-52): energy += sign, flux += sign * v.  Block stage in shared memory
 // (flushed with one global atomic per touched (sensor, step) at the end of the kernel) or straight to global.
+// Shared memory has no native 64-bit add (the compiler emits a compare-and-swap loop), so the staged flux is kept as
+// two 32-bit sums per component - the low 12 bits of every contribution (unsigned) and the rest (signed) - which native
+// ATOMS.ADD can accumulate; the exact 64-bit value (hi << 12) + lo is rebuilt at the flush.  That is exact as long as a
+// block adds fewer than 2^20 contributions to one entry in one launch; the host checks the bound (tally_shared == 1)
+// and otherwise asks for the 64-bit staging (tally_shared == 2).
 __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t local_row,
                                           uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
     const uint32_t S = a.P.n_sensors;
-    if (a.tally_shared) {
+    if (a.tally_shared == 1u) {
+        const uint32_t k = local_row * S + sensor;
+        uint32_t* f = reinterpret_cast<uint32_t*>(acc_f) + 4u * k;
+        atomicAdd(&acc_e[k], e);
+        atomicAdd(&f[0], static_cast<uint32_t>(fx) & 0xFFFu);
+        atomicAdd(reinterpret_cast<int32_t*>(&f[1]), fx >> 12);
+        atomicAdd(&f[2], static_cast<uint32_t>(fy) & 0xFFFu);
+        atomicAdd(reinterpret_cast<int32_t*>(&f[3]), fy >> 12);
+    } else if (a.tally_shared) {
         const uint32_t k = local_row * S + sensor;
         atomicAdd(&acc_e[k], e);
         atomic_add_i64(&acc_f[2 * k], fx);
@@ -96,7 +109,12 @@ __device__ __forceinline__ void tally_flush(const LaunchArgs& a, const int32_t* 
         if (row < a.P.first_tally_step) { continue; }
         const size_t k = static_cast<size_t>(row - a.P.first_tally_step) * S + (i % S);
         const int32_t e = acc_e[i];
-        const long long fx = acc_f[2 * i], fy = acc_f[2 * i + 1];
+        long long fx = acc_f[2 * i], fy = acc_f[2 * i + 1];
+        if (a.tally_shared == 1u) {
+            const uint32_t* f = reinterpret_cast<const uint32_t*>(acc_f) + 4u * i;
+            fx = static_cast<long long>(static_cast<int32_t>(f[1])) * 4096 + static_cast<long long>(f[0]);
+            fy = static_cast<long long>(static_cast<int32_t>(f[3])) * 4096 + static_cast<long long>(f[2]);
+        }
         if (e) { atomicAdd(&a.tally_e[k], e); }
         if (fx) { atomic_add_i64(&a.tally_f[2 * k], fx); }
         if (fy) { atomic_add_i64(&a.tally_f[2 * k + 1], fy); }

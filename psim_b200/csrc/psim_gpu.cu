@@ -73,6 +73,8 @@ struct psim_gpu {
     int64_t opt_tally_shared = -1;
     int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
+    uint32_t last_window = 0;
+    uint32_t max_flux_fixed = 0;     // largest |velocity| in flux fixed-point units
     std::string err;
 };
 
@@ -139,7 +141,7 @@ constexpr uint32_t kManySensors = 256;           // from here on global atomics 
 
 // Measurement intervals a launch may cover (its "window").
 uint32_t effective_steps_per_launch(const psim_gpu* h) {
-    return h->opt_steps_per_launch > 0 ? static_cast<uint32_t>(h->opt_steps_per_launch) : 16u;
+    return h->opt_steps_per_launch > 0 ? static_cast<uint32_t>(h->opt_steps_per_launch) : 32u;  // auto: as many as the staging holds
 }
 
 // How a launch that starts at step s0 tallies, and how far it may reach: windows without a recorded measurement need
@@ -235,6 +237,11 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
     }
     h->sm_count = prop.multiProcessorCount;
     if (int rc = psim::flatten_model(*desc, h->img, h->err)) { return bail(rc); }
+    {
+        float vmax = h->img.scalars.phasor ? 1000.f : 0.f;
+        for (float v : h->img.velocities) { vmax = std::max(vmax, std::fabs(v)); }
+        h->max_flux_fixed = static_cast<uint32_t>(std::min(4.0e9, std::ceil(static_cast<double>(vmax) * (1 << PSIM_FLUX_FRAC_BITS))));
+    }
     auto setup = [&]() -> int {
         if (int rc = upload(h, &h->d_cells, h->img.cells)) { return rc; }
         if (int rc = upload(h, &h->d_subs, h->img.subs)) { return rc; }
@@ -374,12 +381,22 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         h->birth_offset = static_cast<uint32_t>((h->birth_offset + ((a.n_births + 31) >> 5)) % h->n_warps);
         a.tally_e = h->tally_e;
         a.tally_f = h->tally_f;
-        a.tally_shared = shared ? 1u : 0u;
+        a.tally_shared = 0u;
+        if (shared) {
+            // native 32-bit staging of the flux (kernels.cuh:tally_add) is exact while one block adds fewer than 2^20
+            // contributions to one entry: it can add one per phonon it handles and step
+            const uint64_t chunks_per_warp = (((a.n_births + 31) >> 5) + h->n_warps - 1) / h->n_warps;
+            const uint64_t per_block = static_cast<uint64_t>(kWarpsPerBlock) * (h->seg_cap + chunks_per_warp * 32);
+            const uint64_t hi_max = (static_cast<uint64_t>(h->max_flux_fixed) >> 12) + 1;
+            const bool narrow = per_block < (1ull << 20) && per_block * hi_max < (1ull << 31) && h->opt_tally_shared != 2;
+            a.tally_shared = narrow ? 1u : 2u;
+        }
         a.tally_aggregate = h->opt_tally_aggregate ? 1u : 0u;
         a.stats = h->d_stats;
         a.alive_hist = h->d_alive_hist;
         a.launch_index = h->launches;
         h->last_tally_shared = a.tally_shared;
+        h->last_window = s1 - s0;
         if (!h->timing_open) {
             PSIM_CUDA(cudaEventRecord(h->ev_begin, st));
             h->timing_open = true;
@@ -505,7 +522,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     }
     out->kernel_ms = h->kernel_ms;
     out->launches = h->launches;
-    out->steps_per_launch = effective_steps_per_launch(h);
+    out->steps_per_launch = h->last_window ? h->last_window : effective_steps_per_launch(h);  // steps of the last launch
     out->warps = h->n_warps;
     out->tally_in_shared = h->last_tally_shared;
     out->image_bytes = h->img.cells.size() * sizeof(DevCell) + h->img.subs.size() * sizeof(DevSub) +

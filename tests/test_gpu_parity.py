@@ -70,8 +70,8 @@ def test_steps_per_launch_changes_only_rounding(name):
 
 
 def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
-    """Slots kernel (default) vs the lock-step first version, shared-memory vs global tallies, warp aggregation
-    on/off, different numbers of resident warps: a phonon's random stream is addressed by (id, step), so every
+    """Work-queue kernel (default, 2) vs the lane-bound slots kernel (0) vs the lock-step first version (1), tallies staged
+    in shared memory (1: native 32-bit halves, 2: 64-bit) vs straight to global memory, different numbers of resident warps: a phonon's random stream is addressed by (id, step), so every
     variant must produce the same integers (for the same launch windows: a periodic 20-sensor bar, whose tally
     staging fits shared memory for every window length used here)."""
     from psim_b200 import configs
@@ -80,7 +80,7 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
         ref = gpu_run_case(model, 5, steps_per_launch=spl, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
         for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 0, "tally_shared": 1},
                      {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "warps_per_sm": 8}, {"kernel": 2, "tally_shared": 1},
-                     {"kernel": 2, "tally_shared": 0}, {"kernel": 2, "warps_per_sm": 16}):
+                     {"kernel": 2, "tally_shared": 2}, {"kernel": 2, "tally_shared": 0}, {"kernel": 2, "warps_per_sm": 16}):
             got = gpu_run_case(model, 5, steps_per_launch=spl, options=opts, finish=False)
             assert np.array_equal(got["energy"], ref["energy"]), (spl, opts)
             assert np.array_equal(got["fixed"], ref["fixed"]), (spl, opts)
