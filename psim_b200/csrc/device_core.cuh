@@ -41,10 +41,10 @@ PSIM_HD float f_inf() { return __int_as_float(0x7f800000); }
 template<typename T> PSIM_HD T ldg(const T* p) { return __ldg(p); }
 PSIM_HD float4 load_cell_matrix(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const float4*>(cells + i)); }
 PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint4*>(cells + i) + 1); }
-PSIM_HD float2 load_cell_normal(const DevCell* cells, uint32_t i, uint32_t e) {
-    return __ldg(reinterpret_cast<const float2*>(cells + i) + 4 + e);
+PSIM_HD float2 load_cell_normal(const DevWall* walls, uint32_t i, uint32_t e) {
+    return __ldg(reinterpret_cast<const float2*>(walls + i) + e);
 }
-PSIM_HD float load_cell_spec(const DevCell* cells, uint32_t i) { return __ldg(&cells[i].spec); }
+PSIM_HD float load_cell_spec(const DevWall* walls, uint32_t i) { return __ldg(&walls[i].spec); }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) {
     const float4* q = reinterpret_cast<const float4*>(sensors + i);
     union { float4 v[2]; DevSensor s; } u;
@@ -71,12 +71,12 @@ PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) {
     q.x = cells[i].link[0], q.y = cells[i].link[1], q.z = cells[i].link[2], q.w = cells[i].sensor_mat;
     return q;
 }
-PSIM_HD float2 load_cell_normal(const DevCell* cells, uint32_t i, uint32_t e) {
+PSIM_HD float2 load_cell_normal(const DevWall* walls, uint32_t i, uint32_t e) {
     float2 n;
-    n.x = cells[i].n[e][0], n.y = cells[i].n[e][1];
+    n.x = walls[i].n[e][0], n.y = walls[i].n[e][1];
     return n;
 }
-PSIM_HD float load_cell_spec(const DevCell* cells, uint32_t i) { return cells[i].spec; }
+PSIM_HD float load_cell_spec(const DevWall* walls, uint32_t i) { return walls[i].spec; }
 PSIM_HD uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 PSIM_HD uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) { return sensors[i]; }
@@ -323,7 +323,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     (void)j;
     sample_table(P, em.table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
     place_on_edge(em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
-    const float2 n = load_cell_normal(P.cells, p.cell, em.edge);
+    const float2 n = load_cell_normal(P.walls, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
         p.packed = (p.packed & 0xFF000800u) | 1u | (PSIM_CELL_MAT(info.w) << 12);
         p.dx = n.x;
@@ -505,7 +505,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     // Random words this surface can consume - asked for at ONE place, and only if any is needed: a transition
     // into the same sensor area none, into another area 1 (new time to scatter), a blocked material interface 2
     // (back-scatter direction), a wall 3 (specular test + diffuse direction) unless it is perfectly specular.
-    const float spec = (kind == PSIM_LINK_TRANSITION) ? 0.f : load_cell_spec(P.cells, p.cell);
+    const float spec = (kind == PSIM_LINK_TRANSITION) ? 0.f : load_cell_spec(P.walls, p.cell);
     uint32_t ncell = 0u, nsm = 0u, need = (spec >= 1.f) ? 0u : 3u;
     bool pass = true;
     if (kind == PSIM_LINK_TRANSITION) {
@@ -530,7 +530,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
                 p.tts = draw_scatter_time(P, load_sensor(P.sensors, PSIM_CELL_SENSOR(nsm)), p, rng_u01(f.rng));
             }
         } else {  // back into the same cell, about the true inward normal
-            const float2 n = load_cell_normal(P.cells, p.cell, e);
+            const float2 n = load_cell_normal(P.walls, p.cell, e);
             const float u1 = rng_u01(f.rng), u2 = rng_u01(f.rng);
             diffuse_direction(u1, u2, n.x, n.y, p);
         }
@@ -539,7 +539,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
             const DevEmitter* em = P.emitters + PSIM_LINK_INDEX(link);
             if (step >= ldg(&em->k_on) && step < ldg(&em->k_off)) { return EV_DEAD; }  // absorbed
         }  // outside its window an emitting surface is an ordinary wall (surface.cpp:61-65)
-        const float2 n = load_cell_normal(P.cells, p.cell, e);
+        const float2 n = load_cell_normal(P.walls, p.cell, e);
         boundary_reflect(f.rng, spec, n.x, n.y, p);
     }
     update_rates_of_motion(f, p);

@@ -43,12 +43,15 @@
 #define PSIM_ALIGN(n) alignas(n)
 #endif
 
-// 64 bytes, ordered by how often the flight loop needs each 16-byte quad:
-//   quad 0 every interval, quad 1 every interval (sensor_mat) and every impact (links), quads 2-3 only on reflection.
+// What every flight segment and cell transition needs, 32 bytes per cell (two 16-byte loads); what only a reflection
+// needs lives in DevWall, so that a mesh of thousands of cells keeps twice as many cells in L1.
 struct PSIM_ALIGN(16) DevCell {
     float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [P2-P1 | P3-P1])
     uint32_t link[3];          // what lies behind each edge
     uint32_t sensor_mat;       // [31:12] sensor index, [11:4] rate class, [3:0] material index (PSIM_CELL_*)
+};
+
+struct PSIM_ALIGN(16) DevWall {
     float n[3][2];             // unit normals of edges 0..2 pointing INTO the cell (geometry.cpp:97-100)
     float spec;                // specularity of the cell's boundary surfaces, clamped to [0,1] (cell.cpp:115-119)
     uint32_t pad;
@@ -123,6 +126,7 @@ struct DevBirth {
 
 struct DevParams {
     const DevCell* cells;
+    const DevWall* walls;      // [n_cells]
     const DevSub* subs;
     const DevSensor* sensors;
     const DevMaterial* materials;

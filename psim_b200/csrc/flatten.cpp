@@ -163,6 +163,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
 
     // cells
     out.cells.resize(d.num_cells);
+    out.walls.resize(d.num_cells);
     for (uint32_t c = 0; c < d.num_cells; ++c) {
         const psim_cell& in = d.cells[c];
         if (in.sensor >= d.num_sensors) {
@@ -185,14 +186,15 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
             oy = static_cast<float>(y / n);
         };
         DevCell o{};
+        DevWall ow{};
         o.m00 = static_cast<float>(m00);
         o.m01 = static_cast<float>(m01);
         o.m10 = static_cast<float>(m10);
         o.m11 = static_cast<float>(m11);
-        unit(m10, m11, o.n[0][0], o.n[0][1]);                   // edge 0 is b2 = 0: inward = grad b2
-        unit(-(m00 + m10), -(m01 + m11), o.n[1][0], o.n[1][1]); // edge 1 is b1 + b2 = 1
-        unit(m00, m01, o.n[2][0], o.n[2][1]);                   // edge 2 is b1 = 0
-        o.spec = static_cast<float>(std::min(1., std::max(0., in.specularity)));
+        unit(m10, m11, ow.n[0][0], ow.n[0][1]);                   // edge 0 is b2 = 0: inward = grad b2
+        unit(-(m00 + m10), -(m01 + m11), ow.n[1][0], ow.n[1][1]); // edge 1 is b1 + b2 = 1
+        unit(m00, m01, ow.n[2][0], ow.n[2][1]);                   // edge 2 is b1 = 0
+        ow.spec = static_cast<float>(std::min(1., std::max(0., in.specularity)));
         o.sensor_mat = (in.sensor << 12) | (sensor_class[in.sensor] << 4) | d.sensors[in.sensor].material;
         for (int k = 0; k < 3; ++k) {
             const uint32_t n = in.sub_count[k], first = in.sub_first[k];
@@ -248,6 +250,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
             }
         }
         out.cells[c] = o;
+        out.walls[c] = ow;
     }
     if (out.subs.empty()) { out.subs.push_back(DevSub{}); }
     if (out.emitters.empty()) { out.emitters.push_back(DevEmitter{}); }

@@ -13,6 +13,7 @@ namespace psim {
 
 struct HostImage {
     std::vector<DevCell> cells;
+    std::vector<DevWall> walls;      // [cells]
     std::vector<DevSub> subs;
     std::vector<DevSensor> sensors;
     std::vector<DevMaterial> materials;

@@ -449,6 +449,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
 // which has headroom, not on the issue slots, which have none.
 // ---------------------------------------------------------------------------------------------------------------
 enum : int { Q_FLY = 0, Q_SCT, Q_WALL, Q_FIN, Q_FREE, Q_COUNT };
+#ifndef PSIM_FLY_FRONT
+#define PSIM_FLY_FRONT 1
+#endif
 
 template<int NS>
 __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const __grid_constant__ LaunchArgs a) {
@@ -700,11 +703,20 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             const unsigned m_wall = __ballot_sync(0xFFFFFFFFu, dest == Q_WALL), m_fin = __ballot_sync(0xFFFFFFFFu, dest == Q_FIN);
             if (dest >= 0) {
                 const unsigned peers = (dest == Q_FLY) ? m_fly : ((dest == Q_SCT) ? m_sct : ((dest == Q_WALL) ? m_wall : m_fin));
+#if PSIM_FLY_FRONT
+                // a slot that just entered a neighbour cell goes to the FRONT of the flight queue: its next segment runs
+                // while the cell record that the transition loaded is still in L1
+                const uint32_t tail = (dest == Q_FLY) ? q_fly.head - __popc(m_fly)
+#else
                 const uint32_t tail = (dest == Q_FLY) ? q_fly.head + q_fly.count
+#endif
                                                       : ((dest == Q_SCT) ? q_sct.head + q_sct.count
                                                                          : ((dest == Q_WALL) ? q_wall.head + q_wall.count : q_fin.head + q_fin.count));
                 qb[dest * NS + ((tail + __popc(peers & lt_mask)) & (NS - 1))] = static_cast<unsigned char>(k);
             }
+#if PSIM_FLY_FRONT
+            q_fly.head -= __popc(m_fly);
+#endif
             q_fly.count += __popc(m_fly);
             q_sct.count += __popc(m_sct);
             q_wall.count += __popc(m_wall);
@@ -835,7 +847,7 @@ __global__ void probe_flight_kernel(DevParams P, const uint32_t* cell, const flo
     const float t_hit = (fabsf(r1_rate) > fabsf(r2_rate)) ? (p.b1 - b1_start) / r1_rate : (p.b2 - b2_start) / r2_rate;
     float dx = p.dx, dy = p.dy;
     if (ev == psim::EV_IMPACT) {
-        const float2 nrm = psim::load_cell_normal(P.cells, p.cell, f.edge);
+        const float2 nrm = psim::load_cell_normal(P.walls, p.cell, f.edge);
         const float dn = dx * nrm.x + dy * nrm.y;
         dx -= 2.f * dn * nrm.x;
         dy -= 2.f * dn * nrm.y;

@@ -38,6 +38,7 @@ struct psim_gpu {
     psim::BirthPlan plan;
     DevParams P{};  // device pointers
     void* d_cells = nullptr;
+    void* d_walls = nullptr;
     void* d_subs = nullptr;
     void* d_sensors = nullptr;
     void* d_materials = nullptr;
@@ -69,7 +70,8 @@ struct psim_gpu {
     // options
     int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
     int64_t opt_warps_per_sm = 0;
-    int64_t opt_kernel = 2;          // 2: work-queue kernel (default), 0: lane-bound slots kernel, 1: lock-step kernel (both for A/B)
+    int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
+    bool kernel_chosen = false;      // false: psim_gpu_create picks 2 or 0 from the size of the mesh
     int64_t opt_tally_shared = -1;
     int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
@@ -242,8 +244,14 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         for (float v : h->img.velocities) { vmax = std::max(vmax, std::fabs(v)); }
         h->max_flux_fixed = static_cast<uint32_t>(std::min(4.0e9, std::ceil(static_cast<double>(vmax) * (1 << PSIM_FLUX_FRAC_BITS))));
     }
+    // Meshes whose cell records no longer fit L1 (> 4096 cells = 128 KB) make the flight loop wait on L2 instead of on the
+    // issue slots; there the lane-bound slots kernel (depth-first per lane, no bank conflicts, one dependent shared-memory
+    // load less per pass) measured 10 % faster than the work queues (kinked wire, 6174 cells: 261 vs 281 ms); on every
+    // smaller mesh the work queues win (profiles/r01_models.jsonl).  psim_gpu_set_option("kernel") overrides.
+    h->opt_kernel = (h->img.cells.size() > 4096) ? 0 : 2;
     auto setup = [&]() -> int {
         if (int rc = upload(h, &h->d_cells, h->img.cells)) { return rc; }
+        if (int rc = upload(h, &h->d_walls, h->img.walls)) { return rc; }
         if (int rc = upload(h, &h->d_subs, h->img.subs)) { return rc; }
         if (int rc = upload(h, &h->d_sensors, h->img.sensors)) { return rc; }
         if (int rc = upload(h, &h->d_materials, h->img.materials)) { return rc; }
@@ -253,6 +261,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         if (int rc = upload(h, &h->d_guides, h->img.guides)) { return rc; }
         h->P = h->img.scalars;
         h->P.cells = static_cast<const DevCell*>(h->d_cells);
+        h->P.walls = static_cast<const DevWall*>(h->d_walls);
         h->P.subs = static_cast<const DevSub*>(h->d_subs);
         h->P.sensors = static_cast<const DevSensor*>(h->d_sensors);
         h->P.materials = static_cast<const DevMaterial*>(h->d_materials);
@@ -525,7 +534,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     out->steps_per_launch = h->last_window ? h->last_window : effective_steps_per_launch(h);  // steps of the last launch
     out->warps = h->n_warps;
     out->tally_in_shared = h->last_tally_shared;
-    out->image_bytes = h->img.cells.size() * sizeof(DevCell) + h->img.subs.size() * sizeof(DevSub) +
+    out->image_bytes = h->img.cells.size() * (sizeof(DevCell) + sizeof(DevWall)) + h->img.subs.size() * sizeof(DevSub) +
                        h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
                        h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +
                        h->img.velocities.size() * sizeof(float);
@@ -556,6 +565,7 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
             return PSIM_E_STATE;
         }
         h->opt_kernel = value;
+        h->kernel_chosen = true;
     } else if (k == "tally_shared") {
         h->opt_tally_shared = value;
     } else if (k == "tally_aggregate") {
@@ -583,6 +593,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     free_pool(h);
     free_plan(h);
     cudaFree(h->d_cells);
+    cudaFree(h->d_walls);
     cudaFree(h->d_subs);
     cudaFree(h->d_sensors);
     cudaFree(h->d_materials);

@@ -26,6 +26,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     }
     DevParams P = img.scalars;
     P.cells = img.cells.data();
+    P.walls = img.walls.data();
     P.subs = img.subs.data();
     P.sensors = img.sensors.data();
     P.materials = img.materials.data();
