@@ -314,7 +314,7 @@ def run_ours(args):
                        "rng": "Philox4x32-10 keyed by (seed, phonon id, step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(per_gpu, last_stats["steps_per_launch"], args.steps_per_launch == 0),
-                         "peak_source": peak_src, "kernel": {0: "drift_kernel_slots<4>", 1: "drift_kernel_lockstep"}.get(args.kernel, "drift_kernel_queues<128>"),
+                         "peak_source": peak_src, "kernel": {0: "drift_kernel_slots<4>", 1: "drift_kernel_lockstep"}.get(last_stats["kernel"], "drift_kernel_queues<128>"),
                          "algorithmic_bytes_per_drift_step": ALGO_BYTES_PER_DRIFT_STEP,
                          "algorithmic_bytes_per_launch": float(np.mean(drift)) * ALGO_BYTES_PER_DRIFT_STEP / launches_per_job,
                          "avg_launch_ms": k_ms / launches_per_job, "launches_per_job": launches_per_job, "kernel_ms_per_job": k_ms,

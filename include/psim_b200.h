@@ -123,10 +123,13 @@ typedef struct psim_stats {
     uint32_t launches;                  /* drift-kernel launches of the last run */
     uint32_t steps_per_launch;
     uint32_t warps;                     /* resident warps = pool segments */
-    uint32_t tally_in_shared;           /* 1 if sensor tallies were staged in shared memory */
+    uint32_t tally_in_shared;           /* last launch: 0 tallies straight to global memory, 1 staged in shared memory as
+                                           32-bit halves, 2 staged as 64-bit sums */
     uint64_t image_bytes;               /* host->device bytes of the model image (psim_gpu_create) */
     uint64_t plan_bytes;                /* host->device bytes of the sources + birth plan (psim_gpu_set_sources) */
     uint64_t tally_bytes;               /* device->host bytes of psim_gpu_get_tallies */
+    uint32_t kernel;                    /* drift kernel in use: 2 work queues, 0 lane-bound slots, 1 lock step */
+    uint32_t reserved;
 } psim_stats;
 
 typedef struct psim_gpu psim_gpu;

@@ -534,6 +534,8 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     out->steps_per_launch = h->last_window ? h->last_window : effective_steps_per_launch(h);  // steps of the last launch
     out->warps = h->n_warps;
     out->tally_in_shared = h->last_tally_shared;
+    out->kernel = static_cast<uint32_t>(h->opt_kernel);
+    out->reserved = 0;
     out->image_bytes = h->img.cells.size() * (sizeof(DevCell) + sizeof(DevWall)) + h->img.subs.size() * sizeof(DevSub) +
                        h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
                        h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +

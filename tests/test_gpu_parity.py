@@ -88,6 +88,31 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
             assert got["stats"][0]["events"] == ref["stats"][0]["events"], (spl, opts)
 
 
+def test_handle_reuse_across_runs_is_bit_identical():
+    """The runs of a multi-run model go through ONE handle (psim_model_run): set_sources keeps the pool when the next
+    run fits and re-allocates when it does not; either way a run must equal the same run on a fresh handle."""
+    from psim_b200 import configs, lib as psim
+    model = T.load_model(configs.linear(num_phonons=60_000).to_dict())
+    fresh = {seed: gpu_run_case(model, seed, finish=False) for seed in (3, 4)}
+    big = T.load_model(configs.linear(num_phonons=6_000_000).to_dict())
+    big.prepare()
+    model.prepare()
+    g = psim.GpuSimulator(model.describe(), 0)
+    try:
+        for seed, m in ((3, model), (4, model), (9, big), (3, model)):  # same size, same size, grow, shrink
+            src, n = m.sources(seed)
+            g.set_sources(src, n, seed, 0, 1)
+            g.run()
+            e, f, fx = g.tallies(fixed=True)
+            if m is model:
+                assert np.array_equal(e, fresh[seed]["energy"]), seed
+                assert np.array_equal(fx, fresh[seed]["fixed"]), seed
+            else:
+                assert g.stats().total_phonons > 5_000_000
+    finally:
+        g.close()
+
+
 def test_device_sampling_matches_reference_bisection():
     """Material::freqIndex (material.cpp:64-75): the guided search of the flight loop, the plain bisection run on
     the device, and the same bisection run here in numpy on the fp32 table must give identical bins."""
