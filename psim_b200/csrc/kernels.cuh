@@ -68,14 +68,13 @@ __device__ __forceinline__ void atomic_add_i64(long long* p, long long v) {
 __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t local_row,
                                           uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
     const uint32_t S = a.P.n_sensors;
-    if (a.tally_shared == 1u) {
-        const uint32_t k = local_row * S + sensor;
-        uint32_t* f = reinterpret_cast<uint32_t*>(acc_f) + 4u * k;
-        atomicAdd(&acc_e[k], e);
-        atomicAdd(&f[0], static_cast<uint32_t>(fx) & 0xFFFu);
-        atomicAdd(reinterpret_cast<int32_t*>(&f[1]), fx >> 12);
-        atomicAdd(&f[2], static_cast<uint32_t>(fy) & 0xFFFu);
-        atomicAdd(reinterpret_cast<int32_t*>(&f[3]), fy >> 12);
+    if (a.tally_shared == 1u) {  // five consecutive 32-bit words per (step, sensor): e, fx low / high, fy low / high
+        uint32_t* q = reinterpret_cast<uint32_t*>(acc_e) + 5u * (local_row * S + sensor);
+        atomicAdd(reinterpret_cast<int32_t*>(q), e);
+        atomicAdd(q + 1, static_cast<uint32_t>(fx) & 0xFFFu);
+        atomicAdd(reinterpret_cast<int32_t*>(q + 2), fx >> 12);
+        atomicAdd(q + 3, static_cast<uint32_t>(fy) & 0xFFFu);
+        atomicAdd(reinterpret_cast<int32_t*>(q + 4), fy >> 12);
     } else if (a.tally_shared) {
         const uint32_t k = local_row * S + sensor;
         atomicAdd(&acc_e[k], e);
@@ -92,10 +91,14 @@ __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, l
 __device__ __forceinline__ void tally_init(const LaunchArgs& a, int32_t* acc_e, long long* acc_f) {
     if (!a.tally_shared) { return; }
     const uint32_t n = (a.step_end - a.step_begin) * a.P.n_sensors;
-    for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
-        acc_e[i] = 0;
-        acc_f[2 * i] = 0;
-        acc_f[2 * i + 1] = 0;
+    if (a.tally_shared == 1u) {
+        for (uint32_t i = threadIdx.x; i < 5u * n; i += kBlock) { acc_e[i] = 0; }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
+            acc_e[i] = 0;
+            acc_f[2 * i] = 0;
+            acc_f[2 * i + 1] = 0;
+        }
     }
     __syncthreads();
 }
@@ -108,12 +111,17 @@ __device__ __forceinline__ void tally_flush(const LaunchArgs& a, const int32_t* 
         const uint32_t row = a.step_begin + i / S + 1;
         if (row < a.P.first_tally_step) { continue; }
         const size_t k = static_cast<size_t>(row - a.P.first_tally_step) * S + (i % S);
-        const int32_t e = acc_e[i];
-        long long fx = acc_f[2 * i], fy = acc_f[2 * i + 1];
+        int32_t e;
+        long long fx, fy;
         if (a.tally_shared == 1u) {
-            const uint32_t* f = reinterpret_cast<const uint32_t*>(acc_f) + 4u * i;
-            fx = static_cast<long long>(static_cast<int32_t>(f[1])) * 4096 + static_cast<long long>(f[0]);
-            fy = static_cast<long long>(static_cast<int32_t>(f[3])) * 4096 + static_cast<long long>(f[2]);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(acc_e) + 5u * i;
+            e = static_cast<int32_t>(q[0]);
+            fx = static_cast<long long>(static_cast<int32_t>(q[2])) * 4096 + static_cast<long long>(q[1]);
+            fy = static_cast<long long>(static_cast<int32_t>(q[4])) * 4096 + static_cast<long long>(q[3]);
+        } else {
+            e = acc_e[i];
+            fx = acc_f[2 * i];
+            fy = acc_f[2 * i + 1];
         }
         if (e) { atomicAdd(&a.tally_e[k], e); }
         if (fx) { atomic_add_i64(&a.tally_f[2 * k], fx); }
@@ -449,6 +457,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
 // which has headroom, not on the issue slots, which have none.
 // ---------------------------------------------------------------------------------------------------------------
 enum : int { Q_FLY = 0, Q_SCT, Q_WALL, Q_FIN, Q_FREE, Q_COUNT };
+#ifndef PSIM_PREFETCH_DIST
+#define PSIM_PREFETCH_DIST 0
+#endif
 #ifndef PSIM_FLY_FRONT
 #define PSIM_FLY_FRONT 1
 #endif
@@ -604,6 +615,12 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots
             const uint32_t k = pop(q_free, Q_FREE, c_acq, act);
             bool got = false;
+#if PSIM_PREFETCH_DIST > 0
+            if (next + PSIM_PREFETCH_DIST + lane < n_in) {  // the records this warp fetches a few passes from now
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_a + seg + next + PSIM_PREFETCH_DIST + lane));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_b + seg + next + PSIM_PREFETCH_DIST + lane));
+            }
+#endif
             if (act) {
                 const uint32_t idx = next + lane;
                 psim::Phonon p;
