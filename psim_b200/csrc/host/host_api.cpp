@@ -250,9 +250,14 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
         m.runs.clear();
         for (uint64_t run = 0; run < m.num_runs; ++run) {
             if (verbose) { std::cout << "Run: " << run + 1 << '\n'; }
+            const auto h0 = std::chrono::steady_clock::now();
             m.prepare();
             const psim_model_desc& desc = m.describe();
             const auto sources = m.source_counts(seed + run);
+            if (std::getenv("PSIM_TIMING")) {
+                std::cerr << "psim timing [ms]: prepare+describe+sources "
+                          << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count() << '\n';
+            }
             const size_t n_tally = m.sensors.size() * m.recorded_steps;
             std::vector<std::vector<int32_t>> energy(G, std::vector<int32_t>(n_tally));
             std::vector<std::vector<int64_t>> fixed(G, std::vector<int64_t>(2 * n_tally));
@@ -261,6 +266,10 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
             std::vector<std::string> errors(G);
             auto work = [&](size_t d) {
                 int e = PSIM_OK;
+                const bool timing = std::getenv("PSIM_TIMING") != nullptr;  // phase times of device 0's thread on stderr
+                auto now = [] { return std::chrono::steady_clock::now(); };
+                auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                const auto t0 = now();
                 if (!gpus[d]) {
                     e = psim_gpu_create(&desc, devices[d], &gpus[d]);
                     if (e) {
@@ -269,10 +278,17 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                         e = psim_gpu_set_option(gpus[d], "steps_per_launch", steps_per_launch);
                     }
                 }
+                const auto t1 = now();
                 if (!e) { e = psim_gpu_set_sources(gpus[d], sources.data(), sources.size(), seed + run, static_cast<uint32_t>(d), static_cast<uint32_t>(G)); }
+                const auto t2 = now();
                 if (!e) { e = psim_gpu_run(gpus[d]); }
+                const auto t3 = now();
                 if (!e) { e = psim_gpu_get_tallies(gpus[d], energy[d].data(), nullptr, fixed[d].data()); }
                 if (!e) { e = psim_gpu_get_stats(gpus[d], &st[d]); }
+                if (timing && d == 0) {
+                    std::cerr << "psim timing [ms]: create " << ms(t0, t1) << " set_sources " << ms(t1, t2) << " run " << ms(t2, t3)
+                              << " tallies " << ms(t3, now()) << '\n';
+                }
                 if (e && errors[d].empty() && gpus[d]) { errors[d] = psim_gpu_last_error(gpus[d]); }
                 codes[d] = e;
             };
@@ -311,15 +327,25 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     stats->kernel_ms = std::max(stats->kernel_ms, st[d].kernel_ms);
                 }
             }
+            const auto h1 = std::chrono::steady_clock::now();
             m.set_tallies(energy[0].data(), flux.data());
             std::string log;
             m.finish_run(run, &log);
+            if (std::getenv("PSIM_TIMING")) {
+                std::cerr << "psim timing [ms]: epilogue "
+                          << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h1).count() << '\n';
+            }
             if (verbose) { std::cout << log; }
             if (run + 1 < m.num_runs) { m.reset_for_next_run(); }
         }
         return PSIM_OK;
     });
+    const auto t_destroy = std::chrono::steady_clock::now();
     for (psim_gpu* g : gpus) { psim_gpu_destroy(g); }
+    if (std::getenv("PSIM_TIMING")) {
+        std::cerr << "psim timing [ms]: destroy "
+                  << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_destroy).count() << '\n';
+    }
     return rc;
 }
 

@@ -1,9 +1,22 @@
 #!/bin/bash
-mkdir -p gpurun_out
-for n in 8 4; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
+# weak-scaling runs of bench.py on one box (use with gpurun --gpus 8).  usage: tools/gpu_scale.sh [tag]
+tag=${1:-r01}
+out=gpurun_out/evidence
+mkdir -p $out
+for n in 8 4 2; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 3 > $out/${tag}_bench_n$n.json 2> $out/scale_$n.err
 python -c "
 import json
-d=json.load(open('gpurun_out/scale_$n.json')); print($n, d['value']/1e9, d['ms_per_step'], d['roofline']['frac'], d['e2e']['value']/1e9)"
+d=json.load(open('$out/${tag}_bench_n$n.json')); print($n, d['value']/1e9, d['ms_per_step'], d['roofline']['frac'], d['e2e']['value']/1e9, d['e2e']['ms_per_step'])"
 done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/scale_ref2.json 2> gpurun_out/scale_ref2.err; cat gpurun_out/scale_ref2.json | cut -c1-300
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > $out/scale_ref2.json 2> $out/scale_ref2.err; cut -c1-200 $out/scale_ref2.json
+PSIM_DEVICES=0,1,2,3,4,5,6,7 PSIM_TIMING=1 python - <<'PY'
+import json, sys, time
+sys.path.insert(0, '.')
+from psim_b200 import configs, lib as psim
+m = psim.Model(text=json.dumps(configs.si_ge_grid(num_phonons=800_000_000).to_dict()))
+t0 = time.perf_counter()
+st = m.run_devices(list(range(8)), seed=1)
+print("run_devices 8 GPUs, 8e8 phonons: wall %.3f s, kernel_ms (max) %.1f, drift-steps %.4g -> %.4g /s (kernel)" % (
+    time.perf_counter() - t0, st.kernel_ms, st.drift_steps, st.drift_steps / (st.kernel_ms * 1e-3)))
+PY
