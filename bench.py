@@ -148,6 +148,28 @@ def oracle_cpu_run(model: dict, phonons: int, threads: int, drift_steps_per_phon
 
 
 # --------------------------------------------------------------------------------------------------------- ours
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Everything libraries write to stdout (NCCL's version banner, for one) goes to stderr from here on; the result line
+    alone is written to the real stdout by emit()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -339,7 +361,7 @@ def run_ours(args):
             else:
                 out["cpu_baseline"] = {"value": None, "unit": "drift-steps/s", "cores": cores, "kind": "reference",
                                        "sample": "oracle/_ref/psim_ref not present on this box"}
-        print(json.dumps(out), flush=True)
+        emit(out)
     g.close()
     if world > 1:
         dist.barrier()
@@ -360,7 +382,7 @@ def run_reference(args):
     for it in range(args.warmup + args.steps):
         r = reference_cpu_run(model, args.cpu_phonons_per_core, cores, per_phonon)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "reference run failed"}))
+            emit({"impl": "reference", "unavailable": "reference run failed"})
             return
         kind = r["kind"]
         if it >= args.warmup:
@@ -369,7 +391,7 @@ def run_reference(args):
     v = float(np.mean(vals))
     sample = (f"{cores} processes x {args.cpu_phonons_per_core} phonons of the same model per step; "
               f"{per_phonon} drift-steps per phonon (counted by the CUDA path on this model)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "drift-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -377,7 +399,7 @@ def run_reference(args):
                    "phonons_per_step": args.cpu_phonons_per_core * cores},
         "cpu_baseline": {"value": v, "unit": "drift-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "drift-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def main():
@@ -397,6 +419,7 @@ def main():
     ap.add_argument("--ref-drift-steps-per-phonon", type=float, default=133.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

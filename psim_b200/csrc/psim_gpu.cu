@@ -129,10 +129,14 @@ size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
     return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
 }
 
-constexpr size_t kTallyStageBudget = PSIM_STAGE_KB * 1024;  // per block; with the slot storage this keeps kSlotBlocks blocks per SM
 constexpr int kQueueSlots = 32 * kSlots;                     // slots per warp of the queues kernel
 constexpr size_t kQueueBytesPerBlock = kSlotBytesPerBlock + static_cast<size_t>(Q_COUNT) * kQueueSlots * kWarpsPerBlock;
-constexpr size_t kTallyStageBudgetQueues = kTallyStageBudget - 6 * 1024;
+// what a block may use so that kSlotBlocks blocks (plus 1 KB each that the driver reserves) fit the planned carve-out;
+// the tally staging gets what the slot storage leaves
+constexpr size_t kSmemPerBlock = static_cast<size_t>(PSIM_SMEM_KB_PER_SM) * 1024 / kSlotBlocks - 1024;
+static_assert(kSmemPerBlock > kQueueBytesPerBlock + 4096, "no room for the tally staging");
+constexpr size_t kTallyStageBudget = kSmemPerBlock - kSlotBytesPerBlock;
+constexpr size_t kTallyStageBudgetQueues = kSmemPerBlock - kQueueBytesPerBlock;
 
 size_t stage_budget(const psim_gpu* h) {
     return h->opt_kernel == 1 ? 100 * 1024 : (h->opt_kernel == 2 ? kTallyStageBudgetQueues : kTallyStageBudget);
@@ -143,7 +147,7 @@ constexpr uint32_t kManySensors = 256;           // from here on global atomics 
 
 // Measurement intervals a launch may cover (its "window").
 uint32_t effective_steps_per_launch(const psim_gpu* h) {
-    return h->opt_steps_per_launch > 0 ? static_cast<uint32_t>(h->opt_steps_per_launch) : 32u;  // auto: as many as the staging holds
+    return h->opt_steps_per_launch > 0 ? static_cast<uint32_t>(h->opt_steps_per_launch) : 64u;  // auto: as many as the staging holds
 }
 
 // How a launch that starts at step s0 tallies, and how far it may reach: windows without a recorded measurement need
@@ -278,8 +282,8 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaEventCreate(&h->ev_begin));
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
