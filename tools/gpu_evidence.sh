@@ -8,12 +8,12 @@ python bench.py --steps 5 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/bench_n
 python bench.py --impl reference --steps 1 --warmup 0 > $out/${tag}_bench_reference_cpu.json 2> $out/bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_bench.log 2>&1
-# DRAM traffic of every launch of one job (7 launches), then the two --set full captures (long window, recorded window)
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:drift_kernel -c 7 --csv \
+# DRAM traffic of every launch of one job (4 launches), then the two --set full captures (long window, recorded window)
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:drift_kernel -c 4 --csv \
     --log-file $out/${tag}_dram_per_launch.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $out/dram_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 0 -c 1 -f -o $out/prof_long \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $out/ncu_long.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 3 -c 1 -f -o $out/prof_rec \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 2 -c 1 -f -o $out/prof_rec \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $out/ncu_rec.log 2>&1
 timeout 900 python tools/model_walltimes.py 2> $out/models.err > $out/${tag}_models.jsonl
 timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python bench.py --phonons 200000 --steps 1 --warmup 0 --no-cpu-baseline \
