@@ -724,29 +724,27 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 slot_f(SF_T, k) = f.t;
                 slot_u(SF_MISC, k) = misc;
             }
-            // four-way push with one address computation
-            const unsigned m_fly = __ballot_sync(0xFFFFFFFFu, dest == Q_FLY), m_sct = __ballot_sync(0xFFFFFFFFu, dest == Q_SCT);
-            const unsigned m_wall = __ballot_sync(0xFFFFFFFFu, dest == Q_WALL), m_fin = __ballot_sync(0xFFFFFFFFu, dest == Q_FIN);
-            if (dest >= 0) {
-                const unsigned peers = (dest == Q_FLY) ? m_fly : ((dest == Q_SCT) ? m_sct : ((dest == Q_WALL) ? m_wall : m_fin));
+            // four-way push with one address computation (selects on warp-uniform values, no branches)
+            const bool d_fly = dest == Q_FLY, d_sct = dest == Q_SCT, d_wall = dest == Q_WALL, d_fin = dest == Q_FIN;
+            const unsigned m_fly = __ballot_sync(0xFFFFFFFFu, d_fly), m_sct = __ballot_sync(0xFFFFFFFFu, d_sct);
+            const unsigned m_wall = __ballot_sync(0xFFFFFFFFu, d_wall), m_fin = __ballot_sync(0xFFFFFFFFu, d_fin);
+            const uint32_t n_fly = __popc(m_fly), n_sct = __popc(m_sct), n_wall = __popc(m_wall), n_fin = __popc(m_fin);
 #if PSIM_FLY_FRONT
-                // a slot that just entered a neighbour cell goes to the FRONT of the flight queue: its next segment runs
-                // while the cell record that the transition loaded is still in L1
-                const uint32_t tail = (dest == Q_FLY) ? q_fly.head - __popc(m_fly)
+            // a slot that just entered a neighbour cell goes to the FRONT of the flight queue: its next segment runs
+            // while the cell record that the transition loaded is still in L1
+            q_fly.head -= n_fly;
+            const uint32_t t_fly = q_fly.head;
 #else
-                const uint32_t tail = (dest == Q_FLY) ? q_fly.head + q_fly.count
+            const uint32_t t_fly = q_fly.head + q_fly.count;
 #endif
-                                                      : ((dest == Q_SCT) ? q_sct.head + q_sct.count
-                                                                         : ((dest == Q_WALL) ? q_wall.head + q_wall.count : q_fin.head + q_fin.count));
-                qb[dest * NS + ((tail + __popc(peers & lt_mask)) & (NS - 1))] = static_cast<unsigned char>(k);
-            }
-#if PSIM_FLY_FRONT
-            q_fly.head -= __popc(m_fly);
-#endif
-            q_fly.count += __popc(m_fly);
-            q_sct.count += __popc(m_sct);
-            q_wall.count += __popc(m_wall);
-            q_fin.count += __popc(m_fin);
+            const uint32_t t_sct = q_sct.head + q_sct.count, t_wall = q_wall.head + q_wall.count, t_fin = q_fin.head + q_fin.count;
+            const unsigned peers = d_fly ? m_fly : (d_sct ? m_sct : (d_wall ? m_wall : m_fin));
+            const uint32_t tail = d_fly ? t_fly : (d_sct ? t_sct : (d_wall ? t_wall : t_fin));
+            if (dest >= 0) { qb[dest * NS + ((tail + __popc(peers & lt_mask)) & (NS - 1))] = static_cast<unsigned char>(k); }
+            q_fly.count += n_fly;
+            q_sct.count += n_sct;
+            q_wall.count += n_wall;
+            q_fin.count += n_fin;
         }
     }
     n_out = min(n_out, a.seg_cap);
