@@ -148,7 +148,7 @@ PSIM_HD float rng_u01(Rng& r) { return u01_from24(rng_word(r)); }
 
 struct Phonon {
     float b1, b2;     // position in the current cell's frame
-    float dx, dy;     // direction; in-plane speed = velocity * |d|   (phonon.cpp:28-31)
+    float dx, dy;     // in-plane velocity (m/s) = group velocity * direction, |direction| <= 1   (phonon.cpp:28-31)
     float tts;        // time to the next intrinsic scatter (ns); carried from interval to interval like the
                       // reference's time_to_scatter (modelSimulator.cpp:145,155,180)
     uint32_t packed;  // see device_types.h
@@ -228,29 +228,29 @@ PSIM_HD void relax_rates(const DevSensor& s, float w, uint32_t ta, float& rn, fl
 }
 
 // Phonon::setRandDirection (phonon.cpp:28-31)
-PSIM_HD void isotropic_direction(float u1, float u2, Phonon& p) {
+PSIM_HD void isotropic_direction(float u1, float u2, float vel, Phonon& p) {
     const float dx = 2.f * u1 - 1.f;
-    p.dx = dx;
-    p.dy = f_sqrt(fmaxf(1.f - dx * dx, 0.f)) * f_cos2pi(u2);
+    p.dx = vel * dx;
+    p.dy = vel * (f_sqrt(fmaxf(1.f - dx * dx, 0.f)) * f_cos2pi(u2));
 }
 
 // Surface::redirectPhonon (surface.cpp:23-30): cosine-law direction about the inward normal n
-PSIM_HD void diffuse_direction(float u1, float u2, float nx, float ny, Phonon& p) {
+PSIM_HD void diffuse_direction(float u1, float u2, float nx, float ny, float vel, Phonon& p) {
     const float a = f_sqrt(u1);
     const float b = f_sqrt(fmaxf(1.f - u1, 0.f)) * f_cos2pi(u2);
-    p.dx = nx * a - ny * b;
-    p.dy = ny * a + nx * b;
+    p.dx = vel * (nx * a - ny * b);
+    p.dy = vel * (ny * a + nx * b);
 }
 
 // Surface::boundaryHandlePhonon (surface.cpp:32-44); needs up to 3 unread random words
-PSIM_HD void boundary_reflect(Rng& rng, float spec, float nx, float ny, Phonon& p) {
+PSIM_HD void boundary_reflect(Rng& rng, float spec, float nx, float ny, float vel, Phonon& p) {
     if (spec >= 1.f || rng_u01(rng) < spec) {
         const float dn = p.dx * nx + p.dy * ny;
         p.dx -= 2.f * dn * nx;
         p.dy -= 2.f * dn * ny;
     } else {
         const float u1 = rng_u01(rng), u2 = rng_u01(rng);
-        diffuse_direction(u1, u2, nx, ny, p);
+        diffuse_direction(u1, u2, nx, ny, vel, p);
     }
 }
 
@@ -307,7 +307,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
         }
         p.b1 = r1;
         p.b2 = r2;
-        isotropic_direction(u_c, u_d, p);
+        isotropic_direction(u_c, u_d, vel, p);
         rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
         p.tts = draw_scatter_time(P, s, p, rng_u01(rng));
         return P.step_time;  // born at t = 0
@@ -326,10 +326,10 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     const float2 n = load_cell_normal(P.walls, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
         p.packed = (p.packed & 0xFF000800u) | 1u | (PSIM_CELL_MAT(info.w) << 12);
-        p.dx = n.x;
-        p.dy = n.y;
+        p.dx = 1000.f * n.x;
+        p.dy = 1000.f * n.y;
     } else {
-        diffuse_direction(u_b, u_c, n.x, n.y, p);
+        diffuse_direction(u_b, u_c, n.x, n.y, vel, p);
     }
     p.tts = draw_scatter_time(P, load_sensor(P.sensors, PSIM_CELL_SENSOR(info.w)), p, u_d);
     return static_cast<float>((1. - frac) * P.step_time_d);
@@ -373,9 +373,8 @@ PSIM_HD void set_cell_matrix(Flight& f, const float4 m) {
 }
 
 PSIM_HD void update_rates_of_motion(Flight& f, const Phonon& p) {
-    const float vx = p.dx * f.vel, vy = p.dy * f.vel;
-    f.r1 = f.m00 * vx + f.m01 * vy;
-    f.r2 = f.m10 * vx + f.m11 * vy;
+    f.r1 = f.m00 * p.dx + f.m01 * p.dy;
+    f.r2 = f.m10 * p.dx + f.m11 * p.dy;
 }
 
 PSIM_HD float draw_scatter_time(const DevParams& P, const DevSensor& sen, const Phonon& p, float u) {
@@ -532,7 +531,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
         } else {  // back into the same cell, about the true inward normal
             const float2 n = load_cell_normal(P.walls, p.cell, e);
             const float u1 = rng_u01(f.rng), u2 = rng_u01(f.rng);
-            diffuse_direction(u1, u2, n.x, n.y, p);
+            diffuse_direction(u1, u2, n.x, n.y, f.vel, p);
         }
     } else {
         if (kind == PSIM_LINK_EMIT) {
@@ -540,7 +539,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
             if (step >= ldg(&em->k_on) && step < ldg(&em->k_off)) { return EV_DEAD; }  // absorbed
         }  // outside its window an emitting surface is an ordinary wall (surface.cpp:61-65)
         const float2 n = load_cell_normal(P.walls, p.cell, e);
-        boundary_reflect(f.rng, spec, n.x, n.y, p);
+        boundary_reflect(f.rng, spec, n.x, n.y, f.vel, p);
     }
     update_rates_of_motion(f, p);
     if (++f.ncoll > PSIM_MAX_COLLISIONS) {
@@ -575,10 +574,17 @@ PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t st
     const uint32_t u_jit = w0 & 0xFFu;
     const float u_d1 = u01_hi16(w3), u_d2 = u01_lo16(w3), u_tts = u01_from24(w2);
     if (r <= rn + ru) {
+        const float vel_old = f.vel;
         sample_table(P, sen.scatter_table, PSIM_CELL_MAT(f.sensor_mat), u_bin, u_pol, u_jit, p, f.vel);
-        if (r > rn) { isotropic_direction(u_d1, u_d2, p); }  // Umklapp
+        if (r > rn) {  // Umklapp: new direction as well
+            isotropic_direction(u_d1, u_d2, f.vel, p);
+        } else {       // normal process: same direction, new group velocity
+            const float scale = f_div(f.vel, vel_old);
+            p.dx *= scale;
+            p.dy *= scale;
+        }
     } else if (ri > 0.f) {
-        isotropic_direction(u_d1, u_d2, p);
+        isotropic_direction(u_d1, u_d2, f.vel, p);
     }
     f.ncoll = 0;
     p.tts = draw_scatter_time(P, sen, p, u_tts);

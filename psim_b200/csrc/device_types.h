@@ -112,7 +112,7 @@ struct DevBirth {
 };
 
 // Phonon state in HBM: two 16-byte words per phonon, structure-of-arrays.
-//   A = (b1, b2, dx, dy)            position in the cell frame, direction (|d| <= 1: 3-D direction projected)
+//   A = (b1, b2, vx, vy)            position in the cell frame, in-plane velocity = group velocity x projected 3-D direction
 //   B = (tts, packed, cell, id)     tts = time to the next intrinsic scatter (ns)
 //                                   packed = [9:0] bin, [10] polarisation (1 = TA), [11] sign (1 = negative),
 //                                            [15:12] material the (omega, v) pair was sampled in,

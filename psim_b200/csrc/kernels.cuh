@@ -405,11 +405,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 const uint32_t s0 = a.step_begin + PSIM_MISC_STEP(misc);
                 uint32_t s = s0;
                 const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
-                    const uint32_t packed = slot_u(SF_PACKED, k);
-                    const float vel = psim::phonon_velocity(P, packed);
-                    const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
+                    const int32_t sg = PSIM_PACK_NEG(slot_u(SF_PACKED, k)) ? -1 : 1;
                     const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
-                    const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k) * vel) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k) * vel) * sg;
+                    const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k)) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k)) * sg;
                     for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, sg, fx, fy); }
                 });
                 ++n_events;
@@ -424,7 +422,6 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     p.dy = slot_f(SF_DY, k);
                     p.cell = slot_u(SF_CELL, k);
                     f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
-                    f.vel = psim::phonon_velocity(P, slot_u(SF_PACKED, k));
                     if (psim::fast_transition(P, p, f)) {
                         slot_u(SF_CELL, k) = p.cell;
                         slot_f(SF_R1, k) = f.r1;
@@ -687,11 +684,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 const uint32_t s0 = a.step_begin + PSIM_MISC_STEP(misc);
                 uint32_t s = s0;
                 const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
-                    const uint32_t packed = slot_u(SF_PACKED, k);
-                    const float vel = psim::phonon_velocity(P, packed);
-                    const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
+                    const int32_t sg = PSIM_PACK_NEG(slot_u(SF_PACKED, k)) ? -1 : 1;
                     const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
-                    const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k) * vel) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k) * vel) * sg;
+                    const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k)) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k)) * sg;
                     for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, sg, fx, fy); }
                 });
                 ++n_events;
@@ -705,7 +700,6 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                     p.dy = slot_f(SF_DY, k);
                     p.cell = slot_u(SF_CELL, k);
                     f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
-                    f.vel = psim::phonon_velocity(P, slot_u(SF_PACKED, k));
                     if (psim::fast_transition(P, p, f)) {
                         slot_u(SF_CELL, k) = p.cell;
                         slot_f(SF_R1, k) = f.r1;
@@ -795,7 +789,7 @@ __global__ void __launch_bounds__(kBlock, (kBlock <= 256 ? 2 : 1)) drift_kernel_
             alive = psim::advance_window(P, p, t_first, start, a.step_end, n_steps, n_events,
                                          [&](uint32_t k0, uint32_t k1, const psim::Phonon& q, const psim::Flight& f) {
                 const int32_t sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
-                const int32_t fx = psim::flux_fixed(q.dx * f.vel) * sg, fy = psim::flux_fixed(q.dy * f.vel) * sg;
+                const int32_t fx = psim::flux_fixed(q.dx) * sg, fy = psim::flux_fixed(q.dy) * sg;
                 for (uint32_t ks = k0; ks < k1; ++ks) {
                     tally_add(a, acc_e, acc_f, ks - a.step_begin, PSIM_CELL_SENSOR(f.sensor_mat), sg, fx, fy);
                 }
@@ -850,8 +844,8 @@ __global__ void probe_flight_kernel(DevParams P, const uint32_t* cell, const flo
     p.b2 = in[4 * i + 1];
     const float vx = in[4 * i + 2], vy = in[4 * i + 3];
     const float speed = sqrtf(vx * vx + vy * vy);
-    p.dx = vx / speed;
-    p.dy = vy / speed;
+    p.dx = vx;  // the state carries the velocity vector
+    p.dy = vy;
     p.tts = psim::f_inf();
     p.cell = cell[i];
     p.packed = 0u;
@@ -880,8 +874,8 @@ __global__ void probe_flight_kernel(DevParams P, const uint32_t* cell, const flo
     out[6 * i + 1] = t_hit;
     out[6 * i + 2] = p.b1;
     out[6 * i + 3] = p.b2;
-    out[6 * i + 4] = dx;
-    out[6 * i + 5] = dy;
+    out[6 * i + 4] = dx / speed;  // unit direction after a specular reflection
+    out[6 * i + 5] = dy / speed;
 }
 
 __global__ void probe_rates_kernel(DevParams P, uint32_t sensor, const float* w, const uint32_t* ta, size_t n, float* out) {

@@ -1,7 +1,7 @@
 // sm_100a kernels and the C ABI of include/psim_b200.h.
 //
 // Data layout in HBM
-//   phonon pool   two ping-pong copies of  A: float4[W][cap] (b1, b2, dx, dy)   B: uint4[W][cap] (omega, packed, cell, id)
+//   phonon pool   two ping-pong copies of  A: float4[W][cap] (b1, b2, vx, vy)   B: uint4[W][cap] (tts, packed, cell, id)
 //                 W = number of resident warps of the drift kernel.  Warp w owns segment w of both copies:
 //                 it streams its segment of the input copy (two fully coalesced 16-byte loads per lane),
 //                 advances every phonon across the measurement intervals of this launch, and appends the

@@ -54,8 +54,8 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
             for (uint32_t ks = k0; ks < k1; ++ks) {
                 const size_t k = static_cast<size_t>(ks + 1 - P.first_tally_step) * S + PSIM_CELL_SENSOR(f.sensor_mat);
                 te[k] += sg;
-                tf[2 * k] += static_cast<long long>(psim::flux_fixed(q.dx * f.vel)) * sg;
-                tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(q.dy * f.vel)) * sg;
+                tf[2 * k] += static_cast<long long>(psim::flux_fixed(q.dx)) * sg;
+                tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(q.dy)) * sg;
             }
         });
         total_events += n_events;
