@@ -88,6 +88,46 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
             assert got["stats"][0]["events"] == ref["stats"][0]["events"], (spl, opts)
 
 
+FULL_SIZE = {"sige": 100_000_000, "linear_demo": 5_000_000, "sides_ss": 10_000_000, "sides_trans": 10_000_000}
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_runs_agree_with_reduced_size_reference(name):
+    """BASELINE.json's full phonon counts.  The reference cannot be run at these sizes in the test budget, but in
+    deviational mode the expectation of every temperature / flux is independent of the number of phonons (the energy per
+    phonon scales as 1/N), so the full-size GPU result - whose own noise is 5-20x smaller - must lie within the
+    reference's seed-to-seed scatter at the reduced size (z per entry against sigma_ref / sqrt(16), bulk, bias and
+    extremes bounded).  Also at full size: sharding by phonon id changes no integer (2 shards vs 1)."""
+    gold = T.golden(name)
+    reduced = T.case_model(name)["settings"]["num_phonons"]
+    model = T.load_model(T.case_model(name), num_phonons=FULL_SIZE[name])
+    one = gpu_run_case(model, 11)
+    feats = T.run_features(one["energy"], one["flux"], model.info.sim_type, one["six"], one["temps"], one["fluxes"])
+    assert one["stats"][0]["total_phonons"] >= FULL_SIZE[name] - 200
+    keys = ["out6"] if model.info.sim_type == 0 else ["temp_blk", "flux_blk"]
+    n_ref = int(gold["n_seeds"])
+    for key in keys:
+        got, gm, gs = feats[key], gold[key + "_mean"], gold[key + "_std"].astype(np.float64)
+        if key == "out6":
+            got, gm, gs = got[:, [0, 2, 4]], gm[:, [0, 2, 4]], gs[:, [0, 2, 4]]
+        ok = gs > 0
+        # noise of the reference's mean over its seeds + noise of this one run (variance scales as 1 / phonons)
+        se = gs[ok] * np.sqrt(1.0 / n_ref + reduced / FULL_SIZE[name])
+        z = (got[ok] - gm[ok]) / se
+        # sigma comes from 16 seeds (t-distributed z) and, in the traces, from entries that hold a handful of phonons at
+        # the reduced size (skewed): bound the bulk of the distribution and the bias, and the extremes only loosely
+        assert np.median(np.abs(z)) <= 1.0, (name, key, float(np.median(np.abs(z))))
+        assert (np.abs(z) > 3).mean() <= 0.012 + 3.5 * np.sqrt(0.012 / z.size) + 1.0 / z.size, (name, key, float((np.abs(z) > 3).mean()))
+        assert abs(z.mean()) <= max(4.0 / np.sqrt(z.size), 0.35), (name, key, float(z.mean()))
+        if key == "out6":  # (rms and maximum are not robust against the few-phonon entries of the traces)
+            assert np.sqrt((z * z).mean()) <= 1.6, (name, key, float(np.sqrt((z * z).mean())))
+            assert np.abs(z).max() <= 8.0 + np.log10(max(z.size, 10) / 10.0), (name, key, float(np.abs(z).max()))
+    if name in ("sige", "linear_demo"):
+        two = gpu_run_case(model, 11, shards=2, finish=False)
+        assert np.array_equal(two["energy"], one["energy"]) and np.array_equal(two["fixed"], one["fixed"])
+        assert sum(st["drift_steps"] for st in two["stats"]) == one["stats"][0]["drift_steps"]
+
+
 def test_handle_reuse_across_runs_is_bit_identical():
     """The runs of a multi-run model go through ONE handle (psim_model_run): set_sources keeps the pool when the next
     run fits and re-allocates when it does not; either way a run must equal the same run on a fresh handle."""
