@@ -107,7 +107,7 @@ PSIM_HD void rng_refill(Rng& r, const DevParams& P, uint32_t step, uint32_t id_l
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < PSIM_PHILOX_ROUNDS; ++i) {
         const uint32_t hi0 = mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ a;

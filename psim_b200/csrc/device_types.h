@@ -19,6 +19,9 @@
 #define PSIM_FLUX_FRAC_BITS 8    // flux tallies are int64 fixed point, 1/256 m/s resolution
 #define PSIM_FREQ_SCALE 1e-13    // angular frequencies are carried as omega * 1e-13 (fp32 range)
 #define PSIM_BIRTH_STEP 0xFFFFFFFFu  // Philox stream selector for the draws made at emission
+#ifndef PSIM_PHILOX_ROUNDS
+#define PSIM_PHILOX_ROUNDS 10  // Philox4x32-10 (Salmon et al. 2011)
+#endif
 #ifndef PSIM_GUIDE
 #define PSIM_GUIDE 1024          // entries of the per-table guide that brackets the inverse-CDF search
 #endif
