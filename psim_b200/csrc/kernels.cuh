@@ -84,7 +84,7 @@ __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, l
         atomicAdd(reinterpret_cast<int32_t*>(q + 2), fx >> 12);
         atomicAdd(q + 3, static_cast<uint32_t>(fy) & 0xFFFu);
         atomicAdd(reinterpret_cast<int32_t*>(q + 4), fy >> 12);
-    } else if (a.tally_shared) {
+    } else if (a.tally_shared == 2u) {
         const uint32_t k = local_row * S + sensor;
         atomicAdd(&acc_e[k], e);
         atomic_add_i64(&acc_f[2 * k], fx);
@@ -97,8 +97,35 @@ __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, l
     }
 }
 
+// Tally a phonon into the recorded steps [k0, k1) that ended during one flight segment (same sensor, sign and velocity
+// for all of them).  Without staging (tally_shared == 3: models with many sensors, whose staging would not fit) the
+// global rows are kept as DIFFERENCES along the step axis - +v at the first row, -v behind the last - so a segment costs
+// six global REDs however many steps it crossed instead of three per step; psim_gpu.cu:finalize_rows turns the rows
+// into running sums once their window is complete (integers: exact).
+__device__ __forceinline__ void tally_range(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t k0, uint32_t k1,
+                                            uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
+    if (a.tally_shared == 3u) {
+        const uint32_t S = a.P.n_sensors;
+        const uint32_t r0 = k0 + 1u - a.P.first_tally_step, r1 = k1 + 1u - a.P.first_tally_step;
+        const size_t i0 = static_cast<size_t>(r0) * S + sensor;
+        atomicAdd(&a.tally_e[i0], e);
+        atomic_add_i64(&a.tally_f[2 * i0], fx);
+        atomic_add_i64(&a.tally_f[2 * i0 + 1], fy);
+        if (r1 < a.P.recorded_steps) {
+            const size_t i1 = static_cast<size_t>(r1) * S + sensor;
+            atomicAdd(&a.tally_e[i1], -e);
+            atomic_add_i64(&a.tally_f[2 * i1], -static_cast<long long>(fx));
+            atomic_add_i64(&a.tally_f[2 * i1 + 1], -static_cast<long long>(fy));
+        }
+    } else {
+        for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, e, fx, fy); }
+    }
+}
+
+__device__ __forceinline__ bool tally_staged(const LaunchArgs& a) { return a.tally_shared == 1u || a.tally_shared == 2u; }
+
 __device__ __forceinline__ void tally_init(const LaunchArgs& a, int32_t* acc_e, long long* acc_f) {
-    if (!a.tally_shared) { return; }
+    if (!tally_staged(a)) { return; }
     const uint32_t n = (a.step_end - a.step_begin) * a.P.n_sensors;
     if (a.tally_shared == 1u) {
         for (uint32_t i = threadIdx.x; i < 5u * n; i += kBlock) { acc_e[i] = 0; }
@@ -113,7 +140,7 @@ __device__ __forceinline__ void tally_init(const LaunchArgs& a, int32_t* acc_e, 
 }
 
 __device__ __forceinline__ void tally_flush(const LaunchArgs& a, const int32_t* acc_e, const long long* acc_f) {
-    if (!a.tally_shared) { return; }
+    if (!tally_staged(a)) { return; }
     __syncthreads();
     const uint32_t S = a.P.n_sensors, n = (a.step_end - a.step_begin) * S;
     for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
@@ -221,7 +248,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
     tally_init(a, acc_e, acc_f);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t tally_bytes = a.tally_shared ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
+    const size_t tally_bytes = tally_staged(a) ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
     uint32_t* sw = reinterpret_cast<uint32_t*>(smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127))) +
                    (threadIdx.x >> 5) * (SF_COUNT * K * 32) + lane;
     auto slot_u = [&](int field, uint32_t k) -> uint32_t& { return sw[(field * K + k) * 32]; };
@@ -408,7 +435,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     const int32_t sg = PSIM_PACK_NEG(slot_u(SF_PACKED, k)) ? -1 : 1;
                     const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
                     const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k)) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k)) * sg;
-                    for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, sg, fx, fy); }
+                    tally_range(a, acc_e, acc_f, k0, k1, sensor, sg, fx, fy);
                 });
                 ++n_events;
                 // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
@@ -481,7 +508,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     tally_init(a, acc_e, acc_f);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t tally_bytes = a.tally_shared ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
+    const size_t tally_bytes = tally_staged(a) ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
     unsigned char* base = smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127));
     uint32_t* sw = reinterpret_cast<uint32_t*>(base) + (threadIdx.x >> 5) * (SF_COUNT * NS);
     unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SF_COUNT * NS * 4 + (threadIdx.x >> 5) * (Q_COUNT * NS);
@@ -687,7 +714,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                     const int32_t sg = PSIM_PACK_NEG(slot_u(SF_PACKED, k)) ? -1 : 1;
                     const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
                     const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k)) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k)) * sg;
-                    for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, sg, fx, fy); }
+                    tally_range(a, acc_e, acc_f, k0, k1, sensor, sg, fx, fy);
                 });
                 ++n_events;
                 // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
@@ -790,9 +817,7 @@ __global__ void __launch_bounds__(kBlock, (kBlock <= 256 ? 2 : 1)) drift_kernel_
                                          [&](uint32_t k0, uint32_t k1, const psim::Phonon& q, const psim::Flight& f) {
                 const int32_t sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
                 const int32_t fx = psim::flux_fixed(q.dx) * sg, fy = psim::flux_fixed(q.dy) * sg;
-                for (uint32_t ks = k0; ks < k1; ++ks) {
-                    tally_add(a, acc_e, acc_f, ks - a.step_begin, PSIM_CELL_SENSOR(f.sensor_mat), sg, fx, fy);
-                }
+                tally_range(a, acc_e, acc_f, k0, k1, PSIM_CELL_SENSOR(f.sensor_mat), sg, fx, fy);
             });
             if (!alive) { ++n_absorbed; }
         }
@@ -811,6 +836,31 @@ __global__ void __launch_bounds__(kBlock, (kBlock <= 256 ? 2 : 1)) drift_kernel_
     if (lane == 0) { a.cnt_out[w] = n_out; }
     warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
     tally_flush(a, acc_e, acc_f);
+}
+
+// Rows [row_begin, row_end) of the difference-form tallies (tally_range, mode 3) become running sums; `carry` holds the
+// sums at row_begin - 1 and is private to the library, so callers may all-reduce finished rows in place.
+__global__ void finalize_rows_kernel(int32_t* tally_e, long long* tally_f, int32_t* carry_e, long long* carry_f, uint32_t S,
+                                     uint32_t row_begin, uint32_t row_end) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // sensor * 3 + component
+    if (i >= 3u * S) { return; }
+    const uint32_t s = i / 3u, c = i % 3u;
+    if (c == 0u) {
+        int32_t v = carry_e[s];
+        for (uint32_t r = row_begin; r < row_end; ++r) {
+            v += tally_e[static_cast<size_t>(r) * S + s];
+            tally_e[static_cast<size_t>(r) * S + s] = v;
+        }
+        carry_e[s] = v;
+    } else {
+        long long v = carry_f[2u * s + c - 1u];
+        for (uint32_t r = row_begin; r < row_end; ++r) {
+            const size_t k = 2 * (static_cast<size_t>(r) * S + s) + c - 1u;
+            v += tally_f[k];
+            tally_f[k] = v;
+        }
+        carry_f[2u * s + c - 1u] = v;
+    }
 }
 
 __global__ void cell_histogram_kernel(const uint4* pool_b, const uint32_t* cnt, uint32_t seg_cap, uint32_t n_warps,

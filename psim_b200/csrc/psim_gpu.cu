@@ -56,6 +56,9 @@ struct psim_gpu {
     uint32_t seg_cap = 0, n_warps = 0;
     int32_t* tally_e = nullptr;
     long long* tally_f = nullptr;
+    int32_t* carry_e = nullptr;      // [S]   running sums behind the last finalized row (difference-form tallies)
+    long long* carry_f = nullptr;    // [S][2]
+    bool diff_mode = false;          // this run tallies straight to global memory, rows kept as differences until finalized
     unsigned long long* d_stats = nullptr;
     unsigned long long* d_alive_hist = nullptr;
     unsigned long long* d_hist = nullptr;
@@ -166,9 +169,7 @@ void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1
     s1 = std::min(s0 + B, step_end);
     if (s1 + 1 <= h->P.first_tally_step) { return; }  // nothing recorded in this window
     const size_t budget = stage_budget(h);
-    const bool want_shared = h->opt_tally_shared != 0;
-    if (!want_shared) { return; }
-    if (h->opt_tally_shared < 0 && h->P.n_sensors >= kManySensors && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) {
+    if (h->diff_mode) {
         if (h->opt_steps_per_launch <= 0) { s1 = std::min(s0 + kGlobalTallyWindow, step_end); }  // no staging: nothing limits the window
         return;
     }
@@ -183,6 +184,11 @@ int zero_run_state(psim_gpu* h) {
     const size_t n = static_cast<size_t>(P.recorded_steps) * P.n_sensors;
     PSIM_CUDA(cudaMemsetAsync(h->tally_e, 0, n * sizeof(int32_t), h->stream));
     PSIM_CUDA(cudaMemsetAsync(h->tally_f, 0, n * 2 * sizeof(long long), h->stream));
+    PSIM_CUDA(cudaMemsetAsync(h->carry_e, 0, P.n_sensors * sizeof(int32_t), h->stream));
+    PSIM_CUDA(cudaMemsetAsync(h->carry_f, 0, P.n_sensors * 2 * sizeof(long long), h->stream));
+    // Tallies go straight to global memory when the caller asks for it, or when the model has so many sensors that the
+    // per-CTA staging of a useful window would not fit and global atomics are spread thinly enough
+    h->diff_mode = h->opt_tally_shared == 0 || (h->opt_tally_shared < 0 && P.n_sensors >= kManySensors);
     PSIM_CUDA(cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     if (h->d_alive_hist) {
         PSIM_CUDA(cudaMemsetAsync(h->d_alive_hist, 0, static_cast<size_t>(P.num_steps + 1) * sizeof(unsigned long long), h->stream));
@@ -276,6 +282,8 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         const size_t n = static_cast<size_t>(h->P.recorded_steps) * h->P.n_sensors;
         PSIM_CUDA(cudaMalloc(&h->tally_e, n * sizeof(int32_t)));
         PSIM_CUDA(cudaMalloc(&h->tally_f, n * 2 * sizeof(long long)));
+        PSIM_CUDA(cudaMalloc(&h->carry_e, std::max<size_t>(h->P.n_sensors, 1) * sizeof(int32_t)));
+        PSIM_CUDA(cudaMalloc(&h->carry_f, std::max<size_t>(h->P.n_sensors, 1) * 2 * sizeof(long long)));
         PSIM_CUDA(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
         PSIM_CUDA(cudaMalloc(&h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
         PSIM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -394,7 +402,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         h->birth_offset = static_cast<uint32_t>((h->birth_offset + ((a.n_births + 31) >> 5)) % h->n_warps);
         a.tally_e = h->tally_e;
         a.tally_f = h->tally_f;
-        a.tally_shared = 0u;
+        a.tally_shared = h->diff_mode ? 3u : 0u;  // 0: a staged window that did not fit even for one step (plain global adds)
         if (shared) {
             // native 32-bit staging of the flux (kernels.cuh:tally_add) is exact while one block adds fewer than 2^20
             // contributions to one entry: it can add one per phonon it handles and step
@@ -428,6 +436,17 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         PSIM_CUDA(cudaGetLastError());
         h->cur ^= 1;
         ++h->launches;
+    }
+    if (h->diff_mode && step_end + 1 > h->P.first_tally_step) {
+        // the rows whose measurement steps are now complete turn from differences into sums
+        const uint32_t F = h->P.first_tally_step;
+        const uint32_t row_begin = (step_begin + 1 > F) ? step_begin + 1 - F : 0u, row_end = std::min(step_end + 1 - F, h->P.recorded_steps);
+        if (row_end > row_begin) {
+            const uint32_t threads = 3u * h->P.n_sensors;
+            finalize_rows_kernel<<<(threads + 127) / 128, 128, 0, st>>>(h->tally_e, h->tally_f, h->carry_e, h->carry_f, h->P.n_sensors,
+                                                                         row_begin, row_end);
+            PSIM_CUDA(cudaGetLastError());
+        }
     }
     PSIM_CUDA(cudaEventRecord(h->ev_end, st));
     h->next_step = step_end;
@@ -609,6 +628,8 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaFree(h->d_guides);
     cudaFree(h->tally_e);
     cudaFree(h->tally_f);
+    cudaFree(h->carry_e);
+    cudaFree(h->carry_f);
     cudaFree(h->d_stats);
     cudaFree(h->d_hist);
     if (h->ev_begin) { cudaEventDestroy(h->ev_begin); }
