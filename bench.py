@@ -218,7 +218,7 @@ def run_ours(args):
     t_flux = torch.as_tensor(_Dev(f_ptr, (R, S, 2), "<i8"), device=f"cuda:{local}")
     stream = torch.cuda.Stream(device=local)  # the drift kernels are launched on THIS stream, and so are the events
     torch.cuda.set_stream(stream)
-    chunk = max(args.steps_per_launch, args.reduce_every)
+    chunk = max(args.steps_per_launch, args.reduce_every) if args.reduce_every > 0 else 0
 
     def one_job(seed):
         """All measurement steps.  Steps whose measurement is not recorded (steady state: the first 90 %) need no
@@ -230,7 +230,9 @@ def run_ours(args):
             g.run_steps(0, first - 1, stream.cuda_stream)
             s = first - 1
         while s < M - 1:
-            e = min(s + chunk, M - 1)
+            # groups end where the library's own launch windows end (no extra launch for the exchange); --reduce-every N
+            # asks for groups of N steps instead
+            e = min(s + chunk, M - 1) if chunk > 0 else g.next_window(s)
             g.run_steps(s, e, stream.cuda_stream)
             if world > 1:
                 r0, r1 = max(s + 1 - first, 0), e + 1 - first  # tally rows completed by steps [s, e)
@@ -411,7 +413,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--phonons", type=int, default=100_000_000, help="phonons per GPU")
     ap.add_argument("--steps-per-launch", type=int, default=0, help="0 = library default (automatic)")
-    ap.add_argument("--reduce-every", type=int, default=48, help="recorded measurement steps per tally all-reduce group")
+    ap.add_argument("--reduce-every", type=int, default=0,
+                    help="recorded measurement steps per tally all-reduce group (0 = one group per launch window of the library)")
     ap.add_argument("--tally-aggregate", type=int, default=-1)
     ap.add_argument("--tally-shared", type=int, default=-1)
     ap.add_argument("--warps-per-sm", type=int, default=0)

@@ -155,6 +155,11 @@ int psim_gpu_run(psim_gpu* h);
 int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void* cuda_stream);
 int psim_gpu_synchronize(psim_gpu* h);
 
+/* Where the launch window that starts at measurement step `step_begin` would end if nothing cut it short: a caller that
+ * exchanges tallies between groups of steps (bench.py:one_job) cuts its groups at these boundaries, so that its
+ * grouping adds no launch.  Needs psim_gpu_set_sources. */
+int psim_gpu_next_window(psim_gpu* h, uint32_t step_begin, uint32_t* step_end);
+
 /* Replaces reading Sensor::inc_energy_ / inc_flux_ (sensor.h:50-55,73-74).  energy: [num_sensors][R] signed
  * phonon counts; flux: [num_sensors][R][2] sum of sign * velocity (m/s); R = measurement_steps - step_adjustment.
  * flux_fixed (optional, may be NULL) receives the exact integer sums in units of 1/256 m/s. */

@@ -470,6 +470,21 @@ int psim_gpu_synchronize(psim_gpu* h) {
     return PSIM_OK;
 }
 
+int psim_gpu_next_window(psim_gpu* h, uint32_t step_begin, uint32_t* step_end) {
+    if (!h || !step_end) { return PSIM_E_INVALID; }
+    if (!h->have_sources) {
+        h->err = "psim_gpu_set_sources must be called before planning windows";
+        return PSIM_E_STATE;
+    }
+    const uint32_t last = h->P.num_steps - 1;
+    *step_end = last;
+    if (step_begin >= last) { return PSIM_OK; }
+    bool shared = false;
+    size_t smem = 0;
+    plan_launch(h, step_begin, last, *step_end, shared, smem);
+    return PSIM_OK;
+}
+
 int psim_gpu_run(psim_gpu* h) {
     if (!h) { return PSIM_E_INVALID; }
     if (int rc = psim_gpu_run_steps(h, h->next_step, h->P.num_steps - 1, nullptr)) { return rc; }

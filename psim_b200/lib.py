@@ -101,6 +101,7 @@ SYMBOLS = {
     "psim_gpu_run": (C.c_int, [_P]),
     "psim_gpu_run_steps": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
     "psim_gpu_synchronize": (C.c_int, [_P]),
+    "psim_gpu_next_window": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "psim_gpu_get_tallies": (C.c_int, [_P, _P, _P, _P]),
     "psim_gpu_tally_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "psim_gpu_alive": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
@@ -345,6 +346,12 @@ class GpuSimulator:
 
     def run_steps(self, begin: int, end: int, stream: int = 0):
         self._check(self.lib.psim_gpu_run_steps(self.handle, begin, end, C.c_void_p(stream) if stream else None))
+
+    def next_window(self, begin: int) -> int:
+        """End of the launch window the library would start at measurement step `begin`."""
+        end = C.c_uint32()
+        self._check(self.lib.psim_gpu_next_window(self.handle, begin, C.byref(end)))
+        return end.value
 
     def synchronize(self):
         self._check(self.lib.psim_gpu_synchronize(self.handle))

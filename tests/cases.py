@@ -60,3 +60,23 @@ def cases(include_kinked: bool = True):
             c["kinked_diffuse"] = configs.with_specularity(configs.with_settings(kinked, num_phonons=30_000), 0.5)
             c["kinked_rough"] = configs.with_specularity(configs.with_settings(kinked, num_phonons=30_000), 0.0)
     return c
+
+
+def split_bar(num_phonons: int, split=(7, 12)) -> dict:
+    """linear_demo's bar with two of its 20 rectangles cut into a lower and an upper half: the full-height edges of
+    their neighbours then face TWO cells each (partial transition sub-surfaces, compositeSurface.cpp:47-66).  The
+    reference cannot serve as the oracle here - it picks a sub-surface by testing the hit point against the infinite
+    line of each (geometry.cpp:88-90), i.e. always the first of two collinear ones - so the check is self-consistency:
+    cutting cells must not change the physics."""
+    m = configs.ModelFile(num_measurements=1000, sim_time=10, num_phonons=num_phonons, t_eq=300)
+    name = m.material(configs.SILICON)
+    for i in range(20):
+        sid = m.sensor(name, 300.0)
+        if i in split:
+            m.rectangle((i * 50.0, 0.0), ((i + 1) * 50.0, 100.0), sid, 1)
+            m.rectangle((i * 50.0, 100.0), ((i + 1) * 50.0, 200.0), sid, 1)
+        else:
+            m.rectangle((i * 50.0, 0.0), ((i + 1) * 50.0, 200.0), sid, 1)
+    m.emit_surface((0.0, 0.0), (0.0, 200.0), 310)
+    m.emit_surface((1000.0, 0.0), (1000.0, 200.0), 290)
+    return m.to_dict()

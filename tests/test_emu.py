@@ -19,6 +19,44 @@ def _one(args):
     return T.run_features(r["energy"], r["flux"], model.info.sim_type, six, temps, fluxes)
 
 
+def _one_model(args):
+    model_dict, seed = args
+    model = T.load_model(model_dict)
+    model.prepare()
+    r = T.emu_run(model, seed, steps_per_pass=16)
+    model.set_tallies(r["energy"], r["flux"])
+    model.finish_run(0)
+    six, temps, fluxes = model.results(0)
+    return T.run_features(r["energy"], r["flux"], model.info.sim_type, six, temps, fluxes)
+
+
+def _as_gold(runs):
+    gold = {"n_seeds": len(runs)}
+    for key in ("tally_e", "tally_f", "out6"):
+        stack = np.stack([r[key] for r in runs])
+        gold[key + "_mean"], gold[key + "_std"] = stack.mean(axis=0), stack.std(axis=0, ddof=1)
+    return gold
+
+
+def test_partial_edges_do_not_change_the_physics():
+    """A non-conforming mesh (edges that face two cells: partial transition sub-surfaces) against the same bar meshed
+    conformingly - see tests/cases.py:split_bar for why this is a self-consistency check and not a reference parity."""
+    from psim_b200 import configs
+    from tests import cases
+    T.emu_lib()
+    cut = cases.split_bar(100_000)
+    info = T.load_model(cut).info
+    assert info.num_cells == 44 and info.num_partial_links == 8
+    plain = configs.linear(num_phonons=100_000).to_dict()
+    with ProcessPoolExecutor(8) as ex:
+        runs_cut = list(ex.map(_one_model, [(cut, s) for s in range(1, 9)]))
+        runs_plain = list(ex.map(_one_model, [(plain, s) for s in range(11, 19)]))
+    gold = _as_gold(runs_plain)
+    T.assert_parity(T.welch_z(runs_cut, gold, "tally_e"), "cut bar vs plain bar, energy tallies")
+    T.assert_parity(T.welch_z(runs_cut, gold, "tally_f"), "cut bar vs plain bar, flux tallies")
+    T.assert_parity(T.welch_z(runs_cut, gold, "out6")[:, 0], "cut bar vs plain bar, temperatures")
+
+
 def _features(name, seeds, n=None):
     T.emu_lib()
     with ProcessPoolExecutor(8) as ex:

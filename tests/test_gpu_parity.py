@@ -153,6 +153,61 @@ def test_handle_reuse_across_runs_is_bit_identical():
         g.close()
 
 
+def test_partial_edges_do_not_change_the_physics():
+    """Non-conforming mesh (edges facing two cells -> composite links, device_core.cuh:impact_event) against the same
+    bar meshed conformingly, 8 seeds each through the CUDA path; tests/cases.py:split_bar says why the reference is not
+    the oracle for this one."""
+    from psim_b200 import configs
+    from tests import cases
+    feats = {}
+    for label, model_dict, seeds in (("cut", cases.split_bar(400_000), range(1, 9)),
+                                     ("plain", configs.linear(num_phonons=400_000).to_dict(), range(11, 19))):
+        model = T.load_model(model_dict)
+        feats[label] = []
+        for seed in seeds:
+            r = gpu_run_case(model, seed)
+            feats[label].append(T.run_features(r["energy"], r["flux"], 0, r["six"], r["temps"], r["fluxes"]))
+    gold = {"n_seeds": 8}
+    for key in ("tally_e", "tally_f", "out6"):
+        stack = np.stack([r[key] for r in feats["plain"]])
+        gold[key + "_mean"], gold[key + "_std"] = stack.mean(axis=0), stack.std(axis=0, ddof=1)
+    T.assert_parity(T.welch_z(feats["cut"], gold, "tally_e"), "cut bar vs plain bar, energy tallies")
+    T.assert_parity(T.welch_z(feats["cut"], gold, "tally_f"), "cut bar vs plain bar, flux tallies")
+    T.assert_parity(T.welch_z(feats["cut"], gold, "out6")[:, 0], "cut bar vs plain bar, temperatures")
+    # and against the reference's fixture of the plain bar
+    T.assert_parity(T.welch_z(feats["cut"], T.golden("linear_demo"), "out6")[:, 0], "cut bar vs reference linear_demo, temperatures")
+
+
+@pytest.mark.parametrize("sim_type", [0, 1])
+def test_planned_windows_are_the_launches(sim_type):
+    """psim_gpu_next_window: a caller that cuts its groups of measurement steps where the library's own launch windows
+    end (bench.py:one_job, for the tally exchange between ranks) causes no additional launch, and gets the same
+    integers as one blocking psim_gpu_run."""
+    from psim_b200 import configs, lib as psim
+    model = T.load_model(configs.linear(num_phonons=40_000, sim_type=sim_type, step_interval=4).to_dict())
+    whole = gpu_run_case(model, 7, finish=False)
+    model.prepare()
+    M = model.info.measurement_steps
+    g = psim.GpuSimulator(model.describe(), 0)
+    try:
+        src, n = model.sources(7)
+        g.set_sources(src, n, 7, 0, 1)
+        cuts, s = [0], 0
+        while s < M - 1:
+            e = g.next_window(s)
+            assert s < e <= M - 1
+            g.run_steps(s, e)
+            cuts.append(e)
+            s = e
+        assert g.next_window(M - 1) == M - 1
+        e, f, fx = g.tallies(fixed=True)
+        st = g.stats()
+        assert st.launches == len(cuts) - 1 == whole["stats"][0]["launches"]
+        assert np.array_equal(e, whole["energy"]) and np.array_equal(fx, whole["fixed"])
+    finally:
+        g.close()
+
+
 def test_device_sampling_matches_reference_bisection():
     """Material::freqIndex (material.cpp:64-75): the guided search of the flight loop, the plain bisection run on
     the device, and the same bisection run here in numpy on the fp32 table must give identical bins."""
