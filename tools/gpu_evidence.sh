@@ -13,8 +13,11 @@ timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
     --log-file $out/${tag}_dram_per_launch.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $out/dram_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 0 -c 1 -f -o $out/prof_long \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $out/ncu_long.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 2 -c 1 -f -o $out/prof_rec \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 1 -c 1 -f -o $out/prof_rec \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $out/ncu_rec.log 2>&1
+# periodic model with 1000 sensors: recorded tallies go straight to global memory in difference form (launch 3 of 8)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 2 -c 1 -f -o $out/prof_per \
+    python tools/profile_model.py sides_per > $out/ncu_per.log 2>&1
 timeout 900 python tools/model_walltimes.py 2> $out/models.err > $out/${tag}_models.jsonl
 timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python bench.py --phonons 200000 --steps 1 --warmup 0 --no-cpu-baseline \
     > $out/${tag}_memcheck.log 2>&1
