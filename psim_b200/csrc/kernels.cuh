@@ -69,22 +69,18 @@ __device__ __forceinline__ void atomic_add_i64(long long* p, long long v) {
 
 // Sensor::updateHeatParams (sensor.cpp:43-52): energy += sign, flux += sign * v.  Block stage in shared memory
 // (flushed with one global atomic per touched (sensor, step) at the end of the kernel) or straight to global.
-// Shared memory has no native 64-bit add (the compiler emits a compare-and-swap loop), so the staged flux is kept as
-// two 32-bit sums per component - the low 12 bits of every contribution (unsigned) and the rest (signed) - which native
-// ATOMS.ADD can accumulate; the exact 64-bit value (hi << 12) + lo is rebuilt at the flush.  That is exact as long as a
-// block adds fewer than 2^20 contributions to one entry in one launch; the host checks the bound (tally_shared == 1)
-// and otherwise asks for the 64-bit staging (tally_shared == 2).
+// Shared memory has no native 64-bit add (the compiler emits a compare-and-swap loop), so the staged flux is normally
+// kept as two 32-bit sums per component - the low kStageLoBits bits of every contribution (unsigned) and the rest
+// (signed) - which native ATOMS.ADD can accumulate (tally_shared == 1, see tally_range); the exact 64-bit value
+// (hi << kStageLoBits) + lo is rebuilt at the flush.  The host checks the bound that keeps this exact and otherwise asks
+// for the 64-bit staging (tally_shared == 2), which this function serves together with the plain global adds.
+constexpr uint32_t kStageLoBits = 11u;
+constexpr uint32_t kStageLoMask = (1u << kStageLoBits) - 1u;
+
 __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t local_row,
                                           uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
     const uint32_t S = a.P.n_sensors;
-    if (a.tally_shared == 1u) {  // five consecutive 32-bit words per (step, sensor): e, fx low / high, fy low / high
-        uint32_t* q = reinterpret_cast<uint32_t*>(acc_e) + 5u * (local_row * S + sensor);
-        atomicAdd(reinterpret_cast<int32_t*>(q), e);
-        atomicAdd(q + 1, static_cast<uint32_t>(fx) & 0xFFFu);
-        atomicAdd(reinterpret_cast<int32_t*>(q + 2), fx >> 12);
-        atomicAdd(q + 3, static_cast<uint32_t>(fy) & 0xFFFu);
-        atomicAdd(reinterpret_cast<int32_t*>(q + 4), fy >> 12);
-    } else if (a.tally_shared == 2u) {
+    if (a.tally_shared == 2u) {
         const uint32_t k = local_row * S + sensor;
         atomicAdd(&acc_e[k], e);
         atomic_add_i64(&acc_f[2 * k], fx);
@@ -97,14 +93,35 @@ __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, l
     }
 }
 
+// five consecutive 32-bit words per (step, sensor): e, fx low / high, fy low / high
+__device__ __forceinline__ void stage_add_narrow(uint32_t* q, int32_t e, int32_t fx, int32_t fy) {
+    atomicAdd(reinterpret_cast<int32_t*>(q), e);
+    atomicAdd(q + 1, static_cast<uint32_t>(fx) & kStageLoMask);
+    atomicAdd(reinterpret_cast<int32_t*>(q + 2), fx >> kStageLoBits);
+    atomicAdd(q + 3, static_cast<uint32_t>(fy) & kStageLoMask);
+    atomicAdd(reinterpret_cast<int32_t*>(q + 4), fy >> kStageLoBits);
+}
+
 // Tally a phonon into the recorded steps [k0, k1) that ended during one flight segment (same sensor, sign and velocity
-// for all of them).  Without staging (tally_shared == 3: models with many sensors, whose staging would not fit) the
-// global rows are kept as DIFFERENCES along the step axis - +v at the first row, -v behind the last - so a segment costs
-// six global REDs however many steps it crossed instead of three per step; psim_gpu.cu:finalize_rows turns the rows
-// into running sums once their window is complete (integers: exact).
+// for all of them).  Rows are kept as DIFFERENCES along the step axis - +v at the first row, -v behind the last - so a
+// segment costs a fixed number of atomics however many steps it crossed, and no loop whose trip count differs from lane
+// to lane (ncu, looped form: 12 % of the instructions of a recorded window were shared atomics at 6 of 32 lanes).
+//   tally_shared == 1  staged per CTA in shared memory as 32-bit halves: ten native ATOMS.ADD per segment; tally_flush
+//                      turns the rows of the window into running sums (a row's difference beyond the window is dropped:
+//                      the next launch starts its own sums).  Exact while 2 x (phonons a block handles) contributions
+//                      fit the halves: a phonon adds to a row at most twice, once as a first row, once behind a last.
+//   tally_shared == 3  no staging (models with many sensors, whose staging would not fit): six global REDs per segment;
+//                      psim_gpu.cu:finalize_rows turns the rows into running sums once their window is complete.
+// Integers throughout: the sums are exact and independent of the order of the adds.
 __device__ __forceinline__ void tally_range(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t k0, uint32_t k1,
                                             uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
-    if (a.tally_shared == 3u) {
+    if (a.tally_shared == 1u) {
+        const uint32_t S = a.P.n_sensors;
+        const uint32_t l0 = k0 - a.step_begin, l1 = k1 - a.step_begin;
+        uint32_t* q = reinterpret_cast<uint32_t*>(acc_e) + 5u * (l0 * S + sensor);
+        stage_add_narrow(q, e, fx, fy);
+        if (l1 < a.step_end - a.step_begin) { stage_add_narrow(q + 5u * (l1 - l0) * S, -e, -fx, -fy); }
+    } else if (a.tally_shared == 3u) {
         const uint32_t S = a.P.n_sensors;
         const uint32_t r0 = k0 + 1u - a.P.first_tally_step, r1 = k1 + 1u - a.P.first_tally_step;
         const size_t i0 = static_cast<size_t>(r0) * S + sensor;
@@ -142,23 +159,36 @@ __device__ __forceinline__ void tally_init(const LaunchArgs& a, int32_t* acc_e, 
 __device__ __forceinline__ void tally_flush(const LaunchArgs& a, const int32_t* acc_e, const long long* acc_f) {
     if (!tally_staged(a)) { return; }
     __syncthreads();
-    const uint32_t S = a.P.n_sensors, n = (a.step_end - a.step_begin) * S;
+    const uint32_t S = a.P.n_sensors, nst = a.step_end - a.step_begin;
+    if (a.tally_shared == 1u) {
+        // difference rows -> running sums along the steps of the window, one thread per (sensor, component)
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(acc_e);
+        for (uint32_t i = threadIdx.x; i < 3u * S; i += kBlock) {
+            const uint32_t s = i / 3u, c = i % 3u;
+            long long run = 0;
+            for (uint32_t l = 0; l < nst; ++l) {
+                const uint32_t* q = words + 5u * (l * S + s);
+                run += (c == 0u) ? static_cast<long long>(static_cast<int32_t>(q[0]))
+                                 : static_cast<long long>(static_cast<int32_t>(q[2u * c])) * (1 << kStageLoBits) + static_cast<long long>(q[2u * c - 1u]);
+                const uint32_t row = a.step_begin + l + 1u;
+                if (row < a.P.first_tally_step || run == 0) { continue; }
+                const size_t k = static_cast<size_t>(row - a.P.first_tally_step) * S + s;
+                if (c == 0u) {
+                    atomicAdd(&a.tally_e[k], static_cast<int32_t>(run));
+                } else {
+                    atomic_add_i64(&a.tally_f[2 * k + c - 1u], run);
+                }
+            }
+        }
+        return;
+    }
+    const uint32_t n = nst * S;
     for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
         const uint32_t row = a.step_begin + i / S + 1;
         if (row < a.P.first_tally_step) { continue; }
         const size_t k = static_cast<size_t>(row - a.P.first_tally_step) * S + (i % S);
-        int32_t e;
-        long long fx, fy;
-        if (a.tally_shared == 1u) {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(acc_e) + 5u * i;
-            e = static_cast<int32_t>(q[0]);
-            fx = static_cast<long long>(static_cast<int32_t>(q[2])) * 4096 + static_cast<long long>(q[1]);
-            fy = static_cast<long long>(static_cast<int32_t>(q[4])) * 4096 + static_cast<long long>(q[3]);
-        } else {
-            e = acc_e[i];
-            fx = acc_f[2 * i];
-            fy = acc_f[2 * i + 1];
-        }
+        const int32_t e = acc_e[i];
+        const long long fx = acc_f[2 * i], fy = acc_f[2 * i + 1];
         if (e) { atomicAdd(&a.tally_e[k], e); }
         if (fx) { atomic_add_i64(&a.tally_f[2 * k], fx); }
         if (fy) { atomic_add_i64(&a.tally_f[2 * k + 1], fy); }

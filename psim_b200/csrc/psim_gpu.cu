@@ -404,12 +404,13 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         a.tally_f = h->tally_f;
         a.tally_shared = h->diff_mode ? 3u : 0u;  // 0: a staged window that did not fit even for one step (plain global adds)
         if (shared) {
-            // native 32-bit staging of the flux (kernels.cuh:tally_add) is exact while one block adds fewer than 2^20
-            // contributions to one entry: it can add one per phonon it handles and step
+            // native 32-bit staging of the flux (kernels.cuh:tally_range) is exact while the low halves (kStageLoBits bits per
+            // contribution) and the high halves of one entry stay within 32 bits: a block adds at most two contributions per
+            // phonon it handles to one (step, sensor) entry - as the first row of one flight segment, behind the last of another
             const uint64_t chunks_per_warp = (((a.n_births + 31) >> 5) + h->n_warps - 1) / h->n_warps;
-            const uint64_t per_block = static_cast<uint64_t>(kWarpsPerBlock) * (h->seg_cap + chunks_per_warp * 32);
-            const uint64_t hi_max = (static_cast<uint64_t>(h->max_flux_fixed) >> 12) + 1;
-            const bool narrow = per_block < (1ull << 20) && per_block * hi_max < (1ull << 31) && h->opt_tally_shared != 2;
+            const uint64_t per_entry = 2ull * kWarpsPerBlock * (h->seg_cap + chunks_per_warp * 32);
+            const uint64_t hi_max = (static_cast<uint64_t>(h->max_flux_fixed) >> kStageLoBits) + 1;
+            const bool narrow = per_entry < (1ull << (32 - kStageLoBits)) && per_entry * hi_max < (1ull << 31) && h->opt_tally_shared != 2;
             a.tally_shared = narrow ? 1u : 2u;
         }
         a.tally_aggregate = h->opt_tally_aggregate ? 1u : 0u;
@@ -607,6 +608,10 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
         h->opt_kernel = value;
         h->kernel_chosen = true;
     } else if (k == "tally_shared") {
+        if (h->have_sources || value < -1 || value > 2) {  // the tally form of a run (staged / difference rows) is fixed when it starts
+            h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 or 2 (staged, 32- / 64-bit) and set before set_sources";
+            return PSIM_E_STATE;
+        }
         h->opt_tally_shared = value;
     } else if (k == "tally_aggregate") {
         h->opt_tally_aggregate = value;

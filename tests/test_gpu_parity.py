@@ -76,7 +76,7 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
     staging fits shared memory for every window length used here)."""
     from psim_b200 import configs
     model = T.load_model(configs.linear(num_phonons=50_000, sim_type=1, step_interval=4).to_dict())
-    for spl in (1, 3):
+    for spl in (1, 3, 16):
         ref = gpu_run_case(model, 5, steps_per_launch=spl, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
         for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 0, "tally_shared": 1},
                      {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "warps_per_sm": 48}, {"kernel": 2, "tally_shared": 1},
@@ -86,6 +86,22 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
             assert np.array_equal(got["fixed"], ref["fixed"]), (spl, opts)
             assert got["stats"][0]["drift_steps"] == ref["stats"][0]["drift_steps"], (spl, opts)
             assert got["stats"][0]["events"] == ref["stats"][0]["events"], (spl, opts)
+
+
+def test_staged_tally_forms_agree_on_automatic_windows():
+    """The two staged forms - difference rows in 32-bit halves (1) and plain 64-bit sums (2) - need the same shared memory
+    per (step, sensor), so the library plans the same windows for both: identical integers, on the bench model (long
+    unrecorded window + recorded windows as long as the staging holds) and on a periodic bar (every window recorded)."""
+    from psim_b200 import configs
+    for model_dict in (configs.si_ge_grid(num_phonons=300_000).to_dict(),
+                       configs.linear(num_phonons=60_000, sim_type=1, step_interval=4).to_dict()):
+        model = T.load_model(model_dict)
+        a = gpu_run_case(model, 9, options={"tally_shared": 1}, finish=False)
+        b = gpu_run_case(model, 9, options={"tally_shared": 2}, finish=False)
+        assert a["stats"][0]["tally_in_shared"] == 1 and b["stats"][0]["tally_in_shared"] == 2
+        assert a["stats"][0]["launches"] == b["stats"][0]["launches"] > 1
+        assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["fixed"], b["fixed"])
+        assert np.abs(a["energy"]).sum() > 0
 
 
 FULL_SIZE = {"sige": 100_000_000, "linear_demo": 5_000_000, "sides_ss": 10_000_000, "sides_trans": 10_000_000}
