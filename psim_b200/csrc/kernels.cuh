@@ -1,11 +1,13 @@
 // sm_100a kernels of the particle loop.  Included by psim_gpu.cu only.
 //
-// drift_kernel_slots<K>  the drift step (default).  Persistent, one pool segment per resident warp; every lane keeps
-//                        K phonons in flight in shared memory and the warp executes, pass by pass, the kind of work
-//                        (fly / surface interaction / intrinsic scatter / write back / fetch) that most lanes want.
-// drift_kernel_lockstep  the first version: tiles of 32 phonons, one per lane, in lock step.  Kept for A/B
-//                        measurements and as a cross-check: a phonon's random stream is addressed by (id, step), so both
-//                        kernels must produce bit-identical tallies (tests/test_gpu_parity.py).
+// drift_kernel_queues<NS>  the drift step (default).  Persistent, one 24-warp CTA per SM, one pool segment per resident
+//                          warp; a warp keeps NS phonons in flight in shared memory and one queue of slot numbers per kind
+//                          of work (fly / intrinsic scatter / surface interaction / write back / fetch); a pass pops up
+//                          to 32 entries of the fullest queue, lane i takes the i-th.
+// drift_kernel_slots<K>    the version before: every lane owns K slots, the warp votes for the kind most lanes want.
+// drift_kernel_lockstep    the first version: tiles of 32 phonons, one per lane, in lock step.
+//                          Both kept for A/B measurements and as cross-checks: a phonon's random stream is addressed by
+//                          (id, step), so all three must produce bit-identical tallies (tests/test_gpu_parity.py).
 // History of the design, with the ncu numbers that drove it, is in DESIGN.md section 6 and profiles/.
 #ifndef PSIM_B200_KERNELS_CUH
 #define PSIM_B200_KERNELS_CUH

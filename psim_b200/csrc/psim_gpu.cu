@@ -74,7 +74,6 @@ struct psim_gpu {
     int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
     int64_t opt_warps_per_sm = 0;
     int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
-    bool kernel_chosen = false;      // false: psim_gpu_create picks 2 or 0 from the size of the mesh
     int64_t opt_tally_shared = -1;
     int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
@@ -254,11 +253,10 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         for (float v : h->img.velocities) { vmax = std::max(vmax, std::fabs(v)); }
         h->max_flux_fixed = static_cast<uint32_t>(std::min(4.0e9, std::ceil(static_cast<double>(vmax) * (1 << PSIM_FLUX_FRAC_BITS))));
     }
-    // Meshes whose cell records no longer fit L1 (> 4096 cells = 128 KB) make the flight loop wait on L2 instead of on the
-    // issue slots; there the lane-bound slots kernel (depth-first per lane, no bank conflicts, one dependent shared-memory
-    // load less per pass) measured 10 % faster than the work queues (kinked wire, 6174 cells: 261 vs 281 ms); on every
-    // smaller mesh the work queues win (profiles/r01_models.jsonl).  psim_gpu_set_option("kernel") overrides.
-    h->opt_kernel = (h->img.cells.size() > 4096) ? 0 : 2;
+    // The work-queue kernel for every mesh.  (Until the transition was fused into the flight pass and re-queued at the front,
+    // the lane-bound slots kernel was faster on meshes whose cell records do not fit L1; measured again on the final
+    // kernels, kinked wire with 6174 cells: 246 ms queues, 253 ms slots.)  psim_gpu_set_option("kernel") overrides.
+    h->opt_kernel = 2;
     auto setup = [&]() -> int {
         if (int rc = upload(h, &h->d_cells, h->img.cells)) { return rc; }
         if (int rc = upload(h, &h->d_walls, h->img.walls)) { return rc; }
@@ -606,7 +604,6 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
             return PSIM_E_STATE;
         }
         h->opt_kernel = value;
-        h->kernel_chosen = true;
     } else if (k == "tally_shared") {
         if (h->have_sources || value < -1 || value > 2) {  // the tally form of a run (staged / difference rows) is fixed when it starts
             h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 or 2 (staged, 32- / 64-bit) and set before set_sources";
