@@ -74,6 +74,7 @@ struct psim_gpu {
     int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
     int64_t opt_warps_per_sm = 0;
     int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
+    int64_t opt_queue_slots = 32 * kSlots;  // phonons in flight per warp of the work-queue kernel (128, or 64: more L1 left for the mesh)
     int64_t opt_tally_shared = -1;
     int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
@@ -131,17 +132,20 @@ size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
     return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
 }
 
-constexpr int kQueueSlots = 32 * kSlots;                     // slots per warp of the queues kernel
-constexpr size_t kQueueBytesPerBlock = kSlotBytesPerBlock + static_cast<size_t>(Q_COUNT) * kQueueSlots * kWarpsPerBlock;
+constexpr int kQueueSlots = 32 * kSlots;                     // slots per warp of the queues kernel ...
+constexpr int kQueueSlotsSmall = kQueueSlots / 2;            // ... and of its second instantiation (option "queue_slots")
+constexpr size_t queue_bytes_per_block(int slots) {
+    return static_cast<size_t>(SF_COUNT) * slots * 4 * kWarpsPerBlock + static_cast<size_t>(Q_COUNT) * slots * kWarpsPerBlock;
+}
+constexpr size_t kQueueBytesPerBlock = queue_bytes_per_block(kQueueSlots);
 // what a block may use so that kSlotBlocks blocks (plus 1 KB each that the driver reserves) fit the planned carve-out;
 // the tally staging gets what the slot storage leaves
 constexpr size_t kSmemPerBlock = static_cast<size_t>(PSIM_SMEM_KB_PER_SM) * 1024 / kSlotBlocks - 1024;
 static_assert(kSmemPerBlock > kQueueBytesPerBlock + 4096, "no room for the tally staging");
 constexpr size_t kTallyStageBudget = kSmemPerBlock - kSlotBytesPerBlock;
-constexpr size_t kTallyStageBudgetQueues = kSmemPerBlock - kQueueBytesPerBlock;
 
 size_t stage_budget(const psim_gpu* h) {
-    return h->opt_kernel == 1 ? 100 * 1024 : (h->opt_kernel == 2 ? kTallyStageBudgetQueues : kTallyStageBudget);
+    return h->opt_kernel == 1 ? 100 * 1024 : (h->opt_kernel == 2 ? kSmemPerBlock - queue_bytes_per_block(static_cast<int>(h->opt_queue_slots)) : kTallyStageBudget);
 }
 constexpr uint32_t kLongWindow = 1023;           // steps per launch while nothing is recorded (10 bits of step in the slot word)
 constexpr uint32_t kGlobalTallyWindow = 128;     // steps per launch when recorded tallies go straight to global memory
@@ -257,6 +261,12 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
     // the lane-bound slots kernel was faster on meshes whose cell records do not fit L1; measured again on the final
     // kernels, kinked wire with 6174 cells: 246 ms queues, 253 ms slots.)  psim_gpu_set_option("kernel") overrides.
     h->opt_kernel = 2;
+    // Slots per warp: 128 keep the queues of the rare kinds of work full (Si/Ge bench model: 63.6 ms for the long window
+    // against 76.8 ms with 64).  A mesh whose cell + wall records (64 B per cell) outgrow the 92 KB of L1 that 128 slots
+    // leave runs faster with 64 slots and 156 KB of L1 (measured, 128 -> 64: linear_sides with 2000 cells 28.8 -> 27.1 ms
+    // periodic, 41.4 -> 38.3 ms transient, 15.5 -> 14.8 ms steady; kinked wire with 6174 cells 246 -> 238 ms; but
+    // linear_demo with 40 cells 12.0 -> 12.8 ms).  psim_gpu_set_option("queue_slots") overrides.
+    h->opt_queue_slots = (h->img.cells.size() > 1024) ? kQueueSlotsSmall : kQueueSlots;
     auto setup = [&]() -> int {
         if (int rc = upload(h, &h->d_cells, h->img.cells)) { return rc; }
         if (int rc = upload(h, &h->d_walls, h->img.walls)) { return rc; }
@@ -290,6 +300,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
@@ -324,8 +335,11 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
     if (h->opt_kernel == 1) {
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
     } else if (h->opt_kernel == 2) {
-        const size_t dyn = kQueueBytesPerBlock + kTallyStageBudgetQueues;
-        PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlots>, kBlock, dyn));
+        if (h->opt_queue_slots == kQueueSlots) {
+            PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlots>, kBlock, kSmemPerBlock));
+        } else {
+            PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlotsSmall>, kBlock, kSmemPerBlock));
+        }
     } else {  // shared-memory slots + the largest tally staging a launch may ask for
         const size_t dyn = kSlotBytesPerBlock + kTallyStageBudget;
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_slots<kSlots>, kBlock, dyn));
@@ -426,8 +440,12 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         if (h->opt_kernel == 1) {
             drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
         } else if (h->opt_kernel == 2) {
-            const size_t bytes = kQueueBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
-            drift_kernel_queues<kQueueSlots><<<grid, kBlock, bytes, st>>>(a);
+            const size_t bytes = queue_bytes_per_block(static_cast<int>(h->opt_queue_slots)) + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
+            if (h->opt_queue_slots == kQueueSlots) {
+                drift_kernel_queues<kQueueSlots><<<grid, kBlock, bytes, st>>>(a);
+            } else {
+                drift_kernel_queues<kQueueSlotsSmall><<<grid, kBlock, bytes, st>>>(a);
+            }
         } else {
             const size_t slots = kSlotBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
             drift_kernel_slots<kSlots><<<grid, kBlock, slots, st>>>(a);
@@ -604,6 +622,12 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
             return PSIM_E_STATE;
         }
         h->opt_kernel = value;
+    } else if (k == "queue_slots") {
+        if (h->have_sources || (value != kQueueSlots && value != kQueueSlotsSmall)) {
+            h->err = "queue_slots must be " + std::to_string(kQueueSlots) + " or " + std::to_string(kQueueSlotsSmall) + " and set before set_sources";
+            return PSIM_E_STATE;
+        }
+        h->opt_queue_slots = value;
     } else if (k == "tally_shared") {
         if (h->have_sources || value < -1 || value > 2) {  // the tally form of a run (staged / difference rows) is fixed when it starts
             h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 or 2 (staged, 32- / 64-bit) and set before set_sources";

@@ -80,7 +80,8 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
         ref = gpu_run_case(model, 5, steps_per_launch=spl, options={"kernel": 1, "tally_shared": 0, "tally_aggregate": 0}, finish=False)
         for opts in ({"kernel": 1, "tally_shared": 1, "tally_aggregate": 0}, {"kernel": 0, "tally_shared": 1},
                      {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "warps_per_sm": 48}, {"kernel": 2, "tally_shared": 1},
-                     {"kernel": 2, "tally_shared": 2}, {"kernel": 2, "tally_shared": 0}, {"kernel": 2, "warps_per_sm": 48}):
+                     {"kernel": 2, "tally_shared": 2}, {"kernel": 2, "tally_shared": 0}, {"kernel": 2, "warps_per_sm": 48},
+                     {"kernel": 2, "queue_slots": 64}, {"kernel": 2, "queue_slots": 64, "tally_shared": 0}):
             got = gpu_run_case(model, 5, steps_per_launch=spl, options=opts, finish=False)
             assert np.array_equal(got["energy"], ref["energy"]), (spl, opts)
             assert np.array_equal(got["fixed"], ref["fixed"]), (spl, opts)

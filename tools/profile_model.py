@@ -23,6 +23,9 @@ m.prepare()
 g = psim.GpuSimulator(m.describe(), 0)
 if kernel >= 0:
     g.set_option("kernel", kernel)
+for kv in os.environ.get("PSIM_OPTS", "").split(","):  # e.g. PSIM_OPTS=queue_slots=64,tally_shared=0
+    if "=" in kv:
+        g.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 for rep in range(2):
     src, n = m.sources(1 + rep)
     g.set_sources(src, n, 1 + rep, 0, 1)
