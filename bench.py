@@ -200,8 +200,6 @@ def run_ours(args):
 
     g = psim.GpuSimulator(desc, local)
     g.set_option("steps_per_launch", args.steps_per_launch)
-    if args.tally_aggregate >= 0:
-        g.set_option("tally_aggregate", args.tally_aggregate)
     if args.tally_shared >= 0:
         g.set_option("tally_shared", args.tally_shared)
     if args.warps_per_sm > 0:
@@ -415,7 +413,6 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=0, help="0 = library default (automatic)")
     ap.add_argument("--reduce-every", type=int, default=0,
                     help="recorded measurement steps per tally all-reduce group (0 = one group per launch window of the library)")
-    ap.add_argument("--tally-aggregate", type=int, default=-1)
     ap.add_argument("--tally-shared", type=int, default=-1)
     ap.add_argument("--warps-per-sm", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=-1, help="2 work queues (default), 0 lane-bound slots, 1 lock-step first version")

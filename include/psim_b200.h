@@ -180,8 +180,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out);
  * "warps_per_sm" (0 = occupancy-derived), "kernel" (2 work queues = default, 0 lane-bound shared-memory slots, 1 lock-step first version),
  * "queue_slots" (phonons in flight per warp of the work-queue kernel, 128 or 64; default by mesh size; before set_sources),
  * "tally_shared" (-1 automatic = default; 0 straight to global memory, rows kept as differences along the step axis until
- * their window is complete; 1 / 2 staged per CTA in shared memory as 32-bit halves / 64-bit sums; before set_sources),
- * "tally_aggregate" (0/1, lock-step kernel only: warp match/reduce before the shared-memory atomics). */
+ * their window is complete; 1 / 2 staged per CTA in shared memory as 32-bit halves / 64-bit sums; before set_sources). */
 int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value);
 
 /* Replaces ModelSimulator::reset (modelSimulator.h:20-23) + Sensor::reset (sensor.cpp:54-60). */

@@ -28,6 +28,9 @@ namespace {
 #define PSIM_SLOTS 4
 #define PSIM_SLOT_BLOCKS 1
 #endif
+#ifndef PSIM_QUEUE_SLOTS
+#define PSIM_QUEUE_SLOTS 128  // phonons in flight per warp of the work-queue kernel (its second instantiation has 64)
+#endif
 #ifndef PSIM_SMEM_KB_PER_SM
 #define PSIM_SMEM_KB_PER_SM 196  // shared-memory carve-out the launches are planned for (the rest of the 256 KB is L1)
 #endif
@@ -55,7 +58,6 @@ struct LaunchArgs {
     int32_t* tally_e;
     long long* tally_f;
     uint32_t tally_shared;
-    uint32_t tally_aggregate;
     unsigned long long* stats;       // [0] drift steps [1] flight segments [2] absorbed [3] overflow
     unsigned long long* alive_hist;  // [launch]: pool population after this launch
     uint32_t launch_index;
@@ -522,6 +524,11 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
 // which has headroom, not on the issue slots, which have none.
 // ---------------------------------------------------------------------------------------------------------------
 enum : int { Q_FLY = 0, Q_SCT, Q_WALL, Q_FIN, Q_FREE, Q_COUNT };
+__host__ __device__ constexpr uint32_t ring_capacity(int slots) {
+    uint32_t c = 32;
+    while (c < static_cast<uint32_t>(slots)) { c <<= 1; }
+    return c;
+}
 #ifndef PSIM_PREFETCH_DIST
 #define PSIM_PREFETCH_DIST 0
 #endif
@@ -531,7 +538,8 @@ enum : int { Q_FLY = 0, Q_SCT, Q_WALL, Q_FIN, Q_FREE, Q_COUNT };
 
 template<int NS>
 __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const __grid_constant__ LaunchArgs a) {
-    static_assert(NS <= 256 && (NS & (NS - 1)) == 0 && NS >= 32, "slot numbers are bytes; the queues are power-of-two rings");
+    static_assert(NS <= 256 && NS >= 32, "slot numbers are bytes");
+    constexpr uint32_t QC = ring_capacity(NS);  // the queues are power-of-two rings that can hold every slot
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& P = a.P;
     const uint32_t nst = a.step_end - a.step_begin;
@@ -543,7 +551,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     const size_t tally_bytes = tally_staged(a) ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
     unsigned char* base = smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127));
     uint32_t* sw = reinterpret_cast<uint32_t*>(base) + (threadIdx.x >> 5) * (SF_COUNT * NS);
-    unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SF_COUNT * NS * 4 + (threadIdx.x >> 5) * (Q_COUNT * NS);
+    unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SF_COUNT * NS * 4 + (threadIdx.x >> 5) * (Q_COUNT * QC);
     auto slot_u = [&](int field, uint32_t k) -> uint32_t& { return sw[field * NS + k]; };
     auto slot_f = [&](int field, uint32_t k) -> float& { return reinterpret_cast<float*>(sw)[field * NS + k]; };
     struct Queue {
@@ -553,17 +561,17 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     // lane i takes the i-th of the first `take` entries
     auto pop = [&](Queue& q, int qi, uint32_t take, bool& active) -> uint32_t {
         active = lane < take;
-        const uint32_t k = active ? qb[qi * NS + ((q.head + lane) & (NS - 1))] : 0u;
+        const uint32_t k = active ? qb[qi * QC + ((q.head + lane) & (QC - 1u))] : 0u;
         q.head += take;
         q.count -= take;
         return k;
     };
     auto push = [&](Queue& q, int qi, bool mine, uint32_t k) {
         const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
-        if (mine) { qb[qi * NS + ((q.head + q.count + __popc(m & lt_mask)) & (NS - 1))] = static_cast<unsigned char>(k); }
+        if (mine) { qb[qi * QC + ((q.head + q.count + __popc(m & lt_mask)) & (QC - 1u))] = static_cast<unsigned char>(k); }
         q.count += __popc(m);
     };
-    for (uint32_t i = lane; i < NS; i += 32u) { qb[Q_FREE * NS + i] = static_cast<unsigned char>(i); }
+    for (uint32_t i = lane; i < NS; i += 32u) { qb[Q_FREE * QC + i] = static_cast<unsigned char>(i); }
 
     const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const uint32_t W = a.n_warps;
@@ -793,7 +801,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             const uint32_t t_sct = q_sct.head + q_sct.count, t_wall = q_wall.head + q_wall.count, t_fin = q_fin.head + q_fin.count;
             const unsigned peers = d_fly ? m_fly : (d_sct ? m_sct : (d_wall ? m_wall : m_fin));
             const uint32_t tail = d_fly ? t_fly : (d_sct ? t_sct : (d_wall ? t_wall : t_fin));
-            if (dest >= 0) { qb[dest * NS + ((tail + __popc(peers & lt_mask)) & (NS - 1))] = static_cast<unsigned char>(k); }
+            if (dest >= 0) { qb[dest * QC + ((tail + __popc(peers & lt_mask)) & (QC - 1u))] = static_cast<unsigned char>(k); }
             q_fly.count += n_fly;
             q_sct.count += n_sct;
             q_wall.count += n_wall;

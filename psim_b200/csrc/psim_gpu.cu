@@ -10,8 +10,9 @@
 //   tallies       energy int32[R][S], flux int64[R][S][2] (fixed point), R recorded steps, S sensors.
 //   model image   cells / sensors / tables ... (device_types.h), read-only, L1/L2 resident.
 //
-// One launch = one pass of the whole pool over `steps_per_launch` measurement intervals (1 by default: 32 B read
-// + 32 B written per phonon per interval = the 64 algorithmic bytes per drift-step of SURVEY.md 8d).
+// One launch = one pass of the whole pool over a WINDOW of measurement intervals (plan_launch: up to 1023 while nothing
+// is recorded, as many as the tally staging holds otherwise; psim_gpu_set_option("steps_per_launch", 1) gives the
+// one-interval pass that really moves the 64 algorithmic bytes per drift-step of SURVEY.md 8d).
 #include "../../include/psim_b200.h"
 #include "flatten.h"
 #include "kernels.cuh"
@@ -74,9 +75,8 @@ struct psim_gpu {
     int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
     int64_t opt_warps_per_sm = 0;
     int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
-    int64_t opt_queue_slots = 32 * kSlots;  // phonons in flight per warp of the work-queue kernel (128, or 64: more L1 left for the mesh)
+    int64_t opt_queue_slots = PSIM_QUEUE_SLOTS;  // phonons in flight per warp of the work-queue kernel (128, or 64: more L1 left for the mesh)
     int64_t opt_tally_shared = -1;
-    int64_t opt_tally_aggregate = 0;
     uint32_t last_tally_shared = 0;
     uint32_t last_window = 0;
     uint32_t max_flux_fixed = 0;     // largest |velocity| in flux fixed-point units
@@ -132,10 +132,10 @@ size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
     return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
 }
 
-constexpr int kQueueSlots = 32 * kSlots;                     // slots per warp of the queues kernel ...
-constexpr int kQueueSlotsSmall = kQueueSlots / 2;            // ... and of its second instantiation (option "queue_slots")
+constexpr int kQueueSlots = PSIM_QUEUE_SLOTS;                // slots per warp of the queues kernel ...
+constexpr int kQueueSlotsSmall = 64;                         // ... and of its second instantiation (option "queue_slots")
 constexpr size_t queue_bytes_per_block(int slots) {
-    return static_cast<size_t>(SF_COUNT) * slots * 4 * kWarpsPerBlock + static_cast<size_t>(Q_COUNT) * slots * kWarpsPerBlock;
+    return static_cast<size_t>(SF_COUNT) * slots * 4 * kWarpsPerBlock + static_cast<size_t>(Q_COUNT) * ring_capacity(slots) * kWarpsPerBlock;
 }
 constexpr size_t kQueueBytesPerBlock = queue_bytes_per_block(kQueueSlots);
 // what a block may use so that kSlotBlocks blocks (plus 1 KB each that the driver reserves) fit the planned carve-out;
@@ -425,7 +425,6 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
             const bool narrow = per_entry < (1ull << (32 - kStageLoBits)) && per_entry * hi_max < (1ull << 31) && h->opt_tally_shared != 2;
             a.tally_shared = narrow ? 1u : 2u;
         }
-        a.tally_aggregate = h->opt_tally_aggregate ? 1u : 0u;
         a.stats = h->d_stats;
         a.alive_hist = h->d_alive_hist;
         a.launch_index = h->launches;
@@ -634,8 +633,6 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
             return PSIM_E_STATE;
         }
         h->opt_tally_shared = value;
-    } else if (k == "tally_aggregate") {
-        h->opt_tally_aggregate = value;
     } else {
         h->err = "unknown option: " + k;
         return PSIM_E_INVALID;
