@@ -313,9 +313,9 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
     if (!h) { return PSIM_E_INVALID; }
     PSIM_CUDA(cudaSetDevice(h->device));
     PSIM_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_sources = false;  // a failed call leaves the handle without sources, never with a plan that is half replaced
     if (int rc = psim::plan_births(h->img, sources, n, shard, num_shards, h->plan, h->err)) { return rc; }
     free_plan(h);
-    h->have_sources = false;
     if (int rc = upload(h, &h->d_sources, h->plan.sources)) { return rc; }
     {
         void* p = nullptr;
