@@ -160,3 +160,31 @@ def test_phasor_mode_is_exact_kinematics():
     assert np.abs(r["energy"]).max() <= 0.05 * per_sensor + 3
     # flight time across the bar is 1 ns = 100 steps: the population saturates at n / 10
     assert abs(int(r["alive"][16 * 31 - 1]) - n / 10) <= 0.01 * n  # population is recorded at the end of each 16-step pass
+
+
+def _one_of_many_shards_temperatures(run, model, shards):
+    """Temperatures from ONE shard's tallies scaled by the number of shards (deviational mode: every shard is an unbiased
+    sample of the same job), as z against the reference's fixture of the same bar."""
+    model.set_tallies((run["energy"].astype(np.int64) * shards).astype(np.int32), run["flux"] * shards)
+    model.finish_run(0)
+    six, _, _ = model.results(0)
+    gold = T.golden("linear_demo")
+    reduced = T.case_model("linear_demo")["settings"]["num_phonons"]
+    mine = sum(c for _, _, _, c in run["sources"]) / shards
+    se = gold["out6_std"][:, 0] * np.sqrt(reduced / mine + 1.0 / int(gold["n_seeds"]))
+    return (six[:, 0] - gold["out6_mean"][:, 0]) / se
+
+
+def test_phonon_ids_beyond_32_bits():
+    """6e9 phonons: global phonon ids need more than 32 bits (id_lo + the 8 id_hi bits of the packed word, which also key
+    the Philox counter).  Shard 5999 of 6000 simulates the million ids congruent to 5999, most of them above 2^32; its
+    tallies scaled by 6000 must give the temperatures of the bar."""
+    from psim_b200 import configs
+    shards = 6000
+    model = T.load_model(configs.linear(num_phonons=6_000_000_000).to_dict())
+    model.prepare()
+    run = T.emu_run(model, 3, shard=shards - 1, num_shards=shards, steps_per_pass=16)
+    assert sum(c for _, _, _, c in run["sources"]) in range(6_000_000_000 - 2, 6_000_000_000 + 3)
+    assert 0.9e6 * 60 < run["drift_steps"] < 1.1e6 * 70  # a million phonons at ~65 drift-steps each
+    z = _one_of_many_shards_temperatures(run, model, shards)
+    assert np.abs(z).max() < 5.0 and np.sqrt((z * z).mean()) < 2.5, z

@@ -188,3 +188,70 @@ def test_inconsistent_model_description_is_rejected():
         desc.measurement_steps = saved
     assert lib.psim_gpu_create(C.byref(desc), 0, C.byref(out)) == 0
     lib.psim_gpu_destroy(out)
+
+
+def test_cli_end_to_end_files_and_progress_lines(tmp_path):
+    """`psim a.json b.json missing.json` on the device: the reference's progress lines (main.cpp:10-31, model.cpp:141-182),
+    `ss_<stem>.txt` with six columns per sensor (outputManager.cpp:72-78) and `per_<stem>.txt` in the three-column block
+    format its plotting tools parse (outputManager.cpp:82-114), a failing file reported and skipped, results within the
+    reference's golden scatter."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "psim_b200", "bin", "psim")
+    a = configs.save(configs.linear(num_phonons=400_000).to_dict(), str(tmp_path / "bar.json"))
+    b = configs.save(configs.linear(num_phonons=100_000, sim_type=1, step_interval=4, num_runs=2).to_dict(), str(tmp_path / "wave.json"))
+    env = dict(os.environ, PSIM_SEED="11")
+    r = subprocess.run([cli, a, str(tmp_path / "missing.json"), b], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0
+    out = r.stdout.splitlines()
+    assert out[0] == "Run: 1" and out[1].startswith("Stable sensors: ") and out[2] == "System did not stabilize!!"
+    assert out[3].startswith("Time Taken: ") and out[3].endswith("[s]")
+    assert out[4] == "Run: 1" and "Run: 2" in out and out[-1] == "done"
+    assert "missing.json" in r.stderr
+    ss = (tmp_path / "ss_bar.txt").read_text().splitlines()
+    assert ss[0].startswith('Steady State Results from "bar.json" @ ') and ss[0].endswith("[s] over 1 runs")
+    six = np.array([[float(x) for x in line.split()] for line in ss[1:]])
+    assert six.shape == (20, 6)
+    gold = T.golden("linear_demo")  # 16 reference seeds of this very model: one run must lie within their scatter
+    z = (six[:, 0] - gold["out6_mean"][:, 0]) / (gold["out6_std"][:, 0] * np.sqrt(1.0 + 1.0 / int(gold["n_seeds"])))
+    assert np.abs(z).max() < 6.0 and np.sqrt((z * z).mean()) < 3.0, z
+    per = (tmp_path / "per_wave.txt").read_text().splitlines()
+    assert per[0].startswith('Periodic Results from "wave.json" @ ') and per[0].endswith("[s] over 2 runs")
+    body = per[1:]
+    assert len(body) == 250 * 22  # 1000 steps / interval 4 blocks of (step line, sensor count, 20 sensor rows)
+    for blk in (0, 1, 249):
+        assert int(body[22 * blk]) == 4 * blk + 2 and int(body[22 * blk + 1]) == 20
+        rows = np.array([[float(x) for x in line.split()] for line in body[22 * blk + 2:22 * blk + 22]])
+        assert rows.shape == (20, 3) and np.all(rows[:, 0] > 285.0) and np.all(rows[:, 0] < 315.0)
+
+
+def test_phonon_ids_beyond_32_bits():
+    """The same check as tests/test_emu.py:test_phonon_ids_beyond_32_bits on the CUDA path: shard 5999 of 6000 of a
+    6e9-phonon job (ids above 2^32: id_hi bits of the packed word and of the Philox counter), and that shard is
+    bit-identical whether its million phonons run as one shard or as two half-shards of 12000."""
+    from tests.test_emu import _one_of_many_shards_temperatures
+    shards = 6000
+    model = T.load_model(configs.linear(num_phonons=6_000_000_000).to_dict())
+    model.prepare()
+    src, n = model.sources(3)
+    g = psim.GpuSimulator(model.describe(), 0)
+    try:
+        def shard_run(k, of):
+            g.set_sources(src, n, 3, k, of)
+            g.run()
+            e, f, fx = g.tallies(fixed=True)
+            st = g.stats()
+            return e.astype(np.int64), fx, st.drift_steps, st.total_phonons
+        e, fx, steps, total = shard_run(shards - 1, shards)
+        assert total in range(6_000_000_000 - 2, 6_000_000_000 + 3)
+        assert 0.9e6 * 60 < steps < 1.1e6 * 70
+        # ids == 5999 (mod 6000) are the ids == 5999 or 11999 (mod 12000)
+        e1, f1, s1, _ = shard_run(shards - 1, 2 * shards)
+        e2, f2, s2, _ = shard_run(2 * shards - 1, 2 * shards)
+        assert np.array_equal(e1 + e2, e) and np.array_equal(f1 + f2, fx) and s1 + s2 == steps
+        run = {"energy": e, "flux": fx.astype(np.float64) / 256.0, "sources": [(0, 0, 0, total)]}
+        z = _one_of_many_shards_temperatures(run, model, shards)
+        assert np.abs(z).max() < 5.0 and np.sqrt((z * z).mean()) < 2.5, z
+    finally:
+        g.close()
