@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if force or _stale(LIB, deps):
         cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-shared",
-               "-o", LIB, *srcs]
+               "-o", LIB, *srcs, "-ldl"]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -64,7 +64,7 @@ def build_variant(name: str, defines: dict) -> str:
     out = os.path.join(out_dir, f"libpsim_b200_{name}.so")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o", out,
-           *[f"-D{k}={v}" for k, v in defines.items()], *srcs]
+           *[f"-D{k}={v}" for k, v in defines.items()], *srcs, "-ldl"]
     subprocess.run(cmd, check=True)
     return out
 

@@ -2,12 +2,17 @@
 #include "../../../include/psim_host.h"
 #include "model.h"
 
+#include <cuda_runtime_api.h>
+#include <dlfcn.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
 #include <iostream>
 #include <limits>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -31,6 +36,123 @@ template<typename F> int guarded(int model_error_code, F&& f) {
         return model_error_code;
     }
 }
+
+// ---- NCCL for the tally sum of a multi-device run (psim_model_run_devices) --------------------------------------------
+// Bound at run time (dlopen), only when a run really uses several devices: the library has no load-time dependency on
+// NCCL, and inside a process that already carries an NCCL (a torchrun rank with torch's bundled copy) the loader hands
+// back that one instead of a second copy.  Types and enumerators are the ABI-stable ones of nccl.h (ncclInt32 = 2,
+// ncclInt64 = 4, ncclSum = 0, ncclSuccess = 0).
+struct Nccl {
+    using Comm = void*;
+    int (*CommInitAll)(Comm*, int, const int*) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+
+    static const Nccl& get() {
+        static const Nccl instance = [] {
+            Nccl n;
+            void* lib = nullptr;
+            for (const char* name : { "libnccl.so.2", "libnccl.so" }) {
+                lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+                if (lib) { break; }
+            }
+            if (!lib) {
+                n.why = "libnccl.so.2 not found";
+                return n;
+            }
+            auto sym = [&](const char* name) { return dlsym(lib, name); };
+            n.CommInitAll = reinterpret_cast<decltype(n.CommInitAll)>(sym("ncclCommInitAll"));
+            n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(sym("ncclCommDestroy"));
+            n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(sym("ncclAllReduce"));
+            n.GroupStart = reinterpret_cast<decltype(n.GroupStart)>(sym("ncclGroupStart"));
+            n.GroupEnd = reinterpret_cast<decltype(n.GroupEnd)>(sym("ncclGroupEnd"));
+            n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
+            n.ok = n.CommInitAll && n.CommDestroy && n.AllReduce && n.GroupStart && n.GroupEnd && n.GetErrorString;
+            if (!n.ok) { n.why = "libnccl.so.2 lacks an expected symbol"; }
+            return n;
+        }();
+        return instance;
+    }
+};
+constexpr int kNcclInt32 = 2, kNcclInt64 = 4, kNcclSum = 0;
+
+// One communicator and one stream per device of a multi-device run; all_reduce() sums the device-resident tallies of all
+// handles in place (int32 energy, int64 fixed-point flux: exact, so every device ends up with the bits the host sum gives).
+class TallyExchange {
+public:
+    TallyExchange(const int* devices, size_t n) : devices_(devices, devices + n), comms_(n, nullptr), streams_(n, nullptr) {
+        const Nccl& nccl = Nccl::get();
+        if (!nccl.ok) {
+            why_ = nccl.why;
+            return;
+        }
+        if (std::getenv("PSIM_HOST_SUM")) {
+            why_ = "PSIM_HOST_SUM is set";
+            return;
+        }
+        if (const int e = nccl.CommInitAll(comms_.data(), static_cast<int>(n), devices)) {
+            why_ = std::string("ncclCommInitAll: ") + nccl.GetErrorString(e);
+            std::fill(comms_.begin(), comms_.end(), nullptr);
+            return;
+        }
+        for (size_t d = 0; d < n; ++d) {
+            if (cudaSetDevice(devices[d]) != cudaSuccess || cudaStreamCreateWithFlags(&streams_[d], cudaStreamNonBlocking) != cudaSuccess) {
+                why_ = "cudaStreamCreate failed";
+                return;
+            }
+        }
+        ready_ = true;
+    }
+    ~TallyExchange() {
+        for (size_t d = 0; d < devices_.size(); ++d) {
+            if (streams_[d]) {
+                cudaSetDevice(devices_[d]);
+                cudaStreamDestroy(streams_[d]);
+            }
+            if (comms_[d]) { Nccl::get().CommDestroy(comms_[d]); }
+        }
+    }
+    TallyExchange(const TallyExchange&) = delete;
+    TallyExchange& operator=(const TallyExchange&) = delete;
+    bool ready() const { return ready_; }
+    const std::string& why_not() const { return why_; }
+
+    // the handles have finished their runs (psim_gpu_run is blocking); returns an error text or ""
+    std::string all_reduce(const std::vector<psim_gpu*>& gpus) {
+        const Nccl& nccl = Nccl::get();
+        std::vector<void*> e(gpus.size()), f(gpus.size());
+        uint32_t R = 0, S = 0;
+        for (size_t d = 0; d < gpus.size(); ++d) {
+            if (psim_gpu_tally_buffers(gpus[d], &e[d], &f[d], &R, &S)) { return "psim_gpu_tally_buffers failed"; }
+        }
+        const size_t n = static_cast<size_t>(R) * S;
+        int rc = nccl.GroupStart();
+        for (size_t d = 0; d < gpus.size() && !rc; ++d) {
+            rc = nccl.AllReduce(e[d], e[d], n, kNcclInt32, kNcclSum, comms_[d], streams_[d]);
+            if (!rc) { rc = nccl.AllReduce(f[d], f[d], 2 * n, kNcclInt64, kNcclSum, comms_[d], streams_[d]); }
+        }
+        const int rc_end = nccl.GroupEnd();
+        if (rc || rc_end) { return std::string("ncclAllReduce: ") + nccl.GetErrorString(rc ? rc : rc_end); }
+        for (size_t d = 0; d < gpus.size(); ++d) {
+            if (cudaSetDevice(devices_[d]) != cudaSuccess || cudaStreamSynchronize(streams_[d]) != cudaSuccess) {
+                return "synchronising the tally all-reduce failed";
+            }
+        }
+        return "";
+    }
+
+private:
+    std::vector<int> devices_;
+    std::vector<Nccl::Comm> comms_;
+    std::vector<cudaStream_t> streams_;
+    bool ready_ = false;
+    std::string why_;
+};
 
 int load_with(psim_model** out, const std::function<std::unique_ptr<psim::Model>()>& make) {
     if (!out) {
@@ -248,6 +370,14 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
     std::vector<psim_gpu*> gpus(G, nullptr);
     const int rc = guarded(PSIM_E_STATE, [&]() -> int {
         m.runs.clear();
+        // several devices: their tallies are summed with one NCCL all-reduce per run over NVLink (integers: the result is the
+        // one-device result bit for bit); without a usable NCCL the same integers are summed on the host
+        std::unique_ptr<TallyExchange> exchange;
+        if (G > 1) {
+            exchange = std::make_unique<TallyExchange>(devices, G);
+            if (!exchange->ready() && verbose) { std::cerr << "psim: tallies are summed on the host (" << exchange->why_not() << ")\n"; }
+        }
+        const bool use_nccl = exchange && exchange->ready();
         for (uint64_t run = 0; run < m.num_runs; ++run) {
             if (verbose) { std::cout << "Run: " << run + 1 << '\n'; }
             const auto h0 = std::chrono::steady_clock::now();
@@ -283,7 +413,7 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                 const auto t2 = now();
                 if (!e) { e = psim_gpu_run(gpus[d]); }
                 const auto t3 = now();
-                if (!e) { e = psim_gpu_get_tallies(gpus[d], energy[d].data(), nullptr, fixed[d].data()); }
+                if (!e && !use_nccl) { e = psim_gpu_get_tallies(gpus[d], energy[d].data(), nullptr, fixed[d].data()); }
                 if (!e) { e = psim_gpu_get_stats(gpus[d], &st[d]); }
                 if (timing && d == 0) {
                     std::cerr << "psim timing [ms]: create " << ms(t0, t1) << " set_sources " << ms(t1, t2) << " run " << ms(t2, t3)
@@ -305,10 +435,27 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     return codes[d];
                 }
             }
+            size_t summands = G;
+            if (use_nccl) {
+                const auto t4 = std::chrono::steady_clock::now();
+                if (const std::string err = exchange->all_reduce(gpus); !err.empty()) {
+                    g_error = err;
+                    return PSIM_E_CUDA;
+                }
+                if (const int e = psim_gpu_get_tallies(gpus[0], energy[0].data(), nullptr, fixed[0].data())) {
+                    g_error = psim_gpu_last_error(gpus[0]);
+                    return e;
+                }
+                summands = 1;  // device 0 holds the sum
+                if (std::getenv("PSIM_TIMING")) {
+                    std::cerr << "psim timing [ms]: nccl all-reduce + tallies "
+                              << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t4).count() << '\n';
+                }
+            }
             std::vector<double> flux(2 * n_tally);
             for (size_t i = 0; i < n_tally; ++i) {  // integer sums: independent of the number of devices
                 int64_t e = 0, fx = 0, fy = 0;
-                for (size_t d = 0; d < G; ++d) {
+                for (size_t d = 0; d < summands; ++d) {
                     e += energy[d][i];
                     fx += fixed[d][2 * i];
                     fy += fixed[d][2 * i + 1];

@@ -2,6 +2,8 @@
 seeds of the unmodified reference (tests/golden/make_golden.py).  Statistical bar from BASELINE.json: per-sensor
 temperatures / fluxes (steady state) and traces (periodic, transient) within 3 sigma, sigma from >= 8 seeds of
 each implementation; integer bookkeeping bit-exact across shard counts."""
+import os
+
 import numpy as np
 import pytest
 
@@ -367,6 +369,14 @@ def test_model_run_end_to_end_and_multi_run():
     assert text.startswith('Steady State Results from "linear_demo.json" @ now - Time Taken 0.1[s] over 2 runs')
     if torch.cuda.device_count() >= 2:
         m2 = T.load_model(model)
-        m2.run_devices([0, 1], seed=5)
+        m2.run_devices([0, 1], seed=5)  # tallies summed with an NCCL all-reduce between the two devices
         np.testing.assert_array_equal(m2.results(0)[0], six0)
         np.testing.assert_array_equal(m2.results(1)[0], six1)
+        os.environ["PSIM_HOST_SUM"] = "1"  # the same integers summed on the host
+        try:
+            m3 = T.load_model(model)
+            m3.run_devices([0, 1], seed=5)
+        finally:
+            del os.environ["PSIM_HOST_SUM"]
+        np.testing.assert_array_equal(m3.results(0)[0], six0)
+        np.testing.assert_array_equal(m3.results(1)[0], six1)
