@@ -72,7 +72,7 @@ struct psim_gpu {
     uint32_t birth_offset = 0;
     double kernel_ms = 0.;
     // options
-    int64_t opt_steps_per_launch = 0;  // 0: automatic (as many as keep the per-block tally staging within 32 KB, at most 16)
+    int64_t opt_steps_per_launch = 0;  // 0: automatic (plan_launch: long windows while nothing is recorded, then what the tally staging holds)
     int64_t opt_warps_per_sm = 0;
     int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
     int64_t opt_queue_slots = PSIM_QUEUE_SLOTS;  // phonons in flight per warp of the work-queue kernel (128, or 64: more L1 left for the mesh)
