@@ -262,3 +262,54 @@ def test_cli_without_gpu_reports_and_continues(built_library, tmp_path):
     assert r.stdout.strip().endswith("done")
     assert not (tmp_path / "ss_m.txt").exists()
     assert subprocess.run([cli], capture_output=True, text=True).stdout.startswith("Need filenames")
+
+
+def test_result_readers_round_trip(built_library, tmp_path):
+    """psim_b200/results.py reads what the exporter writes - the reference's table formats (outputManager.cpp:72-114) as its
+    own Python tools parse them (plotting_tools.py:84-157) - back into the numbers the host API reports, to the six
+    significant digits of the text."""
+    from psim_b200 import results
+    rng = np.random.default_rng(3)
+    m = T.load_model(T.case_model("linear_demo"), num_phonons=1000)
+    m.prepare()
+    S, R = m.info.num_sensors, m.info.recorded_steps
+    m.set_tallies(rng.integers(-50, 50, (S, R)).astype(np.int32), rng.normal(0, 1e4, (S, R, 2)))
+    m.finish_run(0)
+    path = tmp_path / "bar.json"
+    path.write_text("{}")
+    m.export(str(path), 2.5)
+    ss = results.read_steady_state(str(tmp_path / "ss_bar.txt"))
+    assert ss.header.kind == "Steady State" and ss.header.model_file == "bar.json" and ss.header.seconds == 2.5 and ss.header.runs == 1
+    six, _, _ = m.results(0)
+    np.testing.assert_allclose(ss.table, six, rtol=1e-5)
+    np.testing.assert_allclose(ss.average_flux()[0], six[:, 2].mean(), rtol=1e-5)
+
+    m = T.load_model(T.case_model("sides_per"), num_phonons=1000)
+    m.prepare()
+    S, R, I = m.info.num_sensors, m.info.recorded_steps, m.info.step_interval
+    m.set_tallies(rng.integers(-5, 5, (S, R)).astype(np.int32), rng.normal(0, 1e4, (S, R, 2)))
+    m.finish_run(0)
+    per = results.parse_periodic(m.export_text("wave.json", 0.25, "now"))
+    assert per.header.kind == "Periodic" and per.header.when == "now"
+    _, temps, fluxes = m.results(0)
+    nb = R // I
+    assert per.temps.shape == (nb, S) and np.array_equal(per.measurement_steps, np.arange(nb) * I + I // 2)
+    np.testing.assert_allclose(per.temps, temps[:, :nb * I].reshape(S, nb, I).mean(axis=2).T, rtol=1e-5)
+    np.testing.assert_allclose(per.x_flux, fluxes[:, :nb * I, 0].reshape(S, nb, I).mean(axis=2).T, rtol=2e-5, atol=1e-3)
+    np.testing.assert_allclose(per.y_flux, fluxes[:, :nb * I, 1].reshape(S, nb, I).mean(axis=2).T, rtol=2e-5, atol=1e-3)
+    with pytest.raises(ValueError):
+        results.parse_periodic("title\n2\n3\n300 1 1\n")  # a block that promises three sensors and holds one
+    with pytest.raises(ValueError):
+        results.parse_steady_state("title\n300 0.1 1 2\n")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/psim_python/json/results"), reason="reference tree not mounted")
+def test_result_readers_parse_the_reference_files():
+    """The three result tables shipped with the reference (2022, an older title line without the run count)."""
+    from psim_b200 import results
+    base = "/root/reference/psim_python/json/results/"
+    for name, sensors in (("ss_linear_demo.txt", 20), ("ss_linear_sides_demo_ss.txt", 1000), ("ss_kinked_demo_120_35_spec.txt", 3108)):
+        ss = results.read_steady_state(base + name)
+        assert ss.table.shape == (sensors, 6) and ss.header is not None and ss.header.runs == 1
+        assert 265.0 < ss.temps.min() and ss.temps.max() < 335.0 and (ss.temps_std >= 0).all()
+    assert results.read_steady_state(base + "ss_linear_demo.txt").header.seconds == pytest.approx(18.1199)
