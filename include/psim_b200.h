@@ -124,7 +124,8 @@ typedef struct psim_stats {
     uint32_t steps_per_launch;
     uint32_t warps;                     /* resident warps = pool segments */
     uint32_t tally_in_shared;           /* last launch: 0 tallies straight to global memory, 1 staged in shared memory as
-                                           32-bit halves, 2 staged as 64-bit sums, 3 global memory in difference form */
+                                           32-bit halves, 2 staged as 64-bit sums, 3 global memory in difference form,
+                                           4 staged as three 32-bit parts (pools too large for 1) */
     uint64_t image_bytes;               /* host->device bytes of the model image (psim_gpu_create) */
     uint64_t plan_bytes;                /* host->device bytes of the sources + birth plan (psim_gpu_set_sources) */
     uint64_t tally_bytes;               /* device->host bytes of psim_gpu_get_tallies */
@@ -180,7 +181,8 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out);
  * "warps_per_sm" (0 = occupancy-derived), "kernel" (2 work queues = default, 0 lane-bound shared-memory slots, 1 lock-step first version),
  * "queue_slots" (phonons in flight per warp of the work-queue kernel, 128 or 64; default by mesh size; before set_sources),
  * "tally_shared" (-1 automatic = default; 0 straight to global memory, rows kept as differences along the step axis until
- * their window is complete; 1 / 2 staged per CTA in shared memory as 32-bit halves / 64-bit sums; before set_sources). */
+ * their window is complete; 1 / 4 / 2 staged per CTA in shared memory as two / three 32-bit parts / 64-bit sums - 1 and 4
+ * fall back to the next form when their exactness bound does not hold; before set_sources). */
 int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value);
 
 /* Replaces ModelSimulator::reset (modelSimulator.h:20-23) + Sensor::reset (sensor.cpp:54-60). */

@@ -63,8 +63,15 @@ struct LaunchArgs {
     uint32_t launch_index;
 };
 
-__device__ __forceinline__ size_t tally_smem_offset_f(uint32_t nst, uint32_t S) {
+__host__ __device__ __forceinline__ size_t tally_smem_offset_f(uint32_t nst, uint32_t S) {
     return (static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15);
+}
+
+// Shared-memory bytes of the per-CTA tally staging of a window of nst steps, by form (LaunchArgs::tally_shared): 1 five
+// and 4 seven 32-bit words per (step, sensor), 2 an int32 array followed by an int64[2] array.
+__host__ __device__ __forceinline__ size_t tally_stage_bytes(uint32_t form, uint32_t nst, uint32_t S) {
+    const size_t n = static_cast<size_t>(nst) * S;
+    return form == 4u ? ((n * 28 + 15) & ~static_cast<size_t>(15)) : tally_smem_offset_f(nst, S) + n * 16;
 }
 
 __device__ __forceinline__ void atomic_add_i64(long long* p, long long v) {
@@ -80,6 +87,11 @@ __device__ __forceinline__ void atomic_add_i64(long long* p, long long v) {
 // for the 64-bit staging (tally_shared == 2), which this function serves together with the plain global adds.
 constexpr uint32_t kStageLoBits = 11u;
 constexpr uint32_t kStageLoMask = (1u << kStageLoBits) - 1u;
+// Pools too large for that bound (above ~1.2e8 phonons per GPU) split every contribution in THREE: two unsigned parts of
+// kStageWideBits bits and the signed rest (tally_shared == 4, seven words per entry): 14 native atomics per flight
+// segment instead of 10, exact up to 2^24 contributions per entry.
+constexpr uint32_t kStageWideBits = 8u;
+constexpr uint32_t kStageWideMask = (1u << kStageWideBits) - 1u;
 
 __device__ __forceinline__ void tally_add(const LaunchArgs& a, int32_t* acc_e, long long* acc_f, uint32_t local_row,
                                           uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
@@ -106,6 +118,17 @@ __device__ __forceinline__ void stage_add_narrow(uint32_t* q, int32_t e, int32_t
     atomicAdd(reinterpret_cast<int32_t*>(q + 4), fy >> kStageLoBits);
 }
 
+// seven words: e, fx low / middle / high, fy low / middle / high
+__device__ __forceinline__ void stage_add_wide(uint32_t* q, int32_t e, int32_t fx, int32_t fy) {
+    atomicAdd(reinterpret_cast<int32_t*>(q), e);
+    atomicAdd(q + 1, static_cast<uint32_t>(fx) & kStageWideMask);
+    atomicAdd(q + 2, (static_cast<uint32_t>(fx) >> kStageWideBits) & kStageWideMask);
+    atomicAdd(reinterpret_cast<int32_t*>(q + 3), fx >> (2u * kStageWideBits));
+    atomicAdd(q + 4, static_cast<uint32_t>(fy) & kStageWideMask);
+    atomicAdd(q + 5, (static_cast<uint32_t>(fy) >> kStageWideBits) & kStageWideMask);
+    atomicAdd(reinterpret_cast<int32_t*>(q + 6), fy >> (2u * kStageWideBits));
+}
+
 // Tally a phonon into the recorded steps [k0, k1) that ended during one flight segment (same sensor, sign and velocity
 // for all of them).  Rows are kept as DIFFERENCES along the step axis - +v at the first row, -v behind the last - so a
 // segment costs a fixed number of atomics however many steps it crossed, and no loop whose trip count differs from lane
@@ -125,6 +148,12 @@ __device__ __forceinline__ void tally_range(const LaunchArgs& a, int32_t* acc_e,
         uint32_t* q = reinterpret_cast<uint32_t*>(acc_e) + 5u * (l0 * S + sensor);
         stage_add_narrow(q, e, fx, fy);
         if (l1 < a.step_end - a.step_begin) { stage_add_narrow(q + 5u * (l1 - l0) * S, -e, -fx, -fy); }
+    } else if (a.tally_shared == 4u) {
+        const uint32_t S = a.P.n_sensors;
+        const uint32_t l0 = k0 - a.step_begin, l1 = k1 - a.step_begin;
+        uint32_t* q = reinterpret_cast<uint32_t*>(acc_e) + 7u * (l0 * S + sensor);
+        stage_add_wide(q, e, fx, fy);
+        if (l1 < a.step_end - a.step_begin) { stage_add_wide(q + 7u * (l1 - l0) * S, -e, -fx, -fy); }
     } else if (a.tally_shared == 3u) {
         const uint32_t S = a.P.n_sensors;
         const uint32_t r0 = k0 + 1u - a.P.first_tally_step, r1 = k1 + 1u - a.P.first_tally_step;
@@ -143,13 +172,14 @@ __device__ __forceinline__ void tally_range(const LaunchArgs& a, int32_t* acc_e,
     }
 }
 
-__device__ __forceinline__ bool tally_staged(const LaunchArgs& a) { return a.tally_shared == 1u || a.tally_shared == 2u; }
+__device__ __forceinline__ bool tally_staged(const LaunchArgs& a) { return a.tally_shared == 1u || a.tally_shared == 2u || a.tally_shared == 4u; }
 
 __device__ __forceinline__ void tally_init(const LaunchArgs& a, int32_t* acc_e, long long* acc_f) {
     if (!tally_staged(a)) { return; }
     const uint32_t n = (a.step_end - a.step_begin) * a.P.n_sensors;
-    if (a.tally_shared == 1u) {
-        for (uint32_t i = threadIdx.x; i < 5u * n; i += kBlock) { acc_e[i] = 0; }
+    if (a.tally_shared == 1u || a.tally_shared == 4u) {
+        const uint32_t words = (a.tally_shared == 1u ? 5u : 7u) * n;
+        for (uint32_t i = threadIdx.x; i < words; i += kBlock) { acc_e[i] = 0; }
     } else {
         for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
             acc_e[i] = 0;
@@ -164,16 +194,24 @@ __device__ __forceinline__ void tally_flush(const LaunchArgs& a, const int32_t* 
     if (!tally_staged(a)) { return; }
     __syncthreads();
     const uint32_t S = a.P.n_sensors, nst = a.step_end - a.step_begin;
-    if (a.tally_shared == 1u) {
+    if (a.tally_shared == 1u || a.tally_shared == 4u) {
         // difference rows -> running sums along the steps of the window, one thread per (sensor, component)
         const uint32_t* words = reinterpret_cast<const uint32_t*>(acc_e);
+        const bool wide = a.tally_shared == 4u;
         for (uint32_t i = threadIdx.x; i < 3u * S; i += kBlock) {
             const uint32_t s = i / 3u, c = i % 3u;
             long long run = 0;
             for (uint32_t l = 0; l < nst; ++l) {
-                const uint32_t* q = words + 5u * (l * S + s);
-                run += (c == 0u) ? static_cast<long long>(static_cast<int32_t>(q[0]))
-                                 : static_cast<long long>(static_cast<int32_t>(q[2u * c])) * (1 << kStageLoBits) + static_cast<long long>(q[2u * c - 1u]);
+                const uint32_t* q = words + (wide ? 7u : 5u) * (l * S + s);
+                if (c == 0u) {
+                    run += static_cast<long long>(static_cast<int32_t>(q[0]));
+                } else if (wide) {
+                    const uint32_t* p = q + 3u * c - 2u;  // low, middle, high of this component
+                    run += static_cast<long long>(static_cast<int32_t>(p[2])) * (1 << (2u * kStageWideBits)) +
+                           static_cast<long long>(p[1]) * (1 << kStageWideBits) + static_cast<long long>(p[0]);
+                } else {
+                    run += static_cast<long long>(static_cast<int32_t>(q[2u * c])) * (1 << kStageLoBits) + static_cast<long long>(q[2u * c - 1u]);
+                }
                 const uint32_t row = a.step_begin + l + 1u;
                 if (row < a.P.first_tally_step || run == 0) { continue; }
                 const size_t k = static_cast<size_t>(row - a.P.first_tally_step) * S + s;
@@ -282,7 +320,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
     tally_init(a, acc_e, acc_f);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t tally_bytes = tally_staged(a) ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
+    const size_t tally_bytes = tally_staged(a) ? tally_stage_bytes(a.tally_shared, nst, P.n_sensors) : 0;
     uint32_t* sw = reinterpret_cast<uint32_t*>(smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127))) +
                    (threadIdx.x >> 5) * (SF_COUNT * K * 32) + lane;
     auto slot_u = [&](int field, uint32_t k) -> uint32_t& { return sw[(field * K + k) * 32]; };
@@ -548,7 +586,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     tally_init(a, acc_e, acc_f);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t tally_bytes = tally_staged(a) ? tally_smem_offset_f(nst, P.n_sensors) + static_cast<size_t>(nst) * P.n_sensors * 16 : 0;
+    const size_t tally_bytes = tally_staged(a) ? tally_stage_bytes(a.tally_shared, nst, P.n_sensors) : 0;
     unsigned char* base = smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127));
     uint32_t* sw = reinterpret_cast<uint32_t*>(base) + (threadIdx.x >> 5) * (SF_COUNT * NS);
     unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SF_COUNT * NS * 4 + (threadIdx.x >> 5) * (Q_COUNT * QC);

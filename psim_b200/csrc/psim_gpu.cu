@@ -128,9 +128,6 @@ void free_pool(psim_gpu* h) {
 
 constexpr size_t kSlotBytesPerBlock = static_cast<size_t>(SF_COUNT) * kSlots * 32 * 4 * kWarpsPerBlock;
 
-size_t tally_smem_bytes(uint32_t nst, uint32_t S) {
-    return ((static_cast<size_t>(nst) * S * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(nst) * S * 16;
-}
 
 constexpr int kQueueSlots = PSIM_QUEUE_SLOTS;                // slots per warp of the queues kernel ...
 constexpr int kQueueSlotsSmall = 64;                         // ... and of its second instantiation (option "queue_slots")
@@ -159,9 +156,26 @@ uint32_t effective_steps_per_launch(const psim_gpu* h) {
 // How a launch that starts at step s0 tallies, and how far it may reach: windows without a recorded measurement need
 // no staging at all; otherwise the per-block staging must fit the budget, unless the model has so many sensors that
 // tallying straight into global memory is contention-free - with few sensors the window is shortened instead.
-void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1, bool& shared, size_t& smem) {
+// Which staged form is exact for a launch over the birth entries [e0, e1): a block adds at most two contributions per
+// phonon it handles to one (step, sensor) entry - as the first row of one flight segment, behind the last of another.
+//   1  two 32-bit parts per flux component (kStageLoBits low bits + the signed rest): the fast one
+//   4  three parts (2 x kStageWideBits + rest): pools too large for form 1 (above ~1.2e8 phonons per GPU)
+//   2  64-bit sums (compare-and-swap loops): whatever is left, or on request
+uint32_t staged_form(const psim_gpu* h, uint32_t s0, uint32_t s1) {
+    if (h->opt_tally_shared == 2) { return 2u; }
+    const uint64_t births = h->plan.prefix[h->plan.step_begin[s1]] - h->plan.prefix[h->plan.step_begin[s0]];
+    const uint64_t chunks_per_warp = (((births + 31) >> 5) + h->n_warps - 1) / h->n_warps;
+    const uint64_t per_entry = 2ull * kWarpsPerBlock * (h->seg_cap + chunks_per_warp * 32);
+    const uint64_t flux_max = h->max_flux_fixed;
+    const bool narrow = per_entry < (1ull << (32 - kStageLoBits)) && per_entry * ((flux_max >> kStageLoBits) + 1) < (1ull << 31);
+    const bool wide = per_entry < (1ull << (32 - kStageWideBits)) && per_entry * ((flux_max >> (2 * kStageWideBits)) + 1) < (1ull << 31);
+    if (narrow && h->opt_tally_shared != 4) { return 1u; }
+    return wide ? 4u : 2u;
+}
+
+void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1, uint32_t& form, size_t& smem) {
     const uint32_t B = effective_steps_per_launch(h);
-    shared = false;
+    form = 0;
     smem = 0;
     if (h->opt_steps_per_launch <= 0 && s0 + 2 <= h->P.first_tally_step) {
         // automatic mode, nothing recorded yet (steady state: the first 90 % of the steps): long windows, cut at the
@@ -176,10 +190,14 @@ void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1
         if (h->opt_steps_per_launch <= 0) { s1 = std::min(s0 + kGlobalTallyWindow, step_end); }  // no staging: nothing limits the window
         return;
     }
-    while (s1 > s0 + 1 && tally_smem_bytes(s1 - s0, h->P.n_sensors) > budget) { --s1; }
-    smem = tally_smem_bytes(s1 - s0, h->P.n_sensors);
-    shared = smem <= budget;
-    if (!shared) { smem = 0; }
+    const uint32_t want = staged_form(h, s0, s1);  // a shorter window has no more births: the form stays exact
+    while (s1 > s0 + 1 && tally_stage_bytes(want, s1 - s0, h->P.n_sensors) > budget) { --s1; }
+    smem = tally_stage_bytes(want, s1 - s0, h->P.n_sensors);
+    if (smem <= budget) {
+        form = want;
+    } else {
+        smem = 0;  // not even one step fits: plain global adds
+    }
 }
 
 int zero_run_state(psim_gpu* h) {
@@ -389,9 +407,10 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
     PSIM_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
     for (uint32_t s0 = step_begin, s1 = 0; s0 < step_end; s0 = s1) {
-        bool shared = false;
+        uint32_t form = 0;
         size_t smem = 0;
-        plan_launch(h, s0, step_end, s1, shared, smem);
+        plan_launch(h, s0, step_end, s1, form, smem);
+        const bool shared = form != 0u;
         LaunchArgs a{};
         a.P = h->P;
         a.in_a = h->pool_a[h->cur];
@@ -414,17 +433,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         h->birth_offset = static_cast<uint32_t>((h->birth_offset + ((a.n_births + 31) >> 5)) % h->n_warps);
         a.tally_e = h->tally_e;
         a.tally_f = h->tally_f;
-        a.tally_shared = h->diff_mode ? 3u : 0u;  // 0: a staged window that did not fit even for one step (plain global adds)
-        if (shared) {
-            // native 32-bit staging of the flux (kernels.cuh:tally_range) is exact while the low halves (kStageLoBits bits per
-            // contribution) and the high halves of one entry stay within 32 bits: a block adds at most two contributions per
-            // phonon it handles to one (step, sensor) entry - as the first row of one flight segment, behind the last of another
-            const uint64_t chunks_per_warp = (((a.n_births + 31) >> 5) + h->n_warps - 1) / h->n_warps;
-            const uint64_t per_entry = 2ull * kWarpsPerBlock * (h->seg_cap + chunks_per_warp * 32);
-            const uint64_t hi_max = (static_cast<uint64_t>(h->max_flux_fixed) >> kStageLoBits) + 1;
-            const bool narrow = per_entry < (1ull << (32 - kStageLoBits)) && per_entry * hi_max < (1ull << 31) && h->opt_tally_shared != 2;
-            a.tally_shared = narrow ? 1u : 2u;
-        }
+        a.tally_shared = h->diff_mode ? 3u : form;  // form 0: a staged window that did not fit even for one step (plain global adds)
         a.stats = h->d_stats;
         a.alive_hist = h->d_alive_hist;
         a.launch_index = h->launches;
@@ -495,9 +504,9 @@ int psim_gpu_next_window(psim_gpu* h, uint32_t step_begin, uint32_t* step_end) {
     const uint32_t last = h->P.num_steps - 1;
     *step_end = last;
     if (step_begin >= last) { return PSIM_OK; }
-    bool shared = false;
+    uint32_t form = 0;
     size_t smem = 0;
-    plan_launch(h, step_begin, last, *step_end, shared, smem);
+    plan_launch(h, step_begin, last, *step_end, form, smem);
     return PSIM_OK;
 }
 
@@ -628,8 +637,8 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
         }
         h->opt_queue_slots = value;
     } else if (k == "tally_shared") {
-        if (h->have_sources || value < -1 || value > 2) {  // the tally form of a run (staged / difference rows) is fixed when it starts
-            h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 or 2 (staged, 32- / 64-bit) and set before set_sources";
+        if (h->have_sources || value < -1 || value > 4 || value == 3) {  // the tally form of a run is fixed when it starts
+            h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 / 4 / 2 (staged: two / three 32-bit parts, 64-bit) and set before set_sources";
             return PSIM_E_STATE;
         }
         h->opt_tally_shared = value;

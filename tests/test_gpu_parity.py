@@ -83,7 +83,8 @@ def test_kernel_variants_and_tally_paths_agree_bit_for_bit():
         for opts in ({"kernel": 1, "tally_shared": 1}, {"kernel": 0, "tally_shared": 1},
                      {"kernel": 0, "tally_shared": 0}, {"kernel": 0, "warps_per_sm": 48}, {"kernel": 2, "tally_shared": 1},
                      {"kernel": 2, "tally_shared": 2}, {"kernel": 2, "tally_shared": 0}, {"kernel": 2, "warps_per_sm": 48},
-                     {"kernel": 2, "queue_slots": 64}, {"kernel": 2, "queue_slots": 64, "tally_shared": 0}):
+                     {"kernel": 2, "queue_slots": 64}, {"kernel": 2, "queue_slots": 64, "tally_shared": 0},
+                     {"kernel": 2, "tally_shared": 4}, {"kernel": 0, "tally_shared": 4}, {"kernel": 1, "tally_shared": 4}):
             got = gpu_run_case(model, 5, steps_per_launch=spl, options=opts, finish=False)
             assert np.array_equal(got["energy"], ref["energy"]), (spl, opts)
             assert np.array_equal(got["fixed"], ref["fixed"]), (spl, opts)
@@ -105,6 +106,12 @@ def test_staged_tally_forms_agree_on_automatic_windows():
         assert a["stats"][0]["launches"] == b["stats"][0]["launches"] > 1
         assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["fixed"], b["fixed"])
         assert np.abs(a["energy"]).sum() > 0
+        # the three-part form (pools too large for the two-part bound) takes 28 instead of 20 bytes per entry, so its automatic
+        # windows differ: compared on fixed 16-step windows
+        c = gpu_run_case(model, 9, steps_per_launch=16, options={"tally_shared": 4}, finish=False)
+        d = gpu_run_case(model, 9, steps_per_launch=16, options={"tally_shared": 2}, finish=False)
+        assert c["stats"][0]["tally_in_shared"] == 4 and d["stats"][0]["tally_in_shared"] == 2
+        assert np.array_equal(c["energy"], d["energy"]) and np.array_equal(c["fixed"], d["fixed"])
 
 
 FULL_SIZE = {"sige": 100_000_000, "linear_demo": 5_000_000, "sides_ss": 10_000_000, "sides_trans": 10_000_000}
