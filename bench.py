@@ -170,6 +170,22 @@ def emit(obj):
         os.write(_RESULT_FD, line)
 
 
+def agree_on_cuts(cuts, num_steps: int, world: int, rank: int, device):
+    """Every rank must cut a job into the same groups of measurement steps (each group ends with a collective).  The
+    library's launch windows depend, through the exactness bound of the tally staging, on the capacity of the rank's own
+    pool - which may differ by one phonon between ranks - so rank 0's cuts are broadcast and used by all; a rank whose own
+    windows are shorter simply needs two launches for such a group."""
+    if world == 1:
+        return list(cuts)
+    import torch
+    import torch.distributed as dist
+    t = torch.full((num_steps + 2,), -1, dtype=torch.int64, device=device)
+    if rank == 0:
+        t[:len(cuts)] = torch.tensor(cuts, dtype=torch.int64)
+    dist.broadcast(t, 0)
+    return [int(x) for x in t.tolist() if x >= 0]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -218,26 +234,31 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     chunk = max(args.steps_per_launch, args.reduce_every) if args.reduce_every > 0 else 0
 
-    def one_job(seed):
-        """All measurement steps.  Steps whose measurement is not recorded (steady state: the first 90 %) need no
-        exchange and go to the library in one call (it chooses its own launch windows); for the recorded steps the
-        tally all-reduce of a group of steps is issued as soon as the group's launches are enqueued."""
-        first = M - R  # first step whose measurement is recorded
-        s = 0
+    first = M - R  # first step whose measurement is recorded
+
+    def plan_cuts():
+        """Steps whose measurement is not recorded (steady state: the first 90 %) need no exchange and go to the library
+        in one call (it chooses its own launch windows); the recorded steps go in groups that end where the library's
+        launch windows end (no extra launch for the exchange; --reduce-every N asks for groups of N steps instead)."""
+        cuts, s = [0], 0
         if first > 1:
-            g.run_steps(0, first - 1, stream.cuda_stream)
             s = first - 1
+            cuts.append(s)
         while s < M - 1:
-            # groups end where the library's own launch windows end (no extra launch for the exchange); --reduce-every N
-            # asks for groups of N steps instead
-            e = min(s + chunk, M - 1) if chunk > 0 else g.next_window(s)
+            s = min(s + chunk, M - 1) if chunk > 0 else g.next_window(s)
+            cuts.append(s)
+        return agree_on_cuts(cuts, M, world, rank, f"cuda:{local}")
+
+    def one_job(cuts):
+        """All measurement steps; the tally all-reduce of a group of steps is issued as soon as the group's launches are
+        enqueued."""
+        for s, e in zip(cuts[:-1], cuts[1:]):
             g.run_steps(s, e, stream.cuda_stream)
             if world > 1:
                 r0, r1 = max(s + 1 - first, 0), e + 1 - first  # tally rows completed by steps [s, e)
                 if r1 > r0:
                     dist.all_reduce(t_energy[r0:r1])
                     dist.all_reduce(t_flux[r0:r1])
-            s = e
 
     def barrier():
         torch.cuda.synchronize()
@@ -252,13 +273,14 @@ def run_ours(args):
         seed = 1000 + it
         src, n = model.sources(seed)
         g.set_sources(src, n, seed, rank, world)  # untimed: pool reset, tallies zeroed, birth plan resident in HBM
+        cuts = plan_cuts()
         timed = it >= args.warmup
         if timed and it == args.warmup and sampler:
             sampler.__enter__()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        one_job(seed)
+        one_job(cuts)
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)

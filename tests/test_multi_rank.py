@@ -54,3 +54,30 @@ def test_two_rank_allreduce_equals_single_shard(tmp_path):
         assert np.array_equal(got["energy"], ref["energy"])
         assert np.array_equal(got["fixed"], ref["fixed"])
         assert int(got["steps"][0]) == ref["drift_steps"]
+
+
+def _cuts_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = [0, 899, 935, 971, 999] if rank == 0 else [0, 899, 925, 951, 977, 999]  # e.g. another staging form on this rank
+    cuts = bench.agree_on_cuts(mine, 1000, world, rank, "cpu")
+    with open(os.path.join(out_dir, f"cuts{rank}.txt"), "w") as f:
+        f.write(" ".join(map(str, cuts)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ranks_agree_on_the_groups_of_steps(tmp_path):
+    """bench.py: every group of measurement steps ends with a collective, so all ranks must use the same cuts - rank 0's -
+    even where their own launch windows would differ."""
+    import bench
+    assert bench.agree_on_cuts([0, 5, 9], 10, 1, 0, "cpu") == [0, 5, 9]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_cuts_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        assert (tmp_path / f"cuts{rank}.txt").read_text() == "0 899 935 971 999"
