@@ -6,6 +6,7 @@ import json
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -313,3 +314,13 @@ def test_result_readers_parse_the_reference_files():
         assert ss.table.shape == (sensors, 6) and ss.header is not None and ss.header.runs == 1
         assert 265.0 < ss.temps.min() and ss.temps.max() < 335.0 and (ss.temps_std >= 0).all()
     assert results.read_steady_state(base + "ss_linear_demo.txt").header.seconds == pytest.approx(18.1199)
+
+
+def test_loader_survives_damaged_files(built_library):
+    """800 damaged variants of a valid model file (tests/fuzz_loader.py): every one is either rejected with an error code or
+    loaded; a crash of the loader would end the subprocess with a signal."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz_loader.py"), "7", "800"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-500:])
+    accepted, rejected = (int(x) for x in r.stdout.split()[1::2])
+    assert accepted + rejected >= 790 and rejected > 600 and accepted > 0
