@@ -35,8 +35,9 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         fail(err, PSIM_E_INVALID, "model exceeds packed-index limits (16 materials, 2^20 sensors, 2^27 cells)", rc);
         return rc;
     }
-    if (d.measurement_steps < 2 || !(d.simulation_time > 0.) || d.step_adjustment >= d.measurement_steps) {
-        fail(err, PSIM_E_INVALID, "invalid measurement_steps / simulation_time / step_adjustment", rc);
+    if (d.measurement_steps < 2 || d.measurement_steps > (1u << 24) || !(d.simulation_time > 0.) ||
+        !(d.simulation_time < 1e300) || d.step_adjustment >= d.measurement_steps) {
+        fail(err, PSIM_E_INVALID, "invalid measurement_steps (2 ... 2^24) / simulation_time / step_adjustment", rc);
         return rc;
     }
     const double step_time = d.simulation_time / static_cast<double>(d.measurement_steps);
@@ -202,7 +203,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
                 o.link[k] = PSIM_LINK_BOUNDARY << 30;
                 continue;
             }
-            if (!d.subsurfaces || first + n > d.num_subsurfaces || n > 127) {
+            if (!d.subsurfaces || n > 127 || first >= d.num_subsurfaces || n > d.num_subsurfaces - first) {  // (no 32-bit wrap-around)
                 fail(err, PSIM_E_INVALID, "cell edge sub-surface range is out of bounds", rc);
                 return rc;
             }

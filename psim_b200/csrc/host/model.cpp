@@ -547,6 +547,11 @@ std::vector<psim_source> Model::source_counts(uint64_t seed) {
     // ModelSimulator::initPhononBuilders, modelSimulator.cpp:43-85.  The fractional phonon is resolved with a
     // hash of (seed, source ordinal) instead of the reference's unseeded urand(), so the integers depend on
     // the seed only - never on how many GPUs share the work.
+    // A model in which every cell and every emitting surface sits at t_eq holds no energy: the reference divides by an
+    // energy per phonon of zero there (NaN -> size_t, modelSimulator.cpp:44-49) and never returns; here it is an error.
+    if (!(eff_energy_ > 0.) || !std::isfinite(eff_energy_)) {
+        throw std::runtime_error("The model holds no energy to distribute: every cell and emitting surface is at t_eq.");
+    }
     std::vector<psim_source> out;
     uint64_t ordinal = 0;
     auto phonons_for = [&](double energy) -> uint64_t {

@@ -269,7 +269,12 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         return bail(PSIM_E_NO_DEVICE);
     }
     h->sm_count = prop.multiProcessorCount;
-    if (int rc = psim::flatten_model(*desc, h->img, h->err)) { return bail(rc); }
+    try {  // nothing throws across the ABI: a description whose sizes exhaust the host's memory is an invalid description
+        if (int rc = psim::flatten_model(*desc, h->img, h->err)) { return bail(rc); }
+    } catch (const std::exception& e) {
+        h->err = std::string("model description rejected: ") + e.what();
+        return bail(PSIM_E_INVALID);
+    }
     {
         float vmax = h->img.scalars.phasor ? 1000.f : 0.f;
         for (float v : h->img.velocities) { vmax = std::max(vmax, std::fabs(v)); }
@@ -332,7 +337,12 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
     PSIM_CUDA(cudaSetDevice(h->device));
     PSIM_CUDA(cudaStreamSynchronize(h->stream));
     h->have_sources = false;  // a failed call leaves the handle without sources, never with a plan that is half replaced
-    if (int rc = psim::plan_births(h->img, sources, n, shard, num_shards, h->plan, h->err)) { return rc; }
+    try {
+        if (int rc = psim::plan_births(h->img, sources, n, shard, num_shards, h->plan, h->err)) { return rc; }
+    } catch (const std::exception& e) {
+        h->err = std::string("sources rejected: ") + e.what();
+        return PSIM_E_INVALID;
+    }
     free_plan(h);
     if (int rc = upload(h, &h->d_sources, h->plan.sources)) { return rc; }
     {

@@ -188,3 +188,21 @@ def test_phonon_ids_beyond_32_bits():
     assert 0.9e6 * 60 < run["drift_steps"] < 1.1e6 * 70  # a million phonons at ~65 drift-steps each
     z = _one_of_many_shards_temperatures(run, model, shards)
     assert np.abs(z).max() < 5.0 and np.sqrt((z * z).mean()) < 2.5, z
+
+
+def test_damaged_descriptions_are_rejected_or_run_to_completion():
+    """1500 damaged psim_model_desc / psim_source inputs (tests/fuzz_desc.py) through flatten_model + plan_births and, when
+    accepted, a run of the emulated particle loop: error code or finished run, never a crash (the subprocess would end
+    with a signal) or a hang (timeout)."""
+    import os
+    import subprocess
+    import sys
+    T.emu_lib()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_desc.py"), "5", "1500"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-500:])
+    first, last = r.stdout.strip().splitlines()[0], r.stdout.strip().splitlines()[-1]
+    assert first.startswith("baseline (0,") and "final (0," in last  # the undamaged description runs before and after
+    errors, ok = int(last.split()[1]), int(last.split()[3])
+    assert errors > 500 and ok > 300

@@ -324,3 +324,17 @@ def test_loader_survives_damaged_files(built_library):
     assert r.returncode == 0, (r.returncode, r.stderr[-500:])
     accepted, rejected = (int(x) for x in r.stdout.split()[1::2])
     assert accepted + rejected >= 790 and rejected > 600 and accepted > 0
+
+
+def test_model_without_energy_is_an_error(built_library):
+    """Every temperature equal to t_eq: total energy 0, energy per phonon 0.  The reference turns 0 / 0 into a phonon count
+    (modelSimulator.cpp:44-49) and never returns; the host layer reports it."""
+    m = T.load_model(configs.linear(num_phonons=1000, t_high=300, t_low=300).to_dict())
+    m.prepare()
+    assert m.energy() == (0.0, 0.0)
+    with pytest.raises(psim.PsimError) as ei:
+        m.sources(1)
+    assert "no energy" in ei.value.message
+    with pytest.raises(psim.PsimError) as ei:
+        m.run(device=0, seed=1)
+    assert "no energy" in ei.value.message
