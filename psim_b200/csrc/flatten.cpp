@@ -26,7 +26,8 @@ bool fail(std::string& err, int code, const std::string& msg, int& rc) {
 int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
     int rc = 0;
     if (!d.materials || !d.sensors || !d.cells || !d.tables || !d.velocities || d.num_materials == 0 ||
-        d.num_sensors == 0 || d.num_cells == 0 || d.num_tables == 0) {
+        d.num_sensors == 0 || d.num_cells == 0 || d.num_tables == 0 || (d.num_emitters > 0 && !d.emitters) ||
+        (d.num_subsurfaces > 0 && !d.subsurfaces)) {
         fail(err, PSIM_E_INVALID, "model description has empty or null arrays", rc);
         return rc;
     }
