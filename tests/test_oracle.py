@@ -1,6 +1,8 @@
 """The oracle (oracle/model.py + oracle/sim.c, a CPU restatement of the reference) pinned against the golden
 fixtures produced by the UNMODIFIED reference (tests/golden/, 16 seeds per case): deterministic known answers to
 1e-12, Monte Carlo tallies to 3 sigma."""
+from concurrent.futures import ProcessPoolExecutor
+
 import numpy as np
 import pytest
 
@@ -31,16 +33,21 @@ def test_oracle_tables_and_energies_match_reference(name):
                 np.testing.assert_allclose(tab[-1], kat["tables_last"][mi][ti][kind], rtol=1e-10)
 
 
-def _oracle_features(name, seeds):
-    runs = []
-    for seed in seeds:
-        om = OracleModel(T.case_model(name))
-        om.prepare()
-        e, f, _, _ = om.run(seed)
-        six, temps, fluxes = om.finish_run()
-        order = np.argsort(om.sensor_ids, kind="stable")
-        runs.append(T.run_features(e[order], f[order], om.sim_type, six, temps, fluxes))
-    return runs
+def _oracle_one(args):
+    name, seed = args
+    om = OracleModel(T.case_model(name))
+    om.prepare()
+    e, f, _, _ = om.run(seed)
+    six, temps, fluxes = om.finish_run()
+    order = np.argsort(om.sensor_ids, kind="stable")
+    return T.run_features(e[order], f[order], om.sim_type, six, temps, fluxes)
+
+
+def _oracle_features(name, seeds, processes=1):
+    if processes == 1:
+        return [_oracle_one((name, seed)) for seed in seeds]
+    with ProcessPoolExecutor(processes) as ex:  # model set-up is single-threaded Python: one process per seed
+        return list(ex.map(_oracle_one, [(name, seed) for seed in seeds]))
 
 
 @pytest.mark.parametrize("name", ["linear_demo", "linear_full", "sige"])
@@ -57,7 +64,7 @@ def test_oracle_steady_state_parity_with_reference(name):
 @pytest.mark.slow
 def test_oracle_transient_trace_parity_with_reference():
     gold = T.golden("sides_trans")
-    runs = _oracle_features("sides_trans", range(1, 9))
+    runs = _oracle_features("sides_trans", range(1, 9), processes=4)
     T.assert_parity(T.welch_z(runs, gold, "tally_e_blk"), "oracle sides_trans energy trace")
     T.assert_parity(T.welch_z(runs, gold, "temp_blk"), "oracle sides_trans temperature trace")
     T.assert_parity(T.welch_z(runs, gold, "flux_blk"), "oracle sides_trans flux trace")
