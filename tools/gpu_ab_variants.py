@@ -14,10 +14,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = {
-    "b768_s2": {"PSIM_BLOCK": 768, "PSIM_SLOTS": 2, "PSIM_SLOT_BLOCKS": 1},
-    "b896_s2": {"PSIM_BLOCK": 896, "PSIM_SLOTS": 2, "PSIM_SLOT_BLOCKS": 1},
-    "b1024_s2": {"PSIM_BLOCK": 1024, "PSIM_SLOTS": 2, "PSIM_SLOT_BLOCKS": 1},
+VARIANTS = {  # examples measured in round 1; edit for the next A/B
+    "b896_q104": {"PSIM_BLOCK": 896, "PSIM_QUEUE_SLOTS": 104},
+    "b896_q96": {"PSIM_BLOCK": 896, "PSIM_QUEUE_SLOTS": 96},
 }
 
 
