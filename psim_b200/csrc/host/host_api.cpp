@@ -370,6 +370,9 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
     std::vector<psim_gpu*> gpus(G, nullptr);
     const int rc = guarded(PSIM_E_STATE, [&]() -> int {
         m.runs.clear();
+        // every call starts from the state of the model file: a steady-state run leaves its final temperatures in the
+        // sensors (Model::resetRequired, model.cpp:250-272), which a second call on the same handle must not inherit
+        m.reset_for_next_run();
         // several devices: their tallies are summed with one NCCL all-reduce per run over NVLink (integers: the result is the
         // one-device result bit for bit); without a usable NCCL the same integers are summed on the host
         std::unique_ptr<TallyExchange> exchange;
