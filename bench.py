@@ -57,6 +57,26 @@ def ncu_traffic_per_launch(per_gpu: int, launches_per_job: int, auto_windows: bo
     return None
 
 
+def issue_slot_use(per_gpu: int, kernel_ms: float, recorded_steps: int, sm_mhz, auto_windows: bool):
+    """What actually bounds the kernel: warp instructions issued per second against the issue
+    slots of the chip (148 SMs x 4 schedulers x SM clock).  Instruction counts per launch come from the committed ncu
+    captures of this workload (one long unrecorded window + one 36-step recorded window, scaled to the recorded steps of
+    a job); the time is the one measured live.  None when the captures do not describe this configuration."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        if d["phonons_per_gpu"] != per_gpu or not auto_windows or not sm_mhz:
+            return None
+        long_w, rec_w = d["captures"][0], d["captures"][1]
+        inst = long_w["warp_instructions"] + rec_w["warp_instructions"] * recorded_steps / 36.0
+        peak = 148 * 4 * float(sm_mhz) * 1e6
+        achieved = inst / (kernel_ms * 1e-3)
+        return {"achieved_warp_inst_per_s": achieved, "peak_warp_inst_per_s": peak, "frac": achieved / peak,
+                "threads_active_per_instruction": long_w["threads_active_per_instruction"],
+                "source": "warp instructions per launch from profiles/r01_ncu_summary.json (ncu), time measured live"}
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -362,6 +382,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_drift_step": ALGO_BYTES_PER_DRIFT_STEP,
                          "algorithmic_bytes_per_launch": float(np.mean(drift)) * ALGO_BYTES_PER_DRIFT_STEP / launches_per_job,
                          "avg_launch_ms": k_ms / launches_per_job, "launches_per_job": launches_per_job, "kernel_ms_per_job": k_ms,
+                         "issue_slots": issue_slot_use(per_gpu, k_ms, R, (sampler.summary() or {}).get("sm_mhz") if sampler else None,
+                                                       args.steps_per_launch == 0),
                          "note": "achieved = 64 B x drift-steps / kernel time, the accounting of SURVEY 8d (state read + written once per "
                                  "drift-step).  A launch keeps a phonon on chip for a whole window of measurement steps, so the real "
                                  "DRAM traffic (`traffic`, bytes per launch, ncu) is a small fraction of the algorithmic bytes and frac "
