@@ -50,10 +50,12 @@ def _oracle_features(name, seeds, processes=1):
         return list(ex.map(_oracle_one, [(name, seed) for seed in seeds]))
 
 
-@pytest.mark.parametrize("name", ["linear_demo", "linear_full", "sige"])
+@pytest.mark.parametrize("name", ["linear_demo", "linear_full", "sige", "linear_rough", "linear_impurity", "linear_hot_cells"])
 def test_oracle_steady_state_parity_with_reference(name):
+    """Deviational and full mode, the Si/Ge interface, fully diffuse walls, impurity scattering, cells that start away from
+    t_eq: every branch of the restatement against 16 seeds of the unmodified reference."""
     gold = T.golden(name)
-    runs = _oracle_features(name, range(1, 9))
+    runs = _oracle_features(name, range(1, 9), processes=4)
     T.assert_parity(T.welch_z(runs, gold, "tally_e"), f"oracle {name} energy tallies")
     T.assert_parity(T.welch_z(runs, gold, "tally_f"), f"oracle {name} flux tallies")
     six = T.welch_z(runs, gold, "out6")
