@@ -1,6 +1,7 @@
 """The oracle (oracle/model.py + oracle/sim.c, a CPU restatement of the reference) pinned against the golden
 fixtures produced by the UNMODIFIED reference (tests/golden/, 16 seeds per case): deterministic known answers to
 1e-12, Monte Carlo tallies to 3 sigma."""
+import multiprocessing
 from concurrent.futures import ProcessPoolExecutor
 
 import numpy as np
@@ -46,7 +47,9 @@ def _oracle_one(args):
 def _oracle_features(name, seeds, processes=1):
     if processes == 1:
         return [_oracle_one((name, seed)) for seed in seeds]
-    with ProcessPoolExecutor(processes) as ex:  # model set-up is single-threaded Python: one process per seed
+    # model set-up is single-threaded Python: one process per seed.  Spawned, not forked: the C restatement runs on OpenMP
+    # threads, and a child forked from a process that has already started an OpenMP team hangs in its first parallel region
+    with ProcessPoolExecutor(processes, mp_context=multiprocessing.get_context("spawn")) as ex:
         return list(ex.map(_oracle_one, [(name, seed) for seed in seeds]))
 
 
