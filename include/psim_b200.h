@@ -31,7 +31,8 @@ enum {
     PSIM_E_OVERFLOW = -4,   /* phonon pool capacity exceeded (never silently dropped) */
     PSIM_E_STATE = -5,      /* call order violated (e.g. run before set_sources) */
     PSIM_E_IO = -6,         /* host layer: file could not be read / written */
-    PSIM_E_MODEL = -7       /* host layer: model file rejected (same conditions the reference rejects) */
+    PSIM_E_MODEL = -7,      /* host layer: model file rejected (same conditions the reference rejects) */
+    PSIM_E_RNG = -8         /* a phonon exhausted the random-number blocks of one measurement interval (never a silent reuse) */
 };
 
 /* ---- flat model description -------------------------------------------------------------------------

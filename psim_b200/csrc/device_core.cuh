@@ -39,12 +39,11 @@ PSIM_HD float f_div(float a, float b) {  // a / b with one MUFU.RCP (1 ulp) - am
 }
 PSIM_HD float f_inf() { return __int_as_float(0x7f800000); }
 template<typename T> PSIM_HD T ldg(const T* p) { return __ldg(p); }
-PSIM_HD float4 load_cell_matrix(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const float4*>(cells + i)); }
-PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint4*>(cells + i) + 1); }
-PSIM_HD float2 load_cell_normal(const DevWall* walls, uint32_t i, uint32_t e) {
-    return __ldg(reinterpret_cast<const float2*>(walls + i) + e);
+PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint4*>(cells + i)); }
+PSIM_HD float4 load_shape_matrix(const DevShape* shapes, uint32_t i) { return __ldg(reinterpret_cast<const float4*>(shapes + i)); }
+PSIM_HD float2 load_shape_normal(const DevShape* shapes, uint32_t i, uint32_t e) {
+    return __ldg(reinterpret_cast<const float2*>(shapes[i].n) + e);
 }
-PSIM_HD float load_cell_spec(const DevWall* walls, uint32_t i) { return __ldg(&walls[i].spec); }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) {
     const float4* q = reinterpret_cast<const float4*>(sensors + i);
     union { float4 v[2]; DevSensor s; } u;
@@ -61,26 +60,36 @@ PSIM_HD float f_sqrt(float x) { return std::sqrt(x); }
 PSIM_HD float f_div(float a, float b) { return a / b; }
 PSIM_HD float f_inf() { return INFINITY; }
 template<typename T> PSIM_HD T ldg(const T* p) { return *p; }
-PSIM_HD float4 load_cell_matrix(const DevCell* cells, uint32_t i) {
-    float4 m;
-    m.x = cells[i].m00, m.y = cells[i].m01, m.z = cells[i].m10, m.w = cells[i].m11;
-    return m;
-}
 PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) {
     uint4 q;
     q.x = cells[i].link[0], q.y = cells[i].link[1], q.z = cells[i].link[2], q.w = cells[i].sensor_mat;
     return q;
 }
-PSIM_HD float2 load_cell_normal(const DevWall* walls, uint32_t i, uint32_t e) {
+PSIM_HD float4 load_shape_matrix(const DevShape* shapes, uint32_t i) {
+    float4 m;
+    m.x = shapes[i].m00, m.y = shapes[i].m01, m.z = shapes[i].m10, m.w = shapes[i].m11;
+    return m;
+}
+PSIM_HD float2 load_shape_normal(const DevShape* shapes, uint32_t i, uint32_t e) {
     float2 n;
-    n.x = walls[i].n[e][0], n.y = walls[i].n[e][1];
+    n.x = shapes[i].n[e][0], n.y = shapes[i].n[e][1];
     return n;
 }
-PSIM_HD float load_cell_spec(const DevWall* walls, uint32_t i) { return walls[i].spec; }
 PSIM_HD uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 PSIM_HD uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) { return sensors[i]; }
 #endif
+
+// geometry of a cell = its shape record (device_types.h: DevShape)
+PSIM_HD float4 load_cell_matrix(const DevParams& P, uint32_t cell) { return load_shape_matrix(P.shapes, ldg(&P.cell_shape[cell])); }
+PSIM_HD float2 load_cell_normal(const DevParams& P, uint32_t cell, uint32_t e) { return load_shape_normal(P.shapes, ldg(&P.cell_shape[cell]), e); }
+PSIM_HD float load_cell_spec(const DevParams& P, uint32_t cell) { return ldg(&P.shapes[ldg(&P.cell_shape[cell])].spec); }
+// relaxation-rate record of the sensor area a cell word names: the record of its rate class where it has one (a
+// handful of records for the whole mesh), the sensor's own otherwise
+PSIM_HD DevSensor load_rates(const DevParams& P, uint32_t cell_word) {
+    const uint32_t cls = PSIM_CELL_CLASS(cell_word);
+    return load_sensor((cls != 255u) ? P.classes + cls : P.sensors + PSIM_CELL_SENSOR(cell_word), 0u);  // one load path, the pointer is selected
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Replaces the reference's thread_local mt19937 seeded from
@@ -298,7 +307,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     if (src.kind == 0u) {
         p.cell = src.index;
         const uint4 info = load_cell_info(P.cells, p.cell);
-        const DevSensor s = load_sensor(P.sensors, PSIM_CELL_SENSOR(info.w));
+        const DevSensor s = load_rates(P, info.w);
         sample_table(P, s.base_table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
         float r1 = u_a, r2 = u_b;
         if (r1 + r2 > 1.f) {
@@ -323,7 +332,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     (void)j;
     sample_table(P, em.table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
     place_on_edge(em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
-    const float2 n = load_cell_normal(P.walls, p.cell, em.edge);
+    const float2 n = load_cell_normal(P, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
         p.packed = (p.packed & 0xFF000800u) | 1u | (PSIM_CELL_MAT(info.w) << 12);
         p.dx = 1000.f * n.x;
@@ -331,7 +340,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     } else {
         diffuse_direction(u_b, u_c, n.x, n.y, vel, p);
     }
-    p.tts = draw_scatter_time(P, load_sensor(P.sensors, PSIM_CELL_SENSOR(info.w)), p, u_d);
+    p.tts = draw_scatter_time(P, load_rates(P, info.w), p, u_d);
     return static_cast<float>((1. - frac) * P.step_time_d);
 }
 
@@ -385,7 +394,7 @@ PSIM_HD float draw_scatter_time(const DevParams& P, const DevSensor& sen, const 
 }
 
 PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, float t, uint32_t step) {
-    set_cell_matrix(f, load_cell_matrix(P.cells, p.cell));
+    set_cell_matrix(f, load_cell_matrix(P, p.cell));
     f.sensor_mat = load_cell_info(P.cells, p.cell).w;
     f.vel = phonon_velocity(P, p.packed);
     update_rates_of_motion(f, p);
@@ -463,8 +472,7 @@ PSIM_HD bool rates_differ(uint32_t cell_word_a, uint32_t cell_word_b) {
 // Fast path of a surface interaction, taken inline by the flight loop: the edge is wholly a transition into a
 // neighbour cell with the same material and rate class (by far the most frequent impact inside a mesh).
 // Everything else (walls, emitters, material interfaces, partial edges, stuck-phonon guard) goes to impact_event.
-PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) {
-    const uint4 info = load_cell_info(P.cells, p.cell);
+PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f, const uint4 info /* record of p.cell */) {
     const uint32_t link = (f.edge == 0u) ? info.x : ((f.edge == 1u) ? info.y : info.z);
     if (PSIM_LINK_KIND(link) != PSIM_LINK_TRANSITION || f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
     const uint32_t ncell = PSIM_LINK_INDEX(link);
@@ -473,11 +481,12 @@ PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) {
     place_on_edge((link >> 28) & 3u, (link & (1u << 27)) ? f.s_hit : 1.f - f.s_hit, p);
     p.cell = ncell;
     f.sensor_mat = nsm;
-    set_cell_matrix(f, load_cell_matrix(P.cells, ncell));
+    set_cell_matrix(f, load_cell_matrix(P, ncell));
     update_rates_of_motion(f, p);
     ++f.ncoll;
     return true;
 }
+PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) { return fast_transition(P, p, f, load_cell_info(P.cells, p.cell)); }
 
 PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     f.rng.left = 0;  // every event that needs random numbers starts a fresh Philox block of its (phonon, step) stream
@@ -504,7 +513,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     // Random words this surface can consume - asked for at ONE place, and only if any is needed: a transition
     // into the same sensor area none, into another area 1 (new time to scatter), a blocked material interface 2
     // (back-scatter direction), a wall 3 (specular test + diffuse direction) unless it is perfectly specular.
-    const float spec = (kind == PSIM_LINK_TRANSITION) ? 0.f : load_cell_spec(P.walls, p.cell);
+    const float spec = (kind == PSIM_LINK_TRANSITION) ? 0.f : load_cell_spec(P, p.cell);
     uint32_t ncell = 0u, nsm = 0u, need = (spec >= 1.f) ? 0u : 3u;
     bool pass = true;
     if (kind == PSIM_LINK_TRANSITION) {
@@ -524,12 +533,12 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
             p.cell = ncell;
             const bool new_sensor = rates_differ(nsm, f.sensor_mat);
             f.sensor_mat = nsm;
-            set_cell_matrix(f, load_cell_matrix(P.cells, ncell));
+            set_cell_matrix(f, load_cell_matrix(P, ncell));
             if (new_sensor) {  // the old time-to-scatter is void where the rates differ (modelSimulator.cpp:167-172,192-194)
-                p.tts = draw_scatter_time(P, load_sensor(P.sensors, PSIM_CELL_SENSOR(nsm)), p, rng_u01(f.rng));
+                p.tts = draw_scatter_time(P, load_rates(P, nsm), p, rng_u01(f.rng));
             }
         } else {  // back into the same cell, about the true inward normal
-            const float2 n = load_cell_normal(P.walls, p.cell, e);
+            const float2 n = load_cell_normal(P, p.cell, e);
             const float u1 = rng_u01(f.rng), u2 = rng_u01(f.rng);
             diffuse_direction(u1, u2, n.x, n.y, f.vel, p);
         }
@@ -538,7 +547,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
             const DevEmitter* em = P.emitters + PSIM_LINK_INDEX(link);
             if (step >= ldg(&em->k_on) && step < ldg(&em->k_off)) { return EV_DEAD; }  // absorbed
         }  // outside its window an emitting surface is an ordinary wall (surface.cpp:61-65)
-        const float2 n = load_cell_normal(P.walls, p.cell, e);
+        const float2 n = load_cell_normal(P, p.cell, e);
         boundary_reflect(f.rng, spec, n.x, n.y, f.vel, p);
     }
     update_rates_of_motion(f, p);
@@ -562,7 +571,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
 // then the rates and the time to scatter of the next one (get_scatter_info, :148-153)
 PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
-    const DevSensor sen = load_sensor(P.sensors, PSIM_CELL_SENSOR(f.sensor_mat));
+    const DevSensor sen = load_rates(P, f.sensor_mat);
     float rn, ru, ri;
     relax_rates(sen, phonon_omega(P, p.packed), PSIM_PACK_TA(p.packed), rn, ru, ri);
     // ONE Philox block per scatter: word 0 -> bin (24 bits) + position inside the bin (8 bits), word 1 -> branch

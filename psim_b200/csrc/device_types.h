@@ -46,15 +46,20 @@
 #define PSIM_ALIGN(n) alignas(n)
 #endif
 
-// What every flight segment and cell transition needs, 32 bytes per cell (two 16-byte loads); what only a reflection
-// needs lives in DevWall, so that a mesh of thousands of cells keeps twice as many cells in L1.
+// What every cell transition needs, 16 bytes per cell: what lies behind the three edges and which sensor area /
+// rate class / material the cell belongs to.  The cell's GEOMETRY (barycentric rate matrix, inward normals) and its
+// specularity live in a table of distinct SHAPES: the meshes the reference's builder makes are unions of rectangles
+// cut in two (builder_tools.py:addRectangularCell), so thousands of cells share a few dozen shapes (kinked wire:
+// 6174 cells, 26 shapes) and the records a flight touches - 16 B + a 4-byte shape index per cell - stay in L1 where
+// the 64 B per cell of the first layout did not (profiles/r01_summary.md: L1 hit rate 52 % on that mesh).  A mesh of
+// arbitrary triangles simply has as many shapes as cells.
 struct PSIM_ALIGN(16) DevCell {
-    float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [P2-P1 | P3-P1])
     uint32_t link[3];          // what lies behind each edge
     uint32_t sensor_mat;       // [31:12] sensor index, [11:4] rate class, [3:0] material index (PSIM_CELL_*)
 };
 
-struct PSIM_ALIGN(16) DevWall {
+struct PSIM_ALIGN(16) DevShape {
+    float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [P2-P1 | P3-P1])
     float n[3][2];             // unit normals of edges 0..2 pointing INTO the cell (geometry.cpp:97-100)
     float spec;                // specularity of the cell's boundary surfaces, clamped to [0,1] (cell.cpp:115-119)
     uint32_t pad;
@@ -129,16 +134,18 @@ struct DevBirth {
 
 struct DevParams {
     const DevCell* cells;
-    const DevWall* walls;      // [n_cells]
+    const uint32_t* cell_shape; // [n_cells] index into shapes
+    const DevShape* shapes;     // [n_shapes] distinct (geometry, specularity) records
     const DevSub* subs;
     const DevSensor* sensors;
+    const DevSensor* classes;   // [<= 255] one record per rate class (PSIM_CELL_CLASS): the sensors of a class are identical
     const DevMaterial* materials;
     const DevEmitter* emitters;
     const DevSource* sources;
     const float2* tables;      // [n_tables][PSIM_BINS] (cumulative probability, LA fraction)  (material.cpp:170-180)
     const uint32_t* guides;    // [n_tables][PSIM_GUIDE] search bracket for r in [k/G, (k+1)/G), G = PSIM_GUIDE: low | high << 16
     const float* velocities;   // [n_materials][2][PSIM_BINS] group velocity, LA then TA, m/s == nm/ns
-    uint32_t n_cells, n_sensors, n_materials, n_tables, n_emitters, n_sources;
+    uint32_t n_cells, n_shapes, n_sensors, n_materials, n_tables, n_emitters, n_sources;
     uint32_t num_steps;        // measurement steps M
     uint32_t first_tally_step; // reference step_adjustment_ (modelSimulator.h:24-26)
     uint32_t recorded_steps;   // M - first_tally_step

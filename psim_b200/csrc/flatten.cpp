@@ -2,7 +2,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <sstream>
+#include <unordered_map>
 
 namespace psim {
 namespace {
@@ -150,22 +152,49 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         out.emitters[e] = o;
     }
 
-    // rate classes: sensors of the same material at the same temperature have identical relaxation rates
+    // rate classes: sensors of the same material at the same temperature (and with the same tables) have identical
+    // records; the per-phonon loop reads the record of the class, so a mesh with thousands of sensor areas at a handful
+    // of temperatures touches a handful of records
     std::vector<uint32_t> sensor_class(d.num_sensors, 255u);
     {
-        std::vector<std::pair<uint32_t, double>> classes;
+        struct Key {
+            uint32_t material, base_table, scatter_table;
+            double temperature;
+            bool operator==(const Key& o) const {
+                return material == o.material && base_table == o.base_table && scatter_table == o.scatter_table && temperature == o.temperature;
+            }
+        };
+        std::vector<Key> classes;
         for (uint32_t s = 0; s < d.num_sensors; ++s) {
-            const std::pair<uint32_t, double> key{ d.sensors[s].material, d.sensors[s].temperature };
+            const Key key{ d.sensors[s].material, d.sensors[s].base_table, d.sensors[s].scatter_table, d.sensors[s].temperature };
             size_t k = 0;
-            while (k < classes.size() && classes[k] != key) { ++k; }
-            if (k == classes.size() && classes.size() < 255) { classes.push_back(key); }
+            while (k < classes.size() && !(classes[k] == key)) { ++k; }
+            if (k == classes.size() && classes.size() < 255) {
+                classes.push_back(key);
+                out.classes.push_back(out.sensors[s]);
+            }
             sensor_class[s] = k < 255 ? static_cast<uint32_t>(k) : 255u;
         }
     }
 
     // cells
     out.cells.resize(d.num_cells);
-    out.walls.resize(d.num_cells);
+    out.cell_shape.resize(d.num_cells);
+    // distinct shapes, found by exact comparison of the fp32 records (hash of the bit patterns -> candidates)
+    std::unordered_multimap<uint64_t, uint32_t> shape_index;
+    auto shape_id = [&](const DevShape& sh) -> uint32_t {
+        uint32_t w[sizeof(DevShape) / 4];
+        std::memcpy(w, &sh, sizeof(sh));
+        uint64_t hsh = 0xcbf29ce484222325ull;
+        for (uint32_t x : w) { hsh = (hsh ^ x) * 0x100000001b3ull; }
+        const auto range = shape_index.equal_range(hsh);
+        for (auto it = range.first; it != range.second; ++it) {
+            if (std::memcmp(&out.shapes[it->second], &sh, sizeof(sh)) == 0) { return it->second; }
+        }
+        out.shapes.push_back(sh);
+        shape_index.emplace(hsh, static_cast<uint32_t>(out.shapes.size() - 1));
+        return static_cast<uint32_t>(out.shapes.size() - 1);
+    };
     for (uint32_t c = 0; c < d.num_cells; ++c) {
         const psim_cell& in = d.cells[c];
         if (in.sensor >= d.num_sensors) {
@@ -188,11 +217,11 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
             oy = static_cast<float>(y / n);
         };
         DevCell o{};
-        DevWall ow{};
-        o.m00 = static_cast<float>(m00);
-        o.m01 = static_cast<float>(m01);
-        o.m10 = static_cast<float>(m10);
-        o.m11 = static_cast<float>(m11);
+        DevShape ow{};
+        ow.m00 = static_cast<float>(m00);
+        ow.m01 = static_cast<float>(m01);
+        ow.m10 = static_cast<float>(m10);
+        ow.m11 = static_cast<float>(m11);
         unit(m10, m11, ow.n[0][0], ow.n[0][1]);                   // edge 0 is b2 = 0: inward = grad b2
         unit(-(m00 + m10), -(m01 + m11), ow.n[1][0], ow.n[1][1]); // edge 1 is b1 + b2 = 1
         unit(m00, m01, ow.n[2][0], ow.n[2][1]);                   // edge 2 is b1 = 0
@@ -252,13 +281,14 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
             }
         }
         out.cells[c] = o;
-        out.walls[c] = ow;
+        out.cell_shape[c] = shape_id(ow);
     }
     if (out.subs.empty()) { out.subs.push_back(DevSub{}); }
     if (out.emitters.empty()) { out.emitters.push_back(DevEmitter{}); }
 
     DevParams& P = out.scalars;
     P.n_cells = d.num_cells;
+    P.n_shapes = static_cast<uint32_t>(out.shapes.size());
     P.n_sensors = d.num_sensors;
     P.n_materials = d.num_materials;
     P.n_tables = d.num_tables;

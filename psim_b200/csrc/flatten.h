@@ -13,7 +13,9 @@ namespace psim {
 
 struct HostImage {
     std::vector<DevCell> cells;
-    std::vector<DevWall> walls;      // [cells]
+    std::vector<uint32_t> cell_shape; // [cells] index into shapes
+    std::vector<DevShape> shapes;     // distinct (geometry, specularity) records
+    std::vector<DevSensor> classes;   // one record per rate class (at most 255)
     std::vector<DevSub> subs;
     std::vector<DevSensor> sensors;
     std::vector<DevMaterial> materials;

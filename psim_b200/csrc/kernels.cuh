@@ -58,7 +58,8 @@ struct LaunchArgs {
     int32_t* tally_e;
     long long* tally_f;
     uint32_t tally_shared;
-    unsigned long long* stats;       // [0] drift steps [1] flight segments [2] absorbed [3] overflow
+    long long* tally_acc;            // difference-form accumulator of the many-sensor models: int64 (e, fx, fy, -)[R][S], one 32-byte sector per entry
+    unsigned long long* stats;       // [0] drift steps [1] flight segments [2] absorbed [3] pool overflow [4] Philox block budget exceeded
     unsigned long long* alive_hist;  // [launch]: pool population after this launch
     uint32_t launch_index;
 };
@@ -155,17 +156,18 @@ __device__ __forceinline__ void tally_range(const LaunchArgs& a, int32_t* acc_e,
         stage_add_wide(q, e, fx, fy);
         if (l1 < a.step_end - a.step_begin) { stage_add_wide(q + 7u * (l1 - l0) * S, -e, -fx, -fy); }
     } else if (a.tally_shared == 3u) {
+        // (the lane-bound and lock-step kernels; the work-queue kernel posts these warp-cooperatively, tally_post_global)
         const uint32_t S = a.P.n_sensors;
         const uint32_t r0 = k0 + 1u - a.P.first_tally_step, r1 = k1 + 1u - a.P.first_tally_step;
-        const size_t i0 = static_cast<size_t>(r0) * S + sensor;
-        atomicAdd(&a.tally_e[i0], e);
-        atomic_add_i64(&a.tally_f[2 * i0], fx);
-        atomic_add_i64(&a.tally_f[2 * i0 + 1], fy);
+        long long* q0 = a.tally_acc + 4u * (static_cast<size_t>(r0) * S + sensor);
+        atomic_add_i64(q0, e);
+        atomic_add_i64(q0 + 1, fx);
+        atomic_add_i64(q0 + 2, fy);
         if (r1 < a.P.recorded_steps) {
-            const size_t i1 = static_cast<size_t>(r1) * S + sensor;
-            atomicAdd(&a.tally_e[i1], -e);
-            atomic_add_i64(&a.tally_f[2 * i1], -static_cast<long long>(fx));
-            atomic_add_i64(&a.tally_f[2 * i1 + 1], -static_cast<long long>(fy));
+            long long* q1 = a.tally_acc + 4u * (static_cast<size_t>(r1) * S + sensor);
+            atomic_add_i64(q1, -static_cast<long long>(e));
+            atomic_add_i64(q1 + 1, -static_cast<long long>(fx));
+            atomic_add_i64(q1 + 2, -static_cast<long long>(fy));
         }
     } else {
         for (uint32_t ks = k0; ks < k1; ++ks) { tally_add(a, acc_e, acc_f, ks - a.step_begin, sensor, e, fx, fy); }
@@ -273,18 +275,19 @@ __device__ __forceinline__ float birth_phonon(const LaunchArgs& a, uint64_t item
 }
 
 __device__ __forceinline__ void warp_stats(const LaunchArgs& a, uint32_t lane, unsigned long long steps, unsigned long long events,
-                                           unsigned long long absorbed, bool overflow, uint32_t n_out) {
+                                           unsigned long long absorbed, bool overflow, bool rng_over, uint32_t n_out) {
     for (int o = 16; o > 0; o >>= 1) {
         steps += __shfl_xor_sync(0xFFFFFFFFu, steps, o);
         events += __shfl_xor_sync(0xFFFFFFFFu, events, o);
         absorbed += __shfl_xor_sync(0xFFFFFFFFu, absorbed, o);
     }
-    const bool any_overflow = __any_sync(0xFFFFFFFFu, overflow);
+    const bool any_overflow = __any_sync(0xFFFFFFFFu, overflow), any_rng = __any_sync(0xFFFFFFFFu, rng_over);
     if (lane == 0) {
         if (steps) { atomicAdd(&a.stats[0], steps); }
         if (events) { atomicAdd(&a.stats[1], events); }
         if (absorbed) { atomicAdd(&a.stats[2], absorbed); }
         if (any_overflow) { atomicAdd(&a.stats[3], 1ull); }
+        if (any_rng) { atomicAdd(&a.stats[4], 1ull); }
         if (n_out) { atomicAdd(&a.alive_hist[a.launch_index], static_cast<unsigned long long>(n_out)); }
     }
 }
@@ -303,12 +306,16 @@ __device__ __forceinline__ void warp_stats(const LaunchArgs& a, uint32_t lane, u
 // ---------------------------------------------------------------------------------------------------------------
 enum : int { SF_B1 = 0, SF_B2, SF_DX, SF_DY, SF_TTS, SF_PACKED, SF_CELL, SF_ID, SF_T, SF_R1, SF_R2, SF_MISC, SF_COUNT };
 // SF_MISC: [9:0] measurement step relative to the launch, [16:10] impacts since the last scatter, [18:17] edge hit,
-//          [28:19] next Philox block of this (phonon, step) stream
+//          [31:19] next Philox block of this (phonon, step) stream.  13 bits: a phonon may consume 8191 blocks (scatters,
+//          diffuse wall hits, redraws) inside ONE measurement interval; a kernel that sees more raises the run's
+//          `rng budget` error (psim_gpu_synchronize: PSIM_E_RNG) instead of reusing a block - the lock-step kernel, which
+//          keeps the counter in a register, has no such limit and is what such a model must be run with.
 #define PSIM_MISC_STEP(m) ((m)&1023u)
 #define PSIM_MISC_NCOLL(m) (((m) >> 10) & 127u)
 #define PSIM_MISC_EDGE(m) (((m) >> 17) & 3u)
-#define PSIM_MISC_BLOCK(m) (((m) >> 19) & 1023u)
-#define PSIM_MISC_PACK(step, ncoll, edge, block) ((step) | (min((ncoll), 127u) << 10) | ((edge) << 17) | (min((block), 1023u) << 19))
+#define PSIM_MISC_BLOCK(m) ((m) >> 19)
+#define PSIM_MISC_BLOCK_MAX 8191u
+#define PSIM_MISC_PACK(step, ncoll, edge, block) ((step) | (min((ncoll), 127u) << 10) | ((edge) << 17) | (min((block), PSIM_MISC_BLOCK_MAX) << 19))
 
 template<int K>
 __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const __grid_constant__ LaunchArgs a) {
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
 
     uint32_t next = 0, n_out = 0;
     uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
-    bool overflow = false;
+    bool overflow = false, rng_over = false;
     uint32_t m_free = (1u << K) - 1u, m_fly = 0, m_wall = 0, m_sct = 0, m_fin = 0;  // which of my slots want what
 
     for (;;) {
@@ -362,12 +369,13 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 p.cell = slot_u(SF_CELL, k);
                 p.id_lo = slot_u(SF_ID, k);
                 uint32_t misc = slot_u(SF_MISC, k);
-                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
                 psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
                 misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
                 slot_f(SF_DX, k) = p.dx;
                 slot_f(SF_DY, k) = p.dy;
@@ -403,10 +411,11 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 f.r1 = slot_f(SF_R1, k);
                 f.r2 = slot_f(SF_R2, k);
                 f.t = 0.f;
-                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
                 const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
                 m_wall &= ~(1u << k);
                 if (ev == psim::EV_DEAD) {
                     ++n_steps;
@@ -545,7 +554,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
     }
     n_out = min(n_out, a.seg_cap);
     if (lane == 0) { a.cnt_out[w] = n_out; }
-    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
+    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, rng_over, n_out);
     tally_flush(a, acc_e, acc_f);
 }
 
@@ -567,14 +576,52 @@ __host__ __device__ constexpr uint32_t ring_capacity(int slots) {
     while (c < static_cast<uint32_t>(slots)) { c <<= 1; }
     return c;
 }
-#ifndef PSIM_PREFETCH_DIST
-#define PSIM_PREFETCH_DIST 0
-#endif
 #ifndef PSIM_FLY_FRONT
 #define PSIM_FLY_FRONT 1
 #endif
 
-template<int NS>
+// Slot storage of the work-queue kernel: three 16-byte groups per slot, [group][slot], so that a pass moves a slot with two
+// or three LDS.128 / STS.128 (the first layout, [field][slot] words, took 7-12 scalar accesses per slot and pass: 13 % of
+// the warp instructions of the bench job, profiles/r01_summary.md).
+//   SG_POS   (b1, b2, r1, r2)       position in the cell frame and its rate of change
+//   SG_TIME  (tts, t, misc, cell)   time to the next scatter, time left in the interval, SF_MISC word, current cell
+//   SG_VEL   (dx, dy, packed, id)   in-plane velocity, packed word, low id word
+enum : int { SG_POS = 0, SG_TIME, SG_VEL, SG_COUNT };
+static_assert(SG_COUNT * 4 == SF_COUNT, "both layouts hold the same twelve words per slot");
+// TALLY (what a launch does with the measurement events its window records)
+enum : int { TALLY_NONE = 0,     // the window ends before the first recorded step: no tally code at all
+             TALLY_STAGED = 1,   // per-CTA staging in shared memory (LaunchArgs::tally_shared 1 / 2 / 4) or plain global adds (0)
+             TALLY_GLOBAL = 2 }; // difference rows in global memory (tally_shared 3), posted warp-cooperatively: tally_post_global
+constexpr uint32_t kPostScratchBytes = 64u * 16u;  // per warp: up to two posts per lane
+
+// Many-sensor models (no staging): a flight segment posts +v into the entry of the first recorded step it crossed and -v
+// behind the last (difference form, tally_range).  One entry = one 32-byte sector of `a.tally_acc`: int64 (e, fx, fy, -).
+// Posted lane by lane that is three REDs to three different words of one sector from the SAME lane, which the L2 sees as
+// three sector operations (ncu, round 1: 26 sectors per RED instruction, 38 % of the L2 RED peak at 33 % issue activity).
+// Here the warp first compacts its posts into shared memory, then lane v handles component v % 3 of post v / 3: the three
+// words of an entry are touched by three neighbouring lanes of ONE RED instruction and reach the L2 as one sector.
+__device__ __forceinline__ void tally_post_global(const LaunchArgs& a, uint4* scratch, uint32_t lane, uint32_t lt_mask, bool has,
+                                                  uint32_t k0, uint32_t k1, uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
+    const uint32_t S = a.P.n_sensors, F = a.P.first_tally_step;
+    const uint32_t r0 = k0 + 1u - F, r1 = k1 + 1u - F;
+    const bool has_end = has && r1 < a.P.recorded_steps;
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, has), m1 = __ballot_sync(0xFFFFFFFFu, has_end);
+    if (m0 == 0u) { return; }  // warp-uniform
+    const uint32_t n0 = __popc(m0), n = n0 + __popc(m1);
+    if (has) { scratch[__popc(m0 & lt_mask)] = make_uint4(r0 * S + sensor, static_cast<uint32_t>(e), static_cast<uint32_t>(fx), static_cast<uint32_t>(fy)); }
+    if (has_end) { scratch[n0 + __popc(m1 & lt_mask)] = make_uint4(r1 * S + sensor, static_cast<uint32_t>(-e), static_cast<uint32_t>(-fx), static_cast<uint32_t>(-fy)); }
+    __syncwarp();
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(scratch);
+    for (uint32_t v = lane; v < 3u * n; v += 32u) {
+        const uint32_t post = v / 3u, c = v - 3u * post;
+        const uint32_t entry = words[4u * post];
+        const long long val = static_cast<long long>(static_cast<int32_t>(words[4u * post + 1u + c]));
+        atomic_add_i64(a.tally_acc + 4u * static_cast<size_t>(entry) + c, val);
+    }
+    __syncwarp();
+}
+
+template<int NS, int TALLY>
 __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const __grid_constant__ LaunchArgs a) {
     static_assert(NS <= 256 && NS >= 32, "slot numbers are bytes");
     constexpr uint32_t QC = ring_capacity(NS);  // the queues are power-of-two rings that can hold every slot
@@ -583,15 +630,15 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     const uint32_t nst = a.step_end - a.step_begin;
     int32_t* acc_e = reinterpret_cast<int32_t*>(smem_raw);
     long long* acc_f = reinterpret_cast<long long*>(smem_raw + tally_smem_offset_f(nst, P.n_sensors));
-    tally_init(a, acc_e, acc_f);
-    const uint32_t lane = threadIdx.x & 31u;
+    if (TALLY == TALLY_STAGED) { tally_init(a, acc_e, acc_f); }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t tally_bytes = tally_staged(a) ? tally_stage_bytes(a.tally_shared, nst, P.n_sensors) : 0;
+    const size_t tally_bytes = (TALLY == TALLY_STAGED && tally_staged(a)) ? tally_stage_bytes(a.tally_shared, nst, P.n_sensors) : 0;
     unsigned char* base = smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127));
-    uint32_t* sw = reinterpret_cast<uint32_t*>(base) + (threadIdx.x >> 5) * (SF_COUNT * NS);
-    unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SF_COUNT * NS * 4 + (threadIdx.x >> 5) * (Q_COUNT * QC);
-    auto slot_u = [&](int field, uint32_t k) -> uint32_t& { return sw[field * NS + k]; };
-    auto slot_f = [&](int field, uint32_t k) -> float& { return reinterpret_cast<float*>(sw)[field * NS + k]; };
+    float4* sv = reinterpret_cast<float4*>(base) + warp * (SG_COUNT * NS);
+    unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SG_COUNT * NS * 16 + warp * (Q_COUNT * QC);
+    uint4* post = reinterpret_cast<uint4*>(base + static_cast<size_t>(kWarpsPerBlock) * (SG_COUNT * NS * 16 + Q_COUNT * QC) + warp * kPostScratchBytes);
+    auto grp = [&](int g, uint32_t k) -> float4& { return sv[g * NS + k]; };
     struct Queue {
         uint32_t head, count;
     };
@@ -611,7 +658,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     };
     for (uint32_t i = lane; i < NS; i += 32u) { qb[Q_FREE * QC + i] = static_cast<unsigned char>(i); }
 
-    const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t w = blockIdx.x * kWarpsPerBlock + warp;
     const uint32_t W = a.n_warps;
     const size_t seg = static_cast<size_t>(w) * a.seg_cap;
     const uint32_t n_in = a.cnt_in[w];
@@ -622,7 +669,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
 
     uint32_t next = 0, n_out = 0;
     uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
-    bool overflow = false;
+    bool overflow = false, rng_over = false;
 
     for (;;) {
         __syncwarp();  // slot words and queue entries written by other lanes in the previous pass
@@ -636,28 +683,26 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             // ---- intrinsic scatter
             const uint32_t k = pop(q_sct, Q_SCT, c_sct, act);
             if (act) {
+                const float4 g1 = grp(SG_TIME, k), g2 = grp(SG_VEL, k);
                 psim::Phonon p;
                 psim::Flight f;
-                p.dx = slot_f(SF_DX, k);
-                p.dy = slot_f(SF_DY, k);
-                p.packed = slot_u(SF_PACKED, k);
-                p.cell = slot_u(SF_CELL, k);
-                p.id_lo = slot_u(SF_ID, k);
-                uint32_t misc = slot_u(SF_MISC, k);
-                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                p.dx = g2.x;
+                p.dy = g2.y;
+                p.packed = __float_as_uint(g2.z);
+                p.id_lo = __float_as_uint(g2.w);
+                p.cell = __float_as_uint(g1.w);
+                uint32_t misc = __float_as_uint(g1.z);
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
                 psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
                 misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
-                slot_f(SF_DX, k) = p.dx;
-                slot_f(SF_DY, k) = p.dy;
-                slot_u(SF_PACKED, k) = p.packed;
-                slot_f(SF_TTS, k) = p.tts;
-                slot_f(SF_R1, k) = f.r1;
-                slot_f(SF_R2, k) = f.r2;
-                slot_u(SF_MISC, k) = misc;
+                grp(SG_VEL, k) = make_float4(p.dx, p.dy, __uint_as_float(p.packed), g2.w);
+                grp(SG_TIME, k) = make_float4(p.tts, g1.y, __uint_as_float(misc), g1.w);
+                *reinterpret_cast<float2*>(&grp(SG_POS, k).z) = make_float2(f.r1, f.r2);
             }
             push(q_fly, Q_FLY, act, k);
         } else if (c_wall == best) {
@@ -666,44 +711,40 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             const uint32_t k = pop(q_wall, Q_WALL, c_wall, act);
             bool dead = false;
             if (act) {
+                const float4 g0 = grp(SG_POS, k), g1 = grp(SG_TIME, k), g2 = grp(SG_VEL, k);
                 psim::Phonon p;
                 psim::Flight f;
-                p.b1 = slot_f(SF_B1, k);
-                p.b2 = slot_f(SF_B2, k);
-                p.dx = slot_f(SF_DX, k);
-                p.dy = slot_f(SF_DY, k);
-                p.tts = slot_f(SF_TTS, k);
-                p.packed = slot_u(SF_PACKED, k);
-                p.cell = slot_u(SF_CELL, k);
-                p.id_lo = slot_u(SF_ID, k);
-                uint32_t misc = slot_u(SF_MISC, k);
+                p.b1 = g0.x;
+                p.b2 = g0.y;
+                f.r1 = g0.z;
+                f.r2 = g0.w;
+                p.tts = g1.x;
+                uint32_t misc = __float_as_uint(g1.z);
+                p.cell = __float_as_uint(g1.w);
+                p.dx = g2.x;
+                p.dy = g2.y;
+                p.packed = __float_as_uint(g2.z);
+                p.id_lo = __float_as_uint(g2.w);
                 f.edge = PSIM_MISC_EDGE(misc);
                 f.s_hit = (f.edge == 0u) ? p.b1 : ((f.edge == 1u) ? p.b2 : 1.f - p.b2);
                 f.ncoll = PSIM_MISC_NCOLL(misc);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
-                f.r1 = slot_f(SF_R1, k);
-                f.r2 = slot_f(SF_R2, k);
                 f.t = 0.f;
-                psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+                psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
                 const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
+                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
                 if (ev == psim::EV_DEAD) {
                     ++n_steps;
                     ++n_absorbed;
                     dead = true;
                 } else {
                     misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), f.ncoll, PSIM_MISC_EDGE(misc), f.rng.block);
-                    slot_f(SF_B1, k) = p.b1;
-                    slot_f(SF_B2, k) = p.b2;
-                    slot_f(SF_DX, k) = p.dx;
-                    slot_f(SF_DY, k) = p.dy;
-                    slot_f(SF_TTS, k) = p.tts;
-                    slot_u(SF_CELL, k) = p.cell;
-                    slot_f(SF_R1, k) = f.r1;
-                    slot_f(SF_R2, k) = f.r2;
-                    slot_u(SF_MISC, k) = misc;
+                    grp(SG_POS, k) = make_float4(p.b1, p.b2, f.r1, f.r2);
+                    grp(SG_TIME, k) = make_float4(p.tts, g1.y, __uint_as_float(misc), __uint_as_float(p.cell));
+                    *reinterpret_cast<float2*>(&grp(SG_VEL, k)) = make_float2(p.dx, p.dy);
                 }
             }
             push(q_fly, Q_FLY, act && !dead, k);
@@ -714,8 +755,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             if (act) {
                 const uint32_t slot = n_out + lane;
                 if (slot < a.seg_cap) {
-                    a.out_a[seg + slot] = make_float4(slot_f(SF_B1, k), slot_f(SF_B2, k), slot_f(SF_DX, k), slot_f(SF_DY, k));
-                    a.out_b[seg + slot] = make_uint4(slot_u(SF_TTS, k), slot_u(SF_PACKED, k), slot_u(SF_CELL, k), slot_u(SF_ID, k));
+                    const float4 g0 = grp(SG_POS, k), g1 = grp(SG_TIME, k), g2 = grp(SG_VEL, k);
+                    a.out_a[seg + slot] = make_float4(g0.x, g0.y, g2.x, g2.y);
+                    a.out_b[seg + slot] = make_uint4(__float_as_uint(g1.x), __float_as_uint(g2.z), __float_as_uint(g1.w), __float_as_uint(g2.w));
                 } else {
                     overflow = true;
                 }
@@ -726,12 +768,6 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots
             const uint32_t k = pop(q_free, Q_FREE, c_acq, act);
             bool got = false;
-#if PSIM_PREFETCH_DIST > 0
-            if (next + PSIM_PREFETCH_DIST + lane < n_in) {  // the records this warp fetches a few passes from now
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_a + seg + next + PSIM_PREFETCH_DIST + lane));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_b + seg + next + PSIM_PREFETCH_DIST + lane));
-            }
-#endif
             if (act) {
                 const uint32_t idx = next + lane;
                 psim::Phonon p;
@@ -751,77 +787,84 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 if (got) {
                     psim::Flight f;
                     psim::interval_begin(P, p, f, t_begin, s);
-                    slot_f(SF_B1, k) = p.b1;
-                    slot_f(SF_B2, k) = p.b2;
-                    slot_f(SF_DX, k) = p.dx;
-                    slot_f(SF_DY, k) = p.dy;
-                    slot_f(SF_TTS, k) = p.tts;
-                    slot_u(SF_PACKED, k) = p.packed;
-                    slot_u(SF_CELL, k) = p.cell;
-                    slot_u(SF_ID, k) = p.id_lo;
-                    slot_f(SF_T, k) = f.t;
-                    slot_f(SF_R1, k) = f.r1;
-                    slot_f(SF_R2, k) = f.r2;
-                    slot_u(SF_MISC, k) = s - a.step_begin;
+                    grp(SG_POS, k) = make_float4(p.b1, p.b2, f.r1, f.r2);
+                    grp(SG_TIME, k) = make_float4(p.tts, f.t, __uint_as_float(s - a.step_begin), __uint_as_float(p.cell));
+                    grp(SG_VEL, k) = make_float4(p.dx, p.dy, __uint_as_float(p.packed), __uint_as_float(p.id_lo));
                 }
             }
             next += c_acq;
             push(q_fly, Q_FLY, got, k);
             push(q_free, Q_FREE, act && !got, k);
         } else {
-            // ---- one free-flight segment: to the next edge / scatter / end of the launch window, tallying the
-            //      measurement events it crosses on the way
+            // ---- one free-flight segment: to the next edge / scatter / end of the launch window; the recorded measurement
+            //      events it crosses on the way are tallied after the segment, when the warp has converged again
             const uint32_t k = pop(q_fly, Q_FLY, c_fly, act);
             int dest = -1;
+            uint32_t tk0 = 0, tk1 = 0, sensor = 0;  // recorded steps [tk0, tk1) that ended during this segment
+            float vx = 0.f, vy = 0.f;
+            uint32_t packed = 0;
             if (act) {
+                const float4 g0 = grp(SG_POS, k), g1 = grp(SG_TIME, k);
                 psim::Phonon p;
                 psim::Flight f;
-                p.b1 = slot_f(SF_B1, k);
-                p.b2 = slot_f(SF_B2, k);
-                p.tts = slot_f(SF_TTS, k);
-                f.t = slot_f(SF_T, k);
-                f.r1 = slot_f(SF_R1, k);
-                f.r2 = slot_f(SF_R2, k);
-                uint32_t misc = slot_u(SF_MISC, k);
+                p.b1 = g0.x;
+                p.b2 = g0.y;
+                f.r1 = g0.z;
+                f.r2 = g0.w;
+                p.tts = g1.x;
+                f.t = g1.y;
+                uint32_t misc = __float_as_uint(g1.z);
+                p.cell = __float_as_uint(g1.w);
                 f.edge = 0u;
                 f.ncoll = PSIM_MISC_NCOLL(misc);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 const uint32_t s0 = a.step_begin + PSIM_MISC_STEP(misc);
                 uint32_t s = s0;
                 const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
-                    const int32_t sg = PSIM_PACK_NEG(slot_u(SF_PACKED, k)) ? -1 : 1;
-                    const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
-                    const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k)) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k)) * sg;
-                    tally_range(a, acc_e, acc_f, k0, k1, sensor, sg, fx, fy);
+                    if (TALLY != TALLY_NONE) {
+                        tk0 = k0;
+                        tk1 = k1;
+                    }
                 });
                 ++n_events;
                 // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
                 // block): only the step survives in the packed word; otherwise only the edge changes
                 misc = ((s != s0) ? (s - a.step_begin) : (misc & ~(3u << 17))) | (f.edge << 17);
-                if (ev == psim::EV_IMPACT) {
-                    // the frequent case - a whole-edge transition into a cell with the same material and rates - is done
-                    // at once, and the slot keeps flying; anything else waits for the general surface-interaction kind
-                    p.dx = slot_f(SF_DX, k);
-                    p.dy = slot_f(SF_DY, k);
-                    p.cell = slot_u(SF_CELL, k);
-                    f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
-                    if (psim::fast_transition(P, p, f)) {
-                        slot_u(SF_CELL, k) = p.cell;
-                        slot_f(SF_R1, k) = f.r1;
-                        slot_f(SF_R2, k) = f.r2;
-                        misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
-                        dest = Q_FLY;
-                    } else {
-                        dest = Q_WALL;
+                const bool hit = ev == psim::EV_IMPACT;
+                if (hit || tk1 > tk0) {
+                    const uint4 info = psim::load_cell_info(P.cells, p.cell);  // the cell the segment was flown in
+                    const float4 g2 = grp(SG_VEL, k);
+                    sensor = PSIM_CELL_SENSOR(info.w);
+                    vx = g2.x;
+                    vy = g2.y;
+                    packed = __float_as_uint(g2.z);
+                    if (hit) {
+                        // the frequent case - a whole-edge transition into a cell with the same material and rates - is done
+                        // at once, and the slot keeps flying; anything else waits for the general surface-interaction kind
+                        p.dx = vx;
+                        p.dy = vy;
+                        f.sensor_mat = info.w;
+                        if (psim::fast_transition(P, p, f, info)) {
+                            misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
+                            dest = Q_FLY;
+                        } else {
+                            dest = Q_WALL;
+                        }
                     }
-                } else {
-                    dest = (ev == psim::EV_SCATTER) ? Q_SCT : Q_FIN;
                 }
-                slot_f(SF_B1, k) = p.b1;
-                slot_f(SF_B2, k) = p.b2;
-                slot_f(SF_TTS, k) = p.tts;
-                slot_f(SF_T, k) = f.t;
-                slot_u(SF_MISC, k) = misc;
+                if (!hit) { dest = (ev == psim::EV_SCATTER) ? Q_SCT : Q_FIN; }
+                grp(SG_POS, k) = make_float4(p.b1, p.b2, f.r1, f.r2);
+                grp(SG_TIME, k) = make_float4(p.tts, f.t, __uint_as_float(misc), __uint_as_float(p.cell));
+            }
+            if (TALLY != TALLY_NONE) {
+                const bool has = tk1 > tk0;
+                const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
+                const int32_t fx = psim::flux_fixed(vx) * sg, fy = psim::flux_fixed(vy) * sg;
+                if (TALLY == TALLY_GLOBAL) {
+                    tally_post_global(a, post, lane, lt_mask, has, tk0, tk1, sensor, sg, fx, fy);
+                } else if (has) {
+                    tally_range(a, acc_e, acc_f, tk0, tk1, sensor, sg, fx, fy);
+                }
             }
             // four-way push with one address computation (selects on warp-uniform values, no branches)
             const bool d_fly = dest == Q_FLY, d_sct = dest == Q_SCT, d_wall = dest == Q_WALL, d_fin = dest == Q_FIN;
@@ -848,8 +891,8 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     }
     n_out = min(n_out, a.seg_cap);
     if (lane == 0) { a.cnt_out[w] = n_out; }
-    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
-    tally_flush(a, acc_e, acc_f);
+    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, rng_over, n_out);
+    if (TALLY == TALLY_STAGED) { tally_flush(a, acc_e, acc_f); }
 }
 
 // First version: tiles of 32 phonons in lock step (every lane waits for the slowest phonon of its tile).
@@ -912,31 +955,31 @@ __global__ void __launch_bounds__(kBlock, (kBlock <= 256 ? 2 : 1)) drift_kernel_
     }
     n_out = min(n_out, a.seg_cap);
     if (lane == 0) { a.cnt_out[w] = n_out; }
-    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, n_out);
+    warp_stats(a, lane, n_steps, n_events, n_absorbed, overflow, false, n_out);
     tally_flush(a, acc_e, acc_f);
 }
 
-// Rows [row_begin, row_end) of the difference-form tallies (tally_range, mode 3) become running sums; `carry` holds the
-// sums at row_begin - 1 and is private to the library, so callers may all-reduce finished rows in place.
-__global__ void finalize_rows_kernel(int32_t* tally_e, long long* tally_f, int32_t* carry_e, long long* carry_f, uint32_t S,
-                                     uint32_t row_begin, uint32_t row_end) {
+// Rows [row_begin, row_end) of the difference-form accumulator (tally_shared == 3) become running sums in the caller-visible
+// tally arrays; `carry` holds the sums at row_begin - 1 and is private to the library, so callers may all-reduce finished
+// rows in place.
+__global__ void finalize_rows_kernel(const long long* acc, int32_t* tally_e, long long* tally_f, int32_t* carry_e, long long* carry_f,
+                                     uint32_t S, uint32_t row_begin, uint32_t row_end) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // sensor * 3 + component
     if (i >= 3u * S) { return; }
     const uint32_t s = i / 3u, c = i % 3u;
+    long long v = (c == 0u) ? static_cast<long long>(carry_e[s]) : carry_f[2u * s + c - 1u];
+    for (uint32_t r = row_begin; r < row_end; ++r) {
+        const size_t k = static_cast<size_t>(r) * S + s;
+        v += acc[4u * k + c];
+        if (c == 0u) {
+            tally_e[k] = static_cast<int32_t>(v);
+        } else {
+            tally_f[2u * k + c - 1u] = v;
+        }
+    }
     if (c == 0u) {
-        int32_t v = carry_e[s];
-        for (uint32_t r = row_begin; r < row_end; ++r) {
-            v += tally_e[static_cast<size_t>(r) * S + s];
-            tally_e[static_cast<size_t>(r) * S + s] = v;
-        }
-        carry_e[s] = v;
+        carry_e[s] = static_cast<int32_t>(v);
     } else {
-        long long v = carry_f[2u * s + c - 1u];
-        for (uint32_t r = row_begin; r < row_end; ++r) {
-            const size_t k = 2 * (static_cast<size_t>(r) * S + s) + c - 1u;
-            v += tally_f[k];
-            tally_f[k] = v;
-        }
         carry_f[2u * s + c - 1u] = v;
     }
 }
@@ -978,7 +1021,7 @@ __global__ void probe_flight_kernel(DevParams P, const uint32_t* cell, const flo
     p.cell = cell[i];
     p.packed = 0u;
     p.id_lo = 0u;
-    psim::set_cell_matrix(f, psim::load_cell_matrix(P.cells, p.cell));
+    psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
     f.vel = speed;
     psim::update_rates_of_motion(f, p);
     f.t = 1.0e30f;  // no measurement boundary in the way
@@ -993,7 +1036,7 @@ __global__ void probe_flight_kernel(DevParams P, const uint32_t* cell, const flo
     const float t_hit = (fabsf(r1_rate) > fabsf(r2_rate)) ? (p.b1 - b1_start) / r1_rate : (p.b2 - b2_start) / r2_rate;
     float dx = p.dx, dy = p.dy;
     if (ev == psim::EV_IMPACT) {
-        const float2 nrm = psim::load_cell_normal(P.walls, p.cell, f.edge);
+        const float2 nrm = psim::load_cell_normal(P, p.cell, f.edge);
         const float dn = dx * nrm.x + dy * nrm.y;
         dx -= 2.f * dn * nrm.x;
         dy -= 2.f * dn * nrm.y;

@@ -39,7 +39,9 @@ struct psim_gpu {
     psim::BirthPlan plan;
     DevParams P{};  // device pointers
     void* d_cells = nullptr;
-    void* d_walls = nullptr;
+    void* d_cell_shape = nullptr;
+    void* d_shapes = nullptr;
+    void* d_classes = nullptr;
     void* d_subs = nullptr;
     void* d_sensors = nullptr;
     void* d_materials = nullptr;
@@ -57,6 +59,7 @@ struct psim_gpu {
     uint32_t seg_cap = 0, n_warps = 0;
     int32_t* tally_e = nullptr;
     long long* tally_f = nullptr;
+    long long* tally_acc = nullptr;  // [R][S][4] difference-form accumulator of runs that tally straight to global memory (allocated on first use)
     int32_t* carry_e = nullptr;      // [S]   running sums behind the last finalized row (difference-form tallies)
     long long* carry_f = nullptr;    // [S][2]
     bool diff_mode = false;          // this run tallies straight to global memory, rows kept as differences until finalized
@@ -132,8 +135,9 @@ constexpr size_t kSlotBytesPerBlock = static_cast<size_t>(SF_COUNT) * kSlots * 3
 constexpr int kQueueSlots = PSIM_QUEUE_SLOTS;                // slots per warp of the queues kernel ...
 constexpr int kQueueSlotsSmall = 64;                         // ... and of its second instantiation (option "queue_slots")
 constexpr size_t queue_bytes_per_block(int slots) {
-    return static_cast<size_t>(SF_COUNT) * slots * 4 * kWarpsPerBlock + static_cast<size_t>(Q_COUNT) * ring_capacity(slots) * kWarpsPerBlock;
+    return static_cast<size_t>(SG_COUNT) * slots * 16 * kWarpsPerBlock + static_cast<size_t>(Q_COUNT) * ring_capacity(slots) * kWarpsPerBlock;
 }
+constexpr size_t kPostBytesPerBlock = static_cast<size_t>(kPostScratchBytes) * kWarpsPerBlock;  // tally_post_global's scratch
 constexpr size_t kQueueBytesPerBlock = queue_bytes_per_block(kQueueSlots);
 // what a block may use so that kSlotBlocks blocks (plus 1 KB each that the driver reserves) fit the planned carve-out;
 // the tally staging gets what the slot storage leaves
@@ -144,6 +148,7 @@ constexpr size_t kTallyStageBudget = kSmemPerBlock - kSlotBytesPerBlock;
 size_t stage_budget(const psim_gpu* h) {
     return h->opt_kernel == 1 ? 100 * 1024 : (h->opt_kernel == 2 ? kSmemPerBlock - queue_bytes_per_block(static_cast<int>(h->opt_queue_slots)) : kTallyStageBudget);
 }
+constexpr int kStatWords = 8;                   // LaunchArgs::stats
 constexpr uint32_t kLongWindow = 1023;           // steps per launch while nothing is recorded (10 bits of step in the slot word)
 constexpr uint32_t kGlobalTallyWindow = 128;     // steps per launch when recorded tallies go straight to global memory
 constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
@@ -173,10 +178,11 @@ uint32_t staged_form(const psim_gpu* h, uint32_t s0, uint32_t s1) {
     return wide ? 4u : 2u;
 }
 
-void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1, uint32_t& form, size_t& smem) {
+void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1, uint32_t& form, size_t& smem, bool& records) {
     const uint32_t B = effective_steps_per_launch(h);
     form = 0;
     smem = 0;
+    records = false;
     if (h->opt_steps_per_launch <= 0 && s0 + 2 <= h->P.first_tally_step) {
         // automatic mode, nothing recorded yet (steady state: the first 90 % of the steps): long windows, cut at the
         // first recorded measurement
@@ -185,6 +191,7 @@ void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1
     }
     s1 = std::min(s0 + B, step_end);
     if (s1 + 1 <= h->P.first_tally_step) { return; }  // nothing recorded in this window
+    records = true;
     const size_t budget = stage_budget(h);
     if (h->diff_mode) {
         if (h->opt_steps_per_launch <= 0) { s1 = std::min(s0 + kGlobalTallyWindow, step_end); }  // no staging: nothing limits the window
@@ -210,7 +217,11 @@ int zero_run_state(psim_gpu* h) {
     // Tallies go straight to global memory when the caller asks for it, or when the model has so many sensors that the
     // per-CTA staging of a useful window would not fit and global atomics are spread thinly enough
     h->diff_mode = h->opt_tally_shared == 0 || (h->opt_tally_shared < 0 && P.n_sensors >= kManySensors);
-    PSIM_CUDA(cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
+    if (h->diff_mode) {
+        if (!h->tally_acc) { PSIM_CUDA(cudaMalloc(&h->tally_acc, n * 4 * sizeof(long long))); }
+        PSIM_CUDA(cudaMemsetAsync(h->tally_acc, 0, n * 4 * sizeof(long long), h->stream));
+    }
+    PSIM_CUDA(cudaMemsetAsync(h->d_stats, 0, kStatWords * sizeof(unsigned long long), h->stream));
     if (h->d_alive_hist) {
         PSIM_CUDA(cudaMemsetAsync(h->d_alive_hist, 0, static_cast<size_t>(P.num_steps + 1) * sizeof(unsigned long long), h->stream));
     }
@@ -285,14 +296,16 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
     // kernels, kinked wire with 6174 cells: 246 ms queues, 253 ms slots.)  psim_gpu_set_option("kernel") overrides.
     h->opt_kernel = 2;
     // Slots per warp: 128 keep the queues of the rare kinds of work full (Si/Ge bench model: 63.6 ms for the long window
-    // against 76.8 ms with 64).  A mesh whose cell + wall records (64 B per cell) outgrow the 92 KB of L1 that 128 slots
-    // leave runs faster with 64 slots and 156 KB of L1 (measured, 128 -> 64: linear_sides with 2000 cells 28.8 -> 27.1 ms
-    // periodic, 41.4 -> 38.3 ms transient, 15.5 -> 14.8 ms steady; kinked wire with 6174 cells 246 -> 238 ms; but
-    // linear_demo with 40 cells 12.0 -> 12.8 ms).  psim_gpu_set_option("queue_slots") overrides.
-    h->opt_queue_slots = (h->img.cells.size() > 1024) ? kQueueSlotsSmall : kQueueSlots;
+    // against 76.8 ms with 64) and leave 92 KB of L1.  A mesh whose hot records - 16 B + a 4-byte shape index per cell - do
+    // not fit there beside the tables runs faster with 64 slots and 156 KB of L1 (round 2, compressed records: kinked wire
+    // with 6174 cells 222 ms with 64 slots, 248 ms with 128; linear_sides with 2000 cells steady 13.7 vs 12.7 ms, Si/Ge 91.5
+    // vs 76.0 ms, linear_demo 13.2 vs 12.2 ms).  psim_gpu_set_option("queue_slots") overrides.
+    h->opt_queue_slots = (h->img.cells.size() * (sizeof(DevCell) + sizeof(uint32_t)) > 60u * 1024u) ? kQueueSlotsSmall : kQueueSlots;
     auto setup = [&]() -> int {
         if (int rc = upload(h, &h->d_cells, h->img.cells)) { return rc; }
-        if (int rc = upload(h, &h->d_walls, h->img.walls)) { return rc; }
+        if (int rc = upload(h, &h->d_cell_shape, h->img.cell_shape)) { return rc; }
+        if (int rc = upload(h, &h->d_shapes, h->img.shapes)) { return rc; }
+        if (int rc = upload(h, &h->d_classes, h->img.classes)) { return rc; }
         if (int rc = upload(h, &h->d_subs, h->img.subs)) { return rc; }
         if (int rc = upload(h, &h->d_sensors, h->img.sensors)) { return rc; }
         if (int rc = upload(h, &h->d_materials, h->img.materials)) { return rc; }
@@ -302,7 +315,9 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         if (int rc = upload(h, &h->d_guides, h->img.guides)) { return rc; }
         h->P = h->img.scalars;
         h->P.cells = static_cast<const DevCell*>(h->d_cells);
-        h->P.walls = static_cast<const DevWall*>(h->d_walls);
+        h->P.cell_shape = static_cast<const uint32_t*>(h->d_cell_shape);
+        h->P.shapes = static_cast<const DevShape*>(h->d_shapes);
+        h->P.classes = static_cast<const DevSensor*>(h->d_classes);
         h->P.subs = static_cast<const DevSub*>(h->d_subs);
         h->P.sensors = static_cast<const DevSensor*>(h->d_sensors);
         h->P.materials = static_cast<const DevMaterial*>(h->d_materials);
@@ -315,15 +330,19 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaMalloc(&h->tally_f, n * 2 * sizeof(long long)));
         PSIM_CUDA(cudaMalloc(&h->carry_e, std::max<size_t>(h->P.n_sensors, 1) * sizeof(int32_t)));
         PSIM_CUDA(cudaMalloc(&h->carry_f, std::max<size_t>(h->P.n_sensors, 1) * 2 * sizeof(long long)));
-        PSIM_CUDA(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
+        PSIM_CUDA(cudaMalloc(&h->d_stats, kStatWords * sizeof(unsigned long long)));
         PSIM_CUDA(cudaMalloc(&h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
         PSIM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         PSIM_CUDA(cudaEventCreate(&h->ev_begin));
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
-        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots, TALLY_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots, TALLY_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots, TALLY_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
@@ -364,9 +383,9 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
         PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_lockstep, kBlock, 0));
     } else if (h->opt_kernel == 2) {
         if (h->opt_queue_slots == kQueueSlots) {
-            PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlots>, kBlock, kSmemPerBlock));
+            PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlots, TALLY_STAGED>, kBlock, kSmemPerBlock));
         } else {
-            PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlotsSmall>, kBlock, kSmemPerBlock));
+            PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, drift_kernel_queues<kQueueSlotsSmall, TALLY_STAGED>, kBlock, kSmemPerBlock));
         }
     } else {  // shared-memory slots + the largest tally staging a launch may ask for
         const size_t dyn = kSlotBytesPerBlock + kTallyStageBudget;
@@ -419,7 +438,8 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
     for (uint32_t s0 = step_begin, s1 = 0; s0 < step_end; s0 = s1) {
         uint32_t form = 0;
         size_t smem = 0;
-        plan_launch(h, s0, step_end, s1, form, smem);
+        bool records = false;
+        plan_launch(h, s0, step_end, s1, form, smem, records);
         const bool shared = form != 0u;
         LaunchArgs a{};
         a.P = h->P;
@@ -443,6 +463,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         h->birth_offset = static_cast<uint32_t>((h->birth_offset + ((a.n_births + 31) >> 5)) % h->n_warps);
         a.tally_e = h->tally_e;
         a.tally_f = h->tally_f;
+        a.tally_acc = h->tally_acc;
         a.tally_shared = h->diff_mode ? 3u : form;  // form 0: a staged window that did not fit even for one step (plain global adds)
         a.stats = h->d_stats;
         a.alive_hist = h->d_alive_hist;
@@ -458,11 +479,20 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         if (h->opt_kernel == 1) {
             drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
         } else if (h->opt_kernel == 2) {
-            const size_t bytes = queue_bytes_per_block(static_cast<int>(h->opt_queue_slots)) + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
-            if (h->opt_queue_slots == kQueueSlots) {
-                drift_kernel_queues<kQueueSlots><<<grid, kBlock, bytes, st>>>(a);
+            // one instantiation per (slots per warp, what the window does with its measurement events)
+            const int tally = !records ? TALLY_NONE : (h->diff_mode ? TALLY_GLOBAL : TALLY_STAGED);
+            const size_t bytes = queue_bytes_per_block(static_cast<int>(h->opt_queue_slots)) + (tally == TALLY_GLOBAL ? kPostBytesPerBlock : 0) +
+                                 (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
+            const bool big = h->opt_queue_slots == kQueueSlots;
+            if (tally == TALLY_NONE) {
+                if (big) { drift_kernel_queues<kQueueSlots, TALLY_NONE><<<grid, kBlock, bytes, st>>>(a); }
+                else { drift_kernel_queues<kQueueSlotsSmall, TALLY_NONE><<<grid, kBlock, bytes, st>>>(a); }
+            } else if (tally == TALLY_GLOBAL) {
+                if (big) { drift_kernel_queues<kQueueSlots, TALLY_GLOBAL><<<grid, kBlock, bytes, st>>>(a); }
+                else { drift_kernel_queues<kQueueSlotsSmall, TALLY_GLOBAL><<<grid, kBlock, bytes, st>>>(a); }
             } else {
-                drift_kernel_queues<kQueueSlotsSmall><<<grid, kBlock, bytes, st>>>(a);
+                if (big) { drift_kernel_queues<kQueueSlots, TALLY_STAGED><<<grid, kBlock, bytes, st>>>(a); }
+                else { drift_kernel_queues<kQueueSlotsSmall, TALLY_STAGED><<<grid, kBlock, bytes, st>>>(a); }
             }
         } else {
             const size_t slots = kSlotBytesPerBlock + (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
@@ -478,7 +508,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         const uint32_t row_begin = (step_begin + 1 > F) ? step_begin + 1 - F : 0u, row_end = std::min(step_end + 1 - F, h->P.recorded_steps);
         if (row_end > row_begin) {
             const uint32_t threads = 3u * h->P.n_sensors;
-            finalize_rows_kernel<<<(threads + 127) / 128, 128, 0, st>>>(h->tally_e, h->tally_f, h->carry_e, h->carry_f, h->P.n_sensors,
+            finalize_rows_kernel<<<(threads + 127) / 128, 128, 0, st>>>(h->tally_acc, h->tally_e, h->tally_f, h->carry_e, h->carry_f, h->P.n_sensors,
                                                                          row_begin, row_end);
             PSIM_CUDA(cudaGetLastError());
         }
@@ -496,11 +526,16 @@ int psim_gpu_synchronize(psim_gpu* h) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end) == cudaSuccess) { h->kernel_ms = ms; }
     }
-    unsigned long long st[4] = { 0, 0, 0, 0 };
+    unsigned long long st[kStatWords] = {};
     PSIM_CUDA(cudaMemcpy(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
     if (st[3]) {
         h->err = "phonon pool capacity exceeded";
         return PSIM_E_OVERFLOW;
+    }
+    if (st[4]) {
+        h->err = "a phonon needed more than 8191 random-number blocks inside one measurement interval (thousands of scatters or diffuse "
+                 "wall hits per interval): shorten the measurement interval, or run with the lock-step kernel (option \"kernel\" = 1)";
+        return PSIM_E_RNG;
     }
     return PSIM_OK;
 }
@@ -516,7 +551,8 @@ int psim_gpu_next_window(psim_gpu* h, uint32_t step_begin, uint32_t* step_end) {
     if (step_begin >= last) { return PSIM_OK; }
     uint32_t form = 0;
     size_t smem = 0;
-    plan_launch(h, step_begin, last, *step_end, form, smem);
+    bool records = false;
+    plan_launch(h, step_begin, last, *step_end, form, smem, records);
     return PSIM_OK;
 }
 
@@ -591,7 +627,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     if (!h || !out) { return PSIM_E_INVALID; }
     std::memset(out, 0, sizeof(*out));
     if (int rc = psim_gpu_synchronize(h)) { return rc; }
-    unsigned long long st[4] = { 0, 0, 0, 0 };
+    unsigned long long st[kStatWords] = {};
     PSIM_CUDA(cudaMemcpy(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
     out->total_phonons = h->plan.total_phonons;
     out->shard_phonons = h->plan.shard_phonons + h->plan.shard_unrecorded;
@@ -609,7 +645,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     out->tally_in_shared = h->last_tally_shared;
     out->kernel = static_cast<uint32_t>(h->opt_kernel);
     out->reserved = 0;
-    out->image_bytes = h->img.cells.size() * (sizeof(DevCell) + sizeof(DevWall)) + h->img.subs.size() * sizeof(DevSub) +
+    out->image_bytes = h->img.cells.size() * (sizeof(DevCell) + sizeof(uint32_t)) + h->img.shapes.size() * sizeof(DevShape) + h->img.classes.size() * sizeof(DevSensor) + h->img.subs.size() * sizeof(DevSub) +
                        h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
                        h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +
                        h->img.velocities.size() * sizeof(float);
@@ -675,7 +711,9 @@ void psim_gpu_destroy(psim_gpu* h) {
     free_pool(h);
     free_plan(h);
     cudaFree(h->d_cells);
-    cudaFree(h->d_walls);
+    cudaFree(h->d_cell_shape);
+    cudaFree(h->d_shapes);
+    cudaFree(h->d_classes);
     cudaFree(h->d_subs);
     cudaFree(h->d_sensors);
     cudaFree(h->d_materials);
@@ -685,6 +723,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaFree(h->d_guides);
     cudaFree(h->tally_e);
     cudaFree(h->tally_f);
+    cudaFree(h->tally_acc);
     cudaFree(h->carry_e);
     cudaFree(h->carry_f);
     cudaFree(h->d_stats);

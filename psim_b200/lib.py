@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("PSIM_B200_LIB") or os.path.join(_HERE, "lib", "libpsi
 BINS = 1000
 
 ERRORS = {0: "OK", -1: "PSIM_E_INVALID", -2: "PSIM_E_NO_DEVICE", -3: "PSIM_E_CUDA", -4: "PSIM_E_OVERFLOW",
-          -5: "PSIM_E_STATE", -6: "PSIM_E_IO", -7: "PSIM_E_MODEL"}
+          -5: "PSIM_E_STATE", -6: "PSIM_E_IO", -7: "PSIM_E_MODEL", -8: "PSIM_E_RNG"}
 
 
 class PsimError(RuntimeError):

@@ -26,7 +26,9 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     }
     DevParams P = img.scalars;
     P.cells = img.cells.data();
-    P.walls = img.walls.data();
+    P.cell_shape = img.cell_shape.data();
+    P.shapes = img.shapes.data();
+    P.classes = img.classes.data();
     P.subs = img.subs.data();
     P.sensors = img.sensors.data();
     P.materials = img.materials.data();
