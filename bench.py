@@ -1,22 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the phonon Monte Carlo particle loop (BASELINE.json: phonon drift-steps/sec + HBM roofline %).
+"""Benchmark of the phonon Monte Carlo particle loop (BASELINE.json: phonon drift-steps/sec at 1/2/4/8 B200 + roofline;
+wall-clock per model).
 
-Workload (config.workload): BASELINE.json configs[4], the synthetic 100-cell Si/Ge structure with 1e8 deviational
-phonons PER GPU (weak scaling: an N-GPU job simulates N x 1e8 phonons, rank r owns the phonon ids == r mod N),
-1000 measurement steps over 1 ns.  One bench "step" = one complete simulation of that model: every measurement
-interval of every phonon (emission, drift, scattering, surfaces, cell transitions, tallies) plus the all-reduce of
-the sensor tallies.  1 drift-step = one live phonon advanced across one measurement interval.
+Workload (config.workload): BASELINE.json configs[4], the synthetic 100-cell Si/Ge structure with 1e8 deviational phonons
+IN TOTAL, sharded over the N GPUs of the job (strong scaling: rank r owns the phonon ids == r mod N), 1000 measurement
+steps over 1 ns.  One bench "step" = one complete simulation of that model: every measurement interval of every phonon
+(emission, drift, scattering, surfaces, cell transitions, tallies) plus the NCCL all-reduce of the sensor tallies.
+1 drift-step = one live phonon advanced across one measurement interval.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (one process per GPU under torchrun)
   python bench.py --impl reference ...                         the reference's own CPU code on the host cores
 
-Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
-max over ranks.  The phonon pool (~0.9 GB live per launch) is far larger than the 126 MB L2, so every launch
-streams it from HBM (config.l2: "inputs larger than L2").
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over
+ranks.  Besides the headline the line carries
+  strong      the 64-bit checksums that must be identical at N = 1, 2, 4, 8: reduced int32 / int64 tallies, emitted counts,
+              phonons per cell at mid-run - for the bench job and for the 6174-cell kinked wire (31 MB all-reduce)
+  weak        the same job with 1e8 phonons PER GPU (N > 1 only; at N = 1 it is the headline)
+  models      wall-clock per shipped model at its full phonon count (N = 1), next to the reference's own headers
+  roofline    what bounds the kernel: instruction issue (warp instructions per drift-step from the committed ncu captures,
+              used only while profiles/r02_ncu_summary.json carries the hash of the kernel sources it was taken on) and the
+              measured DRAM traffic against the HBM peak
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -33,58 +41,57 @@ import numpy as np  # noqa: E402
 
 from psim_b200 import configs  # noqa: E402
 
-ALGO_BYTES_PER_DRIFT_STEP = 64  # 32 B state read + 32 B written
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "psim_ref")
 METRIC = "phonon drift-steps/sec"
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_ncu_summary.json")
+WORKLOAD = "synthetic 100-cell Si/Ge 2D structure (BASELINE.json configs[4]), steady-state deviational"
+CHECKSUM_SEED = 4242
+# the reference's own result-file headers (psim_python/json/results/ss_*.txt:1, "Time Taken ...[s]")
+REFERENCE_HEADER_SECONDS = {"linear_demo": 18.1, "linear_sides_demo_ss": 32.0, "kinked_demo_120_35_spec": 212.7}
 
 
 def workload_model(num_phonons: int) -> dict:
     return configs.si_ge_grid(num_phonons=num_phonons).to_dict()
 
 
-def ncu_traffic_per_launch(per_gpu: int, launches_per_job: int, auto_windows: bool):
-    """DRAM bytes per drift-kernel launch, averaged over the launches of one job, from the committed ncu captures
-    (profiles/r01_ncu_summary.json: one long unrecorded window + recorded windows); None if they were taken on another
-    configuration."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
-    try:
-        d = json.load(open(path))
-        if d["phonons_per_gpu"] == per_gpu and auto_windows and launches_per_job >= 2:
-            j = d["default_job"]
-            return int((j["dram_bytes_long_window"] + (launches_per_job - 1) * j["dram_bytes_recorded_window"]) / launches_per_job)
-    except Exception:
-        pass
-    return None
+def csrc_sha16() -> str:
+    """Hash of the kernel / host sources: profiles/*_ncu_summary.json records the value it was captured on, and the
+    ncu-derived constants are used only while it matches the tree that is running."""
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "psim_b200", "csrc")
+    for dirpath, _, files in sorted(os.walk(base)):
+        for f in sorted(files):
+            p = os.path.join(dirpath, f)
+            h.update(os.path.relpath(p, base).encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
 
 
-def issue_slot_use(per_gpu: int, kernel_ms: float, recorded_steps: int, sm_mhz, auto_windows: bool):
-    """What actually bounds the kernel: warp instructions issued per second against the issue
-    slots of the chip (148 SMs x 4 schedulers x SM clock).  Instruction counts per launch come from the committed ncu
-    captures of this workload (one long unrecorded window + one 36-step recorded window, scaled to the recorded steps of
-    a job); the time is the one measured live.  None when the captures do not describe this configuration."""
+def ncu_constants():
+    """profiles/r02_ncu_summary.json if it was captured on THIS source tree, else None (never a stale constant)."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-        if d["phonons_per_gpu"] != per_gpu or not auto_windows or not sm_mhz:
-            return None
-        long_w, rec_w = d["captures"][0], d["captures"][1]
-        inst = long_w["warp_instructions"] + rec_w["warp_instructions"] * recorded_steps / 36.0
-        peak = 148 * 4 * float(sm_mhz) * 1e6
-        achieved = inst / (kernel_ms * 1e-3)
-        return {"achieved_warp_inst_per_s": achieved, "peak_warp_inst_per_s": peak, "frac": achieved / peak,
-                "threads_active_per_instruction": long_w["threads_active_per_instruction"],
-                "source": "warp instructions per launch from profiles/r01_ncu_summary.json (ncu), time measured live"}
+        d = json.load(open(NCU_SUMMARY))
+        return d if d.get("csrc_sha16") == csrc_sha16() else None
     except Exception:
         return None
 
 
-def measured_peak_gbs():
+def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        except Exception:
-            pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def checksum64(*arrays) -> str:
+    h = hashlib.blake2b(digest_size=8)
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
 
 
 class ClockSampler:
@@ -130,12 +137,26 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU reference
+def oracle_drift_steps_per_phonon(model: dict, phonons: int = 100_000) -> float | None:
+    """Drift-steps per phonon of `model`, COUNTED on the CPU by the restatement of the reference's event loop (oracle/sim.c
+    counts one per measurement event and one per exit) on a sample of `phonons` phonons.  The unmodified
+    reference binary has no such counter; its rate is its phonons per second times this figure."""
+    try:
+        from oracle.model import OracleModel
+        om = OracleModel(configs.with_settings(model, num_phonons=phonons))
+        om.prepare()
+        _, _, steps, _ = om.run(1, threads=min(os.cpu_count() or 1, 16))
+        return float(steps) / float(phonons)
+    except Exception:
+        return None
+
+
 def reference_cpu_run(model: dict, phonons_per_proc: int, procs: int, drift_steps_per_phonon: float | None):
     """Runs the reference's own CPU implementation (oracle/_ref/psim_ref: unmodified reference sources + our
     driver main) as `procs` independent processes (no TBB in this image, so std::execution::par is serial; phonons
     are independent, so P processes of n/P phonons are the reference's parallel path).  Wall = slowest process."""
     if not os.path.exists(REF_BIN):
-        return oracle_cpu_run(model, phonons_per_proc * procs, procs, drift_steps_per_phonon)
+        return oracle_cpu_run(model, phonons_per_proc * procs, procs)
     with tempfile.TemporaryDirectory() as tmp:
         path = configs.save(configs.with_settings(model, num_phonons=phonons_per_proc), os.path.join(tmp, "m.json"))
         t0 = time.perf_counter()
@@ -152,8 +173,9 @@ def reference_cpu_run(model: dict, phonons_per_proc: int, procs: int, drift_step
     return out
 
 
-def oracle_cpu_run(model: dict, phonons: int, threads: int, drift_steps_per_phonon):
-    """Fallback when the reference binary is not on the box: the plain-C restatement under oracle/ (OpenMP)."""
+def oracle_cpu_run(model: dict, phonons: int, threads: int):
+    """Fallback when the reference binary is not on the box: the plain-C restatement under oracle/ (OpenMP), which counts
+    its own drift-steps."""
     try:
         from oracle.model import OracleModel
         om = OracleModel(configs.with_settings(model, num_phonons=phonons))
@@ -163,8 +185,7 @@ def oracle_cpu_run(model: dict, phonons: int, threads: int, drift_steps_per_phon
         secs = time.perf_counter() - t0
     except Exception:
         return None
-    return {"phonons": phonons, "seconds": secs, "wall_with_load": secs, "kind": "port",
-            "drift_steps_per_s": (phonons * drift_steps_per_phonon if drift_steps_per_phonon else steps) / secs}
+    return {"phonons": phonons, "seconds": secs, "wall_with_load": secs, "kind": "port", "drift_steps_per_s": steps / secs}
 
 
 # --------------------------------------------------------------------------------------------------------- ours
@@ -190,76 +211,95 @@ def emit(obj):
         os.write(_RESULT_FD, line)
 
 
-def agree_on_cuts(cuts, num_steps: int, world: int, rank: int, device):
-    """Every rank must cut a job into the same groups of measurement steps (each group ends with a collective).  The
-    library's launch windows depend, through the exactness bound of the tally staging, on the capacity of the rank's own
-    pool - which may differ by one phonon between ranks - so rank 0's cuts are broadcast and used by all; a rank whose own
-    windows are shorter simply needs two launches for such a group."""
-    if world == 1:
-        return list(cuts)
-    import torch
-    import torch.distributed as dist
-    t = torch.full((num_steps + 2,), -1, dtype=torch.int64, device=device)
-    if rank == 0:
-        t[:len(cuts)] = torch.tensor(cuts, dtype=torch.int64)
-    dist.broadcast(t, 0)
-    return [int(x) for x in t.tolist() if x >= 0]
+class Env:
+    """Rank / device / process group of this bench process."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.device = f"cuda:{self.local}"
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.Stream(device=self.local)  # the drift kernels are launched on THIS stream, and so are the events
+        torch.cuda.set_stream(self.stream)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_over_ranks(self, values):
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class _Dev:  # expose the library's tally buffers to torch (for the NCCL all-reduce) without a copy
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
-    from psim_b200 import lib as psim
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+class ShardedJob:
+    """One model, its phonons sharded over the ranks by id (rank r owns ids == r mod N): the library handle of this rank,
+    torch views of its device-resident tallies, and the groups of measurement steps between tally all-reduces."""
 
-    per_gpu = args.phonons
-    model_dict = workload_model(per_gpu * world)
-    model = psim.Model(text=json.dumps(model_dict))
-    model.prepare()
-    info = model.info
-    M, S, R = info.measurement_steps, info.num_sensors, info.recorded_steps
-    desc = model.describe()
+    def __init__(self, env: Env, model_dict: dict, args, options=None):
+        from psim_b200 import lib as psim
+        self.env, self.args = env, args
+        self.model = psim.Model(text=json.dumps(model_dict))
+        self.model.prepare()
+        info = self.model.info
+        self.M, self.S, self.R = info.measurement_steps, info.num_sensors, info.recorded_steps
+        self.cells = info.num_cells
+        self.first = self.M - self.R  # first step whose measurement is recorded
+        self.g = psim.GpuSimulator(self.model.describe(), env.local)
+        self.g.set_option("steps_per_launch", args.steps_per_launch)
+        for k, v in (options or {}).items():
+            if v is not None and v >= 0:
+                self.g.set_option(k, v)
+        e_ptr, f_ptr, _, _ = self.g.tally_buffers()
+        self.t_energy = env.torch.as_tensor(_Dev(e_ptr, (self.R, self.S), "<i4"), device=env.device)
+        self.t_flux = env.torch.as_tensor(_Dev(f_ptr, (self.R, self.S, 2), "<i8"), device=env.device)
+        self.sources = None
 
-    g = psim.GpuSimulator(desc, local)
-    g.set_option("steps_per_launch", args.steps_per_launch)
-    if args.tally_shared >= 0:
-        g.set_option("tally_shared", args.tally_shared)
-    if args.warps_per_sm > 0:
-        g.set_option("warps_per_sm", args.warps_per_sm)
-    if args.kernel >= 0:
-        g.set_option("kernel", args.kernel)
+    def close(self):
+        self.g.close()
+        self.model.close()
 
-    class _Dev:  # expose the library's tally buffers to torch (for the NCCL all-reduce) without a copy
-        def __init__(self, ptr, shape, typestr):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+    def set_sources(self, seed: int):
+        src, n = self.model.sources(seed)
+        self.sources = [(src[i].kind, src[i].index, src[i].sign, src[i].count) for i in range(n)]
+        self.g.set_sources(src, n, seed, self.env.rank, self.env.world)  # untimed: pool reset, tallies zeroed, birth plan resident in HBM
 
-    e_ptr, f_ptr, _, _ = g.tally_buffers()
-    t_energy = torch.as_tensor(_Dev(e_ptr, (R, S), "<i4"), device=f"cuda:{local}")
-    t_flux = torch.as_tensor(_Dev(f_ptr, (R, S, 2), "<i8"), device=f"cuda:{local}")
-    stream = torch.cuda.Stream(device=local)  # the drift kernels are launched on THIS stream, and so are the events
-    torch.cuda.set_stream(stream)
-    chunk = max(args.steps_per_launch, args.reduce_every) if args.reduce_every > 0 else 0
-
-    first = M - R  # first step whose measurement is recorded
-
-    def plan_cuts():
+    def plan_cuts(self, extra_cut: int | None = None):
         """Steps whose measurement is not recorded (steady state: the first 90 %) need no exchange and go to the library
         in one call (it chooses its own launch windows); the recorded steps go in groups that end where the library's
-        launch windows end (no extra launch for the exchange; --reduce-every N asks for groups of N steps instead)."""
+        launch windows end (no extra launch for the exchange; --reduce-every N asks for groups of N steps instead).  Every
+        rank must cut a job the same way (each group ends with a collective) and the library's windows depend, through the
+        exactness bound of the tally staging, on the capacity of the rank's own pool - which may differ by one phonon
+        between ranks - so rank 0's cuts are broadcast and used by all."""
+        args, g, M, first = self.args, self.g, self.M, self.first
+        chunk = max(args.steps_per_launch, args.reduce_every) if args.reduce_every > 0 else 0
         cuts, s = [0], 0
         if first > 1:
             s = first - 1
@@ -267,150 +307,301 @@ def run_ours(args):
         while s < M - 1:
             s = min(s + chunk, M - 1) if chunk > 0 else g.next_window(s)
             cuts.append(s)
-        return agree_on_cuts(cuts, M, world, rank, f"cuda:{local}")
+        if extra_cut is not None and extra_cut not in cuts:
+            cuts = sorted(cuts + [extra_cut])
+        env = self.env
+        if env.world > 1:
+            t = env.torch.full((M + 2,), -1, dtype=env.torch.int64, device=env.device)
+            if env.rank == 0:
+                t[:len(cuts)] = env.torch.tensor(cuts, dtype=env.torch.int64)
+            env.dist.broadcast(t, 0)
+            cuts = [int(x) for x in t.tolist() if x >= 0]
+        return cuts
 
-    def one_job(cuts):
+    def run(self, cuts, at_cut=None):
         """All measurement steps; the tally all-reduce of a group of steps is issued as soon as the group's launches are
         enqueued."""
+        env = self.env
         for s, e in zip(cuts[:-1], cuts[1:]):
-            g.run_steps(s, e, stream.cuda_stream)
-            if world > 1:
-                r0, r1 = max(s + 1 - first, 0), e + 1 - first  # tally rows completed by steps [s, e)
+            self.g.run_steps(s, e, env.stream.cuda_stream)
+            if env.world > 1:
+                r0, r1 = max(s + 1 - self.first, 0), e + 1 - self.first  # tally rows completed by steps [s, e)
                 if r1 > r0:
-                    dist.all_reduce(t_energy[r0:r1])
-                    dist.all_reduce(t_flux[r0:r1])
+                    env.dist.all_reduce(self.t_energy[r0:r1])
+                    env.dist.all_reduce(self.t_flux[r0:r1])
+            if at_cut is not None:
+                at_cut(e)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def timed_jobs(self, warmup: int, steps: int, seed0: int, sampler=None):
+        env = self.env
+        times, kernel_ms, drift, events, launches = [], [], [], [], 0
+        cuts = None
+        for it in range(warmup + steps):
+            self.set_sources(seed0 + it)
+            cuts = self.plan_cuts()
+            timed = it >= warmup
+            if timed and it == warmup and sampler:
+                sampler.__enter__()
+            env.barrier()
+            ev0, ev1 = env.torch.cuda.Event(enable_timing=True), env.torch.cuda.Event(enable_timing=True)
+            ev0.record(env.stream)
+            self.run(cuts)
+            ev1.record(env.stream)
+            env.barrier()
+            st = self.g.stats()
+            if timed:
+                times.append(ev0.elapsed_time(ev1))
+                kernel_ms.append(st.kernel_ms)
+                drift.append(st.drift_steps)
+                events.append(st.events)
+                launches += st.launches
+        ms = env.max_over_ranks([np.mean(times)])[0]
+        tot = env.sum_over_ranks([np.mean(drift), np.mean(events)])
+        return {"ms_per_step": ms, "drift_steps": tot[0], "events": tot[1], "kernel_ms": float(np.mean(kernel_ms)),
+                "drift_steps_rank": float(np.mean(drift)), "launches": launches, "cuts": cuts, "stats": self.g.stats().as_dict()}
 
-    times, kernel_ms, drift, launches = [], [], [], 0
-    sampler = ClockSampler(local) if rank == 0 else None
-    total_steps = args.warmup + args.steps
-    for it in range(total_steps):
-        seed = 1000 + it
-        src, n = model.sources(seed)
-        g.set_sources(src, n, seed, rank, world)  # untimed: pool reset, tallies zeroed, birth plan resident in HBM
-        cuts = plan_cuts()
-        timed = it >= args.warmup
-        if timed and it == args.warmup and sampler:
-            sampler.__enter__()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        one_job(cuts)
-        ev1.record(stream)
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        st = g.stats()
-        if timed:
-            times.append(ms)
-            kernel_ms.append(st.kernel_ms)
-            drift.append(st.drift_steps)
-            launches += st.launches
-    last_stats = g.stats().as_dict()
+    def checksum_job(self, seed: int = CHECKSUM_SEED):
+        """One job with a fixed seed whose integers must not depend on the number of GPUs: the reduced tallies, the emitted
+        counts and the number of phonons per cell half-way through the run."""
+        env = self.env
+        self.set_sources(seed)
+        mid = self.M // 2
+        cuts = self.plan_cuts(extra_cut=mid)
+        hist = {}
 
-    # ---- end to end through the host API with HOST buffers, as the runs of a multi-run model go (psim_model_run):
-    # per run the sources / birth plan go host -> device, the GPU runs, the tallies come back device -> host and the
-    # reference's run epilogue (temperatures / fluxes) is done on the host.  The handle (model image, pool) is created
-    # once, as psim_model_run does; the first run through it is the warm-up. ----
-    e2e_ms, e2e_detail = [], []
-    h2d = d2h = 0
-    g2 = psim.GpuSimulator(model.describe(), local)  # uploads cells / sensors / tables (host -> device), once
+        def at_cut(e):
+            if e == mid:
+                h = self.g.cell_histogram().astype(np.int64)
+                t = env.torch.from_numpy(h).to(env.device)
+                if env.world > 1:
+                    env.dist.all_reduce(t)
+                hist["cells"] = t.cpu().numpy()
+
+        env.barrier()
+        self.run(cuts, at_cut)
+        env.barrier()
+        e = self.t_energy.cpu().numpy()
+        f = self.t_flux.cpu().numpy()
+        st = self.g.stats()
+        tot = env.sum_over_ranks([st.drift_steps, st.shard_phonons])
+        counts = np.array([c for (_, _, _, c) in self.sources], dtype=np.uint64)
+        return {"seed": seed, "tallies": checksum64(e, f), "energy": checksum64(e), "flux": checksum64(f),
+                "emitted_counts": checksum64(counts), "cell_histogram_mid_run": checksum64(hist["cells"]),
+                "phonons_emitted": int(counts.sum()), "phonons_alive_mid_run": int(hist["cells"].sum()),
+                "drift_steps": int(tot[0]), "allreduce_bytes_per_job": int(e.nbytes + f.nbytes), "cuts": cuts}
+
+
+def end_to_end(env: Env, model_dict: dict, args, runs: int):
+    """End to end through the host API with HOST buffers, as the runs of a multi-run model go (psim_model_run): per run the
+    sources / birth plan go host -> device, the GPU runs, the tallies come back device -> host and the reference's run
+    epilogue (temperatures / fluxes) is done on the host.  The handle (model image, pool) is created once, as
+    psim_model_run does; the first run through it is the warm-up."""
+    from psim_b200 import lib as psim
+    torch, dist = env.torch, env.dist
+    model = psim.Model(text=json.dumps(model_dict))
+    model.prepare()
+    g2 = psim.GpuSimulator(model.describe(), env.local)  # uploads cells / sensors / tables (host -> device), once
     g2.set_option("steps_per_launch", args.steps_per_launch)
-    for it in range(1 + max(1, min(args.steps, 3))):
+    e2e_ms, detail, h2d, d2h = [], [], 0, 0
+    for it in range(1 + runs):
         seed = 2000 + it
-        barrier()
+        env.barrier()
         t0 = time.perf_counter()
         src, n = model.sources(seed)
-        g2.set_sources(src, n, seed, rank, world)  # birth plan host -> device
+        g2.set_sources(src, n, seed, env.rank, env.world)  # birth plan host -> device
         g2.run()
         e, f = g2.tallies()  # device -> host
-        if world > 1:
+        if env.world > 1:
             te, tf = torch.from_numpy(e.astype(np.int64)).cuda(), torch.from_numpy(f).cuda()
             dist.all_reduce(te)
             dist.all_reduce(tf)
             e, f = te.cpu().numpy().astype(np.int32), tf.cpu().numpy()
         model.set_tallies(e, f)
         model.finish_run(0)
-        six, _, _ = model.results(0, traces=False)
+        model.results(0, traces=False)
         model.next_run()
         model.prepare()
-        barrier()
+        env.barrier()
         ms = (time.perf_counter() - t0) * 1e3
         st2 = g2.stats()
-        e2e_detail.append({"ms": round(ms, 2), "kernel_ms": round(st2.kernel_ms, 2), "phonons": st2.total_phonons,
-                           "drift_steps": st2.drift_steps, "timed": it > 0})
+        detail.append({"ms": round(ms, 2), "kernel_ms": round(st2.kernel_ms, 2), "phonons": st2.total_phonons,
+                       "drift_steps": st2.drift_steps, "timed": it > 0})
         if it > 0:
             e2e_ms.append(ms)
-        h2d = st2.plan_bytes  # sources + birth plan, counted by the library
-        d2h = st2.tally_bytes
+        h2d, d2h = st2.plan_bytes, st2.tally_bytes  # sources + birth plan / tallies, counted by the library
     g2.close()
+    model.close()
+    return env.max_over_ranks([np.mean(e2e_ms)])[0], detail, int(h2d), int(d2h)
+
+
+def shipped_models():
+    from tests import cases
+    m = {
+        "linear_demo": configs.linear().to_dict(),
+        "linear_sides_demo_ss": configs.linear_sides().to_dict(),
+        "linear_sides_demo_per": configs.linear_sides(sim_type=1, step_interval=4).to_dict(),
+        "linear_sides_demo_trans": configs.linear_sides(sim_type=2, step_interval=4, start_time=0.1, duration=0.15).to_dict(),
+    }
+    kinked = cases.kinked_model()
+    if kinked is not None:
+        m["kinked_demo_120_35_spec"] = kinked
+        m["kinked_demo_120_35_spec0.5"] = configs.with_specularity(kinked, 0.5)
+    m["si_ge_grid_1e8"] = configs.si_ge_grid().to_dict()
+    return m
+
+
+def model_walltimes(device: int):
+    """BASELINE.json "wall-clock per model": every shipped configuration at its FULL phonon count, end to end through the
+    host API (psim_model_run: set-up, host -> device, kernels, device -> host, epilogue; the second of two runs, so that the
+    CUDA context and the pool exist), the kernel-only time, and the throughput in drift-steps and in flight segments."""
+    from psim_b200 import lib as psim
+    out = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, model in shipped_models().items():
+            path = configs.save(configs.with_settings(model, num_runs=2), os.path.join(tmp, "m.json"))
+            t0 = time.perf_counter()
+            m = psim.Model(path)
+            t1 = time.perf_counter()
+            st = m.run(device=device, seed=1)  # two runs through one handle
+            t2 = time.perf_counter()
+            m1 = psim.Model(path)
+            m1.set_num_runs(1)
+            t3 = time.perf_counter()
+            m1.run(device=device, seed=1)
+            t4 = time.perf_counter()
+            second_run_ms = max((t2 - t1) - (t4 - t3), 0.0) * 1e3  # the run that found the context, image and pool in place
+            k_ms = st.kernel_ms
+            rec = {"model": name, "phonons": int(st.total_phonons), "cells": int(m.info.num_cells), "sensors": int(m.info.num_sensors),
+                   "measurement_steps": int(m.info.measurement_steps), "sim_type": int(m.info.sim_type), "load_s": round(t1 - t0, 4),
+                   "first_run_s": round(t4 - t3, 4), "ms_e2e": round(second_run_ms, 2), "kernel_ms": round(k_ms, 2), "launches": int(st.launches),
+                   "drift_steps": int(st.drift_steps), "segments": int(st.events),
+                   "drift_steps_per_s": st.drift_steps / (k_ms * 1e-3), "segments_per_s": st.events / (k_ms * 1e-3),
+                   "reference_header_s": REFERENCE_HEADER_SECONDS.get(name)}
+            out.append(rec)
+            m.close()
+            m1.close()
+    return out
+
+
+def run_ours(args):
+    env = Env(args)
+    world, rank = env.world, env.rank
+    total = args.phonons
+    per_gpu = total // world
+    model_dict = workload_model(total)
+    opts = {"tally_shared": args.tally_shared, "warps_per_sm": args.warps_per_sm if args.warps_per_sm > 0 else -1, "kernel": args.kernel}
+
+    sampler = ClockSampler(env.local) if rank == 0 else None
+    job = ShardedJob(env, model_dict, args, opts)
+    main = job.timed_jobs(args.warmup, args.steps, 1000, sampler)
+    strong = {"si_ge_grid": job.checksum_job()}
+    M, S, R, cells = job.M, job.S, job.R, job.cells
+    job.close()
+
+    e2e_ms, e2e_detail, h2d, d2h = end_to_end(env, model_dict, args, max(1, min(args.steps, 3)))
     if sampler:
         sampler.__exit__()  # clocks sampled under load from the first timed job to the last end-to-end run
 
-    t_max = torch.tensor([float(np.mean(times)), float(np.mean(e2e_ms))], device=f"cuda:{local}")
-    d_sum = torch.tensor([float(np.mean(drift))], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-        dist.all_reduce(d_sum, op=dist.ReduceOp.SUM)
-    ms_per_step = float(t_max[0])
-    e2e_ms_max = float(t_max[1])
-    total_drift = float(d_sum[0])
-    value = total_drift / (ms_per_step * 1e-3)
+    weak = None
+    if world > 1 and not args.no_weak:
+        wjob = ShardedJob(env, workload_model(total * world), args, opts)
+        w = wjob.timed_jobs(2, max(1, min(args.steps, 3)), 3000)
+        wjob.close()
+        weak = {"value": w["drift_steps"] / (w["ms_per_step"] * 1e-3), "unit": "drift-steps/s", "ms_per_step": w["ms_per_step"],
+                "phonons_per_gpu": total, "phonons_total": total * world}
 
+    kinked = None
+    if not args.no_kinked:
+        from tests import cases
+        kd = cases.kinked_model()
+        if kd is not None:
+            kjob = ShardedJob(env, kd, args, opts)
+            k = kjob.timed_jobs(1, 2, 5000)
+            kinked = kjob.checksum_job()
+            kinked.update({"workload": "kinked_demo_120_35_spec.json (BASELINE.json configs[1]): 6174 cells, 3108 sensors, 2e7 phonons in total",
+                           "value": k["drift_steps"] / (k["ms_per_step"] * 1e-3), "unit": "drift-steps/s", "ms_per_step": k["ms_per_step"],
+                           "kernel_ms": k["kernel_ms"], "segments_per_s": k["events"] / (k["ms_per_step"] * 1e-3)})
+            kinked.pop("cuts", None)
+            kjob.close()
+            strong["kinked"] = kinked
+
+    ms_per_step = main["ms_per_step"]
+    total_drift = main["drift_steps"]
+    value = total_drift / (ms_per_step * 1e-3)
     out = None
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        k_ms = float(np.mean(kernel_ms))
-        achieved = float(np.mean(drift)) * ALGO_BYTES_PER_DRIFT_STEP / (k_ms * 1e-3) / 1e9
-        launches_per_job = max(1, last_stats["launches"])
+        peak_gbs, sm_max, peak_src = measured_peaks()
+        clocks = sampler.summary() if sampler else None
+        sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+        k_ms = main["kernel_ms"]
+        stats = main["stats"]
+        launches_per_job = max(1, stats["launches"])
+        auto = args.steps_per_launch == 0 and args.kernel < 0 and args.tally_shared < 0 and args.warps_per_sm <= 0
+        ncu = ncu_constants() if auto else None
+        peak_issue = 148 * 4 * sm_mhz * 1e6
+        roof = {"bound": "issue", "unit": "warp-inst/s", "peak": peak_issue, "achieved": None, "frac": None, "traffic": None,
+                "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
+                "kernel": {0: "drift_kernel_slots<4>", 1: "drift_kernel_lockstep"}.get(stats["kernel"], "drift_kernel_queues<128, *>"),
+                "avg_launch_ms": k_ms / launches_per_job, "launches_per_job": launches_per_job, "kernel_ms_per_job": k_ms,
+                "segments_per_s": main["events"] / (ms_per_step * 1e-3), "segments_per_drift_step": main["events"] / total_drift,
+                "hbm": {"bound": "hbm", "unit": "GB/s", "peak": peak_gbs, "peak_source": peak_src, "achieved": None, "frac": None,
+                        "algorithmic_bytes_per_drift_step": 64,
+                        "algorithmic_ratio": main["drift_steps_rank"] * 64 / (k_ms * 1e-3) / 1e9 / peak_gbs,
+                        "note": "achieved = DRAM bytes per job measured by ncu (dram__bytes_read + write over the job's launches) / live kernel "
+                                "time.  algorithmic_ratio = 64 B x drift-steps / kernel time / peak (SURVEY 8d's accounting) is NOT a roofline "
+                                "fraction: a launch keeps a phonon on chip for a whole window of measurement steps"},
+                "ncu": ("profiles/r02_ncu_summary.json (csrc_sha16 matches this tree)" if ncu else
+                        "ncu-derived fields are null: no capture of this source tree / configuration is committed")}
+        if ncu:
+            j = ncu["bench_job"]
+            inst = j["warp_instructions_per_drift_step"] * main["drift_steps_rank"]
+            roof["achieved"] = inst / (k_ms * 1e-3)
+            roof["frac"] = roof["achieved"] / peak_issue
+            roof["warp_instructions_per_drift_step"] = j["warp_instructions_per_drift_step"]
+            roof["warp_instructions_per_segment"] = j["warp_instructions_per_drift_step"] * total_drift / main["events"]
+            roof["threads_active_per_instruction"] = j["threads_active_per_instruction"]
+            dram = j["dram_bytes_per_drift_step"] * main["drift_steps_rank"]
+            roof["traffic"] = int(dram / launches_per_job)
+            roof["hbm"]["achieved"] = dram / (k_ms * 1e-3) / 1e9
+            roof["hbm"]["frac"] = roof["hbm"]["achieved"] / peak_gbs
         out = {
             "metric": METRIC, "value": value, "unit": "drift-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic 100-cell Si/Ge 2D structure (BASELINE.json configs[4]), steady-state deviational",
-                       "phonons_per_gpu": per_gpu, "phonons_total": per_gpu * world, "measurement_steps": M, "cells": info.num_cells,
-                       "sensors": S, "drift_steps_per_job": total_drift, "steps_per_launch": last_stats["steps_per_launch"],
-                       "sharding": f"phonon id mod {world}", "l2": "inputs larger than L2 (live pool >> 126 MB, streamed every launch)",
+            "config": {"workload": WORKLOAD, "phonons_total": total, "phonons_per_gpu": per_gpu, "measurement_steps": M, "cells": cells,
+                       "sensors": S, "drift_steps_per_job": total_drift, "launch_windows": main["cuts"],
+                       "sharding": f"phonon id mod {world}", "l2": "inputs larger than L2 (live pool >> 126 MB, streamed every launch)"
+                       if per_gpu >= 50_000_000 else "live pool of a rank below the 126 MB L2 at this N; jobs alternate between two pool copies and "
+                       "re-create every phonon, nothing is reused between timed jobs",
                        "rng": "Philox4x32-10 keyed by (seed, phonon id, step)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(per_gpu, launches_per_job, args.steps_per_launch == 0),
-                         "peak_source": peak_src, "kernel": {0: "drift_kernel_slots<4>", 1: "drift_kernel_lockstep"}.get(last_stats["kernel"], "drift_kernel_queues<128>"),
-                         "algorithmic_bytes_per_drift_step": ALGO_BYTES_PER_DRIFT_STEP,
-                         "algorithmic_bytes_per_launch": float(np.mean(drift)) * ALGO_BYTES_PER_DRIFT_STEP / launches_per_job,
-                         "avg_launch_ms": k_ms / launches_per_job, "launches_per_job": launches_per_job, "kernel_ms_per_job": k_ms,
-                         "issue_slots": issue_slot_use(per_gpu, k_ms, R, (sampler.summary() or {}).get("sm_mhz") if sampler else None,
-                                                       args.steps_per_launch == 0),
-                         "note": "achieved = 64 B x drift-steps / kernel time, the accounting of SURVEY 8d (state read + written once per "
-                                 "drift-step).  A launch keeps a phonon on chip for a whole window of measurement steps, so the real "
-                                 "DRAM traffic (`traffic`, bytes per launch, ncu) is a small fraction of the algorithmic bytes and frac "
-                                 "can exceed 1: the kernel is issue-bound (issue active 71 %), not HBM-bound"},
-            "e2e": {"value": total_drift / (e2e_ms_max * 1e-3), "unit": "drift-steps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max, "runs": e2e_detail},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary() if sampler else None,
-            "stats": last_stats,
+            "roofline": roof,
+            "e2e": {"value": total_drift / (e2e_ms * 1e-3), "unit": "drift-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "runs": e2e_detail},
+            "gpu_launches": int(main["launches"]),
+            "clocks": clocks,
+            "strong": strong,
+            "weak": weak,
+            "stats": stats,
+            "csrc_sha16": csrc_sha16(),
         }
+        if world == 1 and not args.no_models:
+            out["models"] = model_walltimes(env.local)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            per_phonon = float(np.mean(drift)) / per_gpu
+            per_phonon = oracle_drift_steps_per_phonon(model_dict)
             cpu = reference_cpu_run(model_dict, args.cpu_phonons_per_core, cores, per_phonon)
-            if cpu:
-                out["cpu_baseline"] = {"value": cpu["drift_steps_per_s"], "unit": "drift-steps/s", "cores": cores,
-                                       "kind": cpu["kind"],
-                                       "sample": f"{cores} processes x {args.cpu_phonons_per_core} phonons of the same model "
-                                                 f"({cpu['seconds']:.1f} s); drift-steps per phonon taken from the GPU run"}
+            if cpu and cpu.get("drift_steps_per_s"):
+                out["cpu_baseline"] = {"value": cpu["drift_steps_per_s"], "unit": "drift-steps/s", "cores": cores, "kind": cpu["kind"],
+                                       "sample": f"{cores} processes x {args.cpu_phonons_per_core} phonons of the same model ({cpu['seconds']:.1f} s); "
+                                                 f"{per_phonon:.2f} drift-steps per phonon counted on the CPU by oracle/sim.c on 1e5 phonons"
+                                                 if cpu["kind"] == "reference" else f"oracle/sim.c, {cores} threads, counts its own drift-steps"}
             else:
                 out["cpu_baseline"] = {"value": None, "unit": "drift-steps/s", "cores": cores, "kind": "reference",
-                                       "sample": "oracle/_ref/psim_ref not present on this box"}
+                                       "sample": "neither oracle/_ref/psim_ref nor the oracle library is usable on this box"}
         emit(out)
-    g.close()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     return out
 
 
@@ -420,13 +611,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    model = workload_model(args.phonons * args.gpus)
-    per_phonon = args.ref_drift_steps_per_phonon
+    model = workload_model(args.phonons)
+    per_phonon = args.ref_drift_steps_per_phonon if args.ref_drift_steps_per_phonon > 0 else oracle_drift_steps_per_phonon(model)
     vals, secs = [], []
     kind = "reference"
     for it in range(args.warmup + args.steps):
         r = reference_cpu_run(model, args.cpu_phonons_per_core, cores, per_phonon)
-        if r is None:
+        if r is None or not r.get("drift_steps_per_s"):
             emit({"impl": "reference", "unavailable": "reference run failed"})
             return
         kind = r["kind"]
@@ -434,14 +625,14 @@ def run_reference(args):
             vals.append(r["drift_steps_per_s"])
             secs.append(r["seconds"])
     v = float(np.mean(vals))
-    sample = (f"{cores} processes x {args.cpu_phonons_per_core} phonons of the same model per step; "
-              f"{per_phonon} drift-steps per phonon (counted by the CUDA path on this model)")
+    sample = (f"{cores} processes x {args.cpu_phonons_per_core} phonons of the same model per step; {per_phonon:.2f} drift-steps per "
+              f"phonon, counted on the CPU by the restatement of the reference's event loop (oracle/sim.c) on 1e5 phonons of this model"
+              if kind == "reference" else f"oracle/sim.c with {cores} threads, counting its own drift-steps")
     emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "drift-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic 100-cell Si/Ge 2D structure (BASELINE.json configs[4]), steady-state deviational",
-                   "phonons_per_step": args.cpu_phonons_per_core * cores},
+        "config": {"workload": WORKLOAD, "phonons_per_step": args.cpu_phonons_per_core * cores},
         "cpu_baseline": {"value": v, "unit": "drift-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "drift-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -453,7 +644,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--phonons", type=int, default=100_000_000, help="phonons per GPU")
+    ap.add_argument("--phonons", type=int, default=100_000_000, help="phonons of the job IN TOTAL (sharded over the GPUs)")
     ap.add_argument("--steps-per-launch", type=int, default=0, help="0 = library default (automatic)")
     ap.add_argument("--reduce-every", type=int, default=0,
                     help="recorded measurement steps per tally all-reduce group (0 = one group per launch window of the library)")
@@ -461,8 +652,11 @@ def main():
     ap.add_argument("--warps-per-sm", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=-1, help="2 work queues (default), 0 lane-bound slots, 1 lock-step first version")
     ap.add_argument("--cpu-phonons-per-core", type=int, default=400_000)
-    ap.add_argument("--ref-drift-steps-per-phonon", type=float, default=133.0)
+    ap.add_argument("--ref-drift-steps-per-phonon", type=float, default=0.0, help="0 = count them with oracle/sim.c (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-models", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--no-kinked", action="store_true")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -1,0 +1,142 @@
+"""GPU tests added in round 2: phasor mode on the device, phonons-per-cell across shards, the Philox block budget of the
+packed kernels, the many-sensor tally path against the staged one, and the compressed cell records."""
+import numpy as np
+import pytest
+
+from psim_b200 import configs
+from psim_b200 import lib as psim
+from tests import common as T
+from tests.gpu_runner import gpu_run_case
+
+pytestmark = pytest.mark.gpu
+
+
+def test_phasor_mode_is_exact_kinematics_on_the_device():
+    """phasor_sim (phononBuilder.cpp:42-49, modelSimulator.cpp:189) through the CUDA path: every phonon leaves its wall
+    along the normal at 1000 m/s and never scatters.  In the 1000 nm bar each of the 20 sensors (50 nm = 5 measurement
+    steps of flight) therefore holds, at every recorded step, the phonons emitted during 5 steps by BOTH walls: N * 5 / 1000
+    in total, all carrying +1000 m/s of signed x-velocity (hot phonons move right, cold phonons are negative and move
+    left), no y-velocity at all, and the walls absorb everything that arrives.  (Same statement as tests/test_emu.py's
+    check of the host build of the device functions.)"""
+    model = T.load_model(configs.with_settings(configs.linear(num_phonons=200_000).to_dict(), phasor_sim=True))
+    model.prepare()
+    src, n = model.sources(4)
+    total = sum(src[i].count for i in range(n))
+    per_sensor = total * 5 / 1000.0
+    for kernel in (2, 0, 1):
+        g = psim.GpuSimulator(model.describe(), 0)
+        try:
+            g.set_option("kernel", kernel)
+            g.set_sources(src, n, 4, 0, 1)
+            g.run_steps(0, 496)
+            alive = g.alive()
+            g.run_steps(496, model.info.measurement_steps - 1)
+            e, f = g.tallies()
+        finally:
+            g.close()
+        counts = f[:, :, 0] / 1000.0
+        assert np.abs(counts - per_sensor).max() <= 3.0, kernel     # stratified births: the count is exact up to rounding
+        assert np.abs(f[:, :, 1]).max() == 0.0, kernel
+        assert np.abs(e).max() <= 0.05 * per_sensor + 3, kernel     # hot (+1) and cold (-1) phonons cancel in the energy
+        assert abs(alive - total / 10) <= 0.01 * total, kernel      # flight time across the bar is 1 ns = 100 steps
+
+
+@pytest.mark.parametrize("name", ["linear_demo", "sides_trans", "sige"])
+def test_phonons_per_cell_are_shard_invariant(name):
+    """north star: "the number of phonons per cell" is bit-exact across 1/2/4/8 GPUs.  The histogram over cells of the
+    live pool, summed over the shards, after 40 and after 400 measurement steps (windows cut at the same steps, so that
+    positions are rounded alike)."""
+    model = T.load_model(T.case_model(name), num_phonons=60_000)
+    model.prepare()
+    src, n = model.sources(7)
+
+    def histograms(shards):
+        out = []
+        for shard in range(shards):
+            g = psim.GpuSimulator(model.describe(), 0)
+            try:
+                g.set_sources(src, n, 7, shard, shards)
+                g.run_steps(0, 40)
+                h40 = g.cell_histogram().astype(np.int64)
+                a40 = g.alive()
+                g.run_steps(40, 400)
+                h400 = g.cell_histogram().astype(np.int64)
+                assert int(h40.sum()) == a40 and int(h400.sum()) == g.alive()
+            finally:
+                g.close()
+            out.append((h40, h400))
+        return sum(h[0] for h in out), sum(h[1] for h in out)
+
+    ref40, ref400 = histograms(1)
+    assert ref40.sum() > 0 and ref400.sum() > 0
+    for shards in (2, 4, 8):
+        h40, h400 = histograms(shards)
+        assert np.array_equal(h40, ref40), shards
+        assert np.array_equal(h400, ref400), shards
+
+
+def coarse_model(sim_time_ns: float, num_phonons: int):
+    """linear_demo's bar with measurement intervals of sim_time / 1000: at 10 ns per interval a high-frequency LA phonon
+    (relaxation rate ~ 4e11 / s) scatters thousands of times inside ONE interval."""
+    m = configs.linear(num_phonons=num_phonons).to_dict()
+    return configs.with_settings(m, sim_time=sim_time_ns)
+
+
+def test_random_blocks_of_a_long_interval_do_not_repeat():
+    """the packed kernels kept 10 bits of Philox block counter per (phonon, measurement step) and saturated
+    silently.  Now 13 bits: with 8 ns intervals phonons consume well over 1023 blocks per interval, and the work-queue and
+    lane-bound kernels (packed counter) must still equal the lock-step kernel (counter in a register) bit for bit."""
+    model = T.load_model(coarse_model(8000.0, 3000))
+    ref = gpu_run_case(model, 3, steps_per_launch=4, options={"kernel": 1, "tally_shared": 0}, finish=False)
+    assert ref["stats"][0]["events"] > 1200 * 3000 * 0.02  # many phonons scatter > 1023 times per interval, or the test is void
+    for opts in ({"kernel": 2, "tally_shared": 0}, {"kernel": 0, "tally_shared": 0}, {"kernel": 2, "tally_shared": 1}):
+        got = gpu_run_case(model, 3, steps_per_launch=4, options=opts, finish=False)
+        assert np.array_equal(got["energy"], ref["energy"]), opts
+        assert np.array_equal(got["fixed"], ref["fixed"]), opts
+        assert got["stats"][0]["events"] == ref["stats"][0]["events"], opts
+
+
+def test_exhausted_random_block_budget_is_an_error_not_a_repeat():
+    """Beyond 8191 blocks per (phonon, interval) the packed kernels stop with PSIM_E_RNG; the lock-step kernel runs the same
+    model to completion."""
+    model = T.load_model(coarse_model(200_000.0, 2000))
+    with pytest.raises(psim.PsimError) as err:
+        gpu_run_case(model, 3, steps_per_launch=4, options={"kernel": 2}, finish=False)
+    assert err.value.code == -8 and "random-number blocks" in err.value.message
+    ok = gpu_run_case(model, 3, steps_per_launch=4, options={"kernel": 1}, finish=False)
+    assert ok["stats"][0]["drift_steps"] > 0
+
+
+def test_many_sensor_tally_path_equals_the_staged_and_the_lane_by_lane_one():
+    """linear_sides (1000 sensors): its tallies go to global memory in difference form, posted warp-cooperatively so that
+    the three words of an entry share one L2 sector (kernels.cuh:tally_post_global).  The same integers must come out of
+    the lane-bound kernel (three REDs per lane) and the lock-step kernel, in periodic and in steady-state mode, for both
+    slot counts."""
+    for sim_type in (1, 0):
+        model = T.load_model(configs.linear_sides(num_phonons=60_000, sim_type=sim_type, step_interval=4 if sim_type else 0).to_dict())
+        ref = gpu_run_case(model, 5, steps_per_launch=16, options={"kernel": 1}, finish=False)
+        assert ref["stats"][0]["tally_in_shared"] == 3 and np.abs(ref["energy"]).sum() > 0
+        for opts in ({"kernel": 2}, {"kernel": 2, "queue_slots": 64}, {"kernel": 2, "queue_slots": 128}, {"kernel": 0}):
+            got = gpu_run_case(model, 5, steps_per_launch=16, options=opts, finish=False)
+            assert got["stats"][0]["tally_in_shared"] == 3, opts
+            assert np.array_equal(got["energy"], ref["energy"]), (sim_type, opts)
+            assert np.array_equal(got["fixed"], ref["fixed"]), (sim_type, opts)
+
+
+def test_rate_class_records_equal_per_sensor_records():
+    """The per-phonon loop reads relaxation-rate records by rate CLASS (device_types.h: DevParams::classes).  A model with
+    more than 255 distinct sensor temperatures has no classes (255 = unclassified: the sensor's own record); the first 250
+    sensors of such a model, alone, have classes.  Both must reproduce the probe of the reference's rate formulas."""
+    m = configs.ModelFile(num_measurements=200, sim_time=2, num_phonons=20_000, t_eq=300)
+    name = m.material(configs.SILICON)
+    n = 300
+    for i in range(n):
+        sid = m.sensor(name, 300.0 + 0.1 * (i % 290))
+        m.rectangle((i * 10.0, 0.0), ((i + 1) * 10.0, 50.0), sid, 1)
+    m.emit_surface((0.0, 0.0), (0.0, 50.0), 310)
+    m.emit_surface((n * 10.0, 0.0), (n * 10.0, 50.0), 290)
+    model = T.load_model(m.to_dict())
+    a = gpu_run_case(model, 2, finish=False)
+    b = gpu_run_case(model, 2, options={"kernel": 1}, finish=False)
+    assert a["stats"][0]["drift_steps"] > 0
+    assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["fixed"], b["fixed"])
