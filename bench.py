@@ -211,6 +211,22 @@ def emit(obj):
         os.write(_RESULT_FD, line)
 
 
+def agree_on_cuts(cuts, num_steps: int, world: int, rank: int, device):
+    """Every rank must cut a job into the same groups of measurement steps (each group ends with a collective).  The
+    library's launch windows depend, through the exactness bound of the tally staging, on the capacity of the rank's own
+    pool - which may differ by one phonon between ranks - so rank 0's cuts are broadcast and used by all; a rank whose own
+    windows are shorter simply needs two launches for such a group."""
+    if world == 1:
+        return list(cuts)
+    import torch
+    import torch.distributed as dist
+    t = torch.full((num_steps + 2,), -1, dtype=torch.int64, device=device)
+    if rank == 0:
+        t[:len(cuts)] = torch.tensor(cuts, dtype=torch.int64)
+    dist.broadcast(t, 0)
+    return [int(x) for x in t.tolist() if x >= 0]
+
+
 class Env:
     """Rank / device / process group of this bench process."""
 
@@ -294,10 +310,8 @@ class ShardedJob:
     def plan_cuts(self, extra_cut: int | None = None):
         """Steps whose measurement is not recorded (steady state: the first 90 %) need no exchange and go to the library
         in one call (it chooses its own launch windows); the recorded steps go in groups that end where the library's
-        launch windows end (no extra launch for the exchange; --reduce-every N asks for groups of N steps instead).  Every
-        rank must cut a job the same way (each group ends with a collective) and the library's windows depend, through the
-        exactness bound of the tally staging, on the capacity of the rank's own pool - which may differ by one phonon
-        between ranks - so rank 0's cuts are broadcast and used by all."""
+        launch windows end (no extra launch for the exchange; --reduce-every N asks for groups of N steps instead); all
+        ranks use rank 0's cuts (agree_on_cuts)."""
         args, g, M, first = self.args, self.g, self.M, self.first
         chunk = max(args.steps_per_launch, args.reduce_every) if args.reduce_every > 0 else 0
         cuts, s = [0], 0
@@ -309,14 +323,7 @@ class ShardedJob:
             cuts.append(s)
         if extra_cut is not None and extra_cut not in cuts:
             cuts = sorted(cuts + [extra_cut])
-        env = self.env
-        if env.world > 1:
-            t = env.torch.full((M + 2,), -1, dtype=env.torch.int64, device=env.device)
-            if env.rank == 0:
-                t[:len(cuts)] = env.torch.tensor(cuts, dtype=env.torch.int64)
-            env.dist.broadcast(t, 0)
-            cuts = [int(x) for x in t.tolist() if x >= 0]
-        return cuts
+        return agree_on_cuts(cuts, M, self.env.world, self.env.rank, self.env.device)
 
     def run(self, cuts, at_cut=None):
         """All measurement steps; the tally all-reduce of a group of steps is issued as soon as the group's launches are
@@ -452,34 +459,30 @@ def shipped_models():
 
 def model_walltimes(device: int):
     """BASELINE.json "wall-clock per model": every shipped configuration at its FULL phonon count, end to end through the
-    host API (psim_model_run: set-up, host -> device, kernels, device -> host, epilogue; the second of two runs, so that the
-    CUDA context and the pool exist), the kernel-only time, and the throughput in drift-steps and in flight segments."""
+    host API (ms_e2e = the whole psim_model_run: device image and pool set-up, host -> device, kernels, device -> host, run
+    epilogue - what the reference's "Time Taken" header measures), the kernel-only time, and the throughput in drift-steps and
+    in flight segments.  The process already has its CUDA context (the bench job ran first)."""
     from psim_b200 import lib as psim
     out = []
     with tempfile.TemporaryDirectory() as tmp:
         for name, model in shipped_models().items():
-            path = configs.save(configs.with_settings(model, num_runs=2), os.path.join(tmp, "m.json"))
+            path = configs.save(model, os.path.join(tmp, "m.json"))
             t0 = time.perf_counter()
             m = psim.Model(path)
             t1 = time.perf_counter()
-            st = m.run(device=device, seed=1)  # two runs through one handle
+            st = m.run(device=device, seed=1)  # psim_model_run: device image + pool set-up, H2D, kernels, D2H, run epilogue
             t2 = time.perf_counter()
-            m1 = psim.Model(path)
-            m1.set_num_runs(1)
+            m.export(path, t2 - t1)            # ss_*.txt / per_*.txt next to the model file
             t3 = time.perf_counter()
-            m1.run(device=device, seed=1)
-            t4 = time.perf_counter()
-            second_run_ms = max((t2 - t1) - (t4 - t3), 0.0) * 1e3  # the run that found the context, image and pool in place
             k_ms = st.kernel_ms
             rec = {"model": name, "phonons": int(st.total_phonons), "cells": int(m.info.num_cells), "sensors": int(m.info.num_sensors),
-                   "measurement_steps": int(m.info.measurement_steps), "sim_type": int(m.info.sim_type), "load_s": round(t1 - t0, 4),
-                   "first_run_s": round(t4 - t3, 4), "ms_e2e": round(second_run_ms, 2), "kernel_ms": round(k_ms, 2), "launches": int(st.launches),
+                   "measurement_steps": int(m.info.measurement_steps), "sim_type": int(m.info.sim_type), "load_ms": round((t1 - t0) * 1e3, 2),
+                   "ms_e2e": round((t2 - t1) * 1e3, 2), "export_ms": round((t3 - t2) * 1e3, 2), "kernel_ms": round(k_ms, 2), "launches": int(st.launches),
                    "drift_steps": int(st.drift_steps), "segments": int(st.events),
                    "drift_steps_per_s": st.drift_steps / (k_ms * 1e-3), "segments_per_s": st.events / (k_ms * 1e-3),
                    "reference_header_s": REFERENCE_HEADER_SECONDS.get(name)}
             out.append(rec)
             m.close()
-            m1.close()
     return out
 
 

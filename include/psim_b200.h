@@ -101,6 +101,10 @@ typedef struct psim_model_desc {
     double simulation_time;             /* ns */
     uint32_t full_simulation;           /* t_eq == 0 (Material::setFullSimulation) */
     uint32_t phasor_sim;
+    /* Optional (NULL = the records above hold for every step): [num_sensors][measurement_steps] per-step records of a
+     * transient run that re-iterates (TransientController after reset(false), sensorController.cpp:101-113: the relaxation
+     * rates are evaluated at steady_temps_[step] and scatter_tables_[step] is sampled, :80-88).  base_table is ignored. */
+    const psim_sensor* step_sensors;
 } psim_model_desc;
 
 #define PSIM_SRC_CELL 0u

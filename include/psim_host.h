@@ -41,6 +41,9 @@ int psim_model_get_info(const psim_model* m, psim_model_info* out);
 /* Overrides of the file's settings, for reduced-size parity runs. */
 int psim_model_set_num_phonons(psim_model* m, uint64_t n);
 int psim_model_set_num_runs(psim_model* m, uint64_t n);
+/* Iterations per run: the reference's MAX_ITERS (model.cpp:11), compiled in as 1 upstream - which leaves the re-iteration
+ * of model.cpp:159-172 (new t_eq, sensor temperatures, tables) unreachable.  Also the optional settings key "max_iters". */
+int psim_model_set_max_iters(psim_model* m, uint64_t n);
 
 /* Start of a run: temperature bounds, material tables, energy per phonon (model.cpp:145-155). */
 int psim_model_prepare(psim_model* m);
@@ -61,6 +64,10 @@ int psim_model_sources(psim_model* m, uint64_t seed, psim_source* sources, size_
 
 /* What the hot path produced (layouts of psim_gpu_get_tallies), then the run epilogue (model.cpp:163-177). */
 int psim_model_set_tallies(psim_model* m, const int32_t* energy, const double* flux);
+/* End of one simulated iteration (model.cpp:163-171): *again = 1 if the run has to be simulated once more - the model has
+ * then been reset(false) to the new temperatures and t_eq, and psim_model_describe / psim_model_sources give the next
+ * iteration's inputs.  psim_model_finish_run (storeResults) ends the iteration itself if the caller has not. */
+int psim_model_end_iteration(psim_model* m, int* again);
 int psim_model_finish_run(psim_model* m, uint64_t run_id, int* stable_sensors);
 int psim_model_next_run(psim_model* m);  /* reset(true), model.cpp:178-180 */
 

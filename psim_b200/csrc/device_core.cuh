@@ -84,11 +84,14 @@ PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) { return sen
 PSIM_HD float4 load_cell_matrix(const DevParams& P, uint32_t cell) { return load_shape_matrix(P.shapes, ldg(&P.cell_shape[cell])); }
 PSIM_HD float2 load_cell_normal(const DevParams& P, uint32_t cell, uint32_t e) { return load_shape_normal(P.shapes, ldg(&P.cell_shape[cell]), e); }
 PSIM_HD float load_cell_spec(const DevParams& P, uint32_t cell) { return ldg(&P.shapes[ldg(&P.cell_shape[cell])].spec); }
-// relaxation-rate record of the sensor area a cell word names: the record of its rate class where it has one (a
-// handful of records for the whole mesh), the sensor's own otherwise
-PSIM_HD DevSensor load_rates(const DevParams& P, uint32_t cell_word) {
-    const uint32_t cls = PSIM_CELL_CLASS(cell_word);
-    return load_sensor((cls != 255u) ? P.classes + cls : P.sensors + PSIM_CELL_SENSOR(cell_word), 0u);  // one load path, the pointer is selected
+// relaxation-rate record of the sensor area a cell word names, at measurement step `step`: the record of its rate class
+// where it has one (a handful of records for the whole mesh), the sensor's own otherwise; a transient run that re-iterates
+// has one record per (sensor, step) (TransientController::getSteadyTemp / scatterUpdate, sensorController.cpp:80-88)
+PSIM_HD DevSensor load_rates(const DevParams& P, uint32_t cell_word, uint32_t step) {
+    const uint32_t cls = PSIM_CELL_CLASS(cell_word), sensor = PSIM_CELL_SENSOR(cell_word);
+    const DevSensor* rec = (cls != 255u) ? P.classes + cls : P.sensors + sensor;
+    if (P.step_sensors != nullptr) { rec = P.step_sensors + static_cast<size_t>(sensor) * P.num_steps + min(step, P.num_steps - 1u); }
+    return load_sensor(rec, 0u);  // one load path, the pointer is selected
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -307,7 +310,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     if (src.kind == 0u) {
         p.cell = src.index;
         const uint4 info = load_cell_info(P.cells, p.cell);
-        const DevSensor s = load_rates(P, info.w);
+        const DevSensor s = load_rates(P, info.w, 0u);  // born at t = 0
         sample_table(P, s.base_table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
         float r1 = u_a, r2 = u_b;
         if (r1 + r2 > 1.f) {
@@ -340,7 +343,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     } else {
         diffuse_direction(u_b, u_c, n.x, n.y, vel, p);
     }
-    p.tts = draw_scatter_time(P, load_rates(P, info.w), p, u_d);
+    p.tts = draw_scatter_time(P, load_rates(P, info.w, step), p, u_d);
     return static_cast<float>((1. - frac) * P.step_time_d);
 }
 
@@ -535,7 +538,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
             f.sensor_mat = nsm;
             set_cell_matrix(f, load_cell_matrix(P, ncell));
             if (new_sensor) {  // the old time-to-scatter is void where the rates differ (modelSimulator.cpp:167-172,192-194)
-                p.tts = draw_scatter_time(P, load_rates(P, nsm), p, rng_u01(f.rng));
+                p.tts = draw_scatter_time(P, load_rates(P, nsm, step), p, rng_u01(f.rng));
             }
         } else {  // back into the same cell, about the true inward normal
             const float2 n = load_cell_normal(P, p.cell, e);
@@ -571,7 +574,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
 // then the rates and the time to scatter of the next one (get_scatter_info, :148-153)
 PSIM_HD void scatter_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
-    const DevSensor sen = load_rates(P, f.sensor_mat);
+    const DevSensor sen = load_rates(P, f.sensor_mat, step);
     float rn, ru, ri;
     relax_rates(sen, phonon_omega(P, p.packed), PSIM_PACK_TA(p.packed), rn, ru, ri);
     // ONE Philox block per scatter: word 0 -> bin (24 bits) + position inside the bin (8 bits), word 1 -> branch

@@ -139,6 +139,7 @@ struct DevParams {
     const DevSub* subs;
     const DevSensor* sensors;
     const DevSensor* classes;   // [<= 255] one record per rate class (PSIM_CELL_CLASS): the sensors of a class are identical
+    const DevSensor* step_sensors;  // NULL, or [n_sensors][num_steps]: per-step records of a re-iterated transient run
     const DevMaterial* materials;
     const DevEmitter* emitters;
     const DevSource* sources;

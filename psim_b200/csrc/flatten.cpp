@@ -95,19 +95,15 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
     }
 
     // sensors: fold temperature powers and unit scalings into the rate coefficients (fp64 here, fp32 on device)
-    out.sensors.resize(d.num_sensors);
-    out.sensor_temperature.resize(d.num_sensors);
-    for (uint32_t s = 0; s < d.num_sensors; ++s) {
-        const psim_sensor& in = d.sensors[s];
+    auto dev_sensor = [&](const psim_sensor& in, DevSensor& o) -> bool {
         if (in.material >= d.num_materials || in.base_table >= d.num_tables || in.scatter_table >= d.num_tables ||
             !(in.temperature > 0.)) {
-            fail(err, PSIM_E_INVALID, "sensor refers to a missing material/table or has a non-positive temperature", rc);
-            return rc;
+            return false;
         }
         const psim_material& mt = d.materials[in.material];
         const double T = in.temperature;
         const double k = 1. / PSIM_FREQ_SCALE;  // omega = k * w
-        DevSensor o{};
+        o = DevSensor{};
         o.c_la = static_cast<float>(mt.b_l * T * T * T * k * k * PER_NS);
         o.c_tn = static_cast<float>(mt.b_tn * T * T * T * T * k * PER_NS);
         o.c_tu = static_cast<float>(mt.b_tu * k * k * PER_NS);
@@ -116,8 +112,31 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         o.w_cut = static_cast<float>(mt.w * PSIM_FREQ_SCALE);
         o.scatter_table = in.scatter_table;
         o.base_table = in.base_table;
-        out.sensors[s] = o;
-        out.sensor_temperature[s] = T;
+        return true;
+    };
+    out.sensors.resize(d.num_sensors);
+    out.sensor_temperature.resize(d.num_sensors);
+    for (uint32_t s = 0; s < d.num_sensors; ++s) {
+        if (!dev_sensor(d.sensors[s], out.sensors[s])) {
+            fail(err, PSIM_E_INVALID, "sensor refers to a missing material/table or has a non-positive temperature", rc);
+            return rc;
+        }
+        out.sensor_temperature[s] = d.sensors[s].temperature;
+    }
+    // a transient run that re-iterates: one record per (sensor, measurement step)
+    if (d.step_sensors) {
+        out.step_sensors.resize(static_cast<size_t>(d.num_sensors) * d.measurement_steps);
+        for (uint32_t s = 0; s < d.num_sensors; ++s) {
+            for (uint32_t k = 0; k < d.measurement_steps; ++k) {
+                psim_sensor in = d.step_sensors[static_cast<size_t>(s) * d.measurement_steps + k];
+                in.material = d.sensors[s].material;      // a sensor area does not change its material ...
+                in.base_table = d.sensors[s].base_table;  // ... nor the table its initial phonons are drawn from
+                if (!dev_sensor(in, out.step_sensors[static_cast<size_t>(s) * d.measurement_steps + k])) {
+                    fail(err, PSIM_E_INVALID, "per-step sensor record refers to a missing table or has a non-positive temperature", rc);
+                    return rc;
+                }
+            }
+        }
     }
 
     // emitters
@@ -173,7 +192,8 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
                 classes.push_back(key);
                 out.classes.push_back(out.sensors[s]);
             }
-            sensor_class[s] = k < 255 ? static_cast<uint32_t>(k) : 255u;
+            // (per-step records: the rates change from step to step even inside one sensor area, so nothing is classified)
+            sensor_class[s] = (k < 255 && !d.step_sensors) ? static_cast<uint32_t>(k) : 255u;
         }
     }
 

@@ -16,6 +16,7 @@ struct HostImage {
     std::vector<uint32_t> cell_shape; // [cells] index into shapes
     std::vector<DevShape> shapes;     // distinct (geometry, specularity) records
     std::vector<DevSensor> classes;   // one record per rate class (at most 255)
+    std::vector<DevSensor> step_sensors;  // empty, or [sensors][steps] (psim_model_desc::step_sensors)
     std::vector<DevSub> subs;
     std::vector<DevSensor> sensors;
     std::vector<DevMaterial> materials;

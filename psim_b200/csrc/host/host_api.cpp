@@ -232,6 +232,12 @@ int psim_model_set_num_runs(psim_model* pm, uint64_t n) {
     return PSIM_OK;
 }
 
+int psim_model_set_max_iters(psim_model* pm, uint64_t n) {
+    if (!pm || n == 0) { return PSIM_E_INVALID; }
+    pm->m->max_iters = n;
+    return PSIM_OK;
+}
+
 int psim_model_prepare(psim_model* pm) {
     if (!pm) { return PSIM_E_INVALID; }
     return guarded(PSIM_E_MODEL, [&]() {
@@ -343,6 +349,15 @@ int psim_model_set_tallies(psim_model* pm, const int32_t* energy, const double* 
     return PSIM_OK;
 }
 
+int psim_model_end_iteration(psim_model* pm, int* again) {
+    if (!pm) { return PSIM_E_INVALID; }
+    return guarded(PSIM_E_STATE, [&]() {
+        const bool more = pm->m->end_iteration(nullptr);
+        if (again) { *again = more ? 1 : 0; }
+        return PSIM_OK;
+    });
+}
+
 int psim_model_finish_run(psim_model* pm, uint64_t run_id, int* stable) {
     if (!pm) { return PSIM_E_INVALID; }
     return guarded(PSIM_E_STATE, [&]() {
@@ -372,7 +387,7 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
         m.runs.clear();
         // every call starts from the state of the model file: a steady-state run leaves its final temperatures in the
         // sensors (Model::resetRequired, model.cpp:250-272), which a second call on the same handle must not inherit
-        m.reset_for_next_run();
+        m.restore_file_state();
         // several devices: their tallies are summed with one NCCL all-reduce per run over NVLink (integers: the result is the
         // one-device result bit for bit); without a usable NCCL the same integers are summed on the host
         std::unique_ptr<TallyExchange> exchange;
@@ -385,8 +400,19 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
             if (verbose) { std::cout << "Run: " << run + 1 << '\n'; }
             const auto h0 = std::chrono::steady_clock::now();
             m.prepare();
+            std::string log;
+            // the iterations of one run (model.cpp:159-172; one, unless max_iters was raised): each starts from the sensor
+            // temperatures, tables and t_eq the iteration before left behind
+            for (uint64_t iter = 0;; ++iter) {
+            if (iter > 0) {  // the device image holds the temperatures and tables of the iteration before: rebuild it
+                for (auto& g : gpus) {
+                    psim_gpu_destroy(g);
+                    g = nullptr;
+                }
+            }
             const psim_model_desc& desc = m.describe();
-            const auto sources = m.source_counts(seed + run);
+            const uint64_t run_seed = seed + run + 7919u * iter;
+            const auto sources = m.source_counts(run_seed);
             if (std::getenv("PSIM_TIMING")) {
                 std::cerr << "psim timing [ms]: prepare+describe+sources "
                           << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count() << '\n';
@@ -412,7 +438,7 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     }
                 }
                 const auto t1 = now();
-                if (!e) { e = psim_gpu_set_sources(gpus[d], sources.data(), sources.size(), seed + run, static_cast<uint32_t>(d), static_cast<uint32_t>(G)); }
+                if (!e) { e = psim_gpu_set_sources(gpus[d], sources.data(), sources.size(), run_seed, static_cast<uint32_t>(d), static_cast<uint32_t>(G)); }
                 const auto t2 = now();
                 if (!e) { e = psim_gpu_run(gpus[d]); }
                 const auto t3 = now();
@@ -477,9 +503,10 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     stats->kernel_ms = std::max(stats->kernel_ms, st[d].kernel_ms);
                 }
             }
-            const auto h1 = std::chrono::steady_clock::now();
             m.set_tallies(energy[0].data(), flux.data());
-            std::string log;
+            if (!m.end_iteration(&log)) { break; }
+            }  // iterations
+            const auto h1 = std::chrono::steady_clock::now();
             m.finish_run(run, &log);
             if (std::getenv("PSIM_TIMING")) {
                 std::cerr << "psim timing [ms]: epilogue "

@@ -108,7 +108,9 @@ private:
         ++i;
         return out;
     }
-    static Json value(const std::string& s, size_t& i) {
+    static constexpr int kMaxDepth = 64;  // model files nest four levels deep; '[[[[...' must not overflow the stack
+    static Json value(const std::string& s, size_t& i, int depth = 0) {
+        if (depth > kMaxDepth) { fail("nesting too deep", i); }
         ws(s, i);
         if (i >= s.size()) { fail("unexpected end", i); }
         Json v;
@@ -128,7 +130,7 @@ private:
                 ws(s, i);
                 if (i >= s.size() || s[i] != ':') { fail("':' expected", i); }
                 ++i;
-                v.members.emplace_back(std::move(key), value(s, i));
+                v.members.emplace_back(std::move(key), value(s, i, depth + 1));
                 ws(s, i);
                 if (i < s.size() && s[i] == ',') {
                     ++i;
@@ -150,7 +152,7 @@ private:
                 return v;
             }
             for (;;) {
-                v.items.push_back(value(s, i));
+                v.items.push_back(value(s, i, depth + 1));
                 ws(s, i);
                 if (i < s.size() && s[i] == ',') {
                     ++i;
@@ -183,9 +185,16 @@ private:
             i += 4;
             return v;
         }
+        // JSON numbers only: strtod alone would also take "nan", "inf" and hexadecimal floats
+        if (!(c == '-' || (c >= '0' && c <= '9'))) { fail("value expected", i); }
+        for (size_t k = i; k < s.size() && !(s[k] == ',' || s[k] == '}' || s[k] == ']' || s[k] == ' ' || s[k] == '\n' || s[k] == '\t' || s[k] == '\r'); ++k) {
+            const char d = s[k];
+            if (!((d >= '0' && d <= '9') || d == '-' || d == '+' || d == '.' || d == 'e' || d == 'E')) { fail("malformed number", k); }
+        }
         char* end = nullptr;
         const double d = std::strtod(s.c_str() + i, &end);
         if (end == s.c_str() + i) { fail("value expected", i); }
+        if (!(d == d) || d > 1.7976931348623157e308 || d < -1.7976931348623157e308) { fail("number out of range", i); }
         v.kind = Kind::Number;
         v.number = d;
         i = static_cast<size_t>(end - s.c_str());

@@ -25,6 +25,8 @@ constexpr float TEMP_INTERVAL = 0.1F;     // model.cpp:25
 constexpr double TEMP_BOUND_EPS = 10.;    // model.cpp:19
 constexpr double SENSOR_RESET_THRESHOLD = 0.001;    // sensorController.cpp:9
 constexpr double TRANSIENT_RESET_THRESHOLD = 0.02;  // sensorController.cpp:12
+constexpr size_t SYSTEM_RESET_THRESHOLD = 90;       // model.cpp:13: percentage of sensors that must be stable
+constexpr double TEQ_THRESHOLD = 5.;                // model.cpp:16: |delta t_eq| / t_eq in parts per thousand
 constexpr double INVERSION_EPS = 0.0001;            // sensorInterpreter.cpp:9
 constexpr std::size_t INVERSION_MAX_ITERS = 40;     // sensorInterpreter.cpp:10
 
@@ -235,12 +237,21 @@ std::unique_ptr<Model> Model::from_json_text(const std::string& text) {
     const Json& st = j.at("settings");
     const Json& ph = st.at("phasor_sim");
     m->phasor_sim = (ph.kind == Json::Kind::Bool && ph.boolean);  // reference: dump() == "true" (inputManager.cpp:18)
-    m->measurement_steps = static_cast<uint64_t>(st.at("num_measurements").num());
-    m->num_phonons = static_cast<uint64_t>(st.at("num_phonons").num());
+    // a JSON double becomes a count only if it is one: non-negative, integral after truncation as the reference's
+    // get<std::size_t>() would take it, and exactly representable (< 2^53) - the cast of anything else is undefined
+    auto count = [](const Json& v, const char* what) -> uint64_t {
+        const double d = v.num();
+        if (!(d >= 0.) || !(d < 9007199254740992.)) { throw std::runtime_error(std::string("Invalid settings: ") + what + " is not a valid count.\n"); }
+        return static_cast<uint64_t>(d);
+    };
+    m->measurement_steps = count(st.at("num_measurements"), "num_measurements");
+    m->num_phonons = count(st.at("num_phonons"), "num_phonons");
     m->simulation_time = st.at("sim_time").num();
     m->t_eq = st.at("t_eq").num();
-    if (st.contains("num_runs")) { m->num_runs = static_cast<uint64_t>(st.at("num_runs").num()); }
-    switch (static_cast<int>(st.at("sim_type").num())) {
+    if (st.contains("num_runs")) { m->num_runs = count(st.at("num_runs"), "num_runs"); }
+    if (st.contains("max_iters")) { m->max_iters = std::max<uint64_t>(1, count(st.at("max_iters"), "max_iters")); }  // extension, see model.h
+    m->t_eq_file_ = m->t_eq;
+    switch (count(st.at("sim_type"), "sim_type")) {
     case 1: m->sim_type = SimType::Periodic; break;
     case 2: m->sim_type = SimType::Transient; break;
     default: m->sim_type = SimType::SteadyState; break;
@@ -251,7 +262,7 @@ std::unique_ptr<Model> Model::from_json_text(const std::string& text) {
     // Model::setSimulationType, model.cpp:46-70
     const double M = static_cast<double>(m->measurement_steps);
     if (m->sim_type != SimType::SteadyState) {
-        m->step_interval = static_cast<uint64_t>(st.at("step_interval").num());
+        m->step_interval = count(st.at("step_interval"), "step_interval");
         m->start_step = static_cast<uint64_t>(M - M * SS_STEPS_PERCENT);
         if (m->step_interval == 0) { throw std::runtime_error("Step interval of 0 is invalid for transient and periodic simulations.\n"); }
     }
@@ -293,7 +304,7 @@ std::unique_ptr<Model> Model::from_json_text(const std::string& text) {
     std::map<uint64_t, uint32_t> sensor_index;
     for (const Json& sd : j.at("sensors").items) {
         SensorRec s{};
-        s.id = static_cast<uint64_t>(sd.at("id").num());
+        s.id = count(sd.at("id"), "sensor id");
         if (sensor_index.count(s.id)) { throw std::runtime_error("Sensor with this ID already exists\n"); }
         const auto it = material_ids.find(sd.at("material").str());
         if (it == material_ids.end()) { throw std::runtime_error("Sensor refers to a material that does not exist\n"); }
@@ -313,7 +324,7 @@ std::unique_ptr<Model> Model::from_json_text(const std::string& text) {
         point(t.at("p1"), c.x[0], c.y[0]);
         point(t.at("p2"), c.x[1], c.y[1]);
         point(t.at("p3"), c.x[2], c.y[2]);
-        const auto it = sensor_index.find(static_cast<uint64_t>(cd.at("sensorID").num()));
+        const auto it = sensor_index.find(count(cd.at("sensorID"), "sensorID"));
         if (it == sensor_index.end()) { throw std::runtime_error("Sensor does not exist\n"); }
         c.sensor = it->second;
         c.spec = cd.at("specularity").num();
@@ -513,9 +524,15 @@ void Model::prepare() {
     for (auto& m : materials) { m.set_temperature_grid(lo, hi); }
     for (auto& s : sensors) {
         s.heat_capacity = materials[s.material].base_energy(s.t_init);
-        if (sim_type == SimType::Transient) { s.steady_temps.assign(measurement_steps, s.t_init); }
+        s.table_temp = s.t_init;
+        if (sim_type == SimType::Transient) {
+            s.steady_temps.assign(measurement_steps, s.t_init);
+            s.heat_capacities.assign(measurement_steps, s.heat_capacity);
+        }
     }
     prepared_ = true;
+    iter_ = 0;
+    iteration_ended_ = false;
     refresh();
 }
 
@@ -524,7 +541,7 @@ double Model::total_initial_energy() {
     double total = 0.;
     for (const auto& c : cells) {
         const SensorRec& s = sensors[c.sensor];
-        const double init = c.area * s.heat_capacity;
+        const double init = c.area * heat_capacity_at(s, 0);
         double cell_energy = (t_eq == 0.) ? init : init * std::fabs(init_temp(s) - t_eq);  // cell.cpp:38-41
         double emit = 0.;
         for (int k = 0; k < 3; ++k) {  // cell.cpp:45-63
@@ -563,7 +580,7 @@ std::vector<psim_source> Model::source_counts(uint64_t seed) {
     for (uint32_t ci = 0; ci < cells.size(); ++ci) {
         const CellRec& c = cells[ci];
         const SensorRec& s = sensors[c.sensor];
-        const double init = c.area * s.heat_capacity;
+        const double init = c.area * heat_capacity_at(s, 0);
         const double init_energy = (t_eq == 0.) ? init : init * std::fabs(init_temp(s) - t_eq);
         if (const uint64_t n = phonons_for(init_energy); n > 0) {
             out.push_back(psim_source{ PSIM_SRC_CELL, ci, (init_temp(s) > t_eq) ? 1 : -1, 0, n });
@@ -584,6 +601,7 @@ std::vector<psim_source> Model::source_counts(uint64_t seed) {
 
 void Model::set_tallies(const int32_t* energy, const double* flux) {
     const size_t S = sensors.size(), R = recorded_steps;
+    iteration_ended_ = false;
     inc_energy_.assign(S, std::vector<int32_t>(R, 0));
     inc_flux_.assign(S, std::vector<std::array<double, 2>>(R, { 0., 0. }));
     for (size_t s = 0; s < S; ++s) {
@@ -638,8 +656,9 @@ SensorResult Model::scale_heat_params(size_t si) {
     return sm;
 }
 
-int Model::finish_run(uint64_t run_id, std::string* log) {
-    if (inc_energy_.size() != sensors.size()) { throw std::runtime_error("finish_run without tallies"); }
+bool Model::end_iteration(std::string* log) {
+    if (inc_energy_.size() != sensors.size()) { throw std::runtime_error("end of an iteration without tallies"); }
+    ++iter_;
     // Model::resetRequired, model.cpp:250-272 - note its side effect on every sensor's steady temperature
     int stable = 0;
     for (size_t si = 0; si < sensors.size(); ++si) {
@@ -662,16 +681,72 @@ int Model::finish_run(uint64_t run_id, std::string* log) {
             s.steady_temps = std::move(temps);
         }
     }
+    stable_ = stable;
     if (log) { *log += "Stable sensors: " + std::to_string(stable) + "\n"; }
+    // avgTemp(), model.cpp:230-239: area-weighted getSteadyTemp() of the sensors
+    double new_t_eq = t_eq;
+    if (t_eq != 0. && sim_type != SimType::Transient) {
+        double total_area = 0.;
+        for (const auto& s : sensors) { total_area += s.area; }
+        new_t_eq = 0.;
+        for (const auto& s : sensors) { new_t_eq += steady_temp(s) * s.area / total_area; }
+    }
+    const bool moved = (static_cast<size_t>(stable) * 100 / sensors.size() < SYSTEM_RESET_THRESHOLD) ||
+                       (std::fabs(new_t_eq - t_eq) / t_eq * 1000. > TEQ_THRESHOLD);
+    const bool again = moved && iter_ < max_iters && !phasor_sim;  // model.cpp:163
+    if (again) {
+        reset_iteration();
+        t_eq = new_t_eq;
+        if (log) {
+            std::ostringstream os;
+            os << "system not stable\nupdated t_eq: " << t_eq << "\n";
+            *log += os.str();
+        }
+    }
     refresh();  // model.cpp:171 - in steady state this changes the energy per phonon used for the output scaling
-    if (log) { *log += "System did not stabilize!!\n"; }  // MAX_ITERS = 1, model.cpp:11,173-176
+    if (!again && iter_ >= max_iters && log) { *log += "System did not stabilize!!\n"; }  // model.cpp:173-176
+    iteration_ended_ = true;
+    return again;
+}
+
+// Model::reset(false), model.cpp:274-283 -> Sensor::reset -> the controllers' reset(false), sensorController.cpp:64-113
+void Model::reset_iteration() {
+    for (auto& s : sensors) {
+        Material& mat = materials[s.material];
+        switch (sim_type) {
+        case SimType::SteadyState:  // tables and heat capacity at the steady temperature of the iteration that just ended
+            s.table_temp = s.t_steady;
+            s.heat_capacity = mat.base_energy(s.t_steady);
+            break;
+        case SimType::Periodic:     // tables only
+            s.table_temp = s.t_steady;
+            break;
+        case SimType::Transient:    // one heat capacity and one scatter table per measurement step
+            s.heat_capacities.resize(s.steady_temps.size());
+            for (size_t k = 0; k < s.steady_temps.size(); ++k) { s.heat_capacities[k] = mat.base_energy(s.steady_temps[k]); }
+            break;
+        }
+    }
+    inc_energy_.clear();
+    inc_flux_.clear();
+}
+
+int Model::finish_run(uint64_t run_id, std::string* log) {
+    if (inc_energy_.size() != sensors.size() && !iteration_ended_) { throw std::runtime_error("finish_run without tallies"); }
+    if (!iteration_ended_) {
+        // a caller that drives one iteration per run (the reference's MAX_ITERS = 1)
+        const uint64_t keep = max_iters;
+        max_iters = iter_ + 1;
+        end_iteration(log);
+        max_iters = keep;
+    }
     std::vector<SensorResult> res;
     res.reserve(sensors.size());
     for (size_t si = 0; si < sensors.size(); ++si) { res.push_back(scale_heat_params(si)); }
     std::sort(res.begin(), res.end(), [](const SensorResult& a, const SensorResult& b) { return a.id < b.id; });
     if (runs.size() <= run_id) { runs.resize(run_id + 1); }
     runs[run_id] = std::move(res);
-    return stable;
+    return stable_;
 }
 
 void Model::reset_for_next_run() {
@@ -682,6 +757,11 @@ void Model::reset_for_next_run() {
     inc_energy_.clear();
     inc_flux_.clear();
     prepared_ = false;
+}
+
+void Model::restore_file_state() {
+    t_eq = t_eq_file_;  // a re-iterated run moves t_eq (model.cpp:165); the reference keeps it for the runs that follow
+    reset_for_next_run();
 }
 
 std::vector<SensorResult> Model::averaged() const {
@@ -821,11 +901,12 @@ const psim_model_desc& Model::describe() {
         Material& m = materials[s.material];
         psim_sensor ds{};
         ds.material = s.material;
-        // SensorController::updateTables uses t_init; SteadyState/Periodic getSteadyTemp() is t_steady_, which equals
-        // t_init for the whole run because MAX_ITERS = 1 (model.cpp:11); Transient uses t_init at every step.
-        ds.base_table = table_id(m.table(Material::Base, s.t_init));
-        ds.scatter_table = table_id(m.table(Material::Scatter, s.t_init));
-        ds.temperature = (sim_type == SimType::Transient) ? s.t_init : s.t_steady;
+        // tables at table_temp: t_init (SensorController::updateTables), after a re-iteration the steady temperature
+        // (SteadyState / Periodic reset(false)); a transient controller keeps base_table_ / scatter_table_ at t_init and uses
+        // the per-step records below.  Rates at getSteadyTemp(0).
+        ds.base_table = table_id(m.table(Material::Base, s.table_temp));
+        ds.scatter_table = table_id(m.table(Material::Scatter, s.table_temp));
+        ds.temperature = steady_temp(s);
         d_sensors_.push_back(ds);
     }
     for (const auto& e : emitters) {
@@ -876,6 +957,28 @@ const psim_model_desc& Model::describe() {
     desc_.simulation_time = simulation_time;
     desc_.full_simulation = (t_eq == 0.) ? 1u : 0u;
     desc_.phasor_sim = phasor_sim ? 1u : 0u;
+    // a transient run in its second or later iteration: TransientController::getSteadyTemp(step) and scatter_tables_[step]
+    // (sensorController.cpp:80-88,101-113) differ from step to step
+    d_step_sensors_.clear();
+    if (sim_type == SimType::Transient && iter_ > 0) {
+        d_step_sensors_.reserve(sensors.size() * measurement_steps);
+        for (size_t si = 0; si < sensors.size(); ++si) {
+            const SensorRec& s = sensors[si];
+            Material& m = materials[s.material];
+            for (size_t k = 0; k < measurement_steps; ++k) {
+                psim_sensor ds = d_sensors_[si];
+                ds.temperature = (k == 0) ? s.t_init : s.steady_temps[k];
+                ds.scatter_table = table_id(m.table(Material::Scatter, s.steady_temps[k]));
+                d_step_sensors_.push_back(ds);
+            }
+        }
+        // (table_id may have appended tables: rebuild the table list)
+        d_tables_.clear();
+        for (const Table* t : table_list_) { d_tables_.push_back(psim_table{ t->cumulative.data(), t->la_fraction.data() }); }
+        desc_.num_tables = static_cast<uint32_t>(d_tables_.size());
+        desc_.tables = d_tables_.data();
+        desc_.step_sensors = d_step_sensors_.data();
+    }
     return desc_;
 }
 

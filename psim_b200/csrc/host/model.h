@@ -81,8 +81,10 @@ struct SensorRec {
     double t_init;
     double t_steady;          // SensorController::t_steady_
     double heat_capacity;     // heat_capacity_ (set from t_init by updateTables)
+    double table_temp;        // temperature base_table_ / scatter_table_ are taken at: t_init, after a re-iteration t_steady
     double area = 0.;
-    std::vector<double> steady_temps;  // transient controller only
+    std::vector<double> steady_temps;     // transient controller only: steady_temps_[step]
+    std::vector<double> heat_capacities;  // transient controller only: heat_capacities_[step]
 };
 
 struct EmitRec {
@@ -104,6 +106,9 @@ class Model {
 public:
     // settings (inputManager.cpp:17-30)
     uint64_t num_runs = 1, measurement_steps = 0, num_phonons = 0;
+    // Iterations per run (the reference's MAX_ITERS, model.cpp:11: compiled in as 1, which leaves its re-iteration - new
+    // t_eq, new sensor temperatures and tables, model.cpp:159-172 - unreachable; here a setting, settings key "max_iters")
+    uint64_t max_iters = 1;
     double simulation_time = 0., t_eq = 0.;
     bool phasor_sim = false;
     SimType sim_type = SimType::SteadyState;
@@ -127,7 +132,13 @@ public:
     void refresh();                                   // the `refresh` lambda, model.cpp:148-153
     std::vector<psim_source> source_counts(uint64_t seed);   // initPhononBuilders' integer bookkeeping
     void set_tallies(const int32_t* energy, const double* flux);   // [S][R], [S][R][2] (what the hot path produced)
-    int finish_run(uint64_t run_id, std::string* log);             // model.cpp:163-177; returns stable-sensor count
+    // End of one simulated iteration (model.cpp:163-171): resetRequired(); if the sensors or t_eq moved and max_iters
+    // allows another iteration, reset(false) - tallies cleared, tables and heat capacities at the new temperatures - and the
+    // new t_eq; then refresh().  Returns true if the run must be simulated again (with a fresh describe()).
+    bool end_iteration(std::string* log);
+    int finish_run(uint64_t run_id, std::string* log);             // model.cpp:173-177 (ends the iteration first if the caller
+                                                                   // has not); returns the stable-sensor count
+    void restore_file_state();                                     // t_eq and sensors as the model file gives them
     void reset_for_next_run();                                     // reset(true), model.cpp:178-180,274-283
 
     // flat description for psim_gpu_create (pointers stay valid until the next prepare())
@@ -145,7 +156,12 @@ public:
 private:
     double temp_lo_ = 0., temp_hi_ = 0., lb_ = 0., ub_ = 0.;
     double eff_energy_ = 0.;
+    double t_eq_file_ = 0.;
     bool prepared_ = false;
+    bool iteration_ended_ = false;  // end_iteration() has consumed the tallies set last
+    uint64_t iter_ = 0;             // iterations of the current run simulated so far
+    int stable_ = 0;
+    std::vector<psim_sensor> d_step_sensors_;
     std::vector<std::vector<int32_t>> inc_energy_;                  // [S][R]
     std::vector<std::vector<std::array<double, 2>>> inc_flux_;      // [S][R]
 
@@ -164,7 +180,11 @@ private:
 
     void build_geometry();
     void attach_emit_surface(double p1x, double p1y, double p2x, double p2y, double temp, double duration, double start);
-    double heat_capacity_at(const SensorRec& s, size_t step) const { (void)step; return s.heat_capacity; }
+    double heat_capacity_at(const SensorRec& s, size_t step) const {  // getHeatCapacity(step), sensorController.h:62,80,96
+        return (sim_type == SimType::Transient && step < s.heat_capacities.size()) ? s.heat_capacities[step] : s.heat_capacity;
+    }
+    double steady_temp(const SensorRec& s) const { return sim_type == SimType::Transient ? s.t_init : s.t_steady; }  // getSteadyTemp(0)
+    void reset_iteration();                                                   // Model::reset(false), model.cpp:274-283
     double init_temp(const SensorRec& s) const;
     std::vector<double> find_temperature(size_t sensor, size_t start_step);   // sensorInterpreter.cpp:80-112
     SensorResult scale_heat_params(size_t sensor);                            // sensorInterpreter.cpp:19-66

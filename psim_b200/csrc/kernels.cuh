@@ -558,18 +558,6 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
     tally_flush(a, acc_e, acc_f);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// drift_kernel_queues<NS>: the same work as drift_kernel_slots with the binding between slots and lanes removed.
-//
-// In the slots kernel a lane can only work on its own K slots, so a pass runs with the lanes that happen to hold a
-// slot of the chosen kind (ncu: 26 of 32 for flights, 21-22 for scatters and walls, 19.7 on average).  Here a warp
-// owns NS slots ([field][slot] in shared memory) and ONE QUEUE OF SLOT NUMBERS PER KIND of work; a pass pops up to 32
-// entries of the fullest queue - lane i takes the i-th - so every kind runs with all 32 lanes as soon as 32 slots
-// want it, and rare kinds simply wait in their queue until then.  Queue heads and counts are warp-uniform registers:
-// choosing the kind costs no ballot.  Pushing into the queue of the next kind is a ballot + popc rank.  The price is
-// shared-memory bank conflicts (32 arbitrary slot numbers per access instead of lane == bank), paid on the LSU pipe,
-// which has headroom, not on the issue slots, which have none.
-// ---------------------------------------------------------------------------------------------------------------
 enum : int { Q_FLY = 0, Q_SCT, Q_WALL, Q_FIN, Q_FREE, Q_COUNT };
 __host__ __device__ constexpr uint32_t ring_capacity(int slots) {
     uint32_t c = 32;
@@ -577,7 +565,7 @@ __host__ __device__ constexpr uint32_t ring_capacity(int slots) {
     return c;
 }
 #ifndef PSIM_FLY_FRONT
-#define PSIM_FLY_FRONT 1
+#define PSIM_FLY_FRONT 0
 #endif
 
 // Slot storage of the work-queue kernel: three 16-byte groups per slot, [group][slot], so that a pass moves a slot with two
@@ -594,13 +582,39 @@ enum : int { TALLY_NONE = 0,     // the window ends before the first recorded st
              TALLY_GLOBAL = 2 }; // difference rows in global memory (tally_shared 3), posted warp-cooperatively: tally_post_global
 constexpr uint32_t kPostScratchBytes = 64u * 16u;  // per warp: up to two posts per lane
 
+// Shared memory is addressed with 32-bit shared-window addresses and explicit ld.shared / st.shared: with generic pointers
+// the compiler rebuilt the window base (S2R SR_CgaCtaId + LEA) at most access sites of this register-tight kernel.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 // Many-sensor models (no staging): a flight segment posts +v into the entry of the first recorded step it crossed and -v
 // behind the last (difference form, tally_range).  One entry = one 32-byte sector of `a.tally_acc`: int64 (e, fx, fy, -).
 // Posted lane by lane that is three REDs to three different words of one sector from the SAME lane, which the L2 sees as
 // three sector operations (ncu, round 1: 26 sectors per RED instruction, 38 % of the L2 RED peak at 33 % issue activity).
-// Here the warp first compacts its posts into shared memory, then lane v handles component v % 3 of post v / 3: the three
-// words of an entry are touched by three neighbouring lanes of ONE RED instruction and reach the L2 as one sector.
-__device__ __forceinline__ void tally_post_global(const LaunchArgs& a, uint4* scratch, uint32_t lane, uint32_t lt_mask, bool has,
+// Here the warp first compacts its posts into shared memory, then lanes 3 j, 3 j + 1, 3 j + 2 post the three words of one
+// entry with ONE RED instruction, which reaches the L2 as one sector (ten posts per instruction; lanes 30, 31 idle).
+__device__ __forceinline__ void tally_post_global(const LaunchArgs& a, uint32_t scratch, uint32_t lane, uint32_t lt_mask, bool has,
                                                   uint32_t k0, uint32_t k1, uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
     const uint32_t S = a.P.n_sensors, F = a.P.first_tally_step;
     const uint32_t r0 = k0 + 1u - F, r1 = k1 + 1u - F;
@@ -608,18 +622,38 @@ __device__ __forceinline__ void tally_post_global(const LaunchArgs& a, uint4* sc
     const unsigned m0 = __ballot_sync(0xFFFFFFFFu, has), m1 = __ballot_sync(0xFFFFFFFFu, has_end);
     if (m0 == 0u) { return; }  // warp-uniform
     const uint32_t n0 = __popc(m0), n = n0 + __popc(m1);
-    if (has) { scratch[__popc(m0 & lt_mask)] = make_uint4(r0 * S + sensor, static_cast<uint32_t>(e), static_cast<uint32_t>(fx), static_cast<uint32_t>(fy)); }
-    if (has_end) { scratch[n0 + __popc(m1 & lt_mask)] = make_uint4(r1 * S + sensor, static_cast<uint32_t>(-e), static_cast<uint32_t>(-fx), static_cast<uint32_t>(-fy)); }
+    if (has) { sts128u(scratch + 16u * __popc(m0 & lt_mask), make_uint4(r0 * S + sensor, static_cast<uint32_t>(e), static_cast<uint32_t>(fx), static_cast<uint32_t>(fy))); }
+    if (has_end) { sts128u(scratch + 16u * (n0 + __popc(m1 & lt_mask)), make_uint4(r1 * S + sensor, static_cast<uint32_t>(-e), static_cast<uint32_t>(-fx), static_cast<uint32_t>(-fy))); }
     __syncwarp();
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(scratch);
-    for (uint32_t v = lane; v < 3u * n; v += 32u) {
-        const uint32_t post = v / 3u, c = v - 3u * post;
-        const uint32_t entry = words[4u * post];
-        const long long val = static_cast<long long>(static_cast<int32_t>(words[4u * post + 1u + c]));
-        atomic_add_i64(a.tally_acc + 4u * static_cast<size_t>(entry) + c, val);
+    const uint32_t group = (lane * 11u) >> 5, comp = lane - 3u * group;  // lane / 3 and lane % 3 for lane < 32
+    if (lane < 30u) {
+        for (uint32_t post = group; post < n; post += 10u) {
+            const uint32_t entry = lds32(scratch + 16u * post);
+            const long long val = static_cast<long long>(static_cast<int32_t>(lds32(scratch + 16u * post + 4u + 4u * comp)));
+            atomic_add_i64(a.tally_acc + (static_cast<size_t>(entry) * 4u + comp), val);
+        }
     }
     __syncwarp();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// drift_kernel_queues<NS, TALLY>: a warp owns NS slots in shared memory and ONE QUEUE OF SLOT NUMBERS PER KIND of work; a pass
+// pops up to 32 entries of the fullest queue - lane i takes the i-th - so every kind runs with all 32 lanes as soon as 32
+// slots want it, and rare kinds wait in their queue until then.  Queue heads and counts are warp-uniform registers: choosing
+// the kind costs no ballot.  (The version before, drift_kernel_slots, bound K slots to each lane: a pass ran with the lanes
+// that happened to hold a slot of the chosen kind, 19.7 of 32 on average against 26 here.)
+//
+// Every kind of work except the write-back is followed by a free flight of the same phonon, so every pass ENDS with the
+// flight segment of its lanes ("fetch, then fly", "scatter, then fly", "wall, then fly") instead of sending them through the
+// flight queue: the state is still in registers, and a pass's fixed costs - choosing the queue, pop, slot loads / stores,
+// the push - are paid once per two events.  Only a pass that runs with at least kFuseLanes lanes does so: a sparse pass (a
+// rare kind on a mesh with few slots per warp) hands its slots to the flight queue, where they fly in a full pass (fusing
+// unconditionally cost 10 % more instructions on the kinked wire, whose scatter passes run with 12 lanes on average).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef PSIM_FUSE_LANES
+#define PSIM_FUSE_LANES 24
+#endif
+constexpr uint32_t kFuseLanes = PSIM_FUSE_LANES;
 
 template<int NS, int TALLY>
 __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const __grid_constant__ LaunchArgs a) {
@@ -634,11 +668,11 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const size_t tally_bytes = (TALLY == TALLY_STAGED && tally_staged(a)) ? tally_stage_bytes(a.tally_shared, nst, P.n_sensors) : 0;
-    unsigned char* base = smem_raw + ((tally_bytes + 127) & ~static_cast<size_t>(127));
-    float4* sv = reinterpret_cast<float4*>(base) + warp * (SG_COUNT * NS);
-    unsigned char* qb = base + static_cast<size_t>(kWarpsPerBlock) * SG_COUNT * NS * 16 + warp * (Q_COUNT * QC);
-    uint4* post = reinterpret_cast<uint4*>(base + static_cast<size_t>(kWarpsPerBlock) * (SG_COUNT * NS * 16 + Q_COUNT * QC) + warp * kPostScratchBytes);
-    auto grp = [&](int g, uint32_t k) -> float4& { return sv[g * NS + k]; };
+    const uint32_t base = smem_u32(smem_raw) + static_cast<uint32_t>((tally_bytes + 127) & ~static_cast<size_t>(127));
+    const uint32_t sv = base + warp * (SG_COUNT * NS * 16u);                                                  // slot groups
+    const uint32_t qb = base + kWarpsPerBlock * (SG_COUNT * NS * 16u) + warp * (Q_COUNT * QC);                // queue rings (bytes)
+    const uint32_t post = base + kWarpsPerBlock * (SG_COUNT * NS * 16u + Q_COUNT * QC) + warp * kPostScratchBytes;  // tally_post_global
+    auto grp = [&](int g, uint32_t k) -> uint32_t { return sv + (g * NS + k) * 16u; };
     struct Queue {
         uint32_t head, count;
     };
@@ -646,17 +680,12 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     // lane i takes the i-th of the first `take` entries
     auto pop = [&](Queue& q, int qi, uint32_t take, bool& active) -> uint32_t {
         active = lane < take;
-        const uint32_t k = active ? qb[qi * QC + ((q.head + lane) & (QC - 1u))] : 0u;
+        const uint32_t k = active ? lds8(qb + qi * QC + ((q.head + lane) & (QC - 1u))) : 0u;
         q.head += take;
         q.count -= take;
         return k;
     };
-    auto push = [&](Queue& q, int qi, bool mine, uint32_t k) {
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
-        if (mine) { qb[qi * QC + ((q.head + q.count + __popc(m & lt_mask)) & (QC - 1u))] = static_cast<unsigned char>(k); }
-        q.count += __popc(m);
-    };
-    for (uint32_t i = lane; i < NS; i += 32u) { qb[Q_FREE * QC + i] = static_cast<unsigned char>(i); }
+    for (uint32_t i = lane; i < NS; i += 32u) { sts8(qb + Q_FREE * QC + i, i); }
 
     const uint32_t w = blockIdx.x * kWarpsPerBlock + warp;
     const uint32_t W = a.n_warps;
@@ -671,27 +700,109 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     uint32_t n_steps = 0, n_events = 0, n_absorbed = 0;
     bool overflow = false, rng_over = false;
 
+    // One free-flight segment of the phonon in slot k, whose state the caller holds in registers (`have_vel`: including the
+    // SG_VEL group, which the caller then also wants stored): to the next edge / scatter / end of the launch window.  The
+    // frequent kind of impact - a whole-edge transition into a cell with the same material and rates - is done at once and
+    // the slot keeps flying; the recorded measurement events crossed on the way are tallied after the segment, when the warp
+    // has converged again.  Returns the queue the slot goes to next.  Called by all 32 lanes.
+    auto fly = [&](bool act, uint32_t k, psim::Phonon& p, psim::Flight& f, uint32_t misc, const bool have_vel) -> int {
+        int dest = -1;
+        uint32_t tk0 = 0, tk1 = 0, sensor = 0;  // recorded steps [tk0, tk1) that ended during this segment
+        if (act) {
+            f.edge = 0u;
+            f.ncoll = PSIM_MISC_NCOLL(misc);
+            f.rng.block = PSIM_MISC_BLOCK(misc);
+            const uint32_t s0 = a.step_begin + PSIM_MISC_STEP(misc);
+            uint32_t s = s0;
+            const uint32_t cell0 = p.cell;
+            const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
+                if (TALLY != TALLY_NONE) {
+                    tk0 = k0;
+                    tk1 = k1;
+                }
+            });
+            ++n_events;
+            // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
+            // block): only the step survives in the packed word; otherwise only the edge changes
+            misc = ((s != s0) ? (s - a.step_begin) : (misc & ~(3u << 17))) | (f.edge << 17);
+            const bool hit = ev == psim::EV_IMPACT;
+            if (hit || tk1 > tk0) {
+                const uint4 info = psim::load_cell_info(P.cells, cell0);  // the cell the segment was flown in
+                if (!have_vel) {
+                    const float4 g2 = lds128(grp(SG_VEL, k));
+                    p.dx = g2.x;
+                    p.dy = g2.y;
+                    p.packed = __float_as_uint(g2.z);
+                }
+                sensor = PSIM_CELL_SENSOR(info.w);
+                if (hit) {
+                    f.sensor_mat = info.w;
+                    if (psim::fast_transition(P, p, f, info)) {
+                        misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
+                        dest = Q_FLY;
+                    } else {
+                        dest = Q_WALL;
+                    }
+                }
+            }
+            if (!hit) { dest = (ev == psim::EV_SCATTER) ? Q_SCT : Q_FIN; }
+            sts128(grp(SG_POS, k), make_float4(p.b1, p.b2, f.r1, f.r2));
+            sts128(grp(SG_TIME, k), make_float4(p.tts, f.t, __uint_as_float(misc), __uint_as_float(p.cell)));
+            if (have_vel) { sts128(grp(SG_VEL, k), make_float4(p.dx, p.dy, __uint_as_float(p.packed), __uint_as_float(p.id_lo))); }
+        }
+        if (TALLY != TALLY_NONE) {
+            const bool has = tk1 > tk0;
+            const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
+            const int32_t fx = psim::flux_fixed(p.dx) * sg, fy = psim::flux_fixed(p.dy) * sg;
+            if (TALLY == TALLY_GLOBAL) {
+                tally_post_global(a, post, lane, lt_mask, has, tk0, tk1, sensor, sg, fx, fy);
+            } else if (has) {
+                tally_range(a, acc_e, acc_f, tk0, tk1, sensor, sg, fx, fy);
+            }
+        }
+        return dest;
+    };
+
+    // a sparse pass: the state goes back to the slot and the slot to the flight queue
+    auto park = [&](bool act, uint32_t k, const psim::Phonon& p, const psim::Flight& f, uint32_t misc) -> int {
+        if (act) {
+            sts128(grp(SG_POS, k), make_float4(p.b1, p.b2, f.r1, f.r2));
+            sts128(grp(SG_TIME, k), make_float4(p.tts, f.t, __uint_as_float(misc), __uint_as_float(p.cell)));
+            sts128(grp(SG_VEL, k), make_float4(p.dx, p.dy, __uint_as_float(p.packed), __uint_as_float(p.id_lo)));
+        }
+        return act ? Q_FLY : -1;
+    };
+
     for (;;) {
         __syncwarp();  // slot words and queue entries written by other lanes in the previous pass
         const uint32_t c_fly = min(q_fly.count, 32u), c_wall = min(q_wall.count, 32u), c_sct = min(q_sct.count, 32u);
         const uint32_t c_fin = min(q_fin.count, 32u), c_acq = min(min(q_free.count, total - next), 32u);
         const uint32_t best = max(max(c_fly, c_wall), max(max(c_sct, c_fin), c_acq));
         if (best == 0u) { break; }
+        const bool fuse = best >= kFuseLanes;  // warp-uniform
         bool act;
+        uint32_t k;
+        int dest = -1;
         // the fullest queue runs; ties go to the rarer kinds (they waited longest to get there)
         if (c_sct == best) {
-            // ---- intrinsic scatter
-            const uint32_t k = pop(q_sct, Q_SCT, c_sct, act);
+            // ---- intrinsic scatter, then fly
+            k = pop(q_sct, Q_SCT, c_sct, act);
+            psim::Phonon p;
+            psim::Flight f;
+            uint32_t misc = 0;
+            p.dx = p.dy = 0.f;
+            p.packed = 0u;
             if (act) {
-                const float4 g1 = grp(SG_TIME, k), g2 = grp(SG_VEL, k);
-                psim::Phonon p;
-                psim::Flight f;
+                const float4 g0 = lds128(grp(SG_POS, k)), g1 = lds128(grp(SG_TIME, k)), g2 = lds128(grp(SG_VEL, k));
+                p.b1 = g0.x;
+                p.b2 = g0.y;
+                f.t = g1.y;
+                misc = __float_as_uint(g1.z);
+                p.cell = __float_as_uint(g1.w);
                 p.dx = g2.x;
                 p.dy = g2.y;
                 p.packed = __float_as_uint(g2.z);
                 p.id_lo = __float_as_uint(g2.w);
-                p.cell = __float_as_uint(g1.w);
-                uint32_t misc = __float_as_uint(g1.z);
                 psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
@@ -700,26 +811,26 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
                 rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
                 misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
-                grp(SG_VEL, k) = make_float4(p.dx, p.dy, __uint_as_float(p.packed), g2.w);
-                grp(SG_TIME, k) = make_float4(p.tts, g1.y, __uint_as_float(misc), g1.w);
-                *reinterpret_cast<float2*>(&grp(SG_POS, k).z) = make_float2(f.r1, f.r2);
             }
-            push(q_fly, Q_FLY, act, k);
+            dest = fuse ? fly(act, k, p, f, misc, true) : park(act, k, p, f, misc);
         } else if (c_wall == best) {
             // ---- surface interaction, general case: wall (specular / diffuse), emitting surface, material interface,
-            //      transition into a sensor area with other rates, partial edges, stuck-phonon guard
-            const uint32_t k = pop(q_wall, Q_WALL, c_wall, act);
-            bool dead = false;
+            //      transition into a sensor area with other rates, partial edges, stuck-phonon guard; then fly
+            k = pop(q_wall, Q_WALL, c_wall, act);
+            psim::Phonon p;
+            psim::Flight f;
+            uint32_t misc = 0;
+            bool alive = false;
+            p.dx = p.dy = 0.f;
+            p.packed = 0u;
             if (act) {
-                const float4 g0 = grp(SG_POS, k), g1 = grp(SG_TIME, k), g2 = grp(SG_VEL, k);
-                psim::Phonon p;
-                psim::Flight f;
+                const float4 g0 = lds128(grp(SG_POS, k)), g1 = lds128(grp(SG_TIME, k)), g2 = lds128(grp(SG_VEL, k));
                 p.b1 = g0.x;
                 p.b2 = g0.y;
                 f.r1 = g0.z;
                 f.r2 = g0.w;
                 p.tts = g1.x;
-                uint32_t misc = __float_as_uint(g1.z);
+                misc = __float_as_uint(g1.z);
                 p.cell = __float_as_uint(g1.w);
                 p.dx = g2.x;
                 p.dy = g2.y;
@@ -730,7 +841,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 f.ncoll = PSIM_MISC_NCOLL(misc);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
-                f.t = 0.f;
+                f.t = g1.y;
                 psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
@@ -739,38 +850,39 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 if (ev == psim::EV_DEAD) {
                     ++n_steps;
                     ++n_absorbed;
-                    dead = true;
                 } else {
+                    alive = true;
                     misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), f.ncoll, PSIM_MISC_EDGE(misc), f.rng.block);
-                    grp(SG_POS, k) = make_float4(p.b1, p.b2, f.r1, f.r2);
-                    grp(SG_TIME, k) = make_float4(p.tts, g1.y, __uint_as_float(misc), __uint_as_float(p.cell));
-                    *reinterpret_cast<float2*>(&grp(SG_VEL, k)) = make_float2(p.dx, p.dy);
                 }
             }
-            push(q_fly, Q_FLY, act && !dead, k);
-            push(q_free, Q_FREE, act && dead, k);
+            dest = fuse ? fly(alive, k, p, f, misc, true) : park(alive, k, p, f, misc);
+            if (act && !alive) { dest = Q_FREE; }
         } else if (c_fin == best) {
             // ---- write-back of phonons that reached the end of the launch window (compacted, coalesced)
-            const uint32_t k = pop(q_fin, Q_FIN, c_fin, act);
+            k = pop(q_fin, Q_FIN, c_fin, act);
             if (act) {
                 const uint32_t slot = n_out + lane;
                 if (slot < a.seg_cap) {
-                    const float4 g0 = grp(SG_POS, k), g1 = grp(SG_TIME, k), g2 = grp(SG_VEL, k);
+                    const float4 g0 = lds128(grp(SG_POS, k)), g1 = lds128(grp(SG_TIME, k)), g2 = lds128(grp(SG_VEL, k));
                     a.out_a[seg + slot] = make_float4(g0.x, g0.y, g2.x, g2.y);
                     a.out_b[seg + slot] = make_uint4(__float_as_uint(g1.x), __float_as_uint(g2.z), __float_as_uint(g1.w), __float_as_uint(g2.w));
                 } else {
                     overflow = true;
                 }
+                dest = Q_FREE;
             }
             n_out += c_fin;
-            push(q_free, Q_FREE, act, k);
         } else if (c_acq == best) {
-            // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots
-            const uint32_t k = pop(q_free, Q_FREE, c_acq, act);
+            // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots, then fly
+            k = pop(q_free, Q_FREE, c_acq, act);
+            psim::Phonon p;
+            psim::Flight f;
+            uint32_t misc = 0;
             bool got = false;
+            p.dx = p.dy = 0.f;
+            p.packed = 0u;
             if (act) {
                 const uint32_t idx = next + lane;
-                psim::Phonon p;
                 uint32_t s = a.step_begin;
                 float t_begin = P.step_time;
                 if (idx < n_in) {
@@ -785,109 +897,60 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                     }
                 }
                 if (got) {
-                    psim::Flight f;
                     psim::interval_begin(P, p, f, t_begin, s);
-                    grp(SG_POS, k) = make_float4(p.b1, p.b2, f.r1, f.r2);
-                    grp(SG_TIME, k) = make_float4(p.tts, f.t, __uint_as_float(s - a.step_begin), __uint_as_float(p.cell));
-                    grp(SG_VEL, k) = make_float4(p.dx, p.dy, __uint_as_float(p.packed), __uint_as_float(p.id_lo));
+                    misc = s - a.step_begin;
                 }
             }
             next += c_acq;
-            push(q_fly, Q_FLY, got, k);
-            push(q_free, Q_FREE, act && !got, k);
+            dest = fuse ? fly(got, k, p, f, misc, true) : park(got, k, p, f, misc);
+            if (act && !got) { dest = Q_FREE; }
         } else {
-            // ---- one free-flight segment: to the next edge / scatter / end of the launch window; the recorded measurement
-            //      events it crosses on the way are tallied after the segment, when the warp has converged again
-            const uint32_t k = pop(q_fly, Q_FLY, c_fly, act);
-            int dest = -1;
-            uint32_t tk0 = 0, tk1 = 0, sensor = 0;  // recorded steps [tk0, tk1) that ended during this segment
-            float vx = 0.f, vy = 0.f;
-            uint32_t packed = 0;
+            // ---- fly: slots that entered a neighbour cell
+            k = pop(q_fly, Q_FLY, c_fly, act);
+            psim::Phonon p;
+            psim::Flight f;
+            uint32_t misc = 0;
+            p.dx = p.dy = 0.f;
+            p.packed = 0u;
             if (act) {
-                const float4 g0 = grp(SG_POS, k), g1 = grp(SG_TIME, k);
-                psim::Phonon p;
-                psim::Flight f;
+                const float4 g0 = lds128(grp(SG_POS, k)), g1 = lds128(grp(SG_TIME, k));
                 p.b1 = g0.x;
                 p.b2 = g0.y;
                 f.r1 = g0.z;
                 f.r2 = g0.w;
                 p.tts = g1.x;
                 f.t = g1.y;
-                uint32_t misc = __float_as_uint(g1.z);
+                misc = __float_as_uint(g1.z);
                 p.cell = __float_as_uint(g1.w);
-                f.edge = 0u;
-                f.ncoll = PSIM_MISC_NCOLL(misc);
-                f.rng.block = PSIM_MISC_BLOCK(misc);
-                const uint32_t s0 = a.step_begin + PSIM_MISC_STEP(misc);
-                uint32_t s = s0;
-                const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
-                    if (TALLY != TALLY_NONE) {
-                        tk0 = k0;
-                        tk1 = k1;
-                    }
-                });
-                ++n_events;
-                // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
-                // block): only the step survives in the packed word; otherwise only the edge changes
-                misc = ((s != s0) ? (s - a.step_begin) : (misc & ~(3u << 17))) | (f.edge << 17);
-                const bool hit = ev == psim::EV_IMPACT;
-                if (hit || tk1 > tk0) {
-                    const uint4 info = psim::load_cell_info(P.cells, p.cell);  // the cell the segment was flown in
-                    const float4 g2 = grp(SG_VEL, k);
-                    sensor = PSIM_CELL_SENSOR(info.w);
-                    vx = g2.x;
-                    vy = g2.y;
-                    packed = __float_as_uint(g2.z);
-                    if (hit) {
-                        // the frequent case - a whole-edge transition into a cell with the same material and rates - is done
-                        // at once, and the slot keeps flying; anything else waits for the general surface-interaction kind
-                        p.dx = vx;
-                        p.dy = vy;
-                        f.sensor_mat = info.w;
-                        if (psim::fast_transition(P, p, f, info)) {
-                            misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
-                            dest = Q_FLY;
-                        } else {
-                            dest = Q_WALL;
-                        }
-                    }
-                }
-                if (!hit) { dest = (ev == psim::EV_SCATTER) ? Q_SCT : Q_FIN; }
-                grp(SG_POS, k) = make_float4(p.b1, p.b2, f.r1, f.r2);
-                grp(SG_TIME, k) = make_float4(p.tts, f.t, __uint_as_float(misc), __uint_as_float(p.cell));
             }
-            if (TALLY != TALLY_NONE) {
-                const bool has = tk1 > tk0;
-                const int32_t sg = PSIM_PACK_NEG(packed) ? -1 : 1;
-                const int32_t fx = psim::flux_fixed(vx) * sg, fy = psim::flux_fixed(vy) * sg;
-                if (TALLY == TALLY_GLOBAL) {
-                    tally_post_global(a, post, lane, lt_mask, has, tk0, tk1, sensor, sg, fx, fy);
-                } else if (has) {
-                    tally_range(a, acc_e, acc_f, tk0, tk1, sensor, sg, fx, fy);
-                }
-            }
-            // four-way push with one address computation (selects on warp-uniform values, no branches)
-            const bool d_fly = dest == Q_FLY, d_sct = dest == Q_SCT, d_wall = dest == Q_WALL, d_fin = dest == Q_FIN;
-            const unsigned m_fly = __ballot_sync(0xFFFFFFFFu, d_fly), m_sct = __ballot_sync(0xFFFFFFFFu, d_sct);
-            const unsigned m_wall = __ballot_sync(0xFFFFFFFFu, d_wall), m_fin = __ballot_sync(0xFFFFFFFFu, d_fin);
-            const uint32_t n_fly = __popc(m_fly), n_sct = __popc(m_sct), n_wall = __popc(m_wall), n_fin = __popc(m_fin);
-#if PSIM_FLY_FRONT
-            // a slot that just entered a neighbour cell goes to the FRONT of the flight queue: its next segment runs
-            // while the cell record that the transition loaded is still in L1
-            q_fly.head -= n_fly;
-            const uint32_t t_fly = q_fly.head;
-#else
-            const uint32_t t_fly = q_fly.head + q_fly.count;
-#endif
-            const uint32_t t_sct = q_sct.head + q_sct.count, t_wall = q_wall.head + q_wall.count, t_fin = q_fin.head + q_fin.count;
-            const unsigned peers = d_fly ? m_fly : (d_sct ? m_sct : (d_wall ? m_wall : m_fin));
-            const uint32_t tail = d_fly ? t_fly : (d_sct ? t_sct : (d_wall ? t_wall : t_fin));
-            if (dest >= 0) { qb[dest * QC + ((tail + __popc(peers & lt_mask)) & (QC - 1u))] = static_cast<unsigned char>(k); }
-            q_fly.count += n_fly;
-            q_sct.count += n_sct;
-            q_wall.count += n_wall;
-            q_fin.count += n_fin;
+            dest = fly(act, k, p, f, misc, false);
         }
+        // five-way push with one address computation (selects on warp-uniform values, no branches)
+        const bool d_fly = dest == Q_FLY, d_sct = dest == Q_SCT, d_wall = dest == Q_WALL, d_fin = dest == Q_FIN, d_free = dest == Q_FREE;
+        const unsigned m_fly = __ballot_sync(0xFFFFFFFFu, d_fly), m_sct = __ballot_sync(0xFFFFFFFFu, d_sct);
+        const unsigned m_wall = __ballot_sync(0xFFFFFFFFu, d_wall), m_fin = __ballot_sync(0xFFFFFFFFu, d_fin);
+        const unsigned m_free = __ballot_sync(0xFFFFFFFFu, d_free);
+        const uint32_t n_fly = __popc(m_fly), n_sct = __popc(m_sct), n_wall = __popc(m_wall), n_fin = __popc(m_fin), n_free = __popc(m_free);
+#if PSIM_FLY_FRONT
+        // (round 1) a slot that just entered a neighbour cell goes to the FRONT of the flight queue, so that its next segment
+        // runs while the cell record the transition loaded is still in L1.  With 20-byte cell records the mesh stays in L1
+        // anyway and plain FIFO order is as fast or faster (same box, front / FIFO: linear_demo 12.2 / 11.1 ms, linear_sides
+        // periodic 20.6 / 20.1, Si/Ge 74.4 / 74.2, kinked 218.7 / 217.6), so this is off.
+        q_fly.head -= n_fly;
+        const uint32_t t_fly = q_fly.head;
+#else
+        const uint32_t t_fly = q_fly.head + q_fly.count;
+#endif
+        const uint32_t t_sct = q_sct.head + q_sct.count, t_wall = q_wall.head + q_wall.count, t_fin = q_fin.head + q_fin.count;
+        const uint32_t t_free = q_free.head + q_free.count;
+        const unsigned peers = d_fly ? m_fly : (d_sct ? m_sct : (d_wall ? m_wall : (d_fin ? m_fin : m_free)));
+        const uint32_t tail = d_fly ? t_fly : (d_sct ? t_sct : (d_wall ? t_wall : (d_fin ? t_fin : t_free)));
+        if (dest >= 0) { sts8(qb + dest * QC + ((tail + __popc(peers & lt_mask)) & (QC - 1u)), k); }
+        q_fly.count += n_fly;
+        q_sct.count += n_sct;
+        q_wall.count += n_wall;
+        q_fin.count += n_fin;
+        q_free.count += n_free;
     }
     n_out = min(n_out, a.seg_cap);
     if (lane == 0) { a.cnt_out[w] = n_out; }
@@ -981,6 +1044,40 @@ __global__ void finalize_rows_kernel(const long long* acc, int32_t* tally_e, lon
         carry_e[s] = static_cast<int32_t>(v);
     } else {
         carry_f[2u * s + c - 1u] = v;
+    }
+}
+
+// device [R][S] tallies -> the caller's [S][R] layout (psim_gpu_get_tallies), through a 32 x 33 shared-memory tile so that both
+// the reads and the writes are coalesced; flux also converted from fixed point to m/s
+__global__ void transpose_tallies_kernel(const int32_t* tally_e, const long long* tally_f, uint32_t R, uint32_t S, double scale,
+                                         int32_t* out_e, double* out_f, long long* out_x) {
+    __shared__ int32_t te[32][33];
+    __shared__ long long tx[32][33], ty[32][33];
+    const uint32_t s0 = blockIdx.x * 32u, r0 = blockIdx.y * 32u;
+    for (uint32_t j = threadIdx.y; j < 32u; j += blockDim.y) {
+        const uint32_t r = r0 + j, s = s0 + threadIdx.x;
+        if (r < R && s < S) {
+            const size_t k = static_cast<size_t>(r) * S + s;
+            te[j][threadIdx.x] = tally_e[k];
+            tx[j][threadIdx.x] = tally_f[2 * k];
+            ty[j][threadIdx.x] = tally_f[2 * k + 1];
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.y; j < 32u; j += blockDim.y) {
+        const uint32_t s = s0 + j, r = r0 + threadIdx.x;
+        if (r < R && s < S) {
+            const size_t k = static_cast<size_t>(s) * R + r;
+            if (out_e) { out_e[k] = te[threadIdx.x][j]; }
+            if (out_f) {
+                out_f[2 * k] = static_cast<double>(tx[threadIdx.x][j]) * scale;
+                out_f[2 * k + 1] = static_cast<double>(ty[threadIdx.x][j]) * scale;
+            }
+            if (out_x) {
+                out_x[2 * k] = tx[threadIdx.x][j];
+                out_x[2 * k + 1] = ty[threadIdx.x][j];
+            }
+        }
     }
 }
 

@@ -42,6 +42,7 @@ struct psim_gpu {
     void* d_cell_shape = nullptr;
     void* d_shapes = nullptr;
     void* d_classes = nullptr;
+    void* d_step_sensors = nullptr;
     void* d_subs = nullptr;
     void* d_sensors = nullptr;
     void* d_materials = nullptr;
@@ -68,6 +69,8 @@ struct psim_gpu {
     unsigned long long* d_hist = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    void* pinned = nullptr;          // staging buffer of psim_gpu_get_tallies
+    size_t pinned_bytes = 0;
     bool have_sources = false;
     bool timing_open = false;
     uint32_t next_step = 0;
@@ -99,9 +102,27 @@ int cuda_fail(psim_gpu* h, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) { return cuda_fail(h, e_, #call); }    \
     } while (0)
 
+// device memory that is released on every return path (probes, temporaries)
+struct DeviceBuffer {
+    void* p = nullptr;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    ~DeviceBuffer() { cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template<typename T> T* as() const { return static_cast<T*>(p); }
+    void* release() {
+        void* q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
 template<typename T> int upload(psim_gpu* h, void** dst, const std::vector<T>& v) {
-    PSIM_CUDA(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
-    if (!v.empty()) { PSIM_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    DeviceBuffer b;  // a failed copy does not leave the allocation behind
+    PSIM_CUDA(b.alloc(v.size() * sizeof(T)));
+    if (!v.empty()) { PSIM_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    *dst = b.release();
     return 0;
 }
 
@@ -306,6 +327,9 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         if (int rc = upload(h, &h->d_cell_shape, h->img.cell_shape)) { return rc; }
         if (int rc = upload(h, &h->d_shapes, h->img.shapes)) { return rc; }
         if (int rc = upload(h, &h->d_classes, h->img.classes)) { return rc; }
+        if (!h->img.step_sensors.empty()) {
+            if (int rc = upload(h, &h->d_step_sensors, h->img.step_sensors)) { return rc; }
+        }
         if (int rc = upload(h, &h->d_subs, h->img.subs)) { return rc; }
         if (int rc = upload(h, &h->d_sensors, h->img.sensors)) { return rc; }
         if (int rc = upload(h, &h->d_materials, h->img.materials)) { return rc; }
@@ -318,6 +342,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         h->P.cell_shape = static_cast<const uint32_t*>(h->d_cell_shape);
         h->P.shapes = static_cast<const DevShape*>(h->d_shapes);
         h->P.classes = static_cast<const DevSensor*>(h->d_classes);
+        h->P.step_sensors = static_cast<const DevSensor*>(h->d_step_sensors);
         h->P.subs = static_cast<const DevSub*>(h->d_subs);
         h->P.sensors = static_cast<const DevSensor*>(h->d_sensors);
         h->P.materials = static_cast<const DevMaterial*>(h->d_materials);
@@ -567,25 +592,37 @@ int psim_gpu_get_tallies(psim_gpu* h, int32_t* energy, double* flux, int64_t* fl
     if (int rc = psim_gpu_synchronize(h)) { return rc; }
     const uint32_t R = h->P.recorded_steps, S = h->P.n_sensors;
     const size_t n = static_cast<size_t>(R) * S;
-    std::vector<int32_t> e(n);
-    std::vector<long long> f(2 * n);
-    PSIM_CUDA(cudaMemcpy(e.data(), h->tally_e, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    PSIM_CUDA(cudaMemcpy(f.data(), h->tally_f, 2 * n * sizeof(long long), cudaMemcpyDeviceToHost));
-    const double scale = 1. / static_cast<double>(1 << PSIM_FLUX_FRAC_BITS);
-    for (uint32_t r = 0; r < R; ++r) {
-        for (uint32_t s = 0; s < S; ++s) {  // device [R][S] -> caller [S][R], the reference's per-sensor vectors
-            const size_t src = static_cast<size_t>(r) * S + s, dst = static_cast<size_t>(s) * R + r;
-            if (energy) { energy[dst] = e[src]; }
-            if (flux) {
-                flux[2 * dst] = static_cast<double>(f[2 * src]) * scale;
-                flux[2 * dst + 1] = static_cast<double>(f[2 * src + 1]) * scale;
-            }
-            if (flux_fixed) {
-                flux_fixed[2 * dst] = f[2 * src];
-                flux_fixed[2 * dst + 1] = f[2 * src + 1];
-            }
-        }
+    if (n == 0 || (!energy && !flux && !flux_fixed)) { return PSIM_OK; }
+    // device [R][S] -> caller [S][R] (the reference's per-sensor vectors): transposed and converted on the device, then one
+    // copy per requested array through a pinned staging buffer (31 MB of tallies on the kinked wire: the pageable copy and
+    // the host-side transpose through two temporary vectors were the slowest part of a run's epilogue)
+    PSIM_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = n * (sizeof(int32_t) + 2 * sizeof(double) + 2 * sizeof(long long)) + 16;
+    DeviceBuffer dev;
+    PSIM_CUDA(dev.alloc(bytes));
+    int32_t* d_e = dev.as<int32_t>();
+    double* d_f = reinterpret_cast<double*>(dev.as<unsigned char>() + ((n * sizeof(int32_t) + 15) & ~static_cast<size_t>(15)));
+    long long* d_x = reinterpret_cast<long long*>(d_f + 2 * n);
+    if (h->pinned_bytes < 2 * n * sizeof(double)) {
+        if (h->pinned) { cudaFreeHost(h->pinned); }
+        h->pinned = nullptr;
+        h->pinned_bytes = 0;
+        PSIM_CUDA(cudaMallocHost(&h->pinned, 2 * n * sizeof(double)));
+        h->pinned_bytes = 2 * n * sizeof(double);
     }
+    const dim3 block(32, 8), grid((S + 31) / 32, (R + 31) / 32);
+    transpose_tallies_kernel<<<grid, block, 0, h->stream>>>(h->tally_e, h->tally_f, R, S, 1. / static_cast<double>(1 << PSIM_FLUX_FRAC_BITS),
+                                                             energy ? d_e : nullptr, flux ? d_f : nullptr, flux_fixed ? d_x : nullptr);
+    PSIM_CUDA(cudaGetLastError());
+    auto fetch = [&](void* dst, const void* src, size_t nbytes) -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(h->pinned, src, nbytes, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) { e = cudaStreamSynchronize(h->stream); }
+        if (e == cudaSuccess) { std::memcpy(dst, h->pinned, nbytes); }
+        return e;
+    };
+    if (energy) { PSIM_CUDA(fetch(energy, d_e, n * sizeof(int32_t))); }
+    if (flux) { PSIM_CUDA(fetch(flux, d_f, 2 * n * sizeof(double))); }
+    if (flux_fixed) { PSIM_CUDA(fetch(flux_fixed, d_x, 2 * n * sizeof(long long))); }
     return PSIM_OK;
 }
 
@@ -645,7 +682,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     out->tally_in_shared = h->last_tally_shared;
     out->kernel = static_cast<uint32_t>(h->opt_kernel);
     out->reserved = 0;
-    out->image_bytes = h->img.cells.size() * (sizeof(DevCell) + sizeof(uint32_t)) + h->img.shapes.size() * sizeof(DevShape) + h->img.classes.size() * sizeof(DevSensor) + h->img.subs.size() * sizeof(DevSub) +
+    out->image_bytes = h->img.cells.size() * (sizeof(DevCell) + sizeof(uint32_t)) + h->img.shapes.size() * sizeof(DevShape) + (h->img.classes.size() + h->img.step_sensors.size()) * sizeof(DevSensor) + h->img.subs.size() * sizeof(DevSub) +
                        h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
                        h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +
                        h->img.velocities.size() * sizeof(float);
@@ -714,6 +751,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaFree(h->d_cell_shape);
     cudaFree(h->d_shapes);
     cudaFree(h->d_classes);
+    cudaFree(h->d_step_sensors);
     cudaFree(h->d_subs);
     cudaFree(h->d_sensors);
     cudaFree(h->d_materials);
@@ -728,6 +766,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaFree(h->carry_f);
     cudaFree(h->d_stats);
     cudaFree(h->d_hist);
+    if (h->pinned) { cudaFreeHost(h->pinned); }
     if (h->ev_begin) { cudaEventDestroy(h->ev_begin); }
     if (h->ev_end) { cudaEventDestroy(h->ev_end); }
     if (h->stream) { cudaStreamDestroy(h->stream); }
@@ -741,25 +780,20 @@ int psim_gpu_probe_sample(psim_gpu* h, uint32_t table, const float* u1, const fl
     if (!h || !u1 || !u2 || !out_bin || !out_ta || !out_bin_bisect || table >= h->P.n_tables) { return PSIM_E_INVALID; }
     if (n == 0) { return PSIM_OK; }
     PSIM_CUDA(cudaSetDevice(h->device));
-    float *d1 = nullptr, *d2 = nullptr;
-    uint32_t *db = nullptr, *dt = nullptr, *dp = nullptr;
-    PSIM_CUDA(cudaMalloc(&d1, n * 4));
-    PSIM_CUDA(cudaMalloc(&d2, n * 4));
-    PSIM_CUDA(cudaMalloc(&dp, n * 4));
-    PSIM_CUDA(cudaMalloc(&db, n * 4));
-    PSIM_CUDA(cudaMalloc(&dt, n * 4));
-    PSIM_CUDA(cudaMemcpy(d1, u1, n * 4, cudaMemcpyHostToDevice));
-    PSIM_CUDA(cudaMemcpy(d2, u2, n * 4, cudaMemcpyHostToDevice));
-    probe_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, table, d1, d2, n, db, dt, dp);
+    DeviceBuffer d1, d2, db, dt, dp;
+    PSIM_CUDA(d1.alloc(n * 4));
+    PSIM_CUDA(d2.alloc(n * 4));
+    PSIM_CUDA(dp.alloc(n * 4));
+    PSIM_CUDA(db.alloc(n * 4));
+    PSIM_CUDA(dt.alloc(n * 4));
+    PSIM_CUDA(cudaMemcpy(d1.p, u1, n * 4, cudaMemcpyHostToDevice));
+    PSIM_CUDA(cudaMemcpy(d2.p, u2, n * 4, cudaMemcpyHostToDevice));
+    probe_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, table, d1.as<float>(), d2.as<float>(), n, db.as<uint32_t>(),
+                                                                          dt.as<uint32_t>(), dp.as<uint32_t>());
     PSIM_CUDA(cudaGetLastError());
-    PSIM_CUDA(cudaMemcpy(out_bin_bisect, dp, n * 4, cudaMemcpyDeviceToHost));
-    cudaFree(dp);
-    PSIM_CUDA(cudaMemcpy(out_bin, db, n * 4, cudaMemcpyDeviceToHost));
-    PSIM_CUDA(cudaMemcpy(out_ta, dt, n * 4, cudaMemcpyDeviceToHost));
-    cudaFree(d1);
-    cudaFree(d2);
-    cudaFree(db);
-    cudaFree(dt);
+    PSIM_CUDA(cudaMemcpy(out_bin_bisect, dp.p, n * 4, cudaMemcpyDeviceToHost));
+    PSIM_CUDA(cudaMemcpy(out_bin, db.p, n * 4, cudaMemcpyDeviceToHost));
+    PSIM_CUDA(cudaMemcpy(out_ta, dt.p, n * 4, cudaMemcpyDeviceToHost));
     return PSIM_OK;
 }
 
@@ -773,19 +807,15 @@ int psim_gpu_probe_flight(psim_gpu* h, const uint32_t* cell, const float* in, si
         }
     }
     PSIM_CUDA(cudaSetDevice(h->device));
-    uint32_t* dc = nullptr;
-    float *di = nullptr, *dout = nullptr;
-    PSIM_CUDA(cudaMalloc(&dc, n * 4));
-    PSIM_CUDA(cudaMalloc(&di, n * 16));
-    PSIM_CUDA(cudaMalloc(&dout, n * 24));
-    PSIM_CUDA(cudaMemcpy(dc, cell, n * 4, cudaMemcpyHostToDevice));
-    PSIM_CUDA(cudaMemcpy(di, in, n * 16, cudaMemcpyHostToDevice));
-    probe_flight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, dc, di, n, dout);
+    DeviceBuffer dc, di, dout;
+    PSIM_CUDA(dc.alloc(n * 4));
+    PSIM_CUDA(di.alloc(n * 16));
+    PSIM_CUDA(dout.alloc(n * 24));
+    PSIM_CUDA(cudaMemcpy(dc.p, cell, n * 4, cudaMemcpyHostToDevice));
+    PSIM_CUDA(cudaMemcpy(di.p, in, n * 16, cudaMemcpyHostToDevice));
+    probe_flight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, dc.as<uint32_t>(), di.as<float>(), n, dout.as<float>());
     PSIM_CUDA(cudaGetLastError());
-    PSIM_CUDA(cudaMemcpy(out, dout, n * 24, cudaMemcpyDeviceToHost));
-    cudaFree(dc);
-    cudaFree(di);
-    cudaFree(dout);
+    PSIM_CUDA(cudaMemcpy(out, dout.p, n * 24, cudaMemcpyDeviceToHost));
     return PSIM_OK;
 }
 
@@ -795,19 +825,15 @@ int psim_gpu_probe_rates(psim_gpu* h, uint32_t sensor, const double* omega, cons
     PSIM_CUDA(cudaSetDevice(h->device));
     std::vector<float> w(n), r(3 * n);
     for (size_t i = 0; i < n; ++i) { w[i] = static_cast<float>(omega[i] * PSIM_FREQ_SCALE); }
-    float *dw = nullptr, *dr = nullptr;
-    uint32_t* dta = nullptr;
-    PSIM_CUDA(cudaMalloc(&dw, n * 4));
-    PSIM_CUDA(cudaMalloc(&dr, 3 * n * 4));
-    PSIM_CUDA(cudaMalloc(&dta, n * 4));
-    PSIM_CUDA(cudaMemcpy(dw, w.data(), n * 4, cudaMemcpyHostToDevice));
-    PSIM_CUDA(cudaMemcpy(dta, ta, n * 4, cudaMemcpyHostToDevice));
-    probe_rates_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, sensor, dw, dta, n, dr);
+    DeviceBuffer dw, dr, dta;
+    PSIM_CUDA(dw.alloc(n * 4));
+    PSIM_CUDA(dr.alloc(3 * n * 4));
+    PSIM_CUDA(dta.alloc(n * 4));
+    PSIM_CUDA(cudaMemcpy(dw.p, w.data(), n * 4, cudaMemcpyHostToDevice));
+    PSIM_CUDA(cudaMemcpy(dta.p, ta, n * 4, cudaMemcpyHostToDevice));
+    probe_rates_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, sensor, dw.as<float>(), dta.as<uint32_t>(), n, dr.as<float>());
     PSIM_CUDA(cudaGetLastError());
-    PSIM_CUDA(cudaMemcpy(r.data(), dr, 3 * n * 4, cudaMemcpyDeviceToHost));
-    cudaFree(dw);
-    cudaFree(dr);
-    cudaFree(dta);
+    PSIM_CUDA(cudaMemcpy(r.data(), dr.p, 3 * n * 4, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < 3 * n; ++i) { rates[i] = static_cast<double>(r[i]) * 1e9; }  // 1/ns -> 1/s
     return PSIM_OK;
 }

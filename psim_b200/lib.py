@@ -64,7 +64,7 @@ class ModelDesc(C.Structure):
                 ("sensors", C.POINTER(Sensor)), ("cells", C.POINTER(Cell)), ("subsurfaces", C.POINTER(SubSurface)),
                 ("emitters", C.POINTER(Emitter)), ("tables", C.POINTER(Table)),
                 ("measurement_steps", C.c_uint32), ("step_adjustment", C.c_uint32), ("simulation_time", C.c_double),
-                ("full_simulation", C.c_uint32), ("phasor_sim", C.c_uint32)]
+                ("full_simulation", C.c_uint32), ("phasor_sim", C.c_uint32), ("step_sensors", C.POINTER(Sensor))]
 
 
 class Source(C.Structure):
@@ -122,6 +122,8 @@ SYMBOLS = {
     "psim_model_get_info": (C.c_int, [_P, C.POINTER(ModelInfo)]),
     "psim_model_set_num_phonons": (C.c_int, [_P, C.c_uint64]),
     "psim_model_set_num_runs": (C.c_int, [_P, C.c_uint64]),
+    "psim_model_set_max_iters": (C.c_int, [_P, C.c_uint64]),
+    "psim_model_end_iteration": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "psim_model_prepare": (C.c_int, [_P]),
     "psim_model_energy": (C.c_int, [_P, _DP, _DP]),
     "psim_model_material_arrays": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
@@ -206,6 +208,16 @@ class Model:
 
     def set_num_runs(self, n: int):
         self._check(self.lib.psim_model_set_num_runs(self.handle, int(n)))
+
+    def set_max_iters(self, n: int):
+        """Iterations per run (the reference's MAX_ITERS, model.cpp:11)."""
+        self._check(self.lib.psim_model_set_max_iters(self.handle, int(n)))
+
+    def end_iteration(self) -> bool:
+        """model.cpp:163-171; True if the run must be simulated again with a fresh describe() / sources()."""
+        again = C.c_int()
+        self._check(self.lib.psim_model_end_iteration(self.handle, C.byref(again)))
+        return bool(again.value)
 
     def prepare(self):
         self._check(self.lib.psim_model_prepare(self.handle))

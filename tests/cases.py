@@ -62,6 +62,19 @@ def cases(include_kinked: bool = True):
     return c
 
 
+def iteration_cases():
+    """Cases for the re-iteration of a run (model.cpp:159-172 with MAX_ITERS raised to 3): steady state (new
+    t_eq, per-sensor steady temperatures and tables, cells that now emit), periodic (tables only) and transient (one heat
+    capacity and scatter table per sensor and measurement step).  The wall temperatures are far apart so that the sensors
+    do move by more than the reference's 0.1 % / 2 % stability thresholds and every case really iterates three times."""
+    c = {}
+    c["linear_demo"] = configs.linear(num_phonons=150_000, t_high=340, t_low=280).to_dict()
+    c["sides_per"] = configs.linear_sides(num_phonons=60_000, sim_type=1, step_interval=4, t_high=360, t_low=250).to_dict()
+    c["sides_trans"] = configs.linear_sides(num_phonons=60_000, sim_type=2, step_interval=4, start_time=0.1, duration=0.15,
+                                            t_high=360, t_low=250).to_dict()
+    return c
+
+
 def split_bar(num_phonons: int, split=(7, 12)) -> dict:
     """linear_demo's bar with two of its 20 rectangles cut into a lower and an upper half: the full-height edges of
     their neighbours then face TWO cells each (partial transition sub-surfaces, compositeSurface.cpp:47-66).  The

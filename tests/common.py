@@ -111,6 +111,8 @@ def run_features(energy: np.ndarray, flux: np.ndarray, sim_type: int, six=None, 
          "tally_e_blk": blocks(energy.astype(np.float64), nb), "tally_f_blk": blocks(flux, nb)}
     if six is not None:
         f["out6"] = six
+        f["pool"] = np.array([energy.sum(), flux[:, :, 0].sum(), flux[:, :, 1].sum(), six[:, 0].mean(), six[:, 2].mean(), six[:, 4].mean()],
+                             dtype=np.float64)
     if temps is not None:
         f["temp_blk"] = blocks(temps, nb)
     if fluxes is not None:
@@ -118,10 +120,11 @@ def run_features(energy: np.ndarray, flux: np.ndarray, sim_type: int, six=None, 
     return f
 
 
-def welch_z(runs: list, gold, key: str) -> np.ndarray:
+def welch_z(runs: list, gold, key: str, scale: float = 1.0) -> np.ndarray:
     """Per-entry z = (mean_ours - mean_ref) / sqrt(var_ours/n + var_ref/n_ref), sigma from the independent seeds
-    of each implementation (BASELINE.json: >= 8 seeds each, agree within 3 sigma)."""
-    a = np.stack([r[key] for r in runs])
+    of each implementation (BASELINE.json: >= 8 seeds each, agree within 3 sigma).  `scale` multiplies our values first:
+    tallies are proportional to the number of phonons, so runs with k times the fixture's phonons compare with 1 / k."""
+    a = np.stack([r[key] for r in runs]) * scale
     n = a.shape[0]
     mean, var = a.mean(axis=0), a.var(axis=0, ddof=1)
     gm, gs, gn = gold[key + "_mean"], gold[key + "_std"].astype(np.float64), int(gold["n_seeds"])
@@ -131,28 +134,54 @@ def welch_z(runs: list, gold, key: str) -> np.ndarray:
     return z
 
 
+def assert_pooled(runs: list, gold, what: str, tally_scale: float = 1.0, limit: float = 3.5):
+    """The bias test with ONE degree of freedom per quantity: total energy tally, total x / y flux tallies, and
+    the means over all sensors of the exported temperature and fluxes.  A uniform offset of every sensor - which per-sensor
+    z values of correlated sensors can hide - shows up here undiluted, and the statistic's null distribution is known (Student
+    t with >= 31 degrees of freedom from the reference's 32 seeds: P(|t| > 3.5) = 0.14 %).  Fixtures made before round 2
+    carry no pooled values; nothing is checked for them."""
+    if "pool_mean" not in gold:
+        return None
+    scale = np.array([tally_scale, tally_scale, tally_scale, 1.0, 1.0, 1.0])
+    a = np.stack([r["pool"] for r in runs]) * scale
+    n = a.shape[0]
+    gm, gs, gn = gold["pool_mean"], gold["pool_std"].astype(np.float64), int(gold["n_seeds"])
+    se = np.sqrt(a.var(axis=0, ddof=1) / n + gs * gs / gn)
+    z = (a.mean(axis=0) - gm) / np.where(se > 0, se, np.inf)
+    assert np.abs(z).max() <= limit, f"{what}: pooled z (E, Fx, Fy, <T>, <qx>, <qy>) = {np.round(z, 2).tolist()}"
+    return z
+
+
 def parity_summary(z: np.ndarray) -> dict:
     z = z[np.isfinite(z)] if np.isfinite(z).any() else z
     return {"n": int(z.size), "max": float(np.abs(z).max()), "frac3": float((np.abs(z) > 3).mean()),
             "mean": float(z.mean()), "rms": float(np.sqrt((z * z).mean()))}
 
 
-def assert_parity(z: np.ndarray, what: str, p3: float = 0.012, max_abs: float = 8.0, max_rms: float = 1.6):
+def assert_parity(z: np.ndarray, what: str, p3: float = 0.012, max_abs: float = 8.0, max_rms: float = 1.6, mean_tol: float | None = None):
     """3-sigma agreement over many entries.
 
-    With sigma estimated from 8-16 seeds the per-entry statistic is t-distributed, and there are up to 10^5
+    With sigma estimated from 8-32 seeds the per-entry statistic is t-distributed, and there are up to 10^5
     entries per case, so a few |z| > 3 are expected even between two sets of runs of the reference itself
     (the fixtures record that self-comparison as `selfz_*`: up to 1 % beyond 3, extremes of 5-8).  The test
     therefore bounds the NUMBER beyond 3 sigma (binomial with the t-distribution's tail probability p3, plus
-    3.5 standard deviations), the extreme, and the rms (a systematic offset of even 1 sigma in every entry would
-    raise the rms to 1.4 and is caught there and by the mean)."""
+    3.5 standard deviations), the extreme, the rms and the mean.
+
+    Few entries (n < 50: the 20 sensors of a 1-D bar, the 50 of the Si/Ge grid) are positively correlated - one conserved
+    heat flux, one total energy - so their mean z is wider than 1 / sqrt(n).  Calibration (64 seeds of the CPU restatement of
+    the reference on linear_demo, split at random into 32 + 32, 2000 splits): pairwise correlation 0.18 (T, energy) to 0.32
+    (flux); the mean z has a standard deviation of 0.47 - 0.61, P(|mean| > 1.5) <= 1.6 %, and P(rms > 2.0) <= 0.4 %
+    (P(|mean| > 1.0) would be 4 - 11 % and P(rms > 1.6) 1.5 - 4 % - with 40 such assertions per run a suite that fails every
+    second time).  Those are the bounds below; what makes them SHARP is the denominator: the fixtures of these cases hold 32
+    reference seeds and the GPU side runs 8 seeds at ten times the phonons (tests/test_gpu_parity.py), so one unit of z is
+    0.18 sigma of a single reference run, against 0.43 in round 1, and assert_pooled adds the undiluted one-degree-of-freedom
+    test on totals."""
     s = parity_summary(z)
     n = max(s["n"], 1)
-    # few entries = the sensors of a 1-D bar: their fluctuations are almost perfectly correlated (one conserved heat
-    # flux, one total energy), so a common offset of up to 2 sigma is an ordinary outcome there
-    mean_tol = max(4.0 / np.sqrt(n), 0.35) if n >= 200 else (1.0 if n >= 50 else 2.0)
+    if mean_tol is None:
+        mean_tol = max(4.0 / np.sqrt(n), 0.35) if n >= 200 else (1.0 if n >= 50 else 1.5)
     if n < 50:
-        max_rms = max(max_rms, 2.3)
+        max_rms = max(max_rms, 2.0)
     msg = f"{what}: {s}"
     assert np.isfinite(z).all(), msg
     allowed = np.ceil(n * p3 + 3.5 * np.sqrt(n * p3) + 1.0)

@@ -29,6 +29,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     P.cell_shape = img.cell_shape.data();
     P.shapes = img.shapes.data();
     P.classes = img.classes.data();
+    P.step_sensors = img.step_sensors.empty() ? nullptr : img.step_sensors.data();
     P.subs = img.subs.data();
     P.sensors = img.sensors.data();
     P.materials = img.materials.data();

@@ -35,6 +35,7 @@ from psim_b200 import configs  # noqa: E402
 from tests import cases as test_cases  # noqa: E402
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "psim_ref")
+REF_BIN_ITERS3 = os.path.join(ROOT, "oracle", "_ref", "psim_ref_iters3")
 REF_JSON = "/root/reference/psim_python/json"
 NBLOCKS = 20  # periodic / transient traces are compared as NBLOCKS block means over the recorded steps
 
@@ -97,6 +98,10 @@ def features(meta, run):
         "tally_f_blk": blocks(run["flux"], nb),  # [S,nb,2]
         "temp_blk": blocks(run["final_temps"], nb),  # [S,nb]
         "flux_blk": blocks(run["final_fluxes"], nb),  # [S,nb,2]
+        # pooled scalars (one degree of freedom each, known null distribution): total energy and flux tallies, mean exported
+        # temperature and fluxes - what a uniform bias over all sensors shows up in
+        "pool": np.array([run["energy"].sum(), run["flux"][:, :, 0].sum(), run["flux"][:, :, 1].sum(),
+                          run["out6"][:, 0].mean(), run["out6"][:, 2].mean(), run["out6"][:, 4].mean()], dtype=np.float64),
         "total_phonons": np.float64(meta["total_phonons"]),
         "e_post": np.float64(meta["energy_per_phonon_post"]),
         "seconds": np.float64(meta["seconds"]),
@@ -109,24 +114,30 @@ def main():
     ap.add_argument("--seeds", type=int, default=16)
     ap.add_argument("--jobs", type=int, default=os.cpu_count() or 4)
     ap.add_argument("--only", default="")
+    ap.add_argument("--iters3", action="store_true",
+                    help="run oracle/_ref/psim_ref_iters3 (the reference with MAX_ITERS raised to 3, `make -C oracle ref_iters3`) on "
+                         "tests/cases.py:iteration_cases() and write <case>.iters3.npz")
     args = ap.parse_args()
-    if not os.path.exists(REF_BIN):
-        sys.exit("oracle/_ref/psim_ref is missing: run `make -C oracle ref` first")
-    todo = cases()
+    ref_bin = REF_BIN_ITERS3 if args.iters3 else REF_BIN
+    suffix = ".iters3" if args.iters3 else ""
+    if not os.path.exists(ref_bin):
+        sys.exit(f"{ref_bin} is missing: run `make -C oracle {'ref_iters3' if args.iters3 else 'ref'}` first")
+    todo = test_cases.iteration_cases() if args.iters3 else cases()
     if args.only:
         todo = {k: v for k, v in todo.items() if k in args.only.split(",")}
     with tempfile.TemporaryDirectory() as tmp:
         jobs = []
         for name, model in todo.items():
             path = configs.save(model, os.path.join(tmp, name + ".json"))
-            subprocess.run([REF_BIN, "kat", path, os.path.join(tmp, name + ".kat")], check=True,
-                           stdout=subprocess.DEVNULL)
+            if not args.iters3:
+                subprocess.run([REF_BIN, "kat", path, os.path.join(tmp, name + ".kat")], check=True,
+                               stdout=subprocess.DEVNULL)
             for k in range(args.seeds):
                 jobs.append((name, path, os.path.join(tmp, f"{name}.{k}")))
 
         def run(job):
             name, path, prefix = job
-            subprocess.run([REF_BIN, "run", path, prefix], check=True, stdout=subprocess.DEVNULL)
+            subprocess.run([ref_bin, "run", path, prefix], check=True, stdout=subprocess.DEVNULL)
             return job
 
         with ThreadPoolExecutor(args.jobs) as ex:
@@ -160,7 +171,10 @@ def main():
             out["sensor_ids"] = np.array(meta0["sensor_ids"], dtype=np.int64)
             out["sensor_areas"] = np.array(meta0["sensor_areas"], dtype=np.float64)
             out["settings_json"] = np.array(json.dumps(model["settings"]))
-            np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+            np.savez_compressed(os.path.join(HERE, name + suffix + ".npz"), **out)
+            if args.iters3:
+                print("wrote", name + suffix, flush=True)
+                continue
 
             # deterministic known answers (tables sub-sampled every 25th bin + full-precision sums)
             kmeta = json.load(open(os.path.join(tmp, name + ".kat.meta.json")))

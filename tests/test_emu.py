@@ -1,5 +1,6 @@
 """CPU-side checks of the device algorithm: psim_b200/csrc/device_core.cuh compiled for the host (tests/emu).
 The GPU tests run the same checks on the CUDA build; these keep the algorithm honest where no GPU exists."""
+import os
 from concurrent.futures import ProcessPoolExecutor
 
 import numpy as np
@@ -206,3 +207,56 @@ def test_damaged_descriptions_are_rejected_or_run_to_completion():
     assert first.startswith("baseline (0,") and "final (0," in last  # the undamaged description runs before and after
     errors, ok = int(last.split()[1]), int(last.split()[3])
     assert errors > 500 and ok > 300
+
+
+def _iterated_features(model_dict, seed, engine):
+    """One run of a model whose iteration cap is 3, driven the way psim_model_run drives it: simulate, end the iteration,
+    and - while the model asks for it - describe the model again and simulate again.  `engine(model, seed)` runs the
+    particle loop once and returns (energy, flux)."""
+    m = T.load_model(model_dict)
+    m.set_max_iters(3)
+    m.prepare()
+    iterations = 0
+    while True:
+        e, f = engine(m, seed + 7919 * iterations)
+        iterations += 1
+        m.set_tallies(e, f)
+        if not m.end_iteration():
+            break
+    m.finish_run(0)
+    six, temps, fluxes = m.results(0)
+    feats = T.run_features(e, f, m.info.sim_type, six, temps, fluxes)
+    m.close()
+    return feats, iterations
+
+
+@pytest.mark.parametrize("name", ["linear_demo", "sides_per", "sides_trans"])
+def test_reiterated_runs_match_the_reference_with_its_iteration_cap_raised(name):
+    """the re-iteration of a run (model.cpp:159-172: new t_eq, sensor steady temperatures, tables and heat
+    capacities from the iteration before; per measurement step for a transient run, sensorController.cpp:101-113).  Upstream
+    MAX_ITERS = 1 makes it dead code, so the fixture comes from the reference compiled with that one constant raised to 3
+    (oracle/Makefile: ref_iters3; tests/golden/make_golden.py --iters3).  Here the host logic of psim_b200 (end_iteration,
+    describe with per-sensor and per-step records) around the CPU build of the device functions."""
+    from tests import cases
+    gold_path = os.path.join(T.GOLDEN, name + ".iters3.npz")
+    if not os.path.exists(gold_path):
+        pytest.skip("fixture missing")
+    gold = np.load(gold_path)
+    model = cases.iteration_cases()[name]
+
+    def engine(m, seed):
+        r = T.emu_run(m, seed, steps_per_pass=16)
+        return r["energy"], r["flux"]
+
+    runs = []
+    for seed in range(1, 7):
+        feats, iterations = _iterated_features(model, seed, engine)
+        assert iterations == 3
+        runs.append(feats)
+    if model["settings"]["sim_type"] == 0:
+        z = T.welch_z(runs, gold, "out6")
+        T.assert_parity(z[:, 0], f"emu {name} x3 temperature column")
+        T.assert_parity(z[:, 2], f"emu {name} x3 x-flux column")
+    else:
+        T.assert_parity(T.welch_z(runs, gold, "temp_blk"), f"emu {name} x3 temperature trace")
+        T.assert_parity(T.welch_z(runs, gold, "flux_blk"), f"emu {name} x3 flux trace")

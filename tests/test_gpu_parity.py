@@ -17,6 +17,11 @@ SEEDS = list(range(1, 9))
 STEADY = ["linear_demo", "linear_diffuse", "linear_rough", "linear_hot_cells", "linear_impurity", "linear_full", "sides_ss", "sige",
           "kinked_spec", "kinked_diffuse", "kinked_rough"]
 TRACES = ["sides_per", "sides_trans", "sides_per_full"]
+# The cases with 20 - 50 sensors: their fixtures hold 32 reference seeds, and the GPU side runs its 8 seeds with TEN TIMES the
+# fixture's phonons (deviational mode: every temperature and flux has the same expectation for any number of phonons, tallies
+# scale with it), so that the comparison is limited by the reference's noise alone - tests/common.py:assert_parity.
+# linear_full (non-deviational; its temperatures are found on a 0.1 K table grid) stays at the fixture's size with 32 seeds.
+HIGH_STATISTICS = {"linear_demo": 10, "linear_diffuse": 10, "linear_rough": 10, "linear_hot_cells": 10, "linear_impurity": 10, "sige": 10}
 
 
 @pytest.mark.parametrize("name", STEADY)
@@ -24,13 +29,22 @@ def test_steady_state_parity(name):
     if name not in T.all_case_names():
         pytest.skip("fixture geometry missing")
     gold = T.golden(name)
-    runs = gpu_features(name, SEEDS)
-    T.assert_parity(T.welch_z(runs, gold, "tally_e"), f"{name} energy tallies")
-    T.assert_parity(T.welch_z(runs, gold, "tally_f"), f"{name} flux tallies")
+    factor = HIGH_STATISTICS.get(name, 1)
+    if factor > 1:
+        model = T.load_model(T.case_model(name), num_phonons=factor * T.case_model(name)["settings"]["num_phonons"])
+        runs = []
+        for seed in SEEDS:
+            r = gpu_run_case(model, seed)
+            runs.append(T.run_features(r["energy"], r["flux"], 0, r["six"], r["temps"], r["fluxes"]))
+    else:
+        runs = gpu_features(name, range(1, 33) if name == "linear_full" else SEEDS)
+    T.assert_parity(T.welch_z(runs, gold, "tally_e", 1.0 / factor), f"{name} energy tallies")
+    T.assert_parity(T.welch_z(runs, gold, "tally_f", 1.0 / factor), f"{name} flux tallies")
     six = T.welch_z(runs, gold, "out6")
     T.assert_parity(six[:, 0], f"{name} temperature column")   # T as written to ss_*.txt
     T.assert_parity(six[:, 2], f"{name} x-flux column")
     T.assert_parity(six[:, 4], f"{name} y-flux column")
+    T.assert_pooled(runs, gold, f"{name} totals", 1.0 / factor)
 
 
 @pytest.mark.parametrize("name", TRACES)
@@ -114,7 +128,8 @@ def test_staged_tally_forms_agree_on_automatic_windows():
         assert np.array_equal(c["energy"], d["energy"]) and np.array_equal(c["fixed"], d["fixed"])
 
 
-FULL_SIZE = {"sige": 100_000_000, "linear_demo": 5_000_000, "sides_ss": 10_000_000, "sides_trans": 10_000_000}
+FULL_SIZE = {"sige": 100_000_000, "linear_demo": 5_000_000, "sides_ss": 10_000_000, "sides_trans": 10_000_000, "sides_per": 10_000_000,
+             "kinked_spec": 20_000_000}
 
 
 @pytest.mark.parametrize("name", list(FULL_SIZE))
@@ -124,6 +139,8 @@ def test_full_size_runs_agree_with_reduced_size_reference(name):
     phonon scales as 1/N), so the full-size GPU result - whose own noise is 5-20x smaller - must lie within the
     reference's seed-to-seed scatter at the reduced size (z per entry against sigma_ref / sqrt(16), bulk, bias and
     extremes bounded).  Also at full size: sharding by phonon id changes no integer (2 shards vs 1)."""
+    if name not in T.all_case_names():
+        pytest.skip("fixture geometry missing")
     gold = T.golden(name)
     reduced = T.case_model(name)["settings"]["num_phonons"]
     model = T.load_model(T.case_model(name), num_phonons=FULL_SIZE[name])

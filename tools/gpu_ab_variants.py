@@ -14,9 +14,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = {  # examples measured in round 1; edit for the next A/B
+VARIANTS = {  # round 2: more resident warps with fewer registers, and the pass-fusion threshold (kernels.cuh: PSIM_FUSE_LANES)
+    "b1024_q96": {"PSIM_BLOCK": 1024, "PSIM_QUEUE_SLOTS": 96},
     "b896_q104": {"PSIM_BLOCK": 896, "PSIM_QUEUE_SLOTS": 104},
-    "b896_q96": {"PSIM_BLOCK": 896, "PSIM_QUEUE_SLOTS": 96},
+    "b640_q128": {"PSIM_BLOCK": 640, "PSIM_QUEUE_SLOTS": 128},
+    "fuse33": {"PSIM_FUSE_LANES": 33},
+    "fuse16": {"PSIM_FUSE_LANES": 16},
+    "fuse30": {"PSIM_FUSE_LANES": 30},
+    "front0": {"PSIM_FLY_FRONT": 0},
 }
 
 
