@@ -307,9 +307,9 @@ __device__ __forceinline__ void warp_stats(const LaunchArgs& a, uint32_t lane, u
 enum : int { SF_B1 = 0, SF_B2, SF_DX, SF_DY, SF_TTS, SF_PACKED, SF_CELL, SF_ID, SF_T, SF_R1, SF_R2, SF_MISC, SF_COUNT };
 // SF_MISC: [9:0] measurement step relative to the launch, [16:10] impacts since the last scatter, [18:17] edge hit,
 //          [31:19] next Philox block of this (phonon, step) stream.  13 bits: a phonon may consume 8191 blocks (scatters,
-//          diffuse wall hits, redraws) inside ONE measurement interval; a kernel that sees more raises the run's
-//          `rng budget` error (psim_gpu_synchronize: PSIM_E_RNG) instead of reusing a block - the lock-step kernel, which
-//          keeps the counter in a register, has no such limit and is what such a model must be run with.
+//          diffuse wall hits, redraws) inside ONE measurement interval; a kernel that sees more drops the phonon and raises
+//          the run's `rng budget` error (psim_gpu_synchronize: PSIM_E_RNG) instead of reusing a block - the lock-step
+//          kernel, which keeps the counter in a register, has no such limit and is what such a model must be run with.
 #define PSIM_MISC_STEP(m) ((m)&1023u)
 #define PSIM_MISC_NCOLL(m) (((m) >> 10) & 127u)
 #define PSIM_MISC_EDGE(m) (((m) >> 17) & 3u)
@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
                 psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
-                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
+                const bool spent = f.rng.block > PSIM_MISC_BLOCK_MAX;  // dropped, the run fails (see drift_kernel_queues)
+                rng_over |= spent;
                 misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
                 slot_f(SF_DX, k) = p.dx;
                 slot_f(SF_DY, k) = p.dy;
@@ -385,7 +386,11 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 slot_f(SF_R2, k) = f.r2;
                 slot_u(SF_MISC, k) = misc;
                 m_sct &= ~(1u << k);
-                m_fly |= 1u << k;
+                if (spent) {
+                    m_free |= 1u << k;
+                } else {
+                    m_fly |= 1u << k;
+                }
             }
         } else if (c_wall == best) {
             // ---- surface interaction, general case: wall (specular / diffuse), emitting surface, material interface,
@@ -415,9 +420,10 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
                 const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
-                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
+                const bool spent = f.rng.block > PSIM_MISC_BLOCK_MAX;
+                rng_over |= spent;
                 m_wall &= ~(1u << k);
-                if (ev == psim::EV_DEAD) {
+                if (ev == psim::EV_DEAD || spent) {
                     ++n_steps;
                     ++n_absorbed;
                     m_free |= 1u << k;
@@ -790,6 +796,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             psim::Phonon p;
             psim::Flight f;
             uint32_t misc = 0;
+            bool alive = false;
             p.dx = p.dy = 0.f;
             p.packed = 0u;
             if (act) {
@@ -809,10 +816,15 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
                 psim::scatter_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
-                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
+                // A phonon that has used up the Philox blocks of this interval is DROPPED and the run fails (PSIM_E_RNG): were it
+                // to go on with a frozen block it would redraw the same time to scatter for ever - and if that time is below the
+                // fp32 resolution of the time left in a long interval, the launch would never end.
+                alive = f.rng.block <= PSIM_MISC_BLOCK_MAX;
+                rng_over |= !alive;
                 misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
             }
-            dest = fuse ? fly(act, k, p, f, misc, true) : park(act, k, p, f, misc);
+            dest = fuse ? fly(alive, k, p, f, misc, true) : park(alive, k, p, f, misc);
+            if (act && !alive) { dest = Q_FREE; }
         } else if (c_wall == best) {
             // ---- surface interaction, general case: wall (specular / diffuse), emitting surface, material interface,
             //      transition into a sensor area with other rates, partial edges, stuck-phonon guard; then fly
@@ -846,8 +858,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
                 f.vel = psim::phonon_velocity(P, p.packed);
                 const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
-                rng_over |= f.rng.block > PSIM_MISC_BLOCK_MAX;
-                if (ev == psim::EV_DEAD) {
+                const bool spent = f.rng.block > PSIM_MISC_BLOCK_MAX;  // dropped, see the scatter pass
+                rng_over |= spent;
+                if (ev == psim::EV_DEAD || spent) {
                     ++n_steps;
                     ++n_absorbed;
                 } else {

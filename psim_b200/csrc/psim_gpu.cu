@@ -69,8 +69,6 @@ struct psim_gpu {
     unsigned long long* d_hist = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    void* pinned = nullptr;          // staging buffer of psim_gpu_get_tallies
-    size_t pinned_bytes = 0;
     bool have_sources = false;
     bool timing_open = false;
     uint32_t next_step = 0;
@@ -593,36 +591,27 @@ int psim_gpu_get_tallies(psim_gpu* h, int32_t* energy, double* flux, int64_t* fl
     const uint32_t R = h->P.recorded_steps, S = h->P.n_sensors;
     const size_t n = static_cast<size_t>(R) * S;
     if (n == 0 || (!energy && !flux && !flux_fixed)) { return PSIM_OK; }
-    // device [R][S] -> caller [S][R] (the reference's per-sensor vectors): transposed and converted on the device, then one
-    // copy per requested array through a pinned staging buffer (31 MB of tallies on the kinked wire: the pageable copy and
-    // the host-side transpose through two temporary vectors were the slowest part of a run's epilogue)
+    // device [R][S] -> caller [S][R] (the reference's per-sensor vectors): transposed and converted ON THE DEVICE, then one
+    // copy per requested array straight into the caller's buffer (31 MB of tallies on the kinked wire: the host-side
+    // transpose through two temporary vectors was the slowest part of a run's epilogue in round 1).  A pinned staging buffer
+    // of that size was measured and dropped: on these boxes cudaMallocHost + cudaFreeHost of 25 - 50 MB cost 100 - 400 ms
+    // per handle, more than the pageable copy they would have sped up.
     PSIM_CUDA(cudaSetDevice(h->device));
-    const size_t bytes = n * (sizeof(int32_t) + 2 * sizeof(double) + 2 * sizeof(long long)) + 16;
+    const size_t off_f = (n * sizeof(int32_t) + 15) & ~static_cast<size_t>(15);
+    const size_t bytes = off_f + n * (2 * sizeof(double) + 2 * sizeof(long long));
     DeviceBuffer dev;
     PSIM_CUDA(dev.alloc(bytes));
     int32_t* d_e = dev.as<int32_t>();
-    double* d_f = reinterpret_cast<double*>(dev.as<unsigned char>() + ((n * sizeof(int32_t) + 15) & ~static_cast<size_t>(15)));
+    double* d_f = reinterpret_cast<double*>(dev.as<unsigned char>() + off_f);
     long long* d_x = reinterpret_cast<long long*>(d_f + 2 * n);
-    if (h->pinned_bytes < 2 * n * sizeof(double)) {
-        if (h->pinned) { cudaFreeHost(h->pinned); }
-        h->pinned = nullptr;
-        h->pinned_bytes = 0;
-        PSIM_CUDA(cudaMallocHost(&h->pinned, 2 * n * sizeof(double)));
-        h->pinned_bytes = 2 * n * sizeof(double);
-    }
     const dim3 block(32, 8), grid((S + 31) / 32, (R + 31) / 32);
     transpose_tallies_kernel<<<grid, block, 0, h->stream>>>(h->tally_e, h->tally_f, R, S, 1. / static_cast<double>(1 << PSIM_FLUX_FRAC_BITS),
                                                              energy ? d_e : nullptr, flux ? d_f : nullptr, flux_fixed ? d_x : nullptr);
     PSIM_CUDA(cudaGetLastError());
-    auto fetch = [&](void* dst, const void* src, size_t nbytes) -> cudaError_t {
-        cudaError_t e = cudaMemcpyAsync(h->pinned, src, nbytes, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) { e = cudaStreamSynchronize(h->stream); }
-        if (e == cudaSuccess) { std::memcpy(dst, h->pinned, nbytes); }
-        return e;
-    };
-    if (energy) { PSIM_CUDA(fetch(energy, d_e, n * sizeof(int32_t))); }
-    if (flux) { PSIM_CUDA(fetch(flux, d_f, 2 * n * sizeof(double))); }
-    if (flux_fixed) { PSIM_CUDA(fetch(flux_fixed, d_x, 2 * n * sizeof(long long))); }
+    PSIM_CUDA(cudaStreamSynchronize(h->stream));
+    if (energy) { PSIM_CUDA(cudaMemcpy(energy, d_e, n * sizeof(int32_t), cudaMemcpyDeviceToHost)); }
+    if (flux) { PSIM_CUDA(cudaMemcpy(flux, d_f, 2 * n * sizeof(double), cudaMemcpyDeviceToHost)); }
+    if (flux_fixed) { PSIM_CUDA(cudaMemcpy(flux_fixed, d_x, 2 * n * sizeof(long long), cudaMemcpyDeviceToHost)); }
     return PSIM_OK;
 }
 
@@ -766,7 +755,6 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaFree(h->carry_f);
     cudaFree(h->d_stats);
     cudaFree(h->d_hist);
-    if (h->pinned) { cudaFreeHost(h->pinned); }
     if (h->ev_begin) { cudaEventDestroy(h->ev_begin); }
     if (h->ev_end) { cudaEventDestroy(h->ev_end); }
     if (h->stream) { cudaStreamDestroy(h->stream); }

@@ -39,7 +39,7 @@ def test_struct_layouts_match_headers(built_library):
     assert C.sizeof(psim.Emitter) == 48
     assert C.sizeof(psim.Source) == 24
     assert C.sizeof(psim.Table) == 16
-    assert C.sizeof(psim.ModelDesc) == 104
+    assert C.sizeof(psim.ModelDesc) == 112  # + step_sensors (round 2)
 
 
 def test_no_device_is_a_loud_error(built_library):

@@ -147,3 +147,52 @@ def test_rate_class_records_equal_per_sensor_records():
     b = gpu_run_case(model, 2, options={"kernel": 1}, finish=False)
     assert a["stats"][0]["drift_steps"] > 0
     assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["fixed"], b["fixed"])
+
+
+@pytest.mark.parametrize("name", ["linear_demo", "sides_per", "sides_trans"])
+def test_reiterated_runs_on_the_device_match_the_reference_with_its_iteration_cap_raised(name):
+    """SURVEY.md 8 f2 on the CUDA path: psim_model_run with max_iters = 3 - after every iteration the host takes the new t_eq,
+    the sensors' steady temperatures, tables and heat capacities (per measurement step for a transient run: per-(sensor, step)
+    records in the device image, device_core.cuh:load_rates) and the GPU simulates again - against fixtures from the
+    reference compiled with MAX_ITERS raised to 3 (oracle/Makefile: ref_iters3).  tests/test_emu.py holds the same check for
+    the CPU build of the device functions."""
+    import os
+    from tests import cases
+    gold_path = os.path.join(T.GOLDEN, name + ".iters3.npz")
+    if not os.path.exists(gold_path):
+        pytest.skip("fixture missing")
+    gold = np.load(gold_path)
+    model = cases.iteration_cases()[name]
+    runs = []
+    for seed in range(1, 9):
+        m = T.load_model(model)
+        m.set_max_iters(3)
+        st = m.run(device=0, seed=100 * seed)
+        six, temps, fluxes = m.results(0)
+        info = m.info
+        e = np.zeros((info.num_sensors, info.recorded_steps), dtype=np.int32)  # (tallies are not part of this comparison)
+        runs.append({"out6": six, "temp_blk": T.blocks(temps, T.NBLOCKS), "flux_blk": T.blocks(fluxes, T.NBLOCKS)})
+        assert st.drift_steps > 0 and e.shape[0] > 0
+        m.close()
+    if model["settings"]["sim_type"] == 0:
+        z = T.welch_z(runs, gold, "out6")
+        T.assert_parity(z[:, 0], f"{name} x3 temperature column")
+        T.assert_parity(z[:, 2], f"{name} x3 x-flux column")
+    else:
+        T.assert_parity(T.welch_z(runs, gold, "temp_blk"), f"{name} x3 temperature trace")
+        T.assert_parity(T.welch_z(runs, gold, "flux_blk"), f"{name} x3 flux trace")
+
+
+def test_one_iteration_is_the_default_and_three_change_the_answer():
+    """max_iters = 1 (the reference as shipped) must stay what every other test checks; with three iterations the steady-state
+    bar re-centres t_eq on the mean sensor temperature (309 K between walls at 340 K and 280 K) and its cells emit."""
+    from tests import cases
+    model = cases.iteration_cases()["linear_demo"]
+    one = T.load_model(model)
+    s1 = one.run(device=0, seed=5)
+    three = T.load_model(model)
+    three.set_max_iters(3)
+    s3 = three.run(device=0, seed=5)
+    a, b = one.results(0)[0], three.results(0)[0]
+    assert s3.total_phonons >= s1.total_phonons - 100 and not np.allclose(a[:, 0], b[:, 0], atol=0.05)
+    assert abs(a[:, 0].mean() - 300.0) > 5.0  # one iteration: linearised about t_eq = 300 K, the walls are not symmetric about it
