@@ -39,7 +39,9 @@ PSIM_HD float f_div(float a, float b) {  // a / b with one MUFU.RCP (1 ulp) - am
 }
 PSIM_HD float f_inf() { return __int_as_float(0x7f800000); }
 template<typename T> PSIM_HD T ldg(const T* p) { return __ldg(p); }
-PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint4*>(cells + i)); }
+PSIM_HD uint4 load_cell_links(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint4*>(cells + i)); }
+PSIM_HD uint2 load_cell_tail(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint2*>(&cells[i].sensor_mat)); }
+PSIM_HD uint2 load_cell_tris(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint2*>(cells[i].tri)); }
 PSIM_HD float4 load_shape_matrix(const DevShape* shapes, uint32_t i) { return __ldg(reinterpret_cast<const float4*>(shapes + i)); }
 PSIM_HD float2 load_shape_normal(const DevShape* shapes, uint32_t i, uint32_t e) {
     return __ldg(reinterpret_cast<const float2*>(shapes[i].n) + e);
@@ -60,9 +62,19 @@ PSIM_HD float f_sqrt(float x) { return std::sqrt(x); }
 PSIM_HD float f_div(float a, float b) { return a / b; }
 PSIM_HD float f_inf() { return INFINITY; }
 template<typename T> PSIM_HD T ldg(const T* p) { return *p; }
-PSIM_HD uint4 load_cell_info(const DevCell* cells, uint32_t i) {
+PSIM_HD uint4 load_cell_links(const DevCell* cells, uint32_t i) {
     uint4 q;
-    q.x = cells[i].link[0], q.y = cells[i].link[1], q.z = cells[i].link[2], q.w = cells[i].sensor_mat;
+    q.x = cells[i].link[0], q.y = cells[i].link[1], q.z = cells[i].link[2], q.w = cells[i].link[3];
+    return q;
+}
+PSIM_HD uint2 load_cell_tail(const DevCell* cells, uint32_t i) {
+    uint2 q;
+    q.x = cells[i].sensor_mat, q.y = cells[i].shape;
+    return q;
+}
+PSIM_HD uint2 load_cell_tris(const DevCell* cells, uint32_t i) {
+    uint2 q;
+    q.x = cells[i].tri[0], q.y = cells[i].tri[1];
     return q;
 }
 PSIM_HD float4 load_shape_matrix(const DevShape* shapes, uint32_t i) {
@@ -80,10 +92,21 @@ PSIM_HD uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 PSIM_HD DevSensor load_sensor(const DevSensor* sensors, uint32_t i) { return sensors[i]; }
 #endif
 
+// A phonon's cell word is TAGGED (PSIM_CELL_INDEX / PSIM_CELL_QUAD); every loader takes the tagged word.
+PSIM_HD uint32_t link_of_edge(const uint4 links, uint32_t e) { return (e == 0u) ? links.x : ((e == 1u) ? links.y : ((e == 2u) ? links.z : links.w)); }
+PSIM_HD uint32_t cell_sensor_word(const DevParams& P, uint32_t cell) { return ldg(&P.cells[PSIM_CELL_INDEX(cell)].sensor_mat); }
 // geometry of a cell = its shape record (device_types.h: DevShape)
-PSIM_HD float4 load_cell_matrix(const DevParams& P, uint32_t cell) { return load_shape_matrix(P.shapes, ldg(&P.cell_shape[cell])); }
-PSIM_HD float2 load_cell_normal(const DevParams& P, uint32_t cell, uint32_t e) { return load_shape_normal(P.shapes, ldg(&P.cell_shape[cell]), e); }
-PSIM_HD float load_cell_spec(const DevParams& P, uint32_t cell) { return ldg(&P.shapes[ldg(&P.cell_shape[cell])].spec); }
+PSIM_HD float4 load_cell_matrix(const DevParams& P, uint32_t cell) { return load_shape_matrix(P.shapes, ldg(&P.cells[PSIM_CELL_INDEX(cell)].shape)); }
+PSIM_HD float2 load_cell_normal(const DevParams& P, uint32_t cell, uint32_t e) {
+    return load_shape_normal(P.shapes, ldg(&P.cells[PSIM_CELL_INDEX(cell)].shape), e);
+}
+PSIM_HD float load_cell_spec(const DevParams& P, uint32_t cell) { return ldg(&P.shapes[ldg(&P.cells[PSIM_CELL_INDEX(cell)].shape)].spec); }
+// the model-file cell a phonon at (b1, b2) of flight cell `cell` is in: a parallelogram holds one triangle on either side of
+// its diagonal b1 = b2 (device_types.h: DevCell::tri)
+PSIM_HD uint32_t api_cell_of(const DevParams& P, uint32_t cell, float b1, float b2) {
+    const uint2 t = load_cell_tris(P.cells, PSIM_CELL_INDEX(cell));
+    return (b1 >= b2) ? t.x : t.y;
+}
 // relaxation-rate record of the sensor area a cell word names, at measurement step `step`: the record of its rate class
 // where it has one (a handful of records for the whole mesh), the sensor's own otherwise; a transient run that re-iterates
 // has one record per (sensor, step) (TransientController::getSteadyTemp / scatterUpdate, sensorController.cpp:80-88)
@@ -274,11 +297,22 @@ PSIM_HD float clamp01(float x) {
 #endif
 }
 
-// position on edge `e` at fraction s from the edge's first vertex
-PSIM_HD void place_on_edge(uint32_t e, float s, Phonon& p) {
+// position on edge `e` of a triangle / parallelogram at fraction s from the edge's first vertex (device_types.h)
+PSIM_HD void place_on_edge(uint32_t quad, uint32_t e, float s, Phonon& p) {
     const float r = 1.f - s;
-    p.b1 = (e == 0u) ? s : ((e == 1u) ? r : 0.f);
-    p.b2 = (e == 0u) ? 0.f : ((e == 1u) ? s : r);
+    if (quad) {  // 0: b2 = 0 (s = b1)   1: b1 = 1 (s = b2)   2: b2 = 1 (s = 1 - b1)   3: b1 = 0 (s = 1 - b2)
+        p.b1 = (e == 0u) ? s : ((e == 1u) ? 1.f : ((e == 2u) ? r : 0.f));
+        p.b2 = (e == 0u) ? 0.f : ((e == 1u) ? s : ((e == 2u) ? 1.f : r));
+    } else {     // 0: b2 = 0 (s = b1)   1: b1 + b2 = 1 (s = b2)   2: b1 = 0 (s = 1 - b2)
+        p.b1 = (e == 0u) ? s : ((e == 1u) ? r : 0.f);
+        p.b2 = (e == 0u) ? 0.f : ((e == 1u) ? s : r);
+    }
+}
+
+// ... and back: where on edge `e` the point (b1, b2) of that edge lies
+PSIM_HD float edge_coordinate(uint32_t quad, uint32_t e, float b1, float b2) {
+    if (quad) { return (e == 0u) ? b1 : ((e == 1u) ? b2 : ((e == 2u) ? 1.f - b1 : 1.f - b2)); }
+    return (e == 0u) ? b1 : ((e == 1u) ? b2 : 1.f - b2);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -308,17 +342,22 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     const float u_a = rng_u01(rng), u_b = rng_u01(rng), u_c = rng_u01(rng), u_d = rng_u01(rng);
     float vel;
     if (src.kind == 0u) {
-        p.cell = src.index;
-        const uint4 info = load_cell_info(P.cells, p.cell);
-        const DevSensor s = load_rates(P, info.w, 0u);  // born at t = 0
-        sample_table(P, s.base_table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
+        const DevApiCell ac = P.api_cells[src.index];  // the model-file triangle: its flight cell and its corners in that frame
+        p.cell = ac.cell;
+        const uint32_t sm = cell_sensor_word(P, p.cell);
+        const DevSensor s = load_rates(P, sm, 0u);  // born at t = 0
+        sample_table(P, s.base_table, PSIM_CELL_MAT(sm), u_bin, u_pol, u_jit, p, vel);
         float r1 = u_a, r2 = u_b;
         if (r1 + r2 > 1.f) {
             r1 = 1.f - r1;
             r2 = 1.f - r2;
         }
-        p.b1 = r1;
-        p.b2 = r2;
+        // Triangle::getRandPoint (geometry.cpp:234-242): p1 + (p2 - p1) r1 + (p3 - p1) r2, in the frame of the flight cell
+        const float x1 = static_cast<float>(ac.corners & 1u), y1 = static_cast<float>((ac.corners >> 1) & 1u);
+        const float x2 = static_cast<float>((ac.corners >> 2) & 1u), y2 = static_cast<float>((ac.corners >> 3) & 1u);
+        const float x3 = static_cast<float>((ac.corners >> 4) & 1u), y3 = static_cast<float>((ac.corners >> 5) & 1u);
+        p.b1 = x1 + (x2 - x1) * r1 + (x3 - x1) * r2;
+        p.b2 = y1 + (y2 - y1) * r1 + (y3 - y1) * r2;
         isotropic_direction(u_c, u_d, vel, p);
         rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
         p.tts = draw_scatter_time(P, s, p, rng_u01(rng));
@@ -326,24 +365,24 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     }
     const DevEmitter em = P.emitters[src.index];
     p.cell = em.cell;
-    const uint4 info = load_cell_info(P.cells, p.cell);
+    const uint32_t sm = cell_sensor_word(P, p.cell);
     // birth time: uniform over the part of measurement step `step` that lies inside the emission window
     const double step_lo = static_cast<double>(step) * P.step_time_d;
     const double lo = fmax(em.start - step_lo, 0.), hi = fmin(em.start + em.duration - step_lo, P.step_time_d);
     double frac = (lo + (hi - lo) * static_cast<double>(u_time)) / P.step_time_d;
     frac = frac < 0. ? 0. : (frac > 0.999999 ? 0.999999 : frac);
     (void)j;
-    sample_table(P, em.table, PSIM_CELL_MAT(info.w), u_bin, u_pol, u_jit, p, vel);
-    place_on_edge(em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
+    sample_table(P, em.table, PSIM_CELL_MAT(sm), u_bin, u_pol, u_jit, p, vel);
+    place_on_edge(PSIM_CELL_QUAD(p.cell), em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
     const float2 n = load_cell_normal(P, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
-        p.packed = (p.packed & 0xFF000800u) | 1u | (PSIM_CELL_MAT(info.w) << 12);
+        p.packed = (p.packed & 0xFF000800u) | 1u | (PSIM_CELL_MAT(sm) << 12);
         p.dx = 1000.f * n.x;
         p.dy = 1000.f * n.y;
     } else {
         diffuse_direction(u_b, u_c, n.x, n.y, vel, p);
     }
-    p.tts = draw_scatter_time(P, load_rates(P, info.w, step), p, u_d);
+    p.tts = draw_scatter_time(P, load_rates(P, sm, step), p, u_d);
     return static_cast<float>((1. - frac) * P.step_time_d);
 }
 
@@ -398,7 +437,7 @@ PSIM_HD float draw_scatter_time(const DevParams& P, const DevSensor& sen, const 
 
 PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, float t, uint32_t step) {
     set_cell_matrix(f, load_cell_matrix(P, p.cell));
-    f.sensor_mat = load_cell_info(P.cells, p.cell).w;
+    f.sensor_mat = cell_sensor_word(P, p.cell);
     f.vel = phonon_velocity(P, p.packed);
     update_rates_of_motion(f, p);
     f.t = t;
@@ -418,14 +457,19 @@ PSIM_HD void interval_begin(const DevParams& P, const Phonon& p, Flight& f, floa
 template<class OnMeasure>
 PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s, uint32_t step_end, uint32_t& n_steps,
                           OnMeasure&& on_measure) {
-    // times to the three edges (b2 = 0, b1 + b2 = 1, b1 = 0); a position that rounding left marginally outside gives a
-    // negative time, taken as 0, so that the edge reached is always the one whose time equals the minimum
+    // times to the edges, one division per axis; a position that rounding left marginally outside gives a negative time,
+    // taken as 0, so that the edge reached is always the one whose time equals the minimum.
+    //   b2 axis: edge 0 (b2 = 0) when moving down; a parallelogram also has edge 2 (b2 = 1) when moving up
+    //   b1 axis: edge 2 of a triangle / 3 of a parallelogram (b1 = 0) when moving left; a parallelogram also edge 1 (b1 = 1)
+    //   the hypotenuse of a triangle (edge 1, b1 + b2 = 1)
     const float inf = f_inf();
-    const float t0 = (f.r2 < 0.f) ? fmaxf(f_div(-p.b2, f.r2), 0.f) : inf;
-    const float t2 = (f.r1 < 0.f) ? fmaxf(f_div(-p.b1, f.r1), 0.f) : inf;
+    const bool quad = PSIM_CELL_QUAD(p.cell) != 0u;
+    const bool down = f.r2 < 0.f, left = f.r1 < 0.f;
+    const float tA = (down || (quad && f.r2 > 0.f)) ? fmaxf(f_div(down ? -p.b2 : 1.f - p.b2, f.r2), 0.f) : inf;
+    const float tB = (left || (quad && f.r1 > 0.f)) ? fmaxf(f_div(left ? -p.b1 : 1.f - p.b1, f.r1), 0.f) : inf;
     const float rs = f.r1 + f.r2;
-    const float t1 = (rs > 0.f) ? fmaxf(f_div(1.f - p.b1 - p.b2, rs), 0.f) : inf;
-    const float th = fminf(t0, fminf(t1, t2));
+    const float tC = (!quad && rs > 0.f) ? fmaxf(f_div(1.f - p.b1 - p.b2, rs), 0.f) : inf;
+    const float th = fminf(tA, fminf(tC, tB));
     const bool impact = th <= p.tts;        // reference: impact_time <= time (modelSimulator.cpp:111)
     const float te = impact ? th : p.tts;   // time to the next physical event
     int ev = impact ? EV_IMPACT : EV_SCATTER;
@@ -453,14 +497,18 @@ PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s,
     f.t = t_left;
     const float nb1 = p.b1 + f.r1 * flown, nb2 = p.b2 + f.r2 * flown;
     p.tts = (ev == EV_SCATTER) ? 0.f : p.tts - flown;
-    // an impact snaps the position onto the edge it reached
-    const bool is0 = th == t0, is1 = !is0 && th == t1, hit = ev == EV_IMPACT;
-    const float c1 = clamp01(nb1), c2 = clamp01(nb2), r2 = 1.f - c2;
-    const float hb1 = is0 ? c1 : (is1 ? r2 : 0.f), hb2 = is0 ? 0.f : c2;
+    // an impact snaps the position onto the edge it reached (ties: b2 axis, then hypotenuse, then b1 axis - for a triangle
+    // the order 0, 1, 2)
+    const bool isA = th == tA, isC = !isA && th == tC, hit = ev == EV_IMPACT;
+    const float c1 = clamp01(nb1), c2 = clamp01(nb2);
+    const float wall2 = down ? 0.f : 1.f, wall1 = left ? 0.f : 1.f;  // the coordinate line reached on either axis
+    const float hb1 = isA ? c1 : (isC ? 1.f - c2 : wall1), hb2 = isA ? wall2 : c2;
     p.b1 = hit ? hb1 : nb1;
     p.b2 = hit ? hb2 : nb2;
-    f.edge = hit ? (is0 ? 0u : (is1 ? 1u : 2u)) : 0u;
-    f.s_hit = is0 ? c1 : (is1 ? c2 : r2);  // fraction of the edge from its first vertex
+    const uint32_t eA = down ? 0u : 2u, eB = quad ? (left ? 3u : 1u) : 2u;
+    f.edge = hit ? (isA ? eA : (isC ? 1u : eB)) : 0u;
+    // fraction of the edge from its first vertex (device_types.h: edges run counter to b1 on edge 2 and to b2 on the b1 = 0 edge)
+    f.s_hit = isA ? (down ? c1 : 1.f - c1) : (isC ? c2 : (left ? 1.f - c2 : c2));
     return ev;
 }
 
@@ -475,29 +523,28 @@ PSIM_HD bool rates_differ(uint32_t cell_word_a, uint32_t cell_word_b) {
 // Fast path of a surface interaction, taken inline by the flight loop: the edge is wholly a transition into a
 // neighbour cell with the same material and rate class (by far the most frequent impact inside a mesh).
 // Everything else (walls, emitters, material interfaces, partial edges, stuck-phonon guard) goes to impact_event.
-PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f, const uint4 info /* record of p.cell */) {
-    const uint32_t link = (f.edge == 0u) ? info.x : ((f.edge == 1u) ? info.y : info.z);
+PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f, const uint4 links /* of p.cell */) {
+    const uint32_t link = link_of_edge(links, f.edge);
     if (PSIM_LINK_KIND(link) != PSIM_LINK_TRANSITION || f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
-    const uint32_t ncell = PSIM_LINK_INDEX(link);
-    const uint32_t nsm = load_cell_info(P.cells, ncell).w;
-    if (rates_differ(nsm, f.sensor_mat)) { return false; }
-    place_on_edge((link >> 28) & 3u, (link & (1u << 27)) ? f.s_hit : 1.f - f.s_hit, p);
+    const uint32_t ncell = PSIM_LINK_CELL(link);
+    const uint2 tail = load_cell_tail(P.cells, PSIM_CELL_INDEX(ncell));  // (sensor / class / material word, shape)
+    if (rates_differ(tail.x, f.sensor_mat)) { return false; }
+    place_on_edge(PSIM_CELL_QUAD(ncell), (link >> 28) & 3u, (link & (1u << 27)) ? f.s_hit : 1.f - f.s_hit, p);
     p.cell = ncell;
-    f.sensor_mat = nsm;
-    set_cell_matrix(f, load_cell_matrix(P, ncell));
+    f.sensor_mat = tail.x;
+    set_cell_matrix(f, load_shape_matrix(P.shapes, tail.y));
     update_rates_of_motion(f, p);
     ++f.ncoll;
     return true;
 }
-PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) { return fast_transition(P, p, f, load_cell_info(P.cells, p.cell)); }
+PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) { return fast_transition(P, p, f, load_cell_links(P.cells, PSIM_CELL_INDEX(p.cell))); }
 
 PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     f.rng.left = 0;  // every event that needs random numbers starts a fresh Philox block of its (phonon, step) stream
     const uint32_t e = f.edge;
     const float s = f.s_hit;
     const uint32_t id_hi = PSIM_PACK_IDHI(p.packed);
-    const uint4 info = load_cell_info(P.cells, p.cell);
-    uint32_t link = (e == 0u) ? info.x : ((e == 1u) ? info.y : info.z);
+    uint32_t link = link_of_edge(load_cell_links(P.cells, PSIM_CELL_INDEX(p.cell)), e);
     float ma = (link & (1u << 27)) ? 1.f : -1.f, mb = (link & (1u << 27)) ? 0.f : 1.f;
     if (PSIM_LINK_KIND(link) == PSIM_LINK_COMPOSITE) {
         const uint32_t first = (link >> 7) & 0xFFFFFu, n = link & 0x7Fu;
@@ -520,8 +567,8 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     uint32_t ncell = 0u, nsm = 0u, need = (spec >= 1.f) ? 0u : 3u;
     bool pass = true;
     if (kind == PSIM_LINK_TRANSITION) {
-        ncell = PSIM_LINK_INDEX(link);
-        nsm = load_cell_info(P.cells, ncell).w;
+        ncell = PSIM_LINK_CELL(link);
+        nsm = cell_sensor_word(P, ncell);
         const uint32_t nmat = PSIM_CELL_MAT(nsm);
         if (nmat != PSIM_CELL_MAT(f.sensor_mat)) {  // material interface: no state above the neighbour's cutoff
             const float wmax = PSIM_PACK_TA(p.packed) ? ldg(&P.materials[nmat].w_max_ta) : ldg(&P.materials[nmat].w_max_la);
@@ -532,7 +579,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     rng_need(f.rng, need, P, step, p.id_lo, id_hi);
     if (kind == PSIM_LINK_TRANSITION) {
         if (pass) {
-            place_on_edge((link >> 28) & 3u, clamp01(ma * s + mb), p);
+            place_on_edge(PSIM_CELL_QUAD(ncell), (link >> 28) & 3u, clamp01(ma * s + mb), p);
             p.cell = ncell;
             const bool new_sensor = rates_differ(nsm, f.sensor_mat);
             f.sensor_mat = nsm;
@@ -559,7 +606,7 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
         // reference also forfeits the rest of that free-flight segment - not reproduced, it never fires in practice)
         rng_need(f.rng, 2u, P, step, p.id_lo, id_hi);
         float q1 = rng_u01(f.rng), q2 = rng_u01(f.rng);
-        if (q1 + q2 > 1.f) {
+        if (!PSIM_CELL_QUAD(p.cell) && q1 + q2 > 1.f) {  // (a parallelogram is the whole unit square of its frame)
             q1 = 1.f - q1;
             q2 = 1.f - q2;
         }

@@ -1,13 +1,22 @@
 // Plain-old-data records shared by the host flattener (flatten.cpp) and the CUDA kernels (kernels.cu).
 // Everything the per-phonon loop reads is in these structs; nothing here owns memory.
 //
-// Coordinates: a phonon's position is stored in the BARYCENTRIC frame of its current triangular cell,
-//   p = P1 + b1 (P2 - P1) + b2 (P3 - P1),    b1 >= 0, b2 >= 0, b1 + b2 <= 1,
-// so the three boundary edges are the coordinate lines b2 = 0 (edge 0, P1->P2), b1 + b2 = 1 (edge 1, P2->P3)
-// and b1 = 0 (edge 2, P3->P1), and "time to hit an edge" is one division per edge.  The reference instead
-// intersects the path segment with three slope/intercept lines in absolute fp64 coordinates
-// (reference psim/src/modelSimulator.cpp:87-122, geometry.cpp:104-138); in fp32 that is not watertight, the
-// barycentric form is (a phonon can never be outside its own cell), and it costs a fraction of the arithmetic.
+// Coordinates: a phonon's position is stored in the AFFINE frame of its current flight cell,
+//   p = Q0 + b1 u + b2 v.
+// A flight cell is either one triangular cell of the model file (u = P2 - P1, v = P3 - P1; b1 >= 0, b2 >= 0, b1 + b2 <= 1;
+// edges: 0 b2 = 0 (P1->P2), 1 b1 + b2 = 1 (P2->P3), 2 b1 = 0 (P3->P1)) or a PARALLELOGRAM made of two of them
+// (0 <= b1, b2 <= 1; edges: 0 b2 = 0, 1 b1 = 1, 2 b2 = 1, 3 b1 = 0), and "time to hit an edge" is one division per axis.
+// The reference instead intersects the path segment with three slope/intercept lines in absolute fp64 coordinates
+// (reference psim/src/modelSimulator.cpp:87-122, geometry.cpp:104-138); in fp32 that is not watertight, the frame form
+// is (a phonon can never be outside its own cell), and it costs a fraction of the arithmetic.
+//
+// Why parallelograms: the reference's builder makes every sensor area a rectangle cut into two triangles
+// (builder_tools.py:addRectangularCell).  Crossing that diagonal does nothing to a phonon (same sensor, same material:
+// TransitionSurface::handlePhonon, surface.cpp:71-75, only re-labels its cell), yet it ends a flight segment: 17 - 40 % of
+// all segments of the shipped models are such crossings.  flatten.cpp therefore merges two triangles
+// into one flight cell where that is exactly neutral - same sensor, same specularity, the shared edge a plain whole-edge
+// transition, the union a parallelogram - and the per-phonon loop never sees the diagonal.  Everything the API speaks
+// (cell indices of sources, the per-cell histogram) stays in triangles: DevApiCell / DevCell::tri translate.
 #ifndef PSIM_B200_DEVICE_TYPES_H
 #define PSIM_B200_DEVICE_TYPES_H
 
@@ -28,11 +37,17 @@
 
 // edge link word: [31:30] kind, then payload
 #define PSIM_LINK_BOUNDARY 0u    // payload unused
-#define PSIM_LINK_TRANSITION 1u  // [29:28] neighbour edge, [27] same-direction flag, [26:0] neighbour cell
+#define PSIM_LINK_TRANSITION 1u  // [29:28] neighbour edge, [27] same-direction flag, [26] neighbour is a parallelogram, [25:0] neighbour flight cell
 #define PSIM_LINK_EMIT 2u        // [26:0] emitter index
 #define PSIM_LINK_COMPOSITE 3u   // [26:7] first sub-surface, [6:0] number of sub-surfaces
 #define PSIM_LINK_KIND(w) ((w) >> 30)
-#define PSIM_LINK_INDEX(w) ((w)&0x07FFFFFFu)
+#define PSIM_LINK_INDEX(w) ((w)&0x07FFFFFFu)                          // emitter index
+#define PSIM_LINK_CELL(w) (((w)&0x03FFFFFFu) | (((w) >> 26 & 1u) << 31))  // tagged flight cell word of the neighbour
+
+// A phonon's cell word: [25:0] flight cell, [31] that cell is a parallelogram (the flight needs to know before it has
+// loaded anything)
+#define PSIM_CELL_INDEX(c) ((c)&0x03FFFFFFu)
+#define PSIM_CELL_QUAD(c) ((c) >> 31)
 
 // DevCell::sensor_mat.  Rate class: sensors with the same material and the same temperature have identical
 // relaxation rates; 255 = unclassified (more than 255 distinct classes in the model).
@@ -46,23 +61,33 @@
 #define PSIM_ALIGN(n) alignas(n)
 #endif
 
-// What every cell transition needs, 16 bytes per cell: what lies behind the three edges and which sensor area /
-// rate class / material the cell belongs to.  The cell's GEOMETRY (barycentric rate matrix, inward normals) and its
-// specularity live in a table of distinct SHAPES: the meshes the reference's builder makes are unions of rectangles
-// cut in two (builder_tools.py:addRectangularCell), so thousands of cells share a few dozen shapes (kinked wire:
-// 6174 cells, 26 shapes) and the records a flight touches - 16 B + a 4-byte shape index per cell - stay in L1 where
-// the 64 B per cell of the first layout did not (profiles/r01_summary.md: L1 hit rate 52 % on that mesh).  A mesh of
-// arbitrary triangles simply has as many shapes as cells.
+// What every cell transition needs, one 32-byte sector per flight cell: what lies behind its (up to four) edges, which
+// sensor area / rate class / material it belongs to, its shape, and the model-file triangles it stands for.  The cell's
+// GEOMETRY (frame matrix, inward normals) and its specularity live in a table of distinct SHAPES: the meshes the
+// reference's builder makes are unions of rectangles, so thousands of cells share a few dozen shapes (kinked wire: 3087
+// flight cells, 13 shapes) and the records a flight touches stay in L1 where the 64 B per triangle of the first layout
+// did not (profiles/r01_summary.md: L1 hit rate 52 % on that mesh; 99 % now).  A mesh of arbitrary triangles simply has
+// as many shapes as cells.
 struct PSIM_ALIGN(16) DevCell {
-    uint32_t link[3];          // what lies behind each edge
+    uint32_t link[4];          // what lies behind each edge (a triangle has three)
     uint32_t sensor_mat;       // [31:12] sensor index, [11:4] rate class, [3:0] material index (PSIM_CELL_*)
+    uint32_t shape;            // index into DevParams::shapes
+    uint32_t tri[2];           // model-file cell(s): a triangle names itself twice; a parallelogram its triangle below the
+                               // diagonal Q0-Q2 (b1 >= b2) and the one above
 };
 
 struct PSIM_ALIGN(16) DevShape {
-    float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [P2-P1 | P3-P1])
-    float n[3][2];             // unit normals of edges 0..2 pointing INTO the cell (geometry.cpp:97-100)
+    float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [u | v])
+    float n[4][2];             // unit normals of edges 0..3 pointing INTO the cell (geometry.cpp:97-100)
     float spec;                // specularity of the cell's boundary surfaces, clamped to [0,1] (cell.cpp:115-119)
-    uint32_t pad;
+    uint32_t pad[3];
+};
+
+// A model-file (API) cell: the flight cell it lives in and where its three vertices sit in that cell's frame, two bits
+// (b1, b2 in {0, 1}) per vertex - what a phonon born "at a random point of cell c" (CellOriginBuilder) needs.
+struct DevApiCell {
+    uint32_t cell;             // tagged flight cell word (PSIM_CELL_*)
+    uint32_t corners;          // [1:0] vertex 1, [3:2] vertex 2, [5:4] vertex 3; bit 0 of a pair = b1, bit 1 = b2
 };
 
 // A part of an edge that is a transition to a neighbour or an emitting surface (compositeSurface.h:60-66).
@@ -93,7 +118,7 @@ struct DevMaterial {
 };
 
 struct PSIM_ALIGN(16) DevEmitter {
-    uint32_t cell, edge;
+    uint32_t cell, edge;    // tagged flight cell word and its edge
     float s_p1, s_p2;       // edge coordinate of the surface's two end points (Line::getRandPoint, geometry.cpp:140-143)
     uint32_t table;         // velocity-weighted table at the surface temperature
     uint32_t pad;
@@ -121,7 +146,7 @@ struct DevBirth {
 
 // Phonon state in HBM: two 16-byte words per phonon, structure-of-arrays.
 //   A = (b1, b2, vx, vy)            position in the cell frame, in-plane velocity = group velocity x projected 3-D direction
-//   B = (tts, packed, cell, id)     tts = time to the next intrinsic scatter (ns)
+//   B = (tts, packed, cell, id)     tts = time to the next intrinsic scatter (ns); cell = tagged flight cell word
 //                                   packed = [9:0] bin, [10] polarisation (1 = TA), [11] sign (1 = negative),
 //                                            [15:12] material the (omega, v) pair was sampled in,
 //                                            [23:16] position of omega inside the bin (1/256ths), [31:24] id bits 39:32
@@ -133,9 +158,9 @@ struct DevBirth {
 #define PSIM_PACK_IDHI(p) ((p) >> 24)
 
 struct DevParams {
-    const DevCell* cells;
-    const uint32_t* cell_shape; // [n_cells] index into shapes
+    const DevCell* cells;       // [n_flight_cells]
     const DevShape* shapes;     // [n_shapes] distinct (geometry, specularity) records
+    const DevApiCell* api_cells; // [n_cells] model-file cells
     const DevSub* subs;
     const DevSensor* sensors;
     const DevSensor* classes;   // [<= 255] one record per rate class (PSIM_CELL_CLASS): the sensors of a class are identical
@@ -146,7 +171,7 @@ struct DevParams {
     const float2* tables;      // [n_tables][PSIM_BINS] (cumulative probability, LA fraction)  (material.cpp:170-180)
     const uint32_t* guides;    // [n_tables][PSIM_GUIDE] search bracket for r in [k/G, (k+1)/G), G = PSIM_GUIDE: low | high << 16
     const float* velocities;   // [n_materials][2][PSIM_BINS] group velocity, LA then TA, m/s == nm/ns
-    uint32_t n_cells, n_shapes, n_sensors, n_materials, n_tables, n_emitters, n_sources;
+    uint32_t n_cells, n_flight_cells, n_shapes, n_sensors, n_materials, n_tables, n_emitters, n_sources;
     uint32_t num_steps;        // measurement steps M
     uint32_t first_tally_step; // reference step_adjustment_ (modelSimulator.h:24-26)
     uint32_t recorded_steps;   // M - first_tally_step

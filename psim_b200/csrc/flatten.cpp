@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <sstream>
+#include <array>
 #include <unordered_map>
 
 namespace psim {
@@ -25,7 +26,7 @@ bool fail(std::string& err, int code, const std::string& msg, int& rc) {
 
 }  // namespace
 
-int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
+int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, bool merge_cells) {
     int rc = 0;
     if (!d.materials || !d.sensors || !d.cells || !d.tables || !d.velocities || d.num_materials == 0 ||
         d.num_sensors == 0 || d.num_cells == 0 || d.num_tables == 0 || (d.num_emitters > 0 && !d.emitters) ||
@@ -197,60 +198,42 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
         }
     }
 
-    // cells
-    out.cells.resize(d.num_cells);
-    out.cell_shape.resize(d.num_cells);
-    // distinct shapes, found by exact comparison of the fp32 records (hash of the bit patterns -> candidates)
-    std::unordered_multimap<uint64_t, uint32_t> shape_index;
-    auto shape_id = [&](const DevShape& sh) -> uint32_t {
-        uint32_t w[sizeof(DevShape) / 4];
-        std::memcpy(w, &sh, sizeof(sh));
-        uint64_t hsh = 0xcbf29ce484222325ull;
-        for (uint32_t x : w) { hsh = (hsh ^ x) * 0x100000001b3ull; }
-        const auto range = shape_index.equal_range(hsh);
-        for (auto it = range.first; it != range.second; ++it) {
-            if (std::memcmp(&out.shapes[it->second], &sh, sizeof(sh)) == 0) { return it->second; }
-        }
-        out.shapes.push_back(sh);
-        shape_index.emplace(hsh, static_cast<uint32_t>(out.shapes.size() - 1));
-        return static_cast<uint32_t>(out.shapes.size() - 1);
+    // ---- cells.  Pass 1: every model-file triangle with its links in MODEL terms (target = model cell, model edge)
+    const uint32_t C = d.num_cells;
+    if (C >= (1u << 26)) {
+        fail(err, PSIM_E_INVALID, "model exceeds packed-index limits (2^26 cells)", rc);
+        return rc;
+    }
+    struct Tri {
+        double x[3], y[3];
+        uint32_t link[3];
+        float spec;
     };
-    for (uint32_t c = 0; c < d.num_cells; ++c) {
+    std::vector<Tri> tri(C);
+    for (uint32_t c = 0; c < C; ++c) {
         const psim_cell& in = d.cells[c];
         if (in.sensor >= d.num_sensors) {
             fail(err, PSIM_E_INVALID, "cell refers to a missing sensor", rc);
             return rc;
         }
+        Tri& t = tri[c];
+        for (int k = 0; k < 3; ++k) {
+            t.x[k] = in.x[k];
+            t.y[k] = in.y[k];
+        }
         const double e1x = in.x[1] - in.x[0], e1y = in.y[1] - in.y[0];
         const double e2x = in.x[2] - in.x[0], e2y = in.y[2] - in.y[0];
-        const double det = e1x * e2y - e2x * e1y;
-        if (!(std::fabs(det) > 0.)) {
+        if (!(std::fabs(e1x * e2y - e2x * e1y) > 0.)) {
             std::ostringstream os;
             os << "cell " << c << " is degenerate";
             fail(err, PSIM_E_INVALID, os.str(), rc);
             return rc;
         }
-        const double m00 = e2y / det, m01 = -e2x / det, m10 = -e1y / det, m11 = e1x / det;
-        auto unit = [](double x, double y, float& ox, float& oy) {
-            const double n = std::sqrt(x * x + y * y);
-            ox = static_cast<float>(x / n);
-            oy = static_cast<float>(y / n);
-        };
-        DevCell o{};
-        DevShape ow{};
-        ow.m00 = static_cast<float>(m00);
-        ow.m01 = static_cast<float>(m01);
-        ow.m10 = static_cast<float>(m10);
-        ow.m11 = static_cast<float>(m11);
-        unit(m10, m11, ow.n[0][0], ow.n[0][1]);                   // edge 0 is b2 = 0: inward = grad b2
-        unit(-(m00 + m10), -(m01 + m11), ow.n[1][0], ow.n[1][1]); // edge 1 is b1 + b2 = 1
-        unit(m00, m01, ow.n[2][0], ow.n[2][1]);                   // edge 2 is b1 = 0
-        ow.spec = static_cast<float>(std::min(1., std::max(0., in.specularity)));
-        o.sensor_mat = (in.sensor << 12) | (sensor_class[in.sensor] << 4) | d.sensors[in.sensor].material;
+        t.spec = static_cast<float>(std::min(1., std::max(0., in.specularity)));
         for (int k = 0; k < 3; ++k) {
             const uint32_t n = in.sub_count[k], first = in.sub_first[k];
             if (n == 0) {
-                o.link[k] = PSIM_LINK_BOUNDARY << 30;
+                t.link[k] = PSIM_LINK_BOUNDARY << 30;
                 continue;
             }
             if (!d.subsurfaces || n > 127 || first >= d.num_subsurfaces || n > d.num_subsurfaces - first) {  // (no 32-bit wrap-around)
@@ -283,14 +266,14 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
             float a, b;
             if (whole && (s0.kind == PSIM_SURF_EMIT ||
                           (std::fabs(std::fabs(s0.t1 - s0.t0) - 1.) < 1e-9 && std::min(s0.t0, s0.t1) < 1e-9))) {
-                o.link[k] = word(s0, a, b);  // the whole edge is one neighbour / one emitter: no sub-table lookup
+                t.link[k] = word(s0, a, b);  // the whole edge is one neighbour / one emitter: no sub-table lookup
                 continue;
             }
             if (out.subs.size() + n >= (1u << 20)) {
                 fail(err, PSIM_E_INVALID, "too many partial-edge sub-surfaces", rc);
                 return rc;
             }
-            o.link[k] = (PSIM_LINK_COMPOSITE << 30) | (static_cast<uint32_t>(out.subs.size()) << 7) | n;
+            t.link[k] = (PSIM_LINK_COMPOSITE << 30) | (static_cast<uint32_t>(out.subs.size()) << 7) | n;
             for (uint32_t i = 0; i < n; ++i) {
                 const psim_subsurface& sb = d.subsurfaces[first + i];
                 DevSub ds{};
@@ -300,14 +283,202 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err) {
                 out.subs.push_back(ds);
             }
         }
-        out.cells[c] = o;
-        out.cell_shape[c] = shape_id(ow);
+    }
+
+    // Pass 2: pair triangles into parallelograms where that is exactly neutral (device_types.h): same sensor area, same
+    // specularity, the shared edge a plain whole-edge transition in both directions, the union a parallelogram.
+    std::vector<int> partner(C, -1), shared(C, -1);
+    std::vector<char> opposite_pair(C, 0);  // the pair's second triangle has the opposite orientation
+    if (merge_cells) {
+        for (uint32_t A = 0; A < C; ++A) {
+            if (partner[A] >= 0) { continue; }
+            for (uint32_t k = 0; k < 3 && partner[A] < 0; ++k) {
+                const uint32_t w = tri[A].link[k];
+                if (PSIM_LINK_KIND(w) != PSIM_LINK_TRANSITION) { continue; }
+                const uint32_t B = w & 0x03FFFFFFu, j = (w >> 28) & 3u;
+                if (B == A || partner[B] >= 0 || d.cells[A].sensor != d.cells[B].sensor || tri[A].spec != tri[B].spec) { continue; }
+                const uint32_t back = tri[B].link[j];
+                if (PSIM_LINK_KIND(back) != PSIM_LINK_TRANSITION || (back & 0x03FFFFFFu) != A || ((back >> 28) & 3u) != k ||
+                    ((back ^ w) & (1u << 27))) {
+                    continue;
+                }
+                // Q0 = A[k+1], Q1 = A[k+2], Q2 = A[k] (A's copy of the diagonal runs Q2 -> Q0), Q3 = B[j+2]: parallelogram iff
+                // Q3 - Q0 = Q2 - Q1.  B's copy of the diagonal runs Q0 -> Q2 if B has A's orientation (the usual case: the
+                // link's same-direction flag is clear) and Q2 -> Q0 if it has the opposite one.
+                const bool opposite = (w & (1u << 27)) != 0u;
+                const Tri &ta = tri[A], &tb = tri[B];
+                const uint32_t a0 = (k + 1) % 3, a1 = (k + 2) % 3, a2 = k, b3 = (j + 2) % 3;
+                const uint32_t b_at_q0 = opposite ? (j + 1) % 3 : j, b_at_q2 = opposite ? j : (j + 1) % 3;
+                const double scale = std::fabs(ta.x[a1] - ta.x[a0]) + std::fabs(ta.y[a1] - ta.y[a0]) + std::fabs(ta.x[a2] - ta.x[a1]) + std::fabs(ta.y[a2] - ta.y[a1]);
+                const double tol = 1e-9 * scale;
+                const bool same_diagonal = std::fabs(tb.x[b_at_q0] - ta.x[a0]) <= tol && std::fabs(tb.y[b_at_q0] - ta.y[a0]) <= tol &&
+                                           std::fabs(tb.x[b_at_q2] - ta.x[a2]) <= tol && std::fabs(tb.y[b_at_q2] - ta.y[a2]) <= tol;
+                const bool parallelogram = std::fabs((tb.x[b3] - ta.x[a0]) - (ta.x[a2] - ta.x[a1])) <= tol &&
+                                           std::fabs((tb.y[b3] - ta.y[a0]) - (ta.y[a2] - ta.y[a1])) <= tol;
+                if (!same_diagonal || !parallelogram) { continue; }
+                partner[A] = static_cast<int>(B);
+                partner[B] = static_cast<int>(A);
+                opposite_pair[A] = opposite_pair[B] = opposite ? 1 : 0;
+                shared[A] = static_cast<int>(k);
+                shared[B] = static_cast<int>(j);
+            }
+        }
+    }
+
+    // Pass 3: flight cells.  (model cell, model edge) -> (flight cell word, flight edge); the shared edge of a pair vanishes.
+    std::vector<uint32_t> cell_word(C, 0);
+    std::vector<std::array<int, 3>> edge_map(C, std::array<int, 3>{ 0, 1, 2 });
+    std::vector<std::array<char, 3>> edge_flip(C, std::array<char, 3>{ 0, 0, 0 });  // the flight edge runs against the model edge
+    out.api_cells.assign(C, DevApiCell{});
+    // distinct shapes, found by exact comparison of the fp32 records (hash of the bit patterns -> candidates)
+    std::unordered_multimap<uint64_t, uint32_t> shape_index;
+    auto shape_id = [&](const DevShape& sh) -> uint32_t {
+        uint32_t w[sizeof(DevShape) / 4];
+        std::memcpy(w, &sh, sizeof(sh));
+        uint64_t hsh = 0xcbf29ce484222325ull;
+        for (uint32_t x : w) { hsh = (hsh ^ x) * 0x100000001b3ull; }
+        const auto range = shape_index.equal_range(hsh);
+        for (auto it = range.first; it != range.second; ++it) {
+            if (std::memcmp(&out.shapes[it->second], &sh, sizeof(sh)) == 0) { return it->second; }
+        }
+        out.shapes.push_back(sh);
+        shape_index.emplace(hsh, static_cast<uint32_t>(out.shapes.size() - 1));
+        return static_cast<uint32_t>(out.shapes.size() - 1);
+    };
+    auto unit = [](double x, double y, float* o) {
+        const double n = std::sqrt(x * x + y * y);
+        o[0] = static_cast<float>(x / n);
+        o[1] = static_cast<float>(y / n);
+    };
+    struct Pending {
+        uint32_t model_cell[4];  // which model cell / edge each flight edge comes from
+        uint32_t model_edge[4];
+        uint32_t n_edges;
+    };
+    std::vector<Pending> pending;
+    for (uint32_t A = 0; A < C; ++A) {
+        if (partner[A] >= 0 && static_cast<uint32_t>(partner[A]) < A) { continue; }  // made together with its partner
+        const uint32_t ic = static_cast<uint32_t>(out.cells.size());
+        const Tri& ta = tri[A];
+        DevCell o{};
+        DevShape sh{};
+        Pending pe{};
+        double ox, oy, ux, uy, vx, vy;
+        const bool quad = partner[A] >= 0;
+        if (quad) {
+            const uint32_t B = static_cast<uint32_t>(partner[A]), k = static_cast<uint32_t>(shared[A]), j = static_cast<uint32_t>(shared[B]);
+            const Tri& tb = tri[B];
+            const uint32_t a0 = (k + 1) % 3, a1 = (k + 2) % 3, a2 = k, b3 = (j + 2) % 3;
+            ox = ta.x[a0], oy = ta.y[a0];
+            ux = ta.x[a1] - ox, uy = ta.y[a1] - oy;
+            vx = tb.x[b3] - ox, vy = tb.y[b3] - oy;
+            const bool opposite = opposite_pair[A] != 0;
+            // flight edges 2 (Q2 -> Q3) and 3 (Q3 -> Q0): B's edges j+1, j+2 in B's own direction if B has A's orientation,
+            // else its edges j+2 (Q3 -> Q2) and j+1 (Q0 -> Q3), both run backwards
+            const uint32_t be2 = opposite ? (j + 2) % 3 : (j + 1) % 3, be3 = opposite ? (j + 1) % 3 : (j + 2) % 3;
+            pe = Pending{ { A, A, B, B }, { a0, a1, be2, be3 }, 4 };
+            cell_word[A] = cell_word[B] = ic | (1u << 31);
+            edge_map[A][a0] = 0, edge_map[A][a1] = 1, edge_map[A][k] = -1;
+            edge_map[B][be2] = 2, edge_map[B][be3] = 3, edge_map[B][j] = -1;
+            edge_flip[B][be2] = edge_flip[B][be3] = opposite ? 1 : 0;
+            // corners of the model triangles in this frame, two bits (b1, b2) per vertex
+            auto corners = [](uint32_t v_at_00, uint32_t v_at_second, uint32_t second, uint32_t v_at_third, uint32_t third) {
+                return (0u << (2 * v_at_00)) | (second << (2 * v_at_second)) | (third << (2 * v_at_third));
+            };
+            out.api_cells[A] = DevApiCell{ cell_word[A], corners(a0, a1, 1u /* (1,0) */, a2, 3u /* (1,1) */) };
+            out.api_cells[B] = DevApiCell{ cell_word[B], corners(opposite ? (j + 1) % 3 : j, opposite ? j : (j + 1) % 3, 3u /* (1,1) */, b3, 2u /* (0,1) */) };
+            o.tri[0] = A;  // below the diagonal b1 = b2 (it holds the corner (1, 0))
+            o.tri[1] = B;
+        } else {
+            ox = ta.x[0], oy = ta.y[0];
+            ux = ta.x[1] - ox, uy = ta.y[1] - oy;
+            vx = ta.x[2] - ox, vy = ta.y[2] - oy;
+            pe = Pending{ { A, A, A, A }, { 0, 1, 2, 0 }, 3 };
+            cell_word[A] = ic;
+            out.api_cells[A] = DevApiCell{ ic, (1u << 2) | (2u << 4) };  // (0,0), (1,0), (0,1)
+            o.tri[0] = o.tri[1] = A;
+        }
+        const double det = ux * vy - vx * uy;
+        const double m00 = vy / det, m01 = -vx / det, m10 = -uy / det, m11 = ux / det;
+        sh.m00 = static_cast<float>(m00);
+        sh.m01 = static_cast<float>(m01);
+        sh.m10 = static_cast<float>(m10);
+        sh.m11 = static_cast<float>(m11);
+        unit(m10, m11, sh.n[0]);                                   // edge 0 is b2 = 0: inward = grad b2
+        if (quad) {
+            unit(-m00, -m01, sh.n[1]);                             // edge 1 is b1 = 1
+            unit(-m10, -m11, sh.n[2]);                             // edge 2 is b2 = 1
+            unit(m00, m01, sh.n[3]);                               // edge 3 is b1 = 0
+        } else {
+            unit(-(m00 + m10), -(m01 + m11), sh.n[1]);             // edge 1 is b1 + b2 = 1
+            unit(m00, m01, sh.n[2]);                               // edge 2 is b1 = 0
+        }
+        sh.spec = ta.spec;
+        const uint32_t sensor = d.cells[A].sensor;
+        o.sensor_mat = (sensor << 12) | (sensor_class[sensor] << 4) | d.sensors[sensor].material;
+        o.shape = shape_id(sh);
+        out.cells.push_back(o);
+        pending.push_back(pe);
+    }
+    // Pass 4: links in flight terms.  A flight edge that runs against its model edge (edge_flip) reverses the edge
+    // coordinate: s -> 1 - s on the owner's side, t -> 1 - t on the side of whoever points at it.
+    auto relabel = [&](uint32_t w, bool own_flipped) -> uint32_t {
+        if (PSIM_LINK_KIND(w) != PSIM_LINK_TRANSITION) { return w; }
+        const uint32_t t = w & 0x03FFFFFFu, e = (w >> 28) & 3u;
+        const uint32_t cw = cell_word[t];
+        const int fe = edge_map[t][e];  // >= 0: nothing but the shared edge of a pair vanishes, and nothing else points at it
+        const bool same_dir = (((w >> 27) & 1u) != 0u) != (own_flipped != (edge_flip[t][e] != 0));
+        return (PSIM_LINK_TRANSITION << 30) | (static_cast<uint32_t>(fe < 0 ? 0 : fe) << 28) | (same_dir ? (1u << 27) : 0u) | ((cw >> 31) << 26) |
+               (cw & 0x03FFFFFFu);
+    };
+    for (size_t ic = 0; ic < out.cells.size(); ++ic) {
+        const Pending& pe = pending[ic];
+        for (uint32_t e = 0; e < pe.n_edges; ++e) {
+            const uint32_t mc = pe.model_cell[e], me = pe.model_edge[e];
+            const bool flipped = edge_flip[mc][me] != 0;
+            const uint32_t w = tri[mc].link[me];
+            if (PSIM_LINK_KIND(w) == PSIM_LINK_COMPOSITE) {  // the partial-edge records of this edge (referenced from here only)
+                const uint32_t first = (w >> 7) & 0xFFFFFu, n = w & 0x7Fu;
+                for (uint32_t i = 0; i < n; ++i) {
+                    DevSub& sb = out.subs[first + i];
+                    if (flipped) {  // s' = 1 - s: extent [1 - s1, 1 - s0], position on the neighbour a (1 - s') + b
+                        const float s0 = sb.s0, s1 = sb.s1;
+                        sb.s0 = 1.f - s1;
+                        sb.s1 = 1.f - s0;
+                        sb.b = sb.a + sb.b;
+                        sb.a = -sb.a;
+                    }
+                    if (PSIM_LINK_KIND(sb.link) == PSIM_LINK_TRANSITION && edge_flip[sb.link & 0x03FFFFFFu][(sb.link >> 28) & 3u]) {
+                        sb.a = -sb.a;  // t' = 1 - t
+                        sb.b = 1.f - sb.b;
+                    }
+                    sb.link = relabel(sb.link, flipped);
+                }
+            }
+            out.cells[ic].link[e] = relabel(w, flipped);
+        }
+    }
+    for (uint32_t e = 0; e < d.num_emitters; ++e) {
+        DevEmitter& em = out.emitters[e];
+        const uint32_t c = em.cell, me = em.edge;  // (model cell, model edge) until here
+        const int fe = edge_map[c][me];
+        if (fe < 0) {
+            fail(err, PSIM_E_INVALID, "emitting surface on an edge shared by two cells", rc);
+            return rc;
+        }
+        em.cell = cell_word[c];
+        em.edge = static_cast<uint32_t>(fe);
+        if (edge_flip[c][me]) {
+            em.s_p1 = 1.f - em.s_p1;
+            em.s_p2 = 1.f - em.s_p2;
+        }
     }
     if (out.subs.empty()) { out.subs.push_back(DevSub{}); }
     if (out.emitters.empty()) { out.emitters.push_back(DevEmitter{}); }
 
     DevParams& P = out.scalars;
     P.n_cells = d.num_cells;
+    P.n_flight_cells = static_cast<uint32_t>(out.cells.size());
     P.n_shapes = static_cast<uint32_t>(out.shapes.size());
     P.n_sensors = d.num_sensors;
     P.n_materials = d.num_materials;

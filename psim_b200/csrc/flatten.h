@@ -12,8 +12,8 @@
 namespace psim {
 
 struct HostImage {
-    std::vector<DevCell> cells;
-    std::vector<uint32_t> cell_shape; // [cells] index into shapes
+    std::vector<DevCell> cells;       // flight cells: model triangles, or parallelograms made of two (device_types.h)
+    std::vector<DevApiCell> api_cells; // [model cells]
     std::vector<DevShape> shapes;     // distinct (geometry, specularity) records
     std::vector<DevSensor> classes;   // one record per rate class (at most 255)
     std::vector<DevSensor> step_sensors;  // empty, or [sensors][steps] (psim_model_desc::step_sensors)
@@ -40,7 +40,8 @@ struct BirthPlan {
 };
 
 // returns 0 or a PSIM_E_* code with `err` set
-int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err);
+// merge_cells = false keeps one flight cell per model triangle (the per-function probes and the A/B option "merge_cells")
+int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, bool merge_cells = true);
 int plan_births(const HostImage& img, const psim_source* sources, size_t n, uint32_t shard, uint32_t num_shards,
                 BirthPlan& out, std::string& err);
 

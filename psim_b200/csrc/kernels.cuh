@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 p.id_lo = slot_u(SF_ID, k);
                 uint32_t misc = slot_u(SF_MISC, k);
                 psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
-                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.sensor_mat = psim::cell_sensor_word(P, p.cell);
                 f.vel = psim::phonon_velocity(P, p.packed);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 p.id_lo = slot_u(SF_ID, k);
                 uint32_t misc = slot_u(SF_MISC, k);
                 f.edge = PSIM_MISC_EDGE(misc);
-                f.s_hit = (f.edge == 0u) ? p.b1 : ((f.edge == 1u) ? p.b2 : 1.f - p.b2);
+                f.s_hit = psim::edge_coordinate(PSIM_CELL_QUAD(p.cell), f.edge, p.b1, p.b2);
                 f.ncoll = PSIM_MISC_NCOLL(misc);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 f.r2 = slot_f(SF_R2, k);
                 f.t = 0.f;
                 psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
-                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.sensor_mat = psim::cell_sensor_word(P, p.cell);
                 f.vel = psim::phonon_velocity(P, p.packed);
                 const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
                 const bool spent = f.rng.block > PSIM_MISC_BLOCK_MAX;
@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 p.b1 = slot_f(SF_B1, k);
                 p.b2 = slot_f(SF_B2, k);
                 p.tts = slot_f(SF_TTS, k);
+                p.cell = slot_u(SF_CELL, k);  // (its tag tells the flight whether the cell is a triangle or a parallelogram)
                 f.t = slot_f(SF_T, k);
                 f.r1 = slot_f(SF_R1, k);
                 f.r2 = slot_f(SF_R2, k);
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 uint32_t s = s0;
                 const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
                     const int32_t sg = PSIM_PACK_NEG(slot_u(SF_PACKED, k)) ? -1 : 1;
-                    const uint32_t sensor = PSIM_CELL_SENSOR(psim::load_cell_info(P.cells, slot_u(SF_CELL, k)).w);
+                    const uint32_t sensor = PSIM_CELL_SENSOR(psim::cell_sensor_word(P, slot_u(SF_CELL, k)));
                     const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k)) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k)) * sg;
                     tally_range(a, acc_e, acc_f, k0, k1, sensor, sg, fx, fy);
                 });
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     p.dx = slot_f(SF_DX, k);
                     p.dy = slot_f(SF_DY, k);
                     p.cell = slot_u(SF_CELL, k);
-                    f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                    f.sensor_mat = psim::cell_sensor_word(P, p.cell);
                     if (psim::fast_transition(P, p, f)) {
                         slot_u(SF_CELL, k) = p.cell;
                         slot_f(SF_R1, k) = f.r1;
@@ -733,17 +734,17 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             misc = ((s != s0) ? (s - a.step_begin) : (misc & ~(3u << 17))) | (f.edge << 17);
             const bool hit = ev == psim::EV_IMPACT;
             if (hit || tk1 > tk0) {
-                const uint4 info = psim::load_cell_info(P.cells, cell0);  // the cell the segment was flown in
+                const uint32_t sm0 = psim::cell_sensor_word(P, cell0);  // of the cell the segment was flown in
                 if (!have_vel) {
                     const float4 g2 = lds128(grp(SG_VEL, k));
                     p.dx = g2.x;
                     p.dy = g2.y;
                     p.packed = __float_as_uint(g2.z);
                 }
-                sensor = PSIM_CELL_SENSOR(info.w);
+                sensor = PSIM_CELL_SENSOR(sm0);
                 if (hit) {
-                    f.sensor_mat = info.w;
-                    if (psim::fast_transition(P, p, f, info)) {
+                    f.sensor_mat = sm0;
+                    if (psim::fast_transition(P, p, f, psim::load_cell_links(P.cells, PSIM_CELL_INDEX(cell0)))) {
                         misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
                         dest = Q_FLY;
                     } else {
@@ -786,19 +787,20 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
         const uint32_t best = max(max(c_fly, c_wall), max(max(c_sct, c_fin), c_acq));
         if (best == 0u) { break; }
         const bool fuse = best >= kFuseLanes;  // warp-uniform
-        bool act;
-        uint32_t k;
+        // Stage 1 - what the chosen kind does with its slots; it leaves the lanes that go on to fly with their whole state in
+        // registers (`go`).  Stage 2 - ONE copy of the flight segment for all kinds (four inlined copies cost more in
+        // instruction-cache misses than they saved: ncu stall no_instruction 0.32 -> 1.13 per issue).  Stage 3 - the push.
+        bool act, go = false, have_vel = true, flies = fuse;
+        uint32_t k, misc = 0;
         int dest = -1;
+        psim::Phonon p;
+        psim::Flight f;
+        p.dx = p.dy = 0.f;
+        p.packed = 0u;
         // the fullest queue runs; ties go to the rarer kinds (they waited longest to get there)
         if (c_sct == best) {
-            // ---- intrinsic scatter, then fly
+            // ---- intrinsic scatter
             k = pop(q_sct, Q_SCT, c_sct, act);
-            psim::Phonon p;
-            psim::Flight f;
-            uint32_t misc = 0;
-            bool alive = false;
-            p.dx = p.dy = 0.f;
-            p.packed = 0u;
             if (act) {
                 const float4 g0 = lds128(grp(SG_POS, k)), g1 = lds128(grp(SG_TIME, k)), g2 = lds128(grp(SG_VEL, k));
                 p.b1 = g0.x;
@@ -811,7 +813,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 p.packed = __float_as_uint(g2.z);
                 p.id_lo = __float_as_uint(g2.w);
                 psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
-                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.sensor_mat = psim::cell_sensor_word(P, p.cell);
                 f.vel = psim::phonon_velocity(P, p.packed);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
@@ -819,22 +821,15 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 // A phonon that has used up the Philox blocks of this interval is DROPPED and the run fails (PSIM_E_RNG): were it
                 // to go on with a frozen block it would redraw the same time to scatter for ever - and if that time is below the
                 // fp32 resolution of the time left in a long interval, the launch would never end.
-                alive = f.rng.block <= PSIM_MISC_BLOCK_MAX;
-                rng_over |= !alive;
+                go = f.rng.block <= PSIM_MISC_BLOCK_MAX;
+                rng_over |= !go;
                 misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), 0u, PSIM_MISC_EDGE(misc), f.rng.block);  // impacts since the last scatter := 0
+                if (!go) { dest = Q_FREE; }
             }
-            dest = fuse ? fly(alive, k, p, f, misc, true) : park(alive, k, p, f, misc);
-            if (act && !alive) { dest = Q_FREE; }
         } else if (c_wall == best) {
             // ---- surface interaction, general case: wall (specular / diffuse), emitting surface, material interface,
-            //      transition into a sensor area with other rates, partial edges, stuck-phonon guard; then fly
+            //      transition into a sensor area with other rates, partial edges, stuck-phonon guard
             k = pop(q_wall, Q_WALL, c_wall, act);
-            psim::Phonon p;
-            psim::Flight f;
-            uint32_t misc = 0;
-            bool alive = false;
-            p.dx = p.dy = 0.f;
-            p.packed = 0u;
             if (act) {
                 const float4 g0 = lds128(grp(SG_POS, k)), g1 = lds128(grp(SG_TIME, k)), g2 = lds128(grp(SG_VEL, k));
                 p.b1 = g0.x;
@@ -849,13 +844,13 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 p.packed = __float_as_uint(g2.z);
                 p.id_lo = __float_as_uint(g2.w);
                 f.edge = PSIM_MISC_EDGE(misc);
-                f.s_hit = (f.edge == 0u) ? p.b1 : ((f.edge == 1u) ? p.b2 : 1.f - p.b2);
+                f.s_hit = psim::edge_coordinate(PSIM_CELL_QUAD(p.cell), f.edge, p.b1, p.b2);
                 f.ncoll = PSIM_MISC_NCOLL(misc);
                 f.rng.block = PSIM_MISC_BLOCK(misc);
                 f.rng.left = 0;
                 f.t = g1.y;
                 psim::set_cell_matrix(f, psim::load_cell_matrix(P, p.cell));
-                f.sensor_mat = psim::load_cell_info(P.cells, p.cell).w;
+                f.sensor_mat = psim::cell_sensor_word(P, p.cell);
                 f.vel = psim::phonon_velocity(P, p.packed);
                 const int ev = psim::impact_event(P, p, f, a.step_begin + PSIM_MISC_STEP(misc));
                 const bool spent = f.rng.block > PSIM_MISC_BLOCK_MAX;  // dropped, see the scatter pass
@@ -863,13 +858,12 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 if (ev == psim::EV_DEAD || spent) {
                     ++n_steps;
                     ++n_absorbed;
+                    dest = Q_FREE;
                 } else {
-                    alive = true;
+                    go = true;
                     misc = PSIM_MISC_PACK(PSIM_MISC_STEP(misc), f.ncoll, PSIM_MISC_EDGE(misc), f.rng.block);
                 }
             }
-            dest = fuse ? fly(alive, k, p, f, misc, true) : park(alive, k, p, f, misc);
-            if (act && !alive) { dest = Q_FREE; }
         } else if (c_fin == best) {
             // ---- write-back of phonons that reached the end of the launch window (compacted, coalesced)
             k = pop(q_fin, Q_FIN, c_fin, act);
@@ -885,46 +879,36 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 dest = Q_FREE;
             }
             n_out += c_fin;
+            flies = false;
         } else if (c_acq == best) {
-            // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots, then fly
+            // ---- fetch: the next items of the warp's stream (pool first, then births) into free slots
             k = pop(q_free, Q_FREE, c_acq, act);
-            psim::Phonon p;
-            psim::Flight f;
-            uint32_t misc = 0;
-            bool got = false;
-            p.dx = p.dy = 0.f;
-            p.packed = 0u;
             if (act) {
                 const uint32_t idx = next + lane;
                 uint32_t s = a.step_begin;
                 float t_begin = P.step_time;
                 if (idx < n_in) {
                     load_phonon(a, seg + idx, p);
-                    got = true;
+                    go = true;
                 } else {
                     const uint32_t b = idx - n_in;
                     const uint64_t item = (static_cast<uint64_t>(c0) + static_cast<uint64_t>(b >> 5) * W) * 32u + (b & 31u);
                     if (item < a.n_births) {
                         t_begin = birth_phonon(a, item, p, s);
-                        got = true;
+                        go = true;
                     }
                 }
-                if (got) {
+                if (go) {
                     psim::interval_begin(P, p, f, t_begin, s);
                     misc = s - a.step_begin;
+                } else {
+                    dest = Q_FREE;
                 }
             }
             next += c_acq;
-            dest = fuse ? fly(got, k, p, f, misc, true) : park(got, k, p, f, misc);
-            if (act && !got) { dest = Q_FREE; }
         } else {
-            // ---- fly: slots that entered a neighbour cell
+            // ---- fly: slots that entered a neighbour cell (or were parked by a sparse pass)
             k = pop(q_fly, Q_FLY, c_fly, act);
-            psim::Phonon p;
-            psim::Flight f;
-            uint32_t misc = 0;
-            p.dx = p.dy = 0.f;
-            p.packed = 0u;
             if (act) {
                 const float4 g0 = lds128(grp(SG_POS, k)), g1 = lds128(grp(SG_TIME, k));
                 p.b1 = g0.x;
@@ -935,8 +919,16 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 f.t = g1.y;
                 misc = __float_as_uint(g1.z);
                 p.cell = __float_as_uint(g1.w);
+                go = true;
             }
-            dest = fly(act, k, p, f, misc, false);
+            have_vel = false;
+            flies = true;
+        }
+        if (flies) {
+            const int next_kind = fly(go, k, p, f, misc, have_vel);
+            if (go) { dest = next_kind; }
+        } else if (go) {
+            dest = park(true, k, p, f, misc);  // a sparse pass: its slots fly with a full flight pass
         }
         // five-way push with one address computation (selects on warp-uniform values, no branches)
         const bool d_fly = dest == Q_FLY, d_sct = dest == Q_SCT, d_wall = dest == Q_WALL, d_fin = dest == Q_FIN, d_free = dest == Q_FREE;
@@ -1094,13 +1086,16 @@ __global__ void transpose_tallies_kernel(const int32_t* tally_e, const long long
     }
 }
 
-__global__ void cell_histogram_kernel(const uint4* pool_b, const uint32_t* cnt, uint32_t seg_cap, uint32_t n_warps,
-                                      unsigned long long* hist) {
+// phonons per MODEL cell: a flight cell that is a parallelogram holds one model triangle on either side of its diagonal
+__global__ void cell_histogram_kernel(DevParams P, const float4* pool_a, const uint4* pool_b, const uint32_t* cnt, uint32_t seg_cap,
+                                      uint32_t n_warps, unsigned long long* hist) {
     const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (w >= n_warps) { return; }
     const uint32_t n = cnt[w];
     for (uint32_t i = threadIdx.x & 31u; i < n; i += 32u) {
-        atomicAdd(&hist[pool_b[static_cast<size_t>(w) * seg_cap + i].z], 1ull);
+        const size_t k = static_cast<size_t>(w) * seg_cap + i;
+        const float4 a = pool_a[k];
+        atomicAdd(&hist[psim::api_cell_of(P, pool_b[k].z, a.x, a.y)], 1ull);
     }
 }
 

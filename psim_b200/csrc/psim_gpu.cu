@@ -36,10 +36,11 @@ struct psim_gpu {
     int device = 0;
     int sm_count = 0;
     psim::HostImage img;
+    psim::HostImage img_tri;         // the same model with one flight cell per triangle: geometry arrays only (probes, option "merge_cells")
     psim::BirthPlan plan;
     DevParams P{};  // device pointers
     void* d_cells = nullptr;
-    void* d_cell_shape = nullptr;
+    void* d_api_cells = nullptr;
     void* d_shapes = nullptr;
     void* d_classes = nullptr;
     void* d_step_sensors = nullptr;
@@ -81,6 +82,7 @@ struct psim_gpu {
     int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
     int64_t opt_queue_slots = PSIM_QUEUE_SLOTS;  // phonons in flight per warp of the work-queue kernel (128, or 64: more L1 left for the mesh)
     int64_t opt_tally_shared = -1;
+    int64_t opt_merge_cells = 1;     // 0: one flight cell per model triangle (A/B, per-function probes)
     uint32_t last_tally_shared = 0;
     uint32_t last_window = 0;
     uint32_t max_flux_fixed = 0;     // largest |velocity| in flux fixed-point units
@@ -226,6 +228,28 @@ void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1
     }
 }
 
+// The geometry half of the device image - flight cells, shapes, the model-cell map, partial-edge records, emitters - of
+// either form of the model (merged: h->img, one flight cell per triangle: h->img_tri).
+int upload_geometry(psim_gpu* h, const psim::HostImage& g) {
+    for (void** p : { &h->d_cells, &h->d_shapes, &h->d_api_cells, &h->d_subs, &h->d_emitters }) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (int rc = upload(h, &h->d_cells, g.cells)) { return rc; }
+    if (int rc = upload(h, &h->d_shapes, g.shapes)) { return rc; }
+    if (int rc = upload(h, &h->d_api_cells, g.api_cells)) { return rc; }
+    if (int rc = upload(h, &h->d_subs, g.subs)) { return rc; }
+    if (int rc = upload(h, &h->d_emitters, g.emitters)) { return rc; }
+    h->P.cells = static_cast<const DevCell*>(h->d_cells);
+    h->P.shapes = static_cast<const DevShape*>(h->d_shapes);
+    h->P.api_cells = static_cast<const DevApiCell*>(h->d_api_cells);
+    h->P.subs = static_cast<const DevSub*>(h->d_subs);
+    h->P.emitters = static_cast<const DevEmitter*>(h->d_emitters);
+    h->P.n_flight_cells = static_cast<uint32_t>(g.cells.size());
+    h->P.n_shapes = static_cast<uint32_t>(g.shapes.size());
+    return 0;
+}
+
 int zero_run_state(psim_gpu* h) {
     const DevParams& P = h->P;
     const size_t n = static_cast<size_t>(P.recorded_steps) * P.n_sensors;
@@ -301,6 +325,11 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
     h->sm_count = prop.multiProcessorCount;
     try {  // nothing throws across the ABI: a description whose sizes exhaust the host's memory is an invalid description
         if (int rc = psim::flatten_model(*desc, h->img, h->err)) { return bail(rc); }
+        if (int rc = psim::flatten_model(*desc, h->img_tri, h->err, false)) { return bail(rc); }
+        for (auto* v : { &h->img_tri.tables }) { std::vector<float2>().swap(*v); }  // only its geometry arrays are kept
+        std::vector<uint32_t>().swap(h->img_tri.guides);
+        std::vector<float>().swap(h->img_tri.velocities);
+        std::vector<DevSensor>().swap(h->img_tri.step_sensors);
     } catch (const std::exception& e) {
         h->err = std::string("model description rejected: ") + e.what();
         return bail(PSIM_E_INVALID);
@@ -315,36 +344,27 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
     // kernels, kinked wire with 6174 cells: 246 ms queues, 253 ms slots.)  psim_gpu_set_option("kernel") overrides.
     h->opt_kernel = 2;
     // Slots per warp: 128 keep the queues of the rare kinds of work full (Si/Ge bench model: 63.6 ms for the long window
-    // against 76.8 ms with 64) and leave 92 KB of L1.  A mesh whose hot records - 16 B + a 4-byte shape index per cell - do
-    // not fit there beside the tables runs faster with 64 slots and 156 KB of L1 (round 2, compressed records: kinked wire
-    // with 6174 cells 222 ms with 64 slots, 248 ms with 128; linear_sides with 2000 cells steady 13.7 vs 12.7 ms, Si/Ge 91.5
-    // vs 76.0 ms, linear_demo 13.2 vs 12.2 ms).  psim_gpu_set_option("queue_slots") overrides.
-    h->opt_queue_slots = (h->img.cells.size() * (sizeof(DevCell) + sizeof(uint32_t)) > 60u * 1024u) ? kQueueSlotsSmall : kQueueSlots;
+    // against 76.8 ms with 64) and leave 92 KB of L1; 64 slots leave 156 KB.  With 32-byte flight-cell records every shipped
+    // mesh runs fastest with 128 (round 2, same box, 64 / 128 slots: kinked wire with 3150 flight cells = 100 KB of records
+    // 165.1 / 161.6 ms, linear_sides 15.7 ms with 128, Si/Ge 69.7); 64 is kept for meshes whose records exceed the L1 that 128
+    // slots leave by a wide margin.  psim_gpu_set_option("queue_slots") overrides.
+    h->opt_queue_slots = (h->img.cells.size() * sizeof(DevCell) > 160u * 1024u) ? kQueueSlotsSmall : kQueueSlots;
     auto setup = [&]() -> int {
-        if (int rc = upload(h, &h->d_cells, h->img.cells)) { return rc; }
-        if (int rc = upload(h, &h->d_cell_shape, h->img.cell_shape)) { return rc; }
-        if (int rc = upload(h, &h->d_shapes, h->img.shapes)) { return rc; }
         if (int rc = upload(h, &h->d_classes, h->img.classes)) { return rc; }
         if (!h->img.step_sensors.empty()) {
             if (int rc = upload(h, &h->d_step_sensors, h->img.step_sensors)) { return rc; }
         }
-        if (int rc = upload(h, &h->d_subs, h->img.subs)) { return rc; }
         if (int rc = upload(h, &h->d_sensors, h->img.sensors)) { return rc; }
         if (int rc = upload(h, &h->d_materials, h->img.materials)) { return rc; }
-        if (int rc = upload(h, &h->d_emitters, h->img.emitters)) { return rc; }
         if (int rc = upload(h, &h->d_tables, h->img.tables)) { return rc; }
         if (int rc = upload(h, &h->d_velocities, h->img.velocities)) { return rc; }
         if (int rc = upload(h, &h->d_guides, h->img.guides)) { return rc; }
         h->P = h->img.scalars;
-        h->P.cells = static_cast<const DevCell*>(h->d_cells);
-        h->P.cell_shape = static_cast<const uint32_t*>(h->d_cell_shape);
-        h->P.shapes = static_cast<const DevShape*>(h->d_shapes);
+        if (int rc = upload_geometry(h, h->img)) { return rc; }
         h->P.classes = static_cast<const DevSensor*>(h->d_classes);
         h->P.step_sensors = static_cast<const DevSensor*>(h->d_step_sensors);
-        h->P.subs = static_cast<const DevSub*>(h->d_subs);
         h->P.sensors = static_cast<const DevSensor*>(h->d_sensors);
         h->P.materials = static_cast<const DevMaterial*>(h->d_materials);
-        h->P.emitters = static_cast<const DevEmitter*>(h->d_emitters);
         h->P.tables = static_cast<const float2*>(h->d_tables);
         h->P.velocities = static_cast<const float*>(h->d_velocities);
         h->P.guides = static_cast<const uint32_t*>(h->d_guides);
@@ -643,7 +663,7 @@ int psim_gpu_cell_histogram(psim_gpu* h, uint64_t* per_cell) {
     }
     if (int rc = psim_gpu_synchronize(h)) { return rc; }
     PSIM_CUDA(cudaMemset(h->d_hist, 0, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
-    cell_histogram_kernel<<<h->n_warps / kWarpsPerBlock, kBlock>>>(h->pool_b[h->cur], h->cnt[h->cur], h->seg_cap, h->n_warps, h->d_hist);
+    cell_histogram_kernel<<<h->n_warps / kWarpsPerBlock, kBlock>>>(h->P, h->pool_a[h->cur], h->pool_b[h->cur], h->cnt[h->cur], h->seg_cap, h->n_warps, h->d_hist);
     PSIM_CUDA(cudaGetLastError());
     PSIM_CUDA(cudaMemcpy(per_cell, h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return PSIM_OK;
@@ -670,8 +690,8 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     out->warps = h->n_warps;
     out->tally_in_shared = h->last_tally_shared;
     out->kernel = static_cast<uint32_t>(h->opt_kernel);
-    out->reserved = 0;
-    out->image_bytes = h->img.cells.size() * (sizeof(DevCell) + sizeof(uint32_t)) + h->img.shapes.size() * sizeof(DevShape) + (h->img.classes.size() + h->img.step_sensors.size()) * sizeof(DevSensor) + h->img.subs.size() * sizeof(DevSub) +
+    out->flight_cells = h->P.n_flight_cells;
+    out->image_bytes = h->img.cells.size() * sizeof(DevCell) + h->img.api_cells.size() * sizeof(DevApiCell) + h->img.shapes.size() * sizeof(DevShape) + (h->img.classes.size() + h->img.step_sensors.size()) * sizeof(DevSensor) + h->img.subs.size() * sizeof(DevSub) +
                        h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
                        h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +
                        h->img.velocities.size() * sizeof(float);
@@ -708,6 +728,17 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
             return PSIM_E_STATE;
         }
         h->opt_queue_slots = value;
+    } else if (k == "merge_cells") {
+        if (h->have_sources || (value != 0 && value != 1)) {
+            h->err = "merge_cells must be 0 (one flight cell per model triangle) or 1 (pairs of triangles fly as one parallelogram) and set before set_sources";
+            return PSIM_E_STATE;
+        }
+        if (value != h->opt_merge_cells) {
+            PSIM_CUDA(cudaSetDevice(h->device));
+            PSIM_CUDA(cudaDeviceSynchronize());
+            if (int rc = upload_geometry(h, value ? h->img : h->img_tri)) { return rc; }
+            h->opt_merge_cells = value;
+        }
     } else if (k == "tally_shared") {
         if (h->have_sources || value < -1 || value > 4 || value == 3) {  // the tally form of a run is fixed when it starts
             h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 / 4 / 2 (staged: two / three 32-bit parts, 64-bit) and set before set_sources";
@@ -737,7 +768,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     free_pool(h);
     free_plan(h);
     cudaFree(h->d_cells);
-    cudaFree(h->d_cell_shape);
+    cudaFree(h->d_api_cells);
     cudaFree(h->d_shapes);
     cudaFree(h->d_classes);
     cudaFree(h->d_step_sensors);
@@ -789,19 +820,27 @@ int psim_gpu_probe_flight(psim_gpu* h, const uint32_t* cell, const float* in, si
     if (!h || !cell || !in || !out) { return PSIM_E_INVALID; }
     if (n == 0) { return PSIM_OK; }
     for (size_t i = 0; i < n; ++i) {
-        if (cell[i] >= h->P.n_cells) {
+        if (cell[i] >= h->P.n_cells) {  // model cells
             h->err = "probe_flight: cell index out of range";
             return PSIM_E_INVALID;
         }
     }
     PSIM_CUDA(cudaSetDevice(h->device));
-    DeviceBuffer dc, di, dout;
+    // the probe speaks model triangles: it runs on the one-flight-cell-per-triangle form of the geometry
+    DeviceBuffer dc, di, dout, cells, shapes;
+    PSIM_CUDA(cells.alloc(h->img_tri.cells.size() * sizeof(DevCell)));
+    PSIM_CUDA(shapes.alloc(h->img_tri.shapes.size() * sizeof(DevShape)));
+    PSIM_CUDA(cudaMemcpy(cells.p, h->img_tri.cells.data(), h->img_tri.cells.size() * sizeof(DevCell), cudaMemcpyHostToDevice));
+    PSIM_CUDA(cudaMemcpy(shapes.p, h->img_tri.shapes.data(), h->img_tri.shapes.size() * sizeof(DevShape), cudaMemcpyHostToDevice));
+    DevParams P = h->P;
+    P.cells = cells.as<DevCell>();
+    P.shapes = shapes.as<DevShape>();
     PSIM_CUDA(dc.alloc(n * 4));
     PSIM_CUDA(di.alloc(n * 16));
     PSIM_CUDA(dout.alloc(n * 24));
     PSIM_CUDA(cudaMemcpy(dc.p, cell, n * 4, cudaMemcpyHostToDevice));
     PSIM_CUDA(cudaMemcpy(di.p, in, n * 16, cudaMemcpyHostToDevice));
-    probe_flight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->P, dc.as<uint32_t>(), di.as<float>(), n, dout.as<float>());
+    probe_flight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(P, dc.as<uint32_t>(), di.as<float>(), n, dout.as<float>());
     PSIM_CUDA(cudaGetLastError());
     PSIM_CUDA(cudaMemcpy(out, dout.p, n * 24, cudaMemcpyDeviceToHost));
     return PSIM_OK;

@@ -26,7 +26,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     }
     DevParams P = img.scalars;
     P.cells = img.cells.data();
-    P.cell_shape = img.cell_shape.data();
+    P.api_cells = img.api_cells.data();
     P.shapes = img.shapes.data();
     P.classes = img.classes.data();
     P.step_sensors = img.step_sensors.empty() ? nullptr : img.step_sensors.data();
@@ -81,7 +81,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         pool.swap(next);
         if (alive_per_pass) { alive_per_pass[s1 - 1] = pool.size(); }
         if (cell_hist_steps) {
-            for (const auto& p : pool) { ++cell_hist_steps[static_cast<size_t>(s1 - 1) * P.n_cells + p.cell]; }
+            for (const auto& p : pool) { ++cell_hist_steps[static_cast<size_t>(s1 - 1) * P.n_cells + psim::api_cell_of(P, p.cell, p.b1, p.b2)]; }
         }
     }
     const double scale = 1. / static_cast<double>(1 << PSIM_FLUX_FRAC_BITS);
@@ -101,5 +101,17 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     }
     if (drift_steps) { *drift_steps = n_steps; }
     if (events) { *events = total_events; }
+    return 0;
+}
+
+// flatten_model's view of the mesh: flight cells (with and without merging triangle pairs) and distinct shapes
+extern "C" int psim_emu_mesh_info(const psim_model_desc* desc, int merge_cells, uint32_t* flight_cells, uint32_t* shapes, uint32_t* classes) {
+    psim::HostImage img;
+    std::string e;
+    const int rc = psim::flatten_model(*desc, img, e, merge_cells != 0);
+    if (rc) { return rc; }
+    if (flight_cells) { *flight_cells = static_cast<uint32_t>(img.cells.size()); }
+    if (shapes) { *shapes = static_cast<uint32_t>(img.shapes.size()); }
+    if (classes) { *classes = static_cast<uint32_t>(img.classes.size()); }
     return 0;
 }

@@ -260,3 +260,43 @@ def test_reiterated_runs_match_the_reference_with_its_iteration_cap_raised(name)
     else:
         T.assert_parity(T.welch_z(runs, gold, "temp_blk"), f"emu {name} x3 temperature trace")
         T.assert_parity(T.welch_z(runs, gold, "flux_blk"), f"emu {name} x3 flux trace")
+
+
+def test_flatten_pairs_triangles_into_parallelograms_and_dedupes_shapes():
+    """flatten.cpp: two triangles of one sensor area whose union is a parallelogram become ONE flight cell (device_types.h),
+    and cell geometry is stored once per distinct shape.  The kinked wire: 6174 triangles -> 3087 flight cells; every shipped
+    mesh halves; a bar whose rectangles belong to two sensors each (no pair inside one sensor area) keeps its triangles."""
+    import ctypes as C
+    from psim_b200 import configs
+    from tests import cases
+    lib = T.emu_lib()
+    lib.psim_emu_mesh_info.restype = C.c_int
+
+    def info(model_dict, merge=1):
+        m = T.load_model(model_dict)
+        m.prepare()
+        n, s, k = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        assert lib.psim_emu_mesh_info(m.describe(), merge, C.byref(n), C.byref(s), C.byref(k)) == 0
+        return m.info.num_cells, n.value, s.value, k.value
+
+    for model in (configs.linear(num_phonons=1000).to_dict(), configs.linear_sides(num_phonons=1000).to_dict(),
+                  configs.si_ge_grid(num_phonons=1000).to_dict(), cases.split_bar(1000)):
+        cells, flight, shapes, classes = info(model)
+        assert flight * 2 == cells and shapes <= 2 and classes <= 2
+        assert info(model, merge=0)[1] == cells
+    kinked = cases.kinked_model()
+    if kinked is not None:
+        cells, flight, shapes, classes = info(configs.with_settings(kinked, num_phonons=1000))
+        # 3024 of its 3087 rectangles are parallelograms inside one sensor area (42 in the kinks are trapezoids, 21 are shared by two sensors)
+        assert (cells, flight) == (6174, 6174 - 3024) and shapes <= 160 and classes == 1
+    # two sensors per rectangle: the triangles of a rectangle lie in different sensor areas and must not be merged
+    m = configs.ModelFile(num_measurements=100, sim_time=1, num_phonons=1000, t_eq=300)
+    name = m.material(configs.SILICON)
+    for i in range(4):
+        a, b = m.sensor(name, 300.0), m.sensor(name, 300.0)
+        m.triangle((i * 10.0, 0.0), (i * 10.0, 10.0), ((i + 1) * 10.0, 10.0), a, 1)
+        m.triangle((i * 10.0, 0.0), ((i + 1) * 10.0, 10.0), ((i + 1) * 10.0, 0.0), b, 1)
+    m.emit_surface((0.0, 0.0), (0.0, 10.0), 310)
+    m.emit_surface((40.0, 0.0), (40.0, 10.0), 290)
+    cells, flight, _, _ = info(m.to_dict())
+    assert cells == 8 and flight == 8

@@ -196,3 +196,44 @@ def test_one_iteration_is_the_default_and_three_change_the_answer():
     a, b = one.results(0)[0], three.results(0)[0]
     assert s3.total_phonons >= s1.total_phonons - 100 and not np.allclose(a[:, 0], b[:, 0], atol=0.05)
     assert abs(a[:, 0].mean() - 300.0) > 5.0  # one iteration: linearised about t_eq = 300 K, the walls are not symmetric about it
+
+
+def test_triangle_pairs_fly_as_one_parallelogram_without_changing_the_physics():
+    """flatten.cpp merges two triangles of one sensor area whose union is a parallelogram into one flight cell (crossing their
+    shared edge does nothing to a phonon in the reference either: TransitionSurface::handlePhonon, surface.cpp:71-75).  The
+    kinked wire (6174 triangles, 3024 mergeable pairs) must fly through 3150 cells, a mesh cut so that no pair qualifies must keep its triangles,
+    the integer bookkeeping that does not depend on trajectories must be identical with and without merging, the per-cell
+    histogram must still be in model cells, and 8 seeds each way must agree like two sets of runs of the same code."""
+    name = "kinked_spec" if "kinked_spec" in T.all_case_names() else "sides_ss"
+    model = T.load_model(T.case_model(name), num_phonons=200_000)
+    info = model.info
+    merged = [gpu_run_case(model, seed) for seed in range(1, 9)]
+    plain = [gpu_run_case(model, seed, options={"merge_cells": 0}) for seed in range(11, 19)]
+    assert plain[0]["stats"][0]["flight_cells"] == info.num_cells
+    assert merged[0]["stats"][0]["flight_cells"] == (info.num_cells - 3024 if name == "kinked_spec" else info.num_cells // 2)
+    same_seed = gpu_run_case(model, 1, options={"merge_cells": 0})
+    assert same_seed["sources"] == merged[0]["sources"]
+    # far fewer flight segments for the same drift-steps (the shared edges are gone)
+    assert merged[0]["stats"][0]["events"] < 0.75 * same_seed["stats"][0]["events"]
+    assert abs(merged[0]["stats"][0]["drift_steps"] - same_seed["stats"][0]["drift_steps"]) < 0.01 * same_seed["stats"][0]["drift_steps"]
+    feats = {k: [T.run_features(r["energy"], r["flux"], 0, r["six"], r["temps"], r["fluxes"]) for r in runs] for k, runs in (("m", merged), ("p", plain))}
+    gold = {"n_seeds": 8}
+    for key in ("tally_e", "tally_f", "out6"):
+        stack = np.stack([r[key] for r in feats["p"]])
+        gold[key + "_mean"], gold[key + "_std"] = stack.mean(axis=0), stack.std(axis=0, ddof=1)
+    T.assert_parity(T.welch_z(feats["m"], gold, "tally_e"), "merged vs per-triangle flight cells, energy tallies")
+    T.assert_parity(T.welch_z(feats["m"], gold, "tally_f"), "merged vs per-triangle flight cells, flux tallies")
+    T.assert_parity(T.welch_z(feats["m"], gold, "out6")[:, 0], "merged vs per-triangle flight cells, temperatures")
+    # phonons per MODEL cell after 60 steps: both triangles of the pairs are populated, and the totals agree with the pool
+    model.prepare()
+    src, n = model.sources(3)
+    g = psim.GpuSimulator(model.describe(), 0)
+    try:
+        g.set_sources(src, n, 3, 0, 1)
+        g.run_steps(0, 600 if name == "kinked_spec" else 60)
+        hist, alive = g.cell_histogram(), g.alive()
+    finally:
+        g.close()
+    assert int(hist.sum()) == alive and hist.size == info.num_cells
+    even, odd = int(hist[0::2].sum()), int(hist[1::2].sum())
+    assert abs(even - odd) < 0.1 * alive  # the builder lists the two triangles of a rectangle one after the other
