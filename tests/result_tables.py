@@ -1,4 +1,4 @@
-"""Readers of the result tables psim writes (`ss_<stem>.txt`, `per_<stem>.txt`).
+"""TEST HELPER (not part of the product package): readers of the result tables psim writes (`ss_<stem>.txt`, `per_<stem>.txt`), used to check the exporter.
 
 The formats are the reference's (psim/src/outputManager.cpp:72-114); its Python tools parse them line by line in
 psim_python/psim/plotting_tools.py:84-157 (`parse_ss_data`, `parse_avg_flux`, `parse_periodic_data`).  These readers

@@ -266,10 +266,10 @@ def test_cli_without_gpu_reports_and_continues(built_library, tmp_path):
 
 
 def test_result_readers_round_trip(built_library, tmp_path):
-    """psim_b200/results.py reads what the exporter writes - the reference's table formats (outputManager.cpp:72-114) as its
+    """tests/result_tables.py (a test helper: the readers of the plotting tools are out of scope for the product) reads what the exporter writes - the reference's table formats (outputManager.cpp:72-114) as its
     own Python tools parse them (plotting_tools.py:84-157) - back into the numbers the host API reports, to the six
     significant digits of the text."""
-    from psim_b200 import results
+    from tests import result_tables as results
     rng = np.random.default_rng(3)
     m = T.load_model(T.case_model("linear_demo"), num_phonons=1000)
     m.prepare()
@@ -307,7 +307,7 @@ def test_result_readers_round_trip(built_library, tmp_path):
 @pytest.mark.skipif(not os.path.isdir("/root/reference/psim_python/json/results"), reason="reference tree not mounted")
 def test_result_readers_parse_the_reference_files():
     """The three result tables shipped with the reference (2022, an older title line without the run count)."""
-    from psim_b200 import results
+    from tests import result_tables as results
     base = "/root/reference/psim_python/json/results/"
     for name, sensors in (("ss_linear_demo.txt", 20), ("ss_linear_sides_demo_ss.txt", 1000), ("ss_kinked_demo_120_35_spec.txt", 3108)):
         ss = results.read_steady_state(base + name)
