@@ -137,6 +137,10 @@ typedef struct psim_stats {
     uint32_t kernel;                    /* drift kernel in use: 2 work queues, 0 lane-bound slots, 1 lock step */
     uint32_t flight_cells;              /* cells the per-phonon loop flies through: num_cells, less one for every pair of
                                            triangles that flies as one parallelogram (option "merge_cells") */
+    uint32_t lattice_cells;             /* cells of the lattice image flown by the launches that record nothing (blocks of identical
+                                           parallelograms of one rate class as one cell each); 0: the model has none, or
+                                           "merge_cells" < 2 */
+    uint32_t reserved;
 } psim_stats;
 
 typedef struct psim_gpu psim_gpu;
@@ -186,8 +190,11 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out);
 /* Tunables: "steps_per_launch" (measurement intervals advanced per pass over the pool; 0 = automatic, the default),
  * "warps_per_sm" (0 = occupancy-derived), "kernel" (2 work queues = default, 0 lane-bound shared-memory slots, 1 lock-step first version),
  * "queue_slots" (phonons in flight per warp of the work-queue kernel, 128 or 64; default by mesh size; before set_sources),
- * "merge_cells" (1 = default: two triangles of one sensor area whose union is a parallelogram fly as ONE cell - crossing their
- * shared edge does nothing to a phonon in the reference either, surface.cpp:71-75; 0: one flight cell per triangle; before set_sources),
+ * "merge_cells" (1: two triangles of one sensor area whose union is a parallelogram fly as ONE cell - crossing their
+ * shared edge does nothing to a phonon in the reference either, surface.cpp:71-75; 2 = default: also, in launches that
+ * record nothing, every rectangular block of identical parallelograms of one material and rate class flies as one lattice
+ * cell - where no sensor is read, a transition between two such cells changes nothing but the cell label;
+ * 0: one flight cell per triangle; before set_sources),
  * "tally_shared" (-1 automatic = default; 0 straight to global memory, rows kept as differences along the step axis until
  * their window is complete; 1 / 4 / 2 staged per CTA in shared memory as two / three 32-bit parts / 64-bit sums - 1 and 4
  * fall back to the next form when their exactness bound does not hold; before set_sources). */

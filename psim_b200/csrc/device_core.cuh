@@ -107,6 +107,34 @@ PSIM_HD uint32_t api_cell_of(const DevParams& P, uint32_t cell, float b1, float 
     const uint2 t = load_cell_tris(P.cells, PSIM_CELL_INDEX(cell));
     return (b1 >= b2) ? t.x : t.y;
 }
+PSIM_HD float clamp01(float x) {
+#if defined(__CUDA_ARCH__)
+    return __saturatef(x);
+#else
+    return fminf(fmaxf(x, 0.f), 1.f);
+#endif
+}
+
+// Lattice image (device_types.h): column / row of the parallelogram that holds coordinate x in [0, 1] of an n-wide lattice
+// axis, and the coordinate inside it.  A point on a lattice line belongs to the parallelogram on either side: it lies on the
+// edge of both, and a flight that leaves through that edge at once costs one zero-length segment.
+PSIM_HD uint32_t lattice_split(float x, uint32_t n, float& local) {
+    const float y = x * static_cast<float>(n);
+    const uint32_t i = min(static_cast<uint32_t>(fmaxf(y, 0.f)), n - 1u);
+    local = clamp01(y - static_cast<float>(i));
+    return i;
+}
+// a phonon in lattice coordinates -> the same phonon in its fine flight cell (`cells`, `sub_fine`: of the lattice image)
+PSIM_HD void coarse_to_fine(const DevCell* cells, const uint32_t* sub_fine, uint32_t& cell, float& b1, float& b2) {
+    const uint2 t = load_cell_tris(cells, PSIM_CELL_INDEX(cell));  // (first sub-cell, nx | ny << 16)
+    const uint32_t nx = t.y & 0xFFFFu, ny = t.y >> 16;
+    float l1, l2;
+    const uint32_t ix = lattice_split(b1, nx, l1), iy = lattice_split(b2, ny, l2);
+    cell = ldg(&sub_fine[t.x + iy * nx + ix]);
+    b1 = l1;
+    b2 = l2;
+}
+
 // relaxation-rate record of the sensor area a cell word names, at measurement step `step`: the record of its rate class
 // where it has one (a handful of records for the whole mesh), the sensor's own otherwise; a transient run that re-iterates
 // has one record per (sensor, step) (TransientController::getSteadyTemp / scatterUpdate, sensorController.cpp:80-88)
@@ -289,14 +317,6 @@ PSIM_HD void boundary_reflect(Rng& rng, float spec, float nx, float ny, float ve
     }
 }
 
-PSIM_HD float clamp01(float x) {
-#if defined(__CUDA_ARCH__)
-    return __saturatef(x);
-#else
-    return fminf(fmaxf(x, 0.f), 1.f);
-#endif
-}
-
 // position on edge `e` of a triangle / parallelogram at fraction s from the edge's first vertex (device_types.h)
 PSIM_HD void place_on_edge(uint32_t quad, uint32_t e, float s, Phonon& p) {
     const float r = 1.f - s;
@@ -358,6 +378,11 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
         const float x3 = static_cast<float>((ac.corners >> 4) & 1u), y3 = static_cast<float>((ac.corners >> 5) & 1u);
         p.b1 = x1 + (x2 - x1) * r1 + (x3 - x1) * r2;
         p.b2 = y1 + (y2 - y1) * r1 + (y3 - y1) * r2;
+        if (P.lattice) {  // the triangle's parallelogram is one of nx x ny of its lattice cell
+            const uint32_t dims = ldg(&P.cells[PSIM_CELL_INDEX(p.cell)].tri[1]);
+            p.b1 = clamp01((p.b1 + static_cast<float>((ac.corners >> 6) & 0x1FFFu)) / static_cast<float>(dims & 0xFFFFu));
+            p.b2 = clamp01((p.b2 + static_cast<float>(ac.corners >> 19)) / static_cast<float>(dims >> 16));
+        }
         isotropic_direction(u_c, u_d, vel, p);
         rng_refill(rng, P, PSIM_BIRTH_STEP, p.id_lo, id_hi);
         p.tts = draw_scatter_time(P, s, p, rng_u01(rng));
@@ -549,14 +574,18 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
     if (PSIM_LINK_KIND(link) == PSIM_LINK_COMPOSITE) {
         const uint32_t first = (link >> 7) & 0xFFFFFu, n = link & 0x7Fu;
         link = 0u;  // boundary unless a sub-surface covers the hit point
+        // the records are searched starting at the one an even division of the edge would give (the edges of a lattice
+        // cell are divided evenly: found at once)
+        uint32_t j = min(static_cast<uint32_t>(s * static_cast<float>(n)), n - 1u);
         for (uint32_t i = 0; i < n; ++i) {
-            const float4 q = ldg(reinterpret_cast<const float4*>(P.subs + first + i));
+            const float4 q = ldg(reinterpret_cast<const float4*>(P.subs + first + j));
             if (s >= q.x && s <= q.y) {
                 ma = q.z;
                 mb = q.w;
-                link = ldg(&P.subs[first + i].link);
+                link = ldg(&P.subs[first + j].link);
                 break;
             }
+            j = (j + 1u == n) ? 0u : j + 1u;
         }
     }
     const uint32_t kind = PSIM_LINK_KIND(link);
@@ -609,6 +638,13 @@ PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step
         if (!PSIM_CELL_QUAD(p.cell) && q1 + q2 > 1.f) {  // (a parallelogram is the whole unit square of its frame)
             q1 = 1.f - q1;
             q2 = 1.f - q2;
+        }
+        if (P.lattice) {  // "the current cell" is the parallelogram of the lattice the phonon is in
+            const uint32_t dims = ldg(&P.cells[PSIM_CELL_INDEX(p.cell)].tri[1]);
+            float l1, l2;
+            const uint32_t nx = dims & 0xFFFFu, ny = dims >> 16, ix = lattice_split(p.b1, nx, l1), iy = lattice_split(p.b2, ny, l2);
+            q1 = clamp01((q1 + static_cast<float>(ix)) / static_cast<float>(nx));
+            q2 = clamp01((q2 + static_cast<float>(iy)) / static_cast<float>(ny));
         }
         p.b1 = q1;
         p.b2 = q2;

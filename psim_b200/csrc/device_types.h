@@ -73,8 +73,19 @@ struct PSIM_ALIGN(16) DevCell {
     uint32_t sensor_mat;       // [31:12] sensor index, [11:4] rate class, [3:0] material index (PSIM_CELL_*)
     uint32_t shape;            // index into DevParams::shapes
     uint32_t tri[2];           // model-file cell(s): a triangle names itself twice; a parallelogram its triangle below the
-                               // diagonal Q0-Q2 (b1 >= b2) and the one above
+                               // diagonal Q0-Q2 (b1 >= b2) and the one above.
+                               // In the LATTICE image (below) instead: [0] first entry of the cell in DevParams::sub_fine,
+                               // [1] nx | ny << 16, the cell being a lattice of nx x ny identical parallelograms.
 };
+
+// The LATTICE image of a mesh (flatten.cpp: build_lattices), used by launches whose window records nothing - the first 90 % of
+// the measurement steps of a steady-state run.  Where nothing is recorded a phonon's sensor area is irrelevant; what is left of
+// a cell transition is the change of material / relaxation rates / wall specularity, and between the parallelograms of one
+// rate class that the reference's builder lines up in rows and columns there is none.  So a rectangular block of nx x ny
+// identical parallelograms (same shape record, same material and rate class, linked whole edge to whole edge) flies as ONE cell
+// whose frame spans the block: b1 in [0, 1] covers the nx columns.  Its outer edges are composite surfaces (one sub-surface per
+// fine edge that is not a plain wall).  The pool holds lattice coordinates while such launches run; the first launch that
+// records converts every phonon it fetches back to its fine flight cell (coarse_to_fine, device_core.cuh).
 
 struct PSIM_ALIGN(16) DevShape {
     float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [u | v])
@@ -88,6 +99,7 @@ struct PSIM_ALIGN(16) DevShape {
 struct DevApiCell {
     uint32_t cell;             // tagged flight cell word (PSIM_CELL_*)
     uint32_t corners;          // [1:0] vertex 1, [3:2] vertex 2, [5:4] vertex 3; bit 0 of a pair = b1, bit 1 = b2
+                               // lattice image: also [18:6] column and [31:19] row of the cell's parallelogram in its lattice
 };
 
 // A part of an edge that is a transition to a neighbour or an emitting surface (compositeSurface.h:60-66).
@@ -171,12 +183,14 @@ struct DevParams {
     const float2* tables;      // [n_tables][PSIM_BINS] (cumulative probability, LA fraction)  (material.cpp:170-180)
     const uint32_t* guides;    // [n_tables][PSIM_GUIDE] search bracket for r in [k/G, (k+1)/G), G = PSIM_GUIDE: low | high << 16
     const float* velocities;   // [n_materials][2][PSIM_BINS] group velocity, LA then TA, m/s == nm/ns
+    const uint32_t* sub_fine;  // lattice image only: tagged fine flight-cell word of every parallelogram of every lattice cell, rows first
     uint32_t n_cells, n_flight_cells, n_shapes, n_sensors, n_materials, n_tables, n_emitters, n_sources;
     uint32_t num_steps;        // measurement steps M
     uint32_t first_tally_step; // reference step_adjustment_ (modelSimulator.h:24-26)
     uint32_t recorded_steps;   // M - first_tally_step
     uint32_t full_mode;        // t_eq == 0: bin-centre frequencies, no jitter (material.cpp:77-80)
     uint32_t phasor;           // phasor_sim: no intrinsic scattering (modelSimulator.cpp:189)
+    uint32_t lattice;          // cells / shapes / api_cells / subs / emitters are those of the lattice image
     float step_time;           // ns
     float step_time_inv;
     double step_time_d;

@@ -24,9 +24,243 @@ bool fail(std::string& err, int code, const std::string& msg, int& rc) {
     return false;
 }
 
+
+struct Frame {
+    double ox, oy, ux, uy, vx, vy;  // origin Q0 and the edge vectors u = Q1 - Q0, v = Q3 - Q0 (triangle: P2 - P1, P3 - P1)
+};
+
+// The lattice image of the flattened mesh `img` (device_types.h).  Fine flight cells A, B are lattice neighbours along b1 when
+// both are parallelograms with the SAME shape record (bit-identical fp32 frame matrix, normals and specularity: their frames
+// are parallel and equally oriented), the same material and rate class (a classified one: 255 always redraws), A's edge 1
+// (b1 = 1) is as a whole a plain transition onto B's edge 3 (b1 = 0) and back, and B's origin is A's origin + u; along b2
+// likewise with edges 2 / 0 and v.  Blocks are grown greedily from cells without a left / lower neighbour: a row to the
+// right, then rows upwards while every cell of the row above exists, is free and continues the row.  Everything else - the
+// triangles, parallelograms without such neighbours - is a block of one.  Leaves the lattice arrays empty when no block has
+// more than one cell or an edge would need more than 127 sub-surfaces.
+void build_lattices(HostImage& img, const std::vector<Frame>& frames) {
+    const uint32_t F = static_cast<uint32_t>(img.cells.size());
+    constexpr uint32_t kMaxSide = 120;
+    std::vector<char> quad(F, 0);
+    for (const DevApiCell& a : img.api_cells) { quad[PSIM_CELL_INDEX(a.cell)] = static_cast<char>(PSIM_CELL_QUAD(a.cell)); }
+    auto neighbour = [&](uint32_t c, uint32_t e_out, uint32_t e_in, bool along_u) -> int {
+        if (!quad[c]) { return -1; }
+        const DevCell& A = img.cells[c];
+        const uint32_t w = A.link[e_out];
+        if (PSIM_LINK_KIND(w) != PSIM_LINK_TRANSITION || ((w >> 28) & 3u) != e_in || (w & (1u << 27)) || !((w >> 26) & 1u)) { return -1; }
+        const uint32_t t = w & 0x03FFFFFFu;
+        if (t == c || t >= F || !quad[t]) { return -1; }
+        const DevCell& B = img.cells[t];
+        const uint32_t back = B.link[e_in];
+        if (PSIM_LINK_KIND(back) != PSIM_LINK_TRANSITION || (back & 0x03FFFFFFu) != c || ((back >> 28) & 3u) != e_out || (back & (1u << 27))) { return -1; }
+        if (B.shape != A.shape || ((B.sensor_mat ^ A.sensor_mat) & 0xFFFu) != 0u || PSIM_CELL_CLASS(A.sensor_mat) == 255u) { return -1; }
+        const Frame &fa = frames[c], &fb = frames[t];
+        const double dx = along_u ? fa.ux : fa.vx, dy = along_u ? fa.uy : fa.vy;
+        const double tol = 1e-9 * (std::fabs(fa.ux) + std::fabs(fa.uy) + std::fabs(fa.vx) + std::fabs(fa.vy));
+        if (std::fabs(fb.ox - (fa.ox + dx)) > tol || std::fabs(fb.oy - (fa.oy + dy)) > tol) { return -1; }
+        return static_cast<int>(t);
+    };
+    std::vector<int> right(F), up(F);
+    std::vector<char> has_left(F, 0), has_down(F, 0);
+    for (uint32_t c = 0; c < F; ++c) {
+        right[c] = neighbour(c, 1, 3, true);
+        up[c] = neighbour(c, 2, 0, false);
+        if (right[c] >= 0) { has_left[right[c]] = 1; }
+        if (up[c] >= 0) { has_down[up[c]] = 1; }
+    }
+    struct Block {
+        uint32_t nx, ny, sub_off;
+        std::vector<uint32_t> cells;  // [iy * nx + ix]
+    };
+    std::vector<Block> blocks;
+    std::vector<int> block_of(F, -1);
+    std::vector<uint32_t> ix_of(F, 0), iy_of(F, 0);
+    bool any_merge = false;
+    auto grow = [&](uint32_t c0) {
+        Block b{};
+        std::vector<uint32_t> row{ c0 };
+        for (int r = right[c0]; r >= 0 && block_of[r] < 0 && static_cast<uint32_t>(r) != c0 && row.size() < kMaxSide; r = right[r]) {
+            if (std::find(row.begin(), row.end(), static_cast<uint32_t>(r)) != row.end()) { break; }  // (a ring of cells)
+            row.push_back(static_cast<uint32_t>(r));
+        }
+        b.nx = static_cast<uint32_t>(row.size());
+        b.ny = 0;
+        const int id = static_cast<int>(blocks.size());
+        for (;;) {
+            for (uint32_t i = 0; i < b.nx; ++i) {
+                block_of[row[i]] = id;
+                ix_of[row[i]] = i;
+                iy_of[row[i]] = b.ny;
+                b.cells.push_back(row[i]);
+            }
+            ++b.ny;
+            if (b.ny >= kMaxSide) { break; }
+            std::vector<uint32_t> next(b.nx);
+            bool ok = true;
+            for (uint32_t i = 0; i < b.nx && ok; ++i) {
+                const int u = up[row[i]];
+                ok = u >= 0 && block_of[u] < 0 && (i == 0 || right[next[i - 1]] == u);
+                if (ok) { next[i] = static_cast<uint32_t>(u); }
+            }
+            if (!ok) { break; }
+            row = next;
+        }
+        any_merge |= b.cells.size() > 1;
+        blocks.push_back(std::move(b));
+    };
+    for (uint32_t c = 0; c < F; ++c) {
+        if (block_of[c] < 0 && !has_left[c] && !has_down[c]) { grow(c); }
+    }
+    for (uint32_t c = 0; c < F; ++c) {
+        if (block_of[c] < 0) { grow(c); }
+    }
+    if (!any_merge) { return; }
+    // blocks are numbered in the order of their first fine cell, so that a mesh without lattices maps to itself
+    uint32_t sub_total = 0;
+    for (Block& b : blocks) {
+        b.sub_off = sub_total;
+        sub_total += b.nx * b.ny;
+    }
+    std::vector<DevCell> cells(blocks.size());
+    std::vector<DevShape> shapes;
+    std::vector<DevSub> subs;
+    std::vector<uint32_t> sub_fine(sub_total);
+    auto shape_id = [&](const DevShape& sh) -> uint32_t {
+        for (size_t i = 0; i < shapes.size(); ++i) {
+            if (std::memcmp(&shapes[i], &sh, sizeof(sh)) == 0) { return static_cast<uint32_t>(i); }
+        }
+        shapes.push_back(sh);
+        return static_cast<uint32_t>(shapes.size() - 1);
+    };
+    std::unordered_map<uint64_t, uint32_t> shape_cache;  // (fine shape, nx, ny) -> lattice shape
+    auto word_of = [&](uint32_t block) { return block | (quad[blocks[block].cells[0]] ? (1u << 31) : 0u); };
+    // where fine cell t's edge e lies on the edge of its block: position k of n, counted along the block's edge coordinate
+    auto edge_slot = [&](uint32_t t, uint32_t e, uint32_t& k, uint32_t& n) -> bool {
+        const Block& b = blocks[block_of[t]];
+        const uint32_t ix = ix_of[t], iy = iy_of[t];
+        if (!quad[t]) {
+            k = 0, n = 1;
+            return true;
+        }
+        switch (e) {
+            case 0: k = ix, n = b.nx; return iy == 0;
+            case 1: k = iy, n = b.ny; return ix == b.nx - 1;
+            case 2: k = b.nx - 1 - ix, n = b.nx; return iy == b.ny - 1;
+            default: k = b.ny - 1 - iy, n = b.ny; return ix == 0;
+        }
+    };
+    bool ok = true;
+    for (size_t bi = 0; bi < blocks.size() && ok; ++bi) {
+        const Block& b = blocks[bi];
+        const uint32_t c0 = b.cells[0];
+        DevCell o{};
+        o.sensor_mat = img.cells[c0].sensor_mat;
+        o.tri[0] = b.sub_off;
+        o.tri[1] = b.nx | (b.ny << 16);
+        for (size_t i = 0; i < b.cells.size(); ++i) { sub_fine[b.sub_off + i] = b.cells[i] | (quad[b.cells[i]] ? (1u << 31) : 0u); }
+        const uint64_t key = (static_cast<uint64_t>(img.cells[c0].shape) << 32) | (b.nx << 16) | b.ny;
+        auto it = shape_cache.find(key);
+        if (it == shape_cache.end()) {
+            DevShape sh = img.shapes[img.cells[c0].shape];
+            sh.m00 /= static_cast<float>(b.nx);  // b1 spans nx cells
+            sh.m01 /= static_cast<float>(b.nx);
+            sh.m10 /= static_cast<float>(b.ny);
+            sh.m11 /= static_cast<float>(b.ny);
+            it = shape_cache.emplace(key, shape_id(sh)).first;
+        }
+        o.shape = it->second;
+        const uint32_t n_edges = quad[c0] ? 4u : 3u;
+        for (uint32_t e = 0; e < n_edges && ok; ++e) {
+            const uint32_t n = quad[c0] ? ((e & 1u) ? b.ny : b.nx) : 1u;
+            std::vector<DevSub> list;
+            for (uint32_t k = 0; k < n && ok; ++k) {
+                uint32_t ix = 0, iy = 0;
+                if (quad[c0]) {
+                    ix = e == 0 ? k : (e == 1 ? b.nx - 1 : (e == 2 ? b.nx - 1 - k : 0u));
+                    iy = e == 0 ? 0u : (e == 1 ? k : (e == 2 ? b.ny - 1 : b.ny - 1 - k));
+                }
+                const uint32_t c = b.cells[iy * b.nx + ix];
+                const uint32_t w = img.cells[c].link[e];
+                // one fine sub-surface (or whole-edge link) -> a sub-surface of the block's edge: its extent [s0, s1] of the fine
+                // edge becomes [(k + s0) / n, (k + s1) / n]; a transition that puts a phonon at a f s_fine + b f on the
+                // neighbour's fine edge puts it at (kT + that) / nT on the edge of the neighbour's block, s_fine = n s - k
+                auto add = [&](double s0, double s1, double af, double bf, uint32_t lw) {
+                    DevSub ds{};
+                    ds.s0 = static_cast<float>((k + s0) / n);
+                    ds.s1 = static_cast<float>((k + s1) / n);
+                    if (PSIM_LINK_KIND(lw) == PSIM_LINK_TRANSITION) {
+                        const uint32_t t = lw & 0x03FFFFFFu, te = (lw >> 28) & 3u;
+                        uint32_t kT = 0, nT = 1;
+                        if (t >= F || !edge_slot(t, te, kT, nT)) {
+                            ok = false;
+                            return;
+                        }
+                        ds.a = static_cast<float>(af * n / nT);
+                        ds.b = static_cast<float>((kT + bf - af * k) / nT);
+                        const uint32_t cw = word_of(static_cast<uint32_t>(block_of[t]));
+                        ds.link = (PSIM_LINK_TRANSITION << 30) | (te << 28) | (af > 0. ? (1u << 27) : 0u) | ((cw >> 31) << 26) | (cw & 0x03FFFFFFu);
+                    } else {
+                        ds.link = lw;  // an emitting surface keeps its index
+                    }
+                    list.push_back(ds);
+                };
+                if (PSIM_LINK_KIND(w) == PSIM_LINK_BOUNDARY) { continue; }  // uncovered = wall
+                if (PSIM_LINK_KIND(w) == PSIM_LINK_COMPOSITE) {
+                    const uint32_t first = (w >> 7) & 0xFFFFFu, cnt = w & 0x7Fu;
+                    for (uint32_t i = 0; i < cnt; ++i) {
+                        const DevSub& fs = img.subs[first + i];
+                        add(fs.s0, fs.s1, fs.a, fs.b, fs.link);
+                    }
+                } else if (PSIM_LINK_KIND(w) == PSIM_LINK_TRANSITION) {
+                    const bool same = (w & (1u << 27)) != 0u;
+                    add(0., 1., same ? 1. : -1., same ? 0. : 1., w);
+                } else {
+                    add(0., 1., 0., 0., w);
+                }
+            }
+            if (!ok) { break; }
+            if (list.empty()) {
+                o.link[e] = PSIM_LINK_BOUNDARY << 30;
+            } else if (n == 1 && list.size() == 1 && list[0].s0 <= 0.f && list[0].s1 >= 1.f &&
+                       (PSIM_LINK_KIND(list[0].link) == PSIM_LINK_EMIT || (std::fabs(std::fabs(list[0].a) - 1.f) < 1e-6f && (list[0].b == 0.f || list[0].b == 1.f)))) {
+                o.link[e] = list[0].link;  // whole edge onto a whole edge: the plain link word
+            } else if (list.size() > 127 || subs.size() + list.size() >= (1u << 20)) {
+                ok = false;
+            } else {
+                o.link[e] = (PSIM_LINK_COMPOSITE << 30) | (static_cast<uint32_t>(subs.size()) << 7) | static_cast<uint32_t>(list.size());
+                subs.insert(subs.end(), list.begin(), list.end());
+            }
+        }
+        cells[bi] = o;
+    }
+    if (!ok) { return; }
+    std::vector<DevApiCell> api(img.api_cells.size());
+    for (size_t a = 0; a < api.size(); ++a) {
+        const uint32_t c = PSIM_CELL_INDEX(img.api_cells[a].cell);
+        if (ix_of[c] >= (1u << 13) || iy_of[c] >= (1u << 13)) { return; }
+        api[a] = DevApiCell{ word_of(static_cast<uint32_t>(block_of[c])), (img.api_cells[a].corners & 0x3Fu) | (ix_of[c] << 6) | (iy_of[c] << 19) };
+    }
+    std::vector<DevEmitter> emitters = img.emitters;
+    for (DevEmitter& em : emitters) {
+        const uint32_t c = PSIM_CELL_INDEX(em.cell);
+        uint32_t k = 0, n = 1;
+        if (!edge_slot(c, em.edge, k, n)) { return; }
+        em.cell = word_of(static_cast<uint32_t>(block_of[c]));
+        em.s_p1 = static_cast<float>((k + static_cast<double>(em.s_p1)) / n);
+        em.s_p2 = static_cast<float>((k + static_cast<double>(em.s_p2)) / n);
+    }
+    if (subs.empty()) { subs.push_back(DevSub{}); }
+    if (emitters.empty()) { emitters.push_back(DevEmitter{}); }
+    img.lattice_cells = std::move(cells);
+    img.lattice_shapes = std::move(shapes);
+    img.lattice_subs = std::move(subs);
+    img.lattice_sub_fine = std::move(sub_fine);
+    img.lattice_api_cells = std::move(api);
+    img.lattice_emitters = std::move(emitters);
+}
+
 }  // namespace
 
-int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, bool merge_cells) {
+int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, int merge_cells) {
     int rc = 0;
     if (!d.materials || !d.sensors || !d.cells || !d.tables || !d.velocities || d.num_materials == 0 ||
         d.num_sensors == 0 || d.num_cells == 0 || d.num_tables == 0 || (d.num_emitters > 0 && !d.emitters) ||
@@ -356,6 +590,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, bo
         uint32_t n_edges;
     };
     std::vector<Pending> pending;
+    std::vector<Frame> frames;  // origin and edge vectors of every flight cell (fp64), for build_lattices
     for (uint32_t A = 0; A < C; ++A) {
         if (partner[A] >= 0 && static_cast<uint32_t>(partner[A]) < A) { continue; }  // made together with its partner
         const uint32_t ic = static_cast<uint32_t>(out.cells.size());
@@ -419,6 +654,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, bo
         o.shape = shape_id(sh);
         out.cells.push_back(o);
         pending.push_back(pe);
+        frames.push_back(Frame{ ox, oy, ux, uy, vx, vy });
     }
     // Pass 4: links in flight terms.  A flight edge that runs against its model edge (edge_flip) reverses the edge
     // coordinate: s -> 1 - s on the owner's side, t -> 1 - t on the side of whoever points at it.
@@ -473,6 +709,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, bo
             em.s_p2 = 1.f - em.s_p2;
         }
     }
+    if (merge_cells >= 2) { build_lattices(out, frames); }
     if (out.subs.empty()) { out.subs.push_back(DevSub{}); }
     if (out.emitters.empty()) { out.emitters.push_back(DevEmitter{}); }
 

@@ -18,6 +18,14 @@ struct HostImage {
     std::vector<DevSensor> classes;   // one record per rate class (at most 255)
     std::vector<DevSensor> step_sensors;  // empty, or [sensors][steps] (psim_model_desc::step_sensors)
     std::vector<DevSub> subs;
+    // The lattice image (device_types.h): the same mesh with every rectangular block of identical parallelograms of one rate
+    // class as ONE flight cell; flown by launches that record nothing.  Empty when no block of more than one cell exists.
+    std::vector<DevCell> lattice_cells;
+    std::vector<DevApiCell> lattice_api_cells;
+    std::vector<DevShape> lattice_shapes;
+    std::vector<DevSub> lattice_subs;
+    std::vector<DevEmitter> lattice_emitters;
+    std::vector<uint32_t> lattice_sub_fine;  // DevParams::sub_fine
     std::vector<DevSensor> sensors;
     std::vector<DevMaterial> materials;
     std::vector<DevEmitter> emitters;
@@ -40,8 +48,9 @@ struct BirthPlan {
 };
 
 // returns 0 or a PSIM_E_* code with `err` set
-// merge_cells = false keeps one flight cell per model triangle (the per-function probes and the A/B option "merge_cells")
-int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, bool merge_cells = true);
+// merge_cells = 0 keeps one flight cell per model triangle (the per-function probes and the A/B option "merge_cells"),
+// 1 pairs triangles into parallelograms, 2 (default) also builds the lattice image
+int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, int merge_cells = 2);
 int plan_births(const HostImage& img, const psim_source* sources, size_t n, uint32_t shard, uint32_t num_shards,
                 BirthPlan& out, std::string& err);
 

@@ -62,6 +62,11 @@ struct LaunchArgs {
     unsigned long long* stats;       // [0] drift steps [1] flight segments [2] absorbed [3] pool overflow [4] Philox block budget exceeded
     unsigned long long* alive_hist;  // [launch]: pool population after this launch
     uint32_t launch_index;
+    // the pool this launch reads is in lattice coordinates (device_types.h) and the launch flies the fine image: every phonon
+    // fetched from the pool is converted first (the first recording launch after the unrecorded ones)
+    uint32_t convert_input;
+    const DevCell* lattice_cells;
+    const uint32_t* lattice_sub_fine;
 };
 
 __host__ __device__ __forceinline__ size_t tally_smem_offset_f(uint32_t nst, uint32_t S) {
@@ -250,6 +255,7 @@ __device__ __forceinline__ void load_phonon(const LaunchArgs& a, size_t i, psim:
     p.packed = vb.y;
     p.cell = vb.z;
     p.id_lo = vb.w;
+    if (a.convert_input) { psim::coarse_to_fine(a.lattice_cells, a.lattice_sub_fine, p.cell, p.b1, p.b2); }
 }
 
 __device__ __forceinline__ void store_phonon(const LaunchArgs& a, size_t i, const psim::Phonon& p) {
@@ -1087,15 +1093,18 @@ __global__ void transpose_tallies_kernel(const int32_t* tally_e, const long long
 }
 
 // phonons per MODEL cell: a flight cell that is a parallelogram holds one model triangle on either side of its diagonal
+// (lattice_cells != NULL: the pool is in lattice coordinates; P is always the fine image)
 __global__ void cell_histogram_kernel(DevParams P, const float4* pool_a, const uint4* pool_b, const uint32_t* cnt, uint32_t seg_cap,
-                                      uint32_t n_warps, unsigned long long* hist) {
+                                      uint32_t n_warps, unsigned long long* hist, const DevCell* lattice_cells, const uint32_t* lattice_sub_fine) {
     const uint32_t w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (w >= n_warps) { return; }
     const uint32_t n = cnt[w];
     for (uint32_t i = threadIdx.x & 31u; i < n; i += 32u) {
         const size_t k = static_cast<size_t>(w) * seg_cap + i;
-        const float4 a = pool_a[k];
-        atomicAdd(&hist[psim::api_cell_of(P, pool_b[k].z, a.x, a.y)], 1ull);
+        float4 a = pool_a[k];
+        uint32_t cell = pool_b[k].z;
+        if (lattice_cells != nullptr) { psim::coarse_to_fine(lattice_cells, lattice_sub_fine, cell, a.x, a.y); }
+        atomicAdd(&hist[psim::api_cell_of(P, cell, a.x, a.y)], 1ull);
     }
 }
 

@@ -39,6 +39,15 @@ struct psim_gpu {
     psim::HostImage img_tri;         // the same model with one flight cell per triangle: geometry arrays only (probes, option "merge_cells")
     psim::BirthPlan plan;
     DevParams P{};  // device pointers
+    DevParams PL{}; // the same over the lattice image (device_types.h); valid while have_lattice
+    bool have_lattice = false;      // the model has a lattice image and option "merge_cells" is 2
+    bool pool_in_lattice = false;   // the live pool holds lattice coordinates (the launches so far recorded nothing)
+    void* d_lat_cells = nullptr;
+    void* d_lat_api_cells = nullptr;
+    void* d_lat_shapes = nullptr;
+    void* d_lat_subs = nullptr;
+    void* d_lat_emitters = nullptr;
+    void* d_lat_sub_fine = nullptr;
     void* d_cells = nullptr;
     void* d_api_cells = nullptr;
     void* d_shapes = nullptr;
@@ -82,7 +91,8 @@ struct psim_gpu {
     int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
     int64_t opt_queue_slots = PSIM_QUEUE_SLOTS;  // phonons in flight per warp of the work-queue kernel (128, or 64: more L1 left for the mesh)
     int64_t opt_tally_shared = -1;
-    int64_t opt_merge_cells = 1;     // 0: one flight cell per model triangle (A/B, per-function probes)
+    int64_t opt_merge_cells = 2;     // 0: one flight cell per model triangle (A/B, per-function probes), 1: pairs of triangles as
+                                     // parallelograms, 2: also blocks of parallelograms as lattice cells where nothing is recorded
     uint32_t last_tally_shared = 0;
     uint32_t last_window = 0;
     uint32_t max_flux_fixed = 0;     // largest |velocity| in flux fixed-point units
@@ -250,6 +260,39 @@ int upload_geometry(psim_gpu* h, const psim::HostImage& g) {
     return 0;
 }
 
+// The lattice image, if the model has one: PL = P with the geometry pointers replaced.  Called after P is complete.
+int upload_lattice(psim_gpu* h) {
+    h->have_lattice = false;
+    if (h->img.lattice_cells.empty()) { return 0; }
+    for (void** p : { &h->d_lat_cells, &h->d_lat_shapes, &h->d_lat_api_cells, &h->d_lat_subs, &h->d_lat_emitters, &h->d_lat_sub_fine }) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (int rc = upload(h, &h->d_lat_cells, h->img.lattice_cells)) { return rc; }
+    if (int rc = upload(h, &h->d_lat_shapes, h->img.lattice_shapes)) { return rc; }
+    if (int rc = upload(h, &h->d_lat_api_cells, h->img.lattice_api_cells)) { return rc; }
+    if (int rc = upload(h, &h->d_lat_subs, h->img.lattice_subs)) { return rc; }
+    if (int rc = upload(h, &h->d_lat_emitters, h->img.lattice_emitters)) { return rc; }
+    if (int rc = upload(h, &h->d_lat_sub_fine, h->img.lattice_sub_fine)) { return rc; }
+    h->have_lattice = true;
+    return 0;
+}
+
+// P over the lattice image (the scalars, sources and seed of P as they are now)
+DevParams lattice_params(const psim_gpu* h) {
+    DevParams L = h->P;
+    L.cells = static_cast<const DevCell*>(h->d_lat_cells);
+    L.shapes = static_cast<const DevShape*>(h->d_lat_shapes);
+    L.api_cells = static_cast<const DevApiCell*>(h->d_lat_api_cells);
+    L.subs = static_cast<const DevSub*>(h->d_lat_subs);
+    L.emitters = static_cast<const DevEmitter*>(h->d_lat_emitters);
+    L.sub_fine = static_cast<const uint32_t*>(h->d_lat_sub_fine);
+    L.n_flight_cells = static_cast<uint32_t>(h->img.lattice_cells.size());
+    L.n_shapes = static_cast<uint32_t>(h->img.lattice_shapes.size());
+    L.lattice = 1u;
+    return L;
+}
+
 int zero_run_state(psim_gpu* h) {
     const DevParams& P = h->P;
     const size_t n = static_cast<size_t>(P.recorded_steps) * P.n_sensors;
@@ -273,6 +316,7 @@ int zero_run_state(psim_gpu* h) {
         PSIM_CUDA(cudaMemsetAsync(h->cnt[1], 0, h->n_warps * sizeof(uint32_t), h->stream));
     }
     h->cur = 0;
+    h->pool_in_lattice = false;
     h->next_step = 0;
     h->launches = 0;
     h->birth_offset = 0;
@@ -325,7 +369,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
     h->sm_count = prop.multiProcessorCount;
     try {  // nothing throws across the ABI: a description whose sizes exhaust the host's memory is an invalid description
         if (int rc = psim::flatten_model(*desc, h->img, h->err)) { return bail(rc); }
-        if (int rc = psim::flatten_model(*desc, h->img_tri, h->err, false)) { return bail(rc); }
+        if (int rc = psim::flatten_model(*desc, h->img_tri, h->err, 0)) { return bail(rc); }
         for (auto* v : { &h->img_tri.tables }) { std::vector<float2>().swap(*v); }  // only its geometry arrays are kept
         std::vector<uint32_t>().swap(h->img_tri.guides);
         std::vector<float>().swap(h->img_tri.velocities);
@@ -361,6 +405,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         if (int rc = upload(h, &h->d_guides, h->img.guides)) { return rc; }
         h->P = h->img.scalars;
         if (int rc = upload_geometry(h, h->img)) { return rc; }
+        if (int rc = upload_lattice(h)) { return rc; }
         h->P.classes = static_cast<const DevSensor*>(h->d_classes);
         h->P.step_sensors = static_cast<const DevSensor*>(h->d_step_sensors);
         h->P.sensors = static_cast<const DevSensor*>(h->d_sensors);
@@ -485,7 +530,14 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         plan_launch(h, s0, step_end, s1, form, smem, records);
         const bool shared = form != 0u;
         LaunchArgs a{};
-        a.P = h->P;
+        // A window that records nothing flies the lattice image (device_types.h) - from the start of a run until the first
+        // window that records; that one converts the pool back as it fetches it.
+        const bool lattice = h->have_lattice && h->opt_merge_cells == 2 && !records && (h->pool_in_lattice || s0 == 0);
+        a.P = lattice ? lattice_params(h) : h->P;
+        a.convert_input = (h->pool_in_lattice && !lattice) ? 1u : 0u;
+        a.lattice_cells = static_cast<const DevCell*>(h->d_lat_cells);
+        a.lattice_sub_fine = static_cast<const uint32_t*>(h->d_lat_sub_fine);
+        h->pool_in_lattice = lattice;
         a.in_a = h->pool_a[h->cur];
         a.in_b = h->pool_b[h->cur];
         a.out_a = h->pool_a[h->cur ^ 1];
@@ -663,7 +715,9 @@ int psim_gpu_cell_histogram(psim_gpu* h, uint64_t* per_cell) {
     }
     if (int rc = psim_gpu_synchronize(h)) { return rc; }
     PSIM_CUDA(cudaMemset(h->d_hist, 0, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
-    cell_histogram_kernel<<<h->n_warps / kWarpsPerBlock, kBlock>>>(h->P, h->pool_a[h->cur], h->pool_b[h->cur], h->cnt[h->cur], h->seg_cap, h->n_warps, h->d_hist);
+    cell_histogram_kernel<<<h->n_warps / kWarpsPerBlock, kBlock>>>(h->P, h->pool_a[h->cur], h->pool_b[h->cur], h->cnt[h->cur], h->seg_cap, h->n_warps, h->d_hist,
+                                                                   h->pool_in_lattice ? static_cast<const DevCell*>(h->d_lat_cells) : nullptr,
+                                                                   static_cast<const uint32_t*>(h->d_lat_sub_fine));
     PSIM_CUDA(cudaGetLastError());
     PSIM_CUDA(cudaMemcpy(per_cell, h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return PSIM_OK;
@@ -691,6 +745,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     out->tally_in_shared = h->last_tally_shared;
     out->kernel = static_cast<uint32_t>(h->opt_kernel);
     out->flight_cells = h->P.n_flight_cells;
+    out->lattice_cells = (h->have_lattice && h->opt_merge_cells == 2) ? static_cast<uint32_t>(h->img.lattice_cells.size()) : 0u;
     out->image_bytes = h->img.cells.size() * sizeof(DevCell) + h->img.api_cells.size() * sizeof(DevApiCell) + h->img.shapes.size() * sizeof(DevShape) + (h->img.classes.size() + h->img.step_sensors.size()) * sizeof(DevSensor) + h->img.subs.size() * sizeof(DevSub) +
                        h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
                        h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +
@@ -729,16 +784,17 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
         }
         h->opt_queue_slots = value;
     } else if (k == "merge_cells") {
-        if (h->have_sources || (value != 0 && value != 1)) {
-            h->err = "merge_cells must be 0 (one flight cell per model triangle) or 1 (pairs of triangles fly as one parallelogram) and set before set_sources";
+        if (h->have_sources || value < 0 || value > 2) {
+            h->err = "merge_cells must be 0 (one flight cell per model triangle), 1 (pairs of triangles fly as one parallelogram) or 2 (and blocks of "
+                     "parallelograms as one lattice cell where nothing is recorded) and set before set_sources";
             return PSIM_E_STATE;
         }
-        if (value != h->opt_merge_cells) {
+        if ((value != 0) != (h->opt_merge_cells != 0)) {
             PSIM_CUDA(cudaSetDevice(h->device));
             PSIM_CUDA(cudaDeviceSynchronize());
             if (int rc = upload_geometry(h, value ? h->img : h->img_tri)) { return rc; }
-            h->opt_merge_cells = value;
         }
+        h->opt_merge_cells = value;
     } else if (k == "tally_shared") {
         if (h->have_sources || value < -1 || value > 4 || value == 3) {  // the tally form of a run is fixed when it starts
             h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 / 4 / 2 (staged: two / three 32-bit parts, 64-bit) and set before set_sources";
@@ -767,6 +823,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaDeviceSynchronize();
     free_pool(h);
     free_plan(h);
+    for (void* p : { h->d_lat_cells, h->d_lat_api_cells, h->d_lat_shapes, h->d_lat_subs, h->d_lat_emitters, h->d_lat_sub_fine }) { cudaFree(p); }
     cudaFree(h->d_cells);
     cudaFree(h->d_api_cells);
     cudaFree(h->d_shapes);

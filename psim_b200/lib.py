@@ -77,7 +77,8 @@ class Stats(C.Structure):
                 ("events", C.c_uint64), ("peak_alive", C.c_uint64), ("kernel_ms", C.c_double),
                 ("launches", C.c_uint32), ("steps_per_launch", C.c_uint32), ("warps", C.c_uint32),
                 ("tally_in_shared", C.c_uint32), ("image_bytes", C.c_uint64), ("plan_bytes", C.c_uint64),
-                ("tally_bytes", C.c_uint64), ("kernel", C.c_uint32), ("flight_cells", C.c_uint32)]
+                ("tally_bytes", C.c_uint64), ("kernel", C.c_uint32), ("flight_cells", C.c_uint32),
+                ("lattice_cells", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -10,6 +10,11 @@
 #include <string>
 #include <vector>
 
+// 0: one flight cell per triangle, 1: pairs of triangles as parallelograms, 2 (the library's default): also the lattice image
+// for the passes that record nothing
+static int g_merge_cells = 2;
+extern "C" void psim_emu_set_merge_cells(int level) { g_merge_cells = level; }
+
 extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sources, size_t n_sources, uint64_t seed,
                             uint32_t shard, uint32_t num_shards, uint32_t steps_per_pass, int32_t* energy /*[S][R]*/,
                             double* flux /*[S][R][2]*/, int64_t* flux_fixed, uint64_t* drift_steps, uint64_t* events,
@@ -18,7 +23,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     psim::HostImage img;
     psim::BirthPlan plan;
     std::string e;
-    int rc = psim::flatten_model(*desc, img, e);
+    int rc = psim::flatten_model(*desc, img, e, g_merge_cells);
     if (!rc) { rc = psim::plan_births(img, sources, n_sources, shard, num_shards, plan, e); }
     if (rc) {
         if (err && err_len) { std::strncpy(err, e.c_str(), err_len - 1), err[err_len - 1] = 0; }
@@ -41,6 +46,20 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     P.n_sources = static_cast<uint32_t>(n_sources);
     P.seed_lo = static_cast<uint32_t>(seed);
     P.seed_hi = static_cast<uint32_t>(seed >> 32);
+    // the same parameters over the lattice image (device_types.h), for the passes that record nothing
+    const bool have_lattice = !img.lattice_cells.empty();
+    DevParams PL = P;
+    if (have_lattice) {
+        PL.cells = img.lattice_cells.data();
+        PL.api_cells = img.lattice_api_cells.data();
+        PL.shapes = img.lattice_shapes.data();
+        PL.subs = img.lattice_subs.data();
+        PL.emitters = img.lattice_emitters.data();
+        PL.sub_fine = img.lattice_sub_fine.data();
+        PL.lattice = 1u;
+    }
+    const DevParams PF = P;
+    bool pool_in_lattice = false;
     const uint32_t S = P.n_sensors, R = P.recorded_steps, M = P.num_steps;
     std::vector<long long> te(static_cast<size_t>(R) * S, 0), tf(static_cast<size_t>(R) * S * 2, 0);
     std::vector<psim::Phonon> pool, next;
@@ -69,6 +88,13 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
     for (uint32_t s0 = 0; s0 + 1 < M; s0 += B) {
         const uint32_t s1 = std::min(s0 + B, M - 1);
         next.clear();
+        const bool records = s1 + 1 > P.first_tally_step;
+        const bool lattice_pass = have_lattice && !records && (pool_in_lattice || pool.empty());
+        if (pool_in_lattice && !lattice_pass) {
+            for (auto& p : pool) { psim::coarse_to_fine(PL.cells, PL.sub_fine, p.cell, p.b1, p.b2); }
+        }
+        pool_in_lattice = lattice_pass;
+        P = lattice_pass ? PL : PF;
         for (const auto& p : pool) { run_one(p, s0, P.step_time, s0, s1); }
         for (uint32_t eidx = plan.step_begin[s0]; eidx < plan.step_begin[s1]; ++eidx) {
             const DevBirth& b = plan.births[eidx];
@@ -81,7 +107,10 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         pool.swap(next);
         if (alive_per_pass) { alive_per_pass[s1 - 1] = pool.size(); }
         if (cell_hist_steps) {
-            for (const auto& p : pool) { ++cell_hist_steps[static_cast<size_t>(s1 - 1) * P.n_cells + psim::api_cell_of(P, p.cell, p.b1, p.b2)]; }
+            for (auto p : pool) {
+                if (pool_in_lattice) { psim::coarse_to_fine(PL.cells, PL.sub_fine, p.cell, p.b1, p.b2); }
+                ++cell_hist_steps[static_cast<size_t>(s1 - 1) * P.n_cells + psim::api_cell_of(PF, p.cell, p.b1, p.b2)];
+            }
         }
     }
     const double scale = 1. / static_cast<double>(1 << PSIM_FLUX_FRAC_BITS);
@@ -108,10 +137,29 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
 extern "C" int psim_emu_mesh_info(const psim_model_desc* desc, int merge_cells, uint32_t* flight_cells, uint32_t* shapes, uint32_t* classes) {
     psim::HostImage img;
     std::string e;
-    const int rc = psim::flatten_model(*desc, img, e, merge_cells != 0);
+    const int rc = psim::flatten_model(*desc, img, e, merge_cells);
     if (rc) { return rc; }
     if (flight_cells) { *flight_cells = static_cast<uint32_t>(img.cells.size()); }
     if (shapes) { *shapes = static_cast<uint32_t>(img.shapes.size()); }
     if (classes) { *classes = static_cast<uint32_t>(img.classes.size()); }
+    return 0;
+}
+
+// the lattice image: cells, how many of them stand for more than one fine flight cell, the largest block, partial-edge records
+extern "C" int psim_emu_lattice_info(const psim_model_desc* desc, uint32_t* cells, uint32_t* merged, uint32_t* largest, uint32_t* subs) {
+    psim::HostImage img;
+    std::string e;
+    const int rc = psim::flatten_model(*desc, img, e, 2);
+    if (rc) { return rc; }
+    uint32_t m = 0, big = 0;
+    for (const DevCell& c : img.lattice_cells) {
+        const uint32_t n = (c.tri[1] & 0xFFFFu) * (c.tri[1] >> 16);
+        m += n > 1u;
+        big = std::max(big, n);
+    }
+    if (cells) { *cells = static_cast<uint32_t>(img.lattice_cells.size()); }
+    if (merged) { *merged = m; }
+    if (largest) { *largest = big; }
+    if (subs) { *subs = static_cast<uint32_t>(img.lattice_subs.size()); }
     return 0;
 }

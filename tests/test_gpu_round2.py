@@ -91,11 +91,12 @@ def hot_box(dt_ns: float, num_phonons: int, steps: int = 100):
 def test_random_blocks_of_a_long_interval_do_not_repeat():
     """the packed kernels kept 10 bits of Philox block counter per (phonon, measurement step) and saturated
     silently.  Now 13 bits: with 16 ns intervals a phonon consumes well over 1023 blocks per interval (checked: more than
-    2000 events per drift-step on average), and the work-queue and lane-bound kernels (packed counter) must still equal the
+    1500 events per drift-step on average, nearly all of them scatters - the box is one lattice cell until the recorded
+    steps begin), and the work-queue and lane-bound kernels (packed counter) must still equal the
     lock-step kernel (counter in a register) bit for bit."""
     model = T.load_model(hot_box(16.0, 400))
     ref = gpu_run_case(model, 3, steps_per_launch=4, options={"kernel": 1, "tally_shared": 0}, finish=False)
-    assert ref["stats"][0]["events"] > 2000 * ref["stats"][0]["drift_steps"]  # or the test is void
+    assert ref["stats"][0]["events"] > 1500 * ref["stats"][0]["drift_steps"]  # or the test is void
     for opts in ({"kernel": 2, "tally_shared": 0}, {"kernel": 0, "tally_shared": 0}, {"kernel": 2, "tally_shared": 1}):
         got = gpu_run_case(model, 3, steps_per_launch=4, options=opts, finish=False)
         assert np.array_equal(got["energy"], ref["energy"]), opts
@@ -237,3 +238,65 @@ def test_triangle_pairs_fly_as_one_parallelogram_without_changing_the_physics():
     assert int(hist.sum()) == alive and hist.size == info.num_cells
     even, odd = int(hist[0::2].sum()), int(hist[1::2].sum())
     assert abs(even - odd) < 0.1 * alive  # the builder lists the two triangles of a rectangle one after the other
+
+
+def test_blocks_of_parallelograms_fly_as_one_lattice_cell_where_nothing_is_recorded():
+    """flatten.cpp:build_lattices.  In launches that record nothing (the first 90 % of the steps of a steady-state run) every
+    rectangular block of identical parallelograms of one material and rate class is ONE flight cell: a transition between
+    two of them changes nothing but the sensor label, which such a launch never reads (TransitionSurface::handlePhonon,
+    surface.cpp:71-75; the time to scatter need not be redrawn where the rates are the same, modelSimulator.cpp:192-194).
+    The pool is converted back to fine flight cells by the first launch that records.  Same seed, with and without: the same
+    phonons are emitted, the same random streams drive them, so the runs differ by floating-point rounding only - far less than
+    two seeds differ; 8 seeds each way agree like two sets of runs of the same code; the histogram over MODEL cells taken
+    while the pool is in lattice coordinates agrees with the one taken without lattices; periodic runs (everything recorded)
+    do not use the lattice image at all."""
+    from psim_b200 import configs
+    for name, steps_mid in (("kinked_spec", 600), ("sige", 300), ("sides_ss", 300), ("linear_rough", 300)):
+        if name not in T.all_case_names():
+            continue
+        model = T.load_model(T.case_model(name), num_phonons=200_000)
+        with_l = [gpu_run_case(model, seed) for seed in range(1, 9)]
+        without = [gpu_run_case(model, seed, options={"merge_cells": 1}) for seed in range(1, 9)]
+        s2, s1 = with_l[0]["stats"][0], without[0]["stats"][0]
+        assert s1["lattice_cells"] == 0 and 0 < s2["lattice_cells"] < s2["flight_cells"] == s1["flight_cells"]
+        assert with_l[0]["sources"] == without[0]["sources"]
+        assert s2["events"] < 0.9 * s1["events"], (name, s2["events"], s1["events"])
+        assert abs(s2["drift_steps"] - s1["drift_steps"]) < 0.005 * s1["drift_steps"]
+        # same seed: rounding-level differences, a small fraction of the seed-to-seed scatter
+        e2 = np.stack([r["energy"].sum(axis=1) for r in with_l]).astype(float)
+        e1 = np.stack([r["energy"].sum(axis=1) for r in without]).astype(float)
+        assert np.abs(e2 - e1).mean() < 0.35 * e1.std(axis=0, ddof=1).mean(), name
+        f2 = np.stack([r["flux"].sum(axis=1) for r in with_l])
+        f1 = np.stack([r["flux"].sum(axis=1) for r in without])
+        assert np.abs(f2 - f1).mean() < 0.35 * f1.std(axis=0, ddof=1).mean(), name
+        # different seeds: two sets of runs of the same physics
+        other = [gpu_run_case(model, seed, options={"merge_cells": 1}) for seed in range(11, 19)]
+        feats = {k: [T.run_features(r["energy"], r["flux"], 0, r["six"], r["temps"], r["fluxes"]) for r in runs] for k, runs in (("m", with_l), ("p", other))}
+        gold = {"n_seeds": 8}
+        for key in ("tally_e", "tally_f", "out6"):
+            stack = np.stack([r[key] for r in feats["p"]])
+            gold[key + "_mean"], gold[key + "_std"] = stack.mean(axis=0), stack.std(axis=0, ddof=1)
+        T.assert_parity(T.welch_z(feats["m"], gold, "tally_e"), name + ": lattice vs fine flight cells, energy tallies")
+        T.assert_parity(T.welch_z(feats["m"], gold, "tally_f"), name + ": lattice vs fine flight cells, flux tallies")
+        # phonons per MODEL cell in the middle of the unrecorded part
+        model.prepare()
+        hists = {}
+        for level in (1, 2):
+            src, n = model.sources(3)
+            g = psim.GpuSimulator(model.describe(), 0)
+            try:
+                g.set_option("merge_cells", level)
+                g.set_sources(src, n, 3, 0, 1)
+                g.run_steps(0, steps_mid)
+                hists[level] = (g.cell_histogram(), g.alive())
+            finally:
+                g.close()
+        (h1, a1), (h2, a2) = hists[1], hists[2]
+        assert int(h2.sum()) == a2 and int(h1.sum()) == a1 and abs(a1 - a2) <= 0.002 * a1 + 5
+        assert np.abs(h2.astype(float) - h1.astype(float)).sum() <= 0.05 * a1 + 20, name  # rounding moves a few phonons across a cell edge
+    periodic = T.load_model(configs.linear_sides(sim_type=1, step_interval=4, num_phonons=100_000).to_dict())
+    a = gpu_run_case(periodic, 4, finish=False)
+    b = gpu_run_case(periodic, 4, options={"merge_cells": 1}, finish=False)
+    assert a["stats"][0]["lattice_cells"] > 0  # the image exists ...
+    assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["fixed"], b["fixed"])  # ... and no launch used it
+    assert a["stats"][0]["events"] == b["stats"][0]["events"]
