@@ -20,6 +20,14 @@
 #define PSIM_HD inline
 #endif
 
+// what the flight loop's fast path (fast_impact) takes on besides whole-edge transitions
+#ifndef PSIM_FAST_WALLS
+#define PSIM_FAST_WALLS 0
+#endif
+#ifndef PSIM_FAST_COMPOSITE
+#define PSIM_FAST_COMPOSITE 1
+#endif
+
 namespace psim {
 
 #if defined(__CUDA_ARCH__)
@@ -545,24 +553,60 @@ PSIM_HD bool rates_differ(uint32_t cell_word_a, uint32_t cell_word_b) {
     return ((cell_word_a ^ cell_word_b) & 0xFFFu) != 0u || PSIM_CELL_CLASS(cell_word_a) == 255u;
 }
 
-// Fast path of a surface interaction, taken inline by the flight loop: the edge is wholly a transition into a
-// neighbour cell with the same material and rate class (by far the most frequent impact inside a mesh).
-// Everything else (walls, emitters, material interfaces, partial edges, stuck-phonon guard) goes to impact_event.
-PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f, const uint4 links /* of p.cell */) {
-    const uint32_t link = link_of_edge(links, f.edge);
-    if (PSIM_LINK_KIND(link) != PSIM_LINK_TRANSITION || f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
+// Fast path of a surface interaction, taken inline by the flight loop - the impacts that need no random number and no
+// bookkeeping beyond the phonon's own state:
+//   * a transition into a neighbour cell with the same material and rate class, through a whole edge or through the
+//     sub-surface of a composite edge that an even division of the edge names (the edges of lattice cells, device_types.h);
+//   * the mirror reflection off a perfectly specular wall (Surface::boundaryHandlePhonon, surface.cpp:32-37).
+// Everything else (diffuse walls, emitters, material interfaces, other rates, irregular partial edges, the stuck-phonon
+// guard) goes to impact_event.  Where both can handle an impact they compute the same thing with the same expressions.
+// `links`, `tail` = the two halves of the record of p.cell; `reflected`: the velocity changed.
+PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 links, const uint2 tail, bool& reflected) {
+    reflected = false;
+    if (f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
+    uint32_t link = link_of_edge(links, f.edge);
+    const uint32_t kind = PSIM_LINK_KIND(link);
+    float s_in;  // where on the neighbour's edge the phonon enters
+    if (kind == PSIM_LINK_BOUNDARY) {
+        if (!PSIM_FAST_WALLS || !(link & 1u)) { return false; }  // not perfectly specular: needs random numbers
+        const float2 n = load_shape_normal(P.shapes, tail.y, f.edge);
+        set_cell_matrix(f, load_shape_matrix(P.shapes, tail.y));  // (a caller that only flies keeps r1, r2, not the matrix)
+        const float dn = p.dx * n.x + p.dy * n.y;
+        p.dx -= 2.f * dn * n.x;
+        p.dy -= 2.f * dn * n.y;
+        update_rates_of_motion(f, p);
+        ++f.ncoll;
+        reflected = true;
+        return true;
+    }
+    if (kind == PSIM_LINK_COMPOSITE) {
+        if (!PSIM_FAST_COMPOSITE || !(link & (1u << 27))) { return false; }  // nothing behind this edge that the fast path could handle
+        const uint32_t first = (link >> 7) & 0xFFFFFu, n = link & 0x7Fu;
+        const uint32_t j = first + min(static_cast<uint32_t>(f.s_hit * static_cast<float>(n)), n - 1u);
+        const float4 q = ldg(reinterpret_cast<const float4*>(P.subs + j));
+        link = ldg(&P.subs[j].link);
+        if (!(f.s_hit >= q.x && f.s_hit <= q.y) || PSIM_LINK_KIND(link) != PSIM_LINK_TRANSITION) { return false; }
+        s_in = clamp01(q.z * f.s_hit + q.w);
+    } else if (kind == PSIM_LINK_TRANSITION) {
+        s_in = (link & (1u << 27)) ? f.s_hit : 1.f - f.s_hit;
+    } else {
+        return false;
+    }
     const uint32_t ncell = PSIM_LINK_CELL(link);
-    const uint2 tail = load_cell_tail(P.cells, PSIM_CELL_INDEX(ncell));  // (sensor / class / material word, shape)
-    if (rates_differ(tail.x, f.sensor_mat)) { return false; }
-    place_on_edge(PSIM_CELL_QUAD(ncell), (link >> 28) & 3u, (link & (1u << 27)) ? f.s_hit : 1.f - f.s_hit, p);
+    const uint2 ntail = load_cell_tail(P.cells, PSIM_CELL_INDEX(ncell));  // (sensor / class / material word, shape)
+    if (rates_differ(ntail.x, f.sensor_mat)) { return false; }
+    place_on_edge(PSIM_CELL_QUAD(ncell), (link >> 28) & 3u, s_in, p);
     p.cell = ncell;
-    f.sensor_mat = tail.x;
-    set_cell_matrix(f, load_shape_matrix(P.shapes, tail.y));
+    f.sensor_mat = ntail.x;
+    set_cell_matrix(f, load_shape_matrix(P.shapes, ntail.y));
     update_rates_of_motion(f, p);
     ++f.ncoll;
     return true;
 }
-PSIM_HD bool fast_transition(const DevParams& P, Phonon& p, Flight& f) { return fast_transition(P, p, f, load_cell_links(P.cells, PSIM_CELL_INDEX(p.cell))); }
+PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f) {
+    bool reflected;
+    return fast_impact(P, p, f, load_cell_links(P.cells, PSIM_CELL_INDEX(p.cell)), load_cell_tail(P.cells, PSIM_CELL_INDEX(p.cell)), reflected);
+}
 
 PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {
     f.rng.left = 0;  // every event that needs random numbers starts a fresh Philox block of its (phonon, step) stream
@@ -697,7 +741,7 @@ PSIM_HD bool advance_window(const DevParams& P, Phonon& p, float t_first, uint32
         ++events;
         const int ev = flight_window(P, p, f, s, step_end, n_steps, [&](uint32_t k0, uint32_t k1) { on_measure(k0, k1, p, f); });
         if (ev == EV_IMPACT) {
-            if (fast_transition(P, p, f)) { continue; }
+            if (fast_impact(P, p, f)) { continue; }
             if (impact_event(P, p, f, s) == EV_DEAD) {
                 ++n_steps;
                 return false;

@@ -25,6 +25,29 @@ bool fail(std::string& err, int code, const std::string& msg, int& rc) {
 }
 
 
+// The hints of the flight loop's fast path (device_core.cuh: fast_impact) in the link words of an image: which walls are
+// perfectly specular, and which composite edges have a transition into a cell of the same material and rate class behind them.
+void mark_fast_links(std::vector<DevCell>& cells, const std::vector<DevShape>& shapes, const std::vector<DevSub>& subs) {
+    for (DevCell& c : cells) {
+        for (uint32_t e = 0; e < 4; ++e) {
+            const uint32_t w = c.link[e];
+            if (PSIM_LINK_KIND(w) == PSIM_LINK_BOUNDARY) {
+                c.link[e] = (PSIM_LINK_BOUNDARY << 30) | (shapes[c.shape].spec >= 1.f ? 1u : 0u);
+            } else if (PSIM_LINK_KIND(w) == PSIM_LINK_COMPOSITE) {
+                const uint32_t first = (w >> 7) & 0xFFFFFu, n = w & 0x7Fu;
+                bool any = false;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint32_t lw = subs[first + i].link;
+                    if (PSIM_LINK_KIND(lw) != PSIM_LINK_TRANSITION) { continue; }
+                    const uint32_t sm = cells[lw & 0x03FFFFFFu].sensor_mat;
+                    any |= ((sm ^ c.sensor_mat) & 0xFFFu) == 0u && PSIM_CELL_CLASS(c.sensor_mat) != 255u;
+                }
+                c.link[e] = (w & ~(1u << 27)) | (any ? (1u << 27) : 0u);
+            }
+        }
+    }
+}
+
 struct Frame {
     double ox, oy, ux, uy, vx, vy;  // origin Q0 and the edge vectors u = Q1 - Q0, v = Q3 - Q0 (triangle: P2 - P1, P3 - P1)
 };
@@ -710,6 +733,8 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
         }
     }
     if (merge_cells >= 2) { build_lattices(out, frames); }
+    mark_fast_links(out.cells, out.shapes, out.subs);
+    mark_fast_links(out.lattice_cells, out.lattice_shapes, out.lattice_subs);
     if (out.subs.empty()) { out.subs.push_back(DevSub{}); }
     if (out.emitters.empty()) { out.emitters.push_back(DevEmitter{}); }
 

@@ -543,7 +543,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                     p.dy = slot_f(SF_DY, k);
                     p.cell = slot_u(SF_CELL, k);
                     f.sensor_mat = psim::cell_sensor_word(P, p.cell);
-                    if (psim::fast_transition(P, p, f)) {
+                    if (psim::fast_impact(P, p, f)) {  // (it may have mirrored the velocity off a specular wall)
+                        slot_f(SF_DX, k) = p.dx;
+                        slot_f(SF_DY, k) = p.dy;
                         slot_u(SF_CELL, k) = p.cell;
                         slot_f(SF_R1, k) = f.r1;
                         slot_f(SF_R2, k) = f.r2;
@@ -608,6 +610,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
 }
 __device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
@@ -721,6 +726,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
     auto fly = [&](bool act, uint32_t k, psim::Phonon& p, psim::Flight& f, uint32_t misc, const bool have_vel) -> int {
         int dest = -1;
         uint32_t tk0 = 0, tk1 = 0, sensor = 0;  // recorded steps [tk0, tk1) that ended during this segment
+        int32_t fx = 0, fy = 0;                 // ... and what the segment adds to each of them (sign * fixed-point velocity)
         if (act) {
             f.edge = 0u;
             f.ncoll = PSIM_MISC_NCOLL(misc);
@@ -739,18 +745,23 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             // block): only the step survives in the packed word; otherwise only the edge changes
             misc = ((s != s0) ? (s - a.step_begin) : (misc & ~(3u << 17))) | (f.edge << 17);
             const bool hit = ev == psim::EV_IMPACT;
+            bool reflected = false;
             if (hit || tk1 > tk0) {
-                const uint32_t sm0 = psim::cell_sensor_word(P, cell0);  // of the cell the segment was flown in
+                const uint2 tail0 = psim::load_cell_tail(P.cells, PSIM_CELL_INDEX(cell0));  // of the cell the segment was flown in
                 if (!have_vel) {
                     const float4 g2 = lds128(grp(SG_VEL, k));
                     p.dx = g2.x;
                     p.dy = g2.y;
                     p.packed = __float_as_uint(g2.z);
                 }
-                sensor = PSIM_CELL_SENSOR(sm0);
+                sensor = PSIM_CELL_SENSOR(tail0.x);
+                if (TALLY != TALLY_NONE) {  // with the velocity the segment was flown at: the impact may mirror it
+                    fx = psim::flux_fixed(p.dx);
+                    fy = psim::flux_fixed(p.dy);
+                }
                 if (hit) {
-                    f.sensor_mat = sm0;
-                    if (psim::fast_transition(P, p, f, psim::load_cell_links(P.cells, PSIM_CELL_INDEX(cell0)))) {
+                    f.sensor_mat = tail0.x;
+                    if (psim::fast_impact(P, p, f, psim::load_cell_links(P.cells, PSIM_CELL_INDEX(cell0)), tail0, reflected)) {
                         misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
                         dest = Q_FLY;
                     } else {
@@ -761,12 +772,17 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             if (!hit) { dest = (ev == psim::EV_SCATTER) ? Q_SCT : Q_FIN; }
             sts128(grp(SG_POS, k), make_float4(p.b1, p.b2, f.r1, f.r2));
             sts128(grp(SG_TIME, k), make_float4(p.tts, f.t, __uint_as_float(misc), __uint_as_float(p.cell)));
-            if (have_vel) { sts128(grp(SG_VEL, k), make_float4(p.dx, p.dy, __uint_as_float(p.packed), __uint_as_float(p.id_lo))); }
+            if (have_vel) {
+                sts128(grp(SG_VEL, k), make_float4(p.dx, p.dy, __uint_as_float(p.packed), __uint_as_float(p.id_lo)));
+            } else if (reflected) {
+                sts64(grp(SG_VEL, k), p.dx, p.dy);
+            }
         }
         if (TALLY != TALLY_NONE) {
             const bool has = tk1 > tk0;
             const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
-            const int32_t fx = psim::flux_fixed(p.dx) * sg, fy = psim::flux_fixed(p.dy) * sg;
+            fx *= sg;
+            fy *= sg;
             if (TALLY == TALLY_GLOBAL) {
                 tally_post_global(a, post, lane, lt_mask, has, tk0, tk1, sensor, sg, fx, fy);
             } else if (has) {

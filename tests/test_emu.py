@@ -300,3 +300,53 @@ def test_flatten_pairs_triangles_into_parallelograms_and_dedupes_shapes():
     m.emit_surface((40.0, 0.0), (40.0, 10.0), 290)
     cells, flight, _, _ = info(m.to_dict())
     assert cells == 8 and flight == 8
+
+
+def test_lattice_image_blocks_and_their_neutrality():
+    """flatten.cpp:build_lattices - the image flown by the launches that record nothing: every rectangular block of identical
+    parallelograms of one material and rate class is one cell.  The Si/Ge bench model is two blocks of 5 x 5 (silicon half,
+    germanium half), linear_sides one block of 100 x 10, the bar one of 20 x 1, the kinked wire 250 cells (118 blocks, the
+    largest 21 x 21, plus the triangles and trapezoids of its kinks); a mesh whose sensors all differ in temperature has no
+    block, and neither has a re-iterated transient run (per-step rates).  Neutrality: with the same seed the same phonons are
+    emitted and driven by the same random streams, so a run with the lattice image differs from one without by floating-point
+    rounding only - a small fraction of what two seeds differ by - and far fewer flight segments are flown."""
+    import ctypes as C
+    from psim_b200 import configs
+    from tests import cases
+    lib = T.emu_lib()
+    lib.psim_emu_lattice_info.restype = C.c_int
+
+    def info(model_dict):
+        m = T.load_model(model_dict)
+        m.prepare()
+        v = [C.c_uint32() for _ in range(4)]
+        assert lib.psim_emu_lattice_info(m.describe(), *[C.byref(x) for x in v]) == 0
+        return tuple(x.value for x in v)  # cells, blocks of more than one, largest block, partial-edge records
+
+    assert info(configs.si_ge_grid(num_phonons=1000).to_dict())[:3] == (2, 2, 25)
+    assert info(configs.linear_sides(num_phonons=1000).to_dict())[:3] == (1, 1, 1000)
+    assert info(configs.linear(num_phonons=1000).to_dict())[:3] == (1, 1, 20)
+    kinked = cases.kinked_model()
+    if kinked is not None:
+        cells, merged, largest, subs = info(configs.with_settings(kinked, num_phonons=1000))
+        assert (cells, merged, largest) == (250, 118, 441) and subs < 4000
+    graded = configs.linear(num_phonons=1000).to_dict()
+    graded["sensors"] = [dict(s, t_init=300.0 + 0.1 * i) for i, s in enumerate(graded["sensors"])]
+    assert info(graded)[:3] == (0, 0, 0)  # every sensor its own rate class: nothing to merge, no image
+    try:
+        for name, spp in (("sige", 64), ("sides_ss", 64), ("linear_rough", 64)):
+            model = T.load_model(T.case_model(name), num_phonons=30_000)
+            model.prepare()
+            runs = {}
+            for level in (1, 2):
+                lib.psim_emu_set_merge_cells(level)
+                runs[level] = [T.emu_run(model, seed, steps_per_pass=spp) for seed in (1, 2, 3, 4)]
+            e1 = np.stack([r["energy"].sum(axis=1) for r in runs[1]]).astype(float)
+            e2 = np.stack([r["energy"].sum(axis=1) for r in runs[2]]).astype(float)
+            assert np.abs(e2 - e1).mean() < 0.25 * e1.std(axis=0, ddof=1).mean(), name
+            for a, b in zip(runs[1], runs[2]):
+                assert a["sources"] == b["sources"]
+                assert abs(a["drift_steps"] - b["drift_steps"]) < 0.002 * a["drift_steps"], name
+                assert b["events"] < 0.9 * a["events"], name
+    finally:
+        lib.psim_emu_set_merge_cells(2)

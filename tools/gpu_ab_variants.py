@@ -14,14 +14,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = {  # round 2: more resident warps with fewer registers, and the pass-fusion threshold (kernels.cuh: PSIM_FUSE_LANES)
-    "b1024_q96": {"PSIM_BLOCK": 1024, "PSIM_QUEUE_SLOTS": 96},
-    "b896_q104": {"PSIM_BLOCK": 896, "PSIM_QUEUE_SLOTS": 104},
-    "b640_q128": {"PSIM_BLOCK": 640, "PSIM_QUEUE_SLOTS": 128},
-    "fuse33": {"PSIM_FUSE_LANES": 33},
-    "fuse16": {"PSIM_FUSE_LANES": 16},
-    "fuse30": {"PSIM_FUSE_LANES": 30},
-    "front0": {"PSIM_FLY_FRONT": 0},
+VARIANTS = {  # round 2, lattice cells: what the flight loop's fast path takes on besides whole-edge transitions
+    "fast00": {"PSIM_FAST_WALLS": 0, "PSIM_FAST_COMPOSITE": 0},
+    "fast01": {"PSIM_FAST_WALLS": 0, "PSIM_FAST_COMPOSITE": 1},
+    "fast10": {"PSIM_FAST_WALLS": 1, "PSIM_FAST_COMPOSITE": 0},
 }
 
 
