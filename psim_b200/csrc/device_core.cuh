@@ -561,7 +561,8 @@ PSIM_HD bool rates_differ(uint32_t cell_word_a, uint32_t cell_word_b) {
 // Everything else (diffuse walls, emitters, material interfaces, other rates, irregular partial edges, the stuck-phonon
 // guard) goes to impact_event.  Where both can handle an impact they compute the same thing with the same expressions.
 // `links`, `tail` = the two halves of the record of p.cell; `reflected`: the velocity changed.
-PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 links, const uint2 tail, bool& reflected) {
+// `track_sensor`: the caller keeps f.sensor_mat current across segments (false: it reloads it from the cell record).
+PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 links, const uint2 tail, bool& reflected, const bool track_sensor) {
     reflected = false;
     if (f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
     uint32_t link = link_of_edge(links, f.edge);
@@ -593,6 +594,15 @@ PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 l
         return false;
     }
     const uint32_t ncell = PSIM_LINK_CELL(link);
+    if (link & PSIM_LINK_SAME_FRAME) {
+        // the same shape, material and rates on the other side (the interior of every regular mesh): the rates of motion
+        // stay what they are, only the cell label and the coordinates change - nothing is loaded
+        place_on_edge(PSIM_CELL_QUAD(ncell), (link >> 28) & 3u, s_in, p);
+        p.cell = ncell;
+        if (track_sensor) { f.sensor_mat = cell_sensor_word(P, ncell); }
+        ++f.ncoll;
+        return true;
+    }
     const uint2 ntail = load_cell_tail(P.cells, PSIM_CELL_INDEX(ncell));  // (sensor / class / material word, shape)
     if (rates_differ(ntail.x, f.sensor_mat)) { return false; }
     place_on_edge(PSIM_CELL_QUAD(ncell), (link >> 28) & 3u, s_in, p);
@@ -605,7 +615,7 @@ PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 l
 }
 PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f) {
     bool reflected;
-    return fast_impact(P, p, f, load_cell_links(P.cells, PSIM_CELL_INDEX(p.cell)), load_cell_tail(P.cells, PSIM_CELL_INDEX(p.cell)), reflected);
+    return fast_impact(P, p, f, load_cell_links(P.cells, PSIM_CELL_INDEX(p.cell)), load_cell_tail(P.cells, PSIM_CELL_INDEX(p.cell)), reflected, true);
 }
 
 PSIM_HD int impact_event(const DevParams& P, Phonon& p, Flight& f, uint32_t step) {

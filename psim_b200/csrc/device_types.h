@@ -37,15 +37,18 @@
 
 // edge link word: [31:30] kind, then payload
 #define PSIM_LINK_BOUNDARY 0u    // [0] the wall is perfectly specular (specularity >= 1): a mirror reflection, no random number
-#define PSIM_LINK_TRANSITION 1u  // [29:28] neighbour edge, [27] same-direction flag, [26] neighbour is a parallelogram, [25:0] neighbour flight cell
+#define PSIM_LINK_TRANSITION 1u  // [29:28] neighbour edge, [27] same-direction flag, [26] neighbour is a parallelogram,
+                                 // [25] PSIM_LINK_SAME_FRAME, [24:0] neighbour flight cell
 #define PSIM_LINK_EMIT 2u        // [26:0] emitter index
 #define PSIM_LINK_COMPOSITE 3u   // [27] some sub-surface is a transition into a cell of the same material and rate class (worth
                                  // trying the flight loop's fast path), [26:7] first sub-surface, [6:0] number of sub-surfaces
 #define PSIM_LINK_KIND(w) ((w) >> 30)
 #define PSIM_LINK_INDEX(w) ((w)&0x07FFFFFFu)                          // emitter index
-#define PSIM_LINK_CELL(w) (((w)&0x03FFFFFFu) | (((w) >> 26 & 1u) << 31))  // tagged flight cell word of the neighbour
+#define PSIM_LINK_TARGET(w) ((w)&0x01FFFFFFu)                          // neighbour flight cell
+#define PSIM_LINK_SAME_FRAME (1u << 25)  // the neighbour has the same shape record, material and rate class as this cell
+#define PSIM_LINK_CELL(w) (PSIM_LINK_TARGET(w) | (((w) >> 26 & 1u) << 31))  // tagged flight cell word of the neighbour
 
-// A phonon's cell word: [25:0] flight cell, [31] that cell is a parallelogram (the flight needs to know before it has
+// A phonon's cell word: [24:0] flight cell, [31] that cell is a parallelogram (the flight needs to know before it has
 // loaded anything)
 #define PSIM_CELL_INDEX(c) ((c)&0x03FFFFFFu)
 #define PSIM_CELL_QUAD(c) ((c) >> 31)

@@ -26,21 +26,31 @@ bool fail(std::string& err, int code, const std::string& msg, int& rc) {
 
 
 // The hints of the flight loop's fast path (device_core.cuh: fast_impact) in the link words of an image: which walls are
-// perfectly specular, and which composite edges have a transition into a cell of the same material and rate class behind them.
-void mark_fast_links(std::vector<DevCell>& cells, const std::vector<DevShape>& shapes, const std::vector<DevSub>& subs) {
+// perfectly specular, which composite edges have a transition into a cell of the same material and rate class behind them,
+// and which transitions lead into a cell with the SAME shape record, material and rate class (PSIM_LINK_SAME_FRAME: the
+// phonon's rates of motion and relaxation rates are the same on the other side, nothing has to be loaded to go on).
+void mark_fast_links(std::vector<DevCell>& cells, const std::vector<DevShape>& shapes, std::vector<DevSub>& subs) {
     for (DevCell& c : cells) {
+        const bool classified = PSIM_CELL_CLASS(c.sensor_mat) != 255u;
+        auto same_rates = [&](uint32_t lw) { return classified && ((cells[PSIM_LINK_TARGET(lw)].sensor_mat ^ c.sensor_mat) & 0xFFFu) == 0u; };
+        auto transition = [&](uint32_t lw) {
+            const bool same_frame = same_rates(lw) && cells[PSIM_LINK_TARGET(lw)].shape == c.shape;
+            return (lw & ~PSIM_LINK_SAME_FRAME) | (same_frame ? PSIM_LINK_SAME_FRAME : 0u);
+        };
         for (uint32_t e = 0; e < 4; ++e) {
             const uint32_t w = c.link[e];
             if (PSIM_LINK_KIND(w) == PSIM_LINK_BOUNDARY) {
                 c.link[e] = (PSIM_LINK_BOUNDARY << 30) | (shapes[c.shape].spec >= 1.f ? 1u : 0u);
+            } else if (PSIM_LINK_KIND(w) == PSIM_LINK_TRANSITION) {
+                c.link[e] = transition(w);
             } else if (PSIM_LINK_KIND(w) == PSIM_LINK_COMPOSITE) {
                 const uint32_t first = (w >> 7) & 0xFFFFFu, n = w & 0x7Fu;
                 bool any = false;
                 for (uint32_t i = 0; i < n; ++i) {
-                    const uint32_t lw = subs[first + i].link;
+                    uint32_t& lw = subs[first + i].link;
                     if (PSIM_LINK_KIND(lw) != PSIM_LINK_TRANSITION) { continue; }
-                    const uint32_t sm = cells[lw & 0x03FFFFFFu].sensor_mat;
-                    any |= ((sm ^ c.sensor_mat) & 0xFFFu) == 0u && PSIM_CELL_CLASS(c.sensor_mat) != 255u;
+                    any |= same_rates(lw);
+                    lw = transition(lw);
                 }
                 c.link[e] = (w & ~(1u << 27)) | (any ? (1u << 27) : 0u);
             }
@@ -70,11 +80,11 @@ void build_lattices(HostImage& img, const std::vector<Frame>& frames) {
         const DevCell& A = img.cells[c];
         const uint32_t w = A.link[e_out];
         if (PSIM_LINK_KIND(w) != PSIM_LINK_TRANSITION || ((w >> 28) & 3u) != e_in || (w & (1u << 27)) || !((w >> 26) & 1u)) { return -1; }
-        const uint32_t t = w & 0x03FFFFFFu;
+        const uint32_t t = PSIM_LINK_TARGET(w);
         if (t == c || t >= F || !quad[t]) { return -1; }
         const DevCell& B = img.cells[t];
         const uint32_t back = B.link[e_in];
-        if (PSIM_LINK_KIND(back) != PSIM_LINK_TRANSITION || (back & 0x03FFFFFFu) != c || ((back >> 28) & 3u) != e_out || (back & (1u << 27))) { return -1; }
+        if (PSIM_LINK_KIND(back) != PSIM_LINK_TRANSITION || PSIM_LINK_TARGET(back) != c || ((back >> 28) & 3u) != e_out || (back & (1u << 27))) { return -1; }
         if (B.shape != A.shape || ((B.sensor_mat ^ A.sensor_mat) & 0xFFFu) != 0u || PSIM_CELL_CLASS(A.sensor_mat) == 255u) { return -1; }
         const Frame &fa = frames[c], &fb = frames[t];
         const double dx = along_u ? fa.ux : fa.vx, dy = along_u ? fa.uy : fa.vy;
@@ -211,7 +221,7 @@ void build_lattices(HostImage& img, const std::vector<Frame>& frames) {
                     ds.s0 = static_cast<float>((k + s0) / n);
                     ds.s1 = static_cast<float>((k + s1) / n);
                     if (PSIM_LINK_KIND(lw) == PSIM_LINK_TRANSITION) {
-                        const uint32_t t = lw & 0x03FFFFFFu, te = (lw >> 28) & 3u;
+                        const uint32_t t = PSIM_LINK_TARGET(lw), te = (lw >> 28) & 3u;
                         uint32_t kT = 0, nT = 1;
                         if (t >= F || !edge_slot(t, te, kT, nT)) {
                             ok = false;
@@ -220,7 +230,7 @@ void build_lattices(HostImage& img, const std::vector<Frame>& frames) {
                         ds.a = static_cast<float>(af * n / nT);
                         ds.b = static_cast<float>((kT + bf - af * k) / nT);
                         const uint32_t cw = word_of(static_cast<uint32_t>(block_of[t]));
-                        ds.link = (PSIM_LINK_TRANSITION << 30) | (te << 28) | (af > 0. ? (1u << 27) : 0u) | ((cw >> 31) << 26) | (cw & 0x03FFFFFFu);
+                        ds.link = (PSIM_LINK_TRANSITION << 30) | (te << 28) | (af > 0. ? (1u << 27) : 0u) | ((cw >> 31) << 26) | (cw & 0x01FFFFFFu);
                     } else {
                         ds.link = lw;  // an emitting surface keeps its index
                     }
@@ -457,8 +467,8 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
 
     // ---- cells.  Pass 1: every model-file triangle with its links in MODEL terms (target = model cell, model edge)
     const uint32_t C = d.num_cells;
-    if (C >= (1u << 26)) {
-        fail(err, PSIM_E_INVALID, "model exceeds packed-index limits (2^26 cells)", rc);
+    if (C >= (1u << 25)) {
+        fail(err, PSIM_E_INVALID, "model exceeds packed-index limits (2^25 cells)", rc);
         return rc;
     }
     struct Tri {
@@ -552,10 +562,10 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
             for (uint32_t k = 0; k < 3 && partner[A] < 0; ++k) {
                 const uint32_t w = tri[A].link[k];
                 if (PSIM_LINK_KIND(w) != PSIM_LINK_TRANSITION) { continue; }
-                const uint32_t B = w & 0x03FFFFFFu, j = (w >> 28) & 3u;
+                const uint32_t B = PSIM_LINK_TARGET(w), j = (w >> 28) & 3u;
                 if (B == A || partner[B] >= 0 || d.cells[A].sensor != d.cells[B].sensor || tri[A].spec != tri[B].spec) { continue; }
                 const uint32_t back = tri[B].link[j];
-                if (PSIM_LINK_KIND(back) != PSIM_LINK_TRANSITION || (back & 0x03FFFFFFu) != A || ((back >> 28) & 3u) != k ||
+                if (PSIM_LINK_KIND(back) != PSIM_LINK_TRANSITION || PSIM_LINK_TARGET(back) != A || ((back >> 28) & 3u) != k ||
                     ((back ^ w) & (1u << 27))) {
                     continue;
                 }
@@ -683,12 +693,12 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
     // coordinate: s -> 1 - s on the owner's side, t -> 1 - t on the side of whoever points at it.
     auto relabel = [&](uint32_t w, bool own_flipped) -> uint32_t {
         if (PSIM_LINK_KIND(w) != PSIM_LINK_TRANSITION) { return w; }
-        const uint32_t t = w & 0x03FFFFFFu, e = (w >> 28) & 3u;
+        const uint32_t t = PSIM_LINK_TARGET(w), e = (w >> 28) & 3u;
         const uint32_t cw = cell_word[t];
         const int fe = edge_map[t][e];  // >= 0: nothing but the shared edge of a pair vanishes, and nothing else points at it
         const bool same_dir = (((w >> 27) & 1u) != 0u) != (own_flipped != (edge_flip[t][e] != 0));
         return (PSIM_LINK_TRANSITION << 30) | (static_cast<uint32_t>(fe < 0 ? 0 : fe) << 28) | (same_dir ? (1u << 27) : 0u) | ((cw >> 31) << 26) |
-               (cw & 0x03FFFFFFu);
+               (cw & 0x01FFFFFFu);
     };
     for (size_t ic = 0; ic < out.cells.size(); ++ic) {
         const Pending& pe = pending[ic];
@@ -707,7 +717,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
                         sb.b = sb.a + sb.b;
                         sb.a = -sb.a;
                     }
-                    if (PSIM_LINK_KIND(sb.link) == PSIM_LINK_TRANSITION && edge_flip[sb.link & 0x03FFFFFFu][(sb.link >> 28) & 3u]) {
+                    if (PSIM_LINK_KIND(sb.link) == PSIM_LINK_TRANSITION && edge_flip[PSIM_LINK_TARGET(sb.link)][(sb.link >> 28) & 3u]) {
                         sb.a = -sb.a;  // t' = 1 - t
                         sb.b = 1.f - sb.b;
                     }
