@@ -14,10 +14,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = {  # round 2, lattice cells: what the flight loop's fast path takes on besides whole-edge transitions
+VARIANTS = {  # round 2, lattice cells: what the flight loop's fast path takes on besides whole-edge transitions; the pass-fusion threshold
     "fast00": {"PSIM_FAST_WALLS": 0, "PSIM_FAST_COMPOSITE": 0},
-    "fast01": {"PSIM_FAST_WALLS": 0, "PSIM_FAST_COMPOSITE": 1},
-    "fast10": {"PSIM_FAST_WALLS": 1, "PSIM_FAST_COMPOSITE": 0},
+    "fast11": {"PSIM_FAST_WALLS": 1, "PSIM_FAST_COMPOSITE": 1},
+    "fuse16": {"PSIM_FUSE_LANES": 16},
+    "fuse28": {"PSIM_FUSE_LANES": 28},
+    "fuse33": {"PSIM_FUSE_LANES": 33},
 }
 
 

@@ -22,6 +22,13 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:drif
     python tools/profile_model.py sides_per > $out/ncu_per.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 2 -c 1 -f -o $out/prof_kinked \
     python tools/profile_model.py kinked > $out/ncu_kinked.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:drift_kernel -s 6 -c 1 -f -o $out/prof_kinked_rec \
+    python tools/profile_model.py kinked > $out/ncu_kinked_rec.log 2>&1
+# per-launch times and instructions of every shipped model (which windows the time goes to)
+for m in sige kinked sides_ss sides_per linear; do
+  timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:drift_kernel --csv \
+      --log-file $out/${tag}_launches_$m.csv python tools/profile_model.py $m > $out/launches_$m.log 2>&1
+done
 timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python bench.py --phonons 200000 --steps 1 --warmup 0 --no-cpu-baseline --no-models \
     > $out/${tag}_memcheck.log 2>&1
 tail -3 $out/${tag}_memcheck.log

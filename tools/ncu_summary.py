@@ -16,10 +16,11 @@ PROFILES = os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 CAPTURES = {
-    "long": ("queues_long_window", "bench workload (Si/Ge, 1e8 phonons), 899-step window: first launch of a job, nothing is recorded before step 900"),
+    "long": ("queues_long_window", "bench workload (Si/Ge, 1e8 phonons), 899-step window over the lattice image: first launch of a job, nothing is recorded before step 900"),
     "rec": ("queues_recorded_window", "bench workload, 36-step recorded window (tallies staged in shared memory, difference form)"),
     "per": ("queues_periodic_global", "linear_sides periodic, 1000 sensors: 128-step recorded window, tallies posted to global memory sector by sector"),
-    "kinked": ("queues_kinked_long_window", "kinked wire (6174 cells -> 3150 flight cells), 1023-step window"),
+    "kinked": ("queues_kinked_long_window", "kinked wire (6174 cells -> 3150 flight cells -> 250 lattice cells), 1023-step unrecorded window over the lattice image"),
+    "kinked_rec": ("queues_kinked_recorded_window", "kinked wire, 128-step recorded window over the fine flight cells (3108 sensors: tallies posted to global memory)"),
 }
 KEEP = {
     "gpu__time_duration.sum": "launch_ms_under_ncu",
@@ -148,7 +149,7 @@ def main():
     with open(os.path.join(PROFILES, f"{tag}_ncu_summary.json"), "w") as f:
         json.dump(out, f, indent=1)
     sass_histogram("long", os.path.join(PROFILES, f"{tag}_sass_histogram.txt"))
-    for extra in (f"{tag}_launches.csv", f"{tag}_memcheck.log"):
+    for extra in (f"{tag}_launches.csv", f"{tag}_memcheck.log", *[f"{tag}_launches_{m}.csv" for m in ("sige", "kinked", "sides_ss", "sides_per", "linear")]):
         src = os.path.join(EV, extra)
         if os.path.exists(src):
             open(os.path.join(PROFILES, extra), "w").write(open(src).read())
