@@ -205,6 +205,12 @@ int psim_gpu_reset(psim_gpu* h);
 void psim_gpu_destroy(psim_gpu* h);
 const char* psim_gpu_last_error(const psim_gpu* h); /* h may be NULL: error of the last failed create */
 
+/* Device memory of destroyed handles (phonon pools, tally buffers) is kept for the next handle of the process - a model is
+ * usually run more than once, and cudaMalloc / cudaFree of a multi-GB pool cost more than the kernels of most models
+ * (environment PSIM_DEVICE_CACHE_MB: how much is kept per process, default 16384, 0 = nothing).  This returns all of it to
+ * the driver.  No counterpart in the reference (it has no device). */
+void psim_gpu_release_cached(void);
+
 /* Per-function probes used by the parity tests: run the device implementation of one reference function
  * on caller-supplied inputs.  out_bin/out_ta: Material::freqIndex (material.cpp:64-75) for uniforms u1,u2 as
  * the flight loop computes it (guided search); out_bin_bisect: the reference's plain bisection on the same

@@ -20,6 +20,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -28,6 +32,120 @@
 namespace {
 
 thread_local std::string g_create_error;
+
+// -------------------------------------------------------------------------------------------------------------
+// Device memory of the library goes through a small caching allocator.  cudaMalloc / cudaFree of the phonon pool (7 GB for the
+// 1e8-phonon job) and of the tally staging cost 25 - 100 ms each on these boxes - more than the kernels of most shipped
+// models - and a model is typically run several times by one process (the runs of a multi-run model, the iterations of a
+// re-iterated one, one model after another): a freed block is kept (per device, up to PSIM_DEVICE_CACHE_MB, default 16384;
+// 0 disables) and handed to the next request it fits.  Blocks return to the driver when the cache is full, when an
+// allocation fails, or on psim_gpu_release_cached().  Every caller frees after the work that used the block has completed
+// (synchronous copies, cudaDeviceSynchronize in destroy), so a block is never handed on while it is in use.
+namespace devmem {
+
+struct Block {
+    void* p;
+    size_t bytes;
+    int device;
+};
+std::mutex mu;
+std::vector<Block> cached;
+std::unordered_map<void*, Block> live;
+size_t cached_bytes = 0;
+
+size_t cache_cap() {
+    static const size_t cap = [] {
+        const char* e = std::getenv("PSIM_DEVICE_CACHE_MB");
+        const double mb = e ? std::atof(e) : 16384.;
+        return mb > 0. ? static_cast<size_t>(mb * 1048576.) : size_t{ 0 };
+    }();
+    return cap;
+}
+
+void release_locked(int device /* < 0: every device */) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (size_t i = 0; i < cached.size();) {
+        if (device < 0 || cached[i].device == device) {
+            cudaSetDevice(cached[i].device);
+            cudaFree(cached[i].p);
+            cached_bytes -= cached[i].bytes;
+            cached[i] = cached.back();
+            cached.pop_back();
+        } else {
+            ++i;
+        }
+    }
+    cudaSetDevice(cur);
+}
+
+cudaError_t alloc(void** out, size_t bytes) {
+    const size_t need = (std::max<size_t>(bytes, 1) + 511) & ~static_cast<size_t>(511);
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lock(mu);
+    size_t best = cached.size();
+    for (size_t i = 0; i < cached.size(); ++i) {  // the smallest cached block of this device that fits without wasting half of it
+        const Block& b = cached[i];
+        if (b.device == device && b.bytes >= need && b.bytes <= 2 * need + (1u << 20) && (best == cached.size() || b.bytes < cached[best].bytes)) { best = i; }
+    }
+    if (best < cached.size()) {
+        const Block b = cached[best];
+        cached[best] = cached.back();
+        cached.pop_back();
+        cached_bytes -= b.bytes;
+        live[b.p] = b;
+        *out = b.p;
+        return cudaSuccess;
+    }
+    void* p = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaError_t e = cudaMalloc(&p, need);
+    if (std::getenv("PSIM_TIMING")) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.) { std::fprintf(stderr, "psim timing [ms]: cudaMalloc of %zu bytes took %.1f\n", need, ms); }
+    }
+    if (e != cudaSuccess) {  // give the cache back to the driver and try once more
+        cudaGetLastError();
+        release_locked(device);
+        e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) { return e; }
+    }
+    live[p] = Block{ p, need, device };
+    *out = p;
+    return cudaSuccess;
+}
+
+template<typename T> cudaError_t alloc(T** out, size_t bytes) {
+    void* p = nullptr;
+    const cudaError_t e = alloc(&p, bytes);
+    *out = static_cast<T*>(p);
+    return e;
+}
+
+void free(void* p) {
+    if (!p) { return; }
+    std::lock_guard<std::mutex> lock(mu);
+    const auto it = live.find(p);
+    if (it == live.end()) {  // not ours (never happens): straight to the driver
+        cudaFree(p);
+        return;
+    }
+    const Block b = it->second;
+    live.erase(it);
+    if (cached_bytes + b.bytes <= cache_cap()) {
+        cached.push_back(b);
+        cached_bytes += b.bytes;
+    } else {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(b.device);
+        cudaFree(b.p);
+        cudaSetDevice(cur);
+    }
+}
+
+}  // namespace devmem
 
 }  // namespace
 
@@ -118,8 +236,8 @@ struct DeviceBuffer {
     DeviceBuffer() = default;
     DeviceBuffer(const DeviceBuffer&) = delete;
     DeviceBuffer& operator=(const DeviceBuffer&) = delete;
-    ~DeviceBuffer() { cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DeviceBuffer() { devmem::free(p); }
+    cudaError_t alloc(size_t bytes) { return devmem::alloc(&p, bytes ? bytes : 1); }
     template<typename T> T* as() const { return static_cast<T*>(p); }
     void* release() {
         void* q = p;
@@ -137,9 +255,9 @@ template<typename T> int upload(psim_gpu* h, void** dst, const std::vector<T>& v
 }
 
 void free_plan(psim_gpu* h) {
-    cudaFree(h->d_births);
-    cudaFree(h->d_prefix);
-    cudaFree(h->d_sources);
+    devmem::free(h->d_births);
+    devmem::free(h->d_prefix);
+    devmem::free(h->d_sources);
     h->d_births = nullptr;
     h->d_prefix = nullptr;
     h->d_sources = nullptr;
@@ -147,14 +265,14 @@ void free_plan(psim_gpu* h) {
 
 void free_pool(psim_gpu* h) {
     for (int i = 0; i < 2; ++i) {
-        cudaFree(h->pool_a[i]);
-        cudaFree(h->pool_b[i]);
-        cudaFree(h->cnt[i]);
+        devmem::free(h->pool_a[i]);
+        devmem::free(h->pool_b[i]);
+        devmem::free(h->cnt[i]);
         h->pool_a[i] = nullptr;
         h->pool_b[i] = nullptr;
         h->cnt[i] = nullptr;
     }
-    cudaFree(h->d_alive_hist);
+    devmem::free(h->d_alive_hist);
     h->d_alive_hist = nullptr;
     h->seg_cap = 0;
     h->n_warps = 0;
@@ -242,7 +360,7 @@ void plan_launch(const psim_gpu* h, uint32_t s0, uint32_t step_end, uint32_t& s1
 // either form of the model (merged: h->img, one flight cell per triangle: h->img_tri).
 int upload_geometry(psim_gpu* h, const psim::HostImage& g) {
     for (void** p : { &h->d_cells, &h->d_shapes, &h->d_api_cells, &h->d_subs, &h->d_emitters }) {
-        cudaFree(*p);
+        devmem::free(*p);
         *p = nullptr;
     }
     if (int rc = upload(h, &h->d_cells, g.cells)) { return rc; }
@@ -265,7 +383,7 @@ int upload_lattice(psim_gpu* h) {
     h->have_lattice = false;
     if (h->img.lattice_cells.empty()) { return 0; }
     for (void** p : { &h->d_lat_cells, &h->d_lat_shapes, &h->d_lat_api_cells, &h->d_lat_subs, &h->d_lat_emitters, &h->d_lat_sub_fine }) {
-        cudaFree(*p);
+        devmem::free(*p);
         *p = nullptr;
     }
     if (int rc = upload(h, &h->d_lat_cells, h->img.lattice_cells)) { return rc; }
@@ -304,7 +422,7 @@ int zero_run_state(psim_gpu* h) {
     // per-CTA staging of a useful window would not fit and global atomics are spread thinly enough
     h->diff_mode = h->opt_tally_shared == 0 || (h->opt_tally_shared < 0 && P.n_sensors >= kManySensors);
     if (h->diff_mode) {
-        if (!h->tally_acc) { PSIM_CUDA(cudaMalloc(&h->tally_acc, n * 4 * sizeof(long long))); }
+        if (!h->tally_acc) { PSIM_CUDA(devmem::alloc(&h->tally_acc, n * 4 * sizeof(long long))); }
         PSIM_CUDA(cudaMemsetAsync(h->tally_acc, 0, n * 4 * sizeof(long long), h->stream));
     }
     PSIM_CUDA(cudaMemsetAsync(h->d_stats, 0, kStatWords * sizeof(unsigned long long), h->stream));
@@ -414,12 +532,12 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         h->P.velocities = static_cast<const float*>(h->d_velocities);
         h->P.guides = static_cast<const uint32_t*>(h->d_guides);
         const size_t n = static_cast<size_t>(h->P.recorded_steps) * h->P.n_sensors;
-        PSIM_CUDA(cudaMalloc(&h->tally_e, n * sizeof(int32_t)));
-        PSIM_CUDA(cudaMalloc(&h->tally_f, n * 2 * sizeof(long long)));
-        PSIM_CUDA(cudaMalloc(&h->carry_e, std::max<size_t>(h->P.n_sensors, 1) * sizeof(int32_t)));
-        PSIM_CUDA(cudaMalloc(&h->carry_f, std::max<size_t>(h->P.n_sensors, 1) * 2 * sizeof(long long)));
-        PSIM_CUDA(cudaMalloc(&h->d_stats, kStatWords * sizeof(unsigned long long)));
-        PSIM_CUDA(cudaMalloc(&h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
+        PSIM_CUDA(devmem::alloc(&h->tally_e, n * sizeof(int32_t)));
+        PSIM_CUDA(devmem::alloc(&h->tally_f, n * 2 * sizeof(long long)));
+        PSIM_CUDA(devmem::alloc(&h->carry_e, std::max<size_t>(h->P.n_sensors, 1) * sizeof(int32_t)));
+        PSIM_CUDA(devmem::alloc(&h->carry_f, std::max<size_t>(h->P.n_sensors, 1) * 2 * sizeof(long long)));
+        PSIM_CUDA(devmem::alloc(&h->d_stats, kStatWords * sizeof(unsigned long long)));
+        PSIM_CUDA(devmem::alloc(&h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
         PSIM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         PSIM_CUDA(cudaEventCreate(&h->ev_begin));
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
@@ -497,11 +615,11 @@ int psim_gpu_set_sources(psim_gpu* h, const psim_source* sources, size_t n, uint
         free_pool(h);
         const size_t slots = static_cast<size_t>(seg_cap) * n_warps;
         for (int i = 0; i < 2; ++i) {
-            PSIM_CUDA(cudaMalloc(&h->pool_a[i], slots * sizeof(float4)));
-            PSIM_CUDA(cudaMalloc(&h->pool_b[i], slots * sizeof(uint4)));
-            PSIM_CUDA(cudaMalloc(&h->cnt[i], n_warps * sizeof(uint32_t)));
+            PSIM_CUDA(devmem::alloc(&h->pool_a[i], slots * sizeof(float4)));
+            PSIM_CUDA(devmem::alloc(&h->pool_b[i], slots * sizeof(uint4)));
+            PSIM_CUDA(devmem::alloc(&h->cnt[i], n_warps * sizeof(uint32_t)));
         }
-        PSIM_CUDA(cudaMalloc(&h->d_alive_hist, static_cast<size_t>(h->P.num_steps + 1) * sizeof(unsigned long long)));
+        PSIM_CUDA(devmem::alloc(&h->d_alive_hist, static_cast<size_t>(h->P.num_steps + 1) * sizeof(unsigned long long)));
         h->seg_cap = seg_cap;
         h->n_warps = n_warps;
     }
@@ -823,30 +941,35 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaDeviceSynchronize();
     free_pool(h);
     free_plan(h);
-    for (void* p : { h->d_lat_cells, h->d_lat_api_cells, h->d_lat_shapes, h->d_lat_subs, h->d_lat_emitters, h->d_lat_sub_fine }) { cudaFree(p); }
-    cudaFree(h->d_cells);
-    cudaFree(h->d_api_cells);
-    cudaFree(h->d_shapes);
-    cudaFree(h->d_classes);
-    cudaFree(h->d_step_sensors);
-    cudaFree(h->d_subs);
-    cudaFree(h->d_sensors);
-    cudaFree(h->d_materials);
-    cudaFree(h->d_emitters);
-    cudaFree(h->d_tables);
-    cudaFree(h->d_velocities);
-    cudaFree(h->d_guides);
-    cudaFree(h->tally_e);
-    cudaFree(h->tally_f);
-    cudaFree(h->tally_acc);
-    cudaFree(h->carry_e);
-    cudaFree(h->carry_f);
-    cudaFree(h->d_stats);
-    cudaFree(h->d_hist);
+    for (void* p : { h->d_lat_cells, h->d_lat_api_cells, h->d_lat_shapes, h->d_lat_subs, h->d_lat_emitters, h->d_lat_sub_fine }) { devmem::free(p); }
+    devmem::free(h->d_cells);
+    devmem::free(h->d_api_cells);
+    devmem::free(h->d_shapes);
+    devmem::free(h->d_classes);
+    devmem::free(h->d_step_sensors);
+    devmem::free(h->d_subs);
+    devmem::free(h->d_sensors);
+    devmem::free(h->d_materials);
+    devmem::free(h->d_emitters);
+    devmem::free(h->d_tables);
+    devmem::free(h->d_velocities);
+    devmem::free(h->d_guides);
+    devmem::free(h->tally_e);
+    devmem::free(h->tally_f);
+    devmem::free(h->tally_acc);
+    devmem::free(h->carry_e);
+    devmem::free(h->carry_f);
+    devmem::free(h->d_stats);
+    devmem::free(h->d_hist);
     if (h->ev_begin) { cudaEventDestroy(h->ev_begin); }
     if (h->ev_end) { cudaEventDestroy(h->ev_end); }
     if (h->stream) { cudaStreamDestroy(h->stream); }
     delete h;
+}
+
+void psim_gpu_release_cached(void) {
+    std::lock_guard<std::mutex> lock(devmem::mu);
+    devmem::release_locked(-1);
 }
 
 const char* psim_gpu_last_error(const psim_gpu* h) { return h ? h->err.c_str() : g_create_error.c_str(); }

@@ -112,6 +112,7 @@ SYMBOLS = {
     "psim_gpu_reset": (C.c_int, [_P]),
     "psim_gpu_destroy": (None, [_P]),
     "psim_gpu_last_error": (C.c_char_p, [_P]),
+    "psim_gpu_release_cached": (None, []),
     "psim_gpu_probe_sample": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P, _P, _P]),
     "psim_gpu_probe_rates": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P]),
     "psim_gpu_probe_flight": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
