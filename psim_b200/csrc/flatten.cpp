@@ -862,15 +862,18 @@ int plan_births(const HostImage& img, const psim_source* sources, size_t n, uint
         err = "more than 2^40 phonons";
         return PSIM_E_INVALID;
     }
-    std::stable_sort(births.begin(), births.end(), [](const DevBirth& a, const DevBirth& b) { return a.step < b.step; });
-    out.births = births;
-    out.prefix.assign(births.size() + 1, 0);
+    // by step, sources in their order within a step: a counting sort (the groups arrive source by source, each source's in
+    // step order; a comparison sort of the 2e5 groups of the kinked wire - 42 surfaces x 5000 steps - took 10 ms)
     out.step_begin.assign(M + 1, 0);
-    for (size_t i = 0; i < births.size(); ++i) {
-        out.prefix[i + 1] = out.prefix[i] + births[i].count;
-        out.step_begin[births[i].step + 1] = static_cast<uint32_t>(i + 1);
+    for (const DevBirth& b : births) { ++out.step_begin[b.step + 1]; }
+    for (uint32_t k = 1; k <= M; ++k) { out.step_begin[k] += out.step_begin[k - 1]; }
+    out.births.resize(births.size());
+    {
+        std::vector<uint32_t> next(out.step_begin.begin(), out.step_begin.end() - 1);
+        for (const DevBirth& b : births) { out.births[next[b.step]++] = b; }
     }
-    for (uint32_t k = 1; k <= M; ++k) { out.step_begin[k] = std::max(out.step_begin[k], out.step_begin[k - 1]); }
+    out.prefix.assign(births.size() + 1, 0);
+    for (size_t i = 0; i < out.births.size(); ++i) { out.prefix[i + 1] = out.prefix[i] + out.births[i].count; }
     if (out.sources.empty()) { out.sources.push_back(DevSource{}); }
     return 0;
 }

@@ -418,8 +418,13 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                           << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count() << '\n';
             }
             const size_t n_tally = m.sensors.size() * m.recorded_steps;
-            std::vector<std::vector<int32_t>> energy(G, std::vector<int32_t>(n_tally));
-            std::vector<std::vector<int64_t>> fixed(G, std::vector<int64_t>(2 * n_tally));
+            // One device, or several whose tallies NCCL sums on device 0: energies and fluxes come back from the device as
+            // the host layer wants them (psim_gpu_get_tallies transposes and converts there).  Only the host-side sum of
+            // several devices needs the exact fixed-point integers of each.
+            const bool host_sum = G > 1 && !use_nccl;
+            std::vector<std::vector<int32_t>> energy(host_sum ? G : 1, std::vector<int32_t>(n_tally));
+            std::vector<std::vector<int64_t>> fixed(host_sum ? G : 0, std::vector<int64_t>(host_sum ? 2 * n_tally : 0));
+            std::vector<double> flux(2 * n_tally);
             std::vector<psim_stats> st(G);
             std::vector<int> codes(G, PSIM_OK);
             std::vector<std::string> errors(G);
@@ -442,7 +447,8 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                 const auto t2 = now();
                 if (!e) { e = psim_gpu_run(gpus[d]); }
                 const auto t3 = now();
-                if (!e && !use_nccl) { e = psim_gpu_get_tallies(gpus[d], energy[d].data(), nullptr, fixed[d].data()); }
+                if (!e && host_sum) { e = psim_gpu_get_tallies(gpus[d], energy[d].data(), nullptr, fixed[d].data()); }
+                if (!e && G == 1) { e = psim_gpu_get_tallies(gpus[0], energy[0].data(), flux.data(), nullptr); }
                 if (!e) { e = psim_gpu_get_stats(gpus[d], &st[d]); }
                 if (timing && d == 0) {
                     std::cerr << "psim timing [ms]: create " << ms(t0, t1) << " set_sources " << ms(t1, t2) << " run " << ms(t2, t3)
@@ -464,27 +470,24 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     return codes[d];
                 }
             }
-            size_t summands = G;
             if (use_nccl) {
                 const auto t4 = std::chrono::steady_clock::now();
                 if (const std::string err = exchange->all_reduce(gpus); !err.empty()) {
                     g_error = err;
                     return PSIM_E_CUDA;
                 }
-                if (const int e = psim_gpu_get_tallies(gpus[0], energy[0].data(), nullptr, fixed[0].data())) {
+                if (const int e = psim_gpu_get_tallies(gpus[0], energy[0].data(), flux.data(), nullptr)) {  // device 0 holds the sum
                     g_error = psim_gpu_last_error(gpus[0]);
                     return e;
                 }
-                summands = 1;  // device 0 holds the sum
                 if (std::getenv("PSIM_TIMING")) {
                     std::cerr << "psim timing [ms]: nccl all-reduce + tallies "
                               << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t4).count() << '\n';
                 }
             }
-            std::vector<double> flux(2 * n_tally);
-            for (size_t i = 0; i < n_tally; ++i) {  // integer sums: independent of the number of devices
+            for (size_t i = 0; host_sum && i < n_tally; ++i) {  // integer sums: independent of the number of devices
                 int64_t e = 0, fx = 0, fy = 0;
-                for (size_t d = 0; d < summands; ++d) {
+                for (size_t d = 0; d < G; ++d) {
                     e += energy[d][i];
                     fx += fixed[d][2 * i];
                     fy += fixed[d][2 * i + 1];

@@ -602,13 +602,12 @@ std::vector<psim_source> Model::source_counts(uint64_t seed) {
 void Model::set_tallies(const int32_t* energy, const double* flux) {
     const size_t S = sensors.size(), R = recorded_steps;
     iteration_ended_ = false;
-    inc_energy_.assign(S, std::vector<int32_t>(R, 0));
-    inc_flux_.assign(S, std::vector<std::array<double, 2>>(R, { 0., 0. }));
+    inc_energy_.resize(S);
+    inc_flux_.resize(S);
     for (size_t s = 0; s < S; ++s) {
-        for (size_t r = 0; r < R; ++r) {
-            inc_energy_[s][r] = energy[s * R + r];
-            inc_flux_[s][r] = { flux[2 * (s * R + r)], flux[2 * (s * R + r) + 1] };
-        }
+        inc_energy_[s].assign(energy + s * R, energy + (s + 1) * R);
+        inc_flux_[s].resize(R);
+        for (size_t r = 0; r < R; ++r) { inc_flux_[s][r] = { flux[2 * (s * R + r)], flux[2 * (s * R + r) + 1] }; }
     }
 }
 
