@@ -14,11 +14,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = {  # round 2, lattice cells: what the flight loop's fast path takes on besides whole-edge transitions; the pass-fusion threshold
+VARIANTS = {  # round 2: more resident warps with fewer registers; what the flight loop's fast path takes on; the pass-fusion threshold
+    "b1024_q96": {"PSIM_BLOCK": 1024, "PSIM_QUEUE_SLOTS": 96},
+    "b896_q104": {"PSIM_BLOCK": 896, "PSIM_QUEUE_SLOTS": 104},
+    "b896_q96": {"PSIM_BLOCK": 896, "PSIM_QUEUE_SLOTS": 96},
     "fast00": {"PSIM_FAST_WALLS": 0, "PSIM_FAST_COMPOSITE": 0},
     "fast11": {"PSIM_FAST_WALLS": 1, "PSIM_FAST_COMPOSITE": 1},
     "fuse16": {"PSIM_FUSE_LANES": 16},
-    "fuse28": {"PSIM_FUSE_LANES": 28},
     "fuse33": {"PSIM_FUSE_LANES": 33},
 }
 
