@@ -85,9 +85,13 @@ cudaError_t alloc(void** out, size_t bytes) {
     cudaGetDevice(&device);
     std::lock_guard<std::mutex> lock(mu);
     size_t best = cached.size();
-    for (size_t i = 0; i < cached.size(); ++i) {  // the smallest cached block of this device that fits without wasting half of it
+    // The smallest cached block of this device that fits.  A small request never takes a block more than twice its size (it
+    // would leave the next pool without one); a large one (pools, tally buffers: >= 1 MB) takes whatever is there - on these
+    // boxes a single cudaMalloc stalls for 25 - 100 ms every so often, whatever its size, and HBM is not what a run is short of.
+    const size_t limit = need >= (1u << 20) ? ~size_t{ 0 } : 2 * need + (1u << 20);
+    for (size_t i = 0; i < cached.size(); ++i) {
         const Block& b = cached[i];
-        if (b.device == device && b.bytes >= need && b.bytes <= 2 * need + (1u << 20) && (best == cached.size() || b.bytes < cached[best].bytes)) { best = i; }
+        if (b.device == device && b.bytes >= need && b.bytes <= limit && (best == cached.size() || b.bytes < cached[best].bytes)) { best = i; }
     }
     if (best < cached.size()) {
         const Block b = cached[best];

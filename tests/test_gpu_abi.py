@@ -8,6 +8,7 @@ import pytest
 
 from psim_b200 import configs, lib as psim
 from tests import common as T
+from tests.gpu_runner import gpu_run_case
 
 pytestmark = pytest.mark.gpu
 
@@ -255,3 +256,23 @@ def test_phonon_ids_beyond_32_bits():
         assert np.abs(z).max() < 5.0 and np.sqrt((z * z).mean()) < 2.5, z
     finally:
         g.close()
+
+
+@pytest.mark.gpu
+def test_cached_device_memory_is_reused_and_can_be_released():
+    """psim_gpu_release_cached (include/psim_b200.h): the device memory of a destroyed handle serves the next handle of the
+    process; releasing it in between must change nothing but where the memory comes from - the same run, bit for bit."""
+    model = T.load_model(T.case_model("sides_per"), num_phonons=40_000)
+    a = gpu_run_case(model, 21, finish=False)
+    b = gpu_run_case(model, 21, finish=False)          # pool, tallies, image: all from the cache
+    psim.load_library().psim_gpu_release_cached()
+    c = gpu_run_case(model, 21, finish=False)          # everything from the driver again
+    psim.load_library().psim_gpu_release_cached()
+    psim.load_library().psim_gpu_release_cached()      # releasing an empty cache is a no-op
+    for other in (b, c):
+        assert np.array_equal(a["energy"], other["energy"]) and np.array_equal(a["fixed"], other["fixed"])
+        assert a["stats"][0]["drift_steps"] == other["stats"][0]["drift_steps"]
+    big = T.load_model(T.case_model("sige"), num_phonons=400_000)   # a larger pool after smaller ones, then a smaller one again
+    d = gpu_run_case(big, 5, finish=False)
+    e = gpu_run_case(model, 21, finish=False)
+    assert np.array_equal(a["energy"], e["energy"]) and np.abs(d["energy"]).sum() > 0
