@@ -232,7 +232,7 @@ struct Phonon {
 // called from SensorController::initialUpdate / scatterUpdate, sensorController.cpp:28-36,52-55).
 // Same inverse-CDF bisection as the reference, hence the same quirk: it returns `high`, i.e. bin 0 is never
 // produced.  bisect_table is the reference's loop verbatim in structure; sample_bin brackets the answer with a
-// 256-entry guide first (flatten.cpp builds it with bisect_table), then bisects inside the bracket: for a
+// PSIM_GUIDE-entry guide first (flatten.cpp builds it with bisect_table), then bisects inside the bracket: for a
 // non-decreasing table both return the unique h with cdf[h-1] <= r < cdf[h], so the results are identical.
 // ---------------------------------------------------------------------------------------------------------
 PSIM_HD uint32_t bisect_range(const float2* table, float r, uint32_t lo, uint32_t hi) {

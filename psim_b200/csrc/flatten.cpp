@@ -338,7 +338,7 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
             out.tables[static_cast<size_t>(t) * PSIM_BINS + i] = e;
         }
     }
-    // guide: for r in [k/256, (k+1)/256) the inverse-CDF answer lies in (low, high]; both ends come from the
+    // guide: for r in [k/G, (k+1)/G), G = PSIM_GUIDE, the inverse-CDF answer lies in (low, high]; both ends come from the
     // reference's own bisection (material.cpp:64-75) evaluated on the fp32 table at the bracket's end points
     out.guides.resize(static_cast<size_t>(d.num_tables) * PSIM_GUIDE);
     for (uint32_t t = 0; t < d.num_tables; ++t) {

@@ -579,9 +579,6 @@ __host__ __device__ constexpr uint32_t ring_capacity(int slots) {
     while (c < static_cast<uint32_t>(slots)) { c <<= 1; }
     return c;
 }
-#ifndef PSIM_FLY_FRONT
-#define PSIM_FLY_FRONT 0
-#endif
 
 // Slot storage of the work-queue kernel: three 16-byte groups per slot, [group][slot], so that a pass moves a slot with two
 // or three LDS.128 / STS.128 (the first layout, [field][slot] words, took 7-12 scalar accesses per slot and pass: 13 % of
@@ -958,16 +955,7 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
         const unsigned m_wall = __ballot_sync(0xFFFFFFFFu, d_wall), m_fin = __ballot_sync(0xFFFFFFFFu, d_fin);
         const unsigned m_free = __ballot_sync(0xFFFFFFFFu, d_free);
         const uint32_t n_fly = __popc(m_fly), n_sct = __popc(m_sct), n_wall = __popc(m_wall), n_fin = __popc(m_fin), n_free = __popc(m_free);
-#if PSIM_FLY_FRONT
-        // (round 1) a slot that just entered a neighbour cell goes to the FRONT of the flight queue, so that its next segment
-        // runs while the cell record the transition loaded is still in L1.  With 20-byte cell records the mesh stays in L1
-        // anyway and plain FIFO order is as fast or faster (same box, front / FIFO: linear_demo 12.2 / 11.1 ms, linear_sides
-        // periodic 20.6 / 20.1, Si/Ge 74.4 / 74.2, kinked 218.7 / 217.6), so this is off.
-        q_fly.head -= n_fly;
-        const uint32_t t_fly = q_fly.head;
-#else
         const uint32_t t_fly = q_fly.head + q_fly.count;
-#endif
         const uint32_t t_sct = q_sct.head + q_sct.count, t_wall = q_wall.head + q_wall.count, t_fin = q_fin.head + q_fin.count;
         const uint32_t t_free = q_free.head + q_free.count;
         const unsigned peers = d_fly ? m_fly : (d_sct ? m_sct : (d_wall ? m_wall : (d_fin ? m_fin : m_free)));
