@@ -10,7 +10,11 @@ import numpy as np
 from psim_b200 import configs, lib as psim
 from tests import common as T
 rng = random.Random(int(sys.argv[1]))
-model = T.load_model(configs.linear_sides(num_cells=20, y=20, num_phonons=3000, sim_type=2, step_interval=4, start_time=0.1, duration=0.15).to_dict())
+# FUZZ_STEADY=1: a steady-state model instead, whose unrecorded passes fly the lattice image (device_types.h)
+if os.environ.get("FUZZ_STEADY"):
+    model = T.load_model(configs.linear_sides(num_cells=20, y=20, num_phonons=3000).to_dict())
+else:
+    model = T.load_model(configs.linear_sides(num_cells=20, y=20, num_phonons=3000, sim_type=2, step_interval=4, start_time=0.1, duration=0.15).to_dict())
 model.prepare()
 lib = T.emu_lib()
 desc = model.describe().contents
@@ -19,7 +23,9 @@ S, R, M = info.num_sensors, info.recorded_steps, info.measurement_steps
 _src, _n = model.sources(1)
 def run(nsrc=None, src=None):
     if nsrc is None: nsrc, src = _n, _src
-    e = np.zeros((S, R), dtype=np.int32); f = np.zeros((S, R, 2)); fx = np.zeros((S, R, 2), dtype=np.int64)
+    # (the caller sizes the tally arrays by the description it passes: R = measurement_steps - step_adjustment, which the
+    # mutations below may raise up to M)
+    e = np.zeros((S, M), dtype=np.int32); f = np.zeros((S, M, 2)); fx = np.zeros((S, M, 2), dtype=np.int64)
     steps, events = C.c_uint64(), C.c_uint64(); err = C.create_string_buffer(512)
     return lib.psim_emu_run(C.byref(desc), src, nsrc, 1, 0, 1, 16, e.ctypes.data, f.ctypes.data, fx.ctypes.data, C.byref(steps), C.byref(events), None, None, err, 512), err.value
 print("baseline", run())
