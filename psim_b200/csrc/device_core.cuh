@@ -46,6 +46,11 @@ PSIM_HD float f_div(float a, float b) {  // a / b with one MUFU.RCP (1 ulp) - am
     return a * r;
 }
 PSIM_HD float f_inf() { return __int_as_float(0x7f800000); }
+// a b + c d with ONE association everywhere: fma(a, b, round(c d)).  Left to the compiler, which of the two products is
+// fused depends on the code around the expression, and the kernel variants - which must agree bit for bit - got different
+// roundings on cells whose frame is not axis-aligned (kinked wire: a few flight segments per million went another way).
+PSIM_HD float dot2(float a, float b, float c, float d) { return __fmaf_rn(a, b, __fmul_rn(c, d)); }
+PSIM_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 template<typename T> PSIM_HD T ldg(const T* p) { return __ldg(p); }
 PSIM_HD uint4 load_cell_links(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint4*>(cells + i)); }
 PSIM_HD uint2 load_cell_tail(const DevCell* cells, uint32_t i) { return __ldg(reinterpret_cast<const uint2*>(&cells[i].sensor_mat)); }
@@ -69,6 +74,8 @@ PSIM_HD float f_cos2pi(float u) { return std::cos(6.283185307179586f * u); }
 PSIM_HD float f_sqrt(float x) { return std::sqrt(x); }
 PSIM_HD float f_div(float a, float b) { return a / b; }
 PSIM_HD float f_inf() { return INFINITY; }
+PSIM_HD float dot2(float a, float b, float c, float d) { return std::fmaf(a, b, c * d); }  // (built with -ffp-contract=off)
+PSIM_HD float fma_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 template<typename T> PSIM_HD T ldg(const T* p) { return *p; }
 PSIM_HD uint4 load_cell_links(const DevCell* cells, uint32_t i) {
     uint4 q;
@@ -309,16 +316,16 @@ PSIM_HD void isotropic_direction(float u1, float u2, float vel, Phonon& p) {
 PSIM_HD void diffuse_direction(float u1, float u2, float nx, float ny, float vel, Phonon& p) {
     const float a = f_sqrt(u1);
     const float b = f_sqrt(fmaxf(1.f - u1, 0.f)) * f_cos2pi(u2);
-    p.dx = vel * (nx * a - ny * b);
-    p.dy = vel * (ny * a + nx * b);
+    p.dx = vel * dot2(nx, a, -ny, b);
+    p.dy = vel * dot2(ny, a, nx, b);
 }
 
 // Surface::boundaryHandlePhonon (surface.cpp:32-44); needs up to 3 unread random words
 PSIM_HD void boundary_reflect(Rng& rng, float spec, float nx, float ny, float vel, Phonon& p) {
     if (spec >= 1.f || rng_u01(rng) < spec) {
-        const float dn = p.dx * nx + p.dy * ny;
-        p.dx -= 2.f * dn * nx;
-        p.dy -= 2.f * dn * ny;
+        const float dn = dot2(p.dx, nx, p.dy, ny);
+        p.dx = fma_rn(-2.f * dn, nx, p.dx);
+        p.dy = fma_rn(-2.f * dn, ny, p.dy);
     } else {
         const float u1 = rng_u01(rng), u2 = rng_u01(rng);
         diffuse_direction(u1, u2, nx, ny, vel, p);
@@ -384,8 +391,8 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
         const float x1 = static_cast<float>(ac.corners & 1u), y1 = static_cast<float>((ac.corners >> 1) & 1u);
         const float x2 = static_cast<float>((ac.corners >> 2) & 1u), y2 = static_cast<float>((ac.corners >> 3) & 1u);
         const float x3 = static_cast<float>((ac.corners >> 4) & 1u), y3 = static_cast<float>((ac.corners >> 5) & 1u);
-        p.b1 = x1 + (x2 - x1) * r1 + (x3 - x1) * r2;
-        p.b2 = y1 + (y2 - y1) * r1 + (y3 - y1) * r2;
+        p.b1 = fma_rn(x3 - x1, r2, fma_rn(x2 - x1, r1, x1));
+        p.b2 = fma_rn(y3 - y1, r2, fma_rn(y2 - y1, r1, y1));
         if (P.lattice) {  // the triangle's parallelogram is one of nx x ny of its lattice cell
             const uint32_t dims = ldg(&P.cells[PSIM_CELL_INDEX(p.cell)].tri[1]);
             p.b1 = clamp01((p.b1 + static_cast<float>((ac.corners >> 6) & 0x1FFFu)) / static_cast<float>(dims & 0xFFFFu));
@@ -406,7 +413,7 @@ PSIM_HD float create_phonon(const DevParams& P, const DevSource& src, uint64_t j
     frac = frac < 0. ? 0. : (frac > 0.999999 ? 0.999999 : frac);
     (void)j;
     sample_table(P, em.table, PSIM_CELL_MAT(sm), u_bin, u_pol, u_jit, p, vel);
-    place_on_edge(PSIM_CELL_QUAD(p.cell), em.edge, clamp01(em.s_p1 * u_a + em.s_p2 * (1.f - u_a)), p);
+    place_on_edge(PSIM_CELL_QUAD(p.cell), em.edge, clamp01(dot2(em.s_p1, u_a, em.s_p2, 1.f - u_a)), p);
     const float2 n = load_cell_normal(P, p.cell, em.edge);
     if (src.kind == 2u) {  // phasor: unit frequency, 1000 m/s, straight along the normal
         p.packed = (p.packed & 0xFF000800u) | 1u | (PSIM_CELL_MAT(sm) << 12);
@@ -457,8 +464,8 @@ PSIM_HD void set_cell_matrix(Flight& f, const float4 m) {
 }
 
 PSIM_HD void update_rates_of_motion(Flight& f, const Phonon& p) {
-    f.r1 = f.m00 * p.dx + f.m01 * p.dy;
-    f.r2 = f.m10 * p.dx + f.m11 * p.dy;
+    f.r1 = dot2(f.m00, p.dx, f.m01, p.dy);
+    f.r2 = dot2(f.m10, p.dx, f.m11, p.dy);
 }
 
 PSIM_HD float draw_scatter_time(const DevParams& P, const DevSensor& sen, const Phonon& p, float u) {
@@ -506,6 +513,7 @@ PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s,
     const bool impact = th <= p.tts;        // reference: impact_time <= time (modelSimulator.cpp:111)
     const float te = impact ? th : p.tts;   // time to the next physical event
     int ev = impact ? EV_IMPACT : EV_SCATTER;
+    uint32_t mk0 = 0, mk1 = 0;              // recorded steps [mk0, mk1) that end during this segment
     float flown = te;                       // time flown in this segment
     float t_left = f.t - te;                // time left in the measurement interval in which the segment ends
     if (!(te < f.t)) {
@@ -516,8 +524,8 @@ PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s,
         const float q = fminf(floorf((te - f.t) * P.step_time_inv), 1.0e6f);
         const uint32_t n = min(left, static_cast<uint32_t>(q) + 1u);
         n_steps += n;
-        const uint32_t first = max(P.first_tally_step, s + 1u) - 1u;  // first RECORDED one among them
-        if (first < s + n) { on_measure(first, s + n); }
+        mk0 = max(P.first_tally_step, s + 1u) - 1u;  // first RECORDED one among them
+        mk1 = s + n;
         const float to_last = f.t + static_cast<float>(n - 1u) * P.step_time;  // up to the last boundary crossed
         const bool end = n == left;  // end of the launch window: the state goes back to the pool
         s = end ? step_end - 1u : s + n;
@@ -542,7 +550,39 @@ PSIM_HD int flight_window(const DevParams& P, Phonon& p, Flight& f, uint32_t& s,
     f.edge = hit ? (isA ? eA : (isC ? 1u : eB)) : 0u;
     // fraction of the edge from its first vertex (device_types.h: edges run counter to b1 on edge 2 and to b2 on the b1 = 0 edge)
     f.s_hit = isA ? (down ? c1 : 1.f - c1) : (isC ? c2 : (left ? 1.f - c2 : c2));
+    // the caller's tally, with the state at the END of the segment (position p, rates of motion f.r1 / f.r2, f.t left in the
+    // interval in which it ends): what a lattice cell needs to find where the phonon was at each of the measurements
+    if (mk0 < mk1) { on_measure(mk0, mk1); }
     return ev;
+}
+
+// Recorded windows over the lattice image.  The measurement that ended step k, k0 <= k < k1, of a segment that ended at
+// (e1, e2) of lattice cell `sub` = (first sub-cell, nx | ny << 16) with t_left of its last interval remaining lies
+// (dt - t_left) + (k1 - 1 - k) dt before the end of the segment.
+PSIM_HD float lattice_back(const DevParams& P, float t_left, uint32_t k, uint32_t k1) {
+    return (P.step_time - t_left) + static_cast<float>(k1 - 1u - k) * P.step_time;
+}
+PSIM_HD uint32_t lattice_sensor_at(const DevParams& P, const uint2 sub, float e1, float e2, float r1, float r2, float back) {
+    float l;
+    const uint32_t nx = sub.y & 0xFFFFu, ny = sub.y >> 16;
+    const uint32_t ix = lattice_split(fma_rn(-r1, back, e1), nx, l), iy = lattice_split(fma_rn(-r2, back, e2), ny, l);
+    return ldg(&P.sub_sensor[sub.x + iy * nx + ix]);
+}
+// ... and the runs of equal sensor areas among them, in step order: post(ka, kb, sensor) for every run [ka, kb)
+template<class Post>
+PSIM_HD void lattice_runs(const DevParams& P, uint32_t cell, float e1, float e2, float r1, float r2, float t_left, uint32_t k0,
+                          uint32_t k1, Post&& post) {
+    const uint2 sub = load_cell_tris(P.cells, PSIM_CELL_INDEX(cell));
+    uint32_t run0 = k0, cur = lattice_sensor_at(P, sub, e1, e2, r1, r2, lattice_back(P, t_left, k0, k1));
+    for (uint32_t k = k0 + 1u; k < k1; ++k) {
+        const uint32_t nxt = lattice_sensor_at(P, sub, e1, e2, r1, r2, lattice_back(P, t_left, k, k1));
+        if (nxt != cur) {
+            post(run0, k, cur);
+            run0 = k;
+            cur = nxt;
+        }
+    }
+    post(run0, k1, cur);
 }
 
 // The reference redraws the time to scatter whenever a phonon enters another sensor area (modelSimulator.cpp:
@@ -572,9 +612,9 @@ PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 l
         if (!PSIM_FAST_WALLS || !(link & 1u)) { return false; }  // not perfectly specular: needs random numbers
         const float2 n = load_shape_normal(P.shapes, tail.y, f.edge);
         set_cell_matrix(f, load_shape_matrix(P.shapes, tail.y));  // (a caller that only flies keeps r1, r2, not the matrix)
-        const float dn = p.dx * n.x + p.dy * n.y;
-        p.dx -= 2.f * dn * n.x;
-        p.dy -= 2.f * dn * n.y;
+        const float dn = dot2(p.dx, n.x, p.dy, n.y);
+        p.dx = fma_rn(-2.f * dn, n.x, p.dx);
+        p.dy = fma_rn(-2.f * dn, n.y, p.dy);
         update_rates_of_motion(f, p);
         ++f.ncoll;
         reflected = true;

@@ -90,6 +90,10 @@ struct PSIM_ALIGN(16) DevCell {
 // whose frame spans the block: b1 in [0, 1] covers the nx columns.  Its outer edges are composite surfaces (one sub-surface per
 // fine edge that is not a plain wall).  The pool holds lattice coordinates while such launches run; the first launch that
 // records converts every phonon it fetches back to its fine flight cell (coarse_to_fine, device_core.cuh).
+// Where a phonon crosses several fine cells per measurement step (the kinked wire: 3.8 x 5.1 nm cells, 10 - 18 nm per step)
+// recorded windows fly the lattice image too (psim_gpu.cu decides per model): a flight segment then spans several sensor
+// areas, and the area of every measurement it crossed is found from the phonon's position at that instant
+// (lattice_sensor_at); runs of equal areas are tallied in difference form.
 
 struct PSIM_ALIGN(16) DevShape {
     float m00, m01, m10, m11;  // d(b1)/dt = m00 vx + m01 vy ; d(b2)/dt = m10 vx + m11 vy   (inverse of [u | v])
@@ -188,6 +192,7 @@ struct DevParams {
     const uint32_t* guides;    // [n_tables][PSIM_GUIDE] search bracket for r in [k/G, (k+1)/G), G = PSIM_GUIDE: low | high << 16
     const float* velocities;   // [n_materials][2][PSIM_BINS] group velocity, LA then TA, m/s == nm/ns
     const uint32_t* sub_fine;  // lattice image only: tagged fine flight-cell word of every parallelogram of every lattice cell, rows first
+    const uint32_t* sub_sensor; // lattice image only: ... and its sensor index (recorded windows flown over the lattice image)
     uint32_t n_cells, n_flight_cells, n_shapes, n_sensors, n_materials, n_tables, n_emitters, n_sources;
     uint32_t num_steps;        // measurement steps M
     uint32_t first_tally_step; // reference step_adjustment_ (modelSimulator.h:24-26)

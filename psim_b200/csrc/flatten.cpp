@@ -156,7 +156,8 @@ void build_lattices(HostImage& img, const std::vector<Frame>& frames) {
     std::vector<DevCell> cells(blocks.size());
     std::vector<DevShape> shapes;
     std::vector<DevSub> subs;
-    std::vector<uint32_t> sub_fine(sub_total);
+    std::vector<uint32_t> sub_fine(sub_total), sub_sensor(sub_total);
+    double extent_sum = 0., extent_cells = 0.;
     auto shape_id = [&](const DevShape& sh) -> uint32_t {
         for (size_t i = 0; i < shapes.size(); ++i) {
             if (std::memcmp(&shapes[i], &sh, sizeof(sh)) == 0) { return static_cast<uint32_t>(i); }
@@ -189,7 +190,16 @@ void build_lattices(HostImage& img, const std::vector<Frame>& frames) {
         o.sensor_mat = img.cells[c0].sensor_mat;
         o.tri[0] = b.sub_off;
         o.tri[1] = b.nx | (b.ny << 16);
-        for (size_t i = 0; i < b.cells.size(); ++i) { sub_fine[b.sub_off + i] = b.cells[i] | (quad[b.cells[i]] ? (1u << 31) : 0u); }
+        for (size_t i = 0; i < b.cells.size(); ++i) {
+            sub_fine[b.sub_off + i] = b.cells[i] | (quad[b.cells[i]] ? (1u << 31) : 0u);
+            sub_sensor[b.sub_off + i] = PSIM_CELL_SENSOR(img.cells[b.cells[i]].sensor_mat);
+        }
+        if (b.cells.size() > 1) {  // extent of one of its parallelograms across either pair of edges = 1 / |gradient of b1 (b2)|
+            const DevShape& fs = img.shapes[img.cells[c0].shape];
+            const double w1 = 1. / std::hypot(fs.m00, fs.m01), w2 = 1. / std::hypot(fs.m10, fs.m11);
+            extent_sum += std::min(w1, w2) * static_cast<double>(b.cells.size());
+            extent_cells += static_cast<double>(b.cells.size());
+        }
         const uint64_t key = (static_cast<uint64_t>(img.cells[c0].shape) << 32) | (b.nx << 16) | b.ny;
         auto it = shape_cache.find(key);
         if (it == shape_cache.end()) {
@@ -287,6 +297,10 @@ void build_lattices(HostImage& img, const std::vector<Frame>& frames) {
     img.lattice_shapes = std::move(shapes);
     img.lattice_subs = std::move(subs);
     img.lattice_sub_fine = std::move(sub_fine);
+    img.lattice_sub_sensor = std::move(sub_sensor);
+    float vmax = img.scalars.phasor ? 1000.f : 0.f;
+    for (float v : img.velocities) { vmax = std::max(vmax, std::fabs(v)); }
+    img.lattice_cells_per_step = extent_cells > 0. ? static_cast<double>(vmax) * img.scalars.step_time_d / (extent_sum / extent_cells) : 0.;
     img.lattice_api_cells = std::move(api);
     img.lattice_emitters = std::move(emitters);
 }
@@ -742,9 +756,6 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
             em.s_p2 = 1.f - em.s_p2;
         }
     }
-    if (merge_cells >= 2) { build_lattices(out, frames); }
-    mark_fast_links(out.cells, out.shapes, out.subs);
-    mark_fast_links(out.lattice_cells, out.lattice_shapes, out.lattice_subs);
     if (out.subs.empty()) { out.subs.push_back(DevSub{}); }
     if (out.emitters.empty()) { out.emitters.push_back(DevEmitter{}); }
 
@@ -765,6 +776,9 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
     P.step_time = static_cast<float>(step_time);
     P.step_time_inv = static_cast<float>(1. / step_time);
     P.step_time_d = step_time;
+    if (merge_cells >= 2) { build_lattices(out, frames); }
+    mark_fast_links(out.cells, out.shapes, out.subs);
+    mark_fast_links(out.lattice_cells, out.lattice_shapes, out.lattice_subs);
     return 0;
 }
 

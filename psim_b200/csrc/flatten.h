@@ -26,6 +26,11 @@ struct HostImage {
     std::vector<DevSub> lattice_subs;
     std::vector<DevEmitter> lattice_emitters;
     std::vector<uint32_t> lattice_sub_fine;  // DevParams::sub_fine
+    std::vector<uint32_t> lattice_sub_sensor;  // DevParams::sub_sensor
+    // how many fine cells a phonon at the model's largest group velocity crosses per measurement step, averaged over the
+    // cells that are part of a block (0 without lattice image): where it is large, flying the lattice image pays in recorded
+    // windows too (psim_gpu.cu)
+    double lattice_cells_per_step = 0.;
     std::vector<DevSensor> sensors;
     std::vector<DevMaterial> materials;
     std::vector<DevEmitter> emitters;

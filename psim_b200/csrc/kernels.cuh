@@ -527,9 +527,14 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_slots(const 
                 uint32_t s = s0;
                 const int ev = psim::flight_window(P, p, f, s, a.step_end, n_steps, [&](uint32_t k0, uint32_t k1) {
                     const int32_t sg = PSIM_PACK_NEG(slot_u(SF_PACKED, k)) ? -1 : 1;
-                    const uint32_t sensor = PSIM_CELL_SENSOR(psim::cell_sensor_word(P, slot_u(SF_CELL, k)));
                     const int32_t fx = psim::flux_fixed(slot_f(SF_DX, k)) * sg, fy = psim::flux_fixed(slot_f(SF_DY, k)) * sg;
-                    tally_range(a, acc_e, acc_f, k0, k1, sensor, sg, fx, fy);
+                    if (P.lattice) {  // (called with the state at the end of the segment)
+                        psim::lattice_runs(P, p.cell, p.b1, p.b2, f.r1, f.r2, f.t, k0, k1,
+                                           [&](uint32_t ka, uint32_t kb, uint32_t sn) { tally_range(a, acc_e, acc_f, ka, kb, sn, sg, fx, fy); });
+                    } else {
+                        const uint32_t sensor = PSIM_CELL_SENSOR(psim::cell_sensor_word(P, slot_u(SF_CELL, k)));
+                        tally_range(a, acc_e, acc_f, k0, k1, sensor, sg, fx, fy);
+                    }
                 });
                 ++n_events;
                 // a measurement boundary crossed on the way restarts the per-interval bookkeeping (impact counter, Philox
@@ -591,7 +596,9 @@ static_assert(SG_COUNT * 4 == SF_COUNT, "both layouts hold the same twelve words
 // TALLY (what a launch does with the measurement events its window records)
 enum : int { TALLY_NONE = 0,     // the window ends before the first recorded step: no tally code at all
              TALLY_STAGED = 1,   // per-CTA staging in shared memory (LaunchArgs::tally_shared 1 / 2 / 4) or plain global adds (0)
-             TALLY_GLOBAL = 2 }; // difference rows in global memory (tally_shared 3), posted warp-cooperatively: tally_post_global
+             TALLY_GLOBAL = 2,   // difference rows in global memory (tally_shared 3), posted warp-cooperatively: tally_post_global
+             TALLY_LATTICE = 3 };// the same over the lattice image: the sensor area of every crossed measurement from the phonon's
+                                 // position at that instant, the measurements of a pass dealt evenly over the lanes (tally_lattice)
 constexpr uint32_t kPostScratchBytes = 64u * 16u;  // per warp: up to two posts per lane
 
 // Shared memory is addressed with 32-bit shared-window addresses and explicit ld.shared / st.shared: with generic pointers
@@ -649,6 +656,78 @@ __device__ __forceinline__ void tally_post_global(const LaunchArgs& a, uint32_t 
         }
     }
     __syncwarp();
+}
+
+// Recorded windows over the lattice image (device_types.h).  A flight segment of a lattice cell spans several sensor areas;
+// every measurement it crossed is attributed to the area the phonon was in at that instant.  The number of crossed
+// measurements differs widely from lane to lane (a phonon that flies along a wire crosses many), so they are not walked
+// lane by lane: the (segment, measurement) pairs of the pass are numbered through a warp scan and dealt evenly, 32 per
+// round - lane i of a round takes pair i, finds the lane that owns it, fetches that lane's segment by shuffles and
+// evaluates the area.  Consecutive pairs of one segment sit in consecutive lanes, so a run of equal areas is recognised by
+// comparing with the neighbours: its first pair posts +v into its row, its last -v into the row behind (difference form,
+// tally_range); a run cut by the end of a round is posted as two runs, which sums to the same integers.
+__device__ __forceinline__ void tally_post_marks(const LaunchArgs& a, uint32_t scratch, uint32_t lane, uint32_t lt_mask, bool plus, bool minus,
+                                                 uint32_t k, uint32_t sensor, int32_t e, int32_t fx, int32_t fy) {
+    const uint32_t S = a.P.n_sensors, F = a.P.first_tally_step;
+    const uint32_t r0 = k + 1u - F, r1 = r0 + 1u;  // the row of the measurement that ended step k, and the one behind it
+    const bool has_end = minus && r1 < a.P.recorded_steps;
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, plus), m1 = __ballot_sync(0xFFFFFFFFu, has_end);
+    if ((m0 | m1) == 0u) { return; }  // warp-uniform
+    const uint32_t n0 = __popc(m0), n = n0 + __popc(m1);
+    if (plus) { sts128u(scratch + 16u * __popc(m0 & lt_mask), make_uint4(r0 * S + sensor, static_cast<uint32_t>(e), static_cast<uint32_t>(fx), static_cast<uint32_t>(fy))); }
+    if (has_end) { sts128u(scratch + 16u * (n0 + __popc(m1 & lt_mask)), make_uint4(r1 * S + sensor, static_cast<uint32_t>(-e), static_cast<uint32_t>(-fx), static_cast<uint32_t>(-fy))); }
+    __syncwarp();
+    const uint32_t group = (lane * 11u) >> 5, comp = lane - 3u * group;  // lane / 3 and lane % 3 for lane < 32
+    if (lane < 30u) {
+        for (uint32_t post = group; post < n; post += 10u) {
+            const uint32_t entry = lds32(scratch + 16u * post);
+            const long long val = static_cast<long long>(static_cast<int32_t>(lds32(scratch + 16u * post + 4u + 4u * comp)));
+            atomic_add_i64(a.tally_acc + (static_cast<size_t>(entry) * 4u + comp), val);
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void tally_lattice(const LaunchArgs& a, uint32_t scratch, uint32_t lane, uint32_t lt_mask, bool has, uint32_t k0, uint32_t k1,
+                                              uint32_t cell, float e1, float e2, float r1, float r2, float t_left, int32_t sg, int32_t fx, int32_t fy) {
+    const DevParams& P = a.P;
+    const uint32_t count = has ? k1 - k0 : 0u;
+    uint32_t incl = count;  // inclusive scan over the lanes
+#pragma unroll
+    for (uint32_t d = 1u; d < 32u; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) { incl += t; }
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0u) { return; }  // warp-uniform
+    const uint2 sub = has ? psim::load_cell_tris(P.cells, PSIM_CELL_INDEX(cell)) : make_uint2(0u, 1u | (1u << 16));
+    const uint32_t first = incl - count;  // number of this lane's first pair
+    for (uint32_t base = 0u; base < total; base += 32u) {
+        const bool active = base + lane < total;
+        const uint32_t i = active ? base + lane : total - 1u;
+        // owner = the number of lanes whose pairs all lie before pair i
+        uint32_t owner = 0u;
+#pragma unroll
+        for (uint32_t step = 16u; step > 0u; step >>= 1) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, owner + step - 1u);
+            if (v <= i) { owner += step; }
+        }
+        const uint32_t k = __shfl_sync(0xFFFFFFFFu, k0, owner) + (i - __shfl_sync(0xFFFFFFFFu, first, owner));
+        const uint32_t o_k1 = __shfl_sync(0xFFFFFFFFu, k1, owner);
+        const uint2 o_sub = make_uint2(__shfl_sync(0xFFFFFFFFu, sub.x, owner), __shfl_sync(0xFFFFFFFFu, sub.y, owner));
+        const float o_e1 = __shfl_sync(0xFFFFFFFFu, e1, owner), o_e2 = __shfl_sync(0xFFFFFFFFu, e2, owner);
+        const float o_r1 = __shfl_sync(0xFFFFFFFFu, r1, owner), o_r2 = __shfl_sync(0xFFFFFFFFu, r2, owner);
+        const float o_tl = __shfl_sync(0xFFFFFFFFu, t_left, owner);
+        const int32_t o_sg = __shfl_sync(0xFFFFFFFFu, sg, owner), o_fx = __shfl_sync(0xFFFFFFFFu, fx, owner), o_fy = __shfl_sync(0xFFFFFFFFu, fy, owner);
+        const uint32_t sensor = psim::lattice_sensor_at(P, o_sub, o_e1, o_e2, o_r1, o_r2, psim::lattice_back(P, o_tl, k, o_k1));
+        // a run begins where the lane before holds another segment or another area (or nothing: lane 0), and ends likewise
+        const uint32_t p_owner = __shfl_up_sync(0xFFFFFFFFu, owner, 1), p_sensor = __shfl_up_sync(0xFFFFFFFFu, sensor, 1);
+        const uint32_t n_owner = __shfl_down_sync(0xFFFFFFFFu, owner, 1), n_sensor = __shfl_down_sync(0xFFFFFFFFu, sensor, 1);
+        const bool n_active = __shfl_down_sync(0xFFFFFFFFu, active ? 1u : 0u, 1) != 0u;
+        const bool begins = active && (lane == 0u || p_owner != owner || p_sensor != sensor);
+        const bool ends = active && (lane == 31u || !n_active || n_owner != owner || n_sensor != sensor);
+        tally_post_marks(a, scratch, lane, lt_mask, begins, ends, k, sensor, o_sg, o_fx, o_fy);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -724,6 +803,8 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
         int dest = -1;
         uint32_t tk0 = 0, tk1 = 0, sensor = 0;  // recorded steps [tk0, tk1) that ended during this segment
         int32_t fx = 0, fy = 0;                 // ... and what the segment adds to each of them (sign * fixed-point velocity)
+        float le1 = 0.f, le2 = 0.f, lr1 = 0.f, lr2 = 0.f, ltl = 0.f;  // TALLY_LATTICE: the end of the segment before any impact
+        uint32_t lcell = 0;
         if (act) {
             f.edge = 0u;
             f.ncoll = PSIM_MISC_NCOLL(misc);
@@ -756,6 +837,10 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                     fx = psim::flux_fixed(p.dx);
                     fy = psim::flux_fixed(p.dy);
                 }
+                if (TALLY == TALLY_LATTICE) {
+                    le1 = p.b1, le2 = p.b2, lr1 = f.r1, lr2 = f.r2, ltl = f.t;
+                    lcell = cell0;
+                }
                 if (hit) {
                     f.sensor_mat = tail0.x;
                     if (psim::fast_impact(P, p, f, psim::load_cell_links(P.cells, PSIM_CELL_INDEX(cell0)), tail0, reflected, false)) {
@@ -780,7 +865,9 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
             const int32_t sg = PSIM_PACK_NEG(p.packed) ? -1 : 1;
             fx *= sg;
             fy *= sg;
-            if (TALLY == TALLY_GLOBAL) {
+            if (TALLY == TALLY_LATTICE) {
+                tally_lattice(a, post, lane, lt_mask, has, tk0, tk1, lcell, le1, le2, lr1, lr2, ltl, sg, fx, fy);
+            } else if (TALLY == TALLY_GLOBAL) {
                 tally_post_global(a, post, lane, lt_mask, has, tk0, tk1, sensor, sg, fx, fy);
             } else if (has) {
                 tally_range(a, acc_e, acc_f, tk0, tk1, sensor, sg, fx, fy);
@@ -1016,7 +1103,12 @@ __global__ void __launch_bounds__(kBlock, (kBlock <= 256 ? 2 : 1)) drift_kernel_
                                          [&](uint32_t k0, uint32_t k1, const psim::Phonon& q, const psim::Flight& f) {
                 const int32_t sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
                 const int32_t fx = psim::flux_fixed(q.dx) * sg, fy = psim::flux_fixed(q.dy) * sg;
-                tally_range(a, acc_e, acc_f, k0, k1, PSIM_CELL_SENSOR(f.sensor_mat), sg, fx, fy);
+                if (P.lattice) {
+                    psim::lattice_runs(P, q.cell, q.b1, q.b2, f.r1, f.r2, f.t, k0, k1,
+                                       [&](uint32_t ka, uint32_t kb, uint32_t sn) { tally_range(a, acc_e, acc_f, ka, kb, sn, sg, fx, fy); });
+                } else {
+                    tally_range(a, acc_e, acc_f, k0, k1, PSIM_CELL_SENSOR(f.sensor_mat), sg, fx, fy);
+                }
             });
             if (!alive) { ++n_absorbed; }
         }

@@ -170,6 +170,7 @@ struct psim_gpu {
     void* d_lat_subs = nullptr;
     void* d_lat_emitters = nullptr;
     void* d_lat_sub_fine = nullptr;
+    void* d_lat_sub_sensor = nullptr;
     void* d_cells = nullptr;
     void* d_api_cells = nullptr;
     void* d_shapes = nullptr;
@@ -213,6 +214,8 @@ struct psim_gpu {
     int64_t opt_kernel = 2;          // 2: work-queue kernel, 0: lane-bound slots kernel, 1: lock-step kernel (first version, for A/B)
     int64_t opt_queue_slots = PSIM_QUEUE_SLOTS;  // phonons in flight per warp of the work-queue kernel (128, or 64: more L1 left for the mesh)
     int64_t opt_tally_shared = -1;
+    int64_t opt_lattice_recorded = -1;  // recorded windows over the lattice image: -1 where a phonon crosses kLatticeRecordedCrossings
+                                        // fine cells or more per measurement step, 0 never, 1 wherever the model has the image
     int64_t opt_merge_cells = 2;     // 0: one flight cell per model triangle (A/B, per-function probes), 1: pairs of triangles as
                                      // parallelograms, 2: also blocks of parallelograms as lattice cells where nothing is recorded
     uint32_t last_tally_shared = 0;
@@ -304,6 +307,7 @@ size_t stage_budget(const psim_gpu* h) {
 constexpr int kStatWords = 8;                   // LaunchArgs::stats
 constexpr uint32_t kLongWindow = 1023;           // steps per launch while nothing is recorded (10 bits of step in the slot word)
 constexpr uint32_t kGlobalTallyWindow = 128;     // steps per launch when recorded tallies go straight to global memory
+constexpr double kLatticeRecordedCrossings = 2.0;  // fine cells crossed per step at the largest group velocity (see run_steps)
 constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
 
 // Measurement intervals a launch may cover (its "window").
@@ -386,7 +390,7 @@ int upload_geometry(psim_gpu* h, const psim::HostImage& g) {
 int upload_lattice(psim_gpu* h) {
     h->have_lattice = false;
     if (h->img.lattice_cells.empty()) { return 0; }
-    for (void** p : { &h->d_lat_cells, &h->d_lat_shapes, &h->d_lat_api_cells, &h->d_lat_subs, &h->d_lat_emitters, &h->d_lat_sub_fine }) {
+    for (void** p : { &h->d_lat_cells, &h->d_lat_shapes, &h->d_lat_api_cells, &h->d_lat_subs, &h->d_lat_emitters, &h->d_lat_sub_fine, &h->d_lat_sub_sensor }) {
         devmem::free(*p);
         *p = nullptr;
     }
@@ -396,6 +400,7 @@ int upload_lattice(psim_gpu* h) {
     if (int rc = upload(h, &h->d_lat_subs, h->img.lattice_subs)) { return rc; }
     if (int rc = upload(h, &h->d_lat_emitters, h->img.lattice_emitters)) { return rc; }
     if (int rc = upload(h, &h->d_lat_sub_fine, h->img.lattice_sub_fine)) { return rc; }
+    if (int rc = upload(h, &h->d_lat_sub_sensor, h->img.lattice_sub_sensor)) { return rc; }
     h->have_lattice = true;
     return 0;
 }
@@ -409,6 +414,7 @@ DevParams lattice_params(const psim_gpu* h) {
     L.subs = static_cast<const DevSub*>(h->d_lat_subs);
     L.emitters = static_cast<const DevEmitter*>(h->d_lat_emitters);
     L.sub_fine = static_cast<const uint32_t*>(h->d_lat_sub_fine);
+    L.sub_sensor = static_cast<const uint32_t*>(h->d_lat_sub_sensor);
     L.n_flight_cells = static_cast<uint32_t>(h->img.lattice_cells.size());
     L.n_shapes = static_cast<uint32_t>(h->img.lattice_shapes.size());
     L.lattice = 1u;
@@ -553,6 +559,8 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots, TALLY_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
+        PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         return zero_run_state(h);
     };
     if (int rc = setup()) { return bail(rc); }
@@ -654,7 +662,12 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         LaunchArgs a{};
         // A window that records nothing flies the lattice image (device_types.h) - from the start of a run until the first
         // window that records; that one converts the pool back as it fetches it.
-        const bool lattice = h->have_lattice && h->opt_merge_cells == 2 && !records && (h->pool_in_lattice || s0 == 0);
+        // A model whose phonons cross several fine cells per measurement step flies the lattice image in its recorded windows
+        // too: the sensor area of every crossed measurement is found from the position at that instant (kernels.cuh:
+        // tally_lattice).  Only where the tallies go to global memory - the many-sensor models; few sensors mean large areas.
+        const bool lattice_recorded = h->diff_mode && (h->opt_lattice_recorded > 0 ||
+                                                       (h->opt_lattice_recorded < 0 && h->img.lattice_cells_per_step >= kLatticeRecordedCrossings));
+        const bool lattice = h->have_lattice && h->opt_merge_cells == 2 && (!records || lattice_recorded) && (h->pool_in_lattice || s0 == 0);
         a.P = lattice ? lattice_params(h) : h->P;
         a.convert_input = (h->pool_in_lattice && !lattice) ? 1u : 0u;
         a.lattice_cells = static_cast<const DevCell*>(h->d_lat_cells);
@@ -697,8 +710,8 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
             drift_kernel_lockstep<<<grid, kBlock, dyn, st>>>(a);
         } else if (h->opt_kernel == 2) {
             // one instantiation per (slots per warp, what the window does with its measurement events)
-            const int tally = !records ? TALLY_NONE : (h->diff_mode ? TALLY_GLOBAL : TALLY_STAGED);
-            const size_t bytes = queue_bytes_per_block(static_cast<int>(h->opt_queue_slots)) + (tally == TALLY_GLOBAL ? kPostBytesPerBlock : 0) +
+            const int tally = !records ? TALLY_NONE : (h->diff_mode ? (lattice ? TALLY_LATTICE : TALLY_GLOBAL) : TALLY_STAGED);
+            const size_t bytes = queue_bytes_per_block(static_cast<int>(h->opt_queue_slots)) + ((tally == TALLY_GLOBAL || tally == TALLY_LATTICE) ? kPostBytesPerBlock : 0) +
                                  (shared ? ((smem + 127) & ~static_cast<size_t>(127)) : 0);
             const bool big = h->opt_queue_slots == kQueueSlots;
             if (tally == TALLY_NONE) {
@@ -707,6 +720,9 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
             } else if (tally == TALLY_GLOBAL) {
                 if (big) { drift_kernel_queues<kQueueSlots, TALLY_GLOBAL><<<grid, kBlock, bytes, st>>>(a); }
                 else { drift_kernel_queues<kQueueSlotsSmall, TALLY_GLOBAL><<<grid, kBlock, bytes, st>>>(a); }
+            } else if (tally == TALLY_LATTICE) {
+                if (big) { drift_kernel_queues<kQueueSlots, TALLY_LATTICE><<<grid, kBlock, bytes, st>>>(a); }
+                else { drift_kernel_queues<kQueueSlotsSmall, TALLY_LATTICE><<<grid, kBlock, bytes, st>>>(a); }
             } else {
                 if (big) { drift_kernel_queues<kQueueSlots, TALLY_STAGED><<<grid, kBlock, bytes, st>>>(a); }
                 else { drift_kernel_queues<kQueueSlotsSmall, TALLY_STAGED><<<grid, kBlock, bytes, st>>>(a); }
@@ -917,6 +933,12 @@ int psim_gpu_set_option(psim_gpu* h, const char* name, int64_t value) {
             if (int rc = upload_geometry(h, value ? h->img : h->img_tri)) { return rc; }
         }
         h->opt_merge_cells = value;
+    } else if (k == "lattice_recorded") {
+        if (h->have_sources || value < -1 || value > 1) {
+            h->err = "lattice_recorded must be -1 (automatic), 0 or 1 and set before set_sources";
+            return PSIM_E_STATE;
+        }
+        h->opt_lattice_recorded = value;
     } else if (k == "tally_shared") {
         if (h->have_sources || value < -1 || value > 4 || value == 3) {  // the tally form of a run is fixed when it starts
             h->err = "tally_shared must be -1 (automatic), 0 (global memory), 1 / 4 / 2 (staged: two / three 32-bit parts, 64-bit) and set before set_sources";
@@ -945,7 +967,7 @@ void psim_gpu_destroy(psim_gpu* h) {
     cudaDeviceSynchronize();
     free_pool(h);
     free_plan(h);
-    for (void* p : { h->d_lat_cells, h->d_lat_api_cells, h->d_lat_shapes, h->d_lat_subs, h->d_lat_emitters, h->d_lat_sub_fine }) { devmem::free(p); }
+    for (void* p : { h->d_lat_cells, h->d_lat_api_cells, h->d_lat_shapes, h->d_lat_subs, h->d_lat_emitters, h->d_lat_sub_fine, h->d_lat_sub_sensor }) { devmem::free(p); }
     devmem::free(h->d_cells);
     devmem::free(h->d_api_cells);
     devmem::free(h->d_shapes);

@@ -14,6 +14,9 @@
 // for the passes that record nothing
 static int g_merge_cells = 2;
 extern "C" void psim_emu_set_merge_cells(int level) { g_merge_cells = level; }
+// recorded passes over the lattice image: -1 the library's rule (many sensors, two or more fine cells crossed per step), 0 / 1
+static int g_lattice_recorded = -1;
+extern "C" void psim_emu_set_lattice_recorded(int v) { g_lattice_recorded = v; }
 
 extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sources, size_t n_sources, uint64_t seed,
                             uint32_t shard, uint32_t num_shards, uint32_t steps_per_pass, int32_t* energy /*[S][R]*/,
@@ -56,6 +59,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         PL.subs = img.lattice_subs.data();
         PL.emitters = img.lattice_emitters.data();
         PL.sub_fine = img.lattice_sub_fine.data();
+        PL.sub_sensor = img.lattice_sub_sensor.data();
         PL.lattice = 1u;
     }
     const DevParams PF = P;
@@ -73,11 +77,18 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         const bool alive = psim::advance_window(P, p, t_first, start, s1, steps32, n_events,
                                                 [&](uint32_t k0, uint32_t k1, const psim::Phonon& q, const psim::Flight& f) {
             const int sg = PSIM_PACK_NEG(q.packed) ? -1 : 1;
-            for (uint32_t ks = k0; ks < k1; ++ks) {
-                const size_t k = static_cast<size_t>(ks + 1 - P.first_tally_step) * S + PSIM_CELL_SENSOR(f.sensor_mat);
-                te[k] += sg;
-                tf[2 * k] += static_cast<long long>(psim::flux_fixed(q.dx)) * sg;
-                tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(q.dy)) * sg;
+            auto add = [&](uint32_t ka, uint32_t kb, uint32_t sensor) {
+                for (uint32_t ks = ka; ks < kb; ++ks) {
+                    const size_t k = static_cast<size_t>(ks + 1 - P.first_tally_step) * S + sensor;
+                    te[k] += sg;
+                    tf[2 * k] += static_cast<long long>(psim::flux_fixed(q.dx)) * sg;
+                    tf[2 * k + 1] += static_cast<long long>(psim::flux_fixed(q.dy)) * sg;
+                }
+            };
+            if (P.lattice) {  // the sensor area of every crossed measurement from the position at that instant
+                psim::lattice_runs(P, q.cell, q.b1, q.b2, f.r1, f.r2, f.t, k0, k1, add);
+            } else {
+                add(k0, k1, PSIM_CELL_SENSOR(f.sensor_mat));
             }
         });
         total_events += n_events;
@@ -89,7 +100,8 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         const uint32_t s1 = std::min(s0 + B, M - 1);
         next.clear();
         const bool records = s1 + 1 > P.first_tally_step;
-        const bool lattice_pass = have_lattice && !records && (pool_in_lattice || pool.empty());
+        const bool lattice_recorded = g_lattice_recorded > 0 || (g_lattice_recorded < 0 && S >= 256u && img.lattice_cells_per_step >= 2.0);
+        const bool lattice_pass = have_lattice && (!records || lattice_recorded) && (pool_in_lattice || pool.empty());
         if (pool_in_lattice && !lattice_pass) {
             for (auto& p : pool) { psim::coarse_to_fine(PL.cells, PL.sub_fine, p.cell, p.b1, p.b2); }
         }

@@ -300,3 +300,47 @@ def test_blocks_of_parallelograms_fly_as_one_lattice_cell_where_nothing_is_recor
     assert a["stats"][0]["lattice_cells"] > 0  # the image exists ...
     assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["fixed"], b["fixed"])  # ... and no launch used it
     assert a["stats"][0]["events"] == b["stats"][0]["events"]
+
+
+def test_kernel_variants_agree_bit_for_bit_on_a_mesh_that_is_not_axis_aligned():
+    """The kinked wire: slanted parallelograms (both terms of every frame product are non-zero), triangles and trapezoids in
+    the kinks, composite block edges.  Round 1 / early round 2 left the association of `a b + c d` to the compiler, which
+    fused a different product in the lock-step kernel than in the other two: a few flight segments per million went another
+    way (device_core.cuh: dot2).  Work queues (2), lane-bound slots (0) and lock step (1) must give identical integers with
+    triangles only (merge_cells 0), flight cells (1), lattice cells where nothing is recorded (2) and lattice cells
+    throughout (lattice_recorded 1: the work-queue kernel deals the crossed measurements evenly over the lanes,
+    kernels.cuh:tally_lattice, the other two walk them lane by lane, device_core.cuh:lattice_runs)."""
+    if "kinked_spec" not in T.all_case_names():
+        pytest.skip("kinked wire fixture not available")
+    model = T.load_model(T.case_model("kinked_spec"), num_phonons=40_000)
+    for opts in ({"merge_cells": 0}, {"merge_cells": 1}, {"merge_cells": 2, "lattice_recorded": 0}, {"merge_cells": 2, "lattice_recorded": 1}):
+        ref = gpu_run_case(model, 6, options=dict(opts, kernel=1, tally_shared=0), finish=False)
+        assert np.abs(ref["energy"]).sum() > 0
+        for kern in (2, 0):
+            got = gpu_run_case(model, 6, options=dict(opts, kernel=kern, tally_shared=0), finish=False)
+            assert np.array_equal(got["energy"], ref["energy"]) and np.array_equal(got["fixed"], ref["fixed"]), (opts, kern)
+            assert got["stats"][0]["events"] == ref["stats"][0]["events"] and got["stats"][0]["drift_steps"] == ref["stats"][0]["drift_steps"]
+
+
+def test_recorded_windows_over_the_lattice_image_attribute_every_measurement_to_its_sensor():
+    """Option "lattice_recorded": a flight segment of a lattice cell spans several sensor areas, and the area of every
+    measurement it crossed is found from the phonon's position at that instant.  Same seed with and without: the same phonons,
+    the same random streams - the per-(sensor, step) tallies differ by rounding only (a phonon within 1e-7 of a cell edge at a
+    measurement); far fewer flight segments; the kinked wire uses it by default (its phonons cross 2 - 5 fine cells per step),
+    linear_sides does not (half a cell per step)."""
+    from psim_b200 import configs
+    cases = [("sides_per", T.load_model(configs.linear_sides(sim_type=1, step_interval=4, num_phonons=80_000).to_dict()), False)]
+    if "kinked_spec" in T.all_case_names():
+        cases.append(("kinked_spec", T.load_model(T.case_model("kinked_spec"), num_phonons=100_000), True))
+    for name, model, by_default in cases:
+        on = gpu_run_case(model, 8, options={"lattice_recorded": 1}, finish=False)
+        off = gpu_run_case(model, 8, options={"lattice_recorded": 0}, finish=False)
+        auto = gpu_run_case(model, 8, finish=False)
+        assert np.array_equal(auto["energy"], (on if by_default else off)["energy"]), name
+        assert on["sources"] == off["sources"]
+        assert on["stats"][0]["events"] < 0.85 * off["stats"][0]["events"], name
+        e_on, e_off = on["energy"].astype(np.int64), off["energy"].astype(np.int64)
+        assert np.abs(e_on - e_off).sum() <= 0.01 * np.abs(e_off).sum(), name
+        f_on, f_off = on["fixed"].astype(np.float64), off["fixed"].astype(np.float64)
+        assert np.abs(f_on - f_off).sum() <= 0.01 * np.abs(f_off).sum(), name
+        assert abs(int(e_on.sum()) - int(e_off.sum())) <= 0.002 * np.abs(e_off).sum() + 10, name
