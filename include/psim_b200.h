@@ -140,7 +140,7 @@ typedef struct psim_stats {
     uint32_t lattice_cells;             /* cells of the lattice image flown by the launches that record nothing (blocks of identical
                                            parallelograms of one rate class as one cell each); 0: the model has none, or
                                            "merge_cells" < 2 */
-    uint32_t reserved;
+    uint32_t lattice_recorded;          /* 1: the recorded launches of the last run flew the lattice image too (option "lattice_recorded") */
 } psim_stats;
 
 typedef struct psim_gpu psim_gpu;

@@ -220,6 +220,7 @@ struct psim_gpu {
                                      // parallelograms, 2: also blocks of parallelograms as lattice cells where nothing is recorded
     uint32_t last_tally_shared = 0;
     uint32_t last_window = 0;
+    bool ran_lattice_recorded = false;  // a recording launch of this run flew the lattice image
     uint32_t max_flux_fixed = 0;     // largest |velocity| in flux fixed-point units
     std::string err;
 };
@@ -445,6 +446,7 @@ int zero_run_state(psim_gpu* h) {
     }
     h->cur = 0;
     h->pool_in_lattice = false;
+    h->ran_lattice_recorded = false;
     h->next_step = 0;
     h->launches = 0;
     h->birth_offset = 0;
@@ -673,6 +675,7 @@ int psim_gpu_run_steps(psim_gpu* h, uint32_t step_begin, uint32_t step_end, void
         a.lattice_cells = static_cast<const DevCell*>(h->d_lat_cells);
         a.lattice_sub_fine = static_cast<const uint32_t*>(h->d_lat_sub_fine);
         h->pool_in_lattice = lattice;
+        h->ran_lattice_recorded |= lattice && records;
         a.in_a = h->pool_a[h->cur];
         a.in_b = h->pool_b[h->cur];
         a.out_a = h->pool_a[h->cur ^ 1];
@@ -884,6 +887,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out) {
     out->kernel = static_cast<uint32_t>(h->opt_kernel);
     out->flight_cells = h->P.n_flight_cells;
     out->lattice_cells = (h->have_lattice && h->opt_merge_cells == 2) ? static_cast<uint32_t>(h->img.lattice_cells.size()) : 0u;
+    out->lattice_recorded = h->ran_lattice_recorded ? 1u : 0u;
     out->image_bytes = h->img.cells.size() * sizeof(DevCell) + h->img.api_cells.size() * sizeof(DevApiCell) + h->img.shapes.size() * sizeof(DevShape) + (h->img.classes.size() + h->img.step_sensors.size()) * sizeof(DevSensor) + h->img.subs.size() * sizeof(DevSub) +
                        h->img.sensors.size() * sizeof(DevSensor) + h->img.materials.size() * sizeof(DevMaterial) +
                        h->img.emitters.size() * sizeof(DevEmitter) + h->img.tables.size() * sizeof(float2) +

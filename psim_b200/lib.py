@@ -78,7 +78,7 @@ class Stats(C.Structure):
                 ("launches", C.c_uint32), ("steps_per_launch", C.c_uint32), ("warps", C.c_uint32),
                 ("tally_in_shared", C.c_uint32), ("image_bytes", C.c_uint64), ("plan_bytes", C.c_uint64),
                 ("tally_bytes", C.c_uint64), ("kernel", C.c_uint32), ("flight_cells", C.c_uint32),
-                ("lattice_cells", C.c_uint32), ("reserved", C.c_uint32)]
+                ("lattice_cells", C.c_uint32), ("lattice_recorded", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
