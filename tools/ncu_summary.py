@@ -20,7 +20,7 @@ CAPTURES = {
     "rec": ("queues_recorded_window", "bench workload, 36-step recorded window (tallies staged in shared memory, difference form)"),
     "per": ("queues_periodic_global", "linear_sides periodic, 1000 sensors: 128-step recorded window, tallies posted to global memory sector by sector"),
     "kinked": ("queues_kinked_long_window", "kinked wire (6174 cells -> 3150 flight cells -> 250 lattice cells), 1023-step unrecorded window over the lattice image"),
-    "kinked_rec": ("queues_kinked_recorded_window", "kinked wire, 128-step recorded window over the fine flight cells (3108 sensors: tallies posted to global memory)"),
+    "kinked_rec": ("queues_kinked_recorded_window", "kinked wire, 128-step recorded window over the lattice image (3108 sensors: every crossed measurement attributed to its sensor area, posted to global memory)"),
 }
 KEEP = {
     "gpu__time_duration.sum": "launch_ms_under_ncu",
