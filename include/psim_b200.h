@@ -196,7 +196,7 @@ int psim_gpu_get_stats(psim_gpu* h, psim_stats* out);
  * cell - where no sensor is read, a transition between two such cells changes nothing but the cell label;
  * 0: one flight cell per triangle; before set_sources),
  * "lattice_recorded" (recorded windows of many-sensor models over the lattice cells too, the sensor area of every measurement a
- * flight segment crossed being found from the phonon's position at that instant: -1 = default, where a phonon crosses two or
+ * flight segment crossed being found from the phonon's position at that instant: -1 = default, where a phonon crosses 1.25 or
  * more fine cells per measurement step at the model's largest group velocity; 0 never; 1 always; before set_sources),
  * "tally_shared" (-1 automatic = default; 0 straight to global memory, rows kept as differences along the step axis until
  * their window is complete; 1 / 4 / 2 staged per CTA in shared memory as two / three 32-bit parts / 64-bit sums - 1 and 4

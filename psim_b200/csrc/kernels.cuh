@@ -1,9 +1,11 @@
 // sm_100a kernels of the particle loop.  Included by psim_gpu.cu only.
 //
-// drift_kernel_queues<NS>  the drift step (default).  Persistent, one 24-warp CTA per SM, one pool segment per resident
+// drift_kernel_queues<NS, TALLY>  the drift step (default).  Persistent, one 24-warp CTA per SM, one pool segment per resident
 //                          warp; a warp keeps NS phonons in flight in shared memory and one queue of slot numbers per kind
 //                          of work (fly / intrinsic scatter / surface interaction / write back / fetch); a pass pops up
-//                          to 32 entries of the fullest queue, lane i takes the i-th.
+//                          to 32 entries of the fullest queue, lane i takes the i-th.  One instantiation per way a launch
+//                          window deals with its measurements: none recorded / staged per CTA in shared memory / posted
+//                          to global memory / the same over the lattice image (device_types.h).
 // drift_kernel_slots<K>    the version before: every lane owns K slots, the warp votes for the kind most lanes want.
 // drift_kernel_lockstep    the first version: tiles of 32 phonons, one per lane, in lock step.
 //                          Both kept for A/B measurements and as cross-checks: a phonon's random stream is addressed by

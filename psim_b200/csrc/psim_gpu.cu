@@ -308,7 +308,10 @@ size_t stage_budget(const psim_gpu* h) {
 constexpr int kStatWords = 8;                   // LaunchArgs::stats
 constexpr uint32_t kLongWindow = 1023;           // steps per launch while nothing is recorded (10 bits of step in the slot word)
 constexpr uint32_t kGlobalTallyWindow = 128;     // steps per launch when recorded tallies go straight to global memory
-constexpr double kLatticeRecordedCrossings = 2.0;  // fine cells crossed per step at the largest group velocity (see run_steps)
+// Fine cells crossed per measurement step at the largest group velocity from which recorded windows fly the lattice image
+// (run_steps).  Measured on linear_sides periodic with longer and longer steps (tools/gpu_lattice_threshold.py; fine / lattice
+// kernel ms): 0.46 cells per step 6.9 / 9.3, 0.93: 8.7 / 8.6, 1.85: 10.4 / 8.1, 2.8: 12.1 / 8.2, 3.7: 13.6 / 8.5.
+constexpr double kLatticeRecordedCrossings = 1.25;
 constexpr uint32_t kManySensors = 256;           // from here on global atomics are spread thinly enough to need no staging
 
 // Measurement intervals a launch may cover (its "window").

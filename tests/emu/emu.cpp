@@ -14,7 +14,7 @@
 // for the passes that record nothing
 static int g_merge_cells = 2;
 extern "C" void psim_emu_set_merge_cells(int level) { g_merge_cells = level; }
-// recorded passes over the lattice image: -1 the library's rule (many sensors, two or more fine cells crossed per step), 0 / 1
+// recorded passes over the lattice image: -1 the library's rule (many sensors, 1.25 or more fine cells crossed per step), 0 / 1
 static int g_lattice_recorded = -1;
 extern "C" void psim_emu_set_lattice_recorded(int v) { g_lattice_recorded = v; }
 
@@ -100,7 +100,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         const uint32_t s1 = std::min(s0 + B, M - 1);
         next.clear();
         const bool records = s1 + 1 > P.first_tally_step;
-        const bool lattice_recorded = g_lattice_recorded > 0 || (g_lattice_recorded < 0 && S >= 256u && img.lattice_cells_per_step >= 2.0);
+        const bool lattice_recorded = g_lattice_recorded > 0 || (g_lattice_recorded < 0 && S >= 256u && img.lattice_cells_per_step >= 1.25);
         const bool lattice_pass = have_lattice && (!records || lattice_recorded) && (pool_in_lattice || pool.empty());
         if (pool_in_lattice && !lattice_pass) {
             for (auto& p : pool) { psim::coarse_to_fine(PL.cells, PL.sub_fine, p.cell, p.b1, p.b2); }
