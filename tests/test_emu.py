@@ -353,3 +353,33 @@ def test_lattice_image_blocks_and_their_neutrality():
                 assert b["events"] < 0.9 * a["events"], name
     finally:
         lib.psim_emu_set_merge_cells(2)
+
+
+def test_recorded_passes_over_the_lattice_image_attribute_every_measurement_to_its_sensor():
+    """device_core.cuh:lattice_runs / lattice_sensor_at and flatten.cpp's sub_sensor table, on the CPU: with recorded passes
+    over the lattice image a flight segment spans several sensor areas and the area of every measurement it crossed is found
+    from the position at that instant.  Same seed with and without: the per-(sensor, step) tallies differ by rounding only
+    (a phonon within 1e-7 of a cell edge at a measurement) while far fewer segments are flown; the library's rule switches it
+    on for the kinked wire (4.9 fine cells per step at the largest group velocity) and leaves linear_sides alone (0.46)."""
+    import ctypes as C
+    from psim_b200 import configs
+    lib = T.emu_lib()
+    cases = [("sides_per", configs.linear_sides(sim_type=1, step_interval=4, num_phonons=20_000).to_dict(), 64, False)]
+    if "kinked_spec" in T.all_case_names():
+        cases.append(("kinked_spec", configs.with_settings(T.case_model("kinked_spec"), num_phonons=20_000), 128, True))
+    try:
+        for name, model_dict, spp, by_default in cases:
+            model = T.load_model(model_dict)
+            model.prepare()
+            runs = {}
+            for setting in (0, 1, -1):
+                lib.psim_emu_set_lattice_recorded(setting)
+                runs[setting] = T.emu_run(model, 2, steps_per_pass=spp)
+            off, on, auto = runs[0], runs[1], runs[-1]
+            assert np.array_equal(auto["energy"], (on if by_default else off)["energy"]), name
+            assert on["sources"] == off["sources"] and on["events"] < 0.85 * off["events"], name
+            e_on, e_off = on["energy"].astype(np.int64), off["energy"].astype(np.int64)
+            assert np.abs(e_on - e_off).sum() <= 0.01 * np.abs(e_off).sum(), name
+            assert np.abs(on["fixed"] - off["fixed"]).sum() <= 0.01 * np.abs(off["fixed"]).sum(), name
+    finally:
+        lib.psim_emu_set_lattice_recorded(-1)
