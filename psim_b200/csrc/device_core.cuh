@@ -604,7 +604,7 @@ PSIM_HD bool rates_differ(uint32_t cell_word_a, uint32_t cell_word_b) {
 // `track_sensor`: the caller keeps f.sensor_mat current across segments (false: it reloads it from the cell record).
 PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 links, const uint2 tail, bool& reflected, const bool track_sensor) {
     reflected = false;
-    if (f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
+    if (!(P.fast_links | PSIM_FAST_WALLS) || f.ncoll >= PSIM_MAX_COLLISIONS) { return false; }
     uint32_t link = link_of_edge(links, f.edge);
     const uint32_t kind = PSIM_LINK_KIND(link);
     float s_in;  // where on the neighbour's edge the phonon enters
@@ -655,6 +655,7 @@ PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f, const uint4 l
 }
 PSIM_HD bool fast_impact(const DevParams& P, Phonon& p, Flight& f) {
     bool reflected;
+    if (!(P.fast_links | PSIM_FAST_WALLS)) { return false; }  // (before the cell record is loaded for it)
     return fast_impact(P, p, f, load_cell_links(P.cells, PSIM_CELL_INDEX(p.cell)), load_cell_tail(P.cells, PSIM_CELL_INDEX(p.cell)), reflected, true);
 }
 

@@ -200,6 +200,9 @@ struct DevParams {
     uint32_t full_mode;        // t_eq == 0: bin-centre frequencies, no jitter (material.cpp:77-80)
     uint32_t phasor;           // phasor_sim: no intrinsic scattering (modelSimulator.cpp:189)
     uint32_t lattice;          // cells / shapes / api_cells / subs / emitters are those of the lattice image
+    uint32_t fast_links;       // some edge of this image can be handled by the flight loop's fast path (fast_impact); 0: the flight
+                               // loop does not even try (the lattice image of a mesh that is ONE block per material: every impact
+                               // is a wall, an emitter or a material interface)
     float step_time;           // ns
     float step_time_inv;
     double step_time_d;

@@ -29,7 +29,10 @@ bool fail(std::string& err, int code, const std::string& msg, int& rc) {
 // perfectly specular, which composite edges have a transition into a cell of the same material and rate class behind them,
 // and which transitions lead into a cell with the SAME shape record, material and rate class (PSIM_LINK_SAME_FRAME: the
 // phonon's rates of motion and relaxation rates are the same on the other side, nothing has to be loaded to go on).
-void mark_fast_links(std::vector<DevCell>& cells, const std::vector<DevShape>& shapes, std::vector<DevSub>& subs) {
+// Returns whether the image has any edge the fast path can take (a transition into a cell of the same material and rate
+// class, whole-edge or behind a composite edge).
+bool mark_fast_links(std::vector<DevCell>& cells, const std::vector<DevShape>& shapes, std::vector<DevSub>& subs) {
+    bool any_fast = false;
     for (DevCell& c : cells) {
         const bool classified = PSIM_CELL_CLASS(c.sensor_mat) != 255u;
         auto same_rates = [&](uint32_t lw) { return classified && ((cells[PSIM_LINK_TARGET(lw)].sensor_mat ^ c.sensor_mat) & 0xFFFu) == 0u; };
@@ -43,6 +46,7 @@ void mark_fast_links(std::vector<DevCell>& cells, const std::vector<DevShape>& s
                 c.link[e] = (PSIM_LINK_BOUNDARY << 30) | (shapes[c.shape].spec >= 1.f ? 1u : 0u);
             } else if (PSIM_LINK_KIND(w) == PSIM_LINK_TRANSITION) {
                 c.link[e] = transition(w);
+                any_fast |= same_rates(w);
             } else if (PSIM_LINK_KIND(w) == PSIM_LINK_COMPOSITE) {
                 const uint32_t first = (w >> 7) & 0xFFFFFu, n = w & 0x7Fu;
                 bool any = false;
@@ -53,9 +57,11 @@ void mark_fast_links(std::vector<DevCell>& cells, const std::vector<DevShape>& s
                     lw = transition(lw);
                 }
                 c.link[e] = (w & ~(1u << 27)) | (any ? (1u << 27) : 0u);
+                any_fast |= any;
             }
         }
     }
+    return any_fast;
 }
 
 struct Frame {
@@ -777,8 +783,9 @@ int flatten_model(const psim_model_desc& d, HostImage& out, std::string& err, in
     P.step_time_inv = static_cast<float>(1. / step_time);
     P.step_time_d = step_time;
     if (merge_cells >= 2) { build_lattices(out, frames); }
-    mark_fast_links(out.cells, out.shapes, out.subs);
-    mark_fast_links(out.lattice_cells, out.lattice_shapes, out.lattice_subs);
+    out.fast_links = mark_fast_links(out.cells, out.shapes, out.subs);
+    out.lattice_fast_links = mark_fast_links(out.lattice_cells, out.lattice_shapes, out.lattice_subs);
+    P.fast_links = out.fast_links ? 1u : 0u;
     return 0;
 }
 

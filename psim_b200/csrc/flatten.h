@@ -31,6 +31,7 @@ struct HostImage {
     // cells that are part of a block (0 without lattice image): where it is large, flying the lattice image pays in recorded
     // windows too (psim_gpu.cu)
     double lattice_cells_per_step = 0.;
+    bool fast_links = true, lattice_fast_links = true;  // DevParams::fast_links of either image
     std::vector<DevSensor> sensors;
     std::vector<DevMaterial> materials;
     std::vector<DevEmitter> emitters;

@@ -845,7 +845,8 @@ __global__ void __launch_bounds__(kBlock, kSlotBlocks) drift_kernel_queues(const
                 }
                 if (hit) {
                     f.sensor_mat = tail0.x;
-                    if (psim::fast_impact(P, p, f, psim::load_cell_links(P.cells, PSIM_CELL_INDEX(cell0)), tail0, reflected, false)) {
+                    // (an image without any edge the fast path could take - DevParams::fast_links - does not load the links for it)
+                if ((P.fast_links | PSIM_FAST_WALLS) && psim::fast_impact(P, p, f, psim::load_cell_links(P.cells, PSIM_CELL_INDEX(cell0)), tail0, reflected, false)) {
                         misc += 1u << 10;  // one more impact since the last scatter (< PSIM_MAX_COLLISIONS here)
                         dest = Q_FLY;
                     } else {

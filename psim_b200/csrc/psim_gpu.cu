@@ -387,6 +387,7 @@ int upload_geometry(psim_gpu* h, const psim::HostImage& g) {
     h->P.emitters = static_cast<const DevEmitter*>(h->d_emitters);
     h->P.n_flight_cells = static_cast<uint32_t>(g.cells.size());
     h->P.n_shapes = static_cast<uint32_t>(g.shapes.size());
+    h->P.fast_links = g.fast_links ? 1u : 0u;
     return 0;
 }
 
@@ -422,6 +423,7 @@ DevParams lattice_params(const psim_gpu* h) {
     L.n_flight_cells = static_cast<uint32_t>(h->img.lattice_cells.size());
     L.n_shapes = static_cast<uint32_t>(h->img.lattice_shapes.size());
     L.lattice = 1u;
+    L.fast_links = h->img.lattice_fast_links ? 1u : 0u;
     return L;
 }
 

@@ -61,6 +61,7 @@ extern "C" int psim_emu_run(const psim_model_desc* desc, const psim_source* sour
         PL.sub_fine = img.lattice_sub_fine.data();
         PL.sub_sensor = img.lattice_sub_sensor.data();
         PL.lattice = 1u;
+        PL.fast_links = img.lattice_fast_links ? 1u : 0u;
     }
     const DevParams PF = P;
     bool pool_in_lattice = false;
