@@ -4,6 +4,7 @@ In-tree on purpose: the built library travels with the repository snapshot to th
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -31,11 +32,27 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _stale(target: str, deps) -> bool:
-    if not os.path.exists(target):
+def _digest(deps, cmd) -> str:
+    h = hashlib.sha256(" ".join(cmd).encode())
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read() if os.path.exists(d) else b"<absent>")
+    return h.hexdigest()
+
+
+def _stale(target: str, deps, cmd) -> bool:
+    """By CONTENT, not by mtime: <target>.srchash holds the hash of the inputs and of the command line the target was
+    built from, so a checkout, a copy or a touched file can neither hide a change nor force a rebuild."""
+    try:
+        return not os.path.exists(target) or open(target + ".srchash").read().strip() != _digest(deps, cmd)
+    except OSError:
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _run(target: str, deps, cmd) -> None:
+    subprocess.run(cmd, check=True)
+    with open(target + ".srchash", "w") as f:
+        f.write(_digest(deps, [c for c in cmd if c not in ("-Xptxas", "-v")]) + "\n")
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -43,17 +60,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BIN_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    if force or _stale(LIB, deps):
-        cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-shared",
-               "-o", LIB, *srcs, "-ldl"]
-        if verbose:
-            cmd.insert(1, "-Xptxas")
-            cmd.insert(2, "-v")
-        subprocess.run(cmd, check=True)
+    cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-shared",
+           "-o", LIB, *srcs, "-ldl"]
+    if force or _stale(LIB, deps, cmd):
+        _run(LIB, deps, cmd if not verbose else cmd[:1] + ["-Xptxas", "-v"] + cmd[1:])
     main_src = os.path.join(CSRC, "host", "main.cpp")
-    if force or _stale(CLI, [main_src, LIB]):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-o", CLI, main_src, "-L" + LIB_DIR, "-lpsim_b200",
-                        "-Wl,-rpath,$ORIGIN/../lib"], check=True)
+    cli_deps = [main_src, os.path.join(ROOT, "include", "psim_host.h"), LIB + ".srchash"]
+    cli_cmd = ["g++", "-O2", "-std=c++17", "-o", CLI, main_src, "-L" + LIB_DIR, "-lpsim_b200",
+               "-Wl,-rpath,$ORIGIN/../lib"]
+    if force or _stale(CLI, cli_deps, cli_cmd):
+        _run(CLI, cli_deps, cli_cmd)
     return LIB
 
 
@@ -74,10 +90,11 @@ def build_emu(force: bool = False) -> str:
     src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
     deps = [src, os.path.join(CSRC, "device_core.cuh"), os.path.join(CSRC, "device_types.h"),
             os.path.join(CSRC, "flatten.cpp"), os.path.join(CSRC, "flatten.h")]
-    if force or _stale(EMU, deps):
-        cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
-                        "-I" + cuda_inc, "-o", EMU, src, os.path.join(CSRC, "flatten.cpp")], check=True)
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
+           "-I" + cuda_inc, "-o", EMU, src, os.path.join(CSRC, "flatten.cpp")]
+    if force or _stale(EMU, deps, cmd):
+        _run(EMU, deps, cmd)
     return EMU
 
 
