@@ -33,7 +33,16 @@ def _nvcc() -> str:
 
 
 def _digest(deps, cmd) -> str:
-    h = hashlib.sha256(" ".join(cmd).encode())
+    # the command line without where the tree or the toolkit happen to live (the GPU box runs a copy under another path)
+    def place_free(word: str) -> str:
+        flag = word[:2] if word[:2] in ("-I", "-L") else ""
+        path = word[len(flag):]
+        if path.startswith(ROOT + os.sep):
+            return flag + os.path.relpath(path, ROOT)
+        return flag + (os.path.basename(path) if os.path.isabs(path) else path)
+
+    words = [place_free(c) for c in cmd]
+    h = hashlib.sha256(" ".join(words).encode())
     for d in deps:
         h.update(os.path.basename(d).encode())
         h.update(open(d, "rb").read() if os.path.exists(d) else b"<absent>")
