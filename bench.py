@@ -18,8 +18,9 @@ ranks.  Besides the headline the line carries
   weak        the same job with 1e8 phonons PER GPU (N > 1 only; at N = 1 it is the headline)
   models      wall-clock per shipped model at its full phonon count (N = 1), next to the reference's own headers
   roofline    what bounds the kernel: instruction issue (warp instructions per drift-step from the committed ncu captures,
-              used only while profiles/r02_ncu_summary.json carries the hash of the kernel sources it was taken on) and the
-              measured DRAM traffic against the HBM peak
+              used only while profiles/r02_ncu_summary.json carries the hash of the device sources it was taken on and
+              the job that runs has the captured job's launches and segments per drift-step) and the measured DRAM traffic
+              against the HBM peak
 """
 from __future__ import annotations
 
@@ -54,24 +55,50 @@ def workload_model(num_phonons: int) -> dict:
     return configs.si_ge_grid(num_phonons=num_phonons).to_dict()
 
 
-def csrc_sha16() -> str:
-    """Hash of the kernel / host sources: profiles/*_ncu_summary.json records the value it was captured on, and the
-    ncu-derived constants are used only while it matches the tree that is running."""
+# what decides the work of the kernels: the device code, its launcher and the builder of the device images (the host layer
+# under csrc/host/ - loader, run epilogue, exporter - only feeds them a model description)
+DEVICE_SOURCES = ("device_core.cuh", "device_types.h", "flatten.cpp", "flatten.h", "kernels.cuh", "psim_gpu.cu")
+
+
+def _sha16(paths, base) -> str:
     h = hashlib.sha256()
-    base = os.path.join(ROOT, "psim_b200", "csrc")
-    for dirpath, _, files in sorted(os.walk(base)):
-        for f in sorted(files):
-            p = os.path.join(dirpath, f)
-            h.update(os.path.relpath(p, base).encode())
-            h.update(open(p, "rb").read())
+    for p in paths:
+        h.update(os.path.relpath(p, base).encode())
+        h.update(open(p, "rb").read())
     return h.hexdigest()[:16]
 
 
-def ncu_constants():
-    """profiles/r02_ncu_summary.json if it was captured on THIS source tree, else None (never a stale constant)."""
+def csrc_sha16() -> str:
+    """Hash of every source of the library (kernels, C ABI, host layer)."""
+    base = os.path.join(ROOT, "psim_b200", "csrc")
+    return _sha16([os.path.join(d, f) for d, _, files in sorted(os.walk(base)) for f in sorted(files)], base)
+
+
+def device_sha16() -> str:
+    """Hash of DEVICE_SOURCES: profiles/*_ncu_summary.json records the value its counters were taken on, and the ncu-derived
+    constants are used only while it matches the tree that is running (and the job that runs matches the captured one,
+    `ncu_constants`)."""
+    base = os.path.join(ROOT, "psim_b200", "csrc")
+    return _sha16([os.path.join(base, f) for f in DEVICE_SOURCES], base)
+
+
+def ncu_constants(launches=None, segments_per_drift_step=None, phonons_total=None):
+    """profiles/r02_ncu_summary.json if it was captured on THESE device sources and describes THIS job - the same phonons in
+    total, the same number of launches, the same flight segments per drift-step to 0.5 % (counted live by the run: a change
+    anywhere that altered the kernels' work would show there) - else None (never a stale constant)."""
     try:
         d = json.load(open(NCU_SUMMARY))
-        return d if d.get("csrc_sha16") == csrc_sha16() else None
+        if d.get("device_sha16") != device_sha16():
+            return None
+        if phonons_total is not None and int(phonons_total) != int(d["phonons_per_gpu"]):  # captured on one GPU
+            return None
+        j = d["bench_job"]
+        if launches is not None and int(launches) != int(j["launches"]):
+            return None
+        captured = j["segments_per_job"] / j["drift_steps_per_job"]
+        if segments_per_drift_step is not None and abs(segments_per_drift_step / captured - 1.0) > 5e-3:
+            return None
+        return d
     except Exception:
         return None
 
@@ -470,6 +497,7 @@ def model_walltimes(device: int):
             t0 = time.perf_counter()
             m = psim.Model(path)
             t1 = time.perf_counter()
+            load_ms = (t1 - t0) * 1e3          # JSON -> model: parse, mesh validation, neighbour discovery
             st = m.run(device=device, seed=1)  # psim_model_run: device image + pool set-up, H2D, kernels, D2H, run epilogue
             t2 = time.perf_counter()
             first_ms = (t2 - t1) * 1e3
@@ -485,7 +513,7 @@ def model_walltimes(device: int):
             t3 = time.perf_counter()
             k_ms = st.kernel_ms
             rec = {"model": name, "phonons": int(st.total_phonons), "cells": int(m.info.num_cells), "sensors": int(m.info.num_sensors),
-                   "measurement_steps": int(m.info.measurement_steps), "sim_type": int(m.info.sim_type), "load_ms": round((t1 - t0) * 1e3, 2),
+                   "measurement_steps": int(m.info.measurement_steps), "sim_type": int(m.info.sim_type), "load_ms": round(load_ms, 2),
                    "ms_e2e": round((t2 - t1) * 1e3, 2), "ms_e2e_first_run": round(first_ms, 2), "export_ms": round((t3 - t2) * 1e3, 2), "kernel_ms": round(k_ms, 2), "launches": int(st.launches),
                    "drift_steps": int(st.drift_steps), "segments": int(st.events),
                    "drift_steps_per_s": st.drift_steps / (k_ms * 1e-3), "segments_per_s": st.events / (k_ms * 1e-3),
@@ -549,7 +577,7 @@ def run_ours(args):
         stats = main["stats"]
         launches_per_job = max(1, stats["launches"])
         auto = args.steps_per_launch == 0 and args.kernel < 0 and args.tally_shared < 0 and args.warps_per_sm <= 0
-        ncu = ncu_constants() if auto else None
+        ncu = ncu_constants(launches_per_job, main["events"] / total_drift, total) if auto else None
         peak_issue = 148 * 4 * sm_mhz * 1e6
         roof = {"bound": "issue", "unit": "warp-inst/s", "peak": peak_issue, "achieved": None, "frac": None, "traffic": None,
                 "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
@@ -562,7 +590,7 @@ def run_ours(args):
                         "note": "achieved = DRAM bytes per job measured by ncu (dram__bytes_read + write over the job's launches) / live kernel "
                                 "time.  algorithmic_ratio = 64 B x drift-steps / kernel time / peak (SURVEY 8d's accounting) is NOT a roofline "
                                 "fraction: a launch keeps a phonon on chip for a whole window of measurement steps"},
-                "ncu": ("profiles/r02_ncu_summary.json (csrc_sha16 matches this tree)" if ncu else
+                "ncu": ("profiles/r02_ncu_summary.json (device_sha16 matches this tree; launches and segments per drift-step of this job match the captured one)" if ncu else
                         "ncu-derived fields are null: no capture of this source tree / configuration is committed")}
         if ncu:
             j = ncu["bench_job"]
@@ -595,6 +623,7 @@ def run_ours(args):
             "weak": weak,
             "stats": stats,
             "csrc_sha16": csrc_sha16(),
+            "device_sha16": device_sha16(),
         }
         if world == 1 and not args.no_models:
             out["models"] = model_walltimes(env.local)

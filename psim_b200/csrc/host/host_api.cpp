@@ -383,11 +383,16 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
     psim::Model& m = *pm->m;
     const size_t G = static_cast<size_t>(n_devices);
     std::vector<psim_gpu*> gpus(G, nullptr);
+    const auto t_call = std::chrono::steady_clock::now();
     const int rc = guarded(PSIM_E_STATE, [&]() -> int {
         m.runs.clear();
         // every call starts from the state of the model file: a steady-state run leaves its final temperatures in the
         // sensors (Model::resetRequired, model.cpp:250-272), which a second call on the same handle must not inherit
         m.restore_file_state();
+        if (std::getenv("PSIM_TIMING")) {
+            std::cerr << "psim timing [ms]: results of the call before dropped "
+                      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count() << '\n';
+        }
         // several devices: their tallies are summed with one NCCL all-reduce per run over NVLink (integers: the result is the
         // one-device result bit for bit); without a usable NCCL the same integers are summed on the host
         std::unique_ptr<TallyExchange> exchange;
@@ -422,9 +427,10 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
             // the host layer wants them (psim_gpu_get_tallies transposes and converts there).  Only the host-side sum of
             // several devices needs the exact fixed-point integers of each.
             const bool host_sum = G > 1 && !use_nccl;
-            std::vector<std::vector<int32_t>> energy(host_sum ? G : 1, std::vector<int32_t>(n_tally));
+            // They are written straight into the model's own tally storage, which lives from run to run.
+            const auto [energy_out, flux_out] = m.tally_storage();
+            std::vector<std::vector<int32_t>> energy(host_sum ? G : 0, std::vector<int32_t>(host_sum ? n_tally : 0));
             std::vector<std::vector<int64_t>> fixed(host_sum ? G : 0, std::vector<int64_t>(host_sum ? 2 * n_tally : 0));
-            std::vector<double> flux(2 * n_tally);
             std::vector<psim_stats> st(G);
             std::vector<int> codes(G, PSIM_OK);
             std::vector<std::string> errors(G);
@@ -448,7 +454,7 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                 if (!e) { e = psim_gpu_run(gpus[d]); }
                 const auto t3 = now();
                 if (!e && host_sum) { e = psim_gpu_get_tallies(gpus[d], energy[d].data(), nullptr, fixed[d].data()); }
-                if (!e && G == 1) { e = psim_gpu_get_tallies(gpus[0], energy[0].data(), flux.data(), nullptr); }
+                if (!e && G == 1) { e = psim_gpu_get_tallies(gpus[0], energy_out, flux_out, nullptr); }
                 if (!e) { e = psim_gpu_get_stats(gpus[d], &st[d]); }
                 if (timing && d == 0) {
                     std::cerr << "psim timing [ms]: create " << ms(t0, t1) << " set_sources " << ms(t1, t2) << " run " << ms(t2, t3)
@@ -476,7 +482,7 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     g_error = err;
                     return PSIM_E_CUDA;
                 }
-                if (const int e = psim_gpu_get_tallies(gpus[0], energy[0].data(), flux.data(), nullptr)) {  // device 0 holds the sum
+                if (const int e = psim_gpu_get_tallies(gpus[0], energy_out, flux_out, nullptr)) {  // device 0 holds the sum
                     g_error = psim_gpu_last_error(gpus[0]);
                     return e;
                 }
@@ -492,9 +498,9 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     fx += fixed[d][2 * i];
                     fy += fixed[d][2 * i + 1];
                 }
-                energy[0][i] = static_cast<int32_t>(e);
-                flux[2 * i] = static_cast<double>(fx) / 256.;
-                flux[2 * i + 1] = static_cast<double>(fy) / 256.;
+                energy_out[i] = static_cast<int32_t>(e);
+                flux_out[2 * i] = static_cast<double>(fx) / 256.;
+                flux_out[2 * i + 1] = static_cast<double>(fy) / 256.;
             }
             if (stats) {
                 *stats = st[0];
@@ -506,8 +512,14 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
                     stats->kernel_ms = std::max(stats->kernel_ms, st[d].kernel_ms);
                 }
             }
-            m.set_tallies(energy[0].data(), flux.data());
-            if (!m.end_iteration(&log)) { break; }
+            m.tallies_written();
+            const auto h_end = std::chrono::steady_clock::now();
+            const bool again = m.end_iteration(&log);
+            if (std::getenv("PSIM_TIMING")) {
+                std::cerr << "psim timing [ms]: end of iteration "
+                          << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h_end).count() << '\n';
+            }
+            if (!again) { break; }
             }  // iterations
             const auto h1 = std::chrono::steady_clock::now();
             m.finish_run(run, &log);
@@ -524,7 +536,8 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
     for (psim_gpu* g : gpus) { psim_gpu_destroy(g); }
     if (std::getenv("PSIM_TIMING")) {
         std::cerr << "psim timing [ms]: destroy "
-                  << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_destroy).count() << '\n';
+                  << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_destroy).count() << "  whole call "
+                  << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count() << '\n';
     }
     return rc;
 }

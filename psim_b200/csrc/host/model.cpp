@@ -11,6 +11,7 @@
 #include <numeric>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 
 namespace psim {
@@ -126,14 +127,6 @@ uint64_t splitmix64(uint64_t x) {
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
-}
-
-std::pair<double, double> mean_and_std_error(const std::vector<double>& v) {  // sensorInterpreter.cpp:34-46
-    const double n = static_cast<double>(v.size());
-    const double avg = std::accumulate(v.begin(), v.end(), 0.) / n;
-    double ss = 0.;
-    for (double x : v) { ss += (avg - x) * (avg - x); }
-    return { avg, std::sqrt(ss / n) / std::sqrt(n) };
 }
 
 }  // namespace
@@ -599,25 +592,60 @@ std::vector<psim_source> Model::source_counts(uint64_t seed) {
     return out;
 }
 
-void Model::set_tallies(const int32_t* energy, const double* flux) {
-    const size_t S = sensors.size(), R = recorded_steps;
+std::pair<int32_t*, double*> Model::tally_storage() {
+    const size_t n = sensors.size() * recorded_steps;
+    have_tallies_ = false;
+    if (inc_energy_.size() != n) {
+        inc_energy_.resize(n);
+        inc_flux_.resize(2 * n);
+    }
+    return { inc_energy_.data(), inc_flux_.data() };
+}
+
+void Model::tallies_written() {
+    have_tallies_ = true;
     iteration_ended_ = false;
-    inc_energy_.resize(S);
-    inc_flux_.resize(S);
-    for (size_t s = 0; s < S; ++s) {
-        inc_energy_[s].assign(energy + s * R, energy + (s + 1) * R);
-        inc_flux_[s].resize(R);
-        for (size_t r = 0; r < R; ++r) { inc_flux_[s][r] = { flux[2 * (s * R + r)], flux[2 * (s * R + r) + 1] }; }
+}
+
+void Model::set_tallies(const int32_t* energy, const double* flux) {
+    const auto [e, f] = tally_storage();
+    const size_t n = sensors.size() * recorded_steps;
+    std::copy(energy, energy + n, e);
+    std::copy(flux, flux + 2 * n, f);
+    tallies_written();
+}
+
+template <class F> void Model::for_each_sensor(F&& f) {
+    const size_t S = sensors.size();
+    size_t threads = std::min<size_t>({ std::max(1u, std::thread::hardware_concurrency()), 16, S * recorded_steps / 65536 });
+    if (const char* cap = std::getenv("PSIM_HOST_THREADS")) { threads = std::min<size_t>(threads, std::strtoul(cap, nullptr, 10)); }
+    if (t_eq == 0.) { threads = 1; }  // Material::table() builds its tables on first use
+    if (threads <= 1) {
+        for (size_t si = 0; si < S; ++si) { f(si); }
+        return;
+    }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> errors(threads);
+    for (size_t t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t] {
+            try {
+                for (size_t si = S * t / threads; si < S * (t + 1) / threads; ++si) { f(si); }
+            } catch (...) { errors[t] = std::current_exception(); }
+        });
+    }
+    for (auto& t : pool) { t.join(); }
+    for (const auto& e : errors) {
+        if (e) { std::rethrow_exception(e); }
     }
 }
 
 std::vector<double> Model::find_temperature(size_t si, size_t start) {
     const SensorRec& s = sensors[si];
-    const auto& energies = inc_energy_[si];
-    std::vector<double> temps(energies.size() - start);
+    const int32_t* energies = inc_energy_.data() + si * recorded_steps;
+    std::vector<double> temps(recorded_steps - start);
     Material& mat = materials[s.material];
     size_t index = 0;
-    for (size_t r = start; r < energies.size(); ++r) {
+    for (size_t r = start; r < recorded_steps; ++r) {
         const double energy = eff_energy_ * energies[r];
         if (t_eq != 0.) {
             temps[r - start] = energy / (s.area * heat_capacity_at(s, index++)) + t_eq;
@@ -642,33 +670,49 @@ SensorResult Model::scale_heat_params(size_t si) {
     sm.final_temps = find_temperature(si, 0);
     sm.final_temps.front() = init_temp(s);
     const double f = eff_energy_ / s.area;
-    sm.final_fluxes.resize(inc_flux_[si].size());
-    std::vector<double> fx(sm.final_fluxes.size()), fy(sm.final_fluxes.size());
-    for (size_t r = 0; r < sm.final_fluxes.size(); ++r) {
-        sm.final_fluxes[r] = { inc_flux_[si][r][0] * f, inc_flux_[si][r][1] * f };
-        fx[r] = sm.final_fluxes[r][0];
-        fy[r] = sm.final_fluxes[r][1];
+    const size_t R = recorded_steps;
+    const double* flux = inc_flux_.data() + 2 * si * R;
+    sm.final_fluxes.resize(R);
+    for (size_t r = 0; r < R; ++r) { sm.final_fluxes[r] = { flux[2 * r] * f, flux[2 * r + 1] * f }; }
+    // mean and standard error of the three columns (sensorInterpreter.cpp:34-46): every sum runs over the steps in order,
+    // as the reference's does, the three of them side by side
+    const double n = static_cast<double>(R);
+    double st = 0., sx = 0., sy = 0.;
+    for (size_t r = 0; r < R; ++r) {
+        st += sm.final_temps[r];
+        sx += sm.final_fluxes[r][0];
+        sy += sm.final_fluxes[r][1];
     }
-    std::tie(sm.t_steady, sm.std_t_steady) = mean_and_std_error(sm.final_temps);
-    std::tie(sm.x_flux, sm.std_x_flux) = mean_and_std_error(fx);
-    std::tie(sm.y_flux, sm.std_y_flux) = mean_and_std_error(fy);
+    const double at = st / n, ax = sx / n, ay = sy / n;
+    double qt = 0., qx = 0., qy = 0.;
+    for (size_t r = 0; r < R; ++r) {
+        qt += (at - sm.final_temps[r]) * (at - sm.final_temps[r]);
+        qx += (ax - sm.final_fluxes[r][0]) * (ax - sm.final_fluxes[r][0]);
+        qy += (ay - sm.final_fluxes[r][1]) * (ay - sm.final_fluxes[r][1]);
+    }
+    sm.t_steady = at;
+    sm.std_t_steady = std::sqrt(qt / n) / std::sqrt(n);
+    sm.x_flux = ax;
+    sm.std_x_flux = std::sqrt(qx / n) / std::sqrt(n);
+    sm.y_flux = ay;
+    sm.std_y_flux = std::sqrt(qy / n) / std::sqrt(n);
     return sm;
 }
 
 bool Model::end_iteration(std::string* log) {
-    if (inc_energy_.size() != sensors.size()) { throw std::runtime_error("end of an iteration without tallies"); }
+    if (!have_tallies_) { throw std::runtime_error("end of an iteration without tallies"); }
     ++iter_;
     // Model::resetRequired, model.cpp:250-272 - note its side effect on every sensor's steady temperature
-    int stable = 0;
-    for (size_t si = 0; si < sensors.size(); ++si) {
+    std::vector<char> is_stable(sensors.size(), 0);
+    for_each_sensor([&](size_t si) {
         SensorRec& s = sensors[si];
         if (sim_type != SimType::Transient) {
             double t_final = 0.;
             if (s.area != 0.) {
                 const auto temps = find_temperature(si, start_step);
-                t_final = std::accumulate(temps.begin(), temps.end(), 0.) / static_cast<double>(inc_energy_[si].size() - start_step);
+                t_final = std::accumulate(temps.begin(), temps.end(), 0.) / static_cast<double>(recorded_steps - start_step);
             }
-            if (std::fabs(t_final - s.t_steady) / s.t_steady <= SENSOR_RESET_THRESHOLD) { ++stable; }
+            is_stable[si] = std::fabs(t_final - s.t_steady) / s.t_steady <= SENSOR_RESET_THRESHOLD;
             s.t_steady = t_final;
         } else {
             auto temps = find_temperature(si, 0);
@@ -676,10 +720,11 @@ bool Model::end_iteration(std::string* log) {
             for (size_t r = 0; r < temps.size(); ++r) {
                 if (!(std::fabs(temps[r] - s.steady_temps[r]) / s.steady_temps[r] <= TRANSIENT_RESET_THRESHOLD)) { ok = false; }
             }
-            if (ok) { ++stable; }
+            is_stable[si] = ok;
             s.steady_temps = std::move(temps);
         }
-    }
+    });
+    const int stable = static_cast<int>(std::count(is_stable.begin(), is_stable.end(), 1));
     stable_ = stable;
     if (log) { *log += "Stable sensors: " + std::to_string(stable) + "\n"; }
     // avgTemp(), model.cpp:230-239: area-weighted getSteadyTemp() of the sensors
@@ -726,12 +771,11 @@ void Model::reset_iteration() {
             break;
         }
     }
-    inc_energy_.clear();
-    inc_flux_.clear();
+    have_tallies_ = false;
 }
 
 int Model::finish_run(uint64_t run_id, std::string* log) {
-    if (inc_energy_.size() != sensors.size() && !iteration_ended_) { throw std::runtime_error("finish_run without tallies"); }
+    if (!have_tallies_) { throw std::runtime_error("finish_run without tallies"); }
     if (!iteration_ended_) {
         // a caller that drives one iteration per run (the reference's MAX_ITERS = 1)
         const uint64_t keep = max_iters;
@@ -739,9 +783,8 @@ int Model::finish_run(uint64_t run_id, std::string* log) {
         end_iteration(log);
         max_iters = keep;
     }
-    std::vector<SensorResult> res;
-    res.reserve(sensors.size());
-    for (size_t si = 0; si < sensors.size(); ++si) { res.push_back(scale_heat_params(si)); }
+    std::vector<SensorResult> res(sensors.size());
+    for_each_sensor([&](size_t si) { res[si] = scale_heat_params(si); });
     std::sort(res.begin(), res.end(), [](const SensorResult& a, const SensorResult& b) { return a.id < b.id; });
     if (runs.size() <= run_id) { runs.resize(run_id + 1); }
     runs[run_id] = std::move(res);
@@ -753,8 +796,7 @@ void Model::reset_for_next_run() {
         s.t_steady = s.t_init;  // controller reset(full_reset = true), sensorController.cpp:64-78,101-113
         if (sim_type == SimType::Transient) { s.steady_temps.assign(measurement_steps, s.t_init); }
     }
-    inc_energy_.clear();
-    inc_flux_.clear();
+    have_tallies_ = false;
     prepared_ = false;
 }
 

@@ -132,6 +132,10 @@ public:
     void refresh();                                   // the `refresh` lambda, model.cpp:148-153
     std::vector<psim_source> source_counts(uint64_t seed);   // initPhononBuilders' integer bookkeeping
     void set_tallies(const int32_t* energy, const double* flux);   // [S][R], [S][R][2] (what the hot path produced)
+    // The same without the copy: the model's own tally storage ([S][R] energies, [S][R][2] fluxes; kept from run to run, so
+    // the 31 MB of a 3108-sensor model are allocated and paged in once) for the caller to fill, then tallies_written().
+    std::pair<int32_t*, double*> tally_storage();
+    void tallies_written();
     // End of one simulated iteration (model.cpp:163-171): resetRequired(); if the sensors or t_eq moved and max_iters
     // allows another iteration, reset(false) - tallies cleared, tables and heat capacities at the new temperatures - and the
     // new t_eq; then refresh().  Returns true if the run must be simulated again (with a fresh describe()).
@@ -162,8 +166,9 @@ private:
     uint64_t iter_ = 0;             // iterations of the current run simulated so far
     int stable_ = 0;
     std::vector<psim_sensor> d_step_sensors_;
-    std::vector<std::vector<int32_t>> inc_energy_;                  // [S][R]
-    std::vector<std::vector<std::array<double, 2>>> inc_flux_;      // [S][R]
+    std::vector<int32_t> inc_energy_;   // [S][R]     Sensor::inc_energy_ of every sensor, flat
+    std::vector<double> inc_flux_;      // [S][R][2]  Sensor::inc_flux_
+    bool have_tallies_ = false;
 
     // describe() storage
     psim_model_desc desc_{};
@@ -187,6 +192,9 @@ private:
     void reset_iteration();                                                   // Model::reset(false), model.cpp:274-283
     double init_temp(const SensorRec& s) const;
     std::vector<double> find_temperature(size_t sensor, size_t start_step);   // sensorInterpreter.cpp:80-112
+    // f(sensor) for every sensor, on several threads where the tallies are large and f touches nothing but its own sensor
+    // and the tallies (full mode inverts through the materials' lazily built tables: one thread)
+    template <class F> void for_each_sensor(F&& f);
     SensorResult scale_heat_params(size_t sensor);                            // sensorInterpreter.cpp:19-66
 };
 

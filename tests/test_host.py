@@ -155,6 +155,37 @@ def test_run_epilogue_matches_oracle(name, built_library):
         assert m.energy_per_phonon == pytest.approx(pre, rel=1e-12)
 
 
+@pytest.mark.parametrize("name", ["sides_per", "sides_trans", "kinked_spec"])
+def test_epilogue_on_several_threads_gives_the_same_bytes(name, built_library, monkeypatch):
+    """The run epilogue goes over the sensors on several threads where the tallies are large (1000 sensors x 1000 recorded
+    steps here; `Model::for_each_sensor`); every sensor's sums still run over its steps in order, so the stable-sensor count,
+    the re-iteration decision and every number of the results are those of one thread, bit for bit."""
+    model = T.case_model(name)
+    out = {}
+    for threads in ("1", "7"):
+        monkeypatch.setenv("PSIM_HOST_THREADS", threads)
+        m = T.load_model(model, num_phonons=1000)
+        m.set_max_iters(2)
+        S, R = m.info.num_sensors, m.info.recorded_steps
+        assert S * R >= 2 * 65536
+        rng = np.random.default_rng(11)
+        m.prepare()
+        got = []
+        for _ in range(2):
+            m.describe()
+            m.set_tallies(rng.integers(-4000, 4000, (S, R)).astype(np.int32), rng.normal(0, 1e6, (S, R, 2)))
+            again = m.end_iteration()
+            got.append(bytes([again]))
+            if not again:
+                break
+        got.append(str(m.finish_run(0)).encode())
+        got += [a.tobytes() for a in m.results(0)]
+        got.append(m.export_text("m.json", 1.0, "now").encode())
+        out[threads] = got
+        m.close()
+    assert out["1"] == out["7"]
+
+
 def test_export_formats(built_library, tmp_path):
     # steady state: header + one line of six numbers per sensor (outputManager.cpp:72-78, plotting_tools.py:80-92)
     m = T.load_model(T.case_model("linear_demo"), num_phonons=1000)

@@ -7,6 +7,7 @@ out=gpurun_out/evidence
 mkdir -p $out
 B="python bench.py --no-cpu-baseline --no-models --no-kinked"
 python -c "import bench; print(bench.csrc_sha16())" > $out/${tag}_csrc_sha16.txt
+python -c "import bench; print(bench.device_sha16())" > $out/${tag}_device_sha16.txt
 # launch list of a short bench run: which kernels run, and their share of the GPU time
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     $B --steps 2 --warmup 1 > $out/launches_bench.log 2>&1

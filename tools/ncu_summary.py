@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""profiles/<tag>_ncu_summary.json (what bench.py reads for its roofline block - only while `csrc_sha16` matches the tree that
+"""profiles/<tag>_ncu_summary.json (what bench.py reads for its roofline block - only while `device_sha16` matches the tree that
 runs), the raw-page CSVs of the --set full captures and the SASS opcode histogram of the dominant kernel, from what
 tools/gpu_evidence.sh left in gpurun_out/evidence.  usage: python tools/ncu_summary.py [tag]   (here, no GPU)"""
 import collections
@@ -131,6 +131,7 @@ def job_counters():
 
 def main():
     sha = open(os.path.join(EV, f"{tag}_csrc_sha16.txt")).read().strip()
+    dev_sha = open(os.path.join(EV, f"{tag}_device_sha16.txt")).read().strip()
     captures = []
     for name, (_, what) in CAPTURES.items():
         d = raw_page(name)
@@ -143,8 +144,9 @@ def main():
                 x = number(v)
                 c[key] = x * SCALE.get(unit, 1.0) if (x is not None and key.startswith("dram_bytes")) else x
         captures.append(c)
-    out = {"tag": tag, "csrc_sha16": sha, "phonons_per_gpu": 100_000_000,
-           "note": "bench.py uses bench_job only while csrc_sha16 equals the hash of psim_b200/csrc of the tree that is running",
+    out = {"tag": tag, "csrc_sha16": sha, "device_sha16": dev_sha, "phonons_per_gpu": 100_000_000,
+           "note": "bench.py uses bench_job only while device_sha16 equals the hash of the device sources (bench.py: DEVICE_SOURCES) of the "
+                   "tree that is running and the running job has bench_job's launches and segments per drift-step",
            "bench_job": job_counters(), "captures": captures}
     with open(os.path.join(PROFILES, f"{tag}_ncu_summary.json"), "w") as f:
         json.dump(out, f, indent=1)
