@@ -479,6 +479,15 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         return PSIM_E_NO_DEVICE;
     }
     psim_gpu* h = new psim_gpu();
+    // PSIM_TIMING: which part of a create took more than 2 ms (a call into the driver stalls for 15 - 80 ms every so often)
+    auto lap_t = std::chrono::steady_clock::now();
+    const bool timing = std::getenv("PSIM_TIMING") != nullptr;
+    auto lap = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(now - lap_t).count();
+        if (timing && ms > 2.) { std::fprintf(stderr, "psim timing [ms]: create: %s took %.1f\n", what, ms); }
+        lap_t = now;
+    };
     auto bail = [&](int rc) {
         g_create_error = h->err;
         psim_gpu_destroy(h);
@@ -496,12 +505,11 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         h->err = "cudaSetDevice failed";
         return bail(PSIM_E_NO_DEVICE);
     }
-    cudaDeviceProp prop{};
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
-        h->err = "cudaGetDeviceProperties failed";
+    if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        h->err = "cudaDeviceGetAttribute failed";
         return bail(PSIM_E_NO_DEVICE);
     }
-    h->sm_count = prop.multiProcessorCount;
+    lap("device query");
     try {  // nothing throws across the ABI: a description whose sizes exhaust the host's memory is an invalid description
         if (int rc = psim::flatten_model(*desc, h->img, h->err)) { return bail(rc); }
         if (int rc = psim::flatten_model(*desc, h->img_tri, h->err, 0)) { return bail(rc); }
@@ -513,6 +521,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         h->err = std::string("model description rejected: ") + e.what();
         return bail(PSIM_E_INVALID);
     }
+    lap("device images (host)");
     {
         float vmax = h->img.scalars.phasor ? 1000.f : 0.f;
         for (float v : h->img.velocities) { vmax = std::max(vmax, std::fabs(v)); }
@@ -541,6 +550,7 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         h->P = h->img.scalars;
         if (int rc = upload_geometry(h, h->img)) { return rc; }
         if (int rc = upload_lattice(h)) { return rc; }
+        lap("uploads");
         h->P.classes = static_cast<const DevSensor*>(h->d_classes);
         h->P.step_sensors = static_cast<const DevSensor*>(h->d_step_sensors);
         h->P.sensors = static_cast<const DevSensor*>(h->d_sensors);
@@ -555,9 +565,12 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(devmem::alloc(&h->carry_f, std::max<size_t>(h->P.n_sensors, 1) * 2 * sizeof(long long)));
         PSIM_CUDA(devmem::alloc(&h->d_stats, kStatWords * sizeof(unsigned long long)));
         PSIM_CUDA(devmem::alloc(&h->d_hist, static_cast<size_t>(h->P.n_cells) * sizeof(unsigned long long)));
+        lap("tally / counter buffers");
         PSIM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        lap("cudaStreamCreate");
         PSIM_CUDA(cudaEventCreate(&h->ev_begin));
         PSIM_CUDA(cudaEventCreate(&h->ev_end));
+        lap("cudaEventCreate");
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_slots<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots, TALLY_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
@@ -568,7 +581,10 @@ int psim_gpu_create(const psim_model_desc* desc, int device, psim_gpu** out) {
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlots, TALLY_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
         PSIM_CUDA(cudaFuncSetAttribute(drift_kernel_queues<kQueueSlotsSmall, TALLY_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPerBlock)));
-        return zero_run_state(h);
+        lap("cudaFuncSetAttribute");
+        const int rc = zero_run_state(h);
+        lap("zeroing the run state");
+        return rc;
     };
     if (int rc = setup()) { return bail(rc); }
     *out = h;
