@@ -129,6 +129,14 @@ uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
+// threads for a piece of host work that divides evenly: as many as there are units of work (a unit is what is not worth a
+// thread of its own), at most 16 and at most PSIM_HOST_THREADS
+size_t host_threads(size_t units) {
+    size_t threads = std::min<size_t>({ std::max(1u, std::thread::hardware_concurrency()), 16, units });
+    if (const char* cap = std::getenv("PSIM_HOST_THREADS")) { threads = std::min<size_t>(threads, std::strtoul(cap, nullptr, 10)); }
+    return threads;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- Material
@@ -617,8 +625,7 @@ void Model::set_tallies(const int32_t* energy, const double* flux) {
 
 template <class F> void Model::for_each_sensor(F&& f) {
     const size_t S = sensors.size();
-    size_t threads = std::min<size_t>({ std::max(1u, std::thread::hardware_concurrency()), 16, S * recorded_steps / 65536 });
-    if (const char* cap = std::getenv("PSIM_HOST_THREADS")) { threads = std::min<size_t>(threads, std::strtoul(cap, nullptr, 10)); }
+    size_t threads = host_threads(S * recorded_steps / 65536);
     if (t_eq == 0.) { threads = 1; }  // Material::table() builds its tables on first use
     if (threads <= 1) {
         for (size_t si = 0; si < S; ++si) { f(si); }
@@ -864,31 +871,64 @@ std::string Model::export_text(const std::string& model_filename, double seconds
     if (ms.empty()) { return out.str(); }
     const size_t steps = ms.back().final_temps.size();
     const size_t I = step_interval;
-    std::string text = out.str();
-    text.reserve(text.size() + (steps / I + 1) * (ms.size() * 40 + 24));
-    auto put = [&text](double v, char sep) {
-        char buf[40];
-        const auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 6);
-        text.append(buf, r.ptr);
-        text.push_back(sep);
-    };
-    for (size_t step = 0; step + I <= steps; step += I) {
-        text += std::to_string(step + I / 2);
-        text.push_back('\n');
-        text += std::to_string(ms.size());
-        text.push_back('\n');
-        for (const auto& m : ms) {
+    const size_t S = ms.size();
+    const size_t blocks = (I == 0 || steps < I) ? 0 : steps / I;  // groups of I steps: [0, I), [I, 2I), ...
+    // The means of every group, sensor by sensor (a sensor's traces are contiguous; going group by group through a thousand
+    // sensors' vectors was a cache miss per number) ...
+    std::vector<double> mean(blocks * S * 3);
+    for (size_t si = 0; si < S; ++si) {
+        const SensorResult& m = ms[si];
+        for (size_t b = 0; b < blocks; ++b) {
             double t = 0., fx = 0., fy = 0.;
-            for (size_t k = step; k < step + I; ++k) {
+            for (size_t k = b * I; k < (b + 1) * I; ++k) {
                 t += m.final_temps[k];
                 fx += m.final_fluxes[k][0];
                 fy += m.final_fluxes[k][1];
             }
-            put(t / static_cast<double>(I), ' ');
-            put(fx / static_cast<double>(I), ' ');
-            put(fy / static_cast<double>(I), '\n');
+            double* o = &mean[(b * S + si) * 3];
+            o[0] = t / static_cast<double>(I);
+            o[1] = fx / static_cast<double>(I);
+            o[2] = fy / static_cast<double>(I);
         }
     }
+    // ... then the text, group by group; several threads write the groups of their range, the pieces are joined in order
+    auto write_groups = [&](size_t b0, size_t b1, std::string& text) {
+        text.reserve((b1 - b0) * (S * 40 + 24));
+        char buf[40];
+        auto put = [&](double v, char sep) {
+            const auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 6);
+            text.append(buf, r.ptr);
+            text.push_back(sep);
+        };
+        for (size_t b = b0; b < b1; ++b) {
+            text += std::to_string(b * I + I / 2);
+            text.push_back('\n');
+            text += std::to_string(S);
+            text.push_back('\n');
+            for (size_t si = 0; si < S; ++si) {
+                const double* o = &mean[(b * S + si) * 3];
+                put(o[0], ' ');
+                put(o[1], ' ');
+                put(o[2], '\n');
+            }
+        }
+    };
+    const size_t threads = std::max<size_t>(1, std::min(host_threads(blocks * S * 3 / 32768), blocks));
+    std::vector<std::string> pieces(threads);
+    if (threads == 1) {
+        write_groups(0, blocks, pieces[0]);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < threads; ++t) {
+            pool.emplace_back([&, t] { write_groups(blocks * t / threads, blocks * (t + 1) / threads, pieces[t]); });
+        }
+        for (auto& t : pool) { t.join(); }
+    }
+    std::string text = out.str();
+    size_t total = text.size();
+    for (const auto& piece : pieces) { total += piece.size(); }
+    text.reserve(total);
+    for (const auto& piece : pieces) { text += piece; }
     return text;
 }
 
