@@ -428,7 +428,9 @@ int psim_model_run_devices(psim_model* pm, const int* devices, int n_devices, ui
             // several devices needs the exact fixed-point integers of each.
             const bool host_sum = G > 1 && !use_nccl;
             // They are written straight into the model's own tally storage, which lives from run to run.
-            const auto [energy_out, flux_out] = m.tally_storage();
+            const auto storage = m.tally_storage();
+            int32_t* const energy_out = storage.first;
+            double* const flux_out = storage.second;
             std::vector<std::vector<int32_t>> energy(host_sum ? G : 0, std::vector<int32_t>(host_sum ? n_tally : 0));
             std::vector<std::vector<int64_t>> fixed(host_sum ? G : 0, std::vector<int64_t>(host_sum ? 2 * n_tally : 0));
             std::vector<psim_stats> st(G);
