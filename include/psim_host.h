@@ -7,6 +7,11 @@
  * psim_model_run, which drives psim_gpu_* on one device; multi-GPU callers use psim_model_describe /
  * psim_model_sources / psim_model_set_tallies / psim_model_finish_run around their own per-rank psim_gpu handle.
  *
+ * Threads: the end of an iteration, the run epilogue and the periodic exporter go over the sensors / step groups on up to
+ * 16 threads of the host where the tallies are large (every sensor's sums still run over its steps in order: the numbers
+ * are those of one thread, bit for bit); environment PSIM_HOST_THREADS caps the number (1 = none).  PSIM_TIMING=1 prints
+ * the phase times of psim_model_run on stderr.
+ *
  * Errors: 0 or a negative PSIM_E_* code; psim_host_last_error() returns the message of the calling thread's
  * last failure.  The conditions and messages for rejected model files are the reference's.
  */
