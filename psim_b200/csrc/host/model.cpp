@@ -11,6 +11,7 @@
 #include <numeric>
 #include <sstream>
 #include <stdexcept>
+#include <system_error>
 #include <thread>
 #include <unordered_map>
 
@@ -135,6 +136,28 @@ size_t host_threads(size_t units) {
     size_t threads = std::min<size_t>({ std::max(1u, std::thread::hardware_concurrency()), 16, units });
     if (const char* cap = std::getenv("PSIM_HOST_THREADS")) { threads = std::min<size_t>(threads, std::strtoul(cap, nullptr, 10)); }
     return threads;
+}
+
+// part(t) for t = 0 ... parts - 1, each on a thread of its own (the calling thread takes the last part, and every part a
+// thread could not be started for); the first exception of any part is rethrown once all of them have ended
+template <class F> void run_parts(size_t parts, F&& part) {
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> errors(parts);
+    auto guarded = [&](size_t t) {
+        try {
+            part(t);
+        } catch (...) { errors[t] = std::current_exception(); }
+    };
+    size_t started = 0;
+    try {
+        pool.reserve(parts);
+        for (; started + 1 < parts; ++started) { pool.emplace_back(guarded, started); }
+    } catch (const std::system_error&) {}  // no more threads: the rest runs here
+    for (size_t t = started; t < parts; ++t) { guarded(t); }
+    for (auto& t : pool) { t.join(); }
+    for (const auto& e : errors) {
+        if (e) { std::rethrow_exception(e); }
+    }
 }
 
 }  // namespace
@@ -631,19 +654,9 @@ template <class F> void Model::for_each_sensor(F&& f) {
         for (size_t si = 0; si < S; ++si) { f(si); }
         return;
     }
-    std::vector<std::thread> pool;
-    std::vector<std::exception_ptr> errors(threads);
-    for (size_t t = 0; t < threads; ++t) {
-        pool.emplace_back([&, t] {
-            try {
-                for (size_t si = S * t / threads; si < S * (t + 1) / threads; ++si) { f(si); }
-            } catch (...) { errors[t] = std::current_exception(); }
-        });
-    }
-    for (auto& t : pool) { t.join(); }
-    for (const auto& e : errors) {
-        if (e) { std::rethrow_exception(e); }
-    }
+    run_parts(threads, [&](size_t t) {
+        for (size_t si = S * t / threads; si < S * (t + 1) / threads; ++si) { f(si); }
+    });
 }
 
 std::vector<double> Model::find_temperature(size_t si, size_t start) {
@@ -915,15 +928,7 @@ std::string Model::export_text(const std::string& model_filename, double seconds
     };
     const size_t threads = std::max<size_t>(1, std::min(host_threads(blocks * S * 3 / 32768), blocks));
     std::vector<std::string> pieces(threads);
-    if (threads == 1) {
-        write_groups(0, blocks, pieces[0]);
-    } else {
-        std::vector<std::thread> pool;
-        for (size_t t = 0; t < threads; ++t) {
-            pool.emplace_back([&, t] { write_groups(blocks * t / threads, blocks * (t + 1) / threads, pieces[t]); });
-        }
-        for (auto& t : pool) { t.join(); }
-    }
+    run_parts(threads, [&](size_t t) { write_groups(blocks * t / threads, blocks * (t + 1) / threads, pieces[t]); });
     std::string text = out.str();
     size_t total = text.size();
     for (const auto& piece : pieces) { total += piece.size(); }
